@@ -1,0 +1,198 @@
+"""ctypes bindings for the CPU oracle (oracle/liboracle.so).  TEST INFRASTRUCTURE ONLY.
+
+The oracle is the checker: tests, __graft_entry__.smoke() and bench.py's CPU legs may load it,
+the product (cube_slam_wu_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
+_LIB = None
+
+
+class Params(C.Structure):
+    _fields_ = [("consider_config_1", C.c_int), ("consider_config_2", C.c_int),
+                ("whether_sample_cam_roll_pitch", C.c_int), ("whether_sample_bbox_height", C.c_int),
+                ("max_cuboid_num", C.c_int), ("leak_cam_state", C.c_int),
+                ("nominal_skew_ratio", C.c_double), ("max_cut_skew", C.c_double)]
+
+
+class Task(C.Structure):
+    _fields_ = [("box_id", C.c_int), ("hs_id", C.c_int), ("down_expand", C.c_int), ("left", C.c_int), ("top", C.c_int),
+                ("width", C.c_int), ("height", C.c_int), ("n_top", C.c_int), ("map_offset", C.c_longlong)]
+
+
+class Cuboid(C.Structure):
+    _fields_ = [("pos", C.c_double * 3), ("scale", C.c_double * 3), ("rotY", C.c_double), ("box_config_type", C.c_double * 2),
+                ("box_corners_3d_world", C.c_double * 24), ("rect_detect_2d", C.c_double * 4),
+                ("edge_distance_error", C.c_double), ("edge_angle_error", C.c_double), ("normalized_error", C.c_double),
+                ("skew_ratio", C.c_double), ("down_expand_height", C.c_double), ("camera_roll_delta", C.c_double),
+                ("camera_pitch_delta", C.c_double), ("box_corners_2d", C.c_int * 16), ("task_id", C.c_int), ("raw_cube_ind", C.c_int)]
+
+
+class BAEdges(C.Structure):
+    _fields_ = [("n_ec", C.c_int), ("ec_cam", C.c_void_p), ("ec_cube", C.c_void_p), ("ec_meas10", C.c_void_p), ("ec_info81", C.c_void_p),
+                ("n_ep", C.c_int), ("ep_cam", C.c_void_p), ("ep_cube", C.c_void_p), ("ep_meas4", C.c_void_p), ("ep_info16", C.c_void_p), ("ep_K9", C.c_void_p),
+                ("n_eo", C.c_int), ("eo_i", C.c_void_p), ("eo_j", C.c_void_p), ("eo_meas7", C.c_void_p), ("eo_info36", C.c_void_p)]
+
+
+class BAOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("ec_err", "ec_Ji", "ec_Jj", "ep_err", "ep_Ji", "ep_Jj", "eo_err", "eo_Ji", "eo_Jj",
+                                          "H_cam", "b_cam", "H_cube", "b_cube", "ec_Hij", "ep_Hij", "eo_Hij")]
+
+
+def build(force=False):
+    so = os.path.join(ORACLE_DIR, "liboracle.so")
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle_proposal.cpp", "oracle_ba.cpp", "oracle_math.h", "Makefile")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.orc_detect_frame.restype = C.c_void_p
+        L.orc_num_scored.restype = C.c_longlong
+        L.orc_num_enum.restype = C.c_longlong
+        L.orc_detect_batch.restype = C.c_longlong
+        L.orc_ba_linearize.restype = C.c_double
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def default_params(**kw):
+    p = Params(1, 1, 1, 0, 1, 1, 1.0, 3.0)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def plan(boxes, img_w, img_h, sample_height=False):
+    boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 5)
+    cap = 3 * len(boxes) + 1
+    tasks = (Task * cap)()
+    n = lib().orc_plan(_p(boxes), len(boxes), img_w, img_h, int(sample_height), tasks, cap)
+    assert n >= 0
+    return [tasks[i] for i in range(n)]
+
+
+class FrameResult:
+    """Python view of one oracle detect_cuboid() run."""
+
+    def __init__(self, h):
+        L = lib()
+        self.n_scored = L.orc_num_scored(h)
+        self.n_enum = L.orc_num_enum(h)
+        self.tasks = []
+        for t in range(L.orc_num_tasks(h)):
+            tk = Task(); nv = C.c_int(); ne = C.c_int(); nm = C.c_int(); nk = C.c_int()
+            L.orc_task_info(h, t, C.byref(tk), C.byref(nv), C.byref(ne), C.byref(nm), C.byref(nk))
+            d = dict(task=tk, n_valid=nv.value, n_enum=ne.value,
+                     rows=np.zeros((nv.value, 9)), corners=np.zeros((nv.value, 16)), hyp_id=np.zeros(nv.value, np.int32),
+                     merged=np.zeros((nm.value, 4)), keep=np.zeros(nk.value, np.int32), norm_score=np.zeros(nk.value))
+            L.orc_task_data(h, t, _p(d["rows"]), _p(d["corners"]), _p(d["hyp_id"]), _p(d["merged"]), _p(d["keep"]), _p(d["norm_score"]))
+            self.tasks.append(d)
+        self.boxes = []
+
+
+def detect_frame(K, T, img_w, img_h, boxes, lines, dist_maps, params=None, n_boxes=None):
+    L = lib()
+    params = params or default_params()
+    K = np.ascontiguousarray(K, np.float64); T = np.ascontiguousarray(T, np.float64)
+    boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 5)
+    lines = np.ascontiguousarray(lines, np.float64).reshape(-1, 4)
+    dist_maps = np.ascontiguousarray(dist_maps, np.float32)
+    h = C.c_void_p(L.orc_detect_frame(_p(K), _p(T), img_w, img_h, _p(boxes), len(boxes), _p(lines), len(lines), _p(dist_maps), C.byref(params)))
+    try:
+        R = FrameResult(h)
+        for b in range(len(boxes)):
+            nr = C.c_int(); ns = C.c_int()
+            L.orc_box_info(h, b, C.byref(nr), C.byref(ns))
+            raw = (Cuboid * max(nr.value, 1))()
+            comb = np.zeros(nr.value); srt = np.zeros(ns.value, np.int32)
+            L.orc_box_data(h, b, raw, _p(comb), _p(srt))
+            R.boxes.append(dict(raw=[raw[i] for i in range(nr.value)], combined=comb, sorted=srt))
+        return R
+    finally:
+        L.orc_free(h)
+
+
+def ba_edges(ec=None, ep=None, eo=None):
+    """ec=(cam,cube,meas10,info81), ep=(cam,cube,meas4,info16,K9), eo=(i,j,meas7,info36); arrays kept alive on the struct."""
+    E = BAEdges()
+    keep = []
+
+    def arr(a, dt):
+        a = np.ascontiguousarray(a, dt); keep.append(a); return a.ctypes.data_as(C.c_void_p)
+    if ec is not None:
+        E.n_ec = len(ec[0]); E.ec_cam = arr(ec[0], np.int32); E.ec_cube = arr(ec[1], np.int32); E.ec_meas10 = arr(ec[2], np.float64); E.ec_info81 = arr(ec[3], np.float64)
+    if ep is not None:
+        E.n_ep = len(ep[0]); E.ep_cam = arr(ep[0], np.int32); E.ep_cube = arr(ep[1], np.int32); E.ep_meas4 = arr(ep[2], np.float64); E.ep_info16 = arr(ep[3], np.float64); E.ep_K9 = arr(ep[4], np.float64)
+    if eo is not None:
+        E.n_eo = len(eo[0]); E.eo_i = arr(eo[0], np.int32); E.eo_j = arr(eo[1], np.int32); E.eo_meas7 = arr(eo[2], np.float64); E.eo_info36 = arr(eo[3], np.float64)
+    E._keep = keep
+    return E
+
+
+def ba_linearize(cams7, cam_fixed, cubes10, cube_fixed, E, n_threads=1):
+    cams7 = np.ascontiguousarray(cams7, np.float64).reshape(-1, 7); cubes10 = np.ascontiguousarray(cubes10, np.float64).reshape(-1, 10)
+    cam_fixed = np.ascontiguousarray(cam_fixed, np.int32); cube_fixed = np.ascontiguousarray(cube_fixed, np.int32)
+    nc, nq = len(cams7), len(cubes10)
+    out = dict(ec_err=np.zeros((E.n_ec, 9)), ec_Ji=np.zeros((E.n_ec, 54)), ec_Jj=np.zeros((E.n_ec, 81)),
+               ep_err=np.zeros((E.n_ep, 4)), ep_Ji=np.zeros((E.n_ep, 24)), ep_Jj=np.zeros((E.n_ep, 36)),
+               eo_err=np.zeros((E.n_eo, 6)), eo_Ji=np.zeros((E.n_eo, 36)), eo_Jj=np.zeros((E.n_eo, 36)),
+               H_cam=np.zeros((nc, 36)), b_cam=np.zeros((nc, 6)), H_cube=np.zeros((nq, 81)), b_cube=np.zeros((nq, 9)),
+               ec_Hij=np.zeros((E.n_ec, 54)), ep_Hij=np.zeros((E.n_ep, 54)), eo_Hij=np.zeros((E.n_eo, 36)))
+    O = BAOut(*[_p(out[n]) for n, _ in BAOut._fields_])
+    out["chi2"] = lib().orc_ba_linearize(nc, _p(cams7), _p(cam_fixed), nq, _p(cubes10), _p(cube_fixed), C.byref(E), C.byref(O), n_threads)
+    return out
+
+
+def ba_optimize(cams7, cam_fixed, cubes10, cube_fixed, E, iterations):
+    cams7 = np.array(cams7, np.float64).reshape(-1, 7).copy(); cubes10 = np.array(cubes10, np.float64).reshape(-1, 10).copy()
+    cam_fixed = np.ascontiguousarray(cam_fixed, np.int32); cube_fixed = np.ascontiguousarray(cube_fixed, np.int32)
+    chi = C.c_double()
+    it = lib().orc_ba_optimize(len(cams7), _p(cams7), _p(cam_fixed), len(cubes10), _p(cubes10), _p(cube_fixed), C.byref(E), iterations, C.byref(chi))
+    return cams7, cubes10, it, chi.value
+
+
+def _v(n):
+    return np.zeros(n, np.float64)
+
+
+def cuboid_from_minimal(v9):
+    o = _v(10); lib().orc_cuboid_from_minimal(_p(np.ascontiguousarray(v9, np.float64)), _p(o)); return o
+
+
+def cuboid_transform_to(c10, Twc7):
+    o = _v(10); lib().orc_cuboid_transform_to(_p(np.ascontiguousarray(c10, np.float64)), _p(np.ascontiguousarray(Twc7, np.float64)), _p(o)); return o
+
+
+def cuboid_transform_from(c10, Twc7):
+    o = _v(10); lib().orc_cuboid_transform_from(_p(np.ascontiguousarray(c10, np.float64)), _p(np.ascontiguousarray(Twc7, np.float64)), _p(o)); return o
+
+
+def se3_inverse(a7):
+    o = _v(7); lib().orc_se3_inverse(_p(np.ascontiguousarray(a7, np.float64)), _p(o)); return o
+
+
+def se3_mul(a7, b7):
+    o = _v(7); lib().orc_se3_mul(_p(np.ascontiguousarray(a7, np.float64)), _p(np.ascontiguousarray(b7, np.float64)), _p(o)); return o
+
+
+def se3_log(a7):
+    o = _v(6); lib().orc_se3_log(_p(np.ascontiguousarray(a7, np.float64)), _p(o)); return o
+
+
+def se3_exp(u6):
+    o = _v(7); lib().orc_se3_exp(_p(np.ascontiguousarray(u6, np.float64)), _p(o)); return o
