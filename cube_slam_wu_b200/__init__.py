@@ -1,0 +1,248 @@
+"""cube_slam_wu_b200 -- B200-native CubeSLAM hot path (cuboid proposal scoring + cuboid-BA linearisation).
+
+The product is the C-ABI shared library `libcubeslam_b200.so` (include/cubeslam_b200.h); this package is the thin
+ctypes binding used by the tests and the benchmark.  There is no CPU fallback: if the CUDA library is missing or no
+GPU is usable, the calls fail loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libcubeslam_b200.so")
+_LIB = None
+
+CSB_OK, CSB_ERR_INVALID, CSB_ERR_CUDA, CSB_ERR_CAPACITY, CSB_ERR_STATE = 0, -1, -2, -3, -4
+
+
+class CsbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("cubeslam_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class DetectParams(C.Structure):
+    _fields_ = [("consider_config_1", C.c_int32), ("consider_config_2", C.c_int32), ("whether_sample_cam_roll_pitch", C.c_int32),
+                ("whether_sample_bbox_height", C.c_int32), ("max_cuboid_num", C.c_int32), ("reserved", C.c_int32),
+                ("nominal_skew_ratio", C.c_double), ("max_cut_skew", C.c_double)]
+
+    @staticmethod
+    def default(**kw):
+        p = DetectParams(1, 1, 1, 0, 1, 0, 1.0, 3.0)  # detect_3d_cuboid.h:109-116
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+
+class Frame(C.Structure):
+    _fields_ = [("Kalib", C.c_double * 9), ("transToWolrd", C.c_double * 16), ("img_width", C.c_int32), ("img_height", C.c_int32),
+                ("box_begin", C.c_int32), ("box_end", C.c_int32), ("line_begin", C.c_int32), ("line_end", C.c_int32)]
+
+
+class Task(C.Structure):
+    _fields_ = [("frame_id", C.c_int32), ("box_id", C.c_int32), ("hs_id", C.c_int32), ("down_expand", C.c_int32),
+                ("roi_left", C.c_int32), ("roi_top", C.c_int32), ("roi_width", C.c_int32), ("roi_height", C.c_int32),
+                ("n_top", C.c_int32), ("n_enum", C.c_int32), ("map_offset", C.c_int64)]
+
+
+class Cuboid(C.Structure):
+    _fields_ = [("pos", C.c_double * 3), ("scale", C.c_double * 3), ("rotY", C.c_double), ("box_config_type", C.c_double * 2),
+                ("box_corners_3d_world", C.c_double * 24), ("rect_detect_2d", C.c_double * 4),
+                ("edge_distance_error", C.c_double), ("edge_angle_error", C.c_double), ("normalized_error", C.c_double), ("skew_ratio", C.c_double),
+                ("down_expand_height", C.c_double), ("camera_roll_delta", C.c_double), ("camera_pitch_delta", C.c_double),
+                ("box_corners_2d", C.c_int32 * 16), ("task_id", C.c_int32), ("raw_cube_ind", C.c_int32), ("rank_index", C.c_int32), ("reserved", C.c_int32)]
+
+
+class DetectStats(C.Structure):
+    _fields_ = [("n_enumerated", C.c_int64), ("n_scored", C.c_int64), ("n_kept", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("n_kernel_launches", C.c_int32), ("n_tasks_smem_map", C.c_int32),
+                ("gpu_ms_prep", C.c_float), ("gpu_ms_score", C.c_float), ("gpu_ms_select", C.c_float), ("gpu_ms_rank", C.c_float)]
+
+
+class BAGraph(C.Structure):
+    _fields_ = [("n_cam", C.c_int32), ("n_cube", C.c_int32), ("cam_fixed", C.c_void_p), ("cube_fixed", C.c_void_p),
+                ("n_ec", C.c_int32), ("ec_cam", C.c_void_p), ("ec_cube", C.c_void_p), ("ec_meas", C.c_void_p), ("ec_info", C.c_void_p),
+                ("n_ep", C.c_int32), ("ep_cam", C.c_void_p), ("ep_cube", C.c_void_p), ("ep_meas", C.c_void_p), ("ep_info", C.c_void_p), ("ep_K", C.c_void_p),
+                ("n_eo", C.c_int32), ("eo_cam_i", C.c_void_p), ("eo_cam_j", C.c_void_p), ("eo_meas", C.c_void_p), ("eo_info", C.c_void_p)]
+
+
+BA_OUT_FIELDS = ("ec_err", "ec_Ji", "ec_Jj", "ep_err", "ep_Ji", "ep_Jj", "eo_err", "eo_Ji", "eo_Jj", "H_cam", "b_cam", "H_cube", "b_cube",
+                 "ec_Hij", "ep_Hij", "eo_Hij", "chi2")
+
+
+class BAOutput(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in BA_OUT_FIELDS]
+
+
+def lib():
+    """Load the CUDA library; raises if it has not been built (there is no fallback path)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise CsbError(CSB_ERR_STATE, "libcubeslam_b200.so is not built: run `python -m cube_slam_wu_b200.build` (or __graft_entry__.build())")
+        L = C.CDLL(LIB_PATH)
+        L.csb_last_error.restype = C.c_char_p
+        L.csb_version.restype = C.c_char_p
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def make_frames(Ks, Ts, img_w, img_h, box_ranges, line_ranges):
+    n = len(Ks)
+    fr = (Frame * n)()
+    for i in range(n):
+        fr[i].Kalib[:] = np.asarray(Ks[i], np.float64).ravel().tolist()
+        fr[i].transToWolrd[:] = np.asarray(Ts[i], np.float64).ravel().tolist()
+        fr[i].img_width, fr[i].img_height = int(img_w), int(img_h)
+        fr[i].box_begin, fr[i].box_end = int(box_ranges[i][0]), int(box_ranges[i][1])
+        fr[i].line_begin, fr[i].line_end = int(line_ranges[i][0]), int(line_ranges[i][1])
+    return fr
+
+
+def detect_plan(frames, boxes, params):
+    """csb_detect_plan(): host-only task / ROI planning.  Returns (tasks ctypes array, n_map_floats)."""
+    L = lib()
+    boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 5)
+    nt = C.c_int(); nm = C.c_int64()
+    rc = L.csb_detect_plan(frames, len(frames), _p(boxes), len(boxes), C.byref(params), None, 0, C.byref(nt), C.byref(nm))
+    if rc != CSB_OK:
+        raise CsbError(rc, "csb_detect_plan failed")
+    tasks = (Task * max(nt.value, 1))()
+    rc = L.csb_detect_plan(frames, len(frames), _p(boxes), len(boxes), C.byref(params), tasks, nt.value, C.byref(nt), C.byref(nm))
+    if rc != CSB_OK:
+        raise CsbError(rc, "csb_detect_plan failed")
+    return tasks, nt.value, nm.value
+
+
+class Context:
+    """csb_context wrapper (one CUDA device + stream)."""
+
+    def __init__(self, device=0, stream=None):
+        self._h = C.c_void_p()
+        rc = lib().csb_create(C.byref(self._h), int(device))
+        if rc != CSB_OK:
+            raise CsbError(rc, "csb_create failed: no usable CUDA device %d (this library has no CPU fallback)" % device)
+        if stream is not None:
+            self._chk(lib().csb_set_stream(self._h, C.c_void_p(int(stream))))
+
+    def close(self):
+        if self._h:
+            lib().csb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != CSB_OK:
+            raise CsbError(rc, (lib().csb_last_error(self._h) or b"").decode())
+
+    def synchronize(self):
+        self._chk(lib().csb_synchronize(self._h))
+
+    # ---- proposal half -------------------------------------------------------------------------
+    def _args(self, frames, boxes, lines, tasks, n_tasks, dist_maps, n_map_floats, params):
+        nb = boxes.shape[0] if hasattr(boxes, "shape") else self._nb
+        nl = lines.shape[0] if hasattr(lines, "shape") else self._nl
+        return (self._h, frames, len(frames), _p(boxes), nb, _p(lines), nl, tasks, n_tasks, _p(dist_maps), C.c_int64(n_map_floats), C.byref(params))
+
+    def detect_batch(self, frames, boxes, lines, tasks, n_tasks, dist_maps, n_map_floats, params, want_stats=True):
+        """csb_detect_batch(): host buffers in, host cuboids out (copies inside).  boxes (n,5) f64, lines (m,4) f64, dist_maps f32."""
+        nb = boxes.shape[0]
+        kmax = params.max_cuboid_num
+        cub = (Cuboid * max(nb * kmax, 1))()
+        ncub = np.zeros(max(nb, 1), np.int32)
+        st = DetectStats()
+        self._chk(lib().csb_detect_batch(*self._args(frames, boxes, lines, tasks, n_tasks, dist_maps, n_map_floats, params), cub, _p(ncub),
+                                         C.byref(st) if want_stats else None))
+        return cub, ncub[:nb], st
+
+    def detect_upload(self, frames, boxes, lines, tasks, n_tasks, dist_maps, n_map_floats, params):
+        self._nb, self._kmax = boxes.shape[0], params.max_cuboid_num
+        self._chk(lib().csb_detect_upload(*self._args(frames, boxes, lines, tasks, n_tasks, dist_maps, n_map_floats, params)))
+
+    def detect_run(self, timed=False):
+        self._chk(lib().csb_detect_run(self._h, int(timed)))
+
+    def detect_download(self):
+        cub = (Cuboid * max(self._nb * self._kmax, 1))()
+        ncub = np.zeros(max(self._nb, 1), np.int32)
+        st = DetectStats()
+        self._chk(lib().csb_detect_download(self._h, cub, _p(ncub), C.byref(st)))
+        return cub, ncub[:self._nb], st
+
+    def debug_task(self, task_id, capacity):
+        nv = C.c_int32(); nm = C.c_int32(); nk = C.c_int32()
+        self._chk(lib().csb_detect_debug_task(self._h, task_id, C.byref(nv), C.byref(nm), C.byref(nk), None, None, None, None, None, None, None, 0))
+        cap = max(nv.value, nm.value, nk.value, 1)
+        out = dict(n_valid=nv.value, n_merged=nm.value, n_keep=nk.value, hyp_id=np.zeros(cap, np.int32), dist=np.zeros(cap), angle=np.zeros(cap),
+                   corners=np.zeros((cap, 16)), merged=np.zeros((cap, 4)), keep=np.zeros(cap, np.int32), norm_score=np.zeros(cap))
+        self._chk(lib().csb_detect_debug_task(self._h, task_id, C.byref(nv), C.byref(nm), C.byref(nk), _p(out["hyp_id"]), _p(out["dist"]), _p(out["angle"]),
+                                              _p(out["corners"]), _p(out["merged"]), _p(out["keep"]), _p(out["norm_score"]), cap))
+        for k in ("hyp_id", "dist", "angle", "corners"):
+            out[k] = out[k][:nv.value]
+        out["merged"] = out["merged"][:nm.value]
+        out["keep"] = out["keep"][:nk.value]
+        out["norm_score"] = out["norm_score"][:nk.value]
+        return out
+
+    # ---- BA half -------------------------------------------------------------------------------
+    def ba_set_graph(self, cam_fixed, cube_fixed, ec=None, ep=None, eo=None):
+        """ec=(cam,cube,meas10,info81)  ep=(cam,cube,meas4,info16,K9)  eo=(i,j,meas7,info36)"""
+        keep = []
+
+        def arr(a, dt):
+            a = np.ascontiguousarray(a, dt); keep.append(a); return a.ctypes.data_as(C.c_void_p)
+        g = BAGraph()
+        g.n_cam, g.n_cube = len(cam_fixed), len(cube_fixed)
+        g.cam_fixed, g.cube_fixed = arr(cam_fixed, np.int32), arr(cube_fixed, np.int32)
+        if ec is not None and len(ec[0]):
+            g.n_ec = len(ec[0]); g.ec_cam = arr(ec[0], np.int32); g.ec_cube = arr(ec[1], np.int32); g.ec_meas = arr(ec[2], np.float64); g.ec_info = arr(ec[3], np.float64)
+        if ep is not None and len(ep[0]):
+            g.n_ep = len(ep[0]); g.ep_cam = arr(ep[0], np.int32); g.ep_cube = arr(ep[1], np.int32); g.ep_meas = arr(ep[2], np.float64); g.ep_info = arr(ep[3], np.float64); g.ep_K = arr(ep[4], np.float64)
+        if eo is not None and len(eo[0]):
+            g.n_eo = len(eo[0]); g.eo_cam_i = arr(eo[0], np.int32); g.eo_cam_j = arr(eo[1], np.int32); g.eo_meas = arr(eo[2], np.float64); g.eo_info = arr(eo[3], np.float64)
+        self._chk(lib().csb_ba_set_graph(self._h, C.byref(g)))
+        self._ba_dims = (g.n_cam, g.n_cube, g.n_ec, g.n_ep, g.n_eo)
+
+    def _ba_out(self, jacobians):
+        nc, nq, nec, nep, neo = self._ba_dims
+        shapes = dict(ec_err=(nec, 9), ec_Ji=(nec, 54), ec_Jj=(nec, 81), ep_err=(nep, 4), ep_Ji=(nep, 24), ep_Jj=(nep, 36), eo_err=(neo, 6), eo_Ji=(neo, 36),
+                      eo_Jj=(neo, 36), H_cam=(nc, 36), b_cam=(nc, 6), H_cube=(nq, 81), b_cube=(nq, 9), ec_Hij=(nec, 54), ep_Hij=(nep, 54), eo_Hij=(neo, 36), chi2=(1,))
+        out = {k: np.zeros(v) for k, v in shapes.items()}
+        O = BAOutput()
+        for k in BA_OUT_FIELDS:
+            if not jacobians and k.endswith(("_Ji", "_Jj")):
+                continue
+            setattr(O, k, _p(out[k]))
+        return out, O
+
+    def ba_linearize(self, cams7, cubes10, jacobians=True):
+        cams7 = np.ascontiguousarray(cams7, np.float64); cubes10 = np.ascontiguousarray(cubes10, np.float64)
+        out, O = self._ba_out(jacobians)
+        self._chk(lib().csb_ba_linearize(self._h, _p(cams7), _p(cubes10), C.byref(O)))
+        return out
+
+    def ba_upload_estimates(self, cams7, cubes10):
+        cams7 = np.ascontiguousarray(cams7, np.float64); cubes10 = np.ascontiguousarray(cubes10, np.float64)
+        self._chk(lib().csb_ba_upload_estimates(self._h, _p(cams7), _p(cubes10)))
+
+    def ba_run(self):
+        self._chk(lib().csb_ba_run(self._h))
+
+    def ba_download(self, jacobians=False):
+        out, O = self._ba_out(jacobians)
+        self._chk(lib().csb_ba_download(self._h, C.byref(O)))
+        return out

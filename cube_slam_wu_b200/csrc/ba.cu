@@ -1,0 +1,482 @@
+// ba.cu -- sm_100a kernels + C ABI of the BA half: residuals, central-difference Jacobians and the block normal
+// equations of the camera-cuboid graph (what g2o's BlockSolver::buildSystem() does edge by edge).
+//
+//   k_linearize<TYPE> : half a warp per edge.  Lane c < Di+Dj evaluates the residual at +/-delta along tangent
+//                       direction c of vertex 0 / vertex 1 (the 30 evaluations of BaseBinaryEdge::linearizeOplus,
+//                       base_binary_edge.hpp:130-205, delta = 1e-9) and keeps Jacobian column c in registers; lane 15
+//                       evaluates the unperturbed residual.  The 186-double quadratic form of the edge
+//                       (constructQuadraticForm, base_binary_edge.hpp:54-120) is formed with warp shuffles and stored
+//                       as one contiguous record; the off-diagonal block A^T Omega B goes straight to its BSR slot.
+//   k_gather          : one warp per vertex sums the records of its incident edges in g2o's edge order
+//                       (deterministic: no atomics) into the diagonal blocks H_vv and b_v.
+//
+// Reference: object_slam/include/object_slam/g2o_Object.h:23-292, Thirdparty/g2o/g2o/types/se3quat.h,
+// types_six_dof_expmap.h:59-99, core/block_solver.hpp:501-560.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "ba.h"
+#include "context.h"
+#include "csb_math.cuh"
+
+namespace csb {
+
+// ---- g2o::cuboid (g2o_Object.h) ----------------------------------------------------------------
+__device__ __forceinline__ Cube cube_from_vec10(const double* v) {  // fromVector :45-48 (no normalisation)
+    Cube c;
+    c.pose.r = Quat{v[6], v[3], v[4], v[5]};
+    c.pose.t = V3{v[0], v[1], v[2]};
+    c.scale = V3{v[7], v[8], v[9]};
+    return c;
+}
+__device__ __forceinline__ Cube cube_exp_update(const Cube& c, const double* u) {  // :57-63
+    Cube r;
+    r.pose = se3_mul(c.pose, se3_exp(u));
+    r.scale = V3{c.scale.x + u[6], c.scale.y + u[7], c.scale.z + u[8]};
+    return r;
+}
+__device__ __forceinline__ void cube_log_error(const Cube& self, const Cube& newone, double* res) {  // :66-73
+    SE3 pose_diff = se3_mul(se3_inverse(newone.pose), self.pose);
+    se3_log(pose_diff, res);
+    res[6] = self.scale.x - newone.scale.x; res[7] = self.scale.y - newone.scale.y; res[8] = self.scale.z - newone.scale.z;
+}
+// min_log_error :76-101 with rotate_cuboid :104-114 (yaw -90, 0, 90, 180 deg; x/y scales swap at +-90)
+__device__ __forceinline__ void cube_min_log_error(const Cube& self, const Cube& newone, double* res) {
+    double best_n = 0;
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) {
+        double yaw_angle = (double)(i - 1) * M_PI / 2.0;
+        Cube rc;
+        SE3 rot = se3_make(Quat{cos(yaw_angle * 0.5), 0, 0, sin(yaw_angle * 0.5)}, V3{0, 0, 0});
+        rc.pose = se3_mul(newone.pose, rot);
+        rc.scale = newone.scale;
+        if ((yaw_angle == M_PI / 2.0) || (yaw_angle == -M_PI / 2.0) || (yaw_angle == 3 * M_PI / 2.0)) { double t = rc.scale.x; rc.scale.x = rc.scale.y; rc.scale.y = t; }
+        double e[9];
+        cube_log_error(self, rc, e);
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 9; k++) s += e[k] * e[k];
+        double n = sqrt(s);
+        if (i == 0 || n < best_n) {  // Eigen minCoeff: first minimum
+            best_n = n;
+#pragma unroll
+            for (int k = 0; k < 9; k++) res[k] = e[k];
+        }
+    }
+}
+// projectOntoImageBbox :156-197
+__device__ __forceinline__ void cube_project_bbox(const Cube& c, const SE3& Tcw, const double* K, double* out) {
+    const double bx[8] = {1, 1, -1, -1, 1, 1, -1, -1}, by[8] = {1, -1, -1, 1, 1, -1, -1, 1}, bz[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
+    M3 R = quat_to_rot(c.pose.r);
+    double S[12];
+    double sc[3] = {c.scale.x, c.scale.y, c.scale.z};
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) S[i * 4 + j] = R.m[i * 3 + j] * sc[j];
+    }
+    S[3] = c.pose.t.x; S[7] = c.pose.t.y; S[11] = c.pose.t.z;
+    M3 Rc = quat_to_rot(Tcw.r);
+    double Tc[12];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Tc[i * 4 + j] = Rc.m[i * 3 + j];
+    Tc[3] = Tcw.t.x; Tc[7] = Tcw.t.y; Tc[11] = Tcw.t.z;
+    double minx = 0, miny = 0, maxx = 0, maxy = 0;
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) {
+        double w3 = ((0.0 * bx[k] + 0.0 * by[k]) + 0.0 * bz[k]) + 1.0 * 1.0;
+        double cw[3];
+        for (int r = 0; r < 3; r++) cw[r] = (((S[r * 4] * bx[k] + S[r * 4 + 1] * by[k]) + S[r * 4 + 2] * bz[k]) + S[r * 4 + 3] * 1.0) / w3;
+        double p3 = ((0.0 * cw[0] + 0.0 * cw[1]) + 0.0 * cw[2]) + 1.0 * 1.0;
+        V3 pc;
+        pc.x = (((Tc[0] * cw[0] + Tc[1] * cw[1]) + Tc[2] * cw[2]) + Tc[3] * 1.0) / p3;
+        pc.y = (((Tc[4] * cw[0] + Tc[5] * cw[1]) + Tc[6] * cw[2]) + Tc[7] * 1.0) / p3;
+        pc.z = (((Tc[8] * cw[0] + Tc[9] * cw[1]) + Tc[10] * cw[2]) + Tc[11] * 1.0) / p3;
+        double ux = (K[0] * pc.x + K[1] * pc.y) + K[2] * pc.z, uy = (K[3] * pc.x + K[4] * pc.y) + K[5] * pc.z, uz = (K[6] * pc.x + K[7] * pc.y) + K[8] * pc.z;
+        double u = ux / uz, v = uy / uz;
+        if (k == 0) { minx = maxx = u; miny = maxy = v; }
+        else { if (u > maxx) maxx = u; if (u < minx) minx = u; if (v > maxy) maxy = v; if (v < miny) miny = v; }
+    }
+    out[0] = (maxx + minx) / 2; out[1] = (maxy + miny) / 2; out[2] = maxx - minx; out[3] = maxy - miny;
+}
+
+// ---- edge types ---------------------------------------------------------------------------------
+enum { EDGE_CUBOID = 0, EDGE_PROJ = 1, EDGE_ODOM = 2 };
+template <int TYPE> struct EdgeDims;
+template <> struct EdgeDims<EDGE_CUBOID> { static constexpr int D = 9, Di = 6, Dj = 9, REC = 132; };
+template <> struct EdgeDims<EDGE_PROJ> { static constexpr int D = 4, Di = 6, Dj = 9, REC = 132; };
+template <> struct EdgeDims<EDGE_ODOM> { static constexpr int D = 6, Di = 6, Dj = 6, REC = 84; };
+
+struct EdgeCtx {
+    SE3 cam;          // vertex 0 estimate (world -> camera)
+    SE3 cam2;         // odometry: vertex 1 estimate
+    Cube cube;        // vertex 1 estimate
+    Cube meas_cube;   // EdgeSE3Cuboid measurement
+    SE3 meas_se3;     // EdgeSE3Expmap measurement
+    double meas4[4];  // EdgeSE3CuboidProj measurement
+    const double* K;
+};
+
+// computeError() of the three edge classes with vertex 0 / vertex 1 replaced by (possibly perturbed) estimates
+template <int TYPE>
+__device__ __forceinline__ void edge_error(const EdgeCtx& x, const SE3& v0, const Cube& v1c, const SE3& v1s, double* e) {
+    if (TYPE == EDGE_CUBOID) {  // g2o_Object.h:250-259
+        SE3 Twc = se3_inverse(v0);
+        Cube esti;
+        esti.pose = se3_mul(Twc, x.meas_cube.pose);  // transform_from :117-122
+        esti.scale = x.meas_cube.scale;
+        cube_min_log_error(v1c, esti, e);
+    } else if (TYPE == EDGE_PROJ) {  // g2o_Object.h:279-290
+        double r[4];
+        cube_project_bbox(v1c, v0, x.K, r);
+        for (int i = 0; i < 4; i++) e[i] = r[i] - x.meas4[i];
+    } else {  // types_six_dof_expmap.h:90-99
+        SE3 err = se3_mul(se3_mul(x.meas_se3, v0), se3_inverse(v1s));
+        se3_log(err, e);
+    }
+}
+
+constexpr int LIN_THREADS = 128;  // 8 edges per CTA
+
+template <int TYPE>
+__global__ void __launch_bounds__(LIN_THREADS) k_linearize(BABuffers B, int n_edges, int64_t rec_base, int chi_base, double* Ji_out, double* Jj_out) {
+    constexpr int D = EdgeDims<TYPE>::D, Di = EdgeDims<TYPE>::Di, Dj = EdgeDims<TYPE>::Dj, REC = EdgeDims<TYPE>::REC;
+    const int tid = blockIdx.x * LIN_THREADS + threadIdx.x;
+    const int e = tid >> 4, c = tid & 15;          // edge, column / role
+    const int lane = threadIdx.x & 31, half_base = lane & 16;
+    const unsigned FULL = 0xffffffffu;
+    const bool active = e < n_edges;
+    const int ee = active ? e : 0;
+
+    // ---- load
+    EdgeCtx x;
+    int vi, vj;
+    const double* info;
+    bool i_free, j_free;
+    if (TYPE == EDGE_CUBOID) {
+        vi = B.ec_cam[ee]; vj = B.ec_cube[ee];
+        x.meas_cube = cube_from_vec10(B.ec_meas + 10 * (size_t)ee);
+        info = B.ec_info + 81 * (size_t)ee;
+    } else if (TYPE == EDGE_PROJ) {
+        vi = B.ep_cam[ee]; vj = B.ep_cube[ee];
+        for (int k = 0; k < 4; k++) x.meas4[k] = B.ep_meas[4 * (size_t)ee + k];
+        x.K = B.ep_K + 9 * (size_t)ee;
+        info = B.ep_info + 16 * (size_t)ee;
+    } else {
+        vi = B.eo_i[ee]; vj = B.eo_j[ee];
+        x.meas_se3 = se3_from_vec7(B.eo_meas + 7 * (size_t)ee);
+        info = B.eo_info + 36 * (size_t)ee;
+    }
+    x.cam = se3_from_vec7(B.cams7 + 7 * (size_t)vi);
+    i_free = !B.cam_fixed[vi];
+    if (TYPE == EDGE_ODOM) { x.cam2 = se3_from_vec7(B.cams7 + 7 * (size_t)vj); j_free = !B.cam_fixed[vj]; x.cube = Cube{}; }
+    else { x.cube = cube_from_vec10(B.cubes10 + 10 * (size_t)vj); j_free = !B.cube_fixed[vj]; x.cam2 = x.cam; }
+
+    // ---- residuals: lane 15 -> base error; lane c -> Jacobian column c by central differences
+    double J[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) J[k] = 0;
+    const double delta = 1e-9, scalar = 1.0 / (2 * delta);
+    if (active) {
+        if (c == 15) {
+            edge_error<TYPE>(x, x.cam, x.cube, x.cam2, J);  // J holds the error vector on lane 15
+        } else if (c < Di) {
+            if (i_free) {
+                double add[6] = {0, 0, 0, 0, 0, 0}, ep[D], em[D];
+                add[c] = delta;
+                edge_error<TYPE>(x, se3_mul(se3_exp(add), x.cam), x.cube, x.cam2, ep);  // VertexSE3Expmap::oplusImpl: exp(d) * T
+                add[c] = -delta;
+                edge_error<TYPE>(x, se3_mul(se3_exp(add), x.cam), x.cube, x.cam2, em);
+#pragma unroll
+                for (int k = 0; k < D; k++) J[k] = scalar * (ep[k] - em[k]);
+            }
+        } else if (c < Di + Dj) {
+            if (j_free) {
+                const int d = c - Di;
+                double ep[D], em[D];
+                if (TYPE == EDGE_ODOM) {
+                    double add[6] = {0, 0, 0, 0, 0, 0};
+                    add[d] = delta;
+                    edge_error<TYPE>(x, x.cam, x.cube, se3_mul(se3_exp(add), x.cam2), ep);
+                    add[d] = -delta;
+                    edge_error<TYPE>(x, x.cam, x.cube, se3_mul(se3_exp(add), x.cam2), em);
+                } else {
+                    double add[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                    add[d] = delta;
+                    edge_error<TYPE>(x, x.cam, cube_exp_update(x.cube, add), x.cam2, ep);  // VertexCuboid::oplusImpl
+                    add[d] = -delta;
+                    edge_error<TYPE>(x, x.cam, cube_exp_update(x.cube, add), x.cam2, em);
+                }
+#pragma unroll
+                for (int k = 0; k < D; k++) J[k] = scalar * (ep[k] - em[k]);
+            }
+        }
+    }
+
+    // ---- error, chi2, omega_r = -Omega * e (every lane of the half-warp gets e from lane 15)
+    double err[D], omega_r[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) err[k] = __shfl_sync(FULL, J[k], half_base + 15);
+#pragma unroll
+    for (int r = 0; r < D; r++) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < D; k++) s += info[r * D + k] * err[k];
+        omega_r[r] = -s;
+    }
+    if (active && c == 15) {
+        double* eo = (TYPE == EDGE_CUBOID ? B.ec_err : TYPE == EDGE_PROJ ? B.ep_err : B.eo_err) + (size_t)D * e;
+        double chi = 0;
+#pragma unroll
+        for (int k = 0; k < D; k++) { eo[k] = err[k]; chi += err[k] * (-omega_r[k]); }
+        B.edge_chi2[chi_base + e] = chi;
+    }
+    const bool is_col = c < Di + Dj;
+    if (active && is_col) {
+        if (c < Di && Ji_out) for (int k = 0; k < D; k++) Ji_out[(size_t)e * D * Di + c * D + k] = J[k];
+        if (c >= Di && Jj_out) for (int k = 0; k < D; k++) Jj_out[(size_t)e * D * Dj + (c - Di) * D + k] = J[k];
+    }
+
+    // ---- quadratic form.  Lane i owns row i of [A B]^T Omega [A B]:  JtO_i[k] = sum_m J_i[m] * Omega[m][k]
+    double JtO[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        double s = 0;
+#pragma unroll
+        for (int m = 0; m < D; m++) s += J[m] * info[m * D + k];
+        JtO[k] = s;
+    }
+    double brow = 0;
+#pragma unroll
+    for (int k = 0; k < D; k++) brow += J[k] * omega_r[k];
+    double* rec = B.contrib + rec_base + (size_t)REC * ee;
+    double* Hij = (TYPE == EDGE_CUBOID ? B.ec_Hij : TYPE == EDGE_PROJ ? B.ep_Hij : B.eo_Hij) + (size_t)Di * Dj * ee;
+    const bool row_i = c < Di, row_j = (c >= Di) && (c < Di + Dj);
+#pragma unroll 1
+    for (int cc = 0; cc < Di + Dj; cc++) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < D; k++) s += JtO[k] * __shfl_sync(FULL, J[k], half_base + cc);
+        if (!active) continue;
+        if (row_i) {
+            if (cc < Di) rec[cc * Di + c] = i_free ? s : 0.0;                              // Hii (col-major)
+            else Hij[(cc - Di) * Di + c] = (i_free && j_free) ? s : 0.0;                    // A^T Omega B
+        } else if (row_j) {
+            if (cc >= Di) rec[Di * Di + Di + (cc - Di) * Dj + (c - Di)] = j_free ? s : 0.0;  // Hjj
+        }
+    }
+    if (active) {
+        if (row_i) rec[Di * Di + c] = i_free ? brow : 0.0;
+        else if (row_j) rec[Di * Di + Di + Dj * Dj + (c - Di)] = j_free ? brow : 0.0;
+    }
+}
+
+// one warp per vertex; dim = 6 (cameras) or 9 (cuboids)
+__global__ void __launch_bounds__(128) k_gather(BABuffers B, int n_vertices, int dim, const int* adj_ptr, const int64_t* adj_H, const int64_t* adj_b, double* H, double* b) {
+    const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (v >= n_vertices) return;
+    const int a0 = adj_ptr[v], a1 = adj_ptr[v + 1];
+    const int nn = dim * dim;
+    double acc[3] = {0, 0, 0}, accb = 0;
+    for (int a = a0; a < a1; a++) {
+        const double* hs = B.contrib + adj_H[a];
+        const double* bs = B.contrib + adj_b[a];
+#pragma unroll
+        for (int q = 0; q < 3; q++) { int idx = lane + 32 * q; if (idx < nn) acc[q] += hs[idx]; }
+        if (lane < dim) accb += bs[lane];
+    }
+#pragma unroll
+    for (int q = 0; q < 3; q++) { int idx = lane + 32 * q; if (idx < nn) H[(size_t)v * nn + idx] = acc[q]; }
+    if (lane < dim) b[(size_t)v * dim + lane] = accb;
+}
+
+// deterministic chi2 reduction: one warp, fixed order
+__global__ void __launch_bounds__(32) k_chi2(const double* edge_chi2, int n, double* out) {
+    const unsigned FULL = 0xffffffffu;
+    double s = 0;
+    for (int i = threadIdx.x; i < n; i += 32) s += edge_chi2[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(FULL, s, o);
+    if (threadIdx.x == 0) *out = s;
+}
+
+cudaError_t ba_launch(const BABuffers& B, bool want_J, cudaStream_t st, int* n_launches) {
+    int L = 0;
+    auto grid = [](int n_edges) { return (n_edges * 16 + LIN_THREADS - 1) / LIN_THREADS; };
+    if (B.n_ec) { k_linearize<EDGE_CUBOID><<<grid(B.n_ec), LIN_THREADS, 0, st>>>(B, B.n_ec, 0, 0, want_J ? B.ec_Ji : nullptr, want_J ? B.ec_Jj : nullptr); L++; }
+    if (B.n_ep) { k_linearize<EDGE_PROJ><<<grid(B.n_ep), LIN_THREADS, 0, st>>>(B, B.n_ep, (int64_t)132 * B.n_ec, B.n_ec, want_J ? B.ep_Ji : nullptr, want_J ? B.ep_Jj : nullptr); L++; }
+    if (B.n_eo) { k_linearize<EDGE_ODOM><<<grid(B.n_eo), LIN_THREADS, 0, st>>>(B, B.n_eo, (int64_t)132 * (B.n_ec + B.n_ep), B.n_ec + B.n_ep, want_J ? B.eo_Ji : nullptr, want_J ? B.eo_Jj : nullptr); L++; }
+    if (B.n_cam) { k_gather<<<(B.n_cam * 32 + 127) / 128, 128, 0, st>>>(B, B.n_cam, 6, B.cam_adj_ptr, B.cam_adj_H, B.cam_adj_b, B.H_cam, B.b_cam); L++; }
+    if (B.n_cube) { k_gather<<<(B.n_cube * 32 + 127) / 128, 128, 0, st>>>(B, B.n_cube, 9, B.cube_adj_ptr, B.cube_adj_H, B.cube_adj_b, B.H_cube, B.b_cube); L++; }
+    k_chi2<<<1, 32, 0, st>>>(B.edge_chi2, B.n_ec + B.n_ep + B.n_eo, B.chi2); L++;
+    if (n_launches) *n_launches = L;
+    return cudaGetLastError();
+}
+
+void ba_release(BAState& s) {
+    for (void* p : s.allocs) cudaFree(p);
+    s.allocs.clear();
+    s.has_graph = s.has_estimates = s.ran = false;
+}
+
+}  // namespace csb
+
+using namespace csb;
+
+namespace {
+template <class T>
+int dev_alloc(csb_context* c, T** out, size_t count) {
+    void* p = nullptr;
+    CSB_CUDA(c, cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    c->ba.allocs.push_back(p);
+    *out = reinterpret_cast<T*>(p);
+    return CSB_OK;
+}
+template <class T>
+int dev_upload(csb_context* c, const T** out, const T* host, size_t count) {
+    T* p = nullptr;
+    int rc = dev_alloc(c, &p, count);
+    if (rc != CSB_OK) return rc;
+    if (count) CSB_CUDA(c, cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    *out = p;
+    return CSB_OK;
+}
+}  // namespace
+
+#define CSB_TRY(x) do { int rc__ = (x); if (rc__ != CSB_OK) return rc__; } while (0)
+
+extern "C" {
+
+int csb_ba_set_graph(csb_context* c, const csb_ba_graph* g) {
+    if (!c || !g) return CSB_ERR_INVALID;
+    if (g->n_cam < 0 || g->n_cube < 0 || g->n_ec < 0 || g->n_ep < 0 || g->n_eo < 0) { c->err = "negative size"; return CSB_ERR_INVALID; }
+    CSB_CUDA(c, cudaSetDevice(c->device));
+    CSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    ba_release(c->ba);
+    BAState& s = c->ba;
+    s.n_cam = g->n_cam; s.n_cube = g->n_cube; s.n_ec = g->n_ec; s.n_ep = g->n_ep; s.n_eo = g->n_eo;
+    auto chk = [&](const int32_t* idx, int n, int lim) { for (int i = 0; i < n; i++) if (idx[i] < 0 || idx[i] >= lim) return false; return true; };
+    if (!chk(g->ec_cam, g->n_ec, g->n_cam) || !chk(g->ec_cube, g->n_ec, g->n_cube) || !chk(g->ep_cam, g->n_ep, g->n_cam) || !chk(g->ep_cube, g->n_ep, g->n_cube) ||
+        !chk(g->eo_cam_i, g->n_eo, g->n_cam) || !chk(g->eo_cam_j, g->n_eo, g->n_cam)) { c->err = "edge vertex index out of range"; return CSB_ERR_INVALID; }
+    BABuffers& B = s.B;
+    std::memset(&B, 0, sizeof B);
+    B.n_cam = g->n_cam; B.n_cube = g->n_cube; B.n_ec = g->n_ec; B.n_ep = g->n_ep; B.n_eo = g->n_eo;
+    CSB_TRY(dev_upload(c, &B.cam_fixed, g->cam_fixed, (size_t)g->n_cam));
+    CSB_TRY(dev_upload(c, &B.cube_fixed, g->cube_fixed, (size_t)g->n_cube));
+    CSB_TRY(dev_upload(c, &B.ec_cam, g->ec_cam, (size_t)g->n_ec)); CSB_TRY(dev_upload(c, &B.ec_cube, g->ec_cube, (size_t)g->n_ec));
+    CSB_TRY(dev_upload(c, &B.ec_meas, g->ec_meas, (size_t)g->n_ec * 10)); CSB_TRY(dev_upload(c, &B.ec_info, g->ec_info, (size_t)g->n_ec * 81));
+    CSB_TRY(dev_upload(c, &B.ep_cam, g->ep_cam, (size_t)g->n_ep)); CSB_TRY(dev_upload(c, &B.ep_cube, g->ep_cube, (size_t)g->n_ep));
+    CSB_TRY(dev_upload(c, &B.ep_meas, g->ep_meas, (size_t)g->n_ep * 4)); CSB_TRY(dev_upload(c, &B.ep_info, g->ep_info, (size_t)g->n_ep * 16));
+    CSB_TRY(dev_upload(c, &B.ep_K, g->ep_K, (size_t)g->n_ep * 9));
+    CSB_TRY(dev_upload(c, &B.eo_i, g->eo_cam_i, (size_t)g->n_eo)); CSB_TRY(dev_upload(c, &B.eo_j, g->eo_cam_j, (size_t)g->n_eo));
+    CSB_TRY(dev_upload(c, &B.eo_meas, g->eo_meas, (size_t)g->n_eo * 7)); CSB_TRY(dev_upload(c, &B.eo_info, g->eo_info, (size_t)g->n_eo * 36));
+
+    // buildStructure(): per-vertex adjacency in edge order ec, ep, eo (block_solver.hpp:142-295 allocates the blocks;
+    // sparse_optimizer.cpp:482-487 fixes the edge order)
+    std::vector<std::vector<std::pair<int64_t, int64_t>>> cam_adj(g->n_cam), cube_adj(g->n_cube);
+    for (int e = 0; e < g->n_ec; e++) {
+        int64_t r = (int64_t)132 * e;
+        cam_adj[g->ec_cam[e]].push_back({r, r + 36});
+        cube_adj[g->ec_cube[e]].push_back({r + 42, r + 42 + 81});
+    }
+    for (int e = 0; e < g->n_ep; e++) {
+        int64_t r = (int64_t)132 * (g->n_ec + e);
+        cam_adj[g->ep_cam[e]].push_back({r, r + 36});
+        cube_adj[g->ep_cube[e]].push_back({r + 42, r + 42 + 81});
+    }
+    for (int e = 0; e < g->n_eo; e++) {
+        int64_t r = (int64_t)132 * (g->n_ec + g->n_ep) + (int64_t)84 * e;
+        cam_adj[g->eo_cam_i[e]].push_back({r, r + 36});
+        cam_adj[g->eo_cam_j[e]].push_back({r + 42, r + 42 + 36});
+    }
+    auto flatten = [&](const std::vector<std::vector<std::pair<int64_t, int64_t>>>& adj, const int** d_ptr, const int64_t** d_H, const int64_t** d_b) -> int {
+        std::vector<int> ptr(adj.size() + 1, 0);
+        std::vector<int64_t> hh, bb;
+        for (size_t v = 0; v < adj.size(); v++) {
+            ptr[v + 1] = ptr[v] + (int)adj[v].size();
+            for (auto& pr : adj[v]) { hh.push_back(pr.first); bb.push_back(pr.second); }
+        }
+        CSB_TRY(dev_upload(c, d_ptr, ptr.data(), ptr.size()));
+        CSB_TRY(dev_upload(c, d_H, hh.data(), hh.size()));
+        CSB_TRY(dev_upload(c, d_b, bb.data(), bb.size()));
+        CSB_CUDA(c, cudaStreamSynchronize(c->stream));  // host vectors go out of scope
+        return CSB_OK;
+    };
+    CSB_TRY(flatten(cam_adj, &B.cam_adj_ptr, &B.cam_adj_H, &B.cam_adj_b));
+    CSB_TRY(flatten(cube_adj, &B.cube_adj_ptr, &B.cube_adj_H, &B.cube_adj_b));
+
+    double* tmp = nullptr;
+    CSB_TRY(dev_alloc(c, &tmp, (size_t)g->n_cam * 7)); B.cams7 = tmp;
+    CSB_TRY(dev_alloc(c, &tmp, (size_t)g->n_cube * 10)); B.cubes10 = tmp;
+    CSB_TRY(dev_alloc(c, &B.ec_err, (size_t)g->n_ec * 9)); CSB_TRY(dev_alloc(c, &B.ep_err, (size_t)g->n_ep * 4)); CSB_TRY(dev_alloc(c, &B.eo_err, (size_t)g->n_eo * 6));
+    CSB_TRY(dev_alloc(c, &B.ec_Ji, (size_t)g->n_ec * 54)); CSB_TRY(dev_alloc(c, &B.ec_Jj, (size_t)g->n_ec * 81));
+    CSB_TRY(dev_alloc(c, &B.ep_Ji, (size_t)g->n_ep * 24)); CSB_TRY(dev_alloc(c, &B.ep_Jj, (size_t)g->n_ep * 36));
+    CSB_TRY(dev_alloc(c, &B.eo_Ji, (size_t)g->n_eo * 36)); CSB_TRY(dev_alloc(c, &B.eo_Jj, (size_t)g->n_eo * 36));
+    CSB_TRY(dev_alloc(c, &B.ec_Hij, (size_t)g->n_ec * 54)); CSB_TRY(dev_alloc(c, &B.ep_Hij, (size_t)g->n_ep * 54)); CSB_TRY(dev_alloc(c, &B.eo_Hij, (size_t)g->n_eo * 36));
+    CSB_TRY(dev_alloc(c, &B.contrib, (size_t)132 * (g->n_ec + g->n_ep) + (size_t)84 * g->n_eo));
+    CSB_TRY(dev_alloc(c, &B.edge_chi2, (size_t)(g->n_ec + g->n_ep + g->n_eo)));
+    CSB_TRY(dev_alloc(c, &B.H_cam, (size_t)g->n_cam * 36)); CSB_TRY(dev_alloc(c, &B.b_cam, (size_t)g->n_cam * 6));
+    CSB_TRY(dev_alloc(c, &B.H_cube, (size_t)g->n_cube * 81)); CSB_TRY(dev_alloc(c, &B.b_cube, (size_t)g->n_cube * 9));
+    CSB_TRY(dev_alloc(c, &B.chi2, 1));
+    CSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    s.has_graph = true;
+    return CSB_OK;
+}
+
+int csb_ba_upload_estimates(csb_context* c, const double* cams7, const double* cubes10) {
+    if (!c) return CSB_ERR_INVALID;
+    BAState& s = c->ba;
+    if (!s.has_graph) { c->err = "csb_ba_upload_estimates before csb_ba_set_graph"; return CSB_ERR_STATE; }
+    if ((!cams7 && s.n_cam) || (!cubes10 && s.n_cube)) return CSB_ERR_INVALID;
+    CSB_CUDA(c, cudaSetDevice(c->device));
+    if (s.n_cam) CSB_CUDA(c, cudaMemcpyAsync(const_cast<double*>(s.B.cams7), cams7, 56 * (size_t)s.n_cam, cudaMemcpyHostToDevice, c->stream));
+    if (s.n_cube) CSB_CUDA(c, cudaMemcpyAsync(const_cast<double*>(s.B.cubes10), cubes10, 80 * (size_t)s.n_cube, cudaMemcpyHostToDevice, c->stream));
+    s.has_estimates = true;
+    return CSB_OK;
+}
+
+static int ba_run_impl(csb_context* c, bool want_J) {
+    BAState& s = c->ba;
+    if (!s.has_graph || !s.has_estimates) { c->err = "csb_ba_run before graph/estimates"; return CSB_ERR_STATE; }
+    CSB_CUDA(c, cudaSetDevice(c->device));
+    CSB_CUDA(c, ba_launch(s.B, want_J, c->stream, &s.launches_last));
+    s.ran = true;
+    return CSB_OK;
+}
+
+int csb_ba_run(csb_context* c) {
+    if (!c) return CSB_ERR_INVALID;
+    return ba_run_impl(c, false);
+}
+
+int csb_ba_download(csb_context* c, const csb_ba_output* o) {
+    if (!c || !o) return CSB_ERR_INVALID;
+    BAState& s = c->ba;
+    if (!s.ran) { c->err = "csb_ba_download before csb_ba_run"; return CSB_ERR_STATE; }
+    CSB_CUDA(c, cudaSetDevice(c->device));
+    const BABuffers& B = s.B;
+    auto dl = [&](double* dst, const double* src, size_t n) -> int {
+        if (dst && n) CSB_CUDA(c, cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyDeviceToHost, c->stream));
+        return CSB_OK;
+    };
+    CSB_TRY(dl(o->ec_err, B.ec_err, (size_t)s.n_ec * 9)); CSB_TRY(dl(o->ep_err, B.ep_err, (size_t)s.n_ep * 4)); CSB_TRY(dl(o->eo_err, B.eo_err, (size_t)s.n_eo * 6));
+    CSB_TRY(dl(o->ec_Ji, B.ec_Ji, (size_t)s.n_ec * 54)); CSB_TRY(dl(o->ec_Jj, B.ec_Jj, (size_t)s.n_ec * 81));
+    CSB_TRY(dl(o->ep_Ji, B.ep_Ji, (size_t)s.n_ep * 24)); CSB_TRY(dl(o->ep_Jj, B.ep_Jj, (size_t)s.n_ep * 36));
+    CSB_TRY(dl(o->eo_Ji, B.eo_Ji, (size_t)s.n_eo * 36)); CSB_TRY(dl(o->eo_Jj, B.eo_Jj, (size_t)s.n_eo * 36));
+    CSB_TRY(dl(o->H_cam, B.H_cam, (size_t)s.n_cam * 36)); CSB_TRY(dl(o->b_cam, B.b_cam, (size_t)s.n_cam * 6));
+    CSB_TRY(dl(o->H_cube, B.H_cube, (size_t)s.n_cube * 81)); CSB_TRY(dl(o->b_cube, B.b_cube, (size_t)s.n_cube * 9));
+    CSB_TRY(dl(o->ec_Hij, B.ec_Hij, (size_t)s.n_ec * 54)); CSB_TRY(dl(o->ep_Hij, B.ep_Hij, (size_t)s.n_ep * 54)); CSB_TRY(dl(o->eo_Hij, B.eo_Hij, (size_t)s.n_eo * 36));
+    CSB_TRY(dl(o->chi2, B.chi2, 1));
+    CSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return CSB_OK;
+}
+
+int csb_ba_linearize(csb_context* c, const double* cams7, const double* cubes10, const csb_ba_output* out) {
+    if (!c || !out) return CSB_ERR_INVALID;
+    CSB_TRY(csb_ba_upload_estimates(c, cams7, cubes10));
+    bool want_J = out->ec_Ji || out->ec_Jj || out->ep_Ji || out->ep_Jj || out->eo_Ji || out->eo_Jj;
+    CSB_TRY(ba_run_impl(c, want_J));
+    return csb_ba_download(c, out);
+}
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+// context.h -- the opaque csb_context: device, stream, grow-only device workspaces of both halves.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "ba.h"
+#include "csb_internal.h"
+#include "proposal.h"
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct DetectState {
+    bool uploaded = false, ran = false;
+    int n_frames = 0, n_boxes = 0, n_lines = 0, n_tasks = 0;
+    int max_groups = 0, max_lines_per_frame = 0, max_hyp_per_task = 0, map_cap_floats = 0;
+    int64_t n_map_floats = 0, out_total = 0, line_cap_total = 0;
+    csb_detect_params params{};
+    std::vector<csb::TaskTab> ttab;
+    std::vector<csb::FrameTab> ftab;
+    std::vector<csb_task> tasks;
+    csb::DetectBuffers B{};
+    DevBuf d_ftab, d_ttab, d_order, d_box_begin, d_lines, d_maps, d_ml_seg, d_ml_ang, d_ml_mid, d_n_merged, d_p_dist, d_p_angle, d_p_hyp,
+        d_n_valid, d_keep, d_norm, d_n_keep, d_cand_score, d_cand_pos, d_n_cand, d_sel_idx, d_sel_flag, d_rank_idx, d_cuboids, d_n_cuboids,
+        d_counters, d_dbg;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool timed_last = false;
+    int64_t h2d_bytes = 0, d2h_bytes = 0;
+    int launches_last = 0;
+};
+
+struct csb_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 0, max_smem_optin = 0;
+    std::string err;
+    DetectState det;
+    csb::BAState ba;
+};
+
+#define CSB_CUDA(ctx, call)                                                                   \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                \
+            return CSB_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)

@@ -1,0 +1,214 @@
+// csb_math.cuh -- fixed-size FP64 math shared by the host planner and the sm_100a kernels.
+//
+// Everything is plain IEEE-754 double arithmetic evaluated left to right; the library is compiled with
+// -fmad=false (device) and -ffp-contract=off (host) so that a*b+c is two correctly rounded operations on
+// both sides and results do not depend on where a function runs.  std::min/std::max semantics of the
+// reference (`(b<a)?b:a`, NaN-propagating on the first argument) are kept via cmin/cmax -- CUDA's
+// fmin/fmax treat NaN differently.
+//
+// Reference types restated: Eigen::Quaterniond(Matrix3d), toRotationMatrix, q*v, Matrix3d::inverse
+// (SURVEY.md App. B); matrix_utils.cpp:19-98,344-353; g2o se3quat.h:41-362, se3_ops.hpp:28-48.
+#pragma once
+#include <cmath>
+
+#if defined(__CUDACC__)
+#define CSB_HD __host__ __device__ __forceinline__
+#else
+#define CSB_HD inline
+#endif
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+namespace csb {
+
+struct V2 { double x, y; };
+struct V3 { double x, y, z; };
+struct M3 { double m[9]; };  // row-major
+struct Quat { double w, x, y, z; };
+struct SE3 { Quat r; V3 t; };
+struct Cube { SE3 pose; V3 scale; };
+
+CSB_HD double cmin(double a, double b) { return (b < a) ? b : a; }
+CSB_HD double cmax(double a, double b) { return (a < b) ? b : a; }
+
+CSB_HD V2 sub(V2 a, V2 b) { return {a.x - b.x, a.y - b.y}; }
+CSB_HD double norm2(V2 a) { return sqrt(a.x * a.x + a.y * a.y); }
+CSB_HD double dist2(V2 a, V2 b) { return norm2(sub(a, b)); }
+CSB_HD V3 sub(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+CSB_HD V3 add(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+CSB_HD V3 scl(double s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+CSB_HD double norm3(V3 a) { return sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+CSB_HD V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+
+CSB_HD V3 mul(const M3& A, V3 v) {
+    return {(A.m[0] * v.x + A.m[1] * v.y) + A.m[2] * v.z, (A.m[3] * v.x + A.m[4] * v.y) + A.m[5] * v.z, (A.m[6] * v.x + A.m[7] * v.y) + A.m[8] * v.z};
+}
+CSB_HD M3 mul(const M3& A, const M3& B) {
+    M3 C;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) C.m[i * 3 + j] = (A.m[i * 3] * B.m[j] + A.m[i * 3 + 1] * B.m[3 + j]) + A.m[i * 3 + 2] * B.m[6 + j];
+    return C;
+}
+CSB_HD M3 identity3() { return M3{{1, 0, 0, 0, 1, 0, 0, 0, 1}}; }
+
+CSB_HD double cof3(const M3& a, int i, int j) {
+    int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    return a.m[i1 * 3 + j1] * a.m[i2 * 3 + j2] - a.m[i1 * 3 + j2] * a.m[i2 * 3 + j1];
+}
+// Eigen Matrix3d::inverse(): cofactors of column 0 give the determinant; result(i,j) = cofactor(j,i)/det
+CSB_HD M3 inverse3(const M3& a) {
+    double c0 = cof3(a, 0, 0), c1 = cof3(a, 1, 0), c2 = cof3(a, 2, 0);
+    double det = (c0 * a.m[0] + c1 * a.m[3]) + c2 * a.m[6];
+    double invdet = 1.0 / det;
+    M3 r;
+    r.m[0] = c0 * invdet; r.m[1] = c1 * invdet; r.m[2] = c2 * invdet;
+    r.m[3] = cof3(a, 0, 1) * invdet; r.m[4] = cof3(a, 1, 1) * invdet; r.m[5] = cof3(a, 2, 1) * invdet;
+    r.m[6] = cof3(a, 0, 2) * invdet; r.m[7] = cof3(a, 1, 2) * invdet; r.m[8] = cof3(a, 2, 2) * invdet;
+    return r;
+}
+
+CSB_HD Quat quat_from_rot(const M3& R) {
+    Quat q;
+    double t = (R.m[0] + R.m[4]) + R.m[8];
+    if (t > 0) {
+        t = sqrt(t + 1.0);
+        q.w = 0.5 * t;
+        t = 0.5 / t;
+        q.x = (R.m[7] - R.m[5]) * t;
+        q.y = (R.m[2] - R.m[6]) * t;
+        q.z = (R.m[3] - R.m[1]) * t;
+    } else {
+        int i = 0;
+        if (R.m[4] > R.m[0]) i = 1;
+        if (R.m[8] > R.m[i * 4]) i = 2;
+        int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = sqrt(R.m[i * 4] - R.m[j * 4] - R.m[k * 4] + 1.0);
+        double v[3];
+        v[i] = 0.5 * t;
+        t = 0.5 / t;
+        q.w = (R.m[k * 3 + j] - R.m[j * 3 + k]) * t;
+        v[j] = (R.m[j * 3 + i] + R.m[i * 3 + j]) * t;
+        v[k] = (R.m[k * 3 + i] + R.m[i * 3 + k]) * t;
+        q.x = v[0]; q.y = v[1]; q.z = v[2];
+    }
+    return q;
+}
+CSB_HD M3 quat_to_rot(const Quat& q) {
+    double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+    double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+    double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+    double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+    M3 r;
+    r.m[0] = 1 - (tyy + tzz); r.m[1] = txy - twz; r.m[2] = txz + twy;
+    r.m[3] = txy + twz; r.m[4] = 1 - (txx + tzz); r.m[5] = tyz - twx;
+    r.m[6] = txz - twy; r.m[7] = tyz + twx; r.m[8] = 1 - (txx + tyy);
+    return r;
+}
+CSB_HD V3 quat_rot(const Quat& q, V3 v) {
+    V3 qv{q.x, q.y, q.z};
+    V3 uv = cross(qv, v);
+    uv = add(uv, uv);
+    V3 c = cross(qv, uv);
+    return {(v.x + q.w * uv.x) + c.x, (v.y + q.w * uv.y) + c.y, (v.z + q.w * uv.z) + c.z};
+}
+CSB_HD Quat quat_mul(const Quat& a, const Quat& b) {
+    Quat r;
+    r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+    r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+    r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+    r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+    return r;
+}
+CSB_HD Quat quat_conj(const Quat& q) { return {q.w, -q.x, -q.y, -q.z}; }
+CSB_HD void quat_normalize(Quat& q) {
+    double n = sqrt(((q.x * q.x + q.y * q.y) + q.z * q.z) + q.w * q.w);
+    q.x /= n; q.y /= n; q.z /= n; q.w /= n;
+}
+
+// matrix_utils.cpp:38-49
+CSB_HD void quat_to_euler_zyx(const Quat& q, double& roll, double& pitch, double& yaw) {
+    double qw = q.w, qx = q.x, qy = q.y, qz = q.z;
+    roll = atan2(2 * (qw * qx + qy * qz), 1 - 2 * (qx * qx + qy * qy));
+    pitch = asin(2 * (qw * qy - qz * qx));
+    yaw = atan2(2 * (qw * qz + qx * qy), 1 - 2 * (qy * qy + qz * qz));
+}
+// matrix_utils.cpp:81-96
+CSB_HD M3 euler_zyx_to_rot(double roll, double pitch, double yaw) {
+    double cp = cos(pitch), sp = sin(pitch), sr = sin(roll), cr = cos(roll), sy = sin(yaw), cy = cos(yaw);
+    M3 R;
+    R.m[0] = cp * cy; R.m[1] = (sr * sp * cy) - (cr * sy); R.m[2] = (cr * sp * cy) + (sr * sy);
+    R.m[3] = cp * sy; R.m[4] = (sr * sp * sy) + (cr * cy); R.m[5] = (cr * sp * sy) - (sr * cy);
+    R.m[6] = -sp; R.m[7] = sr * cp; R.m[8] = cr * cp;
+    return R;
+}
+// matrix_utils.cpp:344-353
+CSB_HD double normalize_to_pi(double a) {
+    if (a > M_PI / 2) return a - M_PI;
+    else if (a < -M_PI / 2) return a + M_PI;
+    else return a;
+}
+
+// ---- SE(3), g2o se3quat.h ---------------------------------------------------------------------
+CSB_HD void se3_normalize(SE3& s) {  // :346-351
+    if (s.r.w < 0) { s.r.w = -s.r.w; s.r.x = -s.r.x; s.r.y = -s.r.y; s.r.z = -s.r.z; }
+    quat_normalize(s.r);
+}
+CSB_HD SE3 se3_make(const Quat& q, V3 t) { SE3 s; s.r = q; s.t = t; se3_normalize(s); return s; }
+CSB_HD SE3 se3_from_vec7(const double* v) { return se3_make(Quat{v[6], v[3], v[4], v[5]}, V3{v[0], v[1], v[2]}); }
+CSB_HD SE3 se3_mul(const SE3& a, const SE3& b) {  // :110-116
+    SE3 r;
+    r.t = add(a.t, quat_rot(a.r, b.t));
+    r.r = quat_mul(a.r, b.r);
+    se3_normalize(r);
+    return r;
+}
+CSB_HD SE3 se3_inverse(const SE3& a) {  // :129-134
+    SE3 r;
+    r.r = quat_conj(a.r);
+    r.t = quat_rot(r.r, V3{a.t.x * -1., a.t.y * -1., a.t.z * -1.});
+    return r;
+}
+CSB_HD M3 skew(V3 v) { return M3{{0, -v.z, v.y, v.z, 0, -v.x, -v.y, v.x, 0}}; }
+CSB_HD void se3_log(const SE3& s, double* res) {  // :230-267
+    M3 R = quat_to_rot(s.r);
+    double d = 0.5 * (R.m[0] + R.m[4] + R.m[8] - 1);
+    V3 dR{R.m[7] - R.m[5], R.m[2] - R.m[6], R.m[3] - R.m[1]};
+    V3 omega;
+    double c;
+    if (d > 0.99999) {
+        omega = scl(0.5, dR);
+        c = (1. / 12.);
+    } else {
+        double theta = acos(d);
+        omega = scl(theta / (2 * sqrt(1 - d * d)), dR);
+        c = (1 - theta / (2 * tan(theta / 2))) / (theta * theta);
+    }
+    M3 Om = skew(omega);
+    M3 Om2 = mul(Om, Om);
+    M3 I = identity3();
+    M3 Vinv;
+    for (int i = 0; i < 9; i++) Vinv.m[i] = I.m[i] - 0.5 * Om.m[i] + c * Om2.m[i];
+    V3 ups = mul(Vinv, s.t);
+    res[0] = omega.x; res[1] = omega.y; res[2] = omega.z; res[3] = ups.x; res[4] = ups.y; res[5] = ups.z;
+}
+CSB_HD SE3 se3_exp(const double* u) {  // :275-323
+    V3 omega{u[0], u[1], u[2]}, upsilon{u[3], u[4], u[5]};
+    double theta = norm3(omega);
+    M3 Om = skew(omega);
+    M3 Om2 = mul(Om, Om);
+    M3 I = identity3();
+    M3 R, V;
+    if (theta < 0.00001) {
+        for (int i = 0; i < 9; i++) R.m[i] = I.m[i] + Om.m[i] + Om2.m[i];
+        V = R;
+    } else {
+        double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta), c = (theta - sin(theta)) / (pow(theta, 3));
+        for (int i = 0; i < 9; i++) R.m[i] = I.m[i] + a * Om.m[i] + b * Om2.m[i];
+        for (int i = 0; i < 9; i++) V.m[i] = I.m[i] + b * Om.m[i] + c * Om2.m[i];
+    }
+    return se3_make(quat_from_rot(R), mul(V, upsilon));
+}
+
+}  // namespace csb

@@ -1,0 +1,53 @@
+// proposal.h -- device buffer table + kernel launchers of the proposal half.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "csb_internal.h"
+
+namespace csb {
+
+// All pointers are device pointers.  Per-proposal arrays are indexed by TaskTab::out_offset + i (capacity n_hyp per task),
+// merged-line arrays by TaskTab::line_cap_offset + i (capacity = line count of the task's frame).
+struct DetectBuffers {
+    const FrameTab* ftab;
+    const TaskTab* ttab;
+    const int* task_order;      // tasks sorted by decreasing n_hyp (persistent-CTA queue)
+    const int* box_task_begin;  // n_boxes + 1
+    const double* lines;        // raw frame lines, x1 y1 x2 y2
+    const float* maps;          // packed distance maps
+    int n_tasks;
+    int pad;
+    // k_prep_lines outputs
+    double* ml_seg;  // 4 per merged line
+    double* ml_ang;
+    double* ml_mid;  // 2 per merged line
+    int* n_merged;
+    // k_score outputs (compacted valid proposals in enumeration order)
+    double* p_dist;
+    double* p_angle;
+    int* p_hyp;
+    int* n_valid;
+    // k_select outputs
+    int* keep;
+    double* norm_score;
+    int* n_keep;
+    double* cand_score;
+    int* cand_keeppos;
+    int* n_cand;
+    int* sel_idx;             // 2x capacity, global fallback for very large tasks
+    unsigned char* sel_flag;
+    // k_rank
+    int* rank_idx;
+    csb_cuboid* cuboids;
+    int* n_cuboids;
+    int* counters;  // [0]: k_score task queue head
+    DetectConst dc;
+};
+
+cudaError_t launch_prep_lines(const DetectBuffers& B, int max_lines_per_frame, cudaStream_t st);
+cudaError_t launch_score(const DetectBuffers& B, int max_groups, int num_sms, int max_smem_optin, int* map_cap_floats_out, cudaStream_t st);
+cudaError_t launch_select(const DetectBuffers& B, int max_hyp_per_task, int max_smem_optin, cudaStream_t st);
+cudaError_t launch_rank(const DetectBuffers& B, int n_boxes, cudaStream_t st);
+cudaError_t launch_debug_corners(const DetectBuffers& B, int task, int n_valid, double* out, cudaStream_t st);
+
+}  // namespace csb

@@ -1,0 +1,236 @@
+// proposal_dev.cuh -- device functions of the proposal half (geometry, scoring, 3D recovery, heap emulation).
+//
+// Each function states the reference lines it implements (paths relative to detect_3d_cuboid/src/).
+// Arithmetic is written in the same order as the reference so that, with -fmad=false, the FP64 results are
+// the same IEEE sequence a scalar x86 build produces.
+#pragma once
+#include "csb_internal.h"
+#include "csb_math.cuh"
+
+namespace csb {
+
+struct TaskGeo {
+    double left, top, right, down;          // left_x_raw, top_y_raw, right_x_raw, down_y_expan
+    double roi_l, roi_t, roi_r, roi_d;      // expan_distmap bounds (inclusive)
+};
+
+__device__ __forceinline__ TaskGeo make_geo(const TaskTab& t) {
+    TaskGeo g;
+    g.left = (double)t.left_x_raw; g.top = (double)t.top_y_raw; g.right = (double)t.right_x_raw; g.down = (double)t.down_y_expan;
+    g.roi_l = (double)t.roi_left; g.roi_t = (double)t.roi_top; g.roi_r = (double)t.roi_right; g.roi_d = (double)t.roi_down;
+    return g;
+}
+
+// object_3d_util.cpp:239-242
+__device__ __forceinline__ bool inside_box(V2 p, double l, double t, double r, double d) { return l <= p.x && p.x <= r && t <= p.y && p.y <= d; }
+
+// object_3d_util.cpp:309-353
+__device__ __forceinline__ V2 seg_hit_boundary(V2 ps, V2 pe, double bx0, double by0, double bx1, double by1) {
+    V2 direc = sub(pe, ps);
+    V2 hit{-1.0, -1.0};
+    if (by0 == by1) {
+        double lambd = (by0 - ps.y) / direc.y;
+        if (lambd >= 0) {
+            V2 tmp{ps.x + lambd * direc.x, ps.y + lambd * direc.y};
+            if ((bx0 <= tmp.x) && (tmp.x <= bx1)) { hit = tmp; hit.y = by0; }
+        }
+    }
+    if (bx0 == bx1) {
+        double lambd = (bx0 - ps.x) / direc.x;
+        if (lambd >= 0) {
+            V2 tmp{ps.x + lambd * direc.x, ps.y + lambd * direc.y};
+            if ((by0 <= tmp.y) && (tmp.y <= by1)) { hit = tmp; hit.x = bx0; }
+        }
+    }
+    return hit;
+}
+
+// object_3d_util.cpp:357-382 with infinite_line == true (u_b is dead there)
+__device__ __forceinline__ V2 line_intersect(V2 p1s, V2 p1e, V2 p2s, V2 p2e) {
+    double X2_X1 = p1e.x - p1s.x, Y2_Y1 = p1e.y - p1s.y;
+    double X4_X3 = p2e.x - p2s.x, Y4_Y3 = p2e.y - p2s.y;
+    double X1_X3 = p1s.x - p2s.x, Y1_Y3 = p1s.y - p2s.y;
+    double u_a = (X4_X3 * Y1_Y3 - Y4_Y3 * X1_X3) / (Y4_Y3 * X2_X1 - X4_X3 * Y2_Y1);
+    double INT_X = p1s.x + X2_X1 * u_a;
+    double INT_Y = p1s.y + Y2_Y1 * u_a;
+    return {INT_X * 1.0, INT_Y * 1.0};
+}
+
+// getVanishingPoints, object_3d_util.cpp:928-937.  KinvR row-major; c,s = cos/sin(yaw) from the host table.
+__device__ __forceinline__ void vanishing_points(const double* K, double c, double s, double* vp /*6: x1 y1 x2 y2 x3 y3*/) {
+    double ax = (K[0] * c + K[1] * s) + K[2] * 0.0, ay = (K[3] * c + K[4] * s) + K[5] * 0.0, az = (K[6] * c + K[7] * s) + K[8] * 0.0;
+    double ms = -s;
+    double bx = (K[0] * ms + K[1] * c) + K[2] * 0.0, by = (K[3] * ms + K[4] * c) + K[5] * 0.0, bz = (K[6] * ms + K[7] * c) + K[8] * 0.0;
+    double cx = (K[0] * 0.0 + K[1] * 0.0) + K[2] * 1.0, cy = (K[3] * 0.0 + K[4] * 0.0) + K[5] * 1.0, cz = (K[6] * 0.0 + K[7] * 0.0) + K[8] * 1.0;
+    vp[0] = ax / az; vp[1] = ay / az; vp[2] = bx / bz; vp[3] = by / bz; vp[4] = cx / cz; vp[5] = cy / cz;
+}
+
+// Corner construction + rejection cascade, box_proposal_detail.cpp:413-625.
+// Returns vp_1_position (1 left, 2 right) or 0 if the hypothesis is rejected.  c[0..7] = corners 1..8.
+__device__ __forceinline__ int construct_corners(const TaskGeo& g, const double* vp, double c1x, int config_id, V2* c) {
+    const double shorted_edge_thre = 20;
+    V2 vp_1{vp[0], vp[1]}, vp_2{vp[2], vp[3]}, vp_3{vp[4], vp[5]};
+    V2 corner_1_top{c1x, g.top};
+    int vp_1_position = 0;
+    V2 corner_2_top = seg_hit_boundary(vp_1, corner_1_top, g.right, g.top, g.right, g.down);
+    if (corner_2_top.x == -1) {
+        corner_2_top = seg_hit_boundary(vp_1, corner_1_top, g.left, g.top, g.left, g.down);
+        if (corner_2_top.x != -1) vp_1_position = 2;
+    } else
+        vp_1_position = 1;
+    if (!(vp_1_position > 0)) return 0;
+    if (dist2(corner_1_top, corner_2_top) < shorted_edge_thre) return 0;
+
+    V2 corner_3_top, corner_4_top;
+    if (config_id == 1) {
+        if (vp_1_position == 1) corner_4_top = seg_hit_boundary(vp_2, corner_1_top, g.left, g.top, g.left, g.down);
+        else corner_4_top = seg_hit_boundary(vp_2, corner_1_top, g.right, g.top, g.right, g.down);
+        if (corner_4_top.y == -1) return 0;
+        if (dist2(corner_1_top, corner_4_top) < shorted_edge_thre) return 0;
+        corner_3_top = line_intersect(vp_2, corner_2_top, vp_1, corner_4_top);
+        if (!inside_box(corner_3_top, g.left, g.top, g.right, g.down)) return 0;
+        if ((dist2(corner_3_top, corner_4_top) < shorted_edge_thre) || (dist2(corner_3_top, corner_2_top) < shorted_edge_thre)) return 0;
+    } else {
+        if (vp_1_position == 1) corner_3_top = seg_hit_boundary(vp_2, corner_2_top, g.left, g.top, g.left, g.down);
+        else corner_3_top = seg_hit_boundary(vp_2, corner_2_top, g.right, g.top, g.right, g.down);
+        if (corner_3_top.y == -1) return 0;
+        if (dist2(corner_2_top, corner_3_top) < shorted_edge_thre) return 0;
+        corner_4_top = line_intersect(vp_1, corner_3_top, vp_2, corner_1_top);
+        if (!inside_box(corner_4_top, g.left, g.roi_t, g.right, g.roi_d)) return 0;  // sic: x from the raw box, y from the ROI (:558)
+        if ((dist2(corner_3_top, corner_4_top) < shorted_edge_thre) || (dist2(corner_4_top, corner_1_top) < shorted_edge_thre)) return 0;
+    }
+    V2 corner_5_down = seg_hit_boundary(vp_3, corner_3_top, g.left, g.down, g.right, g.down);
+    if (corner_5_down.y == -1) return 0;
+    if (dist2(corner_3_top, corner_5_down) < shorted_edge_thre) return 0;
+    V2 corner_6_down = line_intersect(vp_2, corner_5_down, vp_3, corner_2_top);
+    if (!inside_box(corner_6_down, g.roi_l, g.roi_t, g.roi_r, g.roi_d)) return 0;
+    if ((dist2(corner_6_down, corner_2_top) < shorted_edge_thre) || (dist2(corner_6_down, corner_5_down) < shorted_edge_thre)) return 0;
+    V2 corner_7_down = line_intersect(vp_1, corner_6_down, vp_3, corner_1_top);
+    if (!inside_box(corner_7_down, g.roi_l, g.roi_t, g.roi_r, g.roi_d)) return 0;
+    if ((dist2(corner_7_down, corner_1_top) < shorted_edge_thre) || (dist2(corner_7_down, corner_6_down) < shorted_edge_thre)) return 0;
+    V2 corner_8_down = line_intersect(vp_1, corner_5_down, vp_2, corner_7_down);
+    if (!inside_box(corner_8_down, g.roi_l, g.roi_t, g.roi_r, g.roi_d)) return 0;
+    if ((dist2(corner_8_down, corner_4_top) < shorted_edge_thre) || (dist2(corner_8_down, corner_5_down) < shorted_edge_thre) ||
+        (dist2(corner_8_down, corner_7_down) < shorted_edge_thre))
+        return 0;
+    c[0] = corner_1_top; c[1] = corner_2_top; c[2] = corner_3_top; c[3] = corner_4_top;
+    c[4] = corner_5_down; c[5] = corner_6_down; c[6] = corner_7_down; c[7] = corner_8_down;
+    return vp_1_position;
+}
+
+// hypothesis id -> (group, top, config).  id = (group * n_top + top) * 2 + (config - 1)
+__device__ __forceinline__ void decode_hyp(int h, int n_top, int& group, int& top, int& cfg) {
+    cfg = (h & 1) + 1;
+    int r = h >> 1;
+    group = r / n_top;
+    top = r - group * n_top;
+}
+
+// ---- 3D recovery -------------------------------------------------------------------------------
+// plane_hits_3d (object_3d_util.cpp:853-875) for one pixel; T = top 3 rows of transToWolrd (3x4 row-major)
+__device__ __forceinline__ V3 plane_hit_3d(const double* T, const double* invK, const double* plane, V2 px) {
+    double rx = (invK[0] * px.x + invK[1] * px.y) + invK[2] * 1.0;
+    double ry = (invK[3] * px.x + invK[4] * px.y) + invK[5] * 1.0;
+    double rz = (invK[6] * px.x + invK[7] * px.y) + invK[8] * 1.0;
+    double denom = (plane[0] * rx + plane[1] * ry) + plane[2] * rz;
+    double frac = -plane[3] / denom;
+    double sx = frac * rx, sy = frac * ry, sz = frac * rz;
+    double h0 = ((T[0] * sx + T[1] * sy) + T[2] * sz) + T[3] * 1.0;
+    double h1 = ((T[4] * sx + T[5] * sy) + T[6] * sz) + T[7] * 1.0;
+    double h2 = ((T[8] * sx + T[9] * sy) + T[10] * sz) + T[11] * 1.0;
+    double h3 = ((0.0 * sx + 0.0 * sy) + 0.0 * sz) + 1.0 * 1.0;
+    return {h0 / h3, h1 / h3, h2 / h3};
+}
+
+struct Obj3D {
+    double pos[3], scale[3];
+};
+// change_2d_corner_to_3d_object (object_3d_util.cpp:941-990): pose/scale part
+__device__ __forceinline__ void corners_to_3d(const V2* c, const double* T, const double* invK, Obj3D& o) {
+    // ground_plane_sensor = transToWolrd^T * (0,0,1,0) = third row of transToWolrd (box_proposal_detail.cpp:130-131, 376)
+    double ground[4];
+    for (int i = 0; i < 4; i++) ground[i] = ((T[i] * 0.0 + T[4 + i] * 0.0) + T[8 + i] * 1.0) + (i == 3 ? 1.0 : 0.0) * 0.0;
+    V3 g0 = plane_hit_3d(T, invK, ground, c[4]), g1 = plane_hit_3d(T, invK, ground, c[5]);
+    V3 g2 = plane_hit_3d(T, invK, ground, c[6]), g3 = plane_hit_3d(T, invK, ground, c[7]);
+    double length_half = norm3(sub(g0, g3)) / 2;
+    double width_half = norm3(sub(g0, g1)) / 2;
+    // get_wall_plane_equation, :909-925
+    V3 n = cross(sub(g0, g1), V3{0, 0, 1});
+    double nn = norm3(n);
+    n = {n.x / nn, n.y / nn, n.z / nn};
+    double dist = ((-n.x) * g0.x + (-n.y) * g0.y) + (-n.z) * g0.z;
+    double wall_w[4] = {n.x, n.y, n.z, dist};
+    if (dist < 0)
+        for (int i = 0; i < 4; i++) wall_w[i] = -wall_w[i];
+    double wall_s[4];
+    for (int i = 0; i < 4; i++) wall_s[i] = ((T[i] * wall_w[0] + T[4 + i] * wall_w[1]) + T[8 + i] * wall_w[2]) + (i == 3 ? 1.0 : 0.0) * wall_w[3];
+    V3 topw = plane_hit_3d(T, invK, wall_s, c[1]);
+    double height_half = topw.z / 2;
+    double mean_x = (((g0.x + g1.x) + g2.x) + g3.x) / 4;
+    double mean_y = (((g0.y + g1.y) + g2.y) + g3.y) / 4;
+    o.pos[0] = mean_x; o.pos[1] = mean_y; o.pos[2] = height_half;
+    o.scale[0] = length_half; o.scale[1] = width_half; o.scale[2] = height_half;
+}
+
+// ---- libstdc++ heap algorithms, restated (bits/stl_heap.h, bits/stl_algo.h __heap_select/__partial_sort) ----
+// The reference ranks with std::partial_sort (matrix_utils.cpp:327-335), which is not stable: which of several
+// equal keys ends up inside the kept prefix depends on these exact sift sequences, so they are reproduced literally.
+template <class Less>
+__device__ void heap_adjust(int* first, int holeIndex, int len, int value, Less less) {
+    const int topIndex = holeIndex;
+    int secondChild = holeIndex;
+    while (secondChild < (len - 1) / 2) {
+        secondChild = 2 * (secondChild + 1);
+        if (less(first[secondChild], first[secondChild - 1])) secondChild--;
+        first[holeIndex] = first[secondChild];
+        holeIndex = secondChild;
+    }
+    if ((len & 1) == 0 && secondChild == (len - 2) / 2) {
+        secondChild = 2 * (secondChild + 1);
+        first[holeIndex] = first[secondChild - 1];
+        holeIndex = secondChild - 1;
+    }
+    // __push_heap
+    int parent = (holeIndex - 1) / 2;
+    while (holeIndex > topIndex && less(first[parent], value)) {
+        first[holeIndex] = first[parent];
+        holeIndex = parent;
+        parent = (holeIndex - 1) / 2;
+    }
+    first[holeIndex] = value;
+}
+template <class Less>
+__device__ void heap_make(int* first, int len, Less less) {
+    if (len < 2) return;
+    int parent = (len - 2) / 2;
+    while (true) {
+        int value = first[parent];
+        heap_adjust(first, parent, len, value, less);
+        if (parent == 0) return;
+        parent--;
+    }
+}
+// __heap_select(first, first+k, first+n)
+template <class Less>
+__device__ void heap_select(int* first, int k, int n, Less less) {
+    heap_make(first, k, less);
+    for (int i = k; i < n; i++)
+        if (less(first[i], first[0])) {  // __pop_heap(first, middle, i)
+            int value = first[i];
+            first[i] = first[0];
+            heap_adjust(first, 0, k, value, less);
+        }
+}
+// __sort_heap(first, first+k)
+template <class Less>
+__device__ void heap_sort(int* first, int k, Less less) {
+    int last = k;
+    while (last > 1) {
+        --last;
+        int value = first[last];
+        first[last] = first[0];
+        heap_adjust(first, 0, last, value, less);
+    }
+}
+
+}  // namespace csb

@@ -1,0 +1,191 @@
+/* cubeslam_b200.h -- C ABI of the B200-native CubeSLAM hot path.
+ *
+ * Drop-in boundary.  Two halves:
+ *
+ *  (1) proposal half -- everything inside detect_3d_cuboid::detect_cuboid()
+ *      (reference: detect_3d_cuboid/include/detect_3d_cuboid/detect_3d_cuboid.h:74-118,
+ *       detect_3d_cuboid/src/box_proposal_detail.cpp:65-861) except cv::Canny + cv::distanceTransform
+ *      (box_proposal_detail.cpp:320-327), which stay with the caller: csb_detect_plan() tells the caller
+ *      which ROIs need a distance map, csb_detect_batch() consumes them.
+ *
+ *  (2) BA half -- what g2o's BlockSolver::buildSystem() does for the cuboid graph
+ *      (reference: object_slam/Thirdparty/g2o/g2o/core/block_solver.hpp:501-560 calling
+ *       base_binary_edge.hpp:54-120,130-205 on the edge/vertex classes of
+ *       object_slam/include/object_slam/g2o_Object.h:202-292 and types_six_dof_expmap.h:59-142).
+ *
+ * All entry points take plain pointers and sizes, return CSB_OK (0) or a negative error code, and never
+ * throw.  Buffers are caller-owned.  A context is bound to one CUDA device and one stream; it is not
+ * re-entrant (like the reference's detect_3d_cuboid object, which mutates cam_pose during the sweep).
+ * There is no CPU fallback: every entry point that computes fails with CSB_ERR_CUDA if no device is usable.
+ */
+#ifndef CUBESLAM_B200_H
+#define CUBESLAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSB_OK 0
+#define CSB_ERR_INVALID (-1)  /* bad argument / inconsistent sizes */
+#define CSB_ERR_CUDA (-2)     /* CUDA runtime error (see csb_last_error) */
+#define CSB_ERR_CAPACITY (-3) /* an output buffer or internal cap is too small */
+#define CSB_ERR_STATE (-4)    /* call order violated (e.g. run before upload) */
+
+typedef struct csb_context csb_context;
+
+int csb_create(csb_context** out, int device_ordinal);
+void csb_destroy(csb_context* ctx);
+const char* csb_last_error(const csb_context* ctx);
+/* Use an existing CUDA stream (cudaStream_t) for all work of this context; NULL = context-owned stream. */
+int csb_set_stream(csb_context* ctx, void* cuda_stream);
+int csb_synchronize(csb_context* ctx);
+const char* csb_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Proposal half
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Public mode flags of class detect_3d_cuboid (detect_3d_cuboid.h:95-117).  Plot/print flags have no
+ * meaning here and are handled (ignored) by the C++ adapter. */
+typedef struct csb_detect_params {
+    int32_t consider_config_1;             /* :109 default 1 */
+    int32_t consider_config_2;             /* :110 default 1 */
+    int32_t whether_sample_cam_roll_pitch; /* :111 default 1 */
+    int32_t whether_sample_bbox_height;    /* :112 default 0 */
+    int32_t max_cuboid_num;                /* :114 default 1 */
+    int32_t reserved;
+    double nominal_skew_ratio; /* :115 default 1 */
+    double max_cut_skew;       /* :116 default 3 */
+} csb_detect_params;
+
+/* One detect_cuboid() call = one frame: calibration (set_calibration), camera pose (transToWolrd, row-major
+ * 4x4), image size, and the row ranges of this frame's 2D boxes and line segments in the batch arrays. */
+typedef struct csb_frame {
+    double Kalib[9];
+    double transToWolrd[16];
+    int32_t img_width, img_height;
+    int32_t box_begin, box_end;   /* rows of boxes[] : x y w h prob (0-based pixels), obj_bbox_coors */
+    int32_t line_begin, line_end; /* rows of lines[] : x1 y1 x2 y2, all_lines_raw */
+} csb_frame;
+
+/* One (2D box, height sample) unit of work.  The caller must supply a float32 distance map of
+ * roi_height x roi_width for each task, computed as the reference does:
+ *   cv::Canny(gray(cv::Rect(roi_left, roi_top, roi_width, roi_height)), e, 80, 200);
+ *   cv::distanceTransform(255 - e, dist_map, CV_DIST_L2, 3);
+ * packed at dist_maps[map_offset .. map_offset + roi_width*roi_height). */
+typedef struct csb_task {
+    int32_t frame_id, box_id; /* box_id indexes boxes[] (batch-global row) */
+    int32_t hs_id, down_expand;
+    int32_t roi_left, roi_top, roi_width, roi_height;
+    int32_t n_top, n_enum; /* top-edge samples; hypotheses enumerated for this task */
+    int64_t map_offset;    /* in floats */
+} csb_task;
+
+/* Mirror of class cuboid (detect_3d_cuboid.h:20-41), POD. */
+typedef struct csb_cuboid {
+    double pos[3];
+    double scale[3];
+    double rotY;
+    double box_config_type[2];       /* configuration id, vp1 left(1)/right(2) */
+    double box_corners_3d_world[24]; /* 3x8 row-major */
+    double rect_detect_2d[4];
+    double edge_distance_error, edge_angle_error, normalized_error, skew_ratio;
+    double down_expand_height, camera_roll_delta, camera_pitch_delta;
+    int32_t box_corners_2d[16]; /* 2x8 row-major */
+    int32_t task_id;            /* provenance: task (index into tasks[]) ... */
+    int32_t raw_cube_ind;       /* ... and index in that task's compacted valid-proposal list */
+    int32_t rank_index;         /* index in the box's raw_obj_proposals list (what sort_idx_small holds) */
+    int32_t reserved;
+} csb_cuboid;
+
+typedef struct csb_detect_stats {
+    int64_t n_enumerated; /* hypotheses enumerated */
+    int64_t n_scored;     /* hypotheses that passed all geometric checks and received both scores */
+    int64_t n_kept;       /* proposals that survived fuse_normalize_scores_v2 */
+    int64_t h2d_bytes, d2h_bytes;
+    int32_t n_kernel_launches, n_tasks_smem_map; /* tasks whose distance map was staged in shared memory */
+    float gpu_ms_prep, gpu_ms_score, gpu_ms_select, gpu_ms_rank; /* CUDA-event times of the last run (0 if not timed) */
+} csb_detect_stats;
+
+/* Host-only integer logic of box_proposal_detail.cpp:143-256: enumerates tasks and ROI rectangles.
+ * tasks_out may be NULL to query the count. */
+int csb_detect_plan(const csb_frame* frames, int n_frames, const double* boxes, int n_boxes, const csb_detect_params* params,
+                    csb_task* tasks_out, int max_tasks, int* n_tasks_out, int64_t* n_map_floats_out);
+
+/* The batched equivalent of calling detect_cuboid() once per frame, with HOST buffers (copies in and out
+ * happen inside).  cuboids_out holds n_boxes * max_cuboid_num entries (box-major, best first),
+ * n_cuboids_out[n_boxes] the number filled per box (0 = empty ObjectSet).  stats may be NULL. */
+int csb_detect_batch(csb_context* ctx, const csb_frame* frames, int n_frames, const double* boxes, int n_boxes, const double* lines,
+                     int n_lines, const csb_task* tasks, int n_tasks, const float* dist_maps, int64_t n_map_floats,
+                     const csb_detect_params* params, csb_cuboid* cuboids_out, int32_t* n_cuboids_out, csb_detect_stats* stats);
+
+/* Device-resident variant: upload once, run the kernels any number of times, download results.
+ * csb_detect_run() is asynchronous on the context stream; timed != 0 records per-kernel CUDA events. */
+int csb_detect_upload(csb_context* ctx, const csb_frame* frames, int n_frames, const double* boxes, int n_boxes, const double* lines,
+                      int n_lines, const csb_task* tasks, int n_tasks, const float* dist_maps, int64_t n_map_floats,
+                      const csb_detect_params* params);
+int csb_detect_run(csb_context* ctx, int timed);
+int csb_detect_download(csb_context* ctx, csb_cuboid* cuboids_out, int32_t* n_cuboids_out, csb_detect_stats* stats);
+
+/* Parity/debug access to the intermediate per-task lists of the last run (all pointers optional):
+ *  n_valid, hyp_id[n_valid], dist_err[n_valid], angle_err[n_valid]      <- all_configs_error_one_objH cols 4,5
+ *  corners[n_valid*16] (x0..x7,y0..y7)                                   <- all_box_corners_2d_one_objH (recomputed)
+ *  merged_lines[n_merged*4], n_keep, keep[n_keep], norm_score[n_keep]    <- merge_break_lines / fuse_normalize_scores_v2 */
+int csb_detect_debug_task(csb_context* ctx, int task_id, int32_t* n_valid, int32_t* n_merged, int32_t* n_keep, int32_t* hyp_id,
+                          double* dist_err, double* angle_err, double* corners, double* merged_lines, int32_t* keep, double* norm_score,
+                          int capacity);
+
+/* ------------------------------------------------------------------------------------------------
+ * BA half
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Camera-object graph in SoA form.
+ *  cameras : VertexSE3Expmap estimates (world->camera), 7 doubles x y z qx qy qz qw (SE3Quat::toVector)
+ *  cuboids : VertexCuboid estimates (object->world), 10 doubles x y z qx qy qz qw sx sy sz (cuboid::toVector)
+ *  ec      : EdgeSE3Cuboid      (vertex0 = camera, vertex1 = cuboid), measurement 10, information 9x9 row-major
+ *  ep      : EdgeSE3CuboidProj  (camera, cuboid), measurement 4 (cx cy w h), information 4x4, Kalib 3x3 row-major
+ *  eo      : EdgeSE3Expmap      (camera i, camera j), measurement 7, information 6x6
+ * Edges are accumulated in the order ec, ep, eo, each in array order (= g2o's id order for main_obj.cpp's ids). */
+typedef struct csb_ba_graph {
+    int32_t n_cam, n_cube;
+    const int32_t* cam_fixed;  /* n_cam  : Vertex::fixed() */
+    const int32_t* cube_fixed; /* n_cube */
+    int32_t n_ec;
+    const int32_t *ec_cam, *ec_cube;
+    const double *ec_meas, *ec_info;
+    int32_t n_ep;
+    const int32_t *ep_cam, *ep_cube;
+    const double *ep_meas, *ep_info, *ep_K;
+    int32_t n_eo;
+    const int32_t *eo_cam_i, *eo_cam_j;
+    const double *eo_meas, *eo_info;
+} csb_ba_graph;
+
+/* Outputs of one linearisation; any pointer may be NULL.  Jacobians and Hessian blocks are column-major
+ * like g2o's Eigen blocks: J is D x dim(vertex); H_cam[i] 6x6, H_cube[j] 9x9, *_Hij = A^T Omega B with
+ * rows = vertex0 dim, cols = vertex1 dim.  b_* = -J^T Omega e accumulated per vertex. */
+typedef struct csb_ba_output {
+    double *ec_err, *ec_Ji, *ec_Jj; /* n_ec x 9, x 54, x 81 */
+    double *ep_err, *ep_Ji, *ep_Jj; /* n_ep x 4, x 24, x 36 */
+    double *eo_err, *eo_Ji, *eo_Jj; /* n_eo x 6, x 36, x 36 */
+    double *H_cam, *b_cam;          /* n_cam x 36, x 6 */
+    double *H_cube, *b_cube;        /* n_cube x 81, x 9 */
+    double *ec_Hij, *ep_Hij, *eo_Hij; /* n_ec x 54, n_ep x 54, n_eo x 36 */
+    double* chi2;                   /* 1 : sum of e^T Omega e (SparseOptimizer::activeRobustChi2) */
+} csb_ba_output;
+
+/* buildStructure(): upload topology, measurements and information matrices; build per-vertex adjacency. */
+int csb_ba_set_graph(csb_context* ctx, const csb_ba_graph* graph);
+/* computeActiveErrors() + buildSystem() with HOST vertex estimates in, HOST blocks out. */
+int csb_ba_linearize(csb_context* ctx, const double* cams7, const double* cubes10, const csb_ba_output* out);
+/* Device-resident: upload estimates once, linearise repeatedly (async), download when needed. */
+int csb_ba_upload_estimates(csb_context* ctx, const double* cams7, const double* cubes10);
+int csb_ba_run(csb_context* ctx);
+int csb_ba_download(csb_context* ctx, const csb_ba_output* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUBESLAM_B200_H */
