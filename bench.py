@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the CubeSLAM hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path ("ours")
+  python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm's CPU path on the host cores
+
+Metric (BASELINE.json): cuboid proposals scored per second.  One step = one pass of the proposal hot path over
+BASELINE config #2: 64 KITTI-shaped frames (1242x375) x 8 2D boxes per GPU, roll/pitch sampling on, both
+configurations, synthetic inputs (seeded; distance maps by cv2.Canny + cv2.distanceTransform exactly as the reference
+computes them).  A "scored proposal" is a hypothesis that passes all geometric checks and receives both scores
+(a row of all_configs_error_one_objH); the enumerated-hypothesis rate is reported next to it.
+
+value : inputs resident in HBM, kernels only (prep_lines, score, select, rank, observe [+ NCCL allgather of the
+        observation records when N > 1]); CUDA events per step on the launching stream, L2 flushed between steps.
+e2e   : the same metric through csb_detect_batch() with pinned HOST buffers: H2D of frames/boxes/lines/distance maps,
+        the kernels, D2H of the cuboid records, all inside the timed region.
+Multi-GPU: frames shard across ranks (weak scaling, fixed 64 frames per GPU), no data-path collective except the final
+allgather of 128-byte observation records.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "cuboid_proposals_scored_per_sec"
+UNIT = "proposals/s"
+FRAMES_PER_GPU = 64
+BOXES_PER_FRAME = 8
+ALGO_BYTES_PER_PROPOSAL = 550.0   # SURVEY.md 8d contract figure: 596 B (config 1) / 508 B (config 2), 0.55 KB mean
+ALGO_BYTES_PER_EDGE = 1856.0      # EdgeSE3Cuboid, fused (Jacobian not materialised)
+
+
+def workload_config(n_gpus):
+    return {"workload": "config#2 batched proposal scoring: %d KITTI-shape frames x %d boxes per GPU, roll/pitch sampling on, both configs"
+                        % (FRAMES_PER_GPU, BOXES_PER_FRAME),
+            "frames_per_gpu": FRAMES_PER_GPU, "boxes_per_frame": BOXES_PER_FRAME, "img": "1242x375", "sharding": "frames over %d GPU(s)" % n_gpus,
+            "l2": "256 MiB buffer written between timed steps (flush), excluded from the timed region"}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_batch(rank):
+    from cube_slam_wu_b200 import synth
+    return synth.make_kitti_batch(FRAMES_PER_GPU, boxes_per_frame=BOXES_PER_FRAME, seed=20260925 + rank)
+
+
+def oracle_batch_inputs(batch):
+    """Pack the batch for orc_detect_batch (oracle plan order, unpadded maps)."""
+    import oracle_lib as O
+    from cube_slam_wu_b200 import synth
+    nF = len(batch["K"])
+    box_off = np.array([batch["box_ranges"][0][0]] + [r[1] for r in batch["box_ranges"]], np.int32)
+    line_off = np.array([batch["line_ranges"][0][0]] + [r[1] for r in batch["line_ranges"]], np.int32)
+    maps, map_off = [], [0]
+    for f in range(nF):
+        b0, b1 = batch["box_ranges"][f]
+        tasks = O.plan(batch["boxes"][b0:b1], batch["img_w"], batch["img_h"], False)
+        for t in tasks:
+            maps.append(synth.dist_map_for_roi(batch["images"][f], t.left, t.top, t.width, t.height).ravel())
+        map_off.append(map_off[-1] + sum(t.width * t.height for t in tasks))
+    maps = np.concatenate(maps + [np.zeros(16, np.float32)])
+    return dict(n_frames=nF, K=np.ascontiguousarray(batch["K"], np.float64), T=np.ascontiguousarray(batch["T"], np.float64),
+                boxes=np.ascontiguousarray(batch["boxes"], np.float64), box_off=box_off, lines=np.ascontiguousarray(batch["lines"], np.float64),
+                line_off=line_off, maps=maps, map_off=np.array(map_off, np.int64), img_w=batch["img_w"], img_h=batch["img_h"])
+
+
+def oracle_run(inp, n_threads):
+    import ctypes as C
+    import oracle_lib as O
+    L = O.lib()
+    P = O.default_params(leak_cam_state=1)
+    n_enum = C.c_longlong()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    t0 = time.perf_counter()
+    n = L.orc_detect_batch(inp["n_frames"], p(inp["K"]), p(inp["T"]), inp["img_w"], inp["img_h"], p(inp["boxes"]), p(inp["box_off"]), p(inp["lines"]),
+                           p(inp["line_off"]), p(inp["maps"]), p(inp["map_off"]), C.byref(P), int(n_threads), None, C.byref(n_enum))
+    return n, n_enum.value, time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference algorithm's CPU path (oracle port; the reference itself needs Eigen/OpenCV/ROS and does
+    not build here) on all host threads.  Rank 0 only."""
+    if rank != 0:
+        return
+    import oracle_lib as O
+    O.build()
+    cores = os.cpu_count() or 1
+    inp = oracle_batch_inputs(build_batch(0))
+    for _ in range(args.warmup):
+        oracle_run(inp, cores)
+    times, scored = [], 0
+    for _ in range(args.steps):
+        n, n_enum, dt = oracle_run(inp, cores)
+        times.append(dt); scored = n
+    tot = sum(times)
+    value = scored * args.steps / tot
+    sample = "%d frames x %d boxes per step (the full N=1 workload), %d std::threads over frames" % (FRAMES_PER_GPU, BOXES_PER_FRAME, cores)
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                      "data": "synthetic", "config": workload_config(args.gpus),
+                      "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                      "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "enumerated_per_s": n_enum * args.steps / tot, "gpu_launches": 0}))
+
+
+def pinned(a):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    return t, t.numpy()
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import cube_slam_wu_b200 as csb
+    from cube_slam_wu_b200 import synth
+    import helpers as H
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream()
+    ctx = csb.Context(local_rank, stream=stream.cuda_stream)
+    params = csb.DetectParams.default()
+
+    batch = build_batch(rank)
+    frames, boxes, lines, tasks, n_tasks, maps, n_map = H.gpu_inputs(csb, batch, params)
+    keep = []
+    tb, boxes = pinned(boxes); tl, lines = pinned(lines); tm, maps = pinned(maps)
+    keep += [tb, tl, tm]
+    n_boxes = boxes.shape[0]
+
+    # ---- device-resident timing ("value")
+    ctx.detect_upload(frames, boxes, lines, tasks, n_tasks, maps, n_map, params)
+    obs = torch.zeros(n_boxes * 16, dtype=torch.float64, device="cuda")
+    obs_all = torch.zeros(world * n_boxes * 16, dtype=torch.float64, device="cuda") if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    L = csb.lib()
+    import ctypes as C
+
+    def step(timed):
+        ctx.detect_run(timed=timed)
+        rc = L.csb_detect_observations_device(ctx._h, C.c_void_p(obs.data_ptr()))
+        assert rc == 0
+        if world > 1:
+            dist.all_gather_into_tensor(obs_all, obs)
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            flush.zero_()
+            step(False)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        score_ms = []
+        t_wall0 = time.perf_counter()
+        for i in range(args.steps):
+            flush.zero_()
+            ev[i][0].record(stream)
+            step(True)
+            ev[i][1].record(stream)
+            # per-kernel events of this step (reads back after the step has finished; outside the event bracket)
+            cub, ncub, st = ctx.detect_download()
+            score_ms.append((st.gpu_ms_prep, st.gpu_ms_score, st.gpu_ms_select, st.gpu_ms_rank))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t_wall = time.perf_counter() - t_wall0
+        clocks = sampler.stop()
+    ms_total = sum(a.elapsed_time(b) for a, b in ev)
+    n_scored, n_enum = int(st.n_scored), int(st.n_enumerated)
+    t = torch.tensor([ms_total, float(n_scored), float(n_enum)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_total, n_scored_all, n_enum_all = float(tmax[0]), float(tsum[1]), float(tsum[2])
+    else:
+        n_scored_all, n_enum_all = float(n_scored), float(n_enum)
+    value = n_scored_all * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e through the C ABI with host buffers
+    torch.cuda.synchronize()
+    e2e_times = []
+    for i in range(args.warmup + args.steps):
+        flush.zero_(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        cub, ncub, st_e = ctx.detect_batch(frames, boxes, lines, tasks, n_tasks, maps, n_map, params, want_stats=True)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            e2e_times.append(dt)
+    e2e_total = sum(e2e_times)
+    te = torch.tensor([e2e_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = n_scored_all * args.steps / float(te[0])
+
+    out = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        k_ms = float(np.mean([s[1] for s in score_ms]))
+        achieved = ALGO_BYTES_PER_PROPOSAL * n_scored / (k_ms * 1e-3) / 1e9
+        traffic = None
+        tf = os.path.join(ROOT, "profiles", "k_score_traffic.json")
+        if os.path.exists(tf):
+            try:
+                traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": workload_config(world), "clocks": clocks,
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(st_e.h2d_bytes), "d2h_bytes_per_step": int(st_e.d2h_bytes),
+                       "ms_per_step": 1e3 * float(te[0]) / args.steps},
+               "gpu_launches": (int(st.n_kernel_launches) + 1) * args.steps,
+               "roofline": {"kernel": "k_score", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PROPOSAL * n_scored,
+                            "kernel_ms": k_ms, "note": "gather/FP64-issue bound, not HBM bound (SURVEY.md 8d)"},
+               "enumerated_per_s": n_enum_all * args.steps / (ms_total * 1e-3),
+               "scored_per_step_per_gpu": n_scored, "enumerated_per_step_per_gpu": n_enum,
+               "kernel_ms": {"prep_lines": float(np.mean([s[0] for s in score_ms])), "score": k_ms, "select": float(np.mean([s[2] for s in score_ms])),
+                             "rank": float(np.mean([s[3] for s in score_ms]))},
+               "wall_s_timed_region": t_wall}
+
+        # ---- secondary metric: BA edges linearised per second (config #4), resident, back to back
+        try:
+            g = synth.make_ba_graph()
+            ctx.ba_set_graph(g["cam_fixed"], g["cube_fixed"], ec=g["ec"], ep=g["ep"], eo=g["eo"])
+            ctx.ba_upload_estimates(g["cams7"], g["cubes10"])
+            n_edges = len(g["ec"][0]) + len(g["eo"][0])
+            with torch.cuda.stream(stream):
+                for _ in range(5):
+                    ctx.ba_run()
+                torch.cuda.synchronize()
+                reps = 200
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for _ in range(reps):
+                    ctx.ba_run()
+                b.record(stream)
+                torch.cuda.synchronize()
+            ba_ms = a.elapsed_time(b) / reps
+            ba_ach = ALGO_BYTES_PER_EDGE * n_edges / (ba_ms * 1e-3) / 1e9
+            out["ba"] = {"metric": "ba_edges_linearised_per_sec", "value": n_edges / (ba_ms * 1e-3), "unit": "edges/s", "edges": n_edges,
+                         "ms_per_linearisation": ba_ms, "config": "config#4: 200 keyframes, 50 cuboids, 4000 EdgeSE3Cuboid + 199 EdgeSE3Expmap, 200 back-to-back linearisations (L2-resident; launch/FP64 bound)",
+                         "roofline": {"bound": "hbm", "achieved": ba_ach, "peak": peak, "unit": "GB/s", "frac": ba_ach / peak, "traffic": None}}
+        except Exception as e:  # the headline line must still print
+            out["ba"] = {"error": str(e)}
+
+        # ---- CPU baseline: oracle port, one thread (the reference is single-threaded), bounded sample
+        if world == 1:
+            try:
+                import oracle_lib as O
+                O.build()
+                inp = oracle_batch_inputs(batch)
+                reps, tot, n = 0, 0.0, 0
+                while tot < 10.0 and reps < 40:
+                    n, _, dt = oracle_run(inp, 1)
+                    tot += dt; reps += 1
+                out["cpu_baseline"] = {"value": n * reps / tot, "unit": UNIT, "cores": 1, "kind": "port",
+                                       "sample": "%d repeats of the full step (%d frames x %d boxes), single thread like the reference" % (reps, FRAMES_PER_GPU, BOXES_PER_FRAME)}
+                if "ba" in out and "value" in out["ba"]:
+                    E = O.ba_edges(ec=g["ec"], ep=g["ep"], eo=g["eo"])
+                    t0 = time.perf_counter(); r = 0
+                    while time.perf_counter() - t0 < 3.0:
+                        O.ba_linearize(g["cams7"], g["cam_fixed"], g["cubes10"], g["cube_fixed"], E, 1); r += 1
+                    out["ba"]["cpu_baseline"] = {"value": n_edges * r / (time.perf_counter() - t0), "unit": "edges/s", "cores": 1, "kind": "port",
+                                                 "sample": "%d linearisations of the config#4 graph" % r}
+            except Exception as e:
+                out["cpu_baseline"] = {"error": str(e)}
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

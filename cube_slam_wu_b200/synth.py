@@ -134,6 +134,22 @@ def se3_inv(a):
     return np.concatenate([quat_rot(qc, -a[:3]), qc])
 
 
+def project_bbox(cube10, Tcw7, K, min_depth=1.0):
+    """cuboid::projectOntoImageBbox (g2o_Object.h:181-197) in numpy; None if a corner is closer than min_depth."""
+    body = np.array([[1, 1, -1, -1, 1, 1, -1, -1], [1, -1, -1, 1, 1, -1, -1, 1], [-1, -1, -1, -1, 1, 1, 1, 1.0]])
+    pts = []
+    for k in range(8):
+        pw = cube10[:3] + quat_rot(cube10[3:7], body[:, k] * cube10[7:])
+        pc = Tcw7[:3] + quat_rot(Tcw7[3:7], pw)
+        if pc[2] < min_depth:
+            return None
+        uv = K @ pc
+        pts.append(uv[:2] / uv[2])
+    pts = np.array(pts)
+    mn, mx = pts.min(0), pts.max(0)
+    return np.array([(mn[0] + mx[0]) / 2, (mn[1] + mx[1]) / 2, mx[0] - mn[0], mx[1] - mn[1]])
+
+
 def make_ba_graph(n_cam=200, n_cube=50, obs_per_cube=80, seed=20260926, with_proj=False):
     """Config #4: returns dict with cams7 (world->camera), cubes10, fixed flags and edge tuples ec / ep / eo."""
     rng = np.random.default_rng(seed)
@@ -155,7 +171,7 @@ def make_ba_graph(n_cam=200, n_cube=50, obs_per_cube=80, seed=20260926, with_pro
         cubes.append(np.concatenate([[r * math.cos(th), r * math.sin(th), s[2]], q, s]))
     cubes = np.array(cubes)
     ec_cam, ec_cube, ec_meas, ec_info = [], [], [], []
-    ep_meas, ep_info, ep_K = [], [], []
+    ep_meas, ep_info, ep_K, ep_ok = [], [], [], []
     K = np.array([[535.4, 0, 320.1], [0, 539.2, 247.6], [0, 0, 1.0]])  # main_obj.cpp:484-486
     for j in range(n_cube):
         # the obs_per_cube nearest keyframes see cuboid j
@@ -178,7 +194,9 @@ def make_ba_graph(n_cam=200, n_cube=50, obs_per_cube=80, seed=20260926, with_pro
             qual = rng.uniform(0.5, 1.0)
             ec_info.append((np.eye(9) * (2 * qual) ** 2).ravel())  # main_obj.cpp:732, 775-780
             if with_proj:
-                ep_meas.append(rng.uniform([100, 100, 40, 40], [540, 380, 200, 200]))
+                bb = project_bbox(cubes[j], Tcw, K)
+                ep_ok.append(bb is not None)
+                ep_meas.append((bb if bb is not None else np.zeros(4)) + rng.normal(0, 2.0, 4))
                 ep_info.append(np.eye(4).ravel()); ep_K.append(K.ravel())
     order = np.lexsort((ec_cube, ec_cam))  # edge ids follow frames, like main_obj.cpp:768 (id = frame index)
     ec_cam = np.array(ec_cam, np.int32)[order]; ec_cube = np.array(ec_cube, np.int32)[order]
@@ -200,5 +218,6 @@ def make_ba_graph(n_cam=200, n_cube=50, obs_per_cube=80, seed=20260926, with_pro
     out = dict(cams7=cams0, cubes10=cubes0, cam_fixed=cam_fixed, cube_fixed=np.zeros(n_cube, np.int32),
                ec=(ec_cam, ec_cube, ec_meas, ec_info), eo=(eo_i, eo_j, np.array(eo_meas), eo_info), ep=None)
     if with_proj:
-        out["ep"] = (ec_cam.copy(), ec_cube.copy(), np.array(ep_meas)[order], np.array(ep_info)[order], np.array(ep_K)[order])
+        ok = np.array(ep_ok)[order]  # EdgeSE3CuboidProj only where the cuboid is fully in front of the camera
+        out["ep"] = (ec_cam[ok].copy(), ec_cube[ok].copy(), np.array(ep_meas)[order][ok], np.array(ep_info)[order][ok], np.array(ep_K)[order][ok])
     return out

@@ -129,6 +129,12 @@ int csb_detect_upload(csb_context* ctx, const csb_frame* frames, int n_frames, c
 int csb_detect_run(csb_context* ctx, int timed);
 int csb_detect_download(csb_context* ctx, csb_cuboid* cuboids_out, int32_t* n_cuboids_out, csb_detect_stats* stats);
 
+/* Per-box observation records for camera-object graph assembly (object_slam/src/main_obj.cpp:643-679, :732): the best
+ * cuboid of each 2D box as a g2o::cuboid measurement in the local camera frame.  Writes n_boxes x 16 doubles into a
+ * DEVICE buffer (asynchronously, on the context stream) so that the records can be all-gathered across GPUs (NCCL)
+ * without a host round trip:  frame_id, box_id, valid, meas_quality, x y z qx qy qz qw sx sy sz, normalized_error, 0. */
+int csb_detect_observations_device(csb_context* ctx, void* device_out);
+
 /* Parity/debug access to the intermediate per-task lists of the last run (all pointers optional):
  *  n_valid, hyp_id[n_valid], dist_err[n_valid], angle_err[n_valid]      <- all_configs_error_one_objH cols 4,5
  *  corners[n_valid*16] (x0..x7,y0..y7)                                   <- all_box_corners_2d_one_objH (recomputed)

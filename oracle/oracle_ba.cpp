@@ -564,3 +564,23 @@ void orc_cuboid_project_bbox(const double* cube10, const double* Tcw7, const dou
     projectOntoImageBbox(cuboid_from_vec10(cube10), se3_from_vec7(Tcw7), K, out4);
 }
 }  // extern "C"
+
+// Observation record of one detected cuboid for graph assembly, object_slam/src/main_obj.cpp:643-679 and :732.
+// in: pos3, rotY, scale3, normalized_error, camera_roll_delta, camera_pitch_delta, transToWolrd (row-major 4x4), sampled flag.
+// out: meas_quality, cube_local_meas (10)
+extern "C" void orc_observation(const double* pos, double rotY, const double* scale, double normalized_error, double roll_delta, double pitch_delta,
+                                const double* T16, int sampled, double* quality, double* local10) {
+    double v9[9] = {pos[0], pos[1], pos[2], 0, 0, rotY, scale[0], scale[1], scale[2]};
+    Cuboid ground = cuboid_from_minimal(v9);
+    M3 R;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R(i, j) = T16[i * 4 + j];
+    if (sampled) {
+        double e0, e1, e2;
+        quat_to_euler_zyx(quat_from_rot(R), e0, e1, e2);  // cam_pose_raw.euler_angle
+        R = euler_zyx_to_rot(e0 + roll_delta, e1 + pitch_delta, e2);
+    }
+    SE3 Twc = se3_from(quat_from_rot(R), V3{T16[3], T16[7], T16[11]});
+    Cuboid local = transform_to(ground, Twc);
+    cuboid_to_vec10(local, local10);
+    *quality = (1 - normalized_error + 0.5) / 2;
+}

@@ -1,0 +1,74 @@
+"""world_size-2 gloo test of the multi-GPU host logic (bench.py's sharding + the allgather of observation records).
+No GPU: the records are produced by the oracle here; on the GPU box bench.py --gpus N uses the CUDA path + NCCL."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle_lib as O
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+    import helpers as H
+    from cube_slam_wu_b200 import synth
+    bench.FRAMES_PER_GPU = 2
+    batch = synth.make_kitti_batch(2, boxes_per_frame=3, seed=20260925 + rank)
+    P = type("P", (), dict(consider_config_1=1, consider_config_2=1, whether_sample_cam_roll_pitch=1, whether_sample_bbox_height=0, max_cuboid_num=1,
+                           nominal_skew_ratio=1.0, max_cut_skew=3.0))
+    res = H.run_oracle(batch, P, leak=0)
+    nb = len(batch["boxes"])
+    rec = np.zeros((nb, 16))
+    import ctypes as C
+    for f, R in enumerate(res):
+        b0, b1 = batch["box_ranges"][f]
+        for b in range(b1 - b0):
+            rec[b0 + b, 0] = rank * 1000 + f; rec[b0 + b, 1] = b0 + b
+            if len(R.boxes[b]["sorted"]):
+                c = R.boxes[b]["raw"][R.boxes[b]["sorted"][0]]
+                q = C.c_double(); loc = np.zeros(10)
+                O.lib().orc_observation((C.c_double * 3)(*c.pos), C.c_double(c.rotY), (C.c_double * 3)(*c.scale), C.c_double(c.normalized_error),
+                                        C.c_double(c.camera_roll_delta), C.c_double(c.camera_pitch_delta),
+                                        np.ascontiguousarray(batch["T"][f]).ctypes.data_as(C.c_void_p), 1, C.byref(q), loc.ctypes.data_as(C.c_void_p))
+                rec[b0 + b, 2] = 1; rec[b0 + b, 3] = q.value; rec[b0 + b, 4:14] = loc; rec[b0 + b, 14] = c.normalized_error
+    t = torch.from_numpy(rec.ravel().copy())
+    allr = torch.zeros(world * t.numel(), dtype=torch.float64)
+    dist.all_gather_into_tensor(allr, t)
+    # scored counts: SUM over ranks, time: MAX over ranks (the bench's reduction)
+    v = torch.tensor([float(sum(r.n_scored for r in res)), 1.0 + rank])
+    vs = v.clone(); dist.all_reduce(vs, op=dist.ReduceOp.SUM)
+    vm = v.clone(); dist.all_reduce(vm, op=dist.ReduceOp.MAX)
+    q.value = 0
+    if rank == 0:
+        qd = dict(all=allr.numpy().reshape(world, nb, 16), mine=rec, scored_sum=float(vs[0]), scored_mine=float(v[0]), tmax=float(vm[1]))
+        np.save(os.environ["CSB_TEST_OUT"], np.array([qd], dtype=object), allow_pickle=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_observation_allgather(tmp_path):
+    port = _free_port()
+    out = str(tmp_path / "r0.npy")
+    os.environ["CSB_TEST_OUT"] = out
+    mp.spawn(_worker, args=(2, port, None), nprocs=2, join=True)
+    d = np.load(out, allow_pickle=True)[0]
+    allr = d["all"]
+    assert allr.shape[0] == 2
+    assert np.array_equal(allr[0], d["mine"])                 # rank 0's own block comes back unchanged
+    assert not np.array_equal(allr[0], allr[1])               # ranks processed different frames (seed + rank)
+    assert set(np.unique(allr[1][:, 0] // 1000)) == {1.0}     # rank 1 frames tagged with its rank
+    assert d["scored_sum"] > d["scored_mine"] > 0 and d["tmax"] == 2.0
+    valid = allr[:, :, 2] == 1
+    assert valid.sum() >= 4
+    qn = np.linalg.norm(allr[valid][:, 7:11], axis=1)
+    assert np.allclose(qn, 1.0, atol=1e-9)                    # unit quaternions in the gathered measurements
+    assert np.all((allr[valid][:, 3] >= 0.25) & (allr[valid][:, 3] <= 0.75))  # meas_quality = (1 - err + 0.5)/2, err in [0,1]
