@@ -57,7 +57,8 @@ class Cuboid(C.Structure):
 class DetectStats(C.Structure):
     _fields_ = [("n_enumerated", C.c_int64), ("n_scored", C.c_int64), ("n_kept", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("n_kernel_launches", C.c_int32), ("n_tasks_smem_map", C.c_int32),
-                ("gpu_ms_prep", C.c_float), ("gpu_ms_score", C.c_float), ("gpu_ms_select", C.c_float), ("gpu_ms_rank", C.c_float)]
+                ("gpu_ms_prep", C.c_float), ("gpu_ms_score", C.c_float), ("gpu_ms_select", C.c_float), ("gpu_ms_recover", C.c_float),
+                ("gpu_ms_rank", C.c_float), ("reserved_f", C.c_float)]
 
 
 class BAGraph(C.Structure):

@@ -279,12 +279,27 @@ __global__ void __launch_bounds__(128) k_gather(BABuffers B, int n_vertices, int
     const int a0 = adj_ptr[v], a1 = adj_ptr[v + 1];
     const int nn = dim * dim;
     double acc[3] = {0, 0, 0}, accb = 0;
-    for (int a = a0; a < a1; a++) {
-        const double* hs = B.contrib + adj_H[a];
-        const double* bs = B.contrib + adj_b[a];
+    // the sum stays in edge order (deterministic, same order as g2o's sequential accumulation); the loads of U records are
+    // issued together so that their latency overlaps
+    constexpr int U = 8;
+    for (int a = a0; a < a1; a += U) {
+        int64_t oh[U], obb[U];
 #pragma unroll
-        for (int q = 0; q < 3; q++) { int idx = lane + 32 * q; if (idx < nn) acc[q] += hs[idx]; }
-        if (lane < dim) accb += bs[lane];
+        for (int u = 0; u < U; u++) { int aa = (a + u < a1) ? a + u : a1 - 1; oh[u] = adj_H[aa]; obb[u] = adj_b[aa]; }
+        double hv[U][3], bv[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+#pragma unroll
+            for (int q = 0; q < 3; q++) { int idx = lane + 32 * q; hv[u][q] = (idx < nn) ? B.contrib[oh[u] + idx] : 0.0; }
+            bv[u] = (lane < dim) ? B.contrib[obb[u] + lane] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (a + u < a1) {
+#pragma unroll
+                for (int q = 0; q < 3; q++) acc[q] += hv[u][q];
+                accb += bv[u];
+            }
     }
 #pragma unroll
     for (int q = 0; q < 3; q++) { int idx = lane + 32 * q; if (idx < nn) H[(size_t)v * nn + idx] = acc[q]; }

@@ -31,7 +31,7 @@ int csb_create(csb_context** out, int device_ordinal) {
     c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return CSB_ERR_CUDA; }
     c->own_stream = true;
-    for (int i = 0; i < 5; i++) cudaEventCreate(&c->det.ev[i]);
+    for (int i = 0; i < 6; i++) cudaEventCreate(&c->det.ev[i]);
     *out = c;
     return CSB_OK;
 }
@@ -42,10 +42,10 @@ void csb_destroy(csb_context* c) {
     cudaStreamSynchronize(c->stream);
     DetectState& d = c->det;
     DevBuf* bufs[] = {&d.d_ftab, &d.d_ttab, &d.d_order, &d.d_box_begin, &d.d_lines, &d.d_maps, &d.d_ml_seg, &d.d_ml_ang, &d.d_ml_mid, &d.d_n_merged,
-                      &d.d_p_dist, &d.d_p_angle, &d.d_p_hyp, &d.d_n_valid, &d.d_keep, &d.d_norm, &d.d_n_keep, &d.d_cand_score, &d.d_cand_pos,
-                      &d.d_n_cand, &d.d_sel_idx, &d.d_sel_flag, &d.d_rank_idx, &d.d_cuboids, &d.d_n_cuboids, &d.d_counters, &d.d_dbg};
+                      &d.d_p_dist, &d.d_p_angle, &d.d_p_hyp, &d.d_n_valid, &d.d_keep, &d.d_norm, &d.d_n_keep, &d.d_cand_score, &d.d_cand_ok,
+                      &d.d_sel_idx, &d.d_sel_flag, &d.d_sel_heap, &d.d_rank_idx, &d.d_cuboids, &d.d_n_cuboids, &d.d_counters, &d.d_dbg};
     for (DevBuf* b : bufs) b->release();
-    for (int i = 0; i < 5; i++)
+    for (int i = 0; i < 6; i++)
         if (d.ev[i]) cudaEventDestroy(d.ev[i]);
     ba_release(c->ba);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -150,11 +150,11 @@ int csb_detect_upload(csb_context* c, const csb_frame* frames, int n_frames, con
     CSB_CUDA(c, d.d_norm.ensure(8 * OT));
     CSB_CUDA(c, d.d_n_keep.ensure(4 * NT));
     CSB_CUDA(c, d.d_cand_score.ensure(8 * OT));
-    CSB_CUDA(c, d.d_cand_pos.ensure(4 * OT));
-    CSB_CUDA(c, d.d_n_cand.ensure(4 * NT));
+    CSB_CUDA(c, d.d_cand_ok.ensure(OT));
     CSB_CUDA(c, d.d_sel_idx.ensure(8 * OT));
     CSB_CUDA(c, d.d_sel_flag.ensure(OT));
-    CSB_CUDA(c, d.d_rank_idx.ensure(4 * OT));
+    CSB_CUDA(c, d.d_sel_heap.ensure(16 * OT));
+    CSB_CUDA(c, d.d_rank_idx.ensure(8 * OT));
     CSB_CUDA(c, d.d_cuboids.ensure(sizeof(csb_cuboid) * (size_t)std::max(n_boxes, 1) * kmax));
     CSB_CUDA(c, d.d_n_cuboids.ensure(4 * (size_t)std::max(n_boxes, 1)));
     CSB_CUDA(c, d.d_counters.ensure(64));
@@ -178,8 +178,8 @@ int csb_detect_upload(csb_context* c, const csb_frame* frames, int n_frames, con
     B.ml_seg = d.d_ml_seg.as<double>(); B.ml_ang = d.d_ml_ang.as<double>(); B.ml_mid = d.d_ml_mid.as<double>(); B.n_merged = d.d_n_merged.as<int>();
     B.p_dist = d.d_p_dist.as<double>(); B.p_angle = d.d_p_angle.as<double>(); B.p_hyp = d.d_p_hyp.as<int>(); B.n_valid = d.d_n_valid.as<int>();
     B.keep = d.d_keep.as<int>(); B.norm_score = d.d_norm.as<double>(); B.n_keep = d.d_n_keep.as<int>();
-    B.cand_score = d.d_cand_score.as<double>(); B.cand_keeppos = d.d_cand_pos.as<int>(); B.n_cand = d.d_n_cand.as<int>();
-    B.sel_idx = d.d_sel_idx.as<int>(); B.sel_flag = d.d_sel_flag.as<unsigned char>();
+    B.cand_score = d.d_cand_score.as<double>(); B.cand_ok = d.d_cand_ok.as<unsigned char>();
+    B.sel_idx = d.d_sel_idx.as<int>(); B.sel_flag = d.d_sel_flag.as<unsigned char>(); B.sel_heap = d.d_sel_heap.as<double>();
     B.rank_idx = d.d_rank_idx.as<int>(); B.cuboids = d.d_cuboids.as<csb_cuboid>(); B.n_cuboids = d.d_n_cuboids.as<int>();
     B.counters = d.d_counters.as<int>();
     B.dc.max_cuboid_num = kmax; B.dc.whether_sample_cam_roll_pitch = params->whether_sample_cam_roll_pitch;
@@ -201,19 +201,22 @@ int csb_detect_run(csb_context* c, int timed) {
         if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[0], st));
         CSB_CUDA(c, launch_prep_lines(d.B, d.max_lines_per_frame, st));
         if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[1], st));
-        CSB_CUDA(c, launch_score(d.B, d.max_groups, c->num_sms, c->max_smem_optin, &d.map_cap_floats, st));
+        CSB_CUDA(c, launch_score(d.B, d.max_groups, d.max_hyp_per_task, c->num_sms, c->max_smem_optin, &d.map_cap_floats, st));
         if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[2], st));
-        CSB_CUDA(c, launch_select(d.B, d.max_hyp_per_task, c->max_smem_optin, st));
+        int nsel = 0;
+        CSB_CUDA(c, launch_select(d.B, d.max_hyp_per_task, c->max_smem_optin, st, &nsel));
         if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[3], st));
-        d.launches_last = 3;
+        CSB_CUDA(c, launch_recover(d.B, st));
+        if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[4], st));
+        d.launches_last = 3 + nsel;
     } else if (timed) {
-        for (int i = 0; i < 4; i++) CSB_CUDA(c, cudaEventRecord(d.ev[i], st));
+        for (int i = 0; i < 5; i++) CSB_CUDA(c, cudaEventRecord(d.ev[i], st));
     }
     if (d.n_boxes > 0) {
         CSB_CUDA(c, launch_rank(d.B, d.n_boxes, st));
         d.launches_last++;
     }
-    if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[4], st));
+    if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[5], st));
     d.ran = true;
     return CSB_OK;
 }
@@ -249,7 +252,8 @@ int csb_detect_download(csb_context* c, csb_cuboid* cuboids_out, int32_t* n_cubo
             cudaEventElapsedTime(&stats->gpu_ms_prep, d.ev[0], d.ev[1]);
             cudaEventElapsedTime(&stats->gpu_ms_score, d.ev[1], d.ev[2]);
             cudaEventElapsedTime(&stats->gpu_ms_select, d.ev[2], d.ev[3]);
-            cudaEventElapsedTime(&stats->gpu_ms_rank, d.ev[3], d.ev[4]);
+            cudaEventElapsedTime(&stats->gpu_ms_recover, d.ev[3], d.ev[4]);
+            cudaEventElapsedTime(&stats->gpu_ms_rank, d.ev[4], d.ev[5]);
         }
     }
     return CSB_OK;

@@ -14,7 +14,7 @@
 #include <cstdint>
 
 #include "proposal.h"
-#include "proposal_dev.cuh"
+#include "proposal_score.cuh"
 
 namespace csb {
 
@@ -66,7 +66,7 @@ __device__ __forceinline__ bool merge_pred(const LineSM& L, int a, int b, double
     double msx, msy, mex, mey;
     if (L.x1[a] < L.x1[b]) { msx = L.x1[a]; msy = L.y1[a]; } else { msx = L.x1[b]; msy = L.y1[b]; }
     if (L.x2[a] > L.x2[b]) { mex = L.x2[a]; mey = L.y2[a]; } else { mex = L.x2[b]; mey = L.y2[b]; }
-    double merged_angle = atan2(mey - msy, mex - msx);
+    double merged_angle = det_atan2(mey - msy, mex - msx);
     double temp = fabs(L.ang[a] - merged_angle);
     double merge_angle_diff = cmin(temp, M_PI - temp);
     if (!(merge_angle_diff < thr_ang)) return false;
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(32) k_prep_lines(DetectBuffers B, int cap) {
         if (in) {
             int pos = total + __popc(bal & ((1u << lane) - 1));
             L.x1[pos] = a; L.y1[pos] = b; L.x2[pos] = c; L.y2[pos] = d;
-            L.ang[pos] = atan2(d - b, c - a);
+            L.ang[pos] = det_atan2(d - b, c - a);
         }
         total += __popc(bal);
     }
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(32) k_prep_lines(DetectBuffers B, int cap) {
         if (keep) {
             size_t pos = ob + n_out + __popc(bal & ((1u << lane) - 1));
             B.ml_seg[4 * pos + 0] = L.x1[i]; B.ml_seg[4 * pos + 1] = L.y1[i]; B.ml_seg[4 * pos + 2] = L.x2[i]; B.ml_seg[4 * pos + 3] = L.y2[i];
-            B.ml_ang[pos] = L.ang[i];  // == atan2(y2-y1, x2-x1) of the stored endpoints
+            B.ml_ang[pos] = L.ang[i];  // == det_atan2(y2-y1, x2-x1) of the stored endpoints
             B.ml_mid[2 * pos + 0] = (L.x1[i] + L.x2[i]) / 2;
             B.ml_mid[2 * pos + 1] = (L.y1[i] + L.y2[i]) / 2;
         }
@@ -190,179 +190,105 @@ __global__ void __launch_bounds__(32) k_prep_lines(DetectBuffers B, int cap) {
 // ------------------------------------------------------------------------------------------------
 // k_score
 // ------------------------------------------------------------------------------------------------
-__constant__ double c_t[11] = {0 / 10.0, 1 / 10.0, 2 / 10.0, 3 / 10.0, 4 / 10.0, 5 / 10.0, 6 / 10.0, 7 / 10.0, 8 / 10.0, 9 / 10.0, 10 / 10.0};
-__constant__ double c_1mt[11] = {1 - 0 / 10.0, 1 - 1 / 10.0, 1 - 2 / 10.0, 1 - 3 / 10.0, 1 - 4 / 10.0, 1 - 5 / 10.0,
-                                 1 - 6 / 10.0, 1 - 7 / 10.0, 1 - 8 / 10.0, 1 - 9 / 10.0, 1 - 10 / 10.0};
-
-// 11 samples along one box edge, object_3d_util.cpp:642-664.  WEIGHT: 0 none, 1 x1.5 (edges 4,5 of config 2), 2 x2 (edge 6)
-template <bool SMEM, int WEIGHT>
-__device__ __forceinline__ float edge_samples(float sum_dist, const float* __restrict__ map, int cols, int last, V2 c1, V2 c2) {
-#pragma unroll 1
-    for (int k = 0; k < 11; k++) {
-        double sx = c_t[k] * c1.x + c_1mt[k] * c2.x;
-        double sy = c_t[k] * c1.y + c_1mt[k] * c2.y;
-        int li = __double2int_rz(sy) * cols + __double2int_rz(sx);
-        li = max(0, min(li, last));  // defined behaviour for samples on the ROI's right/bottom bound (reference: UB)
-        float d1 = SMEM ? map[li] : __ldg(map + li);
-        if (WEIGHT == 1) d1 = (float)((double)d1 * 3.0 / 2.0);
-        if (WEIGHT == 2) d1 = (float)((double)d1 * 2.0);
-        sum_dist = sum_dist + d1;
-    }
-    return sum_dist;
-}
-
-// box_edge_sum_dists, object_3d_util.cpp:622-667 with the visible-edge tables of box_proposal_detail.cpp:646, 663
-template <bool SMEM>
-__device__ __forceinline__ double box_edge_sum_dists(const float* __restrict__ map, int rows, int cols, const V2* c, int config_id) {
-    const int last = rows * cols - 1;
-    float s = 0;
-    s = edge_samples<SMEM, 0>(s, map, cols, last, c[0], c[1]);
-    s = edge_samples<SMEM, 0>(s, map, cols, last, c[1], c[2]);
-    s = edge_samples<SMEM, 0>(s, map, cols, last, c[2], c[3]);
-    s = edge_samples<SMEM, 0>(s, map, cols, last, c[3], c[0]);
-    if (config_id == 1) {
-        s = edge_samples<SMEM, 0>(s, map, cols, last, c[1], c[5]);
-        s = edge_samples<SMEM, 0>(s, map, cols, last, c[2], c[4]);
-        s = edge_samples<SMEM, 0>(s, map, cols, last, c[3], c[7]);
-        s = edge_samples<SMEM, 0>(s, map, cols, last, c[4], c[7]);
-        s = edge_samples<SMEM, 0>(s, map, cols, last, c[4], c[5]);
-    } else {
-        s = edge_samples<SMEM, 1>(s, map, cols, last, c[1], c[5]);
-        s = edge_samples<SMEM, 1>(s, map, cols, last, c[2], c[4]);
-        s = edge_samples<SMEM, 2>(s, map, cols, last, c[4], c[5]);
-    }
-    return (double)s;
-}
-
-// one box edge against the (<=2) supporting line angles of its VP, object_3d_util.cpp:696-715
-__device__ __forceinline__ double edge_angle_diff(V2 a, V2 b, double v0, double v1) {
-    double box_edge_angle = normalize_to_pi(atan2(b.y - a.y, b.x - a.x));
-    double angle_diff_temp = 100;
-    if (!isnan(v0)) {
-        double temp = fabs(box_edge_angle - v0);
-        temp = cmin(temp, M_PI - temp);
-        if (temp < angle_diff_temp) angle_diff_temp = temp;
-    }
-    if (!isnan(v1)) {
-        double temp = fabs(box_edge_angle - v1);
-        temp = cmin(temp, M_PI - temp);
-        if (temp < angle_diff_temp) angle_diff_temp = temp;
-    }
-    return angle_diff_temp;
-}
-// box_edge_alignment_angle_error, object_3d_util.cpp:670-723 with the tables of box_proposal_detail.cpp:651, 665
-__device__ __forceinline__ double box_edge_alignment_angle_error(const double* sup /*6*/, const V2* c, int config_id) {
-    const double not_found_penalty = 30.0 / 180.0 * M_PI * 2;
-    double total = 0;
-    // VP 1: edges (1,2) and (8,5) | (3,4)
-    if (!isnan(sup[0]) || !isnan(sup[1])) {
-        total = total + edge_angle_diff(c[0], c[1], sup[0], sup[1]);
-        total = total + (config_id == 1 ? edge_angle_diff(c[7], c[4], sup[0], sup[1]) : edge_angle_diff(c[2], c[3], sup[0], sup[1]));
-    } else
-        total = total + not_found_penalty;
-    // VP 2: edges (4,1) and (5,6)
-    if (!isnan(sup[2]) || !isnan(sup[3])) {
-        total = total + edge_angle_diff(c[3], c[0], sup[2], sup[3]);
-        total = total + edge_angle_diff(c[4], c[5], sup[2], sup[3]);
-    } else
-        total = total + not_found_penalty;
-    // VP 3: edges (4,8)|(3,5) and (2,6)
-    if (!isnan(sup[4]) || !isnan(sup[5])) {
-        total = total + (config_id == 1 ? edge_angle_diff(c[3], c[7], sup[4], sup[5]) : edge_angle_diff(c[2], c[4], sup[4], sup[5]));
-        total = total + edge_angle_diff(c[1], c[5], sup[4], sup[5]);
-    } else
-        total = total + not_found_penalty;
-    return total;
-}
-
-// VP_support_edge_infos (object_3d_util.cpp:548-619) for one group, executed by one warp; lanes stride over lines.
-__device__ __forceinline__ void vp_support_warp(const double* vp, int n, const double* ang, const double* mid, double* sup_out, int lane) {
-    const unsigned FULL = 0xffffffffu;
-    for (int vp_id = 0; vp_id < 3; vp_id++) {
-        const double thr = (vp_id != 2 ? 15.0 : 10.0) / 180.0 * M_PI;
-        const double vx = vp[2 * vp_id], vy = vp[2 * vp_id + 1];
-        bool have_base = false;
-        double base = 0;
-        // lane-local extrema of the smoothed inlier angles; ties keep the lowest line index (Eigen max/minCoeff)
-        double vmax = 0, vmin = 0;
-        int imax = -1, imin = -1;
-        for (int b0 = 0; b0 < n; b0 += 32) {
-            int e = b0 + lane;
-            bool inl = false;
-            double raw = 0;
-            if (e < n) {
-                raw = atan2(mid[2 * e + 1] - vy, mid[2 * e] - vx);
-                double nrm = normalize_to_pi(raw);
-                double d = fabs(ang[e] - nrm);
-                d = cmin(d, M_PI - d);
-                inl = d < thr;
-            }
-            unsigned bal = __ballot_sync(FULL, inl);
-            if (!have_base && bal) {
-                base = __shfl_sync(FULL, raw, __ffs(bal) - 1);  // smooth_jump_angles: base = first inlier (:285)
-                have_base = true;
-            }
-            if (inl) {
-                double v = raw;
-                if ((raw - base) < -M_PI) v = raw + 2 * M_PI;
-                else if ((raw - base) > M_PI) v = raw - 2 * M_PI;
-                if (imax < 0) { vmax = vmin = v; imax = imin = e; }
-                else {
-                    if (v > vmax) { vmax = v; imax = e; }
-                    if (v < vmin) { vmin = v; imin = e; }
-                }
-            }
-        }
-        // warp reduction, first index wins on ties
-        for (int off = 16; off > 0; off >>= 1) {
-            double ov = __shfl_down_sync(FULL, vmax, off); int oi = __shfl_down_sync(FULL, imax, off);
-            if (oi >= 0 && (imax < 0 || ov > vmax || (ov == vmax && oi < imax))) { vmax = ov; imax = oi; }
-            ov = __shfl_down_sync(FULL, vmin, off); oi = __shfl_down_sync(FULL, imin, off);
-            if (oi >= 0 && (imin < 0 || ov < vmin || (ov == vmin && oi < imin))) { vmin = ov; imin = oi; }
-        }
-        imax = __shfl_sync(FULL, imax, 0);
-        imin = __shfl_sync(FULL, imin, 0);
-        if (lane == 0) {
-            if (imax >= 0) {
-                int low = imax, top = imin;
-                if (vp_id > 0) { int t = low; low = top; top = t; }
-                sup_out[2 * vp_id] = ang[low];
-                sup_out[2 * vp_id + 1] = ang[top];
-            } else {
-                sup_out[2 * vp_id] = nan("");
-                sup_out[2 * vp_id + 1] = nan("");
-            }
-        }
-    }
-}
-
 constexpr int SCORE_THREADS = 512;
 constexpr int LINE_SMEM_CAP = 256;
+constexpr int SUBW = 8;  // lanes per VP-support unit
 
-struct ScoreSmemLayout {
-    int groups_cap;    // groups with tables in shared memory
-    int map_cap_floats;
-    size_t total_bytes;
-};
+// VP_support_edge_infos (object_3d_util.cpp:548-619) for one (vanishing point, line table) unit, executed by an 8-lane
+// sub-group; all 32 lanes of the warp run this in lock step (ballots / shuffles are warp-wide), `active` masks units that
+// do not exist.  Returns the two supporting line angles (NaN if none) on every lane of the sub-group.
+__device__ __forceinline__ void vp_support_unit(bool active, double vx, double vy, double thr, int n, const double* ang, const double* mid, int lane, int swap_lt,
+                                                double& out_low, double& out_top) {
+    const unsigned FULL = 0xffffffffu;
+    const int sl = lane & (SUBW - 1), sbase = lane & ~(SUBW - 1), sshift = sbase;
+    bool have_base = false;
+    double base = 0;
+    // lane-local extrema of the smoothed inlier angles; ties keep the lowest line index (Eigen max/minCoeff: first wins)
+    double vmax = 0, vmin = 0;
+    int imax = -1, imin = -1;
+    for (int b0 = 0; b0 < n; b0 += SUBW) {
+        const int e = b0 + sl;
+        bool inl = false;
+        double raw = 0;
+        if (active && e < n) {
+            raw = det_atan2(mid[2 * e + 1] - vy, mid[2 * e] - vx);
+            double nrm = normalize_to_pi(raw);
+            double d = fabs(ang[e] - nrm);
+            d = cmin(d, M_PI - d);
+            inl = d < thr;
+        }
+        const unsigned sub = (__ballot_sync(FULL, inl) >> sshift) & ((1u << SUBW) - 1);
+        const double cand = __shfl_sync(FULL, raw, sbase + (sub ? (__ffs(sub) - 1) : 0));
+        if (!have_base && sub) { base = cand; have_base = true; }  // smooth_jump_angles: base = first inlier (:285)
+        if (inl) {
+            double v = raw;
+            if ((raw - base) < -M_PI) v = raw + 2 * M_PI;
+            else if ((raw - base) > M_PI) v = raw - 2 * M_PI;
+            if (imax < 0) { vmax = vmin = v; imax = imin = e; }
+            else {
+                if (v > vmax) { vmax = v; imax = e; }
+                if (v < vmin) { vmin = v; imin = e; }
+            }
+        }
+    }
+#pragma unroll
+    for (int off = SUBW / 2; off > 0; off >>= 1) {
+        double ov = __shfl_xor_sync(FULL, vmax, off); int oi = __shfl_xor_sync(FULL, imax, off);
+        if (oi >= 0 && (imax < 0 || ov > vmax || (ov == vmax && oi < imax))) { vmax = ov; imax = oi; }
+        ov = __shfl_xor_sync(FULL, vmin, off); oi = __shfl_xor_sync(FULL, imin, off);
+        if (oi >= 0 && (imin < 0 || ov < vmin || (ov == vmin && oi < imin))) { vmin = ov; imin = oi; }
+    }
+    if (imax >= 0) {
+        int low = imax, top = imin;
+        if (swap_lt) { int t = low; low = top; top = t; }  // "match matlab code" (:609-610)
+        out_low = ang[low];
+        out_top = ang[top];
+    } else {
+        out_low = nan("");
+        out_top = nan("");
+    }
+}
+
+// block-wide exclusive scan of one int per thread; s_w holds one slot per warp
+template <int THREADS>
+__device__ __forceinline__ int block_excl_scan(int v, int* s_w, int tid, int& total) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = tid & 31, warp = tid >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    int pre = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; w++) { int c = s_w[w]; if (w < warp) pre += c; tot += c; }
+    __syncthreads();
+    total = tot;
+    return pre + inc - v;
+}
 
 // Persistent CTA: loops over tasks handed out by an atomic counter (largest first).
-__global__ void __launch_bounds__(SCORE_THREADS, 1) k_score(DetectBuffers B, int groups_cap, int map_cap_floats) {
+//   (a) TMA bulk copy of the task's distance map into shared memory (lands while (b)-(d) run)
+//   (b) merged-line tables -> shared memory
+//   (c) vanishing points per (roll,pitch,yaw) group; VP-support angles by 8-lane units: (group, vp1), (group, vp2), (pair, vp3)
+//   (d) phase 1: every hypothesis through the corner construction / rejection cascade -> validity bitmask (enumeration order)
+//   (e) prefix sums over the bitmask words: proposal i of the compacted list <-> hypothesis id
+//   (f) phase 2: one thread per surviving proposal (all lanes busy): corners again, 99/77 distance-map gathers, edge-angle error
+__global__ void __launch_bounds__(SCORE_THREADS, 1) k_score(DetectBuffers B, int groups_cap, int map_cap_floats, int words_cap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // layout: [map floats][vp tables 6*G][support tables 6*G][line ang][line mid][queue 2T][warp counts][misc]
     float* s_map = reinterpret_cast<float*>(smem_raw);
     double* s_vp = reinterpret_cast<double*>(smem_raw + (size_t)map_cap_floats * 4);
     double* s_sup = s_vp + 6 * (size_t)groups_cap;
     double* s_lang = s_sup + 6 * (size_t)groups_cap;
     double* s_lmid = s_lang + LINE_SMEM_CAP;
-    int* s_queue = reinterpret_cast<int*>(s_lmid + 2 * LINE_SMEM_CAP);
-    int* s_wcnt = s_queue + 2 * SCORE_THREADS;
+    unsigned* s_mask = reinterpret_cast<unsigned*>(s_lmid + 2 * LINE_SMEM_CAP);
+    int* s_wpre = reinterpret_cast<int*>(s_mask + words_cap);  // words_cap + 1 entries
     __shared__ uint64_t s_bar;
     __shared__ int s_task;
+    __shared__ int s_w[SCORE_THREADS / 32];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const unsigned FULL = 0xffffffffu;
-    constexpr int NW = SCORE_THREADS / 32;
-    constexpr int QCAP = 2 * SCORE_THREADS;
 
     if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
     __syncthreads();
@@ -377,104 +303,122 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) k_score(DetectBuffers B, int
         const TaskTab tt = B.ttab[task];
         const FrameTab& ft = B.ftab[tt.frame_id];
         const TaskGeo geo = make_geo(tt);
-        const int n_groups = ft.n_roll * ft.n_pitch * ft.n_yaw;
+        const int n_yaw = ft.n_yaw, n_pairs = ft.n_roll * ft.n_pitch;
+        const int n_groups = n_pairs * n_yaw;
         const int n_lines = B.n_merged[task];
         const int map_floats = tt.roi_w * tt.roi_h;
         const bool map_smem = map_floats <= map_cap_floats;
         const float* gmap = B.maps + tt.map_offset;
 
-        // (a) kick off the TMA bulk copy of the distance map; it lands while the VP tables are built
+        // (a)
         if (map_smem && tid == 0) {
             uint32_t bytes = ((uint32_t)map_floats * 4u + 15u) & ~15u;
             fence_proxy_async();  // previous task's generic reads of s_map are ordered before the async write
             mbar_expect_tx(&s_bar, bytes);
             tma_bulk_g2s(s_map, gmap, bytes, &s_bar);
         }
-        // (b) merged-line tables -> shared memory
+        // (b)
         const double* lang = B.ml_ang + tt.line_cap_offset;
         const double* lmid = B.ml_mid + 2 * (size_t)tt.line_cap_offset;
-        const bool lines_smem = n_lines <= LINE_SMEM_CAP;
-        if (lines_smem) {
+        if (n_lines <= LINE_SMEM_CAP) {
             for (int i = tid; i < n_lines; i += SCORE_THREADS) { s_lang[i] = lang[i]; s_lmid[2 * i] = lmid[2 * i]; s_lmid[2 * i + 1] = lmid[2 * i + 1]; }
+            lang = s_lang; lmid = s_lmid;
         }
-        __syncthreads();
-        // (c) per-group vanishing points and VP-support angles: one warp per group
-        for (int g = warp; g < n_groups; g += NW) {
-            int yaw_id = g % ft.n_yaw, pair = g / ft.n_yaw;
+        // (c) vanishing points
+        for (int g = tid; g < n_groups; g += SCORE_THREADS) {
+            int yaw_id = g % n_yaw, pair = g / n_yaw;
             double vp[6];
             vanishing_points(ft.KinvR[pair], ft.cosy[yaw_id], ft.siny[yaw_id], vp);
-            if (lane == 0) { for (int q = 0; q < 6; q++) s_vp[6 * g + q] = vp[q]; }
-            if (n_lines > 0) vp_support_warp(vp, n_lines, lines_smem ? s_lang : lang, lines_smem ? s_lmid : lmid, s_sup + 6 * g, lane);
-            else if (lane < 6) s_sup[6 * g + lane] = nan("");
+#pragma unroll
+            for (int q = 0; q < 6; q++) s_vp[6 * g + q] = vp[q];
+        }
+        __syncthreads();
+        {
+            const int n_units = 2 * n_groups + n_pairs;
+            constexpr int SUBS = SCORE_THREADS / SUBW;
+            const int sg = tid / SUBW, sl = tid & (SUBW - 1);
+            for (int u0 = 0; u0 < n_units; u0 += SUBS) {
+                const int u = u0 + sg;
+                const bool active = u < n_units;
+                int g = 0, vp_id = 0, pair = 0;
+                if (active) {
+                    if (u < 2 * n_groups) { g = u >> 1; vp_id = u & 1; }
+                    else { pair = u - 2 * n_groups; g = pair * n_yaw; vp_id = 2; }
+                }
+                const double vx = s_vp[6 * g + 2 * vp_id], vy = s_vp[6 * g + 2 * vp_id + 1];
+                const double thr = (vp_id != 2 ? 15.0 : 10.0) / 180.0 * M_PI;
+                double lo, tp;
+                vp_support_unit(active, vx, vy, thr, n_lines, lang, lmid, lane, vp_id > 0, lo, tp);
+                if (active) {
+                    if (vp_id < 2) { if (sl == 0) { s_sup[6 * g + 2 * vp_id] = lo; s_sup[6 * g + 2 * vp_id + 1] = tp; } }
+                    else for (int y = sl; y < n_yaw; y += SUBW) { s_sup[6 * (g + y) + 4] = lo; s_sup[6 * (g + y) + 5] = tp; }  // vp3 is shared by the pair's yaw samples
+                }
+            }
         }
         __syncthreads();
 
-        // (d) sweep.  Phase 1: every thread tests one hypothesis (corner construction + rejection cascade); survivors'
-        // ids are appended to a ring buffer in enumeration order.  Phase 2: whenever a full block's worth is queued
-        // (or at the end), each thread scores one survivor with all lanes active.
-        int q_head = 0, q_count = 0, n_done = 0;
-        bool map_ready = !map_smem;
+        // (d) phase 1 -> validity bitmask
         const int n_hyp = tt.n_hyp;
-        for (int base = 0; base < n_hyp || q_count > 0;) {
-            if (base < n_hyp) {
-                int h = base + tid;
-                bool valid = false;
-                if (h < n_hyp) {
-                    int group, top, cfg;
-                    decode_hyp(h, tt.n_top, group, top, cfg);
-                    if (tt.cfg_mask & cfg) {  // cfg 1 -> bit0, cfg 2 -> bit1
-                        V2 c[8];
-                        valid = construct_corners(geo, s_vp + 6 * group, (double)(tt.top_x0 + top * tt.top_step), cfg, c) > 0;
-                    }
-                }
-                unsigned bal = __ballot_sync(FULL, valid);
-                if (lane == 0) s_wcnt[warp] = __popc(bal);
-                __syncthreads();
-                int pre = 0, tot = 0;
-#pragma unroll
-                for (int w = 0; w < NW; w++) { int cw = s_wcnt[w]; if (w < warp) pre += cw; tot += cw; }
-                if (valid) s_queue[(q_head + q_count + pre + __popc(bal & ((1u << lane) - 1))) % QCAP] = h;
-                q_count += tot;
-                base += SCORE_THREADS;
-                __syncthreads();
-            }
-            const bool flush = (base >= n_hyp);
-            if (q_count >= SCORE_THREADS || (flush && q_count > 0)) {
-                if (!map_ready) { mbar_wait(&s_bar, bar_parity); bar_parity ^= 1; map_ready = true; }
-                const int m = min(q_count, SCORE_THREADS);
-                if (tid < m) {
-                    int h = s_queue[(q_head + tid) % QCAP];
-                    int group, top, cfg;
-                    decode_hyp(h, tt.n_top, group, top, cfg);
+        const int n_words = (n_hyp + 31) >> 5;
+        for (int base = 0; base < n_hyp; base += SCORE_THREADS) {
+            const int h = base + tid;
+            bool valid = false;
+            if (h < n_hyp) {
+                int group, top, cfg;
+                decode_hyp(h, tt.n_top, group, top, cfg);
+                if (tt.cfg_mask & cfg) {  // cfg 1 -> bit0, cfg 2 -> bit1
                     V2 c[8];
-                    construct_corners(geo, s_vp + 6 * group, (double)(tt.top_x0 + top * tt.top_step), cfg, c);
-                    double total_angle_diff = box_edge_alignment_angle_error(s_sup + 6 * group, c, cfg);
-                    V2 cs[8];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) cs[i] = V2{c[i].x - geo.roi_l, c[i].y - geo.roi_t};
-                    double sum_dist = map_smem ? box_edge_sum_dists<true>(s_map, tt.roi_h, tt.roi_w, cs, cfg)
-                                               : box_edge_sum_dists<false>(gmap, tt.roi_h, tt.roi_w, cs, cfg);
-                    size_t o = (size_t)tt.out_offset + n_done + tid;
-                    B.p_dist[o] = sum_dist / tt.diag;
-                    B.p_angle[o] = total_angle_diff;
-                    B.p_hyp[o] = h;
+                    valid = construct_corners(geo, s_vp + 6 * group, (double)(tt.top_x0 + top * tt.top_step), cfg, c) > 0;
                 }
-                q_head = (q_head + m) % QCAP;
-                q_count -= m;
-                n_done += m;
-                __syncthreads();
             }
+            const unsigned bal = __ballot_sync(FULL, valid);
+            if (lane == 0 && (h >> 5) < n_words) s_mask[h >> 5] = bal;
         }
-        if (!map_ready) { mbar_wait(&s_bar, bar_parity); bar_parity ^= 1; }  // drain the copy before the buffer is reused
-        if (tid == 0) B.n_valid[task] = n_done;
+        __syncthreads();
+        // (e) exclusive prefix of the word popcounts
+        int n_valid = 0;
+        for (int w0 = 0; w0 < n_words; w0 += SCORE_THREADS) {
+            const int w = w0 + tid;
+            const int v = (w < n_words) ? __popc(s_mask[w]) : 0;
+            int tot;
+            const int pre = block_excl_scan<SCORE_THREADS>(v, s_w, tid, tot);
+            if (w < n_words) s_wpre[w] = n_valid + pre;
+            n_valid += tot;
+        }
+        __syncthreads();
+        // (f) phase 2
+        if (map_smem) { mbar_wait(&s_bar, bar_parity); bar_parity ^= 1; }
+        for (int i = tid; i < n_valid; i += SCORE_THREADS) {
+            // word containing the i-th set bit: last w with s_wpre[w] <= i
+            int lo = 0, hi = n_words - 1;
+            while (lo < hi) {
+                int mid = (lo + hi + 1) >> 1;
+                if (s_wpre[mid] <= i) lo = mid; else hi = mid - 1;
+            }
+            const int h = (lo << 5) + (int)__fns(s_mask[lo], 0, i - s_wpre[lo] + 1);
+            int group, top, cfg;
+            decode_hyp(h, tt.n_top, group, top, cfg);
+            V2 c[8];
+            construct_corners(geo, s_vp + 6 * group, (double)(tt.top_x0 + top * tt.top_step), cfg, c);
+            const double total_angle_diff = box_edge_alignment_angle_error(s_sup + 6 * group, c, cfg);
+            V2 cs[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) cs[q] = V2{c[q].x - geo.roi_l, c[q].y - geo.roi_t};
+            const double sum_dist = map_smem ? box_edge_sum_dists<true>(s_map, tt.roi_h, tt.roi_w, cs, cfg) : box_edge_sum_dists<false>(gmap, tt.roi_h, tt.roi_w, cs, cfg);
+            const size_t o = (size_t)tt.out_offset + i;
+            B.p_dist[o] = sum_dist / tt.diag;
+            B.p_angle[o] = total_angle_diff;
+            B.p_hyp[o] = h;
+        }
+        if (tid == 0) B.n_valid[task] = n_valid;
         __syncthreads();
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_select
+// k_select : fuse_normalize_scores_v2 (object_3d_util.cpp:726-837), one CTA per task
 // ------------------------------------------------------------------------------------------------
-constexpr int SELECT_THREADS = 256;
+constexpr int SELECT_THREADS = 128;
 
 // bitonic sort of idx[0..npad) by key[idx] ascending, ties by index; idx < 0 are +inf pads
 __device__ __forceinline__ bool key_less(const double* key, int a, int b) {
@@ -483,7 +427,7 @@ __device__ __forceinline__ bool key_less(const double* key, int a, int b) {
     double ka = key[a], kb = key[b];
     return (ka < kb) || (ka == kb && a < b);
 }
-__device__ void bitonic_sort_idx(int* idx, int npad, const double* key, int tid, int nthreads) {
+__device__ __forceinline__ void bitonic_sort_idx(int* idx, int npad, const double* key, int tid, int nthreads) {
     for (int k = 2; k <= npad; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = tid; i < npad; i += nthreads) {
@@ -500,77 +444,54 @@ __device__ void bitonic_sort_idx(int* idx, int npad, const double* key, int tid,
     }
 }
 
-// block-wide exclusive scan of one int per thread (SELECT_THREADS threads); returns prefix, total via smem
-__device__ __forceinline__ int block_excl_scan(int v, int* s_w, int tid, int& total) {
-    const unsigned FULL = 0xffffffffu;
-    int lane = tid & 31, warp = tid >> 5;
-    int inc = v;
-    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) s_w[warp] = inc;
-    __syncthreads();
-    int pre = 0, tot = 0;
-    for (int w = 0; w < SELECT_THREADS / 32; w++) { int c = s_w[w]; if (w < warp) pre += c; tot += c; }
-    __syncthreads();
-    total = tot;
-    return pre + inc - v;
-}
+struct HeapEl {
+    double v;
+    int i, pad;
+};
 
-// Recompute corners + 3D object for proposal (task tt, hypothesis h).  Returns vp_1_position.
-__device__ __forceinline__ int recover_object(const TaskTab& tt, const FrameTab& ft, int h, V2* c, Obj3D& o, int& cfg, int& group) {
-    int top;
-    decode_hyp(h, tt.n_top, group, top, cfg);
-    int yaw_id = group % ft.n_yaw, pair = group / ft.n_yaw;
-    double vp[6];
-    vanishing_points(ft.KinvR[pair], ft.cosy[yaw_id], ft.siny[yaw_id], vp);
-    TaskGeo geo = make_geo(tt);
-    int vp1 = construct_corners(geo, vp, (double)(tt.top_x0 + top * tt.top_step), cfg, c);
-    corners_to_3d(c, ft.Tnew[pair], ft.invK, o);
-    return vp1;
-}
-
-__global__ void __launch_bounds__(SELECT_THREADS) k_select(DetectBuffers B, int n_cap /* smem capacity in proposals */) {
+// Tasks with n_lo < N <= n_hi are handled by this launch (two launches: a small-footprint variant for the common case and a
+// large one).  Working arrays live in shared memory when N <= n_cap, else in the task's global scratch.
+__global__ void __launch_bounds__(SELECT_THREADS) k_select(DetectBuffers B, int n_lo, int n_hi, int n_cap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_w[SELECT_THREADS / 32];
     __shared__ double s_red[4 * (SELECT_THREADS / 32)];
     const int task = blockIdx.x, tid = threadIdx.x;
-    const TaskTab tt = B.ttab[task];
-    const FrameTab& ft = B.ftab[tt.frame_id];
     const int N = B.n_valid[task];
+    if (N <= n_lo || N > n_hi) return;
+    const TaskTab tt = B.ttab[task];
     const size_t ob = (size_t)tt.out_offset;
-    if (N == 0) {
-        if (tid == 0) { B.n_keep[task] = 0; B.n_cand[task] = 0; }
-        return;
-    }
     int npad = 1;
     while (npad < N) npad <<= 1;
-    // working arrays: shared memory when the task fits, else the task's global scratch slots
+    // layout: vd[n_cap] | va[n_cap] | idx[cap_pad] | flag[n_cap];   the heap of (value,index) pairs later aliases va|idx
     double *vd, *va;
     int* idx;
     unsigned char* flag;
+    HeapEl* heap;
     if (N <= n_cap) {
+        int cap_pad = 1; while (cap_pad < n_cap) cap_pad <<= 1;
         vd = reinterpret_cast<double*>(smem_raw);
         va = vd + n_cap;
         idx = reinterpret_cast<int*>(va + n_cap);
-        int cap_pad = 1; while (cap_pad < n_cap) cap_pad <<= 1;
         flag = reinterpret_cast<unsigned char*>(idx + cap_pad);
+        heap = reinterpret_cast<HeapEl*>(va);  // 16 B * k <= 16 * (2N/3 + 1) <= 8 N + 4 npad  for N >= 3
         for (int i = tid; i < N; i += SELECT_THREADS) { vd[i] = B.p_dist[ob + i]; va[i] = B.p_angle[ob + i]; }
     } else {
         vd = B.p_dist + ob; va = B.p_angle + ob;
         idx = B.sel_idx + 2 * ob;  // 2x slots: room for the power-of-two padding (npad < 2N)
         flag = B.sel_flag + ob;
+        heap = reinterpret_cast<HeapEl*>(B.sel_heap + 2 * ob);
     }
     __syncthreads();
 
     int* keep = B.keep + ob;
     int n_keep = 0;
     if (N > 4) {
-        // fuse_normalize_scores_v2, object_3d_util.cpp:736-787
-        const int k = (int)round((double)(float)N / 3.0 * 2.0);  // breaking_num
-        // angle list: only order statistics k-1, k-2 and (if there is a strict gap) the k-1 smallest as a set
+        const int k = (int)round((double)(float)N / 3.0 * 2.0);  // breaking_num (:739)
+        // angle list: only the order statistics k-1, k-2 and (if there is a strict gap) the k-1 smallest as a set
         for (int i = tid; i < npad; i += SELECT_THREADS) idx[i] = (i < N) ? i : -1;
         __syncthreads();
         bitonic_sort_idx(idx, npad, va, tid, SELECT_THREADS);
-        const bool angle_active = va[idx[k - 1]] > va[idx[k - 2]];
+        const bool angle_active = va[idx[k - 1]] > va[idx[k - 2]];  // (:766)
         for (int i = tid; i < N; i += SELECT_THREADS) flag[i] = 0;
         __syncthreads();
         if (angle_active)
@@ -581,63 +502,75 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(DetectBuffers B, int 
         __syncthreads();
         bitonic_sort_idx(idx, npad, vd, tid, SELECT_THREADS);
         const double vk = vd[idx[k - 1]];
-        // does the unstable partial_sort matter?  (a) several elements equal the k-th smallest value -> membership / which
-        // one is dropped depends on the heap; (b) with the angle filter off the kept list keeps partial_sort's ORDER, so any
-        // tie inside the first k positions matters too.
+        // Does the unstable std::partial_sort matter?  (a) several elements equal the k-th smallest value: which of them stay
+        // (and which one is the dropped k-th) depends on the heap; (b) with the angle filter off the kept list keeps
+        // partial_sort's ORDER, so any tie inside the first k positions matters too.
         int local = 0;
         for (int i = tid; i < N; i += SELECT_THREADS) local += (vd[i] == vk) ? 1 : 0;
         int mult;
-        block_excl_scan(local, s_w, tid, mult);
+        block_excl_scan<SELECT_THREADS>(local, s_w, tid, mult);
         int local2 = 0;
         if (!angle_active)
             for (int p = tid; p < k - 1; p += SELECT_THREADS) local2 += (vd[idx[p]] == vd[idx[p + 1]]) ? 1 : 0;
         int inner_ties;
-        block_excl_scan(local2, s_w, tid, inner_ties);
+        block_excl_scan<SELECT_THREADS>(local2, s_w, tid, inner_ties);
         const bool need_emul = (mult > 1) || (!angle_active && inner_ties > 0);
-        if (need_emul) {
-            // literal std::partial_sort on the iota vector (matrix_utils.cpp:327-335), one thread
-            for (int i = tid; i < N; i += SELECT_THREADS) idx[i] = i;
+        if (!need_emul) {
+            if (angle_active) { for (int p = tid; p < k - 1; p += SELECT_THREADS) flag[idx[p]] |= 2; }
+            else { for (int p = tid; p < k - 1; p += SELECT_THREADS) keep[p] = idx[p]; }
+            __syncthreads();
+        } else {
+            // literal std::partial_sort(iota, iota + k, end) (matrix_utils.cpp:327-335) with the heap carrying (value, index)
+            // pairs; va / idx are dead by now and provide the storage
+            __syncthreads();
+            for (int i = tid; i < k; i += SELECT_THREADS) { heap[i].v = vd[i]; heap[i].i = i; }
             __syncthreads();
             if (tid == 0) {
-                auto less = [vd](int a, int b) { return vd[a] < vd[b]; };
-                heap_select(idx, k, N, less);
-                if (!angle_active) heap_sort(idx, k, less);
+                auto less = [](const HeapEl& a, const HeapEl& b) { return a.v < b.v; };
+                heap_make(heap, k, less);
+                for (int i = k; i < N; i++) {
+                    const double vi = vd[i];
+                    if (vi < heap[0].v) {  // __pop_heap(first, middle, i): the evicted top goes to slot i (never read again)
+                        HeapEl value{vi, i, 0};
+                        heap_adjust(heap, 0, k, value, less);
+                    }
+                }
+                if (!angle_active) heap_sort(heap, k, less);
             }
+            __syncthreads();
+            // after __heap_select the k-th (excluded) element is the heap top, heap[0]; after __sort_heap it is heap[k-1]
+            if (angle_active) { for (int p = tid + 1; p < k; p += SELECT_THREADS) flag[heap[p].i] |= 2; }
+            else { for (int p = tid; p < k - 1; p += SELECT_THREADS) keep[p] = heap[p].i; }
             __syncthreads();
         }
         if (angle_active) {
-            // dist_keep = sorted[0..k-1) as a SET (after heap_select the excluded k-th element sits at the heap top, idx[0])
-            if (need_emul) { for (int p = tid + 1; p < k; p += SELECT_THREADS) flag[idx[p]] |= 2; }
-            else { for (int p = tid; p < k - 1; p += SELECT_THREADS) flag[idx[p]] |= 2; }
-            __syncthreads();
-            // std::set_intersection of the two index-sorted sets == ascending indices with both flags
+            // std::set_intersection of the two index-sorted sets == ascending indices carrying both flags (:773-781)
             for (int b0 = 0; b0 < N; b0 += SELECT_THREADS) {
                 int i = b0 + tid;
                 int v = (i < N && flag[i] == 3) ? 1 : 0;
                 int tot;
-                int pre = block_excl_scan(v, s_w, tid, tot);
+                int pre = block_excl_scan<SELECT_THREADS>(v, s_w, tid, tot);
                 if (v) keep[n_keep + pre] = i;
                 n_keep += tot;
             }
-        } else {
-            // final_keep_inds = dist_keep_inds in partial_sort order (:783-786)
-            n_keep = k - 1;
-            for (int p = tid; p < n_keep; p += SELECT_THREADS) keep[p] = idx[p];
-        }
+        } else
+            n_keep = k - 1;  // final_keep_inds = dist_keep_inds in partial_sort order (:783-786)
     } else {
         n_keep = N;
         for (int p = tid; p < N; p += SELECT_THREADS) keep[p] = p;
     }
     __syncthreads();
 
-    // min / max of the kept errors (:798-817) and combined score (:820-836)
+    // min / max of the kept errors (:798-817) and combined score (:820-836); angle values re-read from global (va may be clobbered)
+    const double* ga = B.p_angle + ob;
     double mn_d = 1e300, mx_d = -1e300, mn_a = 1e300, mx_a = -1e300;
     for (int j = tid; j < n_keep; j += SELECT_THREADS) {
-        double d = vd[keep[j]], a = va[keep[j]];
+        double d = vd[keep[j]], a = ga[keep[j]];
         mn_d = cmin(mn_d, d); mx_d = cmax(mx_d, d); mn_a = cmin(mn_a, a); mx_a = cmax(mx_a, a);
     }
     {
         const unsigned FULL = 0xffffffffu;
+#pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             mn_d = cmin(mn_d, __shfl_xor_sync(FULL, mn_d, o)); mx_d = cmax(mx_d, __shfl_xor_sync(FULL, mx_d, o));
             mn_a = cmin(mn_a, __shfl_xor_sync(FULL, mn_a, o)); mx_a = cmax(mx_a, __shfl_xor_sync(FULL, mx_a, o));
@@ -653,7 +586,7 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(DetectBuffers B, int 
     const double w_ang = 0.8;
     double* norm_score = B.norm_score + ob;
     for (int j = tid; j < n_keep; j += SELECT_THREADS) {
-        double d = vd[keep[j]], a = va[keep[j]];
+        double d = vd[keep[j]], a = ga[keep[j]];
         double comb;
         if (n_keep > 1) {
             comb = (d - mn_d) / (mx_d - mn_d);
@@ -665,97 +598,131 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(DetectBuffers B, int 
         norm_score[j] = comb;
     }
     if (tid == 0) B.n_keep[task] = n_keep;
-    __syncthreads();
+}
 
-    // 3D recovery of the kept proposals + skew-augmented score (box_proposal_detail.cpp:723-822); candidates keep list order
-    const double weight_skew_error = 1.5;
-    int n_cand = 0;
-    for (int b0 = 0; b0 < n_keep; b0 += SELECT_THREADS) {
-        int j = b0 + tid;
-        int ok = 0;
-        double score = 0;
-        if (j < n_keep) {
-            int h = B.p_hyp[ob + keep[j]];
-            V2 c[8];
-            Obj3D o;
-            int cfg, group;
-            recover_object(tt, ft, h, c, o, cfg, group);
-            if (!((o.scale[0] < 0) || (o.scale[1] < 0) || (o.scale[2] < 0))) {
-                ok = 1;
-                double skew_ratio = cmax(o.scale[0], o.scale[1]) / cmin(o.scale[0], o.scale[1]);
-                double skew_error = weight_skew_error * cmax(skew_ratio - B.dc.nominal_skew_ratio, 0.0);
-                if (skew_ratio > B.dc.max_cut_skew) skew_error = 100;
-                score = norm_score[j] + weight_skew_error * skew_error;
-            }
-        }
-        int tot;
-        int pre = block_excl_scan(ok, s_w, tid, tot);
-        if (ok) { B.cand_score[ob + n_cand + pre] = score; B.cand_keeppos[ob + n_cand + pre] = j; }
-        n_cand += tot;
-    }
-    if (tid == 0) B.n_cand[task] = n_cand;
+// zero-proposal tasks never enter k_select
+__global__ void k_select_init(DetectBuffers B) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < B.n_tasks) B.n_keep[t] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_rank : one warp per 2D box
+// k_recover : 3D recovery of every kept proposal + skew-augmented score (box_proposal_detail.cpp:723-822)
+// ------------------------------------------------------------------------------------------------
+// Recompute corners + 3D object for proposal (task tt, hypothesis h).  Returns vp_1_position.
+__device__ __forceinline__ int recover_object(const TaskTab& tt, const FrameTab& ft, int h, V2* c, Obj3D& o, int& cfg, int& group) {
+    int top;
+    decode_hyp(h, tt.n_top, group, top, cfg);
+    int yaw_id = group % ft.n_yaw, pair = group / ft.n_yaw;
+    double vp[6];
+    vanishing_points(ft.KinvR[pair], ft.cosy[yaw_id], ft.siny[yaw_id], vp);
+    TaskGeo geo = make_geo(tt);
+    int vp1 = construct_corners(geo, vp, (double)(tt.top_x0 + top * tt.top_step), cfg, c);
+    corners_to_3d(c, ft.Tnew[pair], ft.invK, o);
+    return vp1;
+}
+
+constexpr int RECOVER_THREADS = 128;
+// grid (n_tasks, RECOVER_Y): blocks of a task stride over its kept list.  cand_score[j] / cand_ok[j] are indexed by the
+// position j in the kept list (raw_obj_proposals = the ok ones, in list order).
+__global__ void __launch_bounds__(RECOVER_THREADS) k_recover(DetectBuffers B) {
+    const int task = blockIdx.x;
+    const int n_keep = B.n_keep[task];
+    const int j0 = blockIdx.y * RECOVER_THREADS + threadIdx.x;
+    if (j0 >= n_keep) return;
+    const TaskTab tt = B.ttab[task];
+    const FrameTab& ft = B.ftab[tt.frame_id];
+    const size_t ob = (size_t)tt.out_offset;
+    const double weight_skew_error = 1.5;
+    for (int j = j0; j < n_keep; j += gridDim.y * RECOVER_THREADS) {
+        int h = B.p_hyp[ob + B.keep[ob + j]];
+        V2 c[8];
+        Obj3D o;
+        int cfg, group;
+        recover_object(tt, ft, h, c, o, cfg, group);
+        unsigned char ok = 0;
+        double score = 0;
+        if (!((o.scale[0] < 0) || (o.scale[1] < 0) || (o.scale[2] < 0))) {  // (:766)
+            ok = 1;
+            double skew_ratio = cmax(o.scale[0], o.scale[1]) / cmin(o.scale[0], o.scale[1]);
+            double skew_error = weight_skew_error * cmax(skew_ratio - B.dc.nominal_skew_ratio, 0.0);
+            if (skew_ratio > B.dc.max_cut_skew) skew_error = 100;
+            score = B.norm_score[ob + j] + weight_skew_error * skew_error;  // (:813-820)
+        }
+        B.cand_score[ob + j] = score;
+        B.cand_ok[ob + j] = ok;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_rank : final ranking per 2D box (box_proposal_detail.cpp:804-838), one warp per box
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) k_rank(DetectBuffers B) {
     const int box = blockIdx.x, lane = threadIdx.x;
     const unsigned FULL = 0xffffffffu;
     const int t0 = B.box_task_begin[box], t1 = B.box_task_begin[box + 1];
-    int M = 0;
-    for (int t = t0; t < t1; t++) M += B.n_cand[t];
     const int kmax = B.dc.max_cuboid_num;
+    // candidates of the box = kept proposals with ok flag, in (task, kept position) order; "slot" = position in the
+    // concatenated kept lists, "rank index" = position among the ok ones (index into raw_obj_proposals)
+    int S = 0;
+    for (int t = t0; t < t1; t++) S += B.n_keep[t];
+    auto locate = [&](int slot, int& t, int& j) {
+        t = t0;
+        while (slot >= B.n_keep[t]) { slot -= B.n_keep[t]; t++; }
+        j = slot;
+    };
+    int* ridx = (t1 > t0) ? B.rank_idx + (size_t)B.ttab[t0].out_offset : nullptr;  // scratch: >= S slots
+    // compact the ok slots (ordered) and count them
+    int M = 0;
+    for (int s0 = 0; s0 < S; s0 += 32) {
+        int s = s0 + lane;
+        bool ok = false;
+        if (s < S) { int t, j; locate(s, t, j); ok = B.cand_ok[(size_t)B.ttab[t].out_offset + j] != 0; }
+        unsigned bal = __ballot_sync(FULL, ok);
+        if (ok) ridx[M + __popc(bal & ((1u << lane) - 1))] = s;
+        M += __popc(bal);
+    }
+    __syncwarp();
     const int k = min(kmax, M);
     if (lane == 0) B.n_cuboids[box] = k;
     if (k == 0) return;
-    // candidate r of the box -> (task, position in that task's candidate list); tasks of a box are contiguous
-    auto locate = [&](int r, int& t, int& c) {
-        t = t0;
-        while (r >= B.n_cand[t]) { r -= B.n_cand[t]; t++; }
-        c = r;
-    };
-    auto score_of = [&](int r) {
-        int t, c;
-        locate(r, t, c);
-        return B.cand_score[(size_t)B.ttab[t].out_offset + c];
-    };
-    int* ridx = B.rank_idx + (size_t)B.ttab[t0].out_offset;  // scratch: >= M slots
+    auto score_of_slot = [&](int s) { int t, j; locate(s, t, j); return B.cand_score[(size_t)B.ttab[t].out_offset + j]; };
+    // winners[w] = rank index (position in ridx) of the w-th best
+    int* win = ridx + M;  // scratch behind the compacted list (capacity n_hyp >= 2 * S)
     if (k == 1) {
         // partial_sort(idx, idx+1, end): start with element 0, replace by every later strictly smaller one.  That is the first
         // index of the minimum over the non-NaN scores -- unless score[0] is NaN, which nothing can replace.
         double best = 0; int bi = -1;
         for (int r = lane; r < M; r += 32) {
-            double s = score_of(r);
-            if (s == s && (bi < 0 || s < best)) { best = s; bi = r; }
+            double sc = score_of_slot(ridx[r]);
+            if (sc == sc && (bi < 0 || sc < best)) { best = sc; bi = r; }
         }
         for (int o = 16; o > 0; o >>= 1) {
             double ov = __shfl_down_sync(FULL, best, o); int oi = __shfl_down_sync(FULL, bi, o);
             if (oi >= 0 && (bi < 0 || ov < best || (ov == best && oi < bi))) { best = ov; bi = oi; }
         }
         bi = __shfl_sync(FULL, bi, 0);
-        double s0 = score_of(0);
-        if (s0 != s0 || bi < 0) bi = 0;
-        if (lane == 0) ridx[0] = bi;
+        double s0v = score_of_slot(ridx[0]);
+        if (s0v != s0v || bi < 0) bi = 0;
+        if (lane == 0) win[0] = bi;
     } else {
-        for (int r = lane; r < M; r += 32) ridx[r] = r;
+        for (int r = lane; r < M; r += 32) win[r] = r;
         __syncwarp();
         if (lane == 0) {
-            auto less = [&](int a, int b) { return score_of(a) < score_of(b); };
-            heap_select(ridx, k, M, less);
-            heap_sort(ridx, k, less);
+            auto less = [&](int a, int b) { return score_of_slot(ridx[a]) < score_of_slot(ridx[b]); };
+            heap_select(win, k, M, less);
+            heap_sort(win, k, less);
         }
     }
     __syncwarp();
     // write the k cuboid records (lanes over winners)
     for (int w = lane; w < k; w += 32) {
-        int r = ridx[w];
-        int t, c;
-        locate(r, t, c);
+        const int r = win[w];
+        int t, j;
+        locate(ridx[r], t, j);
         const TaskTab tt = B.ttab[t];
         const FrameTab& ft = B.ftab[tt.frame_id];
         const size_t ob = (size_t)tt.out_offset;
-        int j = B.cand_keeppos[ob + c];
         int vidx = B.keep[ob + j];
         int h = B.p_hyp[ob + vidx];
         V2 cr[8];
@@ -829,8 +796,8 @@ __global__ void k_debug_corners(DetectBuffers B, int task, double* out) {
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-static size_t score_smem_bytes(int groups_cap, int map_cap_floats) {
-    return (size_t)map_cap_floats * 4 + (size_t)groups_cap * 12 * 8 + (size_t)LINE_SMEM_CAP * 3 * 8 + (size_t)(2 * SCORE_THREADS + SCORE_THREADS / 32) * 4 + 64;
+static size_t score_smem_bytes(int groups_cap, int map_cap_floats, int words_cap) {
+    return (size_t)map_cap_floats * 4 + (size_t)groups_cap * 12 * 8 + (size_t)LINE_SMEM_CAP * 3 * 8 + (size_t)(2 * words_cap + 1) * 4 + 64;
 }
 
 cudaError_t launch_prep_lines(const DetectBuffers& B, int max_lines_per_frame, cudaStream_t st) {
@@ -843,32 +810,51 @@ cudaError_t launch_prep_lines(const DetectBuffers& B, int max_lines_per_frame, c
     return cudaGetLastError();
 }
 
-cudaError_t launch_score(const DetectBuffers& B, int max_groups, int num_sms, int max_smem_optin, int* map_cap_floats_out, cudaStream_t st) {
-    int groups_cap = max_groups;
-    size_t fixed = score_smem_bytes(groups_cap, 0);
+cudaError_t launch_score(const DetectBuffers& B, int max_groups, int max_hyp_per_task, int num_sms, int max_smem_optin, int* map_cap_floats_out, cudaStream_t st) {
+    const int groups_cap = max_groups;
+    const int words_cap = (max_hyp_per_task + 31) / 32 + 1;
+    size_t fixed = score_smem_bytes(groups_cap, 0, words_cap);
     size_t budget = (size_t)max_smem_optin - 1024;  // static __shared__ + slack
     if (fixed + 16 * 1024 > budget) return cudaErrorInvalidValue;
     int map_cap = (int)((budget - fixed) / 4) & ~31;
-    size_t smem = score_smem_bytes(groups_cap, map_cap);
+    size_t smem = score_smem_bytes(groups_cap, map_cap, words_cap);
     cudaError_t e = cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (map_cap_floats_out) *map_cap_floats_out = map_cap;
     int grid = B.n_tasks < num_sms ? B.n_tasks : num_sms;
-    k_score<<<grid, SCORE_THREADS, smem, st>>>(B, groups_cap, map_cap);
+    k_score<<<grid, SCORE_THREADS, smem, st>>>(B, groups_cap, map_cap, words_cap);
     return cudaGetLastError();
 }
 
-cudaError_t launch_select(const DetectBuffers& B, int max_hyp_per_task, int max_smem_optin, cudaStream_t st) {
-    // per proposal: 2 doubles + idx (power-of-two padded: <= 2 ints) + 1 flag byte
-    int n_cap = max_hyp_per_task;
-    auto bytes = [](int n) { int p = 1; while (p < n) p <<= 1; return (size_t)n * 16 + (size_t)p * 4 + (size_t)n + 16; };
-    size_t budget = (size_t)max_smem_optin - 4096;
-    if (n_cap > 8192) n_cap = 8192;
-    while (bytes(n_cap) > budget) n_cap -= 256;
-    size_t smem = bytes(n_cap);
-    cudaError_t e = cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+// per proposal: 2 doubles + idx (power-of-two padded ints) + 1 flag byte
+static size_t select_smem_bytes(int n) {
+    int p = 1;
+    while (p < n) p <<= 1;
+    return (size_t)n * 16 + (size_t)p * 4 + (size_t)n + 16;
+}
+
+cudaError_t launch_select(const DetectBuffers& B, int max_hyp_per_task, int max_smem_optin, cudaStream_t st, int* n_launches) {
+    k_select_init<<<(B.n_tasks + 255) / 256, 256, 0, st>>>(B);
+    int L = 1;
+    // small-footprint variant: tasks with up to 2048 valid proposals (several CTAs per SM)
+    const int small_cap = 2048;
+    cudaError_t e = cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin - 2048);
     if (e != cudaSuccess) return e;
-    k_select<<<B.n_tasks, SELECT_THREADS, smem, st>>>(B, n_cap);
+    k_select<<<B.n_tasks, SELECT_THREADS, select_smem_bytes(small_cap), st>>>(B, 0, small_cap, small_cap);
+    L++;
+    if (max_hyp_per_task > small_cap) {
+        int big_cap = max_hyp_per_task > 8192 ? 8192 : max_hyp_per_task;
+        while (select_smem_bytes(big_cap) > (size_t)max_smem_optin - 4096) big_cap -= 256;
+        k_select<<<B.n_tasks, SELECT_THREADS, select_smem_bytes(big_cap), st>>>(B, small_cap, 0x7fffffff, big_cap);
+        L++;
+    }
+    if (n_launches) *n_launches = L;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_recover(const DetectBuffers& B, cudaStream_t st) {
+    dim3 grid(B.n_tasks, 8);
+    k_recover<<<grid, RECOVER_THREADS, 0, st>>>(B);
     return cudaGetLastError();
 }
 

@@ -31,13 +31,14 @@ struct DetectBuffers {
     int* keep;
     double* norm_score;
     int* n_keep;
+    // k_recover outputs (indexed by position in the kept list)
     double* cand_score;
-    int* cand_keeppos;
-    int* n_cand;
+    unsigned char* cand_ok;
     int* sel_idx;             // 2x capacity, global fallback for very large tasks
     unsigned char* sel_flag;
+    double* sel_heap;         // 2 doubles per slot (value,index pairs), global fallback
     // k_rank
-    int* rank_idx;
+    int* rank_idx;            // 2x capacity
     csb_cuboid* cuboids;
     int* n_cuboids;
     int* counters;  // [0]: k_score task queue head
@@ -45,8 +46,9 @@ struct DetectBuffers {
 };
 
 cudaError_t launch_prep_lines(const DetectBuffers& B, int max_lines_per_frame, cudaStream_t st);
-cudaError_t launch_score(const DetectBuffers& B, int max_groups, int num_sms, int max_smem_optin, int* map_cap_floats_out, cudaStream_t st);
-cudaError_t launch_select(const DetectBuffers& B, int max_hyp_per_task, int max_smem_optin, cudaStream_t st);
+cudaError_t launch_score(const DetectBuffers& B, int max_groups, int max_hyp_per_task, int num_sms, int max_smem_optin, int* map_cap_floats_out, cudaStream_t st);
+cudaError_t launch_select(const DetectBuffers& B, int max_hyp_per_task, int max_smem_optin, cudaStream_t st, int* n_launches);
+cudaError_t launch_recover(const DetectBuffers& B, cudaStream_t st);
 cudaError_t launch_rank(const DetectBuffers& B, int n_boxes, cudaStream_t st);
 cudaError_t launch_debug_corners(const DetectBuffers& B, int task, int n_valid, double* out, cudaStream_t st);
 

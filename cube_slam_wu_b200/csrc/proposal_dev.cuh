@@ -175,8 +175,9 @@ __device__ __forceinline__ void corners_to_3d(const V2* c, const double* T, cons
 // ---- libstdc++ heap algorithms, restated (bits/stl_heap.h, bits/stl_algo.h __heap_select/__partial_sort) ----
 // The reference ranks with std::partial_sort (matrix_utils.cpp:327-335), which is not stable: which of several
 // equal keys ends up inside the kept prefix depends on these exact sift sequences, so they are reproduced literally.
-template <class Less>
-__device__ void heap_adjust(int* first, int holeIndex, int len, int value, Less less) {
+// Generic over the element type so that the heap can carry (value, index) pairs.
+template <class T, class Less>
+__device__ __forceinline__ void heap_adjust(T* first, int holeIndex, int len, T value, Less less) {
     const int topIndex = holeIndex;
     int secondChild = holeIndex;
     while (secondChild < (len - 1) / 2) {
@@ -199,20 +200,31 @@ __device__ void heap_adjust(int* first, int holeIndex, int len, int value, Less 
     }
     first[holeIndex] = value;
 }
-template <class Less>
-__device__ void heap_make(int* first, int len, Less less) {
+template <class T, class Less>
+__device__ __forceinline__ void heap_make(T* first, int len, Less less) {
     if (len < 2) return;
     int parent = (len - 2) / 2;
     while (true) {
-        int value = first[parent];
+        T value = first[parent];
         heap_adjust(first, parent, len, value, less);
         if (parent == 0) return;
         parent--;
     }
 }
-// __heap_select(first, first+k, first+n)
+// __sort_heap(first, first+k)
+template <class T, class Less>
+__device__ __forceinline__ void heap_sort(T* first, int k, Less less) {
+    int last = k;
+    while (last > 1) {
+        --last;
+        T value = first[last];
+        first[last] = first[0];
+        heap_adjust(first, 0, last, value, less);
+    }
+}
+// __heap_select(first, first+k, first+n) for an index array (elements beyond k live in the same array)
 template <class Less>
-__device__ void heap_select(int* first, int k, int n, Less less) {
+__device__ __forceinline__ void heap_select(int* first, int k, int n, Less less) {
     heap_make(first, k, less);
     for (int i = k; i < n; i++)
         if (less(first[i], first[0])) {  // __pop_heap(first, middle, i)
@@ -220,17 +232,6 @@ __device__ void heap_select(int* first, int k, int n, Less less) {
             first[i] = first[0];
             heap_adjust(first, 0, k, value, less);
         }
-}
-// __sort_heap(first, first+k)
-template <class Less>
-__device__ void heap_sort(int* first, int k, Less less) {
-    int last = k;
-    while (last > 1) {
-        --last;
-        int value = first[last];
-        first[last] = first[0];
-        heap_adjust(first, 0, last, value, less);
-    }
 }
 
 }  // namespace csb

@@ -106,7 +106,7 @@ typedef struct csb_detect_stats {
     int64_t n_kept;       /* proposals that survived fuse_normalize_scores_v2 */
     int64_t h2d_bytes, d2h_bytes;
     int32_t n_kernel_launches, n_tasks_smem_map; /* tasks whose distance map was staged in shared memory */
-    float gpu_ms_prep, gpu_ms_score, gpu_ms_select, gpu_ms_rank; /* CUDA-event times of the last run (0 if not timed) */
+    float gpu_ms_prep, gpu_ms_score, gpu_ms_select, gpu_ms_recover, gpu_ms_rank, reserved_f; /* CUDA-event times of the last timed run */
 } csb_detect_stats;
 
 /* Host-only integer logic of box_proposal_detail.cpp:143-256: enumerates tasks and ROI rectangles.

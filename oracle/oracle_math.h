@@ -195,4 +195,85 @@ static inline double normalize_to_pi(double angle) {
     else return angle;
 }
 
+
+// ---- deterministic atan2 -----------------------------------------------------------------------------------------
+// The reference calls libm's atan2 (object_3d_util.cpp:273,490,573,702; box_proposal_detail.cpp:313).  libm results are
+// not reproducible across implementations (glibc vs CUDA differ in the last ulp), and the proposal ranking contains
+// structural near-ties (object yaw samples 90 degrees apart describe the same cuboid with vp1/vp2 swapped), so a 1-ulp
+// difference flips ranking indices.  Both the oracle and the device path therefore evaluate atan2 with the same
+// specified algorithm: the classic argument-reduction + degree-11 odd polynomial scheme of Sun's fdlibm (s_atan.c /
+// e_atan2.c, error < 1 ulp), written with plain IEEE-754 double operations only, so that it is bit-reproducible anywhere
+// FMA contraction is off.  tests/test_oracle_golden.py checks it against glibc's atan2 to <= 1 ulp.
+
+static inline double det_atan(double x, unsigned hx_bits) {
+    const double atanhi[4] = {4.63647609000806093515e-01, 7.85398163397448278999e-01, 9.82793723247329054082e-01, 1.57079632679489655800e+00};
+    const double atanlo[4] = {2.26987774529616870924e-17, 3.06161699786838301793e-17, 1.39033110312309984516e-17, 6.12323399573676603587e-17};
+    const double aT[11] = {3.33333333333329318027e-01, -1.99999999998764832476e-01, 1.42857142725034663711e-01, -1.11111104054623557880e-01,
+                           9.09088713343650656196e-02, -7.69187620504482999495e-02, 6.66107313738753120669e-02, -5.83357013379057348645e-02,
+                           4.97687799461593236017e-02, -3.65315727442169155270e-02, 1.62858201153657823623e-02};
+    // x >= 0 here (called with |y/x|); hx_bits = high word of x
+    const unsigned ix = hx_bits & 0x7fffffffu;
+    int id;
+    if (ix >= 0x44100000u) {  // |x| >= 2^66 (or inf/nan: callers filter those)
+        return atanhi[3] + atanlo[3];
+    }
+    if (ix < 0x3fdc0000u) {  // |x| < 0.4375
+        if (ix < 0x3e200000u) return x;  // |x| < 2^-29
+        id = -1;
+    } else if (ix < 0x3ff30000u) {  // |x| < 1.1875
+        if (ix < 0x3fe60000u) { id = 0; x = (2.0 * x - 1.0) / (2.0 + x); }  // 7/16 <= |x| < 11/16
+        else { id = 1; x = (x - 1.0) / (x + 1.0); }                          // 11/16 <= |x| < 19/16
+    } else if (ix < 0x40038000u) { id = 2; x = (x - 1.5) / (1.0 + 1.5 * x); }  // |x| < 2.4375
+    else { id = 3; x = -1.0 / x; }
+    double z = x * x;
+    double w = z * z;
+    double s1 = z * (aT[0] + w * (aT[2] + w * (aT[4] + w * (aT[6] + w * (aT[8] + w * aT[10])))));
+    double s2 = w * (aT[1] + w * (aT[3] + w * (aT[5] + w * (aT[7] + w * aT[9]))));
+    if (id < 0) return x - x * (s1 + s2);
+    return atanhi[id] - ((x * (s1 + s2) - atanlo[id]) - x);
+}
+
+static inline double det_atan2(double y, double x) {
+    const double tiny = 1.0e-300, pi_o_4 = 7.8539816339744827900E-01, pi_o_2 = 1.5707963267948965580E+00, pi = 3.1415926535897931160E+00,
+                 pi_lo = 1.2246467991473531772E-16;
+    if (x != x || y != y) return x + y;
+    unsigned hx, lx, hy, ly;
+    { unsigned long long ux, uy; std::memcpy(&ux, &x, 8); std::memcpy(&uy, &y, 8); hx = (unsigned)(ux >> 32); lx = (unsigned)ux; hy = (unsigned)(uy >> 32); ly = (unsigned)uy; }
+    const unsigned ix = hx & 0x7fffffffu, iy = hy & 0x7fffffffu;
+    const int m = (int)((hy >> 31) & 1u) | (int)((hx >> 30) & 2u);  // 2*sign(x) + sign(y)
+    if ((iy | ly) == 0) {  // y = 0
+        if (m == 0 || m == 1) return y;
+        return (m == 2) ? pi + tiny : -pi - tiny;
+    }
+    if ((ix | lx) == 0) return (hy >> 31) ? -pi_o_2 - tiny : pi_o_2 + tiny;  // x = 0
+    if (ix == 0x7ff00000u) {  // x = inf
+        if (iy == 0x7ff00000u) {
+            if (m == 0) return pi_o_4 + tiny;
+            if (m == 1) return -pi_o_4 - tiny;
+            if (m == 2) return 3.0 * pi_o_4 + tiny;
+            return -3.0 * pi_o_4 - tiny;
+        }
+        if (m == 0) return 0.0;
+        if (m == 1) return -0.0;
+        if (m == 2) return pi + tiny;
+        return -pi - tiny;
+    }
+    if (iy == 0x7ff00000u) return (hy >> 31) ? -pi_o_2 - tiny : pi_o_2 + tiny;  // y = inf
+    const int k = ((int)iy - (int)ix) >> 20;
+    double z;
+    if (k > 60) z = pi_o_2 + 0.5 * pi_lo;            // |y/x| > 2^60
+    else if ((hx >> 31) && k < -60) z = 0.0;          // |y|/x < -2^60
+    else {
+        double q = fabs(y / x);
+        unsigned hq, lq;
+        { unsigned long long uq; std::memcpy(&uq, &q, 8); hq = (unsigned)(uq >> 32); lq = (unsigned)uq; }
+        (void)lq;
+        z = det_atan(q, hq);
+    }
+    if (m == 0) return z;
+    if (m == 1) return -z;
+    if (m == 2) return pi - (z - pi_lo);
+    return (z - pi_lo) - pi;
+}
+
 }  // namespace orc

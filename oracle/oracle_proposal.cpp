@@ -35,6 +35,8 @@ struct orc_params {
     int max_cuboid_num;
     int leak_cam_state;  // 1: literal reference (cam_pose member leaks across boxes); 0: boxes independent
     double nominal_skew_ratio, max_cut_skew;
+    int libm_atan2;      // 1: std::atan2 like the reference; 0 (default): the specified det_atan2 (oracle_math.h) the GPU path also uses
+    int reserved;
 };
 struct orc_cuboid {  // mirror of class cuboid, detect_3d_cuboid.h:20-41
     double pos[3], scale[3], rotY;
@@ -55,6 +57,10 @@ struct orc_task {
 }
 
 namespace {
+
+// atan2 used on the scored path (see oracle_math.h "deterministic atan2"); set once per call from orc_params::libm_atan2
+bool g_libm_atan2 = false;
+inline double sp_atan2(double y, double x) { return g_libm_atan2 ? std::atan2(y, x) : det_atan2(y, x); }
 
 // detect_3d_cuboid.h:59-71
 struct CamPose {
@@ -149,7 +155,7 @@ void merge_break_lines(const std::vector<Line>& all_lines, std::vector<Line>& ou
     while (can_force_merge && (counter < 500)) {
         counter++;
         can_force_merge = false;
-        for (int i = 0; i < total; i++) ang[i] = std::atan2(L[i].y2 - L[i].y1, L[i].x2 - L[i].x1);
+        for (int i = 0; i < total; i++) ang[i] = sp_atan2(L[i].y2 - L[i].y1, L[i].x2 - L[i].x1);
         for (int seg1 = 0; seg1 < total - 1; seg1++) {
             for (int seg2 = seg1 + 1; seg2 < total; seg2++) {
                 double diff = std::abs(ang[seg1] - ang[seg2]);
@@ -163,7 +169,7 @@ void merge_break_lines(const std::vector<Line>& all_lines, std::vector<Line>& ou
                         else ms = {L[seg2].x1, L[seg2].y1};
                         if (L[seg1].x2 > L[seg2].x2) me = {L[seg1].x2, L[seg1].y2};
                         else me = {L[seg2].x2, L[seg2].y2};
-                        double merged_angle = std::atan2(me.y - ms.y, me.x - ms.x);
+                        double merged_angle = sp_atan2(me.y - ms.y, me.x - ms.x);
                         double temp = std::abs(ang[seg1] - merged_angle);
                         double merge_angle_diff = std::min(temp, M_PI - temp);
                         if (merge_angle_diff < pre_merge_angle_thre) {
@@ -202,7 +208,7 @@ void VP_support_edge_infos(const V2 VPs[3], const std::vector<V2>& mid, const st
         double vp_angle_thre = (vp_id != 2 ? thre12_deg : thre3_deg) / 180.0 * M_PI;
         int cnt = 0;
         for (int e = 0; e < n; e++) {
-            double raw = std::atan2(mid[e].y - VPs[vp_id].y, mid[e].x - VPs[vp_id].x);
+            double raw = sp_atan2(mid[e].y - VPs[vp_id].y, mid[e].x - VPs[vp_id].x);
             double nrm = normalize_to_pi(raw);
             double d = std::abs(edge_angles[e] - nrm);
             d = std::min(d, M_PI - d);
@@ -273,7 +279,7 @@ double box_edge_alignment_angle_error(const double vp_bound[6], const int (*vpe)
         if (nv > 0) {
             for (int ee = 0; ee < 2; ee++) {
                 V2 a = c[vpe[vp][2 * ee]], b = c[vpe[vp][2 * ee + 1]];
-                double box_edge_angle = normalize_to_pi(std::atan2(b.y - a.y, b.x - a.x));
+                double box_edge_angle = normalize_to_pi(sp_atan2(b.y - a.y, b.x - a.x));
                 double angle_diff_temp = 100;
                 for (int i = 0; i < nv; i++) {
                     double temp = std::abs(box_edge_angle - valid[i]);
@@ -574,7 +580,7 @@ void detect_cuboid(const double* Kin, const double* Tin, int img_width, int img_
             std::vector<V2> edge_mid_pts(nl);
             for (int i = 0; i < nl; i++) {
                 const Line& l = TR.merged[i];
-                lines_inobj_angles[i] = std::atan2(l.y2 - l.y1, l.x2 - l.x1);
+                lines_inobj_angles[i] = sp_atan2(l.y2 - l.y1, l.x2 - l.x1);
                 edge_mid_pts[i] = {(l.x1 + l.x2) / 2, (l.y1 + l.y2) / 2};
             }
 
@@ -760,6 +766,7 @@ int orc_plan(const double* boxes, int n_boxes, int img_w, int img_h, int sample_
 void* orc_detect_frame(const double* K, const double* T, int img_w, int img_h, const double* boxes, int n_boxes, const double* lines, int n_lines,
                        const float* dist_maps, const orc_params* P) {
     FrameResult* R = new FrameResult();
+    g_libm_atan2 = P->libm_atan2 != 0;
     detect_cuboid(K, T, img_w, img_h, boxes, n_boxes, lines, n_lines, dist_maps, *P, *R);
     return R;
 }
@@ -799,6 +806,7 @@ void orc_box_data(void* h, int b, orc_cuboid* raw, double* combined, int* sorted
 long long orc_detect_batch(int n_frames, const double* K, const double* T, int img_w, int img_h, const double* boxes, const int* box_off,
                            const double* lines, const int* line_off, const float* dist_maps, const long long* map_off, const orc_params* P,
                            int n_threads, orc_cuboid* best, long long* n_enum_out) {
+    g_libm_atan2 = P->libm_atan2 != 0;
     std::vector<long long> scored(n_frames, 0), enumd(n_frames, 0);
     auto work = [&](int tid) {
         for (int f = tid; f < n_frames; f += n_threads) {
@@ -828,6 +836,7 @@ long long orc_detect_batch(int n_frames, const double* K, const double* T, int i
 }
 
 // KAT hooks (tests/test_oracle_golden.py)
+double orc_det_atan2(double y, double x) { return det_atan2(y, x); }
 void orc_kat_ray_plane(const double* rays3xn, int n, const double* plane4, double* out3xn) {
     for (int i = 0; i < n; i++) {
         double rx = rays3xn[i], ry = rays3xn[n + i], rz = rays3xn[2 * n + i];

@@ -20,10 +20,10 @@ def demo_batch():
                 images=None, img_w=img_w, img_h=img_h, demo_map=d["dist_map"], demo_roi=d["roi"])
 
 
-def oracle_params(p, leak):
+def oracle_params(p, leak, libm=0):
     return O.default_params(consider_config_1=p.consider_config_1, consider_config_2=p.consider_config_2,
                             whether_sample_cam_roll_pitch=p.whether_sample_cam_roll_pitch, whether_sample_bbox_height=p.whether_sample_bbox_height,
-                            max_cuboid_num=p.max_cuboid_num, leak_cam_state=leak, nominal_skew_ratio=p.nominal_skew_ratio, max_cut_skew=p.max_cut_skew)
+                            max_cuboid_num=p.max_cuboid_num, leak_cam_state=leak, libm_atan2=libm, nominal_skew_ratio=p.nominal_skew_ratio, max_cut_skew=p.max_cut_skew)
 
 
 def maps_for(batch, f, rois, offsets, total):
@@ -42,7 +42,7 @@ def maps_for(batch, f, rois, offsets, total):
     return buf
 
 
-def run_oracle(batch, params, leak=0):
+def run_oracle(batch, params, leak=0, libm=0):
     """One oracle detect_cuboid() per frame.  Returns list of FrameResult."""
     res = []
     sample_h = bool(params.whether_sample_bbox_height)
@@ -55,7 +55,7 @@ def run_oracle(batch, params, leak=0):
         offs = [t.map_offset for t in tasks]
         total = sum(w * h for (_, _, w, h) in rois)
         maps = maps_for(batch, f, rois, offs, total)
-        res.append(O.detect_frame(batch["K"][f], batch["T"][f], batch["img_w"], batch["img_h"], boxes, batch["lines"][l0:l1], maps, oracle_params(params, leak)))
+        res.append(O.detect_frame(batch["K"][f], batch["T"][f], batch["img_w"], batch["img_h"], boxes, batch["lines"][l0:l1], maps, oracle_params(params, leak, libm)))
     return res
 
 

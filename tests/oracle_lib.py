@@ -18,7 +18,7 @@ class Params(C.Structure):
     _fields_ = [("consider_config_1", C.c_int), ("consider_config_2", C.c_int),
                 ("whether_sample_cam_roll_pitch", C.c_int), ("whether_sample_bbox_height", C.c_int),
                 ("max_cuboid_num", C.c_int), ("leak_cam_state", C.c_int),
-                ("nominal_skew_ratio", C.c_double), ("max_cut_skew", C.c_double)]
+                ("nominal_skew_ratio", C.c_double), ("max_cut_skew", C.c_double), ("libm_atan2", C.c_int), ("reserved", C.c_int)]
 
 
 class Task(C.Structure):
@@ -62,6 +62,8 @@ def lib():
         L.orc_num_enum.restype = C.c_longlong
         L.orc_detect_batch.restype = C.c_longlong
         L.orc_ba_linearize.restype = C.c_double
+        L.orc_det_atan2.restype = C.c_double
+        L.orc_det_atan2.argtypes = [C.c_double, C.c_double]
         _LIB = L
     return _LIB
 
@@ -71,7 +73,7 @@ def _p(a):
 
 
 def default_params(**kw):
-    p = Params(1, 1, 1, 0, 1, 1, 1.0, 3.0)
+    p = Params(1, 1, 1, 0, 1, 1, 1.0, 3.0, 0, 0)
     for k, v in kw.items():
         setattr(p, k, v)
     return p

@@ -20,7 +20,7 @@ def _compare(gpu, ora, tol_rel=2e-5):
     for k in ("ec_err", "ep_err", "eo_err"):
         if gpu[k].size:
             d = np.abs(gpu[k] - ora[k]).max()
-            assert d <= 1e-9, "%s differs by %g" % (k, d)
+            assert d <= 1e-9 * max(1.0, np.abs(ora[k]).max()), "%s differs by %g" % (k, d)
     for k in ("ec_Ji", "ec_Jj", "ep_Ji", "ep_Jj", "eo_Ji", "eo_Jj", "H_cam", "b_cam", "H_cube", "b_cube", "ec_Hij", "ep_Hij", "eo_Hij"):
         if gpu[k].size:
             scale = max(1.0, np.abs(ora[k]).max())
