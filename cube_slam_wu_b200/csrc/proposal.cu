@@ -444,11 +444,6 @@ __device__ __forceinline__ void bitonic_sort_idx(int* idx, int npad, const doubl
     }
 }
 
-struct HeapEl {
-    double v;
-    int i, pad;
-};
-
 // Tasks with n_lo < N <= n_hi are handled by this launch (two launches: a small-footprint variant for the common case and a
 // large one).  Working arrays live in shared memory when N <= n_cap, else in the task's global scratch.
 __global__ void __launch_bounds__(SELECT_THREADS) k_select(DetectBuffers B, int n_lo, int n_hi, int n_cap) {
@@ -462,24 +457,25 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(DetectBuffers B, int 
     const size_t ob = (size_t)tt.out_offset;
     int npad = 1;
     while (npad < N) npad <<= 1;
-    // layout: vd[n_cap] | va[n_cap] | idx[cap_pad] | flag[n_cap];   the heap of (value,index) pairs later aliases va|idx
+    // layout: vd[n_cap] | va[n_cap] | idx[cap_pad] | flag[n_cap];   the emulation heap later aliases va (values) and idx
+    // (indices + larger-child table): k <= 2N/3 + 1, so 8k <= 8N and 4k + 4(k/2) <= 4N
     double *vd, *va;
     int* idx;
     unsigned char* flag;
-    HeapEl* heap;
+    WarpHeap heap;
     if (N <= n_cap) {
         int cap_pad = 1; while (cap_pad < n_cap) cap_pad <<= 1;
         vd = reinterpret_cast<double*>(smem_raw);
         va = vd + n_cap;
         idx = reinterpret_cast<int*>(va + n_cap);
         flag = reinterpret_cast<unsigned char*>(idx + cap_pad);
-        heap = reinterpret_cast<HeapEl*>(va);  // 16 B * k <= 16 * (2N/3 + 1) <= 8 N + 4 npad  for N >= 3
+        heap.hv = va; heap.hi = idx; heap.big = nullptr;  // big = hi + k, set once k is known (k + (k-1)/2 <= N ints)
         for (int i = tid; i < N; i += SELECT_THREADS) { vd[i] = B.p_dist[ob + i]; va[i] = B.p_angle[ob + i]; }
     } else {
         vd = B.p_dist + ob; va = B.p_angle + ob;
         idx = B.sel_idx + 2 * ob;  // 2x slots: room for the power-of-two padding (npad < 2N)
         flag = B.sel_flag + ob;
-        heap = reinterpret_cast<HeapEl*>(B.sel_heap + 2 * ob);
+        heap.hv = B.sel_heap + 2 * ob; heap.hi = reinterpret_cast<int*>(B.sel_heap + 2 * ob + N); heap.big = nullptr;
     }
     __syncthreads();
 
@@ -502,45 +498,34 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(DetectBuffers B, int 
         __syncthreads();
         bitonic_sort_idx(idx, npad, vd, tid, SELECT_THREADS);
         const double vk = vd[idx[k - 1]];
-        // Does the unstable std::partial_sort matter?  (a) several elements equal the k-th smallest value: which of them stay
-        // (and which one is the dropped k-th) depends on the heap; (b) with the angle filter off the kept list keeps
-        // partial_sort's ORDER, so any tie inside the first k positions matters too.
-        int local = 0;
-        for (int i = tid; i < N; i += SELECT_THREADS) local += (vd[i] == vk) ? 1 : 0;
-        int mult;
-        block_excl_scan<SELECT_THREADS>(local, s_w, tid, mult);
-        int local2 = 0;
-        if (!angle_active)
+        // Does the unstable std::partial_sort matter?  With the angle filter on, dist_keep is used as a SET = heap minus its
+        // top after __heap_select.  If only one element of the k-th smallest value vk is inside the heap it is the top (the
+        // dropped k-th) and the set is exactly the k-1 elements below vk; otherwise (position k-2 also equals vk) which of the
+        // tied elements stay depends on the heap.  With the angle filter off the kept list keeps partial_sort's ORDER, so any
+        // tie inside the first k sorted positions matters.
+        bool need_emul;
+        if (angle_active) need_emul = (vd[idx[k - 2]] == vk);
+        else {
+            int local2 = 0;
             for (int p = tid; p < k - 1; p += SELECT_THREADS) local2 += (vd[idx[p]] == vd[idx[p + 1]]) ? 1 : 0;
-        int inner_ties;
-        block_excl_scan<SELECT_THREADS>(local2, s_w, tid, inner_ties);
-        const bool need_emul = (mult > 1) || (!angle_active && inner_ties > 0);
+            int inner_ties;
+            block_excl_scan<SELECT_THREADS>(local2, s_w, tid, inner_ties);
+            need_emul = inner_ties > 0;
+        }
         if (!need_emul) {
             if (angle_active) { for (int p = tid; p < k - 1; p += SELECT_THREADS) flag[idx[p]] |= 2; }
             else { for (int p = tid; p < k - 1; p += SELECT_THREADS) keep[p] = idx[p]; }
             __syncthreads();
         } else {
-            // literal std::partial_sort(iota, iota + k, end) (matrix_utils.cpp:327-335) with the heap carrying (value, index)
-            // pairs; va / idx are dead by now and provide the storage
+            // literal std::partial_sort(iota, iota + k, end) (matrix_utils.cpp:327-335), warp-cooperative (proposal_dev.cuh);
+            // va / idx are dead by now and provide the storage
             __syncthreads();
-            for (int i = tid; i < k; i += SELECT_THREADS) { heap[i].v = vd[i]; heap[i].i = i; }
+            heap.big = heap.hi + k;
+            if (tid < 32) wh_partial_sort(heap, vd, k, N, !angle_active, tid);
             __syncthreads();
-            if (tid == 0) {
-                auto less = [](const HeapEl& a, const HeapEl& b) { return a.v < b.v; };
-                heap_make(heap, k, less);
-                for (int i = k; i < N; i++) {
-                    const double vi = vd[i];
-                    if (vi < heap[0].v) {  // __pop_heap(first, middle, i): the evicted top goes to slot i (never read again)
-                        HeapEl value{vi, i, 0};
-                        heap_adjust(heap, 0, k, value, less);
-                    }
-                }
-                if (!angle_active) heap_sort(heap, k, less);
-            }
-            __syncthreads();
-            // after __heap_select the k-th (excluded) element is the heap top, heap[0]; after __sort_heap it is heap[k-1]
-            if (angle_active) { for (int p = tid + 1; p < k; p += SELECT_THREADS) flag[heap[p].i] |= 2; }
-            else { for (int p = tid; p < k - 1; p += SELECT_THREADS) keep[p] = heap[p].i; }
+            // after __heap_select the k-th (excluded) element is the heap top, hi[0]; after __sort_heap it is hi[k-1]
+            if (angle_active) { for (int p = tid + 1; p < k; p += SELECT_THREADS) flag[heap.hi[p]] |= 2; }
+            else { for (int p = tid; p < k - 1; p += SELECT_THREADS) keep[p] = heap.hi[p]; }
             __syncthreads();
         }
         if (angle_active) {

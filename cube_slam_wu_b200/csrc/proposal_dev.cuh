@@ -234,4 +234,131 @@ __device__ __forceinline__ void heap_select(int* first, int k, int n, Less less)
         }
 }
 
+// ---- warp-cooperative version of the same algorithms (bit-identical results) -------------------------------------
+// The heap lives in three shared/global arrays: hv (value), hi (index) and big (for every node with two children, the
+// child __adjust_heap would move into the hole: the right one unless right < left).  Facts used:
+//  * __make_heap sifts parents in descending index order; nodes of one tree level own disjoint subtrees, so a level can be
+//    sifted by many lanes at once with the same result.
+//  * __adjust_heap first walks the hole from the root to a leaf along `big` (independent of the inserted value), then
+//    __push_heap lifts the value: along that path the old contents are non-increasing, so the final slot is found with one
+//    ballot, and the shift of the path elements is done by all lanes in parallel.
+struct WarpHeap {
+    double* hv;
+    int* hi;
+    int* big;
+};
+
+__device__ __forceinline__ int wh_bigger_child(const WarpHeap& H, int h) {
+    const int r = 2 * h + 2;
+    return (H.hv[r] < H.hv[r - 1]) ? r - 1 : r;
+}
+
+// literal single-lane __adjust_heap on the SoA arrays (used inside the level-parallel make_heap)
+__device__ __forceinline__ void wh_adjust_serial(const WarpHeap& H, int holeIndex, int len, double value, int vidx) {
+    const int topIndex = holeIndex;
+    int secondChild = holeIndex;
+    while (secondChild < (len - 1) / 2) {
+        secondChild = 2 * (secondChild + 1);
+        if (H.hv[secondChild] < H.hv[secondChild - 1]) secondChild--;
+        H.hv[holeIndex] = H.hv[secondChild]; H.hi[holeIndex] = H.hi[secondChild];
+        holeIndex = secondChild;
+    }
+    if ((len & 1) == 0 && secondChild == (len - 2) / 2) {
+        secondChild = 2 * (secondChild + 1);
+        H.hv[holeIndex] = H.hv[secondChild - 1]; H.hi[holeIndex] = H.hi[secondChild - 1];
+        holeIndex = secondChild - 1;
+    }
+    int parent = (holeIndex - 1) / 2;
+    while (holeIndex > topIndex && H.hv[parent] < value) {
+        H.hv[holeIndex] = H.hv[parent]; H.hi[holeIndex] = H.hi[parent];
+        holeIndex = parent;
+        parent = (holeIndex - 1) / 2;
+    }
+    H.hv[holeIndex] = value; H.hi[holeIndex] = vidx;
+}
+
+// __make_heap(first, first+len), one warp
+__device__ __forceinline__ void wh_make(const WarpHeap& H, int len, int lane) {
+    if (len >= 2) {
+        const int last_parent = (len - 2) / 2;
+        int lvl = 0;
+        while ((2 << lvl) - 2 < last_parent) lvl++;  // deepest level holding a parent: nodes [2^lvl - 1, 2^(lvl+1) - 2]
+        for (; lvl >= 0; lvl--) {
+            const int lo = (1 << lvl) - 1;
+            int hi_node = (2 << lvl) - 2;
+            if (hi_node > last_parent) hi_node = last_parent;
+            for (int p = hi_node - lane; p >= lo; p -= 32) wh_adjust_serial(H, p, len, H.hv[p], H.hi[p]);
+            __syncwarp();
+        }
+    }
+    for (int h = lane; h < (len - 1) / 2; h += 32) H.big[h] = wh_bigger_child(H, h);
+    __syncwarp();
+}
+
+// __adjust_heap(first, 0, len, value) executed by one warp; keeps `big` consistent for nodes with two children (< (len-1)/2)
+__device__ __forceinline__ void wh_replace_root(const WarpHeap& H, int len, double value, int vidx, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    // (a) hole path root -> leaf; lane l remembers the node of level l
+    int h = 0, d = 0, mine = 0;
+    const int half = (len - 1) / 2;
+    while (h < half) {
+        h = H.big[h];
+        d++;
+        if (lane == d) mine = h;
+    }
+    if ((len & 1) == 0 && h == (len - 2) / 2) {
+        h = 2 * h + 1;
+        d++;
+        if (lane == d) mine = h;
+    }
+    // (b) old contents along the path; j = number of levels 1..d whose old value is not < value (a prefix, by the heap property)
+    double ov = 0; int oi = 0;
+    if (lane <= d) { ov = H.hv[mine]; oi = H.hi[mine]; }
+    const unsigned stay = __ballot_sync(FULL, lane >= 1 && lane <= d && !(ov < value));
+    const int j = __popc(stay);
+    const double nv = __shfl_down_sync(FULL, ov, 1);
+    const int ni = __shfl_down_sync(FULL, oi, 1);
+    if (lane < j) { H.hv[mine] = nv; H.hi[mine] = ni; }
+    else if (lane == j) { H.hv[mine] = value; H.hi[mine] = vidx; }
+    __syncwarp();
+    // (c) nodes on the path above the final slot had one child rewritten
+    if (lane < j && mine < half) H.big[mine] = wh_bigger_child(H, mine);
+    __syncwarp();
+}
+
+// std::partial_sort(iota, iota + k, iota + N) by vd with the libstdc++ algorithms above; on return hi[0..k) holds the heap
+// (sorted == false: hi[0] is the excluded k-th element) or the sorted prefix (sorted == true).  One warp.
+__device__ __forceinline__ void wh_partial_sort(const WarpHeap& H, const double* vd, int k, int N, bool sorted, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    for (int i = lane; i < k; i += 32) { H.hv[i] = vd[i]; H.hi[i] = i; }
+    __syncwarp();
+    wh_make(H, k, lane);
+    // __heap_select: 32 candidates at a time; everything before the first one that beats the root is a no-op
+    int i = k;
+    while (i < N) {
+        const int c = i + lane;
+        const double root = H.hv[0];
+        const double cv = (c < N) ? vd[c] : 0.0;
+        const unsigned hit = __ballot_sync(FULL, c < N && cv < root);
+        if (!hit) { i += 32; continue; }
+        const int src = __ffs(hit) - 1;
+        const double v = __shfl_sync(FULL, cv, src);
+        wh_replace_root(H, k, v, i + src, lane);
+        i += src + 1;
+    }
+    if (sorted) {
+        // __sort_heap: repeatedly move the root behind the shrinking heap and re-insert the former last leaf
+        for (int last = k - 1; last >= 1; last--) {
+            const double v = H.hv[last]; const int vi = H.hi[last];
+            const double rv = H.hv[0]; const int ri = H.hi[0];
+            __syncwarp();
+            if (lane == 0) { H.hv[last] = rv; H.hi[last] = ri; }
+            __syncwarp();
+            if (last >= 2) wh_replace_root(H, last, v, vi, lane);
+            else if (lane == 0) { H.hv[0] = v; H.hi[0] = vi; }
+            __syncwarp();
+        }
+    }
+}
+
 }  // namespace csb
