@@ -70,31 +70,30 @@ __device__ __forceinline__ void cube_min_log_error(const Cube& self, const Cube&
 }
 // projectOntoImageBbox :156-197
 __device__ __forceinline__ void cube_project_bbox(const Cube& c, const SE3& Tcw, const double* K, double* out) {
-    const double bx[8] = {1, 1, -1, -1, 1, 1, -1, -1}, by[8] = {1, -1, -1, 1, 1, -1, -1, 1}, bz[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
-    M3 R = quat_to_rot(c.pose.r);
-    double S[12];
-    double sc[3] = {c.scale.x, c.scale.y, c.scale.z};
-    for (int i = 0; i < 3; i++) {
-        for (int j = 0; j < 3; j++) S[i * 4 + j] = R.m[i * 3 + j] * sc[j];
-    }
-    S[3] = c.pose.t.x; S[7] = c.pose.t.y; S[11] = c.pose.t.z;
-    M3 Rc = quat_to_rot(Tcw.r);
-    double Tc[12];
-    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Tc[i * 4 + j] = Rc.m[i * 3 + j];
-    Tc[3] = Tcw.t.x; Tc[7] = Tcw.t.y; Tc[11] = Tcw.t.z;
+    const M3 R = quat_to_rot(c.pose.r);
+    const M3 Rc = quat_to_rot(Tcw.r);
+    const double k0 = K[0], k1 = K[1], k2 = K[2], k3 = K[3], k4 = K[4], k5 = K[5], k6 = K[6], k7 = K[7], k8 = K[8];
+    // similarityTransform(): R * diag(scale) | t
+    const double s00 = R.m[0] * c.scale.x, s01 = R.m[1] * c.scale.y, s02 = R.m[2] * c.scale.z;
+    const double s10 = R.m[3] * c.scale.x, s11 = R.m[4] * c.scale.y, s12 = R.m[5] * c.scale.z;
+    const double s20 = R.m[6] * c.scale.x, s21 = R.m[7] * c.scale.y, s22 = R.m[8] * c.scale.z;
     double minx = 0, miny = 0, maxx = 0, maxy = 0;
-#pragma unroll 1
+#pragma unroll
     for (int k = 0; k < 8; k++) {
-        double w3 = ((0.0 * bx[k] + 0.0 * by[k]) + 0.0 * bz[k]) + 1.0 * 1.0;
-        double cw[3];
-        for (int r = 0; r < 3; r++) cw[r] = (((S[r * 4] * bx[k] + S[r * 4 + 1] * by[k]) + S[r * 4 + 2] * bz[k]) + S[r * 4 + 3] * 1.0) / w3;
-        double p3 = ((0.0 * cw[0] + 0.0 * cw[1]) + 0.0 * cw[2]) + 1.0 * 1.0;
-        V3 pc;
-        pc.x = (((Tc[0] * cw[0] + Tc[1] * cw[1]) + Tc[2] * cw[2]) + Tc[3] * 1.0) / p3;
-        pc.y = (((Tc[4] * cw[0] + Tc[5] * cw[1]) + Tc[6] * cw[2]) + Tc[7] * 1.0) / p3;
-        pc.z = (((Tc[8] * cw[0] + Tc[9] * cw[1]) + Tc[10] * cw[2]) + Tc[11] * 1.0) / p3;
-        double ux = (K[0] * pc.x + K[1] * pc.y) + K[2] * pc.z, uy = (K[3] * pc.x + K[4] * pc.y) + K[5] * pc.z, uz = (K[6] * pc.x + K[7] * pc.y) + K[8] * pc.z;
-        double u = ux / uz, v = uy / uz;
+        // corners_body (g2o_Object.h:169-171): x: 1 1 -1 -1 1 1 -1 -1 | y: 1 -1 -1 1 1 -1 -1 1 | z: -1 -1 -1 -1 1 1 1 1
+        const double bx = ((k >> 1) & 1) ? -1.0 : 1.0;
+        const double by = (((k & 3) == 0) || ((k & 3) == 3)) ? 1.0 : -1.0;
+        const double bz = (k < 4) ? -1.0 : 1.0;
+        const double w3 = ((0.0 * bx + 0.0 * by) + 0.0 * bz) + 1.0 * 1.0;
+        const double cwx = (((s00 * bx + s01 * by) + s02 * bz) + c.pose.t.x * 1.0) / w3;
+        const double cwy = (((s10 * bx + s11 * by) + s12 * bz) + c.pose.t.y * 1.0) / w3;
+        const double cwz = (((s20 * bx + s21 * by) + s22 * bz) + c.pose.t.z * 1.0) / w3;
+        const double p3 = ((0.0 * cwx + 0.0 * cwy) + 0.0 * cwz) + 1.0 * 1.0;
+        const double pcx = (((Rc.m[0] * cwx + Rc.m[1] * cwy) + Rc.m[2] * cwz) + Tcw.t.x * 1.0) / p3;
+        const double pcy = (((Rc.m[3] * cwx + Rc.m[4] * cwy) + Rc.m[5] * cwz) + Tcw.t.y * 1.0) / p3;
+        const double pcz = (((Rc.m[6] * cwx + Rc.m[7] * cwy) + Rc.m[8] * cwz) + Tcw.t.z * 1.0) / p3;
+        const double ux = (k0 * pcx + k1 * pcy) + k2 * pcz, uy = (k3 * pcx + k4 * pcy) + k5 * pcz, uz = (k6 * pcx + k7 * pcy) + k8 * pcz;
+        const double u = ux / uz, v = uy / uz;
         if (k == 0) { minx = maxx = u; miny = maxy = v; }
         else { if (u > maxx) maxx = u; if (u < minx) minx = u; if (v > maxy) maxy = v; if (v < miny) miny = v; }
     }
@@ -183,10 +182,12 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(BABuffers B, int n_ed
             edge_error<TYPE>(x, x.cam, x.cube, x.cam2, J);  // J holds the error vector on lane 15
         } else if (c < Di) {
             if (i_free) {
-                double add[6] = {0, 0, 0, 0, 0, 0}, ep[D], em[D];
-                add[c] = delta;
+                double add[6], ep[D], em[D];
+#pragma unroll
+                for (int q = 0; q < 6; q++) add[q] = (q == c) ? delta : 0.0;
                 edge_error<TYPE>(x, se3_mul(se3_exp(add), x.cam), x.cube, x.cam2, ep);  // VertexSE3Expmap::oplusImpl: exp(d) * T
-                add[c] = -delta;
+#pragma unroll
+                for (int q = 0; q < 6; q++) add[q] = (q == c) ? -delta : 0.0;
                 edge_error<TYPE>(x, se3_mul(se3_exp(add), x.cam), x.cube, x.cam2, em);
 #pragma unroll
                 for (int k = 0; k < D; k++) J[k] = scalar * (ep[k] - em[k]);
@@ -196,16 +197,20 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(BABuffers B, int n_ed
                 const int d = c - Di;
                 double ep[D], em[D];
                 if (TYPE == EDGE_ODOM) {
-                    double add[6] = {0, 0, 0, 0, 0, 0};
-                    add[d] = delta;
+                    double add[6];
+#pragma unroll
+                    for (int q = 0; q < 6; q++) add[q] = (q == d) ? delta : 0.0;
                     edge_error<TYPE>(x, x.cam, x.cube, se3_mul(se3_exp(add), x.cam2), ep);
-                    add[d] = -delta;
+#pragma unroll
+                    for (int q = 0; q < 6; q++) add[q] = (q == d) ? -delta : 0.0;
                     edge_error<TYPE>(x, x.cam, x.cube, se3_mul(se3_exp(add), x.cam2), em);
                 } else {
-                    double add[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-                    add[d] = delta;
+                    double add[9];
+#pragma unroll
+                    for (int q = 0; q < 9; q++) add[q] = (q == d) ? delta : 0.0;
                     edge_error<TYPE>(x, x.cam, cube_exp_update(x.cube, add), x.cam2, ep);  // VertexCuboid::oplusImpl
-                    add[d] = -delta;
+#pragma unroll
+                    for (int q = 0; q < 9; q++) add[q] = (q == d) ? -delta : 0.0;
                     edge_error<TYPE>(x, x.cam, cube_exp_update(x.cube, add), x.cam2, em);
                 }
 #pragma unroll

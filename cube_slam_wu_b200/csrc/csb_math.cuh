@@ -81,18 +81,33 @@ CSB_HD Quat quat_from_rot(const M3& R) {
         q.y = (R.m[2] - R.m[6]) * t;
         q.z = (R.m[3] - R.m[1]) * t;
     } else {
+        // i = index of the largest diagonal entry, (j, k) its cyclic successors; written out per case so that nothing is
+        // dynamically indexed (keeps the matrix in registers on the device)
         int i = 0;
         if (R.m[4] > R.m[0]) i = 1;
-        if (R.m[8] > R.m[i * 4]) i = 2;
-        int j = (i + 1) % 3, k = (j + 1) % 3;
-        t = sqrt(R.m[i * 4] - R.m[j * 4] - R.m[k * 4] + 1.0);
-        double v[3];
-        v[i] = 0.5 * t;
-        t = 0.5 / t;
-        q.w = (R.m[k * 3 + j] - R.m[j * 3 + k]) * t;
-        v[j] = (R.m[j * 3 + i] + R.m[i * 3 + j]) * t;
-        v[k] = (R.m[k * 3 + i] + R.m[i * 3 + k]) * t;
-        q.x = v[0]; q.y = v[1]; q.z = v[2];
+        if (R.m[8] > (i == 0 ? R.m[0] : R.m[4])) i = 2;
+        if (i == 0) {  // j = 1, k = 2
+            t = sqrt(R.m[0] - R.m[4] - R.m[8] + 1.0);
+            q.x = 0.5 * t;
+            t = 0.5 / t;
+            q.w = (R.m[7] - R.m[5]) * t;
+            q.y = (R.m[3] + R.m[1]) * t;
+            q.z = (R.m[6] + R.m[2]) * t;
+        } else if (i == 1) {  // j = 2, k = 0
+            t = sqrt(R.m[4] - R.m[8] - R.m[0] + 1.0);
+            q.y = 0.5 * t;
+            t = 0.5 / t;
+            q.w = (R.m[2] - R.m[6]) * t;
+            q.z = (R.m[7] + R.m[5]) * t;
+            q.x = (R.m[1] + R.m[3]) * t;
+        } else {  // j = 0, k = 1
+            t = sqrt(R.m[8] - R.m[0] - R.m[4] + 1.0);
+            q.z = 0.5 * t;
+            t = 0.5 / t;
+            q.w = (R.m[3] - R.m[1]) * t;
+            q.x = (R.m[2] + R.m[6]) * t;
+            q.y = (R.m[5] + R.m[7]) * t;
+        }
     }
     return q;
 }

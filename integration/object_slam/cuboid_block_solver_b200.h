@@ -1,0 +1,133 @@
+// g2o batch hook for the BA half: a BlockSolver whose buildSystem() linearises every EdgeSE3Cuboid / EdgeSE3CuboidProj /
+// EdgeSE3Expmap of the graph on the GPU in one call and writes the blocks into the Hessian memory g2o mapped in
+// buildStructure().  The vertex / edge classes of object_slam/include/object_slam/g2o_Object.h stay untouched (they still
+// define computeError()/oplusImpl(), which g2o uses for chi2 and the update step); only the per-edge virtual
+// linearizeOplus()+constructQuadraticForm() loop of block_solver.hpp:501-560 is replaced.
+//
+// Usage in object_slam/src/main_obj.cpp:512-517 (one changed line):
+//     g2o::BlockSolverX* solver_ptr = new g2o::CuboidBlockSolverB200(linearSolver);
+//
+// NOT compiled in the build container (needs Eigen + the vendored g2o); see INTEGRATION.md.
+#pragma once
+
+#include <vector>
+
+#include "Thirdparty/g2o/g2o/core/block_solver.h"
+#include "Thirdparty/g2o/g2o/types/types_six_dof_expmap.h"
+#include "object_slam/g2o_Object.h"
+
+#include "cubeslam_b200.h"
+
+namespace g2o {
+
+class CuboidBlockSolverB200 : public BlockSolverX {
+public:
+    explicit CuboidBlockSolverB200(LinearSolverType* linearSolver) : BlockSolverX(linearSolver) { csb_create(&ctx_, 0); }
+    ~CuboidBlockSolverB200() { csb_destroy(ctx_); }
+
+    // buildStructure() of the base class allocates Hpp blocks and maps them into vertices (diagonal) and edges (off-diagonal);
+    // afterwards the graph topology, measurements and information matrices go to the device once.
+    virtual bool buildStructure(bool zeroBlocks = false)
+    {
+        if (!BlockSolverX::buildStructure(zeroBlocks)) return false;
+        cams_.clear(); cubes_.clear(); cam_fixed_.clear(); cube_fixed_.clear();
+        ec_.clear(); ep_.clear(); eo_.clear();
+        std::map<const OptimizableGraph::Vertex*, int> cam_id, cube_id;
+        auto cam_of = [&](OptimizableGraph::Vertex* v) {
+            auto it = cam_id.find(v);
+            if (it != cam_id.end()) return it->second;
+            int id = (int)cams_.size(); cam_id[v] = id; cams_.push_back(static_cast<VertexSE3Expmap*>(v)); cam_fixed_.push_back(v->fixed()); return id; };
+        auto cube_of = [&](OptimizableGraph::Vertex* v) {
+            auto it = cube_id.find(v);
+            if (it != cube_id.end()) return it->second;
+            int id = (int)cubes_.size(); cube_id[v] = id; cubes_.push_back(static_cast<VertexCuboid*>(v)); cube_fixed_.push_back(v->fixed()); return id; };
+        // activeEdges() is sorted by edge id (sparse_optimizer.cpp:482-487); the C ABI accumulates ec, ep, eo in array order, which
+        // equals that order for main_obj.cpp's id scheme (cuboid edges: frame index, odometry edges: N + frame index).
+        std::vector<int32_t> ec_cam, ec_cube, ep_cam, ep_cube, eo_i, eo_j;
+        std::vector<double> ec_meas, ec_info, ep_meas, ep_info, ep_K, eo_meas, eo_info;
+        for (OptimizableGraph::Edge* e : _optimizer->activeEdges()) {
+            auto* v0 = static_cast<OptimizableGraph::Vertex*>(e->vertex(0));
+            auto* v1 = static_cast<OptimizableGraph::Vertex*>(e->vertex(1));
+            if (auto* c = dynamic_cast<EdgeSE3Cuboid*>(e)) {
+                ec_.push_back(c); ec_cam.push_back(cam_of(v0)); ec_cube.push_back(cube_of(v1));
+                Vector10d m = c->measurement().toVector();
+                ec_meas.insert(ec_meas.end(), m.data(), m.data() + 10);
+                for (int r = 0; r < 9; r++) for (int k = 0; k < 9; k++) ec_info.push_back(c->information()(r, k));
+            } else if (auto* p = dynamic_cast<EdgeSE3CuboidProj*>(e)) {
+                ep_.push_back(p); ep_cam.push_back(cam_of(v0)); ep_cube.push_back(cube_of(v1));
+                for (int k = 0; k < 4; k++) ep_meas.push_back(p->measurement()(k));
+                for (int r = 0; r < 4; r++) for (int k = 0; k < 4; k++) ep_info.push_back(p->information()(r, k));
+                for (int r = 0; r < 3; r++) for (int k = 0; k < 3; k++) ep_K.push_back(p->Kalib(r, k));
+            } else if (auto* o = dynamic_cast<EdgeSE3Expmap*>(e)) {
+                eo_.push_back(o); eo_i.push_back(cam_of(v0)); eo_j.push_back(cam_of(v1));
+                Vector7d m = o->measurement().toVector();
+                eo_meas.insert(eo_meas.end(), m.data(), m.data() + 7);
+                for (int r = 0; r < 6; r++) for (int k = 0; k < 6; k++) eo_info.push_back(o->information()(r, k));
+            } else
+                return false;  // an edge type this solver does not know: fall back to a stock BlockSolverX in the caller
+        }
+        csb_ba_graph g;
+        g.n_cam = (int)cams_.size(); g.n_cube = (int)cubes_.size(); g.cam_fixed = cam_fixed_.data(); g.cube_fixed = cube_fixed_.data();
+        g.n_ec = (int)ec_.size(); g.ec_cam = ec_cam.data(); g.ec_cube = ec_cube.data(); g.ec_meas = ec_meas.data(); g.ec_info = ec_info.data();
+        g.n_ep = (int)ep_.size(); g.ep_cam = ep_cam.data(); g.ep_cube = ep_cube.data(); g.ep_meas = ep_meas.data(); g.ep_info = ep_info.data(); g.ep_K = ep_K.data();
+        g.n_eo = (int)eo_.size(); g.eo_cam_i = eo_i.data(); g.eo_cam_j = eo_j.data(); g.eo_meas = eo_meas.data(); g.eo_info = eo_info.data();
+        ec_cam_ = ec_cam; ec_cube_ = ec_cube; ep_cam_ = ep_cam; ep_cube_ = ep_cube; eo_i_ = eo_i; eo_j_ = eo_j;
+        return csb_ba_set_graph(ctx_, &g) == CSB_OK;
+    }
+
+    // One GPU linearisation instead of the per-edge loop; then copy blocks into the memory g2o mapped (Eigen blocks are
+    // column-major, like the C ABI's) and gather b, exactly as block_solver.hpp:546-557 does.
+    virtual bool buildSystem()
+    {
+        const size_t nc = cams_.size(), nq = cubes_.size();
+        std::vector<double> cams7(7 * nc), cubes10(10 * nq);
+        for (size_t i = 0; i < nc; i++) { Vector7d v = cams_[i]->estimate().toVector(); std::copy(v.data(), v.data() + 7, &cams7[7 * i]); }
+        for (size_t i = 0; i < nq; i++) { Vector10d v = cubes_[i]->estimate().toVector(); std::copy(v.data(), v.data() + 10, &cubes10[10 * i]); }
+        H_cam_.resize(36 * nc); b_cam_.resize(6 * nc); H_cube_.resize(81 * nq); b_cube_.resize(9 * nq);
+        ec_Hij_.resize(54 * ec_.size()); ep_Hij_.resize(54 * ep_.size()); eo_Hij_.resize(36 * eo_.size());
+        csb_ba_output out = {};
+        out.H_cam = H_cam_.data(); out.b_cam = b_cam_.data(); out.H_cube = H_cube_.data(); out.b_cube = b_cube_.data();
+        out.ec_Hij = ec_Hij_.data(); out.ep_Hij = ep_Hij_.data(); out.eo_Hij = eo_Hij_.data();
+        if (csb_ba_linearize(ctx_, cams7.data(), cubes10.data(), &out) != CSB_OK) return false;
+        _Hpp->clear();
+        for (size_t i = 0; i < nc; i++) if (!cams_[i]->fixed()) {
+            std::copy(&H_cam_[36 * i], &H_cam_[36 * i] + 36, cams_[i]->hessianData());
+            std::copy(&b_cam_[6 * i], &b_cam_[6 * i] + 6, cams_[i]->bData());
+        }
+        for (size_t i = 0; i < nq; i++) if (!cubes_[i]->fixed()) {
+            std::copy(&H_cube_[81 * i], &H_cube_[81 * i] + 81, cubes_[i]->hessianData());
+            std::copy(&b_cube_[9 * i], &b_cube_[9 * i] + 9, cubes_[i]->bData());
+        }
+        // off-diagonal blocks: the edge holds the mapped block (possibly transposed: base_binary_edge.hpp:207-218).  A small accessor
+        // (friend or public wrapper around _hessian/_hessianTransposed/_hessianRowMajor) has to be added to BaseBinaryEdge for this copy.
+        for (size_t e = 0; e < ec_.size(); e++) writeOffDiagonal(ec_[e], &ec_Hij_[54 * e], 6, 9);
+        for (size_t e = 0; e < ep_.size(); e++) writeOffDiagonal(ep_[e], &ep_Hij_[54 * e], 6, 9);
+        for (size_t e = 0; e < eo_.size(); e++) writeOffDiagonal(eo_[e], &eo_Hij_[36 * e], 6, 6);
+        for (size_t i = 0; i < _optimizer->indexMapping().size(); ++i) {
+            OptimizableGraph::Vertex* v = _optimizer->indexMapping()[i];
+            v->copyB(_b + v->colInHessian());
+        }
+        return true;
+    }
+
+private:
+    template <class Edge>
+    static void writeOffDiagonal(Edge* e, const double* blk, int di, int dj)
+    {
+        double* dst = e->mappedHessianData();          // accessor to add: returns the pointer given to mapHessianMemory()
+        if (!dst) return;                              // a vertex is fixed: no block
+        if (!e->mappedHessianRowMajor()) std::copy(blk, blk + di * dj, dst);
+        else for (int r = 0; r < di; r++) for (int c = 0; c < dj; c++) dst[r * dj + c] = blk[c * di + r];  // transposed block (dj x di, column-major)
+    }
+
+    csb_context* ctx_ = nullptr;
+    std::vector<VertexSE3Expmap*> cams_;
+    std::vector<VertexCuboid*> cubes_;
+    std::vector<int32_t> cam_fixed_, cube_fixed_, ec_cam_, ec_cube_, ep_cam_, ep_cube_, eo_i_, eo_j_;
+    std::vector<EdgeSE3Cuboid*> ec_;
+    std::vector<EdgeSE3CuboidProj*> ep_;
+    std::vector<EdgeSE3Expmap*> eo_;
+    std::vector<double> H_cam_, b_cam_, H_cube_, b_cube_, ec_Hij_, ep_Hij_, eo_Hij_;
+};
+
+}  // namespace g2o
