@@ -420,28 +420,58 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) k_score(DetectBuffers B, int
 // ------------------------------------------------------------------------------------------------
 constexpr int SELECT_THREADS = 128;
 
-// bitonic sort of idx[0..npad) by key[idx] ascending, ties by index; idx < 0 are +inf pads
-__device__ __forceinline__ bool key_less(const double* key, int a, int b) {
-    if (b < 0) return a >= 0;
-    if (a < 0) return false;
-    double ka = key[a], kb = key[b];
-    return (ka < kb) || (ka == kb && a < b);
+// order-preserving map double -> uint64 (negative values reversed, sign bit flipped)
+__device__ __forceinline__ unsigned long long ordered_key(double v) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
-__device__ __forceinline__ void bitonic_sort_idx(int* idx, int npad, const double* key, int tid, int nthreads) {
-    for (int k = 2; k <= npad; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < npad; i += nthreads) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    int a = idx[i], b = idx[ixj];
-                    bool up = ((i & k) == 0);
-                    bool swap = up ? key_less(key, b, a) : key_less(key, a, b);
-                    if (swap) { idx[i] = b; idx[ixj] = a; }
-                }
-            }
-            __syncthreads();
+__device__ __forceinline__ double ordered_key_inv(unsigned long long k) {
+    unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// k-th smallest (1-based) of v[0..N) by an 8-pass MSB radix select over the ordered keys; also returns how many elements
+// are strictly smaller.  All threads of the block call it; hist = 256 ints of shared memory.
+template <int THREADS>
+__device__ __forceinline__ double radix_select_kth(const double* v, int N, int k, int* hist, int* s_bc, int tid, int& n_less) {
+    unsigned long long prefix = 0, mask = 0;
+    int rank = k - 1, below = 0;  // 0-based rank inside the current candidate set
+    for (int pass = 0; pass < 8; pass++) {
+        const int shift = 56 - 8 * pass;
+        for (int b = tid; b < 256; b += THREADS) hist[b] = 0;
+        __syncthreads();
+        for (int i = tid; i < N; i += THREADS) {
+            unsigned long long key = ordered_key(v[i]);
+            if ((key & mask) == prefix) atomicAdd(&hist[(int)((key >> shift) & 255ull)], 1);
         }
+        __syncthreads();
+        if (tid < 32) {
+            // lane owns bins [8*lane, 8*lane+8): find the bin where the cumulative count passes `rank`
+            int c[8], s = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) { c[q] = hist[8 * tid + q]; s += c[q]; }
+            int inc = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += t; }
+            int excl = inc - s;
+            if (rank >= excl && rank < inc) {
+                int acc = excl, bin = 0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) { if (rank >= acc + c[q]) { acc += c[q]; } else { bin = q; break; } }
+                s_bc[0] = 8 * tid + bin;
+                s_bc[1] = acc;  // elements of the candidate set below the chosen bin
+            }
+        }
+        __syncthreads();
+        const int bin = s_bc[0], acc = s_bc[1];
+        prefix |= ((unsigned long long)bin) << shift;
+        mask |= 255ull << shift;
+        rank -= acc;
+        below += acc;
+        __syncthreads();
     }
+    n_less = below;
+    return ordered_key_inv(prefix);
 }
 
 // Tasks with n_lo < N <= n_hi are handled by this launch (two launches: a small-footprint variant for the common case and a
@@ -450,76 +480,60 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(DetectBuffers B, int 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_w[SELECT_THREADS / 32];
     __shared__ double s_red[4 * (SELECT_THREADS / 32)];
+    __shared__ int s_hist[256];
+    __shared__ int s_bc[2];
     const int task = blockIdx.x, tid = threadIdx.x;
     const int N = B.n_valid[task];
     if (N <= n_lo || N > n_hi) return;
     const TaskTab tt = B.ttab[task];
     const size_t ob = (size_t)tt.out_offset;
-    int npad = 1;
-    while (npad < N) npad <<= 1;
-    // layout: vd[n_cap] | va[n_cap] | idx[cap_pad] | flag[n_cap];   the emulation heap later aliases va (values) and idx
-    // (indices + larger-child table): k <= 2N/3 + 1, so 8k <= 8N and 4k + 4(k/2) <= 4N
+    // layout: vd[n_cap] | va[n_cap] | ibuf[n_cap] | flag[n_cap].  The partial_sort replay, when needed, aliases va (heap values)
+    // and ibuf (heap indices + larger-child table): k <= 2N/3 + 1, so 8k <= 8N and 4(k + k/2) <= 4N.
     double *vd, *va;
-    int* idx;
+    int* ibuf;
     unsigned char* flag;
     WarpHeap heap;
     if (N <= n_cap) {
-        int cap_pad = 1; while (cap_pad < n_cap) cap_pad <<= 1;
         vd = reinterpret_cast<double*>(smem_raw);
         va = vd + n_cap;
-        idx = reinterpret_cast<int*>(va + n_cap);
-        flag = reinterpret_cast<unsigned char*>(idx + cap_pad);
-        heap.hv = va; heap.hi = idx; heap.big = nullptr;  // big = hi + k, set once k is known (k + (k-1)/2 <= N ints)
+        ibuf = reinterpret_cast<int*>(va + n_cap);
+        flag = reinterpret_cast<unsigned char*>(ibuf + n_cap);
+        heap.hv = va;
         for (int i = tid; i < N; i += SELECT_THREADS) { vd[i] = B.p_dist[ob + i]; va[i] = B.p_angle[ob + i]; }
     } else {
         vd = B.p_dist + ob; va = B.p_angle + ob;
-        idx = B.sel_idx + 2 * ob;  // 2x slots: room for the power-of-two padding (npad < 2N)
+        ibuf = B.sel_idx + 2 * ob;
         flag = B.sel_flag + ob;
-        heap.hv = B.sel_heap + 2 * ob; heap.hi = reinterpret_cast<int*>(B.sel_heap + 2 * ob + N); heap.big = nullptr;
+        heap.hv = B.sel_heap + 2 * ob;
     }
+    heap.hi = ibuf;
+    heap.big = nullptr;
     __syncthreads();
 
     int* keep = B.keep + ob;
     int n_keep = 0;
     if (N > 4) {
+        // fuse_normalize_scores_v2, object_3d_util.cpp:736-787
         const int k = (int)round((double)(float)N / 3.0 * 2.0);  // breaking_num (:739)
-        // angle list: only the order statistics k-1, k-2 and (if there is a strict gap) the k-1 smallest as a set
-        for (int i = tid; i < npad; i += SELECT_THREADS) idx[i] = (i < N) ? i : -1;
-        __syncthreads();
-        bitonic_sort_idx(idx, npad, va, tid, SELECT_THREADS);
-        const bool angle_active = va[idx[k - 1]] > va[idx[k - 2]];  // (:766)
-        for (int i = tid; i < N; i += SELECT_THREADS) flag[i] = 0;
-        __syncthreads();
-        if (angle_active)
-            for (int p = tid; p < k - 1; p += SELECT_THREADS) flag[idx[p]] = 1;
-        __syncthreads();
-        // distance list
-        for (int i = tid; i < npad; i += SELECT_THREADS) idx[i] = (i < N) ? i : -1;
-        __syncthreads();
-        bitonic_sort_idx(idx, npad, vd, tid, SELECT_THREADS);
-        const double vk = vd[idx[k - 1]];
-        // Does the unstable std::partial_sort matter?  With the angle filter on, dist_keep is used as a SET = heap minus its
-        // top after __heap_select.  If only one element of the k-th smallest value vk is inside the heap it is the top (the
-        // dropped k-th) and the set is exactly the k-1 elements below vk; otherwise (position k-2 also equals vk) which of the
-        // tied elements stay depends on the heap.  With the angle filter off the kept list keeps partial_sort's ORDER, so any
-        // tie inside the first k sorted positions matters.
-        bool need_emul;
-        if (angle_active) need_emul = (vd[idx[k - 2]] == vk);
-        else {
-            int local2 = 0;
-            for (int p = tid; p < k - 1; p += SELECT_THREADS) local2 += (vd[idx[p]] == vd[idx[p + 1]]) ? 1 : 0;
-            int inner_ties;
-            block_excl_scan<SELECT_THREADS>(local2, s_w, tid, inner_ties);
-            need_emul = inner_ties > 0;
+        // angle list: sorted[k-1] > sorted[k-2] (:766)  <=>  exactly k-1 elements are strictly below the k-th smallest value;
+        // then the kept k-1 are precisely those elements
+        int lessA;
+        const double vkA = radix_select_kth<SELECT_THREADS>(va, N, k, s_hist, s_bc, tid, lessA);
+        const bool angle_active = (lessA == k - 1);
+        // distance list: dist_keep = first k-1 of std::partial_sort(iota, iota+k, end) (matrix_utils.cpp:327-335, unstable).
+        int lessD;
+        const double vk = radix_select_kth<SELECT_THREADS>(vd, N, k, s_hist, s_bc, tid, lessD);
+        // With the angle filter on, dist_keep is used as a SET = heap minus its top after __heap_select.  If only one element of
+        // value vk is inside the heap (lessD == k-1) it is the top (the dropped k-th) and the set is exactly {d < vk}; otherwise
+        // which of the tied elements stay depends on the heap -> replay.  With the angle filter off the kept list keeps
+        // partial_sort's ORDER (:783-786): replay (it also yields the sorted order).
+        const bool need_emul = angle_active ? (lessD != k - 1) : true;
+        if (angle_active) {
+            for (int i = tid; i < N; i += SELECT_THREADS) flag[i] = ((va[i] < vkA) ? 1 : 0) | ((!need_emul && vd[i] < vk) ? 2 : 0);
         }
-        if (!need_emul) {
-            if (angle_active) { for (int p = tid; p < k - 1; p += SELECT_THREADS) flag[idx[p]] |= 2; }
-            else { for (int p = tid; p < k - 1; p += SELECT_THREADS) keep[p] = idx[p]; }
-            __syncthreads();
-        } else {
-            // literal std::partial_sort(iota, iota + k, end) (matrix_utils.cpp:327-335), warp-cooperative (proposal_dev.cuh);
-            // va / idx are dead by now and provide the storage
-            __syncthreads();
+        __syncthreads();
+        if (need_emul) {
+            // literal libstdc++ __heap_select (+ __sort_heap), warp-cooperative (proposal_dev.cuh); va / ibuf provide the storage
             heap.big = heap.hi + k;
             if (tid < 32) wh_partial_sort(heap, vd, k, N, !angle_active, tid);
             __syncthreads();
@@ -539,7 +553,7 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(DetectBuffers B, int 
                 n_keep += tot;
             }
         } else
-            n_keep = k - 1;  // final_keep_inds = dist_keep_inds in partial_sort order (:783-786)
+            n_keep = k - 1;
     } else {
         n_keep = N;
         for (int p = tid; p < N; p += SELECT_THREADS) keep[p] = p;
