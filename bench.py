@@ -57,17 +57,19 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md recipe).  nvidia-smi needs ~0.1 s to start, so it is launched
+    early; only rows that arrive inside [mark_begin, mark_end] (the under-load window) are reported."""
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.rows = []
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -76,24 +78,32 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc:
+            time.sleep(0.03)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        rows = [r for (t, r) in self.rows if len(r) >= 7 and (self.t0 is None or t >= self.t0) and (self.t1 is None or t <= self.t1 + 0.02)]
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 7:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
+                "window": "warm-up + timed steps (under load)"}
 
 
 def build_batch(rank):
@@ -174,6 +184,8 @@ def run_ours(args, rank, local_rank, world):
     import helpers as H
 
     torch.cuda.set_device(local_rank)
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # early: nvidia-smi start-up latency; rows are filtered to the under-load window later
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.Stream()
@@ -203,8 +215,7 @@ def run_ours(args, rank, local_rank, world):
             dist.all_gather_into_tensor(obs_all, obs)
 
     with torch.cuda.stream(stream):
-        sampler = ClockSampler(local_rank)
-        sampler.start()  # samples through warm-up and the timed region (both under load); the timed region alone is only tens of ms
+        sampler.mark_begin()
         for _ in range(args.warmup):
             flush.zero_()
             step(False)
@@ -227,6 +238,7 @@ def run_ours(args, rank, local_rank, world):
         if world > 1:
             dist.barrier()
         t_wall = time.perf_counter() - t_wall0
+        sampler.mark_end()
         clocks = sampler.stop()
     ms_total = sum(a.elapsed_time(b) for a, b in ev)
     n_scored, n_enum = int(st.n_scored), int(st.n_enumerated)
@@ -340,7 +352,7 @@ def run_ours(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
