@@ -197,8 +197,13 @@ constexpr int SUBW = 8;  // lanes per VP-support unit
 // VP_support_edge_infos (object_3d_util.cpp:548-619) for one (vanishing point, line table) unit, executed by an 8-lane
 // sub-group; all 32 lanes of the warp run this in lock step (ballots / shuffles are warp-wide), `active` masks units that
 // do not exist.  Returns the two supporting line angles (NaN if none) on every lane of the sub-group.
-__device__ __forceinline__ void vp_support_unit(bool active, double vx, double vy, double thr, int n, const double* ang, const double* mid, int lane, int swap_lt,
-                                                double& out_low, double& out_top) {
+//
+// lcs (optional, n <= 64): cos/sin of every line angle.  A line supports the VP iff the angle between its direction and the
+// ray VP -> midpoint is below thr modulo pi, i.e. |cross(u_line, d)|^2 < sin^2(thr) |d|^2.  Lines that fail this test with a
+// margin of 1e-6 rad are certain outliers and never reach atan2; the remaining candidates (typically 10-20 %) are packed
+// densely onto the lanes and decided exactly as the reference does (atan2 -> normalize_to_pi -> compare).
+__device__ __forceinline__ void vp_support_unit(bool active, double vx, double vy, double thr, double s2_margin, int n, const double* ang, const double* mid,
+                                                const double* lcs, int lane, int swap_lt, double& out_low, double& out_top) {
     const unsigned FULL = 0xffffffffu;
     const int sl = lane & (SUBW - 1), sbase = lane & ~(SUBW - 1), sshift = sbase;
     bool have_base = false;
@@ -206,11 +211,36 @@ __device__ __forceinline__ void vp_support_unit(bool active, double vx, double v
     // lane-local extrema of the smoothed inlier angles; ties keep the lowest line index (Eigen max/minCoeff: first wins)
     double vmax = 0, vmin = 0;
     int imax = -1, imin = -1;
-    for (int b0 = 0; b0 < n; b0 += SUBW) {
-        const int e = b0 + sl;
+    const bool packed = (lcs != nullptr) && (n <= 64);
+    unsigned cm_lo = 0, cm_hi = 0;  // candidate lines of this unit (bit e)
+    int n_iter = n;
+    if (packed) {
+        for (int b0 = 0; b0 < n; b0 += SUBW) {
+            const int e = b0 + sl;
+            bool cand = false;
+            if (active && e < n) {
+                const double dx = mid[2 * e] - vx, dy = mid[2 * e + 1] - vy;
+                const double cr = dx * lcs[2 * e + 1] - dy * lcs[2 * e];
+                cand = !(cr * cr > s2_margin * (dx * dx + dy * dy));  // NaN / inf -> candidate (decided exactly below)
+            }
+            const unsigned sub = (__ballot_sync(FULL, cand) >> sshift) & ((1u << SUBW) - 1);
+            if (b0 < 32) cm_lo |= sub << b0; else cm_hi |= sub << (b0 - 32);
+        }
+        n_iter = __popc(cm_lo) + __popc(cm_hi);
+        // all sub-groups of the warp must run the same number of (ballot / shuffle) rounds
+        for (int off = 16; off >= SUBW; off >>= 1) n_iter = max(n_iter, __shfl_xor_sync(FULL, n_iter, off));
+    }
+    const int n_lo = __popc(cm_lo), n_cand = n_lo + __popc(cm_hi);
+    for (int b0 = 0; b0 < n_iter; b0 += SUBW) {
+        int e = b0 + sl;
+        bool have = active && e < n;
+        if (packed) {
+            have = active && e < n_cand;
+            if (have) e = (e < n_lo) ? (int)__fns(cm_lo, 0, e + 1) : 32 + (int)__fns(cm_hi, 0, e - n_lo + 1);
+        }
         bool inl = false;
         double raw = 0;
-        if (active && e < n) {
+        if (have) {
             raw = det_atan2(mid[2 * e + 1] - vy, mid[2 * e] - vx);
             double nrm = normalize_to_pi(raw);
             double d = fabs(ang[e] - nrm);
@@ -281,7 +311,8 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) k_score(DetectBuffers B, int
     double* s_sup = s_vp + 6 * (size_t)groups_cap;
     double* s_lang = s_sup + 6 * (size_t)groups_cap;
     double* s_lmid = s_lang + LINE_SMEM_CAP;
-    unsigned* s_mask = reinterpret_cast<unsigned*>(s_lmid + 2 * LINE_SMEM_CAP);
+    double* s_lcs = s_lmid + 2 * LINE_SMEM_CAP;  // cos, sin of the line angles (prefilter only)
+    unsigned* s_mask = reinterpret_cast<unsigned*>(s_lcs + 2 * LINE_SMEM_CAP);
     int* s_wpre = reinterpret_cast<int*>(s_mask + words_cap);  // words_cap + 1 entries
     __shared__ uint64_t s_bar;
     __shared__ int s_task;
@@ -321,9 +352,17 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) k_score(DetectBuffers B, int
         const double* lang = B.ml_ang + tt.line_cap_offset;
         const double* lmid = B.ml_mid + 2 * (size_t)tt.line_cap_offset;
         if (n_lines <= LINE_SMEM_CAP) {
-            for (int i = tid; i < n_lines; i += SCORE_THREADS) { s_lang[i] = lang[i]; s_lmid[2 * i] = lmid[2 * i]; s_lmid[2 * i + 1] = lmid[2 * i + 1]; }
+            for (int i = tid; i < n_lines; i += SCORE_THREADS) {
+                const double a = lang[i];
+                s_lang[i] = a; s_lmid[2 * i] = lmid[2 * i]; s_lmid[2 * i + 1] = lmid[2 * i + 1];
+                s_lcs[2 * i] = cos(a); s_lcs[2 * i + 1] = sin(a);  // only feeds the conservative prefilter of vp_support_unit
+            }
             lang = s_lang; lmid = s_lmid;
         }
+        const double* lcs = (n_lines <= 64) ? s_lcs : nullptr;
+        // sin^2(thr + 1e-6): outlier test with margin (decisions near the threshold are taken exactly, via atan2)
+        const double s12 = sin(15.0 / 180.0 * M_PI + 1e-6), s3 = sin(10.0 / 180.0 * M_PI + 1e-6);
+        const double s2m12 = s12 * s12, s2m3 = s3 * s3;
         // (c) vanishing points
         for (int g = tid; g < n_groups; g += SCORE_THREADS) {
             int yaw_id = g % n_yaw, pair = g / n_yaw;
@@ -348,7 +387,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) k_score(DetectBuffers B, int
                 const double vx = s_vp[6 * g + 2 * vp_id], vy = s_vp[6 * g + 2 * vp_id + 1];
                 const double thr = (vp_id != 2 ? 15.0 : 10.0) / 180.0 * M_PI;
                 double lo, tp;
-                vp_support_unit(active, vx, vy, thr, n_lines, lang, lmid, lane, vp_id > 0, lo, tp);
+                vp_support_unit(active, vx, vy, thr, (vp_id != 2 ? s2m12 : s2m3), n_lines, lang, lmid, lcs, lane, vp_id > 0, lo, tp);
                 if (active) {
                     if (vp_id < 2) { if (sl == 0) { s_sup[6 * g + 2 * vp_id] = lo; s_sup[6 * g + 2 * vp_id + 1] = tp; } }
                     else for (int y = sl; y < n_yaw; y += SUBW) { s_sup[6 * (g + y) + 4] = lo; s_sup[6 * (g + y) + 5] = tp; }  // vp3 is shared by the pair's yaw samples
@@ -360,19 +399,32 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) k_score(DetectBuffers B, int
         // (d) phase 1 -> validity bitmask
         const int n_hyp = tt.n_hyp;
         const int n_words = (n_hyp + 31) >> 5;
-        for (int base = 0; base < n_hyp; base += SCORE_THREADS) {
-            const int h = base + tid;
-            bool valid = false;
-            if (h < n_hyp) {
-                int group, top, cfg;
-                decode_hyp(h, tt.n_top, group, top, cfg);
-                if (tt.cfg_mask & cfg) {  // cfg 1 -> bit0, cfg 2 -> bit1
+        // one thread per (group, top sample): corner 2 once, then both configurations; hypothesis id = 2 * pair + (cfg - 1), so a
+        // warp's 32 pairs fill two mask words (bits interleaved: even = configuration 1, odd = configuration 2)
+        const int n_pairs_gt = n_hyp >> 1;
+        for (int base = 0; base < n_pairs_gt; base += SCORE_THREADS) {
+            const int p = base + tid;
+            bool v1 = false, v2 = false;
+            if (p < n_pairs_gt) {
+                const int group = p / tt.n_top, top = p - group * tt.n_top;
+                const double c1x = (double)(tt.top_x0 + top * tt.top_step);
+                V2 c2;
+                const int vp1 = construct_corner2(geo, s_vp + 6 * group, c1x, c2);
+                if (vp1 > 0) {
                     V2 c[8];
-                    valid = construct_corners(geo, s_vp + 6 * group, (double)(tt.top_x0 + top * tt.top_step), cfg, c) > 0;
+                    if (tt.cfg_mask & 1) v1 = construct_rest(geo, s_vp + 6 * group, c1x, c2, vp1, 1, c) > 0;
+                    if (tt.cfg_mask & 2) v2 = construct_rest(geo, s_vp + 6 * group, c1x, c2, vp1, 2, c) > 0;
                 }
             }
-            const unsigned bal = __ballot_sync(FULL, valid);
-            if (lane == 0 && (h >> 5) < n_words) s_mask[h >> 5] = bal;
+            const unsigned b1 = __ballot_sync(FULL, v1), b2 = __ballot_sync(FULL, v2);
+            if (lane < 2) {
+                // spread 16 bits of each ballot to even / odd positions
+                unsigned x = (lane == 0) ? (b1 & 0xffffu) : (b1 >> 16), y = (lane == 0) ? (b2 & 0xffffu) : (b2 >> 16);
+                x = (x | (x << 8)) & 0x00ff00ffu; x = (x | (x << 4)) & 0x0f0f0f0fu; x = (x | (x << 2)) & 0x33333333u; x = (x | (x << 1)) & 0x55555555u;
+                y = (y | (y << 8)) & 0x00ff00ffu; y = (y | (y << 4)) & 0x0f0f0f0fu; y = (y | (y << 2)) & 0x33333333u; y = (y | (y << 1)) & 0x55555555u;
+                const int w = ((base + (tid & ~31)) >> 4) + lane;  // first hypothesis of the warp = 2 * pair -> word (2 * pair) / 32
+                if (w < n_words) s_mask[w] = x | (y << 1);
+            }
         }
         __syncthreads();
         // (e) exclusive prefix of the word popcounts
@@ -796,7 +848,7 @@ __global__ void k_debug_corners(DetectBuffers B, int task, double* out) {
 // launchers
 // ------------------------------------------------------------------------------------------------
 static size_t score_smem_bytes(int groups_cap, int map_cap_floats, int words_cap) {
-    return (size_t)map_cap_floats * 4 + (size_t)groups_cap * 12 * 8 + (size_t)LINE_SMEM_CAP * 3 * 8 + (size_t)(2 * words_cap + 1) * 4 + 64;
+    return (size_t)map_cap_floats * 4 + (size_t)groups_cap * 12 * 8 + (size_t)LINE_SMEM_CAP * 5 * 8 + (size_t)(2 * words_cap + 1) * 4 + 64;
 }
 
 cudaError_t launch_prep_lines(const DetectBuffers& B, int max_lines_per_frame, cudaStream_t st) {

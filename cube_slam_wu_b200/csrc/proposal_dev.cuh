@@ -67,12 +67,14 @@ __device__ __forceinline__ void vanishing_points(const double* K, double c, doub
 
 // Corner construction + rejection cascade, box_proposal_detail.cpp:413-625.
 // Returns vp_1_position (1 left, 2 right) or 0 if the hypothesis is rejected.  c[0..7] = corners 1..8.
-__device__ __forceinline__ int construct_corners(const TaskGeo& g, const double* vp, double c1x, int config_id, V2* c) {
+// Split in two: corner 2 (box_proposal_detail.cpp:413-461) does not depend on the configuration, so the sweep computes it once
+// per (group, top sample) and runs the rest (:467-625) for both configurations.
+__device__ __forceinline__ int construct_corner2(const TaskGeo& g, const double* vp, double c1x, V2& corner_2_top) {
     const double shorted_edge_thre = 20;
-    V2 vp_1{vp[0], vp[1]}, vp_2{vp[2], vp[3]}, vp_3{vp[4], vp[5]};
+    V2 vp_1{vp[0], vp[1]};
     V2 corner_1_top{c1x, g.top};
     int vp_1_position = 0;
-    V2 corner_2_top = seg_hit_boundary(vp_1, corner_1_top, g.right, g.top, g.right, g.down);
+    corner_2_top = seg_hit_boundary(vp_1, corner_1_top, g.right, g.top, g.right, g.down);
     if (corner_2_top.x == -1) {
         corner_2_top = seg_hit_boundary(vp_1, corner_1_top, g.left, g.top, g.left, g.down);
         if (corner_2_top.x != -1) vp_1_position = 2;
@@ -80,7 +82,22 @@ __device__ __forceinline__ int construct_corners(const TaskGeo& g, const double*
         vp_1_position = 1;
     if (!(vp_1_position > 0)) return 0;
     if (dist2(corner_1_top, corner_2_top) < shorted_edge_thre) return 0;
+    return vp_1_position;
+}
 
+__device__ __forceinline__ int construct_rest(const TaskGeo& g, const double* vp, double c1x, V2 corner_2_top, int vp_1_position, int config_id, V2* c);
+
+__device__ __forceinline__ int construct_corners(const TaskGeo& g, const double* vp, double c1x, int config_id, V2* c) {
+    V2 corner_2_top;
+    int vp_1_position = construct_corner2(g, vp, c1x, corner_2_top);
+    if (vp_1_position == 0) return 0;
+    return construct_rest(g, vp, c1x, corner_2_top, vp_1_position, config_id, c);
+}
+
+__device__ __forceinline__ int construct_rest(const TaskGeo& g, const double* vp, double c1x, V2 corner_2_top, int vp_1_position, int config_id, V2* c) {
+    const double shorted_edge_thre = 20;
+    V2 vp_1{vp[0], vp[1]}, vp_2{vp[2], vp[3]}, vp_3{vp[4], vp[5]};
+    V2 corner_1_top{c1x, g.top};
     V2 corner_3_top, corner_4_top;
     if (config_id == 1) {
         if (vp_1_position == 1) corner_4_top = seg_hit_boundary(vp_2, corner_1_top, g.left, g.top, g.left, g.down);
