@@ -167,7 +167,7 @@ def run_reference(args, rank, world):
                       "data": "synthetic", "config": workload_config(args.gpus),
                       "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
                       "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                      "enumerated_per_s": n_enum * args.steps / tot, "gpu_launches": 0}))
+                      "enumerated_per_s": n_enum * args.steps / tot, "gpu_launches": 0}), flush=True)
 
 
 def pinned(a):
@@ -342,7 +342,8 @@ def run_ours(args, rank, local_rank, world):
                                                  "sample": "%d linearisations of the config#4 graph" % r}
             except Exception as e:
                 out["cpu_baseline"] = {"error": str(e)}
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)  # flush: under torchrun stdout is a block-buffered pipe/file
+        sys.stdout.flush()
     ctx.close()
     if world > 1:
         dist.barrier()
