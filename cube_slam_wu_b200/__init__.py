@@ -58,7 +58,7 @@ class DetectStats(C.Structure):
     _fields_ = [("n_enumerated", C.c_int64), ("n_scored", C.c_int64), ("n_kept", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("n_kernel_launches", C.c_int32), ("n_tasks_smem_map", C.c_int32),
                 ("gpu_ms_prep", C.c_float), ("gpu_ms_score", C.c_float), ("gpu_ms_select", C.c_float), ("gpu_ms_recover", C.c_float),
-                ("gpu_ms_rank", C.c_float), ("reserved_f", C.c_float)]
+                ("gpu_ms_rank", C.c_float), ("gpu_ms_distmap", C.c_float)]
 
 
 class BAGraph(C.Structure):
@@ -169,6 +169,32 @@ class Context:
         self._chk(lib().csb_detect_batch(*self._args(frames, boxes, lines, tasks, n_tasks, dist_maps, n_map_floats, params), cub, _p(ncub),
                                          C.byref(st) if want_stats else None))
         return cub, ncub[:nb], st
+
+    def detect_batch_gray(self, frames, boxes, lines, tasks, n_tasks, gray, params, want_stats=True):
+        """csb_detect_batch_gray(): like detect_batch but from packed uint8 gray frames (Canny + distance transform on the GPU)."""
+        nb = boxes.shape[0]
+        kmax = params.max_cuboid_num
+        cub = (Cuboid * max(nb * kmax, 1))()
+        ncub = np.zeros(max(nb, 1), np.int32)
+        st = DetectStats()
+        self._nb, self._kmax = nb, kmax
+        self._chk(lib().csb_detect_batch_gray(self._h, frames, len(frames), _p(boxes), nb, _p(lines), lines.shape[0], tasks, n_tasks, _p(gray),
+                                              C.c_int64(gray.size), C.byref(params), cub, _p(ncub), C.byref(st) if want_stats else None))
+        return cub, ncub[:nb], st
+
+    def detect_upload_gray(self, frames, boxes, lines, tasks, n_tasks, gray, params):
+        self._nb, self._kmax = boxes.shape[0], params.max_cuboid_num
+        self._chk(lib().csb_detect_upload_gray(self._h, frames, len(frames), _p(boxes), boxes.shape[0], _p(lines), lines.shape[0], tasks, n_tasks, _p(gray),
+                                               C.c_int64(gray.size), C.byref(params)))
+
+    def debug_map(self, task_index, task, edges=False):
+        """Distance map (and optionally the 0/1/2 Canny map) of tasks[task_index] after a run."""
+        n = task.roi_width * task.roi_height
+        dm = np.zeros(n, np.float32)
+        ed = np.zeros(n, np.uint8) if edges else None
+        self._chk(lib().csb_detect_debug_map(self._h, int(task_index), _p(dm), _p(ed), n))
+        shape = (task.roi_height, task.roi_width)
+        return (dm.reshape(shape), ed.reshape(shape)) if edges else dm.reshape(shape)
 
     def detect_upload(self, frames, boxes, lines, tasks, n_tasks, dist_maps, n_map_floats, params):
         self._nb, self._kmax = boxes.shape[0], params.max_cuboid_num

@@ -31,7 +31,7 @@ int csb_create(csb_context** out, int device_ordinal) {
     c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return CSB_ERR_CUDA; }
     c->own_stream = true;
-    for (int i = 0; i < 6; i++) cudaEventCreate(&c->det.ev[i]);
+    for (int i = 0; i < 7; i++) cudaEventCreate(&c->det.ev[i]);
     *out = c;
     return CSB_OK;
 }
@@ -43,9 +43,9 @@ void csb_destroy(csb_context* c) {
     DetectState& d = c->det;
     DevBuf* bufs[] = {&d.d_ftab, &d.d_ttab, &d.d_order, &d.d_box_begin, &d.d_lines, &d.d_maps, &d.d_ml_seg, &d.d_ml_ang, &d.d_ml_mid, &d.d_n_merged,
                       &d.d_p_dist, &d.d_p_angle, &d.d_p_hyp, &d.d_n_valid, &d.d_keep, &d.d_norm, &d.d_n_keep, &d.d_cand_score, &d.d_cand_ok,
-                      &d.d_sel_idx, &d.d_sel_flag, &d.d_sel_heap, &d.d_rank_idx, &d.d_cuboids, &d.d_n_cuboids, &d.d_counters, &d.d_dbg};
+                      &d.d_sel_idx, &d.d_sel_flag, &d.d_sel_heap, &d.d_rank_idx, &d.d_cuboids, &d.d_n_cuboids, &d.d_counters, &d.d_dbg, &d.d_gray, &d.d_cmap, &d.d_queue, &d.d_dtmp};
     for (DevBuf* b : bufs) b->release();
-    for (int i = 0; i < 6; i++)
+    for (int i = 0; i < 7; i++)
         if (d.ev[i]) cudaEventDestroy(d.ev[i]);
     ba_release(c->ba);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -84,10 +84,13 @@ int csb_detect_plan(const csb_frame* frames, int n_frames, const double* boxes, 
     return CSB_OK;
 }
 
-int csb_detect_upload(csb_context* c, const csb_frame* frames, int n_frames, const double* boxes, int n_boxes, const double* lines, int n_lines,
-                      const csb_task* tasks, int n_tasks, const float* dist_maps, int64_t n_map_floats, const csb_detect_params* params) {
+// Shared by csb_detect_upload (caller-computed distance maps) and csb_detect_upload_gray (gray frames; Canny + distance
+// transform run on the device at the start of every csb_detect_run).
+static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_frames, const double* boxes, int n_boxes, const double* lines, int n_lines,
+                              const csb_task* tasks, int n_tasks, const float* dist_maps, int64_t n_map_floats, const uint8_t* gray, int64_t n_gray_bytes,
+                              const csb_detect_params* params) {
     if (!c) return CSB_ERR_INVALID;
-    if (!frames || n_frames <= 0 || !params || (!boxes && n_boxes > 0) || (!lines && n_lines > 0) || (!dist_maps && n_map_floats > 0)) {
+    if (!frames || n_frames <= 0 || !params || (!boxes && n_boxes > 0) || (!lines && n_lines > 0) || (!dist_maps && !gray && n_map_floats > 0)) {
         c->err = "csb_detect_upload: null argument";
         return CSB_ERR_INVALID;
     }
@@ -113,6 +116,11 @@ int csb_detect_upload(csb_context* c, const csb_frame* frames, int n_frames, con
         d.max_groups = std::max(d.max_groups, d.ftab[f].n_roll * d.ftab[f].n_pitch * d.ftab[f].n_yaw);
         d.max_lines_per_frame = std::max(d.max_lines_per_frame, frames[f].line_end - frames[f].line_begin);
     }
+    // gray frames are packed back to back (img_height x img_width bytes each)
+    int64_t gray_total = 0;
+    for (int f = 0; f < n_frames; f++) { d.ftab[f].gray_offset = gray_total; gray_total += (int64_t)frames[f].img_width * frames[f].img_height; }
+    d.gray_mode = gray != nullptr;
+    if (d.gray_mode && n_gray_bytes != gray_total) { c->err = "csb_detect_upload_gray: n_gray_bytes != sum of img_width*img_height"; return CSB_ERR_INVALID; }
     d.n_frames = n_frames; d.n_boxes = n_boxes; d.n_lines = n_lines; d.n_tasks = n_tasks; d.n_map_floats = nm;
     d.out_total = 0; d.line_cap_total = 0; d.max_hyp_per_task = 1;
     for (const TaskTab& t : d.ttab) {
@@ -158,6 +166,12 @@ int csb_detect_upload(csb_context* c, const csb_frame* frames, int n_frames, con
     CSB_CUDA(c, d.d_cuboids.ensure(sizeof(csb_cuboid) * (size_t)std::max(n_boxes, 1) * kmax));
     CSB_CUDA(c, d.d_n_cuboids.ensure(4 * (size_t)std::max(n_boxes, 1)));
     CSB_CUDA(c, d.d_counters.ensure(64));
+    if (d.gray_mode) {
+        CSB_CUDA(c, d.d_gray.ensure((size_t)gray_total + 64));
+        CSB_CUDA(c, d.d_cmap.ensure((size_t)nm + 64));
+        CSB_CUDA(c, d.d_queue.ensure(4 * (size_t)nm + 64));
+        CSB_CUDA(c, d.d_dtmp.ensure(4 * (size_t)nm + 64));
+    }
 
     cudaStream_t st = c->stream;
     CSB_CUDA(c, cudaMemcpyAsync(d.d_ftab.p, d.ftab.data(), sizeof(FrameTab) * n_frames, cudaMemcpyHostToDevice, st));
@@ -167,10 +181,12 @@ int csb_detect_upload(csb_context* c, const csb_frame* frames, int n_frames, con
     }
     CSB_CUDA(c, cudaMemcpyAsync(d.d_box_begin.p, box_begin.data(), 4 * (size_t)(n_boxes + 1), cudaMemcpyHostToDevice, st));
     if (n_lines) CSB_CUDA(c, cudaMemcpyAsync(d.d_lines.p, lines, 32 * (size_t)n_lines, cudaMemcpyHostToDevice, st));
-    if (nm) CSB_CUDA(c, cudaMemcpyAsync(d.d_maps.p, dist_maps, 4 * (size_t)nm, cudaMemcpyHostToDevice, st));
+    if (d.gray_mode) { if (gray_total) CSB_CUDA(c, cudaMemcpyAsync(d.d_gray.p, gray, (size_t)gray_total, cudaMemcpyHostToDevice, st)); }
+    else if (nm) CSB_CUDA(c, cudaMemcpyAsync(d.d_maps.p, dist_maps, 4 * (size_t)nm, cudaMemcpyHostToDevice, st));
     // the small host vectors above are pageable and go out of scope: make sure they are consumed
     CSB_CUDA(c, cudaStreamSynchronize(st));
-    d.h2d_bytes = (int64_t)(sizeof(FrameTab) * n_frames + (sizeof(TaskTab) + 4) * (size_t)n_tasks + 4 * (size_t)(n_boxes + 1) + 32 * (size_t)n_lines + 4 * (size_t)nm);
+    d.h2d_bytes = (int64_t)(sizeof(FrameTab) * n_frames + (sizeof(TaskTab) + 4) * (size_t)n_tasks + 4 * (size_t)(n_boxes + 1) + 32 * (size_t)n_lines +
+                            (d.gray_mode ? (size_t)gray_total : 4 * (size_t)nm));
 
     DetectBuffers& B = d.B;
     B.ftab = d.d_ftab.as<FrameTab>(); B.ttab = d.d_ttab.as<TaskTab>(); B.task_order = d.d_order.as<int>(); B.box_task_begin = d.d_box_begin.as<int>();
@@ -188,6 +204,22 @@ int csb_detect_upload(csb_context* c, const csb_frame* frames, int n_frames, con
     return CSB_OK;
 }
 
+int csb_detect_upload(csb_context* c, const csb_frame* frames, int n_frames, const double* boxes, int n_boxes, const double* lines, int n_lines,
+                      const csb_task* tasks, int n_tasks, const float* dist_maps, int64_t n_map_floats, const csb_detect_params* params) {
+    return detect_upload_impl(c, frames, n_frames, boxes, n_boxes, lines, n_lines, tasks, n_tasks, dist_maps, n_map_floats, nullptr, 0, params);
+}
+
+int csb_detect_upload_gray(csb_context* c, const csb_frame* frames, int n_frames, const double* boxes, int n_boxes, const double* lines, int n_lines,
+                           const csb_task* tasks, int n_tasks, const uint8_t* gray, int64_t n_gray_bytes, const csb_detect_params* params) {
+    if (!c) return CSB_ERR_INVALID;
+    if (!gray) { c->err = "csb_detect_upload_gray: null gray buffer"; return CSB_ERR_INVALID; }
+    int nt = 0;
+    int64_t nm = 0;
+    int rc = csb_detect_plan(frames, n_frames, boxes, n_boxes, params, nullptr, 0, &nt, &nm);
+    if (rc != CSB_OK) { c->err = "csb_detect_upload_gray: planning failed"; return rc; }
+    return detect_upload_impl(c, frames, n_frames, boxes, n_boxes, lines, n_lines, tasks, n_tasks, nullptr, nm, gray, n_gray_bytes, params);
+}
+
 int csb_detect_run(csb_context* c, int timed) {
     if (!c) return CSB_ERR_INVALID;
     DetectState& d = c->det;
@@ -198,6 +230,10 @@ int csb_detect_run(csb_context* c, int timed) {
     d.timed_last = timed != 0;
     if (d.n_tasks > 0) {
         CSB_CUDA(c, cudaMemsetAsync(d.d_counters.p, 0, 64, st));
+        if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[6], st));
+        if (d.gray_mode) {
+            CSB_CUDA(c, launch_distmaps(d.B, d.d_gray.as<uint8_t>(), d.d_cmap.as<uint8_t>(), d.d_queue.as<int>(), d.d_dtmp.as<unsigned>(), d.d_maps.as<float>(), st));
+        }
         if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[0], st));
         CSB_CUDA(c, launch_prep_lines(d.B, d.max_lines_per_frame, st));
         if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[1], st));
@@ -208,8 +244,9 @@ int csb_detect_run(csb_context* c, int timed) {
         if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[3], st));
         CSB_CUDA(c, launch_recover(d.B, st));
         if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[4], st));
-        d.launches_last = 3 + nsel;
+        d.launches_last = 3 + nsel + (d.gray_mode ? 3 : 0);
     } else if (timed) {
+        CSB_CUDA(c, cudaEventRecord(d.ev[6], st));
         for (int i = 0; i < 5; i++) CSB_CUDA(c, cudaEventRecord(d.ev[i], st));
     }
     if (d.n_boxes > 0) {
@@ -254,6 +291,7 @@ int csb_detect_download(csb_context* c, csb_cuboid* cuboids_out, int32_t* n_cubo
             cudaEventElapsedTime(&stats->gpu_ms_select, d.ev[2], d.ev[3]);
             cudaEventElapsedTime(&stats->gpu_ms_recover, d.ev[3], d.ev[4]);
             cudaEventElapsedTime(&stats->gpu_ms_rank, d.ev[4], d.ev[5]);
+            cudaEventElapsedTime(&stats->gpu_ms_distmap, d.ev[6], d.ev[0]);
         }
     }
     return CSB_OK;
@@ -267,6 +305,34 @@ int csb_detect_batch(csb_context* c, const csb_frame* frames, int n_frames, cons
     rc = csb_detect_run(c, stats != nullptr);
     if (rc != CSB_OK) return rc;
     return csb_detect_download(c, cuboids_out, n_cuboids_out, stats);
+}
+
+int csb_detect_batch_gray(csb_context* c, const csb_frame* frames, int n_frames, const double* boxes, int n_boxes, const double* lines, int n_lines,
+                          const csb_task* tasks, int n_tasks, const uint8_t* gray, int64_t n_gray_bytes, const csb_detect_params* params,
+                          csb_cuboid* cuboids_out, int32_t* n_cuboids_out, csb_detect_stats* stats) {
+    int rc = csb_detect_upload_gray(c, frames, n_frames, boxes, n_boxes, lines, n_lines, tasks, n_tasks, gray, n_gray_bytes, params);
+    if (rc != CSB_OK) return rc;
+    rc = csb_detect_run(c, stats != nullptr);
+    if (rc != CSB_OK) return rc;
+    return csb_detect_download(c, cuboids_out, n_cuboids_out, stats);
+}
+
+int csb_detect_debug_map(csb_context* c, int task_id, float* dist_map_out, uint8_t* edges_out, int capacity) {
+    if (!c) return CSB_ERR_INVALID;
+    DetectState& d = c->det;
+    if (!d.ran) { c->err = "debug before run"; return CSB_ERR_STATE; }
+    if (task_id < 0 || task_id >= d.n_tasks) return CSB_ERR_INVALID;
+    const TaskTab& t = d.ttab[task_id];
+    const int n = t.roi_w * t.roi_h;
+    if (n > capacity) return CSB_ERR_CAPACITY;
+    CSB_CUDA(c, cudaSetDevice(c->device));
+    CSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (dist_map_out) CSB_CUDA(c, cudaMemcpy(dist_map_out, d.d_maps.as<float>() + t.map_offset, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    if (edges_out) {
+        if (!d.gray_mode) { c->err = "edge maps exist only after csb_detect_upload_gray"; return CSB_ERR_STATE; }
+        CSB_CUDA(c, cudaMemcpy(edges_out, d.d_cmap.as<uint8_t>() + t.map_offset, (size_t)n, cudaMemcpyDeviceToHost));
+    }
+    return CSB_OK;
 }
 
 int csb_detect_debug_task(csb_context* c, int task_id, int32_t* n_valid, int32_t* n_merged, int32_t* n_keep, int32_t* hyp_id, double* dist_err,

@@ -43,8 +43,9 @@ struct DetectState {
     csb::DetectBuffers B{};
     DevBuf d_ftab, d_ttab, d_order, d_box_begin, d_lines, d_maps, d_ml_seg, d_ml_ang, d_ml_mid, d_n_merged, d_p_dist, d_p_angle, d_p_hyp,
         d_n_valid, d_keep, d_norm, d_n_keep, d_cand_score, d_cand_ok, d_sel_idx, d_sel_flag, d_sel_heap, d_rank_idx, d_cuboids, d_n_cuboids,
-        d_counters, d_dbg;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        d_counters, d_dbg, d_gray, d_cmap, d_queue, d_dtmp;
+    bool gray_mode = false;
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool timed_last = false;
     int64_t h2d_bytes = 0, d2h_bytes = 0;
     int launches_last = 0;

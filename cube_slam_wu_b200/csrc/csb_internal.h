@@ -22,6 +22,7 @@ struct FrameTab {
     double Tnew[MAX_PAIRS][12];   // top three rows of transToWolrd_new (row-major 3x4); row 3 is 0 0 0 1
     int32_t n_roll, n_pitch, n_yaw, sample_rp;
     int32_t line_begin, line_end, img_w, img_h;
+    int64_t gray_offset;  // byte offset of this frame in the packed gray buffer (csb_detect_upload_gray)
 };
 
 // Per-(box, height sample) task geometry: the integer logic of box_proposal_detail.cpp:143-256.

@@ -221,3 +221,22 @@ def make_ba_graph(n_cam=200, n_cube=50, obs_per_cube=80, seed=20260926, with_pro
         ok = np.array(ep_ok)[order]  # EdgeSE3CuboidProj only where the cuboid is fully in front of the camera
         out["ep"] = (ec_cam[ok].copy(), ec_cube[ok].copy(), np.array(ep_meas)[order][ok], np.array(ep_info)[order][ok], np.array(ep_K)[order][ok])
     return out
+
+
+def dist_map_for_roi_reference(gray, left, top, width, height, return_edges=False):
+    """What the reference's C++ computes for `cv::Canny(gray_img(object_bbox), ...)` + `cv::distanceTransform(..., CV_DIST_L2, 3)`
+    (box_proposal_detail.cpp:320-327): on a cv::Mat ROI *view* the Sobel filter of cv::Canny sees the ROI's real neighbours inside the
+    parent image (python slices lose that), and OpenCV's own 3x3 chamfer transform is the fixed-point one (a cv2 build with IPP swaps in
+    a closed-source float variant, so IPP is switched off around the call).  This is the parity target of the GPU path (distmap.cu)."""
+    import cv2
+    dx = cv2.Sobel(gray, cv2.CV_16S, 1, 0, ksize=3, borderType=cv2.BORDER_REPLICATE)
+    dy = cv2.Sobel(gray, cv2.CV_16S, 0, 1, ksize=3, borderType=cv2.BORDER_REPLICATE)
+    sl = (slice(top, top + height), slice(left, left + width))
+    edges = cv2.Canny(np.ascontiguousarray(dx[sl]), np.ascontiguousarray(dy[sl]), 80, 200)
+    ipp = cv2.ipp.useIPP()
+    cv2.ipp.setUseIPP(False)
+    try:
+        dm = cv2.distanceTransform(255 - edges, cv2.DIST_L2, 3).astype(np.float32)
+    finally:
+        cv2.ipp.setUseIPP(ipp)
+    return (dm, edges) if return_edges else dm

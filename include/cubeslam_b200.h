@@ -106,7 +106,7 @@ typedef struct csb_detect_stats {
     int64_t n_kept;       /* proposals that survived fuse_normalize_scores_v2 */
     int64_t h2d_bytes, d2h_bytes;
     int32_t n_kernel_launches, n_tasks_smem_map; /* tasks whose distance map was staged in shared memory */
-    float gpu_ms_prep, gpu_ms_score, gpu_ms_select, gpu_ms_recover, gpu_ms_rank, reserved_f; /* CUDA-event times of the last timed run */
+    float gpu_ms_prep, gpu_ms_score, gpu_ms_select, gpu_ms_recover, gpu_ms_rank, gpu_ms_distmap; /* CUDA-event times of the last timed run */
 } csb_detect_stats;
 
 /* Host-only integer logic of box_proposal_detail.cpp:143-256: enumerates tasks and ROI rectangles.
@@ -128,6 +128,20 @@ int csb_detect_upload(csb_context* ctx, const csb_frame* frames, int n_frames, c
                       const csb_detect_params* params);
 int csb_detect_run(csb_context* ctx, int timed);
 int csb_detect_download(csb_context* ctx, csb_cuboid* cuboids_out, int32_t* n_cuboids_out, csb_detect_stats* stats);
+
+/* Gray-frame variants: instead of caller-computed distance maps the caller passes the 8-bit gray frames
+ * (img_height x img_width bytes each, packed in frame order).  Every csb_detect_run() then starts with, per task ROI,
+ *   cv::Canny(gray(roi), e, 80, 200)  +  cv::distanceTransform(255 - e, dist, CV_DIST_L2, 3)      (box_proposal_detail.cpp:320-327)
+ * computed on the device with OpenCV's own algorithms (Sobel 3x3 that sees the ROI's true neighbours like a cv::Mat ROI view,
+ * L1 magnitude, NMS, hysteresis; 16.16 fixed-point 3x3 chamfer transform) -- bit-identical to cv2 4.13 with IPP disabled. */
+int csb_detect_upload_gray(csb_context* ctx, const csb_frame* frames, int n_frames, const double* boxes, int n_boxes, const double* lines,
+                           int n_lines, const csb_task* tasks, int n_tasks, const uint8_t* gray, int64_t n_gray_bytes,
+                           const csb_detect_params* params);
+int csb_detect_batch_gray(csb_context* ctx, const csb_frame* frames, int n_frames, const double* boxes, int n_boxes, const double* lines,
+                          int n_lines, const csb_task* tasks, int n_tasks, const uint8_t* gray, int64_t n_gray_bytes,
+                          const csb_detect_params* params, csb_cuboid* cuboids_out, int32_t* n_cuboids_out, csb_detect_stats* stats);
+/* Parity/debug: the distance map (and, in gray mode, the 0/1/2 Canny map: 2 = edge) of one task after a run. */
+int csb_detect_debug_map(csb_context* ctx, int task_id, float* dist_map_out, uint8_t* edges_out, int capacity);
 
 /* Per-box observation records for camera-object graph assembly (object_slam/src/main_obj.cpp:643-679, :732): the best
  * cuboid of each 2D box as a g2o::cuboid measurement in the local camera frame.  Writes n_boxes x 16 doubles into a

@@ -1,0 +1,72 @@
+"""GPU parity of the Canny + distance-transform stage (SURVEY.md 8 "next" row f-1): csb_detect_batch_gray vs python cv2 4.13.
+
+Parity target = what the reference's C++ computes (box_proposal_detail.cpp:320-327) with OpenCV's open-source algorithms:
+Sobel on the parent image (a cv::Mat ROI view sees its real neighbours), cv::Canny(dx, dy, 80, 200) on the ROI, fixed-point 3x3
+chamfer distance transform (cv2 with IPP disabled).  Bar: Canny map and float32 distance map bit-exact; the scored path fed by the
+GPU maps then matches the oracle fed by the cv2 maps exactly as in test_proposal_gpu.py."""
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _gray(batch):
+    return np.ascontiguousarray(np.concatenate([im.ravel() for im in batch["images"]]).astype(np.uint8))
+
+
+def _run_gray(ctx, csb, batch, params):
+    from cube_slam_wu_b200 import synth
+    frames = csb.make_frames(batch["K"], batch["T"], batch["img_w"], batch["img_h"], batch["box_ranges"], batch["line_ranges"])
+    boxes = np.ascontiguousarray(batch["boxes"], np.float64).reshape(-1, 5)
+    lines = np.ascontiguousarray(batch["lines"], np.float64).reshape(-1, 4)
+    tasks, n_tasks, n_map = csb.detect_plan(frames, boxes, params)
+    cub, ncub, st = ctx.detect_batch_gray(frames, boxes, lines, tasks, n_tasks, _gray(batch), params)
+    worst = 0.0
+    for i in range(n_tasks):
+        t = tasks[i]
+        dm, ed = ctx.debug_map(i, t, edges=True)
+        ref_dm, ref_ed = synth.dist_map_for_roi_reference(batch["images"][t.frame_id], t.roi_left, t.roi_top, t.roi_width, t.roi_height, return_edges=True)
+        assert np.array_equal((ed == 2), ref_ed > 0), "task %d: Canny map differs in %d px" % (i, int(((ed == 2) != (ref_ed > 0)).sum()))
+        assert np.array_equal(dm, ref_dm), "task %d: distance map differs, max %g" % (i, float(np.abs(dm - ref_dm).max()))
+        worst = max(worst, float(dm.max()))
+    return cub, ncub, st, tasks, n_tasks
+
+
+def test_maps_and_cuboids_kitti(ctx, csb):
+    from cube_slam_wu_b200 import synth
+    batch = synth.make_kitti_batch(3, seed=77)
+    p = csb.DetectParams.default()
+    cub, ncub, st, tasks, n_tasks = _run_gray(ctx, csb, batch, p)
+    assert st.gpu_ms_distmap > 0
+    # scored path on top of the GPU maps == oracle on top of the cv2 maps
+    imgs = batch["images"]
+    batch["map_fn"] = lambda f, l, t, w, h: synth.dist_map_for_roi_reference(imgs[f], l, t, w, h)
+    ora = H.run_oracle(batch, p, leak=0)
+    H.compare_with_oracle(ctx, csb, batch, p, cub, ncub, ora)
+
+
+def test_noise_frames_and_image_borders(ctx, csb):
+    """Dense edges (uniform noise) and ROIs clamped at the image border (BORDER_REPLICATE there, real neighbours elsewhere)."""
+    from cube_slam_wu_b200 import synth
+    rng = np.random.default_rng(5)
+    batch = synth.make_kitti_batch(2, seed=78)
+    W, Hh = batch["img_w"], batch["img_h"]
+    batch["images"] = [rng.integers(0, 256, (Hh, W)).astype(np.uint8), (rng.integers(0, 2, (Hh, W)) * 255).astype(np.uint8)]
+    b0 = batch["box_ranges"][0][0]
+    batch["boxes"][b0] = [0, 0, 150, 120, 0.5]
+    batch["boxes"][b0 + 1] = [W - 201, Hh - 141, 200, 140, 0.5]
+    batch["boxes"][b0 + 2] = [3, Hh - 90, 130, 85, 0.5]
+    _run_gray(ctx, csb, batch, csb.DetectParams.default())
+
+
+def test_blank_and_single_edge_rois(ctx, csb):
+    """No edge pixel at all in a ROI (distance saturates at DIST_MAX) and a single vertical step edge."""
+    from cube_slam_wu_b200 import synth
+    batch = synth.make_kitti_batch(2, seed=79)
+    W, Hh = batch["img_w"], batch["img_h"]
+    blank = np.full((Hh, W), 90, np.uint8)
+    step = np.full((Hh, W), 20, np.uint8); step[:, W // 2:] = 220
+    batch["images"] = [blank, step]
+    _run_gray(ctx, csb, batch, csb.DetectParams.default(whether_sample_bbox_height=1))
