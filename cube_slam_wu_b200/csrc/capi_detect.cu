@@ -122,11 +122,12 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
     d.gray_mode = gray != nullptr;
     if (d.gray_mode && n_gray_bytes != gray_total) { c->err = "csb_detect_upload_gray: n_gray_bytes != sum of img_width*img_height"; return CSB_ERR_INVALID; }
     d.n_frames = n_frames; d.n_boxes = n_boxes; d.n_lines = n_lines; d.n_tasks = n_tasks; d.n_map_floats = nm;
-    d.out_total = 0; d.line_cap_total = 0; d.max_hyp_per_task = 1;
+    d.out_total = 0; d.line_cap_total = 0; d.max_hyp_per_task = 1; d.max_roi_w = 1;
     for (const TaskTab& t : d.ttab) {
         d.out_total = std::max<int64_t>(d.out_total, t.out_offset + t.n_hyp);
         d.line_cap_total = std::max<int64_t>(d.line_cap_total, (int64_t)t.line_cap_offset + (d.ftab[t.frame_id].line_end - d.ftab[t.frame_id].line_begin));
         d.max_hyp_per_task = std::max(d.max_hyp_per_task, t.n_hyp);
+        d.max_roi_w = std::max(d.max_roi_w, t.roi_w);
     }
     // task queue: biggest first; box -> task range
     std::vector<int> order(n_tasks);
@@ -232,7 +233,7 @@ int csb_detect_run(csb_context* c, int timed) {
         CSB_CUDA(c, cudaMemsetAsync(d.d_counters.p, 0, 64, st));
         if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[6], st));
         if (d.gray_mode) {
-            CSB_CUDA(c, launch_distmaps(d.B, d.d_gray.as<uint8_t>(), d.d_cmap.as<uint8_t>(), d.d_queue.as<int>(), d.d_dtmp.as<unsigned>(), d.d_maps.as<float>(), st));
+            CSB_CUDA(c, launch_distmaps(d.B, d.d_gray.as<uint8_t>(), d.d_cmap.as<uint8_t>(), d.d_queue.as<int>(), d.d_dtmp.as<unsigned>(), d.d_maps.as<float>(), d.max_roi_w, st));
         }
         if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[0], st));
         CSB_CUDA(c, launch_prep_lines(d.B, d.max_lines_per_frame, st));

@@ -14,8 +14,8 @@
 //
 //   k_canny_nms  : per ROI pixel: Sobel at the pixel and at the two neighbours its gradient direction selects -> 0 weak / 1 no / 2 strong
 //   k_canny_hyst : per task: breadth-first promotion of weak pixels 8-connected to strong ones (work list in global memory)
-//   k_dist3x3    : per task: forward / backward chamfer passes; each row is a min-plus prefix scan
-//                  d[j] = min_m (c[m] + a (j - m)) done with warp shuffles, rows are sequential
+//   k_dist3x3    : one warp per task: forward / backward chamfer passes; each row is a min-plus prefix scan
+//                  d[j] = min_m (c[m] + a (j - m)) done with warp shuffles, previous row in registers, rows sequential
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -124,109 +124,134 @@ __global__ void __launch_bounds__(256) k_canny_hyst(DetectBuffers B, uint8_t* cm
 constexpr unsigned DT_HV = 62587u;                 // cvRound(0.955f  * 65536)
 constexpr unsigned DT_DG = 89738u;                 // cvRound(1.3693f * 65536)
 constexpr unsigned DT_MAX = 0xffffffffu - DT_DG;   // DIST_MAX; also used for the border cells (behaves like OpenCV's INIT_DIST0)
-constexpr int DT_THREADS = 256;
+constexpr int DT_WARPS = 4;  // warps (= tasks) per CTA
 
-// block-wide inclusive prefix-min of one int64 per thread; carry = min of everything before this segment
-__device__ __forceinline__ long long block_prefix_min(long long v, long long carry, long long* s_agg, int tid, long long& seg_min) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        long long t = __shfl_up_sync(FULL, v, o);
-        if (lane >= o && t < v) v = t;
-    }
-    if (lane == 31) s_agg[warp] = v;
-    __syncthreads();
-    long long pre = carry, tot = carry;
-#pragma unroll
-    for (int w = 0; w < DT_THREADS / 32; w++) {
-        const long long a = s_agg[w];
-        if (w < warp && a < pre) pre = a;
-        if (a < tot) tot = a;
-    }
-    __syncthreads();
-    seg_min = tot;
-    return (pre < v) ? pre : v;
-}
+__device__ __forceinline__ long long shfl_up_ll(long long v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ long long shfl_dn_ll(long long v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 
-// one CTA per task.  tmp = 32-bit fixed-point distances of the whole ROI (global, L2 resident).
-__global__ void __launch_bounds__(DT_THREADS) k_dist3x3(DetectBuffers B, const uint8_t* cmap, unsigned* dtmp, float* maps) {
-    const int task = blockIdx.x, tid = threadIdx.x;
+// One warp per task; lane l owns columns [l*CH, l*CH + CH).  The previous row lives in registers, neighbours' boundary cells come
+// by shuffle, each row is a min-plus scan:  forward  d[j] = min_{m<=j} (c[m] - a m) + a j,   backward  d[j] = min_{m>=j} (c[m] + a m) - a j
+// (a = DT_HV; c = 0 on edge pixels, else the 3-neighbour minimum over the already finished adjacent row).  No block barriers.
+template <int CH>
+__global__ void __launch_bounds__(32 * DT_WARPS) k_dist3x3(DetectBuffers B, const uint8_t* cmap, unsigned* dtmp, float* maps) {
+    const int task = blockIdx.x * DT_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (task >= B.n_tasks) return;
     const TaskTab t = B.ttab[task];
     const int W = t.roi_w, H = t.roi_h;
     const uint8_t* map = cmap + t.map_offset;
     unsigned* tmp = dtmp + t.map_offset;
     float* out = maps + t.map_offset;
-    __shared__ long long s_agg[DT_THREADS / 32];
     const float scale = 1.f / 65536.f;
-    // forward pass: rows top -> bottom, within a row left -> right
+    const long long INF = 0x7fffffffffffffffLL;
+    const int j0 = lane * CH;
+    unsigned prev[CH];
+    // ---- forward pass
+#pragma unroll
+    for (int k = 0; k < CH; k++) prev[k] = DT_MAX;  // row -1 = border
     for (int i = 0; i < H; i++) {
-        const unsigned* up = tmp + (size_t)(i - 1) * W;
-        long long carry = (long long)DT_MAX + DT_HV;  // left border cell at position -1:  INIT - HV * (-1)
-        for (int j0 = 0; j0 < W; j0 += DT_THREADS) {
-            const int j = j0 + tid;
-            long long v = 0x7fffffffffffffffLL;
+        const unsigned pl = __shfl_up_sync(0xffffffffu, prev[CH - 1], 1), pr = __shfl_down_sync(0xffffffffu, prev[0], 1);
+        const unsigned left_in = (lane == 0) ? DT_MAX : pl, right_in = (lane == 31) ? DT_MAX : pr;
+        long long v[CH];
+        long long run = INF;
+#pragma unroll
+        for (int k = 0; k < CH; k++) {
+            const int j = j0 + k;
+            long long x = INF;
             if (j < W) {
                 unsigned c;
                 if (map[(size_t)i * W + j] == 2) c = 0;
                 else {
-                    const unsigned ul = (i > 0 && j > 0) ? up[j - 1] : DT_MAX, u = (i > 0) ? up[j] : DT_MAX, ur = (i > 0 && j + 1 < W) ? up[j + 1] : DT_MAX;
-                    unsigned long long t0 = (unsigned long long)ul + DT_DG, tt = (unsigned long long)u + DT_HV;
+                    const unsigned ul = (k > 0) ? prev[k - 1] : left_in;
+                    const unsigned ur = (k + 1 < CH) ? ((j + 1 < W) ? prev[k + 1] : DT_MAX) : ((j + 1 < W) ? right_in : DT_MAX);
+                    unsigned long long t0 = (unsigned long long)ul + DT_DG, tt = (unsigned long long)prev[k] + DT_HV;
                     if (t0 > tt) t0 = tt;
                     tt = (unsigned long long)ur + DT_DG;
                     if (t0 > tt) t0 = tt;
                     c = (t0 > DT_MAX) ? DT_MAX : (unsigned)t0;
                 }
-                v = (long long)c - (long long)DT_HV * j;
+                x = (long long)c - (long long)DT_HV * j;
             }
-            long long seg;
-            const long long pm = block_prefix_min(v, carry, s_agg, tid, seg);
-            if (j < W) {
-                long long d = pm + (long long)DT_HV * j;
-                tmp[(size_t)i * W + j] = (d > (long long)DT_MAX) ? DT_MAX : (unsigned)d;
-            }
-            carry = seg;
+            if (x < run) run = x;
+            v[k] = run;  // inclusive prefix min inside the chunk
         }
-        __syncthreads();  // row i visible before row i+1 reads it
+        // exclusive prefix min of the chunk minima across lanes; the left border cell (column -1) contributes DT_MAX + a
+        long long inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { long long y = shfl_up_ll(inc, o); if (lane >= o && y < inc) inc = y; }
+        long long excl = shfl_up_ll(inc, 1);
+        if (lane == 0) excl = INF;
+        const long long border = (long long)DT_MAX + DT_HV;
+        if (border < excl) excl = border;
+#pragma unroll
+        for (int k = 0; k < CH; k++) {
+            const int j = j0 + k;
+            long long d = ((excl < v[k]) ? excl : v[k]) + (long long)DT_HV * j;
+            const unsigned dv = (d > (long long)DT_MAX) ? DT_MAX : (unsigned)d;
+            prev[k] = dv;
+            if (j < W) tmp[(size_t)i * W + j] = dv;
+        }
     }
-    // backward pass: rows bottom -> top, within a row right -> left (scan over q = W-1-j)
+    // ---- backward pass
+#pragma unroll
+    for (int k = 0; k < CH; k++) prev[k] = DT_MAX;  // row H = border
+    unsigned self[CH];
+#pragma unroll
+    for (int k = 0; k < CH; k++) { const int j = j0 + k; self[k] = (j < W && H > 0) ? tmp[(size_t)(H - 1) * W + j] : DT_MAX; }
     for (int i = H - 1; i >= 0; i--) {
-        const unsigned* dn = tmp + (size_t)(i + 1) * W;
-        long long carry = (long long)DT_MAX + DT_HV;
-        for (int q0 = 0; q0 < W; q0 += DT_THREADS) {
-            const int q = q0 + tid, j = W - 1 - q;
-            long long v = 0x7fffffffffffffffLL;
-            if (q < W) {
-                const unsigned self = tmp[(size_t)i * W + j];
-                const unsigned dr = (i + 1 < H && j + 1 < W) ? dn[j + 1] : DT_MAX, d = (i + 1 < H) ? dn[j] : DT_MAX, dl = (i + 1 < H && j > 0) ? dn[j - 1] : DT_MAX;
-                unsigned long long t0 = self, tt = (unsigned long long)dr + DT_DG;
+        unsigned nself[CH];  // prefetch the row above while this one is processed
+#pragma unroll
+        for (int k = 0; k < CH; k++) { const int j = j0 + k; nself[k] = (i > 0 && j < W) ? tmp[(size_t)(i - 1) * W + j] : DT_MAX; }
+        const unsigned pl = __shfl_up_sync(0xffffffffu, prev[CH - 1], 1), pr = __shfl_down_sync(0xffffffffu, prev[0], 1);
+        const unsigned left_in = (lane == 0) ? DT_MAX : pl, right_in = (lane == 31) ? DT_MAX : pr;
+        long long v[CH];
+        long long run = INF;
+#pragma unroll
+        for (int k = CH - 1; k >= 0; k--) {
+            const int j = j0 + k;
+            long long x = INF;
+            if (j < W) {
+                const unsigned dl = (k > 0) ? prev[k - 1] : left_in;
+                const unsigned dr = (k + 1 < CH) ? ((j + 1 < W) ? prev[k + 1] : DT_MAX) : ((j + 1 < W) ? right_in : DT_MAX);
+                unsigned long long t0 = self[k], tt = (unsigned long long)dr + DT_DG;
                 if (t0 > tt) t0 = tt;
-                tt = (unsigned long long)d + DT_HV;
+                tt = (unsigned long long)prev[k] + DT_HV;
                 if (t0 > tt) t0 = tt;
                 tt = (unsigned long long)dl + DT_DG;
                 if (t0 > tt) t0 = tt;
-                v = (long long)t0 - (long long)DT_HV * q;
+                x = (long long)t0 + (long long)DT_HV * j;
             }
-            long long seg;
-            const long long pm = block_prefix_min(v, carry, s_agg, tid, seg);
-            if (q < W) {
-                long long d = pm + (long long)DT_HV * q;
-                const unsigned t0 = (d > (long long)DT_MAX) ? DT_MAX : (unsigned)d;
-                tmp[(size_t)i * W + j] = t0;
-                out[(size_t)i * W + j] = (float)t0 * scale;
-            }
-            carry = seg;
+            if (x < run) run = x;
+            v[k] = run;  // inclusive suffix min inside the chunk
         }
-        __syncthreads();
+        long long inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { long long y = shfl_dn_ll(inc, o); if (lane + o < 32 && y < inc) inc = y; }
+        long long excl = shfl_dn_ll(inc, 1);
+        if (lane == 31) excl = INF;
+        const long long border = (long long)DT_MAX + (long long)DT_HV * W;  // right border cell at column W
+        if (border < excl) excl = border;
+#pragma unroll
+        for (int k = 0; k < CH; k++) {
+            const int j = j0 + k;
+            long long d = ((excl < v[k]) ? excl : v[k]) - (long long)DT_HV * j;
+            const unsigned dv = (d > (long long)DT_MAX) ? DT_MAX : (unsigned)d;
+            prev[k] = (j < W) ? dv : DT_MAX;
+            if (j < W) out[(size_t)i * W + j] = (float)dv * scale;
+            self[k] = nself[k];
+        }
     }
 }
 
-cudaError_t launch_distmaps(const DetectBuffers& B, const uint8_t* gray, uint8_t* cmap, int* queue, unsigned* dtmp, float* maps, cudaStream_t st) {
+cudaError_t launch_distmaps(const DetectBuffers& B, const uint8_t* gray, uint8_t* cmap, int* queue, unsigned* dtmp, float* maps, int max_roi_w, cudaStream_t st) {
     if (B.n_tasks == 0) return cudaSuccess;
     dim3 g(B.n_tasks, 8);
     k_canny_nms<<<g, 256, 0, st>>>(B, gray, cmap, 80, 200);
     k_canny_hyst<<<B.n_tasks, 256, 0, st>>>(B, cmap, queue);
-    k_dist3x3<<<B.n_tasks, DT_THREADS, 0, st>>>(B, cmap, dtmp, maps);
+    const int grid = (B.n_tasks + DT_WARPS - 1) / DT_WARPS;
+    if (max_roi_w <= 32 * 8) k_dist3x3<8><<<grid, 32 * DT_WARPS, 0, st>>>(B, cmap, dtmp, maps);
+    else if (max_roi_w <= 32 * 16) k_dist3x3<16><<<grid, 32 * DT_WARPS, 0, st>>>(B, cmap, dtmp, maps);
+    else if (max_roi_w <= 32 * 40) k_dist3x3<40><<<grid, 32 * DT_WARPS, 0, st>>>(B, cmap, dtmp, maps);
+    else return cudaErrorInvalidValue;  // ROI wider than 1280 px
     return cudaGetLastError();
 }
 
