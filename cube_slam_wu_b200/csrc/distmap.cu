@@ -124,119 +124,114 @@ __global__ void __launch_bounds__(256) k_canny_hyst(DetectBuffers B, uint8_t* cm
 constexpr unsigned DT_HV = 62587u;                 // cvRound(0.955f  * 65536)
 constexpr unsigned DT_DG = 89738u;                 // cvRound(1.3693f * 65536)
 constexpr unsigned DT_MAX = 0xffffffffu - DT_DG;   // DIST_MAX; also used for the border cells (behaves like OpenCV's INIT_DIST0)
-constexpr int DT_WARPS = 4;  // warps (= tasks) per CTA
-
-__device__ __forceinline__ long long shfl_up_ll(long long v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
-__device__ __forceinline__ long long shfl_dn_ll(long long v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+constexpr int DT_WARPS = 4;            // warps (= tasks) per CTA
+constexpr int DT_INF = 0x3fffffff;     // "no path yet" inside the kernel (32-bit arithmetic); becomes DT_MAX on output
 
 // One warp per task; lane l owns columns [l*CH, l*CH + CH).  The previous row lives in registers, neighbours' boundary cells come
 // by shuffle, each row is a min-plus scan:  forward  d[j] = min_{m<=j} (c[m] - a m) + a j,   backward  d[j] = min_{m>=j} (c[m] + a m) - a j
 // (a = DT_HV; c = 0 on edge pixels, else the 3-neighbour minimum over the already finished adjacent row).  No block barriers.
+// 32-bit arithmetic: OpenCV saturates unreachable cells at DIST_MAX (~2^32); with at least one edge pixel in the ROI every final
+// value is a real path length (< 2^27 for ROIs up to 1280 px), and saturated cells only ever lose comparisons, so any "infinity"
+// that survives the additions gives the same result.  A ROI without edge pixels ends at DT_INF everywhere -> DIST_MAX, as in OpenCV.
+// Only tasks with w_lo < roi_w <= 32*CH are handled by an instantiation (one launch per width class).
 template <int CH>
-__global__ void __launch_bounds__(32 * DT_WARPS) k_dist3x3(DetectBuffers B, const uint8_t* cmap, unsigned* dtmp, float* maps) {
+__global__ void __launch_bounds__(32 * DT_WARPS) k_dist3x3(DetectBuffers B, const uint8_t* cmap, int* dtmp, float* maps, int w_lo) {
     const int task = blockIdx.x * DT_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (task >= B.n_tasks) return;
     const TaskTab t = B.ttab[task];
     const int W = t.roi_w, H = t.roi_h;
+    if (W <= w_lo || W > 32 * CH) return;
     const uint8_t* map = cmap + t.map_offset;
-    unsigned* tmp = dtmp + t.map_offset;
+    int* tmp = dtmp + t.map_offset;
     float* out = maps + t.map_offset;
     const float scale = 1.f / 65536.f;
-    const long long INF = 0x7fffffffffffffffLL;
+    const int HV = (int)DT_HV, DG = (int)DT_DG;
     const int j0 = lane * CH;
-    unsigned prev[CH];
+    int prev[CH];
     // ---- forward pass
 #pragma unroll
-    for (int k = 0; k < CH; k++) prev[k] = DT_MAX;  // row -1 = border
+    for (int k = 0; k < CH; k++) prev[k] = DT_INF;  // row -1 = border
+    uint8_t feat[CH], nfeat[CH];
+#pragma unroll
+    for (int k = 0; k < CH; k++) { const int j = j0 + k; feat[k] = (j < W) ? map[j] : 1; }
     for (int i = 0; i < H; i++) {
-        const unsigned pl = __shfl_up_sync(0xffffffffu, prev[CH - 1], 1), pr = __shfl_down_sync(0xffffffffu, prev[0], 1);
-        const unsigned left_in = (lane == 0) ? DT_MAX : pl, right_in = (lane == 31) ? DT_MAX : pr;
-        long long v[CH];
-        long long run = INF;
+#pragma unroll
+        for (int k = 0; k < CH; k++) { const int j = j0 + k; nfeat[k] = (i + 1 < H && j < W) ? map[(size_t)(i + 1) * W + j] : 1; }  // prefetch
+        const int pl = __shfl_up_sync(0xffffffffu, prev[CH - 1], 1), pr = __shfl_down_sync(0xffffffffu, prev[0], 1);
+        const int left_in = (lane == 0) ? DT_INF : pl, right_in = (lane == 31) ? DT_INF : pr;
+        int v[CH];
+        int run = 0x7fffffff;
 #pragma unroll
         for (int k = 0; k < CH; k++) {
             const int j = j0 + k;
-            long long x = INF;
+            int x = 0x7fffffff;
             if (j < W) {
-                unsigned c;
-                if (map[(size_t)i * W + j] == 2) c = 0;
+                int c;
+                if (feat[k] == 2) c = 0;
                 else {
-                    const unsigned ul = (k > 0) ? prev[k - 1] : left_in;
-                    const unsigned ur = (k + 1 < CH) ? ((j + 1 < W) ? prev[k + 1] : DT_MAX) : ((j + 1 < W) ? right_in : DT_MAX);
-                    unsigned long long t0 = (unsigned long long)ul + DT_DG, tt = (unsigned long long)prev[k] + DT_HV;
-                    if (t0 > tt) t0 = tt;
-                    tt = (unsigned long long)ur + DT_DG;
-                    if (t0 > tt) t0 = tt;
-                    c = (t0 > DT_MAX) ? DT_MAX : (unsigned)t0;
+                    const int ul = (k > 0) ? prev[k - 1] : left_in;
+                    const int ur = (k + 1 < CH) ? ((j + 1 < W) ? prev[k + 1] : DT_INF) : ((j + 1 < W) ? right_in : DT_INF);
+                    c = min(min(ul + DG, prev[k] + HV), min(ur + DG, DT_INF));
                 }
-                x = (long long)c - (long long)DT_HV * j;
+                x = c - HV * j;
             }
-            if (x < run) run = x;
+            run = min(run, x);
             v[k] = run;  // inclusive prefix min inside the chunk
         }
-        // exclusive prefix min of the chunk minima across lanes; the left border cell (column -1) contributes DT_MAX + a
-        long long inc = run;
+        int inc = run;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { long long y = shfl_up_ll(inc, o); if (lane >= o && y < inc) inc = y; }
-        long long excl = shfl_up_ll(inc, 1);
-        if (lane == 0) excl = INF;
-        const long long border = (long long)DT_MAX + DT_HV;
-        if (border < excl) excl = border;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = min(inc, y); }
+        int excl = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) excl = 0x7fffffff;
+        excl = min(excl, DT_INF + HV);  // left border cell (column -1)
 #pragma unroll
         for (int k = 0; k < CH; k++) {
             const int j = j0 + k;
-            long long d = ((excl < v[k]) ? excl : v[k]) + (long long)DT_HV * j;
-            const unsigned dv = (d > (long long)DT_MAX) ? DT_MAX : (unsigned)d;
-            prev[k] = dv;
+            const int dv = min(min(excl, v[k]) + HV * j, DT_INF);
+            prev[k] = (j < W) ? dv : DT_INF;
             if (j < W) tmp[(size_t)i * W + j] = dv;
+            feat[k] = nfeat[k];
         }
     }
     // ---- backward pass
 #pragma unroll
-    for (int k = 0; k < CH; k++) prev[k] = DT_MAX;  // row H = border
-    unsigned self[CH];
+    for (int k = 0; k < CH; k++) prev[k] = DT_INF;  // row H = border
+    int self[CH];
 #pragma unroll
-    for (int k = 0; k < CH; k++) { const int j = j0 + k; self[k] = (j < W && H > 0) ? tmp[(size_t)(H - 1) * W + j] : DT_MAX; }
+    for (int k = 0; k < CH; k++) { const int j = j0 + k; self[k] = (j < W) ? tmp[(size_t)(H - 1) * W + j] : DT_INF; }
     for (int i = H - 1; i >= 0; i--) {
-        unsigned nself[CH];  // prefetch the row above while this one is processed
+        int nself[CH];  // prefetch the row above while this one is processed
 #pragma unroll
-        for (int k = 0; k < CH; k++) { const int j = j0 + k; nself[k] = (i > 0 && j < W) ? tmp[(size_t)(i - 1) * W + j] : DT_MAX; }
-        const unsigned pl = __shfl_up_sync(0xffffffffu, prev[CH - 1], 1), pr = __shfl_down_sync(0xffffffffu, prev[0], 1);
-        const unsigned left_in = (lane == 0) ? DT_MAX : pl, right_in = (lane == 31) ? DT_MAX : pr;
-        long long v[CH];
-        long long run = INF;
+        for (int k = 0; k < CH; k++) { const int j = j0 + k; nself[k] = (i > 0 && j < W) ? tmp[(size_t)(i - 1) * W + j] : DT_INF; }
+        const int pl = __shfl_up_sync(0xffffffffu, prev[CH - 1], 1), pr = __shfl_down_sync(0xffffffffu, prev[0], 1);
+        const int left_in = (lane == 0) ? DT_INF : pl, right_in = (lane == 31) ? DT_INF : pr;
+        int v[CH];
+        int run = 0x7fffffff;
 #pragma unroll
         for (int k = CH - 1; k >= 0; k--) {
             const int j = j0 + k;
-            long long x = INF;
+            int x = 0x7fffffff;
             if (j < W) {
-                const unsigned dl = (k > 0) ? prev[k - 1] : left_in;
-                const unsigned dr = (k + 1 < CH) ? ((j + 1 < W) ? prev[k + 1] : DT_MAX) : ((j + 1 < W) ? right_in : DT_MAX);
-                unsigned long long t0 = self[k], tt = (unsigned long long)dr + DT_DG;
-                if (t0 > tt) t0 = tt;
-                tt = (unsigned long long)prev[k] + DT_HV;
-                if (t0 > tt) t0 = tt;
-                tt = (unsigned long long)dl + DT_DG;
-                if (t0 > tt) t0 = tt;
-                x = (long long)t0 + (long long)DT_HV * j;
+                const int dl = (k > 0) ? prev[k - 1] : left_in;
+                const int dr = (k + 1 < CH) ? ((j + 1 < W) ? prev[k + 1] : DT_INF) : ((j + 1 < W) ? right_in : DT_INF);
+                const int t0 = min(min(self[k], dr + DG), min(prev[k] + HV, dl + DG));
+                x = t0 + HV * j;
             }
-            if (x < run) run = x;
+            run = min(run, x);
             v[k] = run;  // inclusive suffix min inside the chunk
         }
-        long long inc = run;
+        int inc = run;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { long long y = shfl_dn_ll(inc, o); if (lane + o < 32 && y < inc) inc = y; }
-        long long excl = shfl_dn_ll(inc, 1);
-        if (lane == 31) excl = INF;
-        const long long border = (long long)DT_MAX + (long long)DT_HV * W;  // right border cell at column W
-        if (border < excl) excl = border;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_down_sync(0xffffffffu, inc, o); if (lane + o < 32) inc = min(inc, y); }
+        int excl = __shfl_down_sync(0xffffffffu, inc, 1);
+        if (lane == 31) excl = 0x7fffffff;
+        excl = min(excl, DT_INF + HV * W);  // right border cell (column W)
 #pragma unroll
         for (int k = 0; k < CH; k++) {
             const int j = j0 + k;
-            long long d = ((excl < v[k]) ? excl : v[k]) - (long long)DT_HV * j;
-            const unsigned dv = (d > (long long)DT_MAX) ? DT_MAX : (unsigned)d;
-            prev[k] = (j < W) ? dv : DT_MAX;
-            if (j < W) out[(size_t)i * W + j] = (float)dv * scale;
+            const int dv = min(min(excl, v[k]) - HV * j, DT_INF);
+            prev[k] = (j < W) ? dv : DT_INF;
+            if (j < W) out[(size_t)i * W + j] = (float)((dv >= DT_INF) ? DT_MAX : (unsigned)dv) * scale;
             self[k] = nself[k];
         }
     }
@@ -248,10 +243,11 @@ cudaError_t launch_distmaps(const DetectBuffers& B, const uint8_t* gray, uint8_t
     k_canny_nms<<<g, 256, 0, st>>>(B, gray, cmap, 80, 200);
     k_canny_hyst<<<B.n_tasks, 256, 0, st>>>(B, cmap, queue);
     const int grid = (B.n_tasks + DT_WARPS - 1) / DT_WARPS;
-    if (max_roi_w <= 32 * 8) k_dist3x3<8><<<grid, 32 * DT_WARPS, 0, st>>>(B, cmap, dtmp, maps);
-    else if (max_roi_w <= 32 * 16) k_dist3x3<16><<<grid, 32 * DT_WARPS, 0, st>>>(B, cmap, dtmp, maps);
-    else if (max_roi_w <= 32 * 40) k_dist3x3<40><<<grid, 32 * DT_WARPS, 0, st>>>(B, cmap, dtmp, maps);
-    else return cudaErrorInvalidValue;  // ROI wider than 1280 px
+    if (max_roi_w > 32 * 40) return cudaErrorInvalidValue;  // ROI wider than 1280 px
+    int* itmp = reinterpret_cast<int*>(dtmp);
+    k_dist3x3<8><<<grid, 32 * DT_WARPS, 0, st>>>(B, cmap, itmp, maps, 0);
+    if (max_roi_w > 32 * 8) k_dist3x3<16><<<grid, 32 * DT_WARPS, 0, st>>>(B, cmap, itmp, maps, 32 * 8);
+    if (max_roi_w > 32 * 16) k_dist3x3<40><<<grid, 32 * DT_WARPS, 0, st>>>(B, cmap, itmp, maps, 32 * 16);
     return cudaGetLastError();
 }
 
