@@ -31,6 +31,9 @@ int csb_create(csb_context** out, int device_ordinal) {
     c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return CSB_ERR_CUDA; }
     c->own_stream = true;
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return CSB_ERR_CUDA; }
+    if (cudaHostAlloc((void**)&c->h_epoch, 64, cudaHostAllocDefault) != cudaSuccess) { delete c; return CSB_ERR_CUDA; }
+    *c->h_epoch = 0;
     for (int i = 0; i < 7; i++) cudaEventCreate(&c->det.ev[i]);
     *out = c;
     return CSB_OK;
@@ -43,11 +46,13 @@ void csb_destroy(csb_context* c) {
     DetectState& d = c->det;
     DevBuf* bufs[] = {&d.d_ftab, &d.d_ttab, &d.d_order, &d.d_box_begin, &d.d_lines, &d.d_maps, &d.d_ml_seg, &d.d_ml_ang, &d.d_ml_mid, &d.d_n_merged,
                       &d.d_p_dist, &d.d_p_angle, &d.d_p_hyp, &d.d_n_valid, &d.d_keep, &d.d_norm, &d.d_n_keep, &d.d_cand_score, &d.d_cand_ok,
-                      &d.d_sel_idx, &d.d_sel_flag, &d.d_sel_heap, &d.d_rank_idx, &d.d_cuboids, &d.d_n_cuboids, &d.d_counters, &d.d_dbg, &d.d_gray, &d.d_cmap, &d.d_queue, &d.d_dtmp};
+                      &d.d_sel_idx, &d.d_sel_flag, &d.d_sel_heap, &d.d_rank_idx, &d.d_cuboids, &d.d_n_cuboids, &d.d_counters, &d.d_dbg, &d.d_gray, &d.d_cmap, &d.d_queue, &d.d_dtmp, &d.d_flags};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 7; i++)
         if (d.ev[i]) cudaEventDestroy(d.ev[i]);
     ba_release(c->ba);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->h_epoch) cudaFreeHost(c->h_epoch);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -88,7 +93,7 @@ int csb_detect_plan(const csb_frame* frames, int n_frames, const double* boxes, 
 // transform run on the device at the start of every csb_detect_run).
 static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_frames, const double* boxes, int n_boxes, const double* lines, int n_lines,
                               const csb_task* tasks, int n_tasks, const float* dist_maps, int64_t n_map_floats, const uint8_t* gray, int64_t n_gray_bytes,
-                              const csb_detect_params* params) {
+                              const csb_detect_params* params, bool stream_maps) {
     if (!c) return CSB_ERR_INVALID;
     if (!frames || n_frames <= 0 || !params || (!boxes && n_boxes > 0) || (!lines && n_lines > 0) || (!dist_maps && !gray && n_map_floats > 0)) {
         c->err = "csb_detect_upload: null argument";
@@ -132,7 +137,16 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
     // task queue: biggest first; box -> task range
     std::vector<int> order(n_tasks);
     std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return d.ttab[a].n_hyp > d.ttab[b].n_hyp; });
+    // chunked streaming (csb_detect_batch): tasks of an earlier chunk first (their maps arrive first), largest first inside a chunk
+    // (chunks are equal slices of the packed map buffer; maps are laid out in task order, so a chunk is a contiguous range)
+    const int64_t nm_total = std::max<int64_t>(n_map_floats, 1);
+    const int n_chunks = (stream_maps && !gray && n_map_floats >= (1 << 18)) ? 8 : 1;
+    auto chunk_of = [&](int task) { return (int)std::min<int64_t>(n_chunks - 1, d.ttab[task].map_offset * n_chunks / nm_total); };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        int ca = chunk_of(a), cb = chunk_of(b);
+        if (ca != cb) return ca < cb;
+        return d.ttab[a].n_hyp > d.ttab[b].n_hyp;
+    });
     std::vector<int> box_begin(n_boxes + 1, 0);
     {
         std::vector<int> cnt(n_boxes, 0);
@@ -182,8 +196,25 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
     }
     CSB_CUDA(c, cudaMemcpyAsync(d.d_box_begin.p, box_begin.data(), 4 * (size_t)(n_boxes + 1), cudaMemcpyHostToDevice, st));
     if (n_lines) CSB_CUDA(c, cudaMemcpyAsync(d.d_lines.p, lines, 32 * (size_t)n_lines, cudaMemcpyHostToDevice, st));
+    bool streaming = false;
     if (d.gray_mode) { if (gray_total) CSB_CUDA(c, cudaMemcpyAsync(d.d_gray.p, gray, (size_t)gray_total, cudaMemcpyHostToDevice, st)); }
-    else if (nm) CSB_CUDA(c, cudaMemcpyAsync(d.d_maps.p, dist_maps, 4 * (size_t)nm, cudaMemcpyHostToDevice, st));
+    else if (nm && n_chunks > 1 && n_tasks > 0) {
+        // distance maps go out chunk by chunk on the copy stream; k_score starts right away and waits per chunk on a flag word
+        // that is copied after the chunk's data (same stream => ordered)
+        streaming = true;
+        CSB_CUDA(c, d.d_flags.ensure(4 * 16));
+        d.epoch++;
+        *c->h_epoch = d.epoch;
+        std::vector<int64_t> chunk_begin(n_chunks + 1, nm);
+        for (int t = 0; t < n_tasks; t++) { int k = chunk_of(t); chunk_begin[k] = std::min<int64_t>(chunk_begin[k], d.ttab[t].map_offset); }
+        for (int k = n_chunks - 1; k >= 0; k--) chunk_begin[k] = std::min(chunk_begin[k], chunk_begin[k + 1]);
+        chunk_begin[0] = 0;
+        for (int k = 0; k < n_chunks; k++) {
+            const int64_t b0 = chunk_begin[k], b1 = chunk_begin[k + 1];
+            if (b1 > b0) CSB_CUDA(c, cudaMemcpyAsync(d.d_maps.as<float>() + b0, dist_maps + b0, 4 * (size_t)(b1 - b0), cudaMemcpyHostToDevice, c->copy_stream));
+            CSB_CUDA(c, cudaMemcpyAsync(d.d_flags.as<unsigned>() + k, c->h_epoch, 4, cudaMemcpyHostToDevice, c->copy_stream));
+        }
+    } else if (nm) CSB_CUDA(c, cudaMemcpyAsync(d.d_maps.p, dist_maps, 4 * (size_t)nm, cudaMemcpyHostToDevice, st));
     // the small host vectors above are pageable and go out of scope: make sure they are consumed
     CSB_CUDA(c, cudaStreamSynchronize(st));
     d.h2d_bytes = (int64_t)(sizeof(FrameTab) * n_frames + (sizeof(TaskTab) + 4) * (size_t)n_tasks + 4 * (size_t)(n_boxes + 1) + 32 * (size_t)n_lines +
@@ -199,6 +230,8 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
     B.sel_idx = d.d_sel_idx.as<int>(); B.sel_flag = d.d_sel_flag.as<unsigned char>(); B.sel_heap = d.d_sel_heap.as<double>();
     B.rank_idx = d.d_rank_idx.as<int>(); B.cuboids = d.d_cuboids.as<csb_cuboid>(); B.n_cuboids = d.d_n_cuboids.as<int>();
     B.counters = d.d_counters.as<int>();
+    B.ready_flags = streaming ? d.d_flags.as<unsigned>() : nullptr;
+    B.epoch = d.epoch; B.n_chunks = n_chunks; B.map_total = nm_total;
     B.dc.max_cuboid_num = kmax; B.dc.whether_sample_cam_roll_pitch = params->whether_sample_cam_roll_pitch;
     B.dc.nominal_skew_ratio = params->nominal_skew_ratio; B.dc.max_cut_skew = params->max_cut_skew;
     d.uploaded = true;
@@ -207,7 +240,7 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
 
 int csb_detect_upload(csb_context* c, const csb_frame* frames, int n_frames, const double* boxes, int n_boxes, const double* lines, int n_lines,
                       const csb_task* tasks, int n_tasks, const float* dist_maps, int64_t n_map_floats, const csb_detect_params* params) {
-    return detect_upload_impl(c, frames, n_frames, boxes, n_boxes, lines, n_lines, tasks, n_tasks, dist_maps, n_map_floats, nullptr, 0, params);
+    return detect_upload_impl(c, frames, n_frames, boxes, n_boxes, lines, n_lines, tasks, n_tasks, dist_maps, n_map_floats, nullptr, 0, params, false);
 }
 
 int csb_detect_upload_gray(csb_context* c, const csb_frame* frames, int n_frames, const double* boxes, int n_boxes, const double* lines, int n_lines,
@@ -218,7 +251,7 @@ int csb_detect_upload_gray(csb_context* c, const csb_frame* frames, int n_frames
     int64_t nm = 0;
     int rc = csb_detect_plan(frames, n_frames, boxes, n_boxes, params, nullptr, 0, &nt, &nm);
     if (rc != CSB_OK) { c->err = "csb_detect_upload_gray: planning failed"; return rc; }
-    return detect_upload_impl(c, frames, n_frames, boxes, n_boxes, lines, n_lines, tasks, n_tasks, nullptr, nm, gray, n_gray_bytes, params);
+    return detect_upload_impl(c, frames, n_frames, boxes, n_boxes, lines, n_lines, tasks, n_tasks, nullptr, nm, gray, n_gray_bytes, params, false);
 }
 
 int csb_detect_run(csb_context* c, int timed) {
@@ -279,6 +312,7 @@ int csb_detect_download(csb_context* c, csb_cuboid* cuboids_out, int32_t* n_cubo
         d2h += 8 * (size_t)d.n_tasks;
     }
     CSB_CUDA(c, cudaStreamSynchronize(st));
+    CSB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
     d.d2h_bytes = d2h;
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
@@ -301,7 +335,7 @@ int csb_detect_download(csb_context* c, csb_cuboid* cuboids_out, int32_t* n_cubo
 int csb_detect_batch(csb_context* c, const csb_frame* frames, int n_frames, const double* boxes, int n_boxes, const double* lines, int n_lines,
                      const csb_task* tasks, int n_tasks, const float* dist_maps, int64_t n_map_floats, const csb_detect_params* params,
                      csb_cuboid* cuboids_out, int32_t* n_cuboids_out, csb_detect_stats* stats) {
-    int rc = csb_detect_upload(c, frames, n_frames, boxes, n_boxes, lines, n_lines, tasks, n_tasks, dist_maps, n_map_floats, params);
+    int rc = detect_upload_impl(c, frames, n_frames, boxes, n_boxes, lines, n_lines, tasks, n_tasks, dist_maps, n_map_floats, nullptr, 0, params, true);
     if (rc != CSB_OK) return rc;
     rc = csb_detect_run(c, stats != nullptr);
     if (rc != CSB_OK) return rc;

@@ -43,8 +43,9 @@ struct DetectState {
     csb::DetectBuffers B{};
     DevBuf d_ftab, d_ttab, d_order, d_box_begin, d_lines, d_maps, d_ml_seg, d_ml_ang, d_ml_mid, d_n_merged, d_p_dist, d_p_angle, d_p_hyp,
         d_n_valid, d_keep, d_norm, d_n_keep, d_cand_score, d_cand_ok, d_sel_idx, d_sel_flag, d_sel_heap, d_rank_idx, d_cuboids, d_n_cuboids,
-        d_counters, d_dbg, d_gray, d_cmap, d_queue, d_dtmp;
+        d_counters, d_dbg, d_gray, d_cmap, d_queue, d_dtmp, d_flags;
     bool gray_mode = false;
+    unsigned epoch = 0;
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool timed_last = false;
     int64_t h2d_bytes = 0, d2h_bytes = 0;
@@ -54,6 +55,8 @@ struct DetectState {
 struct csb_context {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // chunked host->device streaming of csb_detect_batch
+    unsigned* h_epoch = nullptr;         // pinned word copied behind every chunk
     bool own_stream = false;
     int num_sms = 0, max_smem_optin = 0;
     std::string err;

@@ -133,14 +133,11 @@ constexpr int DT_INF = 0x3fffffff;     // "no path yet" inside the kernel (32-bi
 // 32-bit arithmetic: OpenCV saturates unreachable cells at DIST_MAX (~2^32); with at least one edge pixel in the ROI every final
 // value is a real path length (< 2^27 for ROIs up to 1280 px), and saturated cells only ever lose comparisons, so any "infinity"
 // that survives the additions gives the same result.  A ROI without edge pixels ends at DT_INF everywhere -> DIST_MAX, as in OpenCV.
-// Only tasks with w_lo < roi_w <= 32*CH are handled by an instantiation (one launch per width class).
+// The chunk size CH (8 / 16 / 40 columns per lane) is chosen per task from its ROI width; all classes run in one launch so that
+// the launch lasts as long as the slowest warp, not the sum of the classes.
 template <int CH>
-__global__ void __launch_bounds__(32 * DT_WARPS) k_dist3x3(DetectBuffers B, const uint8_t* cmap, int* dtmp, float* maps, int w_lo) {
-    const int task = blockIdx.x * DT_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (task >= B.n_tasks) return;
-    const TaskTab t = B.ttab[task];
+__device__ __forceinline__ void dist3x3_warp(const TaskTab& t, const uint8_t* cmap, int* dtmp, float* maps, int lane) {
     const int W = t.roi_w, H = t.roi_h;
-    if (W <= w_lo || W > 32 * CH) return;
     const uint8_t* map = cmap + t.map_offset;
     int* tmp = dtmp + t.map_offset;
     float* out = maps + t.map_offset;
@@ -237,6 +234,15 @@ __global__ void __launch_bounds__(32 * DT_WARPS) k_dist3x3(DetectBuffers B, cons
     }
 }
 
+__global__ void __launch_bounds__(32 * DT_WARPS) k_dist3x3(DetectBuffers B, const uint8_t* cmap, int* dtmp, float* maps) {
+    const int task = blockIdx.x * DT_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (task >= B.n_tasks) return;
+    const TaskTab t = B.ttab[task];
+    if (t.roi_w <= 32 * 8) dist3x3_warp<8>(t, cmap, dtmp, maps, lane);
+    else if (t.roi_w <= 32 * 16) dist3x3_warp<16>(t, cmap, dtmp, maps, lane);
+    else dist3x3_warp<40>(t, cmap, dtmp, maps, lane);
+}
+
 cudaError_t launch_distmaps(const DetectBuffers& B, const uint8_t* gray, uint8_t* cmap, int* queue, unsigned* dtmp, float* maps, int max_roi_w, cudaStream_t st) {
     if (B.n_tasks == 0) return cudaSuccess;
     dim3 g(B.n_tasks, 8);
@@ -244,10 +250,7 @@ cudaError_t launch_distmaps(const DetectBuffers& B, const uint8_t* gray, uint8_t
     k_canny_hyst<<<B.n_tasks, 256, 0, st>>>(B, cmap, queue);
     const int grid = (B.n_tasks + DT_WARPS - 1) / DT_WARPS;
     if (max_roi_w > 32 * 40) return cudaErrorInvalidValue;  // ROI wider than 1280 px
-    int* itmp = reinterpret_cast<int*>(dtmp);
-    k_dist3x3<8><<<grid, 32 * DT_WARPS, 0, st>>>(B, cmap, itmp, maps, 0);
-    if (max_roi_w > 32 * 8) k_dist3x3<16><<<grid, 32 * DT_WARPS, 0, st>>>(B, cmap, itmp, maps, 32 * 8);
-    if (max_roi_w > 32 * 16) k_dist3x3<40><<<grid, 32 * DT_WARPS, 0, st>>>(B, cmap, itmp, maps, 32 * 16);
+    k_dist3x3<<<grid, 32 * DT_WARPS, 0, st>>>(B, cmap, reinterpret_cast<int*>(dtmp), maps);
     return cudaGetLastError();
 }
 

@@ -326,7 +326,19 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) k_score(DetectBuffers B, int
     uint32_t bar_parity = 0;
 
     while (true) {
-        if (tid == 0) s_task = atomicAdd(B.counters, 1);
+        if (tid == 0) {
+            const int sl = atomicAdd(B.counters, 1);
+            s_task = sl;
+            // Host-buffer entry point: the distance maps arrive chunk by chunk on a copy stream while this kernel already runs;
+            // a chunk is usable once its flag (copied right after it, same stream) carries the current epoch.
+            if (B.ready_flags && sl < B.n_tasks) {
+                const long long ck = (long long)B.ttab[B.task_order[sl]].map_offset * B.n_chunks / B.map_total;
+            const int chunk = ck < B.n_chunks - 1 ? (int)ck : B.n_chunks - 1;
+                const volatile unsigned* fl = B.ready_flags + chunk;
+                while (*fl != B.epoch) __nanosleep(256);
+                __threadfence();
+            }
+        }
         __syncthreads();
         const int slot = s_task;
         if (slot >= B.n_tasks) break;

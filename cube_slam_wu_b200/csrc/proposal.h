@@ -42,6 +42,11 @@ struct DetectBuffers {
     csb_cuboid* cuboids;
     int* n_cuboids;
     int* counters;  // [0]: k_score task queue head
+    // chunked host->device streaming of the distance maps (csb_detect_batch): NULL when everything is resident before launch
+    const unsigned* ready_flags;
+    unsigned epoch;
+    int n_chunks;
+    long long map_total;  // chunk of a task = map_offset * n_chunks / map_total
     DetectConst dc;
 };
 
