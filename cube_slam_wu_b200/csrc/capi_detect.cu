@@ -44,10 +44,12 @@ void csb_destroy(csb_context* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DetectState& d = c->det;
-    DevBuf* bufs[] = {&d.d_ftab, &d.d_ttab, &d.d_order, &d.d_box_begin, &d.d_lines, &d.d_maps, &d.d_ml_seg, &d.d_ml_ang, &d.d_ml_mid, &d.d_n_merged,
-                      &d.d_p_dist, &d.d_p_angle, &d.d_p_hyp, &d.d_n_valid, &d.d_keep, &d.d_norm, &d.d_n_keep, &d.d_cand_score, &d.d_cand_ok,
-                      &d.d_sel_idx, &d.d_sel_flag, &d.d_sel_heap, &d.d_rank_idx, &d.d_cuboids, &d.d_n_cuboids, &d.d_counters, &d.d_dbg, &d.d_gray, &d.d_cmap, &d.d_queue, &d.d_dtmp, &d.d_flags};
+    DevBuf* bufs[] = {&d.d_tables, &d.d_results, &d.d_maps, &d.d_ml_seg, &d.d_ml_ang, &d.d_ml_mid, &d.d_n_merged,
+                      &d.d_p_dist, &d.d_p_angle, &d.d_p_hyp, &d.d_keep, &d.d_norm, &d.d_cand_score, &d.d_cand_ok,
+                      &d.d_sel_idx, &d.d_sel_flag, &d.d_sel_heap, &d.d_rank_idx, &d.d_counters, &d.d_dbg, &d.d_gray, &d.d_cmap, &d.d_queue, &d.d_dtmp, &d.d_flags};
     for (DevBuf* b : bufs) b->release();
+    d.h_tables.release(); d.h_results.release();
+    if (d.ev_tables) cudaEventDestroy(d.ev_tables);
     for (int i = 0; i < 7; i++)
         if (d.ev[i]) cudaEventDestroy(d.ev[i]);
     ba_release(c->ba);
@@ -89,78 +91,155 @@ int csb_detect_plan(const csb_frame* frames, int n_frames, const double* boxes, 
     return CSB_OK;
 }
 
-// Shared by csb_detect_upload (caller-computed distance maps) and csb_detect_upload_gray (gray frames; Canny + distance
-// transform run on the device at the start of every csb_detect_run).
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// Shared by csb_detect_upload (caller-computed distance maps), csb_detect_batch (the same, streamed in chunks) and
+// csb_detect_upload_gray (gray frames; Canny + distance transform run on the device at the start of every csb_detect_run;
+// n_map_floats < 0 = "not known to the caller").
+//
+// Order of work: the bulk payload (maps or gray frames) is queued on the copy engine FIRST, then the host plans tasks and builds the
+// sweep tables while it is in flight; the tables go out as one copy from a pinned staging arena.
 static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_frames, const double* boxes, int n_boxes, const double* lines, int n_lines,
                               const csb_task* tasks, int n_tasks, const float* dist_maps, int64_t n_map_floats, const uint8_t* gray, int64_t n_gray_bytes,
                               const csb_detect_params* params, bool stream_maps) {
     if (!c) return CSB_ERR_INVALID;
-    if (!frames || n_frames <= 0 || !params || (!boxes && n_boxes > 0) || (!lines && n_lines > 0) || (!dist_maps && !gray && n_map_floats > 0)) {
+    if (!frames || n_frames <= 0 || !params || (!boxes && n_boxes > 0) || (!lines && n_lines > 0) || (!dist_maps && !gray && n_map_floats > 0) || n_tasks < 0) {
         c->err = "csb_detect_upload: null argument";
         return CSB_ERR_INVALID;
     }
     if (params->max_cuboid_num < 1) { c->err = "max_cuboid_num must be >= 1"; return CSB_ERR_INVALID; }
     CSB_CUDA(c, cudaSetDevice(c->device));
     DetectState& d = c->det;
+    cudaStream_t st = c->stream;
     d.uploaded = false; d.ran = false;
     d.params = *params;
+    d.gray_mode = gray != nullptr;
+
+    // ---- 1. bulk payload on its way
+    int64_t gray_total = 0;
+    for (int f = 0; f < n_frames; f++) gray_total += (int64_t)frames[f].img_width * frames[f].img_height;
+    bool streaming = false;
+    int n_chunks = 1;
+    int64_t chunk_end[CSB_MAX_CHUNKS];
+    for (int k = 0; k < CSB_MAX_CHUNKS; k++) chunk_end[k] = n_map_floats;
+    if (d.gray_mode) {
+        // gray frames are packed back to back (img_height x img_width bytes each)
+        if (n_gray_bytes != gray_total) { c->err = "csb_detect_upload_gray: n_gray_bytes != sum of img_width*img_height"; return CSB_ERR_INVALID; }
+        CSB_CUDA(c, d.d_gray.ensure((size_t)gray_total + 64));
+        if (gray_total) CSB_CUDA(c, cudaMemcpyAsync(d.d_gray.p, gray, (size_t)gray_total, cudaMemcpyHostToDevice, st));
+    } else if (n_map_floats > 0) {
+        CSB_CUDA(c, d.d_maps.ensure(4 * (size_t)n_map_floats + 64));
+        if (stream_maps && n_map_floats >= (1 << 18)) {
+            // csb_detect_batch: equal slices on the copy stream, each followed by its flag word (same stream => ordered).  k_score starts
+            // right away and a task waits for the slice that holds the END of its map (slices complete in order).
+            streaming = true;
+            n_chunks = CSB_MAX_CHUNKS;
+            CSB_CUDA(c, d.d_flags.ensure(4 * CSB_MAX_CHUNKS));
+            CSB_CUDA(c, cudaStreamSynchronize(c->copy_stream));  // nothing may still be reading the epoch word
+            d.epoch++;
+            *c->h_epoch = d.epoch;
+            int64_t b0 = 0;
+            for (int k = 0; k < n_chunks; k++) {
+                const int64_t b1 = (k == n_chunks - 1) ? n_map_floats : ((n_map_floats * (k + 1) / n_chunks) & ~(int64_t)3);
+                chunk_end[k] = b1;
+                if (b1 > b0) CSB_CUDA(c, cudaMemcpyAsync(d.d_maps.as<float>() + b0, dist_maps + b0, 4 * (size_t)(b1 - b0), cudaMemcpyHostToDevice, c->copy_stream));
+                CSB_CUDA(c, cudaMemcpyAsync(d.d_flags.as<unsigned>() + k, c->h_epoch, 4, cudaMemcpyHostToDevice, c->copy_stream));
+                b0 = b1;
+            }
+        } else {
+            CSB_CUDA(c, cudaMemcpyAsync(d.d_maps.p, dist_maps, 4 * (size_t)n_map_floats, cudaMemcpyHostToDevice, st));
+        }
+    }
+    // from here on an error return must not leave the copy stream reading the caller's buffer
+    auto fail = [&](int code, const char* msg) { cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(st); c->err = msg; return code; };
+
+    // ---- 2. host planning while the payload is in flight
     d.tasks.clear(); d.ttab.clear();
     int64_t nm = 0;
     int rc = plan_tasks(frames, n_frames, boxes, n_boxes, *params, d.tasks, &d.ttab, &nm);
-    if (rc != CSB_OK) { c->err = "csb_detect_upload: planning failed (bad frame/box ranges or sweep tables over capacity)"; return rc; }
-    if ((int)d.tasks.size() != n_tasks || nm != n_map_floats) { c->err = "csb_detect_upload: tasks / n_map_floats do not match csb_detect_plan() for these inputs"; return CSB_ERR_INVALID; }
+    if (rc != CSB_OK) return fail(rc, "csb_detect_upload: planning failed (bad frame/box ranges or sweep tables over capacity)");
+    if ((int)d.tasks.size() != n_tasks || (n_map_floats >= 0 && nm != n_map_floats))
+        return fail(CSB_ERR_INVALID, "csb_detect_upload: tasks / n_map_floats do not match csb_detect_plan() for these inputs");
     if (tasks)
         for (int i = 0; i < n_tasks; i++)
-            if (tasks[i].map_offset != d.tasks[i].map_offset || tasks[i].box_id != d.tasks[i].box_id) { c->err = "csb_detect_upload: task list differs from plan"; return CSB_ERR_INVALID; }
+            if (tasks[i].map_offset != d.tasks[i].map_offset || tasks[i].box_id != d.tasks[i].box_id) return fail(CSB_ERR_INVALID, "csb_detect_upload: task list differs from plan");
+    d.n_frames = n_frames; d.n_boxes = n_boxes; d.n_lines = n_lines; d.n_tasks = n_tasks; d.n_map_floats = nm;
+
+    // table arena layout (device and pinned host mirror)
+    const size_t NT = (size_t)std::max(n_tasks, 1);
+    const size_t off_ftab = 0;
+    const size_t off_ttab = align256(off_ftab + sizeof(FrameTab) * (size_t)n_frames);
+    const size_t off_order = align256(off_ttab + sizeof(TaskTab) * NT);
+    const size_t off_box = align256(off_order + 4 * NT);
+    const size_t off_lines = align256(off_box + 4 * (size_t)(n_boxes + 1));
+    const size_t tab_bytes = align256(off_lines + 32 * (size_t)std::max(n_lines, 1));
+    if (d.ev_tables) CSB_CUDA(c, cudaEventSynchronize(d.ev_tables));  // previous upload's copy out of h_tables
+    CSB_CUDA(c, d.h_tables.ensure(tab_bytes));
+    CSB_CUDA(c, d.d_tables.ensure(tab_bytes));
+    char* hb = d.h_tables.as<char>();
+    FrameTab* h_ftab = reinterpret_cast<FrameTab*>(hb + off_ftab);
+    TaskTab* h_ttab = reinterpret_cast<TaskTab*>(hb + off_ttab);
+    int* h_order = reinterpret_cast<int*>(hb + off_order);
+    int* h_box = reinterpret_cast<int*>(hb + off_box);
+
     d.ftab.resize(n_frames);
     d.max_groups = 0; d.max_lines_per_frame = 0;
+    int64_t goff = 0;
     for (int f = 0; f < n_frames; f++) {
-        if (frames[f].line_begin < 0 || frames[f].line_end > n_lines || frames[f].line_begin > frames[f].line_end) { c->err = "bad line range"; return CSB_ERR_INVALID; }
-        rc = build_frame_tab(frames[f], *params, d.ftab[f]);
-        if (rc != CSB_OK) { c->err = "sweep tables over capacity"; return rc; }
-        d.max_groups = std::max(d.max_groups, d.ftab[f].n_roll * d.ftab[f].n_pitch * d.ftab[f].n_yaw);
+        if (frames[f].line_begin < 0 || frames[f].line_end > n_lines || frames[f].line_begin > frames[f].line_end) return fail(CSB_ERR_INVALID, "bad line range");
+        FrameTab& ft = h_ftab[f];
+        rc = build_frame_tab(frames[f], *params, ft);
+        if (rc != CSB_OK) return fail(rc, "sweep tables over capacity");
+        ft.gray_offset = goff;
+        goff += (int64_t)frames[f].img_width * frames[f].img_height;
+        d.max_groups = std::max(d.max_groups, ft.n_roll * ft.n_pitch * ft.n_yaw);
         d.max_lines_per_frame = std::max(d.max_lines_per_frame, frames[f].line_end - frames[f].line_begin);
     }
-    // gray frames are packed back to back (img_height x img_width bytes each)
-    int64_t gray_total = 0;
-    for (int f = 0; f < n_frames; f++) { d.ftab[f].gray_offset = gray_total; gray_total += (int64_t)frames[f].img_width * frames[f].img_height; }
-    d.gray_mode = gray != nullptr;
-    if (d.gray_mode && n_gray_bytes != gray_total) { c->err = "csb_detect_upload_gray: n_gray_bytes != sum of img_width*img_height"; return CSB_ERR_INVALID; }
-    d.n_frames = n_frames; d.n_boxes = n_boxes; d.n_lines = n_lines; d.n_tasks = n_tasks; d.n_map_floats = nm;
     d.out_total = 0; d.line_cap_total = 0; d.max_hyp_per_task = 1; d.max_roi_w = 1;
     for (const TaskTab& t : d.ttab) {
         d.out_total = std::max<int64_t>(d.out_total, t.out_offset + t.n_hyp);
-        d.line_cap_total = std::max<int64_t>(d.line_cap_total, (int64_t)t.line_cap_offset + (d.ftab[t.frame_id].line_end - d.ftab[t.frame_id].line_begin));
+        d.line_cap_total = std::max<int64_t>(d.line_cap_total, (int64_t)t.line_cap_offset + (frames[t.frame_id].line_end - frames[t.frame_id].line_begin));
         d.max_hyp_per_task = std::max(d.max_hyp_per_task, t.n_hyp);
         d.max_roi_w = std::max(d.max_roi_w, t.roi_w);
     }
-    // task queue: biggest first; box -> task range
-    std::vector<int> order(n_tasks);
-    std::iota(order.begin(), order.end(), 0);
-    // chunked streaming (csb_detect_batch): tasks of an earlier chunk first (their maps arrive first), largest first inside a chunk
-    // (chunks are equal slices of the packed map buffer; maps are laid out in task order, so a chunk is a contiguous range)
-    const int64_t nm_total = std::max<int64_t>(n_map_floats, 1);
-    const int n_chunks = (stream_maps && !gray && n_map_floats >= (1 << 18)) ? 8 : 1;
-    auto chunk_of = [&](int task) { return (int)std::min<int64_t>(n_chunks - 1, d.ttab[task].map_offset * n_chunks / nm_total); };
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-        int ca = chunk_of(a), cb = chunk_of(b);
-        if (ca != cb) return ca < cb;
-        return d.ttab[a].n_hyp > d.ttab[b].n_hyp;
-    });
-    std::vector<int> box_begin(n_boxes + 1, 0);
+    if (n_tasks) std::memcpy(h_ttab, d.ttab.data(), sizeof(TaskTab) * (size_t)n_tasks);
+    // task queue: tasks whose slice arrives first go first; inside a slice the biggest first
+    auto chunk_of = [&](int task) {
+        const TaskTab& t = d.ttab[task];
+        const int64_t last = t.map_offset + (int64_t)t.roi_w * t.roi_h - 1;
+        int k = 0;
+        while (k < n_chunks - 1 && chunk_end[k] <= last) k++;
+        return k;
+    };
     {
-        std::vector<int> cnt(n_boxes, 0);
-        for (const TaskTab& t : d.ttab) cnt[t.box_id]++;
-        for (int b = 0; b < n_boxes; b++) box_begin[b + 1] = box_begin[b] + cnt[b];
+        std::vector<int> ck(n_tasks);
+        for (int i = 0; i < n_tasks; i++) { h_order[i] = i; ck[i] = streaming ? chunk_of(i) : 0; }
+        std::stable_sort(h_order, h_order + n_tasks, [&](int a, int b) {
+            if (ck[a] != ck[b]) return ck[a] < ck[b];
+            return d.ttab[a].n_hyp > d.ttab[b].n_hyp;
+        });
     }
-    const size_t OT = (size_t)std::max<int64_t>(d.out_total, 1), LT = (size_t)std::max<int64_t>(d.line_cap_total, 1), NT = (size_t)std::max(n_tasks, 1);
+    {
+        std::fill(h_box, h_box + n_boxes + 1, 0);
+        for (const TaskTab& t : d.ttab) h_box[t.box_id + 1]++;
+        for (int b = 0; b < n_boxes; b++) h_box[b + 1] += h_box[b];
+    }
+    if (n_lines) std::memcpy(hb + off_lines, lines, 32 * (size_t)n_lines);
+    CSB_CUDA(c, cudaMemcpyAsync(d.d_tables.p, hb, tab_bytes, cudaMemcpyHostToDevice, st));
+    if (!d.ev_tables) CSB_CUDA(c, cudaEventCreateWithFlags(&d.ev_tables, cudaEventDisableTiming));
+    CSB_CUDA(c, cudaEventRecord(d.ev_tables, st));
+
+    // ---- 3. work buffers
+    const size_t OT = (size_t)std::max<int64_t>(d.out_total, 1), LT = (size_t)std::max<int64_t>(d.line_cap_total, 1);
     const int kmax = params->max_cuboid_num;
-    CSB_CUDA(c, d.d_ftab.ensure(sizeof(FrameTab) * n_frames));
-    CSB_CUDA(c, d.d_ttab.ensure(sizeof(TaskTab) * NT));
-    CSB_CUDA(c, d.d_order.ensure(4 * NT));
-    CSB_CUDA(c, d.d_box_begin.ensure(4 * (size_t)(n_boxes + 1)));
-    CSB_CUDA(c, d.d_lines.ensure(32 * (size_t)std::max(n_lines, 1)));
-    CSB_CUDA(c, d.d_maps.ensure(4 * (size_t)nm + 64));
+    const size_t NB = (size_t)std::max(n_boxes, 1);
+    d.res_off_ncub = align256(sizeof(csb_cuboid) * NB * kmax);
+    d.res_off_nvalid = align256(d.res_off_ncub + 4 * NB);
+    d.res_off_nkeep = align256(d.res_off_nvalid + 4 * NT);
+    d.res_bytes = align256(d.res_off_nkeep + 4 * NT);
+    CSB_CUDA(c, d.d_results.ensure(d.res_bytes));
+    CSB_CUDA(c, d.h_results.ensure(d.res_bytes));
+    if (d.gray_mode || n_map_floats <= 0) CSB_CUDA(c, d.d_maps.ensure(4 * (size_t)nm + 64));
     CSB_CUDA(c, d.d_ml_seg.ensure(32 * LT));
     CSB_CUDA(c, d.d_ml_ang.ensure(8 * LT));
     CSB_CUDA(c, d.d_ml_mid.ensure(16 * LT));
@@ -168,72 +247,42 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
     CSB_CUDA(c, d.d_p_dist.ensure(8 * OT));
     CSB_CUDA(c, d.d_p_angle.ensure(8 * OT));
     CSB_CUDA(c, d.d_p_hyp.ensure(4 * OT));
-    CSB_CUDA(c, d.d_n_valid.ensure(4 * NT));
     CSB_CUDA(c, d.d_keep.ensure(4 * OT));
     CSB_CUDA(c, d.d_norm.ensure(8 * OT));
-    CSB_CUDA(c, d.d_n_keep.ensure(4 * NT));
     CSB_CUDA(c, d.d_cand_score.ensure(8 * OT));
     CSB_CUDA(c, d.d_cand_ok.ensure(OT));
     CSB_CUDA(c, d.d_sel_idx.ensure(8 * OT));
     CSB_CUDA(c, d.d_sel_flag.ensure(OT));
     CSB_CUDA(c, d.d_sel_heap.ensure(16 * OT));
     CSB_CUDA(c, d.d_rank_idx.ensure(8 * OT));
-    CSB_CUDA(c, d.d_cuboids.ensure(sizeof(csb_cuboid) * (size_t)std::max(n_boxes, 1) * kmax));
-    CSB_CUDA(c, d.d_n_cuboids.ensure(4 * (size_t)std::max(n_boxes, 1)));
     CSB_CUDA(c, d.d_counters.ensure(64));
     if (d.gray_mode) {
-        CSB_CUDA(c, d.d_gray.ensure((size_t)gray_total + 64));
         CSB_CUDA(c, d.d_cmap.ensure((size_t)nm + 64));
         CSB_CUDA(c, d.d_queue.ensure(4 * (size_t)nm + 64));
         CSB_CUDA(c, d.d_dtmp.ensure(4 * (size_t)nm + 64));
     }
-
-    cudaStream_t st = c->stream;
-    CSB_CUDA(c, cudaMemcpyAsync(d.d_ftab.p, d.ftab.data(), sizeof(FrameTab) * n_frames, cudaMemcpyHostToDevice, st));
-    if (n_tasks) {
-        CSB_CUDA(c, cudaMemcpyAsync(d.d_ttab.p, d.ttab.data(), sizeof(TaskTab) * n_tasks, cudaMemcpyHostToDevice, st));
-        CSB_CUDA(c, cudaMemcpyAsync(d.d_order.p, order.data(), 4 * (size_t)n_tasks, cudaMemcpyHostToDevice, st));
-    }
-    CSB_CUDA(c, cudaMemcpyAsync(d.d_box_begin.p, box_begin.data(), 4 * (size_t)(n_boxes + 1), cudaMemcpyHostToDevice, st));
-    if (n_lines) CSB_CUDA(c, cudaMemcpyAsync(d.d_lines.p, lines, 32 * (size_t)n_lines, cudaMemcpyHostToDevice, st));
-    bool streaming = false;
-    if (d.gray_mode) { if (gray_total) CSB_CUDA(c, cudaMemcpyAsync(d.d_gray.p, gray, (size_t)gray_total, cudaMemcpyHostToDevice, st)); }
-    else if (nm && n_chunks > 1 && n_tasks > 0) {
-        // distance maps go out chunk by chunk on the copy stream; k_score starts right away and waits per chunk on a flag word
-        // that is copied after the chunk's data (same stream => ordered)
-        streaming = true;
-        CSB_CUDA(c, d.d_flags.ensure(4 * 16));
-        d.epoch++;
-        *c->h_epoch = d.epoch;
-        std::vector<int64_t> chunk_begin(n_chunks + 1, nm);
-        for (int t = 0; t < n_tasks; t++) { int k = chunk_of(t); chunk_begin[k] = std::min<int64_t>(chunk_begin[k], d.ttab[t].map_offset); }
-        for (int k = n_chunks - 1; k >= 0; k--) chunk_begin[k] = std::min(chunk_begin[k], chunk_begin[k + 1]);
-        chunk_begin[0] = 0;
-        for (int k = 0; k < n_chunks; k++) {
-            const int64_t b0 = chunk_begin[k], b1 = chunk_begin[k + 1];
-            if (b1 > b0) CSB_CUDA(c, cudaMemcpyAsync(d.d_maps.as<float>() + b0, dist_maps + b0, 4 * (size_t)(b1 - b0), cudaMemcpyHostToDevice, c->copy_stream));
-            CSB_CUDA(c, cudaMemcpyAsync(d.d_flags.as<unsigned>() + k, c->h_epoch, 4, cudaMemcpyHostToDevice, c->copy_stream));
-        }
-    } else if (nm) CSB_CUDA(c, cudaMemcpyAsync(d.d_maps.p, dist_maps, 4 * (size_t)nm, cudaMemcpyHostToDevice, st));
-    // the small host vectors above are pageable and go out of scope: make sure they are consumed
-    CSB_CUDA(c, cudaStreamSynchronize(st));
-    d.h2d_bytes = (int64_t)(sizeof(FrameTab) * n_frames + (sizeof(TaskTab) + 4) * (size_t)n_tasks + 4 * (size_t)(n_boxes + 1) + 32 * (size_t)n_lines +
-                            (d.gray_mode ? (size_t)gray_total : 4 * (size_t)nm));
+    d.h2d_bytes = (int64_t)(tab_bytes + (d.gray_mode ? (size_t)gray_total : 4 * (size_t)nm) + (streaming ? 4 * (size_t)n_chunks : 0));
 
     DetectBuffers& B = d.B;
-    B.ftab = d.d_ftab.as<FrameTab>(); B.ttab = d.d_ttab.as<TaskTab>(); B.task_order = d.d_order.as<int>(); B.box_task_begin = d.d_box_begin.as<int>();
-    B.lines = d.d_lines.as<double>(); B.maps = d.d_maps.as<float>(); B.n_tasks = n_tasks; B.pad = 0;
+    char* db = d.d_tables.as<char>();
+    char* dr = d.d_results.as<char>();
+    B.ftab = reinterpret_cast<const FrameTab*>(db + off_ftab); B.ttab = reinterpret_cast<const TaskTab*>(db + off_ttab);
+    B.task_order = reinterpret_cast<const int*>(db + off_order); B.box_task_begin = reinterpret_cast<const int*>(db + off_box);
+    B.lines = reinterpret_cast<const double*>(db + off_lines); B.maps = d.d_maps.as<float>(); B.n_tasks = n_tasks; B.pad = 0;
     B.ml_seg = d.d_ml_seg.as<double>(); B.ml_ang = d.d_ml_ang.as<double>(); B.ml_mid = d.d_ml_mid.as<double>(); B.n_merged = d.d_n_merged.as<int>();
-    B.p_dist = d.d_p_dist.as<double>(); B.p_angle = d.d_p_angle.as<double>(); B.p_hyp = d.d_p_hyp.as<int>(); B.n_valid = d.d_n_valid.as<int>();
-    B.keep = d.d_keep.as<int>(); B.norm_score = d.d_norm.as<double>(); B.n_keep = d.d_n_keep.as<int>();
+    B.p_dist = d.d_p_dist.as<double>(); B.p_angle = d.d_p_angle.as<double>(); B.p_hyp = d.d_p_hyp.as<int>();
+    B.n_valid = reinterpret_cast<int*>(dr + d.res_off_nvalid);
+    B.keep = d.d_keep.as<int>(); B.norm_score = d.d_norm.as<double>(); B.n_keep = reinterpret_cast<int*>(dr + d.res_off_nkeep);
     B.cand_score = d.d_cand_score.as<double>(); B.cand_ok = d.d_cand_ok.as<unsigned char>();
     B.sel_idx = d.d_sel_idx.as<int>(); B.sel_flag = d.d_sel_flag.as<unsigned char>(); B.sel_heap = d.d_sel_heap.as<double>();
-    B.rank_idx = d.d_rank_idx.as<int>(); B.cuboids = d.d_cuboids.as<csb_cuboid>(); B.n_cuboids = d.d_n_cuboids.as<int>();
+    B.rank_idx = d.d_rank_idx.as<int>(); B.cuboids = reinterpret_cast<csb_cuboid*>(dr); B.n_cuboids = reinterpret_cast<int*>(dr + d.res_off_ncub);
     B.counters = d.d_counters.as<int>();
     B.ready_flags = streaming ? d.d_flags.as<unsigned>() : nullptr;
-    B.epoch = d.epoch; B.n_chunks = n_chunks; B.map_total = nm_total;
+    B.epoch = d.epoch; B.n_chunks = n_chunks;
+    for (int k = 0; k < CSB_MAX_CHUNKS; k++) B.chunk_end[k] = chunk_end[k];
     B.dc.max_cuboid_num = kmax; B.dc.whether_sample_cam_roll_pitch = params->whether_sample_cam_roll_pitch;
     B.dc.nominal_skew_ratio = params->nominal_skew_ratio; B.dc.max_cut_skew = params->max_cut_skew;
+    for (int f = 0; f < n_frames; f++) d.ftab[f] = h_ftab[f];  // host copy for the debug entries (h_tables is reused by the next upload)
     d.uploaded = true;
     return CSB_OK;
 }
@@ -247,11 +296,7 @@ int csb_detect_upload_gray(csb_context* c, const csb_frame* frames, int n_frames
                            const csb_task* tasks, int n_tasks, const uint8_t* gray, int64_t n_gray_bytes, const csb_detect_params* params) {
     if (!c) return CSB_ERR_INVALID;
     if (!gray) { c->err = "csb_detect_upload_gray: null gray buffer"; return CSB_ERR_INVALID; }
-    int nt = 0;
-    int64_t nm = 0;
-    int rc = csb_detect_plan(frames, n_frames, boxes, n_boxes, params, nullptr, 0, &nt, &nm);
-    if (rc != CSB_OK) { c->err = "csb_detect_upload_gray: planning failed"; return rc; }
-    return detect_upload_impl(c, frames, n_frames, boxes, n_boxes, lines, n_lines, tasks, n_tasks, nullptr, nm, gray, n_gray_bytes, params, false);
+    return detect_upload_impl(c, frames, n_frames, boxes, n_boxes, lines, n_lines, tasks, n_tasks, nullptr, -1, gray, n_gray_bytes, params, false);
 }
 
 int csb_detect_run(csb_context* c, int timed) {
@@ -299,20 +344,19 @@ int csb_detect_download(csb_context* c, csb_cuboid* cuboids_out, int32_t* n_cubo
     CSB_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     const int kmax = d.params.max_cuboid_num;
-    int64_t d2h = 0;
-    if (d.n_boxes > 0) {
-        if (cuboids_out) { CSB_CUDA(c, cudaMemcpyAsync(cuboids_out, d.d_cuboids.p, sizeof(csb_cuboid) * (size_t)d.n_boxes * kmax, cudaMemcpyDeviceToHost, st)); d2h += sizeof(csb_cuboid) * (size_t)d.n_boxes * kmax; }
-        if (n_cuboids_out) { CSB_CUDA(c, cudaMemcpyAsync(n_cuboids_out, d.d_n_cuboids.p, 4 * (size_t)d.n_boxes, cudaMemcpyDeviceToHost, st)); d2h += 4 * (size_t)d.n_boxes; }
-    }
-    std::vector<int> nv, nk;
-    if (stats && d.n_tasks > 0) {
-        nv.resize(d.n_tasks); nk.resize(d.n_tasks);
-        CSB_CUDA(c, cudaMemcpyAsync(nv.data(), d.d_n_valid.p, 4 * (size_t)d.n_tasks, cudaMemcpyDeviceToHost, st));
-        CSB_CUDA(c, cudaMemcpyAsync(nk.data(), d.d_n_keep.p, 4 * (size_t)d.n_tasks, cudaMemcpyDeviceToHost, st));
-        d2h += 8 * (size_t)d.n_tasks;
-    }
+    // one copy of the result arena (cuboids | n_cuboids | n_valid | n_keep) into pinned memory, then plain memcpy to the caller
+    const size_t take = stats ? d.res_bytes : d.res_off_nvalid;
+    CSB_CUDA(c, cudaMemcpyAsync(d.h_results.p, d.d_results.p, take, cudaMemcpyDeviceToHost, st));
     CSB_CUDA(c, cudaStreamSynchronize(st));
     CSB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    const char* hr = d.h_results.as<char>();
+    if (d.n_boxes > 0) {
+        if (cuboids_out) std::memcpy(cuboids_out, hr, sizeof(csb_cuboid) * (size_t)d.n_boxes * kmax);
+        if (n_cuboids_out) std::memcpy(n_cuboids_out, hr + d.res_off_ncub, 4 * (size_t)d.n_boxes);
+    }
+    const int* nv = reinterpret_cast<const int*>(hr + d.res_off_nvalid);
+    const int* nk = reinterpret_cast<const int*>(hr + d.res_off_nkeep);
+    const int64_t d2h = (int64_t)take;
     d.d2h_bytes = d2h;
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
@@ -381,9 +425,9 @@ int csb_detect_debug_task(csb_context* c, int task_id, int32_t* n_valid, int32_t
     CSB_CUDA(c, cudaStreamSynchronize(st));
     const TaskTab& t = d.ttab[task_id];
     int nv = 0, nm = 0, nk = 0;
-    CSB_CUDA(c, cudaMemcpy(&nv, d.d_n_valid.as<int>() + task_id, 4, cudaMemcpyDeviceToHost));
+    CSB_CUDA(c, cudaMemcpy(&nv, d.B.n_valid + task_id, 4, cudaMemcpyDeviceToHost));
     CSB_CUDA(c, cudaMemcpy(&nm, d.d_n_merged.as<int>() + task_id, 4, cudaMemcpyDeviceToHost));
-    CSB_CUDA(c, cudaMemcpy(&nk, d.d_n_keep.as<int>() + task_id, 4, cudaMemcpyDeviceToHost));
+    CSB_CUDA(c, cudaMemcpy(&nk, d.B.n_keep + task_id, 4, cudaMemcpyDeviceToHost));
     if (n_valid) *n_valid = nv;
     if (n_merged) *n_merged = nm;
     if (n_keep) *n_keep = nk;

@@ -31,6 +31,29 @@ struct DevBuf {
     T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// pinned host staging memory (grows, never shrinks)
+struct HostBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
 struct DetectState {
     bool uploaded = false, ran = false;
     int n_frames = 0, n_boxes = 0, n_lines = 0, n_tasks = 0;
@@ -41,9 +64,13 @@ struct DetectState {
     std::vector<csb::FrameTab> ftab;
     std::vector<csb_task> tasks;
     csb::DetectBuffers B{};
-    DevBuf d_ftab, d_ttab, d_order, d_box_begin, d_lines, d_maps, d_ml_seg, d_ml_ang, d_ml_mid, d_n_merged, d_p_dist, d_p_angle, d_p_hyp,
-        d_n_valid, d_keep, d_norm, d_n_keep, d_cand_score, d_cand_ok, d_sel_idx, d_sel_flag, d_sel_heap, d_rank_idx, d_cuboids, d_n_cuboids,
-        d_counters, d_dbg, d_gray, d_cmap, d_queue, d_dtmp, d_flags;
+    // d_tables: frame/task/order/box/line tables, one H2D copy from h_tables.  d_results: cuboids | n_cuboids | n_valid | n_keep, one D2H
+    // copy into h_results.
+    DevBuf d_tables, d_results, d_maps, d_ml_seg, d_ml_ang, d_ml_mid, d_n_merged, d_p_dist, d_p_angle, d_p_hyp, d_keep, d_norm, d_cand_score, d_cand_ok,
+        d_sel_idx, d_sel_flag, d_sel_heap, d_rank_idx, d_counters, d_dbg, d_gray, d_cmap, d_queue, d_dtmp, d_flags;
+    HostBuf h_tables, h_results;
+    size_t res_off_ncub = 0, res_off_nvalid = 0, res_off_nkeep = 0, res_bytes = 0;
+    cudaEvent_t ev_tables = nullptr;  // h_tables consumed by the device
     bool gray_mode = false;
     unsigned epoch = 0;
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

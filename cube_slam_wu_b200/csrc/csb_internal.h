@@ -4,6 +4,8 @@
 
 #include "../../include/cubeslam_b200.h"
 
+#define CSB_MAX_CHUNKS 16  // slices of the streamed distance-map upload (csb_detect_batch)
+
 namespace csb {
 
 constexpr int MAX_RP = 8;      // max camera roll (or pitch) samples; the reference yields 4..5 (matrix_utils.cpp:368-380)

@@ -24,6 +24,35 @@ static void linespace(T starting, T ending, T step, std::vector<T>& res) {
     }
 }
 
+// Sample angles of a frame (cheap part of the table: one quaternion->Euler conversion and the accumulating linespaces).
+static int frame_angles(const csb_frame& f, const csb_detect_params& p, double euler_raw[3], std::vector<double>& yaws, std::vector<double>& rolls,
+                        std::vector<double>& pitches) {
+    M3 Rraw;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) Rraw.m[i * 3 + j] = f.transToWolrd[i * 4 + j];
+    quat_to_euler_zyx(quat_from_rot(Rraw), euler_raw[0], euler_raw[1], euler_raw[2]);
+    double yaw_init = euler_raw[2] - 90.0 / 180.0 * M_PI;
+    linespace<double>(yaw_init - 45.0 / 180.0 * M_PI, yaw_init + 45.0 / 180.0 * M_PI, 6.0 / 180.0 * M_PI, yaws);
+    if (p.whether_sample_cam_roll_pitch) {
+        linespace<double>(euler_raw[0] - 6.0 / 180.0 * M_PI, euler_raw[0] + 6.0 / 180.0 * M_PI, 3.0 / 180.0 * M_PI, rolls);
+        linespace<double>(euler_raw[1] - 6.0 / 180.0 * M_PI, euler_raw[1] + 6.0 / 180.0 * M_PI, 3.0 / 180.0 * M_PI, pitches);
+    } else {
+        rolls.push_back(euler_raw[0]);
+        pitches.push_back(euler_raw[1]);
+    }
+    if ((int)yaws.size() > MAX_YAW || (int)rolls.size() > MAX_RP || (int)pitches.size() > MAX_RP) return CSB_ERR_CAPACITY;
+    return CSB_OK;
+}
+
+int frame_group_count(const csb_frame& f, const csb_detect_params& p, int* n_groups) {
+    double e[3];
+    std::vector<double> yaws, rolls, pitches;
+    int rc = frame_angles(f, p, e, yaws, rolls, pitches);
+    if (rc != CSB_OK) return rc;
+    *n_groups = (int)(yaws.size() * rolls.size() * pitches.size());
+    return CSB_OK;
+}
+
 int build_frame_tab(const csb_frame& f, const csb_detect_params& p, FrameTab& ft) {
     std::memset(&ft, 0, sizeof ft);
     M3 K;
@@ -81,14 +110,6 @@ int build_frame_tab(const csb_frame& f, const csb_detect_params& p, FrameTab& ft
     return CSB_OK;
 }
 
-// number of (roll, pitch, yaw) groups a frame will sweep -- needed by the planner before tables exist
-static int groups_of(const csb_frame& f, const csb_detect_params& p, int* n_groups) {
-    FrameTab ft;
-    int rc = build_frame_tab(f, p, ft);
-    if (rc != CSB_OK) return rc;
-    *n_groups = ft.n_roll * ft.n_pitch * ft.n_yaw;
-    return CSB_OK;
-}
 
 int plan_tasks(const csb_frame* frames, int n_frames, const double* boxes, int n_boxes, const csb_detect_params& p, std::vector<csb_task>& tasks,
                std::vector<TaskTab>* tabs, int64_t* n_map_floats) {
@@ -99,7 +120,7 @@ int plan_tasks(const csb_frame* frames, int n_frames, const double* boxes, int n
         const csb_frame& fr = frames[f];
         if (fr.box_begin < 0 || fr.box_end > n_boxes || fr.box_begin > fr.box_end) return CSB_ERR_INVALID;
         int n_groups = 0;
-        int rc = groups_of(fr, p, &n_groups);
+        int rc = frame_group_count(fr, p, &n_groups);
         if (rc != CSB_OK) return rc;
         if (n_groups > MAX_GROUPS) return CSB_ERR_CAPACITY;
         const int img_width = fr.img_width, img_height = fr.img_height;
@@ -124,8 +145,9 @@ int plan_tasks(const csb_frame* frames, int n_frames, const double* boxes, int n
                 double diag = std::sqrt((double)(obj_width_raw * obj_width_raw + obj_height_expan * obj_height_expan));
                 int top_sample_resolution = (int)std::round(std::min(20, obj_width_raw / 10));  // :212
                 if (top_sample_resolution < 1) break;                                            // :215-216
-                std::vector<int> tops;
-                linespace<int>(left_x_raw + 5, right_x_raw - 5, top_sample_resolution, tops);  // :219
+                int n_tops = 0;  // linespace<int>(left_x_raw + 5, right_x_raw - 5, top_sample_resolution) :219, counted
+                for (int x = left_x_raw + 5; x <= right_x_raw - 5; x += top_sample_resolution)
+                    if (++n_tops > 1000) break;
                 // :242-248
                 int w = std::min(std::max(std::min(20, obj_width_raw - 100), 10), std::max(std::min(20, obj_height_expan - 100), 10));
                 int left_e = std::max(0, left_x_raw - w), right_e = std::min(img_width - 1, right_x_raw + w);
@@ -137,7 +159,7 @@ int plan_tasks(const csb_frame* frames, int n_frames, const double* boxes, int n
                 std::memset(&t, 0, sizeof t);
                 t.frame_id = f; t.box_id = b; t.hs_id = hs; t.down_expand = down_expand_sample;
                 t.roi_left = left_e; t.roi_top = top_e; t.roi_width = width_e; t.roi_height = height_e;
-                t.n_top = (int)tops.size();
+                t.n_top = n_tops;
                 t.n_enum = n_groups * t.n_top * n_cfg;
                 t.map_offset = map_off;
                 tasks.push_back(t);

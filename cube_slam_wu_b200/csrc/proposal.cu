@@ -332,9 +332,11 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) k_score(DetectBuffers B, int
             // Host-buffer entry point: the distance maps arrive chunk by chunk on a copy stream while this kernel already runs;
             // a chunk is usable once its flag (copied right after it, same stream) carries the current epoch.
             if (B.ready_flags && sl < B.n_tasks) {
-                const long long ck = (long long)B.ttab[B.task_order[sl]].map_offset * B.n_chunks / B.map_total;
-            const int chunk = ck < B.n_chunks - 1 ? (int)ck : B.n_chunks - 1;
-                const volatile unsigned* fl = B.ready_flags + chunk;
+                const TaskTab& tq = B.ttab[B.task_order[sl]];
+            const long long last = (long long)tq.map_offset + (long long)tq.roi_w * tq.roi_h - 1;
+            int chunk = 0;
+            while (chunk < B.n_chunks - 1 && B.chunk_end[chunk] <= last) chunk++;
+            const volatile unsigned* fl = B.ready_flags + chunk;
                 while (*fl != B.epoch) __nanosleep(256);
                 __threadfence();
             }

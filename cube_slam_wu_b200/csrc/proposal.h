@@ -46,7 +46,7 @@ struct DetectBuffers {
     const unsigned* ready_flags;
     unsigned epoch;
     int n_chunks;
-    long long map_total;  // chunk of a task = map_offset * n_chunks / map_total
+    long long chunk_end[CSB_MAX_CHUNKS];  // slice k holds map floats [chunk_end[k-1], chunk_end[k]); a task waits for the slice of its last float
     DetectConst dc;
 };
 
