@@ -74,16 +74,38 @@ __device__ __forceinline__ bool merge_pred(const LineSM& L, int a, int b, double
     return true;
 }
 
-// One warp per task.  Dynamic shared memory: 5 * cap doubles.
-__global__ void __launch_bounds__(32) k_prep_lines(DetectBuffers B, int cap) {
+constexpr int PREP_THREADS = 256;
+constexpr int PREP_WARPS = PREP_THREADS / 32;
+
+// order-preserving block compaction step: returns this thread's output slot (valid when `in`) and adds the chunk's count to total
+__device__ __forceinline__ int prep_compact(bool in, int* s_cnt, int tid, int& total) {
+    const unsigned bal = __ballot_sync(0xffffffffu, in);
+    const int lane = tid & 31, warp = tid >> 5;
+    if (lane == 0) s_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < PREP_WARPS; w++) { int c = s_cnt[w]; if (w < warp) before += c; all += c; }
+    const int pos = total + before + __popc(bal & ((1u << lane) - 1));
+    total += all;
+    __syncthreads();
+    return pos;
+}
+
+// One block (8 warps) per task.  Dynamic shared memory: 5 * cap doubles + 2 * cap ints.
+__global__ void __launch_bounds__(PREP_THREADS) k_prep_lines(DetectBuffers B, int cap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int s_cnt[PREP_WARPS];
+    __shared__ int s_hit, s_njobs;
     const int task = blockIdx.x;
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TaskTab& tt = B.ttab[task];
     const FrameTab& ft = B.ftab[tt.frame_id];
     LineSM L;
     L.x1 = reinterpret_cast<double*>(smem_raw);
     L.y1 = L.x1 + cap; L.x2 = L.y1 + cap; L.y2 = L.x2 + cap; L.ang = L.y2 + cap;
+    int* first = reinterpret_cast<int*>(L.ang + cap);
+    int* jobs = first + cap;  // rows to re-scan this round, packed (row, from) as row * 65536 + from is too small: two ints per job
     const unsigned FULL = 0xffffffffu;
 
     // (1) align left->right (object_3d_util.cpp:246-258) and keep lines with both endpoints inside the expanded ROI
@@ -91,8 +113,8 @@ __global__ void __launch_bounds__(32) k_prep_lines(DetectBuffers B, int cap) {
     const double rl = (double)tt.roi_left, rt = (double)tt.roi_top, rr = (double)tt.roi_right, rd = (double)tt.roi_down;
     int total = 0;
     const int n_raw = ft.line_end - ft.line_begin;
-    for (int base = 0; base < n_raw; base += 32) {
-        int i = base + lane;
+    for (int base = 0; base < n_raw; base += PREP_THREADS) {
+        int i = base + tid;
         bool in = false;
         double a = 0, b = 0, c = 0, d = 0;
         if (i < n_raw) {
@@ -101,90 +123,120 @@ __global__ void __launch_bounds__(32) k_prep_lines(DetectBuffers B, int cap) {
             if (c < a) { double t0 = a, t1 = b; a = c; b = d; c = t0; d = t1; }
             in = inside_box(V2{a, b}, rl, rt, rr, rd) && inside_box(V2{c, d}, rl, rt, rr, rd);
         }
-        unsigned bal = __ballot_sync(FULL, in);
+        const int pos = prep_compact(in, s_cnt, tid, total);
         if (in) {
-            int pos = total + __popc(bal & ((1u << lane) - 1));
             L.x1[pos] = a; L.y1[pos] = b; L.x2[pos] = c; L.y2[pos] = d;
             L.ang[pos] = det_atan2(d - b, c - a);
         }
-        total += __popc(bal);
     }
-    __syncwarp();
+    __syncthreads();
 
     // (2) merge_break_lines (object_3d_util.cpp:431-511): repeatedly merge the first (seg1, seg2) pair in lexicographic
-    // order that passes the angle / gap / merged-angle tests, then restart.  The restart only needs to revisit pairs
-    // whose rows changed: after a merge at (m, s2), rows < m failed against every row except the new content of row m
-    // (the row moved into slot s2 already failed against them), so the next pass tests (a, m) for a < m, then scans
-    // seg1 = m, m+1, ... in full.  Angles are cached per row (atan2 of unchanged endpoints is unchanged).
+    // order that passes the angle / gap / merged-angle tests, then restart from scratch (<= 500 rounds).
+    // The restart is replayed exactly but incrementally: first[s1] memoises the smallest seg2 > s1 that passes against
+    // s1 (-1: none).  A merge at (m, s2) rewrites row m, moves the last row into slot s2 and drops the last slot; every
+    // other pair is unchanged, so a row only (i) re-tests the two rewritten slots and (ii) re-scans from its old first hit
+    // if that hit was one of the rewritten / dropped slots.  Each round costs O(rows) pair tests spread over the block.
     const double thr_ang = 5.0 / 180.0 * M_PI, thr_dist = 20.0;
-    bool can_force_merge = true;
+    // warp-cooperative scan of row s1 from slot `from`: smallest passing partner or -1 (uniform over the warp)
+    auto scan_row = [&](int s1, int from) -> int {
+        for (int base = from; base < total; base += 32) {
+            int bb = base + lane;
+            double o[5];
+            bool ok = (bb < total) && merge_pred(L, s1, bb, thr_ang, thr_dist, o);
+            unsigned bal = __ballot_sync(FULL, ok);
+            if (bal) return base + __ffs(bal) - 1;
+        }
+        return -1;
+    };
+    for (int s1 = warp; s1 < total; s1 += PREP_WARPS) {
+        int f = scan_row(s1, s1 + 1);
+        if (lane == 0) first[s1] = f;
+    }
+    __syncthreads();
     int counter = 0;
-    int marker = -1;  // seg1 of the previous merge; -1: nothing known yet
-    while (can_force_merge && counter < 500) {
+    while (counter < 500) {
         counter++;
-        can_force_merge = false;
-        int hit_a = -1, hit_b = -1;
-        double mg[5];
-        if (marker >= 0) {
-            for (int base = 0; base < marker && hit_a < 0; base += 32) {
-                int a = base + lane;
+        // the first row that has a partner (warp 0 scans, everyone reads)
+        if (warp == 0) {
+            int hit = -1;
+            for (int base = 0; base < total && hit < 0; base += 32) {
+                int r = base + lane;
+                unsigned bal = __ballot_sync(FULL, r < total && first[r] >= 0);
+                if (bal) hit = base + __ffs(bal) - 1;
+            }
+            if (lane == 0) { s_hit = hit; s_njobs = 0; }
+        }
+        __syncthreads();
+        const int hit_a = s_hit;
+        if (hit_a < 0) break;
+        const int hit_b = first[hit_a];
+        __syncthreads();  // everyone has read first[hit_a] before the tables change
+        if (tid == 0) {
+            double mg[5];
+            merge_pred(L, hit_a, hit_b, thr_ang, thr_dist, mg);
+            L.x1[hit_a] = mg[0]; L.y1[hit_a] = mg[1]; L.x2[hit_a] = mg[2]; L.y2[hit_a] = mg[3]; L.ang[hit_a] = mg[4];
+            // fast_RemoveRow (matrix_utils.cpp:183-187)
+            L.x1[hit_b] = L.x1[total - 1]; L.y1[hit_b] = L.y1[total - 1]; L.x2[hit_b] = L.x2[total - 1]; L.y2[hit_b] = L.y2[total - 1];
+            L.ang[hit_b] = L.ang[total - 1];
+        }
+        total--;
+        const int dropped = total;  // index of the slot that no longer exists
+        __syncthreads();
+        // thread-parallel memo update of the untouched rows; rows that must re-scan are queued as jobs (row, from)
+        for (int r = tid; r < total; r += PREP_THREADS) {
+            int f, rescan_from = -1;
+            if (r == hit_a || r == hit_b) {
+                rescan_from = r + 1;  // rewritten row: full scan
+                f = -1;
+            } else {
+                f = first[r];
+                if (f == hit_a || f == hit_b) { rescan_from = f; f = -1; }   // that slot holds a different line now
+                else if (f == dropped) f = -1;                               // its line lives in slot hit_b now (re-tested below)
                 double o[5];
-                bool ok = (a < marker) && merge_pred(L, a, marker, thr_ang, thr_dist, o);
-                unsigned bal = __ballot_sync(FULL, ok);
-                if (bal) {
-                    int src = __ffs(bal) - 1;
-                    hit_a = base + src; hit_b = marker;
-                    for (int k = 0; k < 5; k++) mg[k] = __shfl_sync(FULL, o[k], src);
+                // the two rewritten slots, smaller index first, only where they could precede the current first hit
+                int c0 = hit_a < hit_b ? hit_a : hit_b, c1 = hit_a < hit_b ? hit_b : hit_a;
+                if (c1 >= total) c1 = -1;  // hit_b was the last slot: nothing moved there
+                bool found = false;
+                if (c0 > r && (rescan_from < 0 ? (f < 0 || c0 < f) : c0 < rescan_from)) {
+                    if (merge_pred(L, r, c0, thr_ang, thr_dist, o)) { f = c0; found = true; rescan_from = -1; }
+                }
+                if (!found && c1 > r && (rescan_from < 0 ? (f < 0 || c1 < f) : c1 < rescan_from)) {
+                    if (merge_pred(L, r, c1, thr_ang, thr_dist, o)) { f = c1; rescan_from = -1; }
                 }
             }
-        }
-        if (hit_a < 0) {
-            for (int s1 = (marker < 0 ? 0 : marker); s1 < total - 1 && hit_a < 0; s1++) {
-                for (int base = s1 + 1; base < total && hit_a < 0; base += 32) {
-                    int b = base + lane;
-                    double o[5];
-                    bool ok = (b < total) && merge_pred(L, s1, b, thr_ang, thr_dist, o);
-                    unsigned bal = __ballot_sync(FULL, ok);
-                    if (bal) {
-                        int src = __ffs(bal) - 1;
-                        hit_a = s1; hit_b = base + src;
-                        for (int k = 0; k < 5; k++) mg[k] = __shfl_sync(FULL, o[k], src);
-                    }
-                }
+            first[r] = f;
+            if (rescan_from >= 0) {
+                int slot = atomicAdd(&s_njobs, 1);
+                jobs[2 * slot] = r; jobs[2 * slot + 1] = rescan_from;
             }
         }
-        if (hit_a >= 0) {
-            if (lane == 0) {
-                L.x1[hit_a] = mg[0]; L.y1[hit_a] = mg[1]; L.x2[hit_a] = mg[2]; L.y2[hit_a] = mg[3]; L.ang[hit_a] = mg[4];
-                // fast_RemoveRow (matrix_utils.cpp:183-187)
-                L.x1[hit_b] = L.x1[total - 1]; L.y1[hit_b] = L.y1[total - 1]; L.x2[hit_b] = L.x2[total - 1]; L.y2[hit_b] = L.y2[total - 1];
-                L.ang[hit_b] = L.ang[total - 1];
-            }
-            total--;
-            marker = hit_a;
-            can_force_merge = true;
-            __syncwarp();
+        __syncthreads();
+        const int nj = s_njobs;
+        for (int q = warp; q < nj; q += PREP_WARPS) {
+            const int row = jobs[2 * q], from = jobs[2 * q + 1];
+            int f = scan_row(row, from);
+            if (lane == 0) first[row] = f;
         }
+        __syncthreads();
     }
 
     // (3) length filter > 30 px (object_3d_util.cpp:517-539) + angle / midpoint tables (box_proposal_detail.cpp:309-315)
     const size_t ob = (size_t)tt.line_cap_offset;
     int n_out = 0;
-    for (int base = 0; base < total; base += 32) {
-        int i = base + lane;
+    for (int base = 0; base < total; base += PREP_THREADS) {
+        int i = base + tid;
         bool keep = false;
         if (i < total) keep = norm2(V2{L.x2[i] - L.x1[i], L.y2[i] - L.y1[i]}) > 30.0;
-        unsigned bal = __ballot_sync(FULL, keep);
+        const size_t pos = ob + prep_compact(keep, s_cnt, tid, n_out);
         if (keep) {
-            size_t pos = ob + n_out + __popc(bal & ((1u << lane) - 1));
             B.ml_seg[4 * pos + 0] = L.x1[i]; B.ml_seg[4 * pos + 1] = L.y1[i]; B.ml_seg[4 * pos + 2] = L.x2[i]; B.ml_seg[4 * pos + 3] = L.y2[i];
             B.ml_ang[pos] = L.ang[i];  // == det_atan2(y2-y1, x2-x1) of the stored endpoints
             B.ml_mid[2 * pos + 0] = (L.x1[i] + L.x2[i]) / 2;
             B.ml_mid[2 * pos + 1] = (L.y1[i] + L.y2[i]) / 2;
         }
-        n_out += __popc(bal);
     }
-    if (lane == 0) B.n_merged[task] = n_out;
+    if (tid == 0) B.n_merged[task] = n_out;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -867,11 +919,11 @@ static size_t score_smem_bytes(int groups_cap, int map_cap_floats, int words_cap
 
 cudaError_t launch_prep_lines(const DetectBuffers& B, int max_lines_per_frame, cudaStream_t st) {
     int cap = max_lines_per_frame < 1 ? 1 : max_lines_per_frame;
-    size_t smem = (size_t)cap * 5 * 8;
+    size_t smem = (size_t)cap * (5 * 8 + 4 + 8 + 8);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k_prep_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_prep_lines<<<B.n_tasks, 32, smem, st>>>(B, cap);
+    k_prep_lines<<<B.n_tasks, PREP_THREADS, smem, st>>>(B, cap);
     return cudaGetLastError();
 }
 

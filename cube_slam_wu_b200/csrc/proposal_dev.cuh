@@ -343,6 +343,76 @@ __device__ __forceinline__ void wh_replace_root(const WarpHeap& H, int len, doub
     __syncwarp();
 }
 
+// ---- preferred-leaf variant used by the __heap_select phase (fixed heap length) ----------------------------------------
+// H.big doubles as pl[]: for every internal node h (2h+1 < len) the leaf reached from h by always stepping to the bigger
+// child (the single child for the last parent of an even-length heap).  The hole path of __adjust_heap(first, 0, len, ..)
+// is then the ancestor chain of pl[0] -- computed arithmetically by all lanes at once instead of a 10-step pointer chase.
+__device__ __forceinline__ int wh_depth(int node) { return 31 - __clz(node + 1); }
+__device__ __forceinline__ int wh_ancestor(int leaf, int leaf_depth, int depth) { return ((leaf + 1) >> (leaf_depth - depth)) - 1; }
+__device__ __forceinline__ int wh_pl_of(const WarpHeap& H, int node, int half) { return node < half ? H.big[node] : node; }
+
+__device__ __forceinline__ void wh_build_pl(const WarpHeap& H, int len, int lane) {
+    const int half = len >> 1;  // internal nodes are [0, half)
+    if (half == 0) return;
+    int lvl = wh_depth(half - 1);
+    for (; lvl >= 0; lvl--) {
+        const int lo = (1 << lvl) - 1;
+        int hi_node = (2 << lvl) - 2;
+        if (hi_node > half - 1) hi_node = half - 1;
+        for (int h = lo + lane; h <= hi_node; h += 32) {
+            const int bc = (2 * h + 2 < len) ? wh_bigger_child(H, h) : 2 * h + 1;
+            H.big[h] = wh_pl_of(H, bc, half);
+        }
+        __syncwarp();
+    }
+}
+
+// pl[] -> big[] (bigger child of every node with two children), in place
+__device__ __forceinline__ void wh_pl_to_big(const WarpHeap& H, int len, int lane) {
+    for (int h = lane; h < (len - 1) / 2; h += 32) {
+        const int leaf = H.big[h];
+        H.big[h] = wh_ancestor(leaf, wh_depth(leaf), wh_depth(h) + 1);
+    }
+    __syncwarp();
+}
+
+// __adjust_heap(first, 0, len, value) with the preferred-leaf table; len >= 2
+__device__ __forceinline__ void wh_replace_root_pl(const WarpHeap& H, int len, double value, int vidx, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    const int half = len >> 1;
+    const int leaf = H.big[0];
+    const int d = wh_depth(leaf);
+    const int mine = (lane <= d) ? wh_ancestor(leaf, d, lane) : 0;
+    // old contents along the path; j = number of levels 1..d whose old value is not < value (a prefix, by the heap property)
+    double ov = 0; int oi = 0;
+    if (lane <= d) { ov = H.hv[mine]; oi = H.hi[mine]; }
+    const unsigned stay = __ballot_sync(FULL, lane >= 1 && lane <= d && !(ov < value));
+    const int j = __popc(stay);
+    const double nv = __shfl_down_sync(FULL, ov, 1);
+    const int ni = __shfl_down_sync(FULL, oi, 1);
+    if (lane < j) { H.hv[mine] = nv; H.hi[mine] = ni; }
+    else if (lane == j) { H.hv[mine] = value; H.hi[mine] = vidx; }
+    __syncwarp();
+    if (j == 0) return;  // the value stays at the root: no child changed anywhere
+    // path nodes above the final slot had one child rewritten: new bigger child, then the new preferred leaf.  A node whose
+    // bigger child leaves the path ("terminal") takes that child's (unchanged) leaf; the node in the final slot keeps its own;
+    // the others inherit from the next terminal level below them.
+    bool terminal = false;
+    int tval = 0;
+    if (lane < j) {
+        const int bc = (2 * mine + 2 < len) ? wh_bigger_child(H, mine) : 2 * mine + 1;
+        if (bc != wh_ancestor(leaf, d, lane + 1)) { terminal = true; tval = wh_pl_of(H, bc, half); }
+    } else if (lane == j) {
+        terminal = true;
+        tval = wh_pl_of(H, mine, half);
+    }
+    const unsigned tb = __ballot_sync(FULL, terminal);
+    const int src = __ffs(tb & ~((1u << lane) - 1u)) - 1;  // first terminal level at or below this one (lane j always is)
+    const int nl = __shfl_sync(FULL, tval, src < 0 ? 0 : src);
+    if (lane < j) H.big[mine] = nl;
+    __syncwarp();
+}
+
 // std::partial_sort(iota, iota + k, iota + N) by vd with the libstdc++ algorithms above; on return hi[0..k) holds the heap
 // (sorted == false: hi[0] is the excluded k-th element) or the sorted prefix (sorted == true).  One warp.
 __device__ __forceinline__ void wh_partial_sort(const WarpHeap& H, const double* vd, int k, int N, bool sorted, int lane) {
@@ -350,6 +420,7 @@ __device__ __forceinline__ void wh_partial_sort(const WarpHeap& H, const double*
     for (int i = lane; i < k; i += 32) { H.hv[i] = vd[i]; H.hi[i] = i; }
     __syncwarp();
     wh_make(H, k, lane);
+    wh_build_pl(H, k, lane);  // H.big holds the preferred-leaf table during __heap_select
     // __heap_select: 32 candidates at a time; everything before the first one that beats the root is a no-op
     int i = k;
     while (i < N) {
@@ -360,10 +431,11 @@ __device__ __forceinline__ void wh_partial_sort(const WarpHeap& H, const double*
         if (!hit) { i += 32; continue; }
         const int src = __ffs(hit) - 1;
         const double v = __shfl_sync(FULL, cv, src);
-        wh_replace_root(H, k, v, i + src, lane);
+        wh_replace_root_pl(H, k, v, i + src, lane);
         i += src + 1;
     }
     if (sorted) {
+        wh_pl_to_big(H, k, lane);
         // __sort_heap: repeatedly move the root behind the shrinking heap and re-insert the former last leaf
         for (int last = k - 1; last >= 1; last--) {
             const double v = H.hv[last]; const int vi = H.hi[last];
