@@ -196,6 +196,11 @@ class Context:
         shape = (task.roi_height, task.roi_width)
         return (dm.reshape(shape), ed.reshape(shape)) if edges else dm.reshape(shape)
 
+    def score_phases(self, reset=True):
+        out = np.zeros(12, np.uint64)
+        self._chk(lib().csb_detect_debug_score_phases(self._h, _p(out), int(reset)))
+        return out
+
     def detect_upload(self, frames, boxes, lines, tasks, n_tasks, dist_maps, n_map_floats, params):
         self._nb, self._kmax = boxes.shape[0], params.max_cuboid_num
         self._chk(lib().csb_detect_upload(*self._args(frames, boxes, lines, tasks, n_tasks, dist_maps, n_map_floats, params)))

@@ -44,7 +44,7 @@ void csb_destroy(csb_context* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DetectState& d = c->det;
-    DevBuf* bufs[] = {&d.d_tables, &d.d_results, &d.d_maps, &d.d_ml_seg, &d.d_ml_ang, &d.d_ml_mid, &d.d_n_merged,
+    DevBuf* bufs[] = {&d.d_tables, &d.d_results, &d.d_maps, &d.d_ml_seg, &d.d_ml_ang, &d.d_ml_mid, &d.d_n_merged, &d.d_vp_sup,
                       &d.d_p_dist, &d.d_p_angle, &d.d_p_hyp, &d.d_keep, &d.d_norm, &d.d_cand_score, &d.d_cand_ok,
                       &d.d_sel_idx, &d.d_sel_flag, &d.d_sel_heap, &d.d_rank_idx, &d.d_counters, &d.d_dbg, &d.d_gray, &d.d_cmap, &d.d_queue, &d.d_dtmp, &d.d_flags};
     for (DevBuf* b : bufs) b->release();
@@ -244,6 +244,7 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
     CSB_CUDA(c, d.d_ml_ang.ensure(8 * LT));
     CSB_CUDA(c, d.d_ml_mid.ensure(16 * LT));
     CSB_CUDA(c, d.d_n_merged.ensure(4 * NT));
+    CSB_CUDA(c, d.d_vp_sup.ensure(48 * NT * (size_t)std::max(d.max_groups, 1)));
     CSB_CUDA(c, d.d_p_dist.ensure(8 * OT));
     CSB_CUDA(c, d.d_p_angle.ensure(8 * OT));
     CSB_CUDA(c, d.d_p_hyp.ensure(4 * OT));
@@ -270,6 +271,7 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
     B.task_order = reinterpret_cast<const int*>(db + off_order); B.box_task_begin = reinterpret_cast<const int*>(db + off_box);
     B.lines = reinterpret_cast<const double*>(db + off_lines); B.maps = d.d_maps.as<float>(); B.n_tasks = n_tasks; B.pad = 0;
     B.ml_seg = d.d_ml_seg.as<double>(); B.ml_ang = d.d_ml_ang.as<double>(); B.ml_mid = d.d_ml_mid.as<double>(); B.n_merged = d.d_n_merged.as<int>();
+    B.vp_sup = d.d_vp_sup.as<double>(); B.sup_stride = 6 * (long long)std::max(d.max_groups, 1);
     B.p_dist = d.d_p_dist.as<double>(); B.p_angle = d.d_p_angle.as<double>(); B.p_hyp = d.d_p_hyp.as<int>();
     B.n_valid = reinterpret_cast<int*>(dr + d.res_off_nvalid);
     B.keep = d.d_keep.as<int>(); B.norm_score = d.d_norm.as<double>(); B.n_keep = reinterpret_cast<int*>(dr + d.res_off_nkeep);
@@ -314,7 +316,7 @@ int csb_detect_run(csb_context* c, int timed) {
             CSB_CUDA(c, launch_distmaps(d.B, d.d_gray.as<uint8_t>(), d.d_cmap.as<uint8_t>(), d.d_queue.as<int>(), d.d_dtmp.as<unsigned>(), d.d_maps.as<float>(), d.max_roi_w, st));
         }
         if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[0], st));
-        CSB_CUDA(c, launch_prep_lines(d.B, d.max_lines_per_frame, st));
+        CSB_CUDA(c, launch_prep_lines(d.B, d.max_lines_per_frame, d.max_groups, st));
         if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[1], st));
         CSB_CUDA(c, launch_score(d.B, d.max_groups, d.max_hyp_per_task, c->num_sms, c->max_smem_optin, &d.map_cap_floats, st));
         if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[2], st));
@@ -394,6 +396,16 @@ int csb_detect_batch_gray(csb_context* c, const csb_frame* frames, int n_frames,
     rc = csb_detect_run(c, stats != nullptr);
     if (rc != CSB_OK) return rc;
     return csb_detect_download(c, cuboids_out, n_cuboids_out, stats);
+}
+
+int csb_detect_debug_score_phases(csb_context* c, uint64_t* cycles8, int reset) {  // 12 entries, see the header
+    if (!c || !cycles8) return CSB_ERR_INVALID;
+    CSB_CUDA(c, cudaSetDevice(c->device));
+    CSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    unsigned long long v[12];
+    CSB_CUDA(c, score_phase_cycles(v, reset != 0));
+    for (int i = 0; i < 12; i++) cycles8[i] = v[i];
+    return CSB_OK;
 }
 
 int csb_detect_debug_map(csb_context* c, int task_id, float* dist_map_out, uint8_t* edges_out, int capacity) {

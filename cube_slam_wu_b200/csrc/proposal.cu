@@ -74,6 +74,204 @@ __device__ __forceinline__ bool merge_pred(const LineSM& L, int a, int b, double
     return true;
 }
 
+// Per-phase cycle counters of k_score (thread 0 of every CTA, summed over CTAs and tasks; 7 atomics per task).  Read and
+// reset through csb_detect_debug_score_phases().
+__device__ unsigned long long g_score_phase_cycles[12];  // [8..10]: VP-support units decided by the float / double / exact tier
+#define SCORE_PHASE(idx)                                                            \
+    do {                                                                            \
+        if (tid == 0) {                                                             \
+            const long long now__ = clock64();                                      \
+            atomicAdd(&g_score_phase_cycles[idx], (unsigned long long)(now__ - t_prev)); \
+            t_prev = now__;                                                         \
+        }                                                                           \
+    } while (0)
+
+cudaError_t score_phase_cycles(unsigned long long* out12, bool reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out12, g_score_phase_cycles, sizeof(unsigned long long) * 12);
+    if (e != cudaSuccess) return e;
+    if (reset) {
+        unsigned long long z[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        e = cudaMemcpyToSymbol(g_score_phase_cycles, z, sizeof z);
+    }
+    return e;
+}
+
+constexpr int SCORE_THREADS = 512;
+constexpr int LINE_SMEM_CAP = 256;
+constexpr int SUBW = 8;  // lanes per VP-support unit
+
+// VP_support_edge_infos (object_3d_util.cpp:548-619) for one (vanishing point, line table) unit, executed by an 8-lane
+// sub-group; all 32 lanes of the warp run this in lock step (ballots / shuffles are warp-wide), `active` masks units that
+// do not exist.  Returns the two supporting line angles (NaN if none) on every lane of the sub-group.
+//
+// lcs (optional, n <= 64): cos/sin of every line angle.  A line supports the VP iff the angle between its direction and the
+// ray VP -> midpoint is below thr modulo pi, i.e. |cross(u_line, d)|^2 < sin^2(thr) |d|^2.  Lines that fail this test with a
+// margin of 1e-6 rad are certain outliers and never reach atan2; the remaining candidates (typically 10-20 %) are packed
+// densely onto the lanes and decided exactly as the reference does (atan2 -> normalize_to_pi -> compare).
+__device__ __forceinline__ void vp_support_unit(bool active, double vx, double vy, double thr, double s2_margin, int n, const double* ang, const double* mid,
+                                                const double* lcs, int lane, int swap_lt, double& out_low, double& out_top) {
+    const unsigned FULL = 0xffffffffu;
+    const int sl = lane & (SUBW - 1), sbase = lane & ~(SUBW - 1), sshift = sbase;
+    bool have_base = false;
+    double base = 0;
+    // lane-local extrema of the smoothed inlier angles; ties keep the lowest line index (Eigen max/minCoeff: first wins)
+    double vmax = 0, vmin = 0;
+    int imax = -1, imin = -1;
+    const bool packed = (lcs != nullptr) && (n <= 64);
+    unsigned cm_lo = 0, cm_hi = 0;  // candidate lines of this unit (bit e)
+    int n_iter = n;
+    if (packed) {
+        for (int b0 = 0; b0 < n; b0 += SUBW) {
+            const int e = b0 + sl;
+            bool cand = false;
+            if (active && e < n) {
+                const double dx = mid[2 * e] - vx, dy = mid[2 * e + 1] - vy;
+                const double cr = dx * lcs[2 * e + 1] - dy * lcs[2 * e];
+                cand = !(cr * cr > s2_margin * (dx * dx + dy * dy));  // NaN / inf -> candidate (decided exactly below)
+            }
+            const unsigned sub = (__ballot_sync(FULL, cand) >> sshift) & ((1u << SUBW) - 1);
+            if (b0 < 32) cm_lo |= sub << b0; else cm_hi |= sub << (b0 - 32);
+        }
+        n_iter = __popc(cm_lo) + __popc(cm_hi);
+        // all sub-groups of the warp must run the same number of (ballot / shuffle) rounds
+        for (int off = 16; off >= SUBW; off >>= 1) n_iter = max(n_iter, __shfl_xor_sync(FULL, n_iter, off));
+    }
+    const int n_lo = __popc(cm_lo), n_cand = n_lo + __popc(cm_hi);
+    for (int b0 = 0; b0 < n_iter; b0 += SUBW) {
+        int e = b0 + sl;
+        bool have = active && e < n;
+        if (packed) {
+            have = active && e < n_cand;
+            if (have) e = (e < n_lo) ? (int)__fns(cm_lo, 0, e + 1) : 32 + (int)__fns(cm_hi, 0, e - n_lo + 1);
+        }
+        bool inl = false;
+        double raw = 0;
+        if (have) {
+            raw = det_atan2(mid[2 * e + 1] - vy, mid[2 * e] - vx);
+            double nrm = normalize_to_pi(raw);
+            double d = fabs(ang[e] - nrm);
+            d = cmin(d, M_PI - d);
+            inl = d < thr;
+        }
+        const unsigned sub = (__ballot_sync(FULL, inl) >> sshift) & ((1u << SUBW) - 1);
+        const double cand = __shfl_sync(FULL, raw, sbase + (sub ? (__ffs(sub) - 1) : 0));
+        if (!have_base && sub) { base = cand; have_base = true; }  // smooth_jump_angles: base = first inlier (:285)
+        if (inl) {
+            double v = raw;
+            if ((raw - base) < -M_PI) v = raw + 2 * M_PI;
+            else if ((raw - base) > M_PI) v = raw - 2 * M_PI;
+            if (imax < 0) { vmax = vmin = v; imax = imin = e; }
+            else {
+                if (v > vmax) { vmax = v; imax = e; }
+                if (v < vmin) { vmin = v; imin = e; }
+            }
+        }
+    }
+#pragma unroll
+    for (int off = SUBW / 2; off > 0; off >>= 1) {
+        double ov = __shfl_xor_sync(FULL, vmax, off); int oi = __shfl_xor_sync(FULL, imax, off);
+        if (oi >= 0 && (imax < 0 || ov > vmax || (ov == vmax && oi < imax))) { vmax = ov; imax = oi; }
+        ov = __shfl_xor_sync(FULL, vmin, off); oi = __shfl_xor_sync(FULL, imin, off);
+        if (oi >= 0 && (imin < 0 || ov < vmin || (ov == vmin && oi < imin))) { vmin = ov; imin = oi; }
+    }
+    if (imax >= 0) {
+        int low = imax, top = imin;
+        if (swap_lt) { int t = low; low = top; top = t; }  // "match matlab code" (:609-610)
+        out_low = ang[low];
+        out_top = ang[top];
+    } else {
+        out_low = nan("");
+        out_top = nan("");
+    }
+}
+
+// Fast path of VP_support_edge_infos (vp_support_mixed), one THREAD per unit, no atan2.  The reference's decisions are all angle comparisons:
+//  * inlier: acute angle between the line direction u and the ray d = mid - VP below thr  <=>  cross(u, d)^2 < sin^2(thr) |d|^2;
+//  * smooth_jump_angles + max/minCoeff: with d0 the ray of the first inlier, v - base is the signed angle from d0 to d wrapped to
+//    (-pi, pi]; the largest v is the most counter-clockwise ray of the open upper half plane cross(d0, d) > 0 (d0 itself if that is
+//    empty), the smallest v the most clockwise ray of the lower half plane; inside a half plane "more counter-clockwise" is the
+//    sign of one cross product.
+// Every comparison is taken with a guard band that is orders of magnitude wider than the rounding of the arithmetic used here and of
+// the reference's atan2 / subtractions, so a decision taken here equals the reference's; anything inside a guard band (also NaN /
+// inf from a vanishing point at infinity, duplicate rays, rays opposite to d0) is escalated:
+//   float  (guards: 1e-4 rad around thr and between rays, rays shorter than 10 px refused)   -> every test, FP32 pipe
+//   double (guards: 1e-6 rad around thr, 1e-9 rad between rays)                              -> the single tests float refused, inline
+//   vp_support_unit(), the reference's expressions literally (atan2, normalize_to_pi, smooth_jump_angles) -> units with a test that
+//   double refused as well (function returns false)
+// +1: ray e is counter-clockwise of ray r, -1: clockwise, 0: cannot tell (inside the guard band even in double)
+__device__ __forceinline__ int ray_ccw(int r, float rx, float ry, float rn2, int e, float ex, float ey, float en2, double vxd, double vyd, const double* mid) {
+    const float cf = rx * ey - ry * ex;
+    if (cf * cf > 1e-8f * rn2 * en2 && rn2 > 100.0f && en2 > 100.0f) return cf > 0 ? 1 : -1;  // > 1e-4 rad apart, rays longer than 10 px
+    const double ax = mid[2 * r] - vxd, ay = mid[2 * r + 1] - vyd, bx = mid[2 * e] - vxd, by = mid[2 * e + 1] - vyd;
+    const double c = ax * by - ay * bx;
+    if (c * c > 1e-18 * (ax * ax + ay * ay) * (bx * bx + by * by)) return c > 0 ? 1 : -1;        // > 1e-9 rad apart
+    return 0;
+}
+
+__device__ __forceinline__ bool vp_support_mixed(double vxd, double vyd, float s2_lo_f, float s2_hi_f, double s2_lo_d, double s2_hi_d, int n, const double* ang,
+                                                 const double* mid, const double* lcs, const float* midf, const float* lcsf, int swap_lt, double& out_low,
+                                                 double& out_top) {
+    const float vx = (float)vxd, vy = (float)vyd;
+    bool amb = false;
+    int ibase = -1, imax = -1, imin = -1;
+    float bx = 0, by = 0, bn2 = 0, ux = 0, uy = 0, un2 = 0, lx = 0, ly = 0, ln2 = 0;
+    for (int e0 = 0; e0 < n; e0 += 32) {
+        // inlier bits of 32 lines (registers only), then the ordering logic on the set bits, in line order
+        unsigned m = 0;
+        const int cnt = (n - e0 < 32) ? (n - e0) : 32;
+        for (int b = 0; b < cnt; b++) {
+            const int e = e0 + b;
+            const float dx = midf[2 * e] - vx, dy = midf[2 * e + 1] - vy;
+            const float cr = dx * lcsf[2 * e + 1] - dy * lcsf[2 * e];
+            const float n2 = dx * dx + dy * dy, cr2 = cr * cr;
+            bool in = cr2 < s2_lo_f * n2;
+            const bool out = cr2 > s2_hi_f * n2;
+            if (!(in || out) || !(n2 > 100.0f)) {
+                const double ddx = mid[2 * e] - vxd, ddy = mid[2 * e + 1] - vyd;
+                const double dcr = ddx * lcs[2 * e + 1] - ddy * lcs[2 * e];
+                const double dn2 = ddx * ddx + ddy * ddy, dcr2 = dcr * dcr;
+                const bool in_d = dcr2 < s2_lo_d * dn2, out_d = dcr2 > s2_hi_d * dn2;
+                if (!(in_d || out_d)) amb = true;
+                in = in_d;
+            }
+            m |= (in ? 1u : 0u) << b;
+        }
+        while (m) {
+            const int e = e0 + __ffs(m) - 1;
+            m &= m - 1;
+            const float dx = midf[2 * e] - vx, dy = midf[2 * e + 1] - vy;
+            const float n2 = dx * dx + dy * dy;
+            if (ibase < 0) { ibase = e; bx = dx; by = dy; bn2 = n2; }
+            else {
+                const int side = ray_ccw(ibase, bx, by, bn2, e, dx, dy, n2, vxd, vyd, mid);  // upper / lower half plane of d0
+                if (side == 0) amb = true;  // along d0 or opposite to it
+                else if (side > 0) {
+                    if (imax < 0) { imax = e; ux = dx; uy = dy; un2 = n2; }
+                    else {
+                        const int o = ray_ccw(imax, ux, uy, un2, e, dx, dy, n2, vxd, vyd, mid);
+                        if (o == 0) amb = true;
+                        else if (o > 0) { imax = e; ux = dx; uy = dy; un2 = n2; }
+                    }
+                } else {
+                    if (imin < 0) { imin = e; lx = dx; ly = dy; ln2 = n2; }
+                    else {
+                        const int o = ray_ccw(imin, lx, ly, ln2, e, dx, dy, n2, vxd, vyd, mid);
+                        if (o == 0) amb = true;
+                        else if (o < 0) { imin = e; lx = dx; ly = dy; ln2 = n2; }
+                    }
+                }
+            }
+        }
+    }
+    if (amb) return false;
+    if (ibase < 0) { out_low = nan(""); out_top = nan(""); return true; }
+    int low = imax >= 0 ? imax : ibase, top = imin >= 0 ? imin : ibase;
+    if (swap_lt) { int t = low; low = top; top = t; }  // "match matlab code" (:609-610)
+    out_low = ang[low];
+    out_top = ang[top];
+    return true;
+}
+
 constexpr int PREP_THREADS = 256;
 constexpr int PREP_WARPS = PREP_THREADS / 32;
 
@@ -92,8 +290,11 @@ __device__ __forceinline__ int prep_compact(bool in, int* s_cnt, int tid, int& t
     return pos;
 }
 
-// One block (8 warps) per task.  Dynamic shared memory: 5 * cap doubles + 2 * cap ints.
-__global__ void __launch_bounds__(PREP_THREADS) k_prep_lines(DetectBuffers B, int cap) {
+// One block (8 warps) per task: merged long-line table of the task's ROI, then the VP-support angles of every (roll, pitch, yaw)
+// group of the task's frame against that table (B.vp_sup, 6 doubles per group: low/top of vp1, vp2, vp3).
+// Dynamic shared memory: cap * (5 doubles + 3 ints) for the merge, cap * (5 doubles + 4 floats) for the kept-line tables,
+// amb_cap ints for the exact-tier queue.
+__global__ void __launch_bounds__(PREP_THREADS, 4) k_prep_lines(DetectBuffers B, int cap, int amb_cap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_cnt[PREP_WARPS];
     __shared__ int s_hit, s_njobs;
@@ -105,7 +306,14 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prep_lines(DetectBuffers B, in
     L.x1 = reinterpret_cast<double*>(smem_raw);
     L.y1 = L.x1 + cap; L.x2 = L.y1 + cap; L.y2 = L.x2 + cap; L.ang = L.y2 + cap;
     int* first = reinterpret_cast<int*>(L.ang + cap);
-    int* jobs = first + cap;  // rows to re-scan this round, packed (row, from) as row * 65536 + from is too small: two ints per job
+    int* jobs = first + cap;  // rows to re-scan this round: two ints (row, from) per job
+    double* k_ang = reinterpret_cast<double*>(jobs + 2 * cap + (cap & 1));  // kept lines: angle | midpoint | cos,sin | float copies
+    double* k_mid = k_ang + cap;
+    double* k_cs = k_mid + 2 * cap;
+    float* k_midf = reinterpret_cast<float*>(k_cs + 2 * cap);
+    float* k_csf = k_midf + 2 * cap;
+    int* s_amb = reinterpret_cast<int*>(k_csf + 2 * cap);
+    __shared__ int s_namb;
     const unsigned FULL = 0xffffffffu;
 
     // (1) align left->right (object_3d_util.cpp:246-258) and keep lines with both endpoints inside the expanded ROI
@@ -228,109 +436,89 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prep_lines(DetectBuffers B, in
         int i = base + tid;
         bool keep = false;
         if (i < total) keep = norm2(V2{L.x2[i] - L.x1[i], L.y2[i] - L.y1[i]}) > 30.0;
-        const size_t pos = ob + prep_compact(keep, s_cnt, tid, n_out);
+        const int lp = prep_compact(keep, s_cnt, tid, n_out);
+        const size_t pos = ob + lp;
         if (keep) {
+            const double a = L.ang[i];  // == det_atan2(y2-y1, x2-x1) of the stored endpoints
+            const double mx = (L.x1[i] + L.x2[i]) / 2, my = (L.y1[i] + L.y2[i]) / 2;
             B.ml_seg[4 * pos + 0] = L.x1[i]; B.ml_seg[4 * pos + 1] = L.y1[i]; B.ml_seg[4 * pos + 2] = L.x2[i]; B.ml_seg[4 * pos + 3] = L.y2[i];
-            B.ml_ang[pos] = L.ang[i];  // == det_atan2(y2-y1, x2-x1) of the stored endpoints
-            B.ml_mid[2 * pos + 0] = (L.x1[i] + L.x2[i]) / 2;
-            B.ml_mid[2 * pos + 1] = (L.y1[i] + L.y2[i]) / 2;
+            B.ml_ang[pos] = a;
+            B.ml_mid[2 * pos + 0] = mx;
+            B.ml_mid[2 * pos + 1] = my;
+            const double ca = cos(a), sa = sin(a);  // only feed guarded tests (vp_support_mixed) / the prefilter of vp_support_unit
+            k_ang[lp] = a; k_mid[2 * lp] = mx; k_mid[2 * lp + 1] = my; k_cs[2 * lp] = ca; k_cs[2 * lp + 1] = sa;
+            k_midf[2 * lp] = (float)mx; k_midf[2 * lp + 1] = (float)my; k_csf[2 * lp] = (float)ca; k_csf[2 * lp + 1] = (float)sa;
         }
     }
-    if (tid == 0) B.n_merged[task] = n_out;
+    if (tid == 0) { B.n_merged[task] = n_out; s_namb = 0; }
+    __syncthreads();
+
+    // (4) VP_support_edge_infos for every unit: (group, vp1), (group, vp2), (roll-pitch pair, vp3)
+    {
+        const int n_lines = n_out;
+        const int n_yaw = ft.n_yaw, n_pairs = ft.n_roll * ft.n_pitch, n_groups = n_pairs * n_yaw;
+        const int n_units = 2 * n_groups + n_pairs;
+        double* sup = B.vp_sup + (size_t)task * B.sup_stride;
+        auto unit_of = [&](int u, int& g, int& vp_id) {
+            if (u < 2 * n_groups) { g = u >> 1; vp_id = u & 1; }
+            else { g = (u - 2 * n_groups) * n_yaw; vp_id = 2; }
+        };
+        auto unit_vp = [&](int g, int vp_id, double& vx, double& vy) {
+            const int yaw_id = g % n_yaw, pair = g / n_yaw;
+            double vp[6];
+            vanishing_points(ft.KinvR[pair], ft.cosy[yaw_id], ft.siny[yaw_id], vp);
+            vx = vp_id == 0 ? vp[0] : (vp_id == 1 ? vp[2] : vp[4]);
+            vy = vp_id == 0 ? vp[1] : (vp_id == 1 ? vp[3] : vp[5]);
+        };
+        auto store_unit = [&](int g, int vp_id, double lo, double tp, int first_lane, int stride) {
+            if (vp_id < 2) { if (first_lane == 0) { sup[6 * g + 2 * vp_id] = lo; sup[6 * g + 2 * vp_id + 1] = tp; } }
+            else for (int y = first_lane; y < n_yaw; y += stride) { sup[6 * (g + y) + 4] = lo; sup[6 * (g + y) + 5] = tp; }  // vp3 is shared by the pair's yaw samples
+        };
+        // sin^2 of the guard-band edges around the 15 / 10 degree thresholds
+        const float fl12 = sinf((float)(15.0 / 180.0 * M_PI) - 1e-4f), fh12 = sinf((float)(15.0 / 180.0 * M_PI) + 1e-4f);
+        const float fl3 = sinf((float)(10.0 / 180.0 * M_PI) - 1e-4f), fh3 = sinf((float)(10.0 / 180.0 * M_PI) + 1e-4f);
+        const double dl12 = sin(15.0 / 180.0 * M_PI - 1e-6), dh12 = sin(15.0 / 180.0 * M_PI + 1e-6);
+        const double dl3 = sin(10.0 / 180.0 * M_PI - 1e-6), dh3 = sin(10.0 / 180.0 * M_PI + 1e-6);
+        for (int u = tid; u < n_units; u += PREP_THREADS) {
+            int g, vp_id;
+            unit_of(u, g, vp_id);
+            double vx, vy, lo, tp;
+            unit_vp(g, vp_id, vx, vy);
+            const bool v3 = vp_id == 2;
+            const bool ok = vp_support_mixed(vx, vy, v3 ? fl3 * fl3 : fl12 * fl12, v3 ? fh3 * fh3 : fh12 * fh12, v3 ? dl3 * dl3 : dl12 * dl12, v3 ? dh3 * dh3 : dh12 * dh12,
+                                             n_lines, k_ang, k_mid, k_cs, k_midf, k_csf, vp_id > 0, lo, tp);
+            if (ok) store_unit(g, vp_id, lo, tp, 0, 1);
+            else {
+                const int slot = atomicAdd(&s_namb, 1);
+                if (slot < amb_cap) s_amb[slot] = u;
+            }
+        }
+        __syncthreads();
+        // exact tier: 8-lane sub-groups replay the reference's expressions for the queued units
+        const int n_amb = s_namb < amb_cap ? s_namb : amb_cap;
+        constexpr int SUBS = PREP_THREADS / SUBW;
+        const int sg = tid / SUBW, sl = tid & (SUBW - 1);
+        const double* lcs = (n_lines <= 64) ? k_cs : nullptr;
+        for (int u0 = 0; u0 < n_amb; u0 += SUBS) {
+            const bool active = u0 + sg < n_amb;
+            int g = 0, vp_id = 0;
+            if (active) unit_of(s_amb[u0 + sg], g, vp_id);
+            double vx, vy, lo, tp;
+            unit_vp(g, vp_id, vx, vy);
+            vp_support_unit(active, vx, vy, (vp_id != 2 ? 15.0 : 10.0) / 180.0 * M_PI, (vp_id != 2 ? dh12 * dh12 : dh3 * dh3), n_lines, k_ang, k_mid, lcs, lane, vp_id > 0, lo, tp);
+            if (active) store_unit(g, vp_id, lo, tp, sl, SUBW);
+        }
+        if (tid == 0) {
+            atomicAdd(&g_score_phase_cycles[8], (unsigned long long)(n_units - n_amb));
+            atomicAdd(&g_score_phase_cycles[10], (unsigned long long)n_amb);
+        }
+    }
 }
+
 
 // ------------------------------------------------------------------------------------------------
 // k_score
 // ------------------------------------------------------------------------------------------------
-constexpr int SCORE_THREADS = 512;
-constexpr int LINE_SMEM_CAP = 256;
-constexpr int SUBW = 8;  // lanes per VP-support unit
-
-// VP_support_edge_infos (object_3d_util.cpp:548-619) for one (vanishing point, line table) unit, executed by an 8-lane
-// sub-group; all 32 lanes of the warp run this in lock step (ballots / shuffles are warp-wide), `active` masks units that
-// do not exist.  Returns the two supporting line angles (NaN if none) on every lane of the sub-group.
-//
-// lcs (optional, n <= 64): cos/sin of every line angle.  A line supports the VP iff the angle between its direction and the
-// ray VP -> midpoint is below thr modulo pi, i.e. |cross(u_line, d)|^2 < sin^2(thr) |d|^2.  Lines that fail this test with a
-// margin of 1e-6 rad are certain outliers and never reach atan2; the remaining candidates (typically 10-20 %) are packed
-// densely onto the lanes and decided exactly as the reference does (atan2 -> normalize_to_pi -> compare).
-__device__ __forceinline__ void vp_support_unit(bool active, double vx, double vy, double thr, double s2_margin, int n, const double* ang, const double* mid,
-                                                const double* lcs, int lane, int swap_lt, double& out_low, double& out_top) {
-    const unsigned FULL = 0xffffffffu;
-    const int sl = lane & (SUBW - 1), sbase = lane & ~(SUBW - 1), sshift = sbase;
-    bool have_base = false;
-    double base = 0;
-    // lane-local extrema of the smoothed inlier angles; ties keep the lowest line index (Eigen max/minCoeff: first wins)
-    double vmax = 0, vmin = 0;
-    int imax = -1, imin = -1;
-    const bool packed = (lcs != nullptr) && (n <= 64);
-    unsigned cm_lo = 0, cm_hi = 0;  // candidate lines of this unit (bit e)
-    int n_iter = n;
-    if (packed) {
-        for (int b0 = 0; b0 < n; b0 += SUBW) {
-            const int e = b0 + sl;
-            bool cand = false;
-            if (active && e < n) {
-                const double dx = mid[2 * e] - vx, dy = mid[2 * e + 1] - vy;
-                const double cr = dx * lcs[2 * e + 1] - dy * lcs[2 * e];
-                cand = !(cr * cr > s2_margin * (dx * dx + dy * dy));  // NaN / inf -> candidate (decided exactly below)
-            }
-            const unsigned sub = (__ballot_sync(FULL, cand) >> sshift) & ((1u << SUBW) - 1);
-            if (b0 < 32) cm_lo |= sub << b0; else cm_hi |= sub << (b0 - 32);
-        }
-        n_iter = __popc(cm_lo) + __popc(cm_hi);
-        // all sub-groups of the warp must run the same number of (ballot / shuffle) rounds
-        for (int off = 16; off >= SUBW; off >>= 1) n_iter = max(n_iter, __shfl_xor_sync(FULL, n_iter, off));
-    }
-    const int n_lo = __popc(cm_lo), n_cand = n_lo + __popc(cm_hi);
-    for (int b0 = 0; b0 < n_iter; b0 += SUBW) {
-        int e = b0 + sl;
-        bool have = active && e < n;
-        if (packed) {
-            have = active && e < n_cand;
-            if (have) e = (e < n_lo) ? (int)__fns(cm_lo, 0, e + 1) : 32 + (int)__fns(cm_hi, 0, e - n_lo + 1);
-        }
-        bool inl = false;
-        double raw = 0;
-        if (have) {
-            raw = det_atan2(mid[2 * e + 1] - vy, mid[2 * e] - vx);
-            double nrm = normalize_to_pi(raw);
-            double d = fabs(ang[e] - nrm);
-            d = cmin(d, M_PI - d);
-            inl = d < thr;
-        }
-        const unsigned sub = (__ballot_sync(FULL, inl) >> sshift) & ((1u << SUBW) - 1);
-        const double cand = __shfl_sync(FULL, raw, sbase + (sub ? (__ffs(sub) - 1) : 0));
-        if (!have_base && sub) { base = cand; have_base = true; }  // smooth_jump_angles: base = first inlier (:285)
-        if (inl) {
-            double v = raw;
-            if ((raw - base) < -M_PI) v = raw + 2 * M_PI;
-            else if ((raw - base) > M_PI) v = raw - 2 * M_PI;
-            if (imax < 0) { vmax = vmin = v; imax = imin = e; }
-            else {
-                if (v > vmax) { vmax = v; imax = e; }
-                if (v < vmin) { vmin = v; imin = e; }
-            }
-        }
-    }
-#pragma unroll
-    for (int off = SUBW / 2; off > 0; off >>= 1) {
-        double ov = __shfl_xor_sync(FULL, vmax, off); int oi = __shfl_xor_sync(FULL, imax, off);
-        if (oi >= 0 && (imax < 0 || ov > vmax || (ov == vmax && oi < imax))) { vmax = ov; imax = oi; }
-        ov = __shfl_xor_sync(FULL, vmin, off); oi = __shfl_xor_sync(FULL, imin, off);
-        if (oi >= 0 && (imin < 0 || ov < vmin || (ov == vmin && oi < imin))) { vmin = ov; imin = oi; }
-    }
-    if (imax >= 0) {
-        int low = imax, top = imin;
-        if (swap_lt) { int t = low; low = top; top = t; }  // "match matlab code" (:609-610)
-        out_low = ang[low];
-        out_top = ang[top];
-    } else {
-        out_low = nan("");
-        out_top = nan("");
-    }
-}
-
 // block-wide exclusive scan of one int per thread; s_w holds one slot per warp
 template <int THREADS>
 __device__ __forceinline__ int block_excl_scan(int v, int* s_w, int tid, int& total) {
@@ -351,8 +539,8 @@ __device__ __forceinline__ int block_excl_scan(int v, int* s_w, int tid, int& to
 
 // Persistent CTA: loops over tasks handed out by an atomic counter (largest first).
 //   (a) TMA bulk copy of the task's distance map into shared memory (lands while (b)-(d) run)
-//   (b) merged-line tables -> shared memory
-//   (c) vanishing points per (roll,pitch,yaw) group; VP-support angles by 8-lane units: (group, vp1), (group, vp2), (pair, vp3)
+//   (b) vanishing points per (roll,pitch,yaw) group -> shared memory
+//   (c) VP-support angles of the groups (computed by k_prep_lines) -> shared memory
 //   (d) phase 1: every hypothesis through the corner construction / rejection cascade -> validity bitmask (enumeration order)
 //   (e) prefix sums over the bitmask words: proposal i of the compacted list <-> hypothesis id
 //   (f) phase 2: one thread per surviving proposal (all lanes busy): corners again, 99/77 distance-map gathers, edge-angle error
@@ -361,10 +549,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) k_score(DetectBuffers B, int
     float* s_map = reinterpret_cast<float*>(smem_raw);
     double* s_vp = reinterpret_cast<double*>(smem_raw + (size_t)map_cap_floats * 4);
     double* s_sup = s_vp + 6 * (size_t)groups_cap;
-    double* s_lang = s_sup + 6 * (size_t)groups_cap;
-    double* s_lmid = s_lang + LINE_SMEM_CAP;
-    double* s_lcs = s_lmid + 2 * LINE_SMEM_CAP;  // cos, sin of the line angles (prefilter only)
-    unsigned* s_mask = reinterpret_cast<unsigned*>(s_lcs + 2 * LINE_SMEM_CAP);
+    unsigned* s_mask = reinterpret_cast<unsigned*>(s_sup + 6 * (size_t)groups_cap);
     int* s_wpre = reinterpret_cast<int*>(s_mask + words_cap);  // words_cap + 1 entries
     __shared__ uint64_t s_bar;
     __shared__ int s_task;
@@ -376,6 +561,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) k_score(DetectBuffers B, int
     if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
     __syncthreads();
     uint32_t bar_parity = 0;
+    long long t_prev = clock64();
 
     while (true) {
         if (tid == 0) {
@@ -396,13 +582,13 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) k_score(DetectBuffers B, int
         __syncthreads();
         const int slot = s_task;
         if (slot >= B.n_tasks) break;
+        SCORE_PHASE(0);  // task fetch (+ chunk wait)
         const int task = B.task_order[slot];
         const TaskTab tt = B.ttab[task];
         const FrameTab& ft = B.ftab[tt.frame_id];
         const TaskGeo geo = make_geo(tt);
         const int n_yaw = ft.n_yaw, n_pairs = ft.n_roll * ft.n_pitch;
         const int n_groups = n_pairs * n_yaw;
-        const int n_lines = B.n_merged[task];
         const int map_floats = tt.roi_w * tt.roi_h;
         const bool map_smem = map_floats <= map_cap_floats;
         const float* gmap = B.maps + tt.map_offset;
@@ -414,22 +600,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) k_score(DetectBuffers B, int
             mbar_expect_tx(&s_bar, bytes);
             tma_bulk_g2s(s_map, gmap, bytes, &s_bar);
         }
-        // (b)
-        const double* lang = B.ml_ang + tt.line_cap_offset;
-        const double* lmid = B.ml_mid + 2 * (size_t)tt.line_cap_offset;
-        if (n_lines <= LINE_SMEM_CAP) {
-            for (int i = tid; i < n_lines; i += SCORE_THREADS) {
-                const double a = lang[i];
-                s_lang[i] = a; s_lmid[2 * i] = lmid[2 * i]; s_lmid[2 * i + 1] = lmid[2 * i + 1];
-                s_lcs[2 * i] = cos(a); s_lcs[2 * i + 1] = sin(a);  // only feeds the conservative prefilter of vp_support_unit
-            }
-            lang = s_lang; lmid = s_lmid;
-        }
-        const double* lcs = (n_lines <= 64) ? s_lcs : nullptr;
-        // sin^2(thr + 1e-6): outlier test with margin (decisions near the threshold are taken exactly, via atan2)
-        const double s12 = sin(15.0 / 180.0 * M_PI + 1e-6), s3 = sin(10.0 / 180.0 * M_PI + 1e-6);
-        const double s2m12 = s12 * s12, s2m3 = s3 * s3;
-        // (c) vanishing points
+        // (b) vanishing points per group + the VP-support angles k_prep_lines left in global memory
         for (int g = tid; g < n_groups; g += SCORE_THREADS) {
             int yaw_id = g % n_yaw, pair = g / n_yaw;
             double vp[6];
@@ -437,30 +608,13 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) k_score(DetectBuffers B, int
 #pragma unroll
             for (int q = 0; q < 6; q++) s_vp[6 * g + q] = vp[q];
         }
-        __syncthreads();
         {
-            const int n_units = 2 * n_groups + n_pairs;
-            constexpr int SUBS = SCORE_THREADS / SUBW;
-            const int sg = tid / SUBW, sl = tid & (SUBW - 1);
-            for (int u0 = 0; u0 < n_units; u0 += SUBS) {
-                const int u = u0 + sg;
-                const bool active = u < n_units;
-                int g = 0, vp_id = 0, pair = 0;
-                if (active) {
-                    if (u < 2 * n_groups) { g = u >> 1; vp_id = u & 1; }
-                    else { pair = u - 2 * n_groups; g = pair * n_yaw; vp_id = 2; }
-                }
-                const double vx = s_vp[6 * g + 2 * vp_id], vy = s_vp[6 * g + 2 * vp_id + 1];
-                const double thr = (vp_id != 2 ? 15.0 : 10.0) / 180.0 * M_PI;
-                double lo, tp;
-                vp_support_unit(active, vx, vy, thr, (vp_id != 2 ? s2m12 : s2m3), n_lines, lang, lmid, lcs, lane, vp_id > 0, lo, tp);
-                if (active) {
-                    if (vp_id < 2) { if (sl == 0) { s_sup[6 * g + 2 * vp_id] = lo; s_sup[6 * g + 2 * vp_id + 1] = tp; } }
-                    else for (int y = sl; y < n_yaw; y += SUBW) { s_sup[6 * (g + y) + 4] = lo; s_sup[6 * (g + y) + 5] = tp; }  // vp3 is shared by the pair's yaw samples
-                }
-            }
+            const double* sup = B.vp_sup + (size_t)task * B.sup_stride;
+            for (int i = tid; i < 6 * n_groups; i += SCORE_THREADS) s_sup[i] = sup[i];
         }
+        SCORE_PHASE(1);
         __syncthreads();
+        SCORE_PHASE(2);  // VP support
 
         // (d) phase 1 -> validity bitmask
         const int n_hyp = tt.n_hyp;
@@ -493,6 +647,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) k_score(DetectBuffers B, int
             }
         }
         __syncthreads();
+        SCORE_PHASE(3);  // phase 1
         // (e) exclusive prefix of the word popcounts
         int n_valid = 0;
         for (int w0 = 0; w0 < n_words; w0 += SCORE_THREADS) {
@@ -505,7 +660,9 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) k_score(DetectBuffers B, int
         }
         __syncthreads();
         // (f) phase 2
+        SCORE_PHASE(4);  // prefix
         if (map_smem) { mbar_wait(&s_bar, bar_parity); bar_parity ^= 1; }
+        SCORE_PHASE(5);  // wait for the map
         for (int i = tid; i < n_valid; i += SCORE_THREADS) {
             // word containing the i-th set bit: last w with s_wpre[w] <= i
             int lo = 0, hi = n_words - 1;
@@ -530,7 +687,9 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) k_score(DetectBuffers B, int
         }
         if (tid == 0) B.n_valid[task] = n_valid;
         __syncthreads();
+        SCORE_PHASE(6);  // phase 2
     }
+    SCORE_PHASE(7);  // idle tail: exit of this CTA relative to its last task (total kernel time is the slowest CTA)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -914,16 +1073,17 @@ __global__ void k_debug_corners(DetectBuffers B, int task, double* out) {
 // launchers
 // ------------------------------------------------------------------------------------------------
 static size_t score_smem_bytes(int groups_cap, int map_cap_floats, int words_cap) {
-    return (size_t)map_cap_floats * 4 + (size_t)groups_cap * 12 * 8 + (size_t)LINE_SMEM_CAP * 5 * 8 + (size_t)(2 * words_cap + 1) * 4 + 64;
+    return (size_t)map_cap_floats * 4 + (size_t)groups_cap * 12 * 8 + (size_t)(2 * words_cap + 1) * 4 + 64;
 }
 
-cudaError_t launch_prep_lines(const DetectBuffers& B, int max_lines_per_frame, cudaStream_t st) {
+cudaError_t launch_prep_lines(const DetectBuffers& B, int max_lines_per_frame, int max_groups, cudaStream_t st) {
     int cap = max_lines_per_frame < 1 ? 1 : max_lines_per_frame;
-    size_t smem = (size_t)cap * (5 * 8 + 4 + 8 + 8);
+    const int amb_cap = 2 * max_groups + MAX_RP * MAX_RP;
+    size_t smem = (size_t)cap * (5 * 8 + 3 * 4) + 8 + (size_t)cap * (5 * 8 + 4 * 4) + (size_t)amb_cap * 4 + 16;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k_prep_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_prep_lines<<<B.n_tasks, PREP_THREADS, smem, st>>>(B, cap);
+    k_prep_lines<<<B.n_tasks, PREP_THREADS, smem, st>>>(B, cap, amb_cap);
     return cudaGetLastError();
 }
 

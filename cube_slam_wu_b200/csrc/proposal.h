@@ -22,6 +22,8 @@ struct DetectBuffers {
     double* ml_ang;
     double* ml_mid;  // 2 per merged line
     int* n_merged;
+    double* vp_sup;      // 6 doubles per (task, group): VP-support angles low/top of vp1, vp2, vp3; task stride sup_stride
+    long long sup_stride;
     // k_score outputs (compacted valid proposals in enumeration order)
     double* p_dist;
     double* p_angle;
@@ -50,12 +52,13 @@ struct DetectBuffers {
     DetectConst dc;
 };
 
-cudaError_t launch_prep_lines(const DetectBuffers& B, int max_lines_per_frame, cudaStream_t st);
+cudaError_t launch_prep_lines(const DetectBuffers& B, int max_lines_per_frame, int max_groups, cudaStream_t st);
 cudaError_t launch_score(const DetectBuffers& B, int max_groups, int max_hyp_per_task, int num_sms, int max_smem_optin, int* map_cap_floats_out, cudaStream_t st);
 cudaError_t launch_select(const DetectBuffers& B, int max_hyp_per_task, int max_smem_optin, cudaStream_t st, int* n_launches);
 cudaError_t launch_recover(const DetectBuffers& B, cudaStream_t st);
 cudaError_t launch_rank(const DetectBuffers& B, int n_boxes, cudaStream_t st);
 cudaError_t launch_distmaps(const DetectBuffers& B, const uint8_t* gray, uint8_t* cmap, int* queue, unsigned* dtmp, float* maps, int max_roi_w, cudaStream_t st);
+cudaError_t score_phase_cycles(unsigned long long* out12, bool reset);
 cudaError_t launch_debug_corners(const DetectBuffers& B, int task, int n_valid, double* out, cudaStream_t st);
 
 }  // namespace csb

@@ -142,6 +142,11 @@ int csb_detect_batch_gray(csb_context* ctx, const csb_frame* frames, int n_frame
                           const csb_detect_params* params, csb_cuboid* cuboids_out, int32_t* n_cuboids_out, csb_detect_stats* stats);
 /* Parity/debug: the distance map (and, in gray mode, the 0/1/2 Canny map: 2 = edge) of one task after a run. */
 int csb_detect_debug_map(csb_context* ctx, int task_id, float* dist_map_out, uint8_t* edges_out, int capacity);
+/* Profiling/debug: SM cycles spent per phase of the scoring kernel (thread 0 of every CTA, summed over CTAs and tasks) since the last
+ * reset: [0] task fetch / chunk wait, [1] line tables + vanishing points, [2] VP support, [3] corner construction + rejection,
+ * [4] prefix sums, [5] wait for the distance map, [6] scoring, [7] exit; [8..10] VP-support units decided by the float / double /
+ * exact tier, [11] unused.  The buffer holds 12 entries. */
+int csb_detect_debug_score_phases(csb_context* ctx, uint64_t* cycles12, int reset);
 
 /* Per-box observation records for camera-object graph assembly (object_slam/src/main_obj.cpp:643-679, :732): the best
  * cuboid of each 2D box as a g2o::cuboid measurement in the local camera frame.  Writes n_boxes x 16 doubles into a
