@@ -290,11 +290,8 @@ __device__ __forceinline__ int prep_compact(bool in, int* s_cnt, int tid, int& t
     return pos;
 }
 
-// One block (8 warps) per task: merged long-line table of the task's ROI, then the VP-support angles of every (roll, pitch, yaw)
-// group of the task's frame against that table (B.vp_sup, 6 doubles per group: low/top of vp1, vp2, vp3).
-// Dynamic shared memory: cap * (5 doubles + 3 ints) for the merge, cap * (5 doubles + 4 floats) for the kept-line tables,
-// amb_cap ints for the exact-tier queue.
-__global__ void __launch_bounds__(PREP_THREADS, 4) k_prep_lines(DetectBuffers B, int cap, int amb_cap) {
+// One block (8 warps) per task: merged long-line table of the task's ROI.  Dynamic shared memory: cap * (5 doubles + 3 ints).
+__global__ void __launch_bounds__(PREP_THREADS, 4) k_prep_lines(DetectBuffers B, int cap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_cnt[PREP_WARPS];
     __shared__ int s_hit, s_njobs;
@@ -307,13 +304,6 @@ __global__ void __launch_bounds__(PREP_THREADS, 4) k_prep_lines(DetectBuffers B,
     L.y1 = L.x1 + cap; L.x2 = L.y1 + cap; L.y2 = L.x2 + cap; L.ang = L.y2 + cap;
     int* first = reinterpret_cast<int*>(L.ang + cap);
     int* jobs = first + cap;  // rows to re-scan this round: two ints (row, from) per job
-    double* k_ang = reinterpret_cast<double*>(jobs + 2 * cap + (cap & 1));  // kept lines: angle | midpoint | cos,sin | float copies
-    double* k_mid = k_ang + cap;
-    double* k_cs = k_mid + 2 * cap;
-    float* k_midf = reinterpret_cast<float*>(k_cs + 2 * cap);
-    float* k_csf = k_midf + 2 * cap;
-    int* s_amb = reinterpret_cast<int*>(k_csf + 2 * cap);
-    __shared__ int s_namb;
     const unsigned FULL = 0xffffffffu;
 
     // (1) align left->right (object_3d_util.cpp:246-258) and keep lines with both endpoints inside the expanded ROI
@@ -436,8 +426,7 @@ __global__ void __launch_bounds__(PREP_THREADS, 4) k_prep_lines(DetectBuffers B,
         int i = base + tid;
         bool keep = false;
         if (i < total) keep = norm2(V2{L.x2[i] - L.x1[i], L.y2[i] - L.y1[i]}) > 30.0;
-        const int lp = prep_compact(keep, s_cnt, tid, n_out);
-        const size_t pos = ob + lp;
+        const size_t pos = ob + prep_compact(keep, s_cnt, tid, n_out);
         if (keep) {
             const double a = L.ang[i];  // == det_atan2(y2-y1, x2-x1) of the stored endpoints
             const double mx = (L.x1[i] + L.x2[i]) / 2, my = (L.y1[i] + L.y2[i]) / 2;
@@ -445,41 +434,72 @@ __global__ void __launch_bounds__(PREP_THREADS, 4) k_prep_lines(DetectBuffers B,
             B.ml_ang[pos] = a;
             B.ml_mid[2 * pos + 0] = mx;
             B.ml_mid[2 * pos + 1] = my;
-            const double ca = cos(a), sa = sin(a);  // only feed guarded tests (vp_support_mixed) / the prefilter of vp_support_unit
-            k_ang[lp] = a; k_mid[2 * lp] = mx; k_mid[2 * lp + 1] = my; k_cs[2 * lp] = ca; k_cs[2 * lp + 1] = sa;
-            k_midf[2 * lp] = (float)mx; k_midf[2 * lp + 1] = (float)my; k_csf[2 * lp] = (float)ca; k_csf[2 * lp + 1] = (float)sa;
         }
     }
-    if (tid == 0) { B.n_merged[task] = n_out; s_namb = 0; }
-    __syncthreads();
+    if (tid == 0) B.n_merged[task] = n_out;
+}
 
-    // (4) VP_support_edge_infos for every unit: (group, vp1), (group, vp2), (roll-pitch pair, vp3)
+// ------------------------------------------------------------------------------------------------
+// k_vp_support : VP_support_edge_infos for every unit of every task -- (group, vp1), (group, vp2), (roll-pitch pair, vp3) --
+// against the task's merged-line table; B.vp_sup gets 6 doubles per group (low/top of vp1, vp2, vp3).
+// grid = (unit chunks, tasks), VPS_THREADS units per block, one thread per unit.  Dynamic shared memory: cap * (5 doubles + 4 floats).
+// ------------------------------------------------------------------------------------------------
+constexpr int VPS_THREADS = 128;
+
+__global__ void __launch_bounds__(VPS_THREADS) k_vp_support(DetectBuffers B, int cap) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int s_amb[VPS_THREADS];
+    __shared__ int s_namb;
+    const int task = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const TaskTab& tt = B.ttab[task];
+    const FrameTab& ft = B.ftab[tt.frame_id];
+    const int n_yaw = ft.n_yaw, n_pairs = ft.n_roll * ft.n_pitch, n_groups = n_pairs * n_yaw;
+    const int n_units = 2 * n_groups + n_pairs;
+    const int u_begin = blockIdx.x * VPS_THREADS;
+    if (u_begin >= n_units) return;
+    double* k_ang = reinterpret_cast<double*>(smem_raw);  // kept lines: angle | midpoint | cos,sin | float copies
+    double* k_mid = k_ang + cap;
+    double* k_cs = k_mid + 2 * cap;
+    float* k_midf = reinterpret_cast<float*>(k_cs + 2 * cap);
+    float* k_csf = k_midf + 2 * cap;
+    const int n_lines = B.n_merged[task];
     {
-        const int n_lines = n_out;
-        const int n_yaw = ft.n_yaw, n_pairs = ft.n_roll * ft.n_pitch, n_groups = n_pairs * n_yaw;
-        const int n_units = 2 * n_groups + n_pairs;
-        double* sup = B.vp_sup + (size_t)task * B.sup_stride;
-        auto unit_of = [&](int u, int& g, int& vp_id) {
-            if (u < 2 * n_groups) { g = u >> 1; vp_id = u & 1; }
-            else { g = (u - 2 * n_groups) * n_yaw; vp_id = 2; }
-        };
-        auto unit_vp = [&](int g, int vp_id, double& vx, double& vy) {
-            const int yaw_id = g % n_yaw, pair = g / n_yaw;
-            double vp[6];
-            vanishing_points(ft.KinvR[pair], ft.cosy[yaw_id], ft.siny[yaw_id], vp);
-            vx = vp_id == 0 ? vp[0] : (vp_id == 1 ? vp[2] : vp[4]);
-            vy = vp_id == 0 ? vp[1] : (vp_id == 1 ? vp[3] : vp[5]);
-        };
-        auto store_unit = [&](int g, int vp_id, double lo, double tp, int first_lane, int stride) {
-            if (vp_id < 2) { if (first_lane == 0) { sup[6 * g + 2 * vp_id] = lo; sup[6 * g + 2 * vp_id + 1] = tp; } }
-            else for (int y = first_lane; y < n_yaw; y += stride) { sup[6 * (g + y) + 4] = lo; sup[6 * (g + y) + 5] = tp; }  // vp3 is shared by the pair's yaw samples
-        };
-        // sin^2 of the guard-band edges around the 15 / 10 degree thresholds
-        const float fl12 = sinf((float)(15.0 / 180.0 * M_PI) - 1e-4f), fh12 = sinf((float)(15.0 / 180.0 * M_PI) + 1e-4f);
-        const float fl3 = sinf((float)(10.0 / 180.0 * M_PI) - 1e-4f), fh3 = sinf((float)(10.0 / 180.0 * M_PI) + 1e-4f);
-        const double dl12 = sin(15.0 / 180.0 * M_PI - 1e-6), dh12 = sin(15.0 / 180.0 * M_PI + 1e-6);
-        const double dl3 = sin(10.0 / 180.0 * M_PI - 1e-6), dh3 = sin(10.0 / 180.0 * M_PI + 1e-6);
-        for (int u = tid; u < n_units; u += PREP_THREADS) {
+        const double* lang = B.ml_ang + tt.line_cap_offset;
+        const double* lmid = B.ml_mid + 2 * (size_t)tt.line_cap_offset;
+        for (int i = tid; i < n_lines; i += VPS_THREADS) {
+            const double a = lang[i], mx = lmid[2 * i], my = lmid[2 * i + 1];
+            const double ca = cos(a), sa = sin(a);  // only feed guarded tests (vp_support_mixed) / the prefilter of vp_support_unit
+            k_ang[i] = a; k_mid[2 * i] = mx; k_mid[2 * i + 1] = my; k_cs[2 * i] = ca; k_cs[2 * i + 1] = sa;
+            k_midf[2 * i] = (float)mx; k_midf[2 * i + 1] = (float)my; k_csf[2 * i] = (float)ca; k_csf[2 * i + 1] = (float)sa;
+        }
+        if (tid == 0) s_namb = 0;
+    }
+    __syncthreads();
+    double* sup = B.vp_sup + (size_t)task * B.sup_stride;
+    auto unit_of = [&](int u, int& g, int& vp_id) {
+        if (u < 2 * n_groups) { g = u >> 1; vp_id = u & 1; }
+        else { g = (u - 2 * n_groups) * n_yaw; vp_id = 2; }
+    };
+    auto unit_vp = [&](int g, int vp_id, double& vx, double& vy) {
+        const int yaw_id = g % n_yaw, pair = g / n_yaw;
+        double vp[6];
+        vanishing_points(ft.KinvR[pair], ft.cosy[yaw_id], ft.siny[yaw_id], vp);
+        vx = vp_id == 0 ? vp[0] : (vp_id == 1 ? vp[2] : vp[4]);
+        vy = vp_id == 0 ? vp[1] : (vp_id == 1 ? vp[3] : vp[5]);
+    };
+    auto store_unit = [&](int g, int vp_id, double lo, double tp, int first_lane, int stride) {
+        if (vp_id < 2) { if (first_lane == 0) { sup[6 * g + 2 * vp_id] = lo; sup[6 * g + 2 * vp_id + 1] = tp; } }
+        else for (int y = first_lane; y < n_yaw; y += stride) { sup[6 * (g + y) + 4] = lo; sup[6 * (g + y) + 5] = tp; }  // vp3 is shared by the pair's yaw samples
+    };
+    // sin^2 of the guard-band edges around the 15 / 10 degree thresholds
+    const float fl12 = sinf((float)(15.0 / 180.0 * M_PI) - 1e-4f), fh12 = sinf((float)(15.0 / 180.0 * M_PI) + 1e-4f);
+    const float fl3 = sinf((float)(10.0 / 180.0 * M_PI) - 1e-4f), fh3 = sinf((float)(10.0 / 180.0 * M_PI) + 1e-4f);
+    const double dl12 = sin(15.0 / 180.0 * M_PI - 1e-6), dh12 = sin(15.0 / 180.0 * M_PI + 1e-6);
+    const double dl3 = sin(10.0 / 180.0 * M_PI - 1e-6), dh3 = sin(10.0 / 180.0 * M_PI + 1e-6);
+    {
+        const int u = u_begin + tid;
+        if (u < n_units) {
             int g, vp_id;
             unit_of(u, g, vp_id);
             double vx, vy, lo, tp;
@@ -488,37 +508,31 @@ __global__ void __launch_bounds__(PREP_THREADS, 4) k_prep_lines(DetectBuffers B,
             const bool ok = vp_support_mixed(vx, vy, v3 ? fl3 * fl3 : fl12 * fl12, v3 ? fh3 * fh3 : fh12 * fh12, v3 ? dl3 * dl3 : dl12 * dl12, v3 ? dh3 * dh3 : dh12 * dh12,
                                              n_lines, k_ang, k_mid, k_cs, k_midf, k_csf, vp_id > 0, lo, tp);
             if (ok) store_unit(g, vp_id, lo, tp, 0, 1);
-            else {
-                const int slot = atomicAdd(&s_namb, 1);
-                if (slot < amb_cap) s_amb[slot] = u;
-            }
+            else s_amb[atomicAdd(&s_namb, 1)] = u;
         }
-        __syncthreads();
-        // exact tier: 8-lane sub-groups replay the reference's expressions for the queued units
-        const int n_amb = s_namb < amb_cap ? s_namb : amb_cap;
-        constexpr int SUBS = PREP_THREADS / SUBW;
-        const int sg = tid / SUBW, sl = tid & (SUBW - 1);
-        const double* lcs = (n_lines <= 64) ? k_cs : nullptr;
-        for (int u0 = 0; u0 < n_amb; u0 += SUBS) {
-            const bool active = u0 + sg < n_amb;
-            int g = 0, vp_id = 0;
-            if (active) unit_of(s_amb[u0 + sg], g, vp_id);
-            double vx, vy, lo, tp;
-            unit_vp(g, vp_id, vx, vy);
-            vp_support_unit(active, vx, vy, (vp_id != 2 ? 15.0 : 10.0) / 180.0 * M_PI, (vp_id != 2 ? dh12 * dh12 : dh3 * dh3), n_lines, k_ang, k_mid, lcs, lane, vp_id > 0, lo, tp);
-            if (active) store_unit(g, vp_id, lo, tp, sl, SUBW);
-        }
-        if (tid == 0) {
-            atomicAdd(&g_score_phase_cycles[8], (unsigned long long)(n_units - n_amb));
-            atomicAdd(&g_score_phase_cycles[10], (unsigned long long)n_amb);
-        }
+    }
+    __syncthreads();
+    // exact tier: 8-lane sub-groups replay the reference's expressions for the queued units
+    const int n_amb = s_namb;
+    constexpr int SUBS = VPS_THREADS / SUBW;
+    const int sg = tid / SUBW, sl = tid & (SUBW - 1);
+    const double* lcs = (n_lines <= 64) ? k_cs : nullptr;
+    for (int u0 = 0; u0 < n_amb; u0 += SUBS) {
+        const bool active = u0 + sg < n_amb;
+        int g = 0, vp_id = 0;
+        if (active) unit_of(s_amb[u0 + sg], g, vp_id);
+        double vx, vy, lo, tp;
+        unit_vp(g, vp_id, vx, vy);
+        vp_support_unit(active, vx, vy, (vp_id != 2 ? 15.0 : 10.0) / 180.0 * M_PI, (vp_id != 2 ? dh12 * dh12 : dh3 * dh3), n_lines, k_ang, k_mid, lcs, lane, vp_id > 0, lo, tp);
+        if (active) store_unit(g, vp_id, lo, tp, sl, SUBW);
+    }
+    if (tid == 0) {
+        const int mine = (n_units - u_begin < VPS_THREADS) ? (n_units - u_begin) : VPS_THREADS;
+        atomicAdd(&g_score_phase_cycles[8], (unsigned long long)(mine - n_amb));
+        atomicAdd(&g_score_phase_cycles[10], (unsigned long long)n_amb);
     }
 }
 
-
-// ------------------------------------------------------------------------------------------------
-// k_score
-// ------------------------------------------------------------------------------------------------
 // block-wide exclusive scan of one int per thread; s_w holds one slot per warp
 template <int THREADS>
 __device__ __forceinline__ int block_excl_scan(int v, int* s_w, int tid, int& total) {
@@ -1078,12 +1092,19 @@ static size_t score_smem_bytes(int groups_cap, int map_cap_floats, int words_cap
 
 cudaError_t launch_prep_lines(const DetectBuffers& B, int max_lines_per_frame, int max_groups, cudaStream_t st) {
     int cap = max_lines_per_frame < 1 ? 1 : max_lines_per_frame;
-    const int amb_cap = 2 * max_groups + MAX_RP * MAX_RP;
-    size_t smem = (size_t)cap * (5 * 8 + 3 * 4) + 8 + (size_t)cap * (5 * 8 + 4 * 4) + (size_t)amb_cap * 4 + 16;
+    size_t smem = (size_t)cap * (5 * 8 + 3 * 4) + 16;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k_prep_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_prep_lines<<<B.n_tasks, PREP_THREADS, smem, st>>>(B, cap, amb_cap);
+    k_prep_lines<<<B.n_tasks, PREP_THREADS, smem, st>>>(B, cap);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const size_t smem2 = (size_t)cap * (5 * 8 + 4 * 4) + 16;
+    e = cudaFuncSetAttribute(k_vp_support, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e != cudaSuccess) return e;
+    const int n_units_max = 2 * max_groups + MAX_RP * MAX_RP;
+    dim3 grid((n_units_max + VPS_THREADS - 1) / VPS_THREADS, B.n_tasks);
+    k_vp_support<<<grid, VPS_THREADS, smem2, st>>>(B, cap);
     return cudaGetLastError();
 }
 
