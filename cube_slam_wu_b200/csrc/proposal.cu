@@ -212,6 +212,8 @@ __device__ __forceinline__ bool vp_support_mixed(double vxd, double vyd, float s
                                                  const double* mid, const double* lcs, const float* midf, const float* lcsf, int swap_lt, double& out_low,
                                                  double& out_top) {
     const float vx = (float)vxd, vy = (float)vyd;
+    const float2* midf2 = reinterpret_cast<const float2*>(midf);
+    const float2* lcsf2 = reinterpret_cast<const float2*>(lcsf);
     bool amb = false;
     int ibase = -1, imax = -1, imin = -1;
     float bx = 0, by = 0, bn2 = 0, ux = 0, uy = 0, un2 = 0, lx = 0, ly = 0, ln2 = 0;
@@ -219,11 +221,13 @@ __device__ __forceinline__ bool vp_support_mixed(double vxd, double vyd, float s
         // inlier bits of 32 lines (registers only), then the ordering logic on the set bits, in line order
         unsigned m = 0;
         const int cnt = (n - e0 < 32) ? (n - e0) : 32;
+#pragma unroll 4
         for (int b = 0; b < cnt; b++) {
             const int e = e0 + b;
-            const float dx = midf[2 * e] - vx, dy = midf[2 * e + 1] - vy;
-            const float cr = dx * lcsf[2 * e + 1] - dy * lcsf[2 * e];
-            const float n2 = dx * dx + dy * dy, cr2 = cr * cr;
+            const float2 mp = midf2[e], cs = lcsf2[e];
+            const float dx = mp.x - vx, dy = mp.y - vy;
+            const float cr = __fmaf_rn(dx, cs.y, -dy * cs.x);  // guarded test: contraction is harmless here
+            const float n2 = __fmaf_rn(dx, dx, dy * dy), cr2 = cr * cr;
             bool in = cr2 < s2_lo_f * n2;
             const bool out = cr2 > s2_hi_f * n2;
             if (!(in || out) || !(n2 > 100.0f)) {
@@ -239,10 +243,26 @@ __device__ __forceinline__ bool vp_support_mixed(double vxd, double vyd, float s
         while (m) {
             const int e = e0 + __ffs(m) - 1;
             m &= m - 1;
-            const float dx = midf[2 * e] - vx, dy = midf[2 * e + 1] - vy;
-            const float n2 = dx * dx + dy * dy;
-            if (ibase < 0) { ibase = e; bx = dx; by = dy; bn2 = n2; }
-            else {
+            const float2 mp = midf2[e];
+            const float dx = mp.x - vx, dy = mp.y - vy;
+            const float n2 = __fmaf_rn(dx, dx, dy * dy);
+            // float crosses against the base ray and both current extremes (select-only fast path; the branchy generic path below
+            // runs when a needed comparison falls inside the float guard band)
+            const float cb = __fmaf_rn(bx, dy, -by * dx), cu = __fmaf_rn(ux, dy, -uy * dx), cl = __fmaf_rn(lx, dy, -ly * dx);
+            const bool longe = n2 > 100.0f;
+            const bool okb = longe && bn2 > 100.0f && cb * cb > 1e-8f * bn2 * n2;
+            const bool oku = longe && un2 > 100.0f && cu * cu > 1e-8f * un2 * n2;
+            const bool okl = longe && ln2 > 100.0f && cl * cl > 1e-8f * ln2 * n2;
+            const bool first = ibase < 0;
+            const bool upper = cb > 0;
+            const bool need_u = !first && upper && imax >= 0, need_l = !first && !upper && imin >= 0;
+            if (first || (okb && (!need_u || oku) && (!need_l || okl))) {
+                const bool take_u = !first && upper && (imax < 0 || cu > 0);
+                const bool take_l = !first && !upper && (imin < 0 || cl < 0);
+                if (first) { ibase = e; bx = dx; by = dy; bn2 = n2; }
+                if (take_u) { imax = e; ux = dx; uy = dy; un2 = n2; }
+                if (take_l) { imin = e; lx = dx; ly = dy; ln2 = n2; }
+            } else {
                 const int side = ray_ccw(ibase, bx, by, bn2, e, dx, dy, n2, vxd, vyd, mid);  // upper / lower half plane of d0
                 if (side == 0) amb = true;  // along d0 or opposite to it
                 else if (side > 0) {
@@ -688,7 +708,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) k_score(DetectBuffers B, int
             int group, top, cfg;
             decode_hyp(h, tt.n_top, group, top, cfg);
             V2 c[8];
-            construct_corners(geo, s_vp + 6 * group, (double)(tt.top_x0 + top * tt.top_step), cfg, c);
+            construct_corners<false>(geo, s_vp + 6 * group, (double)(tt.top_x0 + top * tt.top_step), cfg, c);
             const double total_angle_diff = box_edge_alignment_angle_error(s_sup + 6 * group, c, cfg);
             V2 cs[8];
 #pragma unroll
@@ -907,7 +927,7 @@ __device__ __forceinline__ int recover_object(const TaskTab& tt, const FrameTab&
     double vp[6];
     vanishing_points(ft.KinvR[pair], ft.cosy[yaw_id], ft.siny[yaw_id], vp);
     TaskGeo geo = make_geo(tt);
-    int vp1 = construct_corners(geo, vp, (double)(tt.top_x0 + top * tt.top_step), cfg, c);
+    int vp1 = construct_corners<false>(geo, vp, (double)(tt.top_x0 + top * tt.top_step), cfg, c);
     corners_to_3d(c, ft.Tnew[pair], ft.invK, o);
     return vp1;
 }

@@ -69,6 +69,8 @@ __device__ __forceinline__ void vanishing_points(const double* K, double c, doub
 // Returns vp_1_position (1 left, 2 right) or 0 if the hypothesis is rejected.  c[0..7] = corners 1..8.
 // Split in two: corner 2 (box_proposal_detail.cpp:413-461) does not depend on the configuration, so the sweep computes it once
 // per (group, top sample) and runs the rest (:467-625) for both configurations.
+// CHECK = false recomputes the corners of a hypothesis that is already known to pass: same arithmetic, rejection tests dropped.
+template <bool CHECK = true>
 __device__ __forceinline__ int construct_corner2(const TaskGeo& g, const double* vp, double c1x, V2& corner_2_top) {
     const double shorted_edge_thre = 20;
     V2 vp_1{vp[0], vp[1]};
@@ -80,20 +82,23 @@ __device__ __forceinline__ int construct_corner2(const TaskGeo& g, const double*
         if (corner_2_top.x != -1) vp_1_position = 2;
     } else
         vp_1_position = 1;
-    if (!(vp_1_position > 0)) return 0;
-    if (dist2(corner_1_top, corner_2_top) < shorted_edge_thre) return 0;
+    if (CHECK && (!(vp_1_position > 0))) return 0;
+    if (CHECK && (dist2(corner_1_top, corner_2_top) < shorted_edge_thre)) return 0;
     return vp_1_position;
 }
 
+template <bool CHECK = true>
 __device__ __forceinline__ int construct_rest(const TaskGeo& g, const double* vp, double c1x, V2 corner_2_top, int vp_1_position, int config_id, V2* c);
 
+template <bool CHECK = true>
 __device__ __forceinline__ int construct_corners(const TaskGeo& g, const double* vp, double c1x, int config_id, V2* c) {
     V2 corner_2_top;
-    int vp_1_position = construct_corner2(g, vp, c1x, corner_2_top);
-    if (vp_1_position == 0) return 0;
-    return construct_rest(g, vp, c1x, corner_2_top, vp_1_position, config_id, c);
+    int vp_1_position = construct_corner2<CHECK>(g, vp, c1x, corner_2_top);
+    if (CHECK && (vp_1_position == 0)) return 0;
+    return construct_rest<CHECK>(g, vp, c1x, corner_2_top, vp_1_position, config_id, c);
 }
 
+template <bool CHECK>
 __device__ __forceinline__ int construct_rest(const TaskGeo& g, const double* vp, double c1x, V2 corner_2_top, int vp_1_position, int config_id, V2* c) {
     const double shorted_edge_thre = 20;
     V2 vp_1{vp[0], vp[1]}, vp_2{vp[2], vp[3]}, vp_3{vp[4], vp[5]};
@@ -102,33 +107,33 @@ __device__ __forceinline__ int construct_rest(const TaskGeo& g, const double* vp
     if (config_id == 1) {
         if (vp_1_position == 1) corner_4_top = seg_hit_boundary(vp_2, corner_1_top, g.left, g.top, g.left, g.down);
         else corner_4_top = seg_hit_boundary(vp_2, corner_1_top, g.right, g.top, g.right, g.down);
-        if (corner_4_top.y == -1) return 0;
-        if (dist2(corner_1_top, corner_4_top) < shorted_edge_thre) return 0;
+        if (CHECK && (corner_4_top.y == -1)) return 0;
+        if (CHECK && (dist2(corner_1_top, corner_4_top) < shorted_edge_thre)) return 0;
         corner_3_top = line_intersect(vp_2, corner_2_top, vp_1, corner_4_top);
-        if (!inside_box(corner_3_top, g.left, g.top, g.right, g.down)) return 0;
-        if ((dist2(corner_3_top, corner_4_top) < shorted_edge_thre) || (dist2(corner_3_top, corner_2_top) < shorted_edge_thre)) return 0;
+        if (CHECK && (!inside_box(corner_3_top, g.left, g.top, g.right, g.down))) return 0;
+        if (CHECK && ((dist2(corner_3_top, corner_4_top) < shorted_edge_thre) || (dist2(corner_3_top, corner_2_top) < shorted_edge_thre))) return 0;
     } else {
         if (vp_1_position == 1) corner_3_top = seg_hit_boundary(vp_2, corner_2_top, g.left, g.top, g.left, g.down);
         else corner_3_top = seg_hit_boundary(vp_2, corner_2_top, g.right, g.top, g.right, g.down);
-        if (corner_3_top.y == -1) return 0;
-        if (dist2(corner_2_top, corner_3_top) < shorted_edge_thre) return 0;
+        if (CHECK && (corner_3_top.y == -1)) return 0;
+        if (CHECK && (dist2(corner_2_top, corner_3_top) < shorted_edge_thre)) return 0;
         corner_4_top = line_intersect(vp_1, corner_3_top, vp_2, corner_1_top);
-        if (!inside_box(corner_4_top, g.left, g.roi_t, g.right, g.roi_d)) return 0;  // sic: x from the raw box, y from the ROI (:558)
-        if ((dist2(corner_3_top, corner_4_top) < shorted_edge_thre) || (dist2(corner_4_top, corner_1_top) < shorted_edge_thre)) return 0;
+        if (CHECK && (!inside_box(corner_4_top, g.left, g.roi_t, g.right, g.roi_d))) return 0;  // sic: x from the raw box, y from the ROI (:558)
+        if (CHECK && ((dist2(corner_3_top, corner_4_top) < shorted_edge_thre) || (dist2(corner_4_top, corner_1_top) < shorted_edge_thre))) return 0;
     }
     V2 corner_5_down = seg_hit_boundary(vp_3, corner_3_top, g.left, g.down, g.right, g.down);
-    if (corner_5_down.y == -1) return 0;
-    if (dist2(corner_3_top, corner_5_down) < shorted_edge_thre) return 0;
+    if (CHECK && (corner_5_down.y == -1)) return 0;
+    if (CHECK && (dist2(corner_3_top, corner_5_down) < shorted_edge_thre)) return 0;
     V2 corner_6_down = line_intersect(vp_2, corner_5_down, vp_3, corner_2_top);
-    if (!inside_box(corner_6_down, g.roi_l, g.roi_t, g.roi_r, g.roi_d)) return 0;
-    if ((dist2(corner_6_down, corner_2_top) < shorted_edge_thre) || (dist2(corner_6_down, corner_5_down) < shorted_edge_thre)) return 0;
+    if (CHECK && (!inside_box(corner_6_down, g.roi_l, g.roi_t, g.roi_r, g.roi_d))) return 0;
+    if (CHECK && ((dist2(corner_6_down, corner_2_top) < shorted_edge_thre) || (dist2(corner_6_down, corner_5_down) < shorted_edge_thre))) return 0;
     V2 corner_7_down = line_intersect(vp_1, corner_6_down, vp_3, corner_1_top);
-    if (!inside_box(corner_7_down, g.roi_l, g.roi_t, g.roi_r, g.roi_d)) return 0;
-    if ((dist2(corner_7_down, corner_1_top) < shorted_edge_thre) || (dist2(corner_7_down, corner_6_down) < shorted_edge_thre)) return 0;
+    if (CHECK && (!inside_box(corner_7_down, g.roi_l, g.roi_t, g.roi_r, g.roi_d))) return 0;
+    if (CHECK && ((dist2(corner_7_down, corner_1_top) < shorted_edge_thre) || (dist2(corner_7_down, corner_6_down) < shorted_edge_thre))) return 0;
     V2 corner_8_down = line_intersect(vp_1, corner_5_down, vp_2, corner_7_down);
-    if (!inside_box(corner_8_down, g.roi_l, g.roi_t, g.roi_r, g.roi_d)) return 0;
-    if ((dist2(corner_8_down, corner_4_top) < shorted_edge_thre) || (dist2(corner_8_down, corner_5_down) < shorted_edge_thre) ||
-        (dist2(corner_8_down, corner_7_down) < shorted_edge_thre))
+    if (CHECK && (!inside_box(corner_8_down, g.roi_l, g.roi_t, g.roi_r, g.roi_d))) return 0;
+    if (CHECK && ((dist2(corner_8_down, corner_4_top) < shorted_edge_thre) || (dist2(corner_8_down, corner_5_down) < shorted_edge_thre) ||
+                  (dist2(corner_8_down, corner_7_down) < shorted_edge_thre)))
         return 0;
     c[0] = corner_1_top; c[1] = corner_2_top; c[2] = corner_3_top; c[3] = corner_4_top;
     c[4] = corner_5_down; c[5] = corner_6_down; c[6] = corner_7_down; c[7] = corner_8_down;
