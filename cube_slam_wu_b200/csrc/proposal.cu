@@ -96,7 +96,8 @@ cudaError_t score_phase_cycles(unsigned long long* out12, bool reset) {
     return e;
 }
 
-constexpr int SCORE_THREADS = 512;
+constexpr int SCORE_CTAS_PER_SM = 1;  // 2 x 256 threads was measured slower (maps no longer fit shared memory, coarser tail)
+constexpr int SCORE_THREADS = 512 / SCORE_CTAS_PER_SM;
 constexpr int LINE_SMEM_CAP = 256;
 constexpr int SUBW = 8;  // lanes per VP-support unit
 
@@ -578,7 +579,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int* s_w, int tid, int& to
 //   (d) phase 1: every hypothesis through the corner construction / rejection cascade -> validity bitmask (enumeration order)
 //   (e) prefix sums over the bitmask words: proposal i of the compacted list <-> hypothesis id
 //   (f) phase 2: one thread per surviving proposal (all lanes busy): corners again, 99/77 distance-map gathers, edge-angle error
-__global__ void __launch_bounds__(SCORE_THREADS, 1) k_score(DetectBuffers B, int groups_cap, int map_cap_floats, int words_cap) {
+__global__ void __launch_bounds__(SCORE_THREADS, SCORE_CTAS_PER_SM) k_score(DetectBuffers B, int groups_cap, int map_cap_floats, int words_cap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_map = reinterpret_cast<float*>(smem_raw);
     double* s_vp = reinterpret_cast<double*>(smem_raw + (size_t)map_cap_floats * 4);
@@ -1132,14 +1133,15 @@ cudaError_t launch_score(const DetectBuffers& B, int max_groups, int max_hyp_per
     const int groups_cap = max_groups;
     const int words_cap = (max_hyp_per_task + 31) / 32 + 1;
     size_t fixed = score_smem_bytes(groups_cap, 0, words_cap);
-    size_t budget = (size_t)max_smem_optin - 1024;  // static __shared__ + slack
+    // static __shared__ + slack; with two CTAs per SM each gets half of the SM's 228 KB (1 KB per CTA is reserved by the system)
+    size_t budget = SCORE_CTAS_PER_SM == 1 ? (size_t)max_smem_optin - 1024 : (size_t)(228 * 1024) / SCORE_CTAS_PER_SM - 2048;
     if (fixed + 16 * 1024 > budget) return cudaErrorInvalidValue;
     int map_cap = (int)((budget - fixed) / 4) & ~31;
     size_t smem = score_smem_bytes(groups_cap, map_cap, words_cap);
     cudaError_t e = cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (map_cap_floats_out) *map_cap_floats_out = map_cap;
-    int grid = B.n_tasks < num_sms ? B.n_tasks : num_sms;
+    int grid = B.n_tasks < SCORE_CTAS_PER_SM * num_sms ? B.n_tasks : SCORE_CTAS_PER_SM * num_sms;
     k_score<<<grid, SCORE_THREADS, smem, st>>>(B, groups_cap, map_cap, words_cap);
     return cudaGetLastError();
 }
