@@ -377,6 +377,20 @@ def run_ours(args, rank, local_rank, world):
             out["ba"] = {"metric": "ba_edges_linearised_per_sec", "value": n_edges / (ba_ms * 1e-3), "unit": "edges/s", "edges": n_edges,
                          "ms_per_linearisation": ba_ms, "config": "config#4: 200 keyframes, 50 cuboids, 4000 EdgeSE3Cuboid + 199 EdgeSE3Expmap, 200 back-to-back linearisations (L2-resident; launch/FP64 bound)",
                          "roofline": {"bound": "hbm", "achieved": ba_ach, "peak": peak, "unit": "GB/s", "frac": ba_ach / peak, "traffic": None}}
+            # Levenberg-Marquardt on the device (row f-3): 5 outer iterations from the same initial estimates, best of 3
+            try:
+                best = None
+                for _ in range(3):
+                    ctx.ba_upload_estimates(g["cams7"], g["cubes10"])
+                    _, _, so = ctx.ba_optimize(5)
+                    if best is None or so.gpu_ms < best.gpu_ms:
+                        best = so
+                out["ba"]["optimize"] = {"iterations": int(best.iterations), "linear_solves": int(best.trials), "gpu_ms": float(best.gpu_ms),
+                                         "ms_per_linear_solve": float(best.gpu_ms) / max(int(best.trials), 1), "schur_dim": int(best.schur_dim),
+                                         "chi2": float(best.chi2), "kernel_launches": int(best.n_kernel_launches),
+                                         "note": "csb_ba_optimize: cuboid elimination + reduced camera system + blocked Cholesky + LM trials on the device"}
+            except Exception as e:
+                out["ba"]["optimize"] = {"error": str(e)}
         except Exception as e:  # the headline line must still print
             out["ba"] = {"error": str(e)}
 
@@ -399,6 +413,11 @@ def run_ours(args, rank, local_rank, world):
                         O.ba_linearize(g["cams7"], g["cam_fixed"], g["cubes10"], g["cube_fixed"], E, 1); r += 1
                     out["ba"]["cpu_baseline"] = {"value": n_edges * r / (time.perf_counter() - t0), "unit": "edges/s", "cores": 1, "kind": "port",
                                                  "sample": "%d linearisations of the config#4 graph" % r}
+                    if "optimize" in out["ba"] and "gpu_ms" in out["ba"]["optimize"]:
+                        t0 = time.perf_counter()
+                        _, _, oit, ochi = O.ba_optimize(g["cams7"], g["cam_fixed"], g["cubes10"], g["cube_fixed"], E, 5)
+                        out["ba"]["optimize"]["cpu_baseline"] = {"ms": 1e3 * (time.perf_counter() - t0), "iterations": int(oit), "chi2": float(ochi), "cores": 1,
+                                                                 "kind": "port", "sample": "the same 5 LM iterations, dense LDL^T of the full system"}
             except Exception as e:
                 out["cpu_baseline"] = {"error": str(e)}
         print(json.dumps(out), flush=True)  # flush: under torchrun stdout is a block-buffered pipe/file

@@ -72,6 +72,11 @@ BA_OUT_FIELDS = ("ec_err", "ec_Ji", "ec_Jj", "ep_err", "ep_Ji", "ep_Jj", "eo_err
                  "ec_Hij", "ep_Hij", "eo_Hij", "chi2")
 
 
+class BAOptimizeStats(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("trials", C.c_int32), ("n_kernel_launches", C.c_int32), ("schur_dim", C.c_int32),
+                ("chi2", C.c_double), ("lambda_", C.c_double), ("gpu_ms", C.c_float), ("pad", C.c_float)]
+
+
 class BAOutput(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in BA_OUT_FIELDS]
 
@@ -239,6 +244,7 @@ class Context:
             a = np.ascontiguousarray(a, dt); keep.append(a); return a.ctypes.data_as(C.c_void_p)
         g = BAGraph()
         g.n_cam, g.n_cube = len(cam_fixed), len(cube_fixed)
+        self._ba_n_cam, self._ba_n_cube = len(cam_fixed), len(cube_fixed)
         g.cam_fixed, g.cube_fixed = arr(cam_fixed, np.int32), arr(cube_fixed, np.int32)
         if ec is not None and len(ec[0]):
             g.n_ec = len(ec[0]); g.ec_cam = arr(ec[0], np.int32); g.ec_cube = arr(ec[1], np.int32); g.ec_meas = arr(ec[2], np.float64); g.ec_info = arr(ec[3], np.float64)
@@ -273,6 +279,13 @@ class Context:
 
     def ba_run(self):
         self._chk(lib().csb_ba_run(self._h))
+
+    def ba_optimize(self, iterations):
+        """csb_ba_optimize(): LM on the device from the uploaded estimates.  Returns (cams7, cubes10, stats)."""
+        cams = np.zeros((self._ba_n_cam, 7)); cubes = np.zeros((self._ba_n_cube, 10))
+        st = BAOptimizeStats()
+        self._chk(lib().csb_ba_optimize(self._h, int(iterations), _p(cams), _p(cubes), C.byref(st)))
+        return cams, cubes, st
 
     def ba_download(self, jacobians=False):
         out, O = self._ba_out(jacobians)

@@ -20,121 +20,11 @@
 #include <vector>
 
 #include "ba.h"
+#include "ba_dev.cuh"
 #include "context.h"
 #include "csb_math.cuh"
 
 namespace csb {
-
-// ---- g2o::cuboid (g2o_Object.h) ----------------------------------------------------------------
-__device__ __forceinline__ Cube cube_from_vec10(const double* v) {  // fromVector :45-48 (no normalisation)
-    Cube c;
-    c.pose.r = Quat{v[6], v[3], v[4], v[5]};
-    c.pose.t = V3{v[0], v[1], v[2]};
-    c.scale = V3{v[7], v[8], v[9]};
-    return c;
-}
-__device__ __forceinline__ Cube cube_exp_update(const Cube& c, const double* u) {  // :57-63
-    Cube r;
-    r.pose = se3_mul(c.pose, se3_exp(u));
-    r.scale = V3{c.scale.x + u[6], c.scale.y + u[7], c.scale.z + u[8]};
-    return r;
-}
-__device__ __forceinline__ void cube_log_error(const Cube& self, const Cube& newone, double* res) {  // :66-73
-    SE3 pose_diff = se3_mul(se3_inverse(newone.pose), self.pose);
-    se3_log(pose_diff, res);
-    res[6] = self.scale.x - newone.scale.x; res[7] = self.scale.y - newone.scale.y; res[8] = self.scale.z - newone.scale.z;
-}
-// min_log_error :76-101 with rotate_cuboid :104-114 (yaw -90, 0, 90, 180 deg; x/y scales swap at +-90)
-__device__ __forceinline__ void cube_min_log_error(const Cube& self, const Cube& newone, double* res) {
-    double best_n = 0;
-#pragma unroll 1
-    for (int i = 0; i < 4; i++) {
-        double yaw_angle = (double)(i - 1) * M_PI / 2.0;
-        Cube rc;
-        SE3 rot = se3_make(Quat{cos(yaw_angle * 0.5), 0, 0, sin(yaw_angle * 0.5)}, V3{0, 0, 0});
-        rc.pose = se3_mul(newone.pose, rot);
-        rc.scale = newone.scale;
-        if ((yaw_angle == M_PI / 2.0) || (yaw_angle == -M_PI / 2.0) || (yaw_angle == 3 * M_PI / 2.0)) { double t = rc.scale.x; rc.scale.x = rc.scale.y; rc.scale.y = t; }
-        double e[9];
-        cube_log_error(self, rc, e);
-        double s = 0;
-#pragma unroll
-        for (int k = 0; k < 9; k++) s += e[k] * e[k];
-        double n = sqrt(s);
-        if (i == 0 || n < best_n) {  // Eigen minCoeff: first minimum
-            best_n = n;
-#pragma unroll
-            for (int k = 0; k < 9; k++) res[k] = e[k];
-        }
-    }
-}
-// projectOntoImageBbox :156-197
-__device__ __forceinline__ void cube_project_bbox(const Cube& c, const SE3& Tcw, const double* K, double* out) {
-    const M3 R = quat_to_rot(c.pose.r);
-    const M3 Rc = quat_to_rot(Tcw.r);
-    const double k0 = K[0], k1 = K[1], k2 = K[2], k3 = K[3], k4 = K[4], k5 = K[5], k6 = K[6], k7 = K[7], k8 = K[8];
-    // similarityTransform(): R * diag(scale) | t
-    const double s00 = R.m[0] * c.scale.x, s01 = R.m[1] * c.scale.y, s02 = R.m[2] * c.scale.z;
-    const double s10 = R.m[3] * c.scale.x, s11 = R.m[4] * c.scale.y, s12 = R.m[5] * c.scale.z;
-    const double s20 = R.m[6] * c.scale.x, s21 = R.m[7] * c.scale.y, s22 = R.m[8] * c.scale.z;
-    double minx = 0, miny = 0, maxx = 0, maxy = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        // corners_body (g2o_Object.h:169-171): x: 1 1 -1 -1 1 1 -1 -1 | y: 1 -1 -1 1 1 -1 -1 1 | z: -1 -1 -1 -1 1 1 1 1
-        const double bx = ((k >> 1) & 1) ? -1.0 : 1.0;
-        const double by = (((k & 3) == 0) || ((k & 3) == 3)) ? 1.0 : -1.0;
-        const double bz = (k < 4) ? -1.0 : 1.0;
-        const double w3 = ((0.0 * bx + 0.0 * by) + 0.0 * bz) + 1.0 * 1.0;
-        const double cwx = (((s00 * bx + s01 * by) + s02 * bz) + c.pose.t.x * 1.0) / w3;
-        const double cwy = (((s10 * bx + s11 * by) + s12 * bz) + c.pose.t.y * 1.0) / w3;
-        const double cwz = (((s20 * bx + s21 * by) + s22 * bz) + c.pose.t.z * 1.0) / w3;
-        const double p3 = ((0.0 * cwx + 0.0 * cwy) + 0.0 * cwz) + 1.0 * 1.0;
-        const double pcx = (((Rc.m[0] * cwx + Rc.m[1] * cwy) + Rc.m[2] * cwz) + Tcw.t.x * 1.0) / p3;
-        const double pcy = (((Rc.m[3] * cwx + Rc.m[4] * cwy) + Rc.m[5] * cwz) + Tcw.t.y * 1.0) / p3;
-        const double pcz = (((Rc.m[6] * cwx + Rc.m[7] * cwy) + Rc.m[8] * cwz) + Tcw.t.z * 1.0) / p3;
-        const double ux = (k0 * pcx + k1 * pcy) + k2 * pcz, uy = (k3 * pcx + k4 * pcy) + k5 * pcz, uz = (k6 * pcx + k7 * pcy) + k8 * pcz;
-        const double u = ux / uz, v = uy / uz;
-        if (k == 0) { minx = maxx = u; miny = maxy = v; }
-        else { if (u > maxx) maxx = u; if (u < minx) minx = u; if (v > maxy) maxy = v; if (v < miny) miny = v; }
-    }
-    out[0] = (maxx + minx) / 2; out[1] = (maxy + miny) / 2; out[2] = maxx - minx; out[3] = maxy - miny;
-}
-
-// ---- edge types ---------------------------------------------------------------------------------
-enum { EDGE_CUBOID = 0, EDGE_PROJ = 1, EDGE_ODOM = 2 };
-template <int TYPE> struct EdgeDims;
-template <> struct EdgeDims<EDGE_CUBOID> { static constexpr int D = 9, Di = 6, Dj = 9, REC = 132; };
-template <> struct EdgeDims<EDGE_PROJ> { static constexpr int D = 4, Di = 6, Dj = 9, REC = 132; };
-template <> struct EdgeDims<EDGE_ODOM> { static constexpr int D = 6, Di = 6, Dj = 6, REC = 84; };
-
-struct EdgeCtx {
-    SE3 cam;          // vertex 0 estimate (world -> camera)
-    SE3 cam2;         // odometry: vertex 1 estimate
-    Cube cube;        // vertex 1 estimate
-    Cube meas_cube;   // EdgeSE3Cuboid measurement
-    SE3 meas_se3;     // EdgeSE3Expmap measurement
-    double meas4[4];  // EdgeSE3CuboidProj measurement
-    const double* K;
-};
-
-// computeError() of the three edge classes with vertex 0 / vertex 1 replaced by (possibly perturbed) estimates
-template <int TYPE>
-__device__ __forceinline__ void edge_error(const EdgeCtx& x, const SE3& v0, const Cube& v1c, const SE3& v1s, double* e) {
-    if (TYPE == EDGE_CUBOID) {  // g2o_Object.h:250-259
-        SE3 Twc = se3_inverse(v0);
-        Cube esti;
-        esti.pose = se3_mul(Twc, x.meas_cube.pose);  // transform_from :117-122
-        esti.scale = x.meas_cube.scale;
-        cube_min_log_error(v1c, esti, e);
-    } else if (TYPE == EDGE_PROJ) {  // g2o_Object.h:279-290
-        double r[4];
-        cube_project_bbox(v1c, v0, x.K, r);
-        for (int i = 0; i < 4; i++) e[i] = r[i] - x.meas4[i];
-    } else {  // types_six_dof_expmap.h:90-99
-        SE3 err = se3_mul(se3_mul(x.meas_se3, v0), se3_inverse(v1s));
-        se3_log(err, e);
-    }
-}
 
 constexpr int LIN_THREADS = 128;  // 8 edges per CTA
 
@@ -334,6 +224,7 @@ cudaError_t ba_launch(const BABuffers& B, bool want_J, cudaStream_t st, int* n_l
 }
 
 void ba_release(BAState& s) {
+    ba_solver_release(s);
     for (void* p : s.allocs) cudaFree(p);
     s.allocs.clear();
     s.has_graph = s.has_estimates = s.ran = false;
@@ -378,6 +269,10 @@ int csb_ba_set_graph(csb_context* c, const csb_ba_graph* g) {
     auto chk = [&](const int32_t* idx, int n, int lim) { for (int i = 0; i < n; i++) if (idx[i] < 0 || idx[i] >= lim) return false; return true; };
     if (!chk(g->ec_cam, g->n_ec, g->n_cam) || !chk(g->ec_cube, g->n_ec, g->n_cube) || !chk(g->ep_cam, g->n_ep, g->n_cam) || !chk(g->ep_cube, g->n_ep, g->n_cube) ||
         !chk(g->eo_cam_i, g->n_eo, g->n_cam) || !chk(g->eo_cam_j, g->n_eo, g->n_cam)) { c->err = "edge vertex index out of range"; return CSB_ERR_INVALID; }
+    s.host.cam_fixed.assign(g->cam_fixed, g->cam_fixed + g->n_cam); s.host.cube_fixed.assign(g->cube_fixed, g->cube_fixed + g->n_cube);
+    s.host.ec_cam.assign(g->ec_cam, g->ec_cam + g->n_ec); s.host.ec_cube.assign(g->ec_cube, g->ec_cube + g->n_ec);
+    s.host.ep_cam.assign(g->ep_cam, g->ep_cam + g->n_ep); s.host.ep_cube.assign(g->ep_cube, g->ep_cube + g->n_ep);
+    s.host.eo_i.assign(g->eo_cam_i, g->eo_cam_i + g->n_eo); s.host.eo_j.assign(g->eo_cam_j, g->eo_cam_j + g->n_eo);
     BABuffers& B = s.B;
     std::memset(&B, 0, sizeof B);
     B.n_cam = g->n_cam; B.n_cube = g->n_cube; B.n_ec = g->n_ec; B.n_ep = g->n_ep; B.n_eo = g->n_eo;

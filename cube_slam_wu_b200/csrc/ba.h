@@ -29,8 +29,15 @@ struct BABuffers {
     double *H_cam, *b_cam, *H_cube, *b_cube, *chi2;
 };
 
+// host copy of the topology (structure of the reduced camera system is built from it on the first csb_ba_optimize)
+struct HostGraph {
+    std::vector<int> cam_fixed, cube_fixed, ec_cam, ec_cube, ep_cam, ep_cube, eo_i, eo_j;
+};
+
 struct BAState {
     bool has_graph = false, has_estimates = false, ran = false;
+    HostGraph host;
+    void* solver = nullptr;  // SolveState of ba_solve.cu
     int n_cam = 0, n_cube = 0, n_ec = 0, n_ep = 0, n_eo = 0;
     BABuffers B{};
     std::vector<void*> allocs;  // everything cudaMalloc'ed for the current graph
@@ -38,6 +45,7 @@ struct BAState {
 };
 
 void ba_release(BAState& s);
+void ba_solver_release(BAState& s);
 cudaError_t ba_launch(const BABuffers& B, bool want_jacobians, cudaStream_t st, int* n_launches);
 
 }  // namespace csb

@@ -1,0 +1,621 @@
+// ba_solve.cu -- Levenberg-Marquardt on the device for the camera-cuboid graph.
+//
+// What the reference does per outer iteration (Thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.cpp:61-189,
+// block_solver.hpp:353-486, linear_solver_dense.h:65-113): computeActiveErrors, buildSystem, then up to 10 trials of
+// "(H + lambda I) x = b -> oplus -> computeActiveErrors -> rho test".  Here the whole trial runs on the device:
+//
+//   k_cube_inv     (H_ll + lambda I)^-1 of every free cuboid block and t_l = that * b_l            (one thread per cuboid)
+//   k_edge_w       W_e = H_pl(e) (H_ll + lambda I)^-1 for every camera-cuboid edge                  (54 threads per edge)
+//   k_schur_blocks S_IJ = [H_pp + lambda I]_IJ - sum_e1,e2 W_e1 H_pl(e2)^T (+ odometry H_ij), lower block triangle,
+//                  one warp per 6x6 block, contributions gathered in a fixed order (no atomics)
+//   k_schur_rhs    r_I = b_I - sum_e W_e b_l(e)
+//   k_chol_*       blocked right-looking Cholesky of S (32x32 tiles): diagonal tile, panel solve, trailing update
+//   k_trsv         L y = r, L^T x = y (one CTA, 32-wide steps)
+//   k_cube_back    x_l = (H_ll + lambda I)^-1 (b_l - sum_e H_pl(e)^T x_cam(e))
+//   k_apply        trial estimates = oplus(estimates, x): cameras exp(dx) * T, cuboids pose * exp(dx), scale + ds
+//   k_edge_chi2    chi2 of every edge at the trial estimates (residual only), reduced in a fixed order
+//   k_scale        x^T (lambda x + b)
+// The reference solves the full (cuboids + cameras) dense system with Eigen's LDLT; eliminating the block-diagonal cuboid part
+// first is the same linear system, so the iterates agree to round-off.  The accept / reject logic (rho, lambda, ni) is scalar
+// and stays on the host, reading three doubles per trial.
+//
+// These kernels are not on the bit-exact path (the reference's own solve is only reproducible to round-off), so they use fma().
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "ba.h"
+#include "ba_dev.cuh"
+#include "context.h"
+
+namespace csb {
+
+struct SolveView {
+    int n_fc, n_fl;       // free cameras / free cuboids
+    int n, ld;            // Schur system size (6 * n_fc) and leading dimension (multiple of 32)
+    int n_pl;             // camera-cuboid edges with both ends free (ec first, then ep)
+    const int *cam_col, *cube_col;      // vertex -> free index or -1
+    const int *fc_cam, *fl_cube;        // free index -> vertex
+    const int *pl_cam, *pl_cube;        // per pl edge: free camera / free cuboid index
+    const int *pl_src;                  // per pl edge: index into ec_Hij (>= 0) or -1 - index into ep_Hij
+    const int *blk_ptr, *blk_I, *blk_J; // S block list (lower block triangle incl. diagonal)
+    const int2* blk_ent;                // entries: (e1, e2) Schur pair | (-1, eo) odometry block | (-2, eo) transposed
+    int n_blk;
+    const int *cam_pl_ptr, *cam_pl_e;   // pl edges of every free camera, edge order
+    const int *cube_pl_ptr, *cube_pl_e; // pl edges of every free cuboid, edge order
+    double *Ainv, *tl, *W, *S, *rhs, *x_cam, *x_cube, *scal;  // scal: [0] trial chi2, [1] scale, [2] max diag, [3] cholesky ok (1/0)
+    double *trial_cams7, *trial_cubes10, *edge_chi2;
+};
+
+__device__ __forceinline__ const double* pl_hij(const BABuffers& B, const SolveView& V, int e) {
+    const int s = V.pl_src[e];
+    return s >= 0 ? B.ec_Hij + 54 * (size_t)s : B.ep_Hij + 54 * (size_t)(-1 - s);
+}
+
+// ---- (H_ll + lambda I)^-1 by Cholesky, one thread per free cuboid ---------------------------------------------------
+__global__ void k_cube_inv(BABuffers B, SolveView V, double lambda) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= V.n_fl) return;
+    const int v = V.fl_cube[l];
+    double A[81], Li[81];
+    for (int i = 0; i < 81; i++) A[i] = B.H_cube[81 * (size_t)v + i];  // symmetric: storage order irrelevant
+    for (int i = 0; i < 9; i++) A[i * 9 + i] += lambda;
+    // Cholesky A = L L^T (lower, row-major in A)
+    bool ok = true;
+    for (int j = 0; j < 9; j++) {
+        double s = A[j * 9 + j];
+        for (int k = 0; k < j; k++) s = fma(-A[j * 9 + k], A[j * 9 + k], s);
+        if (!(s > 0)) { ok = false; s = 1; }
+        const double d = sqrt(s);
+        A[j * 9 + j] = d;
+        for (int i = j + 1; i < 9; i++) {
+            double t = A[i * 9 + j];
+            for (int k = 0; k < j; k++) t = fma(-A[i * 9 + k], A[j * 9 + k], t);
+            A[i * 9 + j] = t / d;
+        }
+    }
+    // Li = L^-1 (lower), then Ainv = Li^T Li
+    for (int c = 0; c < 9; c++)
+        for (int r = 0; r < 9; r++) {
+            if (r < c) { Li[r * 9 + c] = 0; continue; }
+            double t = (r == c) ? 1.0 : 0.0;
+            for (int k = c; k < r; k++) t = fma(-A[r * 9 + k], Li[k * 9 + c], t);
+            Li[r * 9 + c] = t / A[r * 9 + r];
+        }
+    double* out = V.Ainv + 81 * (size_t)l;
+    for (int r = 0; r < 9; r++)
+        for (int c = 0; c < 9; c++) {
+            double t = 0;
+            for (int k = (r > c ? r : c); k < 9; k++) t = fma(Li[k * 9 + r], Li[k * 9 + c], t);
+            out[r * 9 + c] = ok ? t : 0.0;
+        }
+    for (int r = 0; r < 9; r++) {
+        double t = 0;
+        for (int c = 0; c < 9; c++) t = fma(out[r * 9 + c], B.b_cube[9 * (size_t)v + c], t);
+        V.tl[9 * (size_t)l + r] = t;
+    }
+    if (!ok) V.scal[3] = 0.0;
+}
+
+// W_e (6x9, column-major like H_ij) = H_pl(e) * Ainv(l(e))
+__global__ void k_edge_w(BABuffers B, SolveView V) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = t / 54, idx = t - e * 54;
+    if (e >= V.n_pl) return;
+    const int c = idx / 6, r = idx - c * 6;
+    const double* H = pl_hij(B, V, e);
+    const double* Ai = V.Ainv + 81 * (size_t)V.pl_cube[e];
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) s = fma(H[k * 6 + r], Ai[k * 9 + c], s);
+    V.W[54 * (size_t)e + idx] = s;
+}
+
+// one warp per listed 6x6 block of the lower block triangle of S (row-major, leading dimension ld)
+__global__ void __launch_bounds__(128) k_schur_blocks(BABuffers B, SolveView V, double lambda) {
+    const int blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (blk >= V.n_blk) return;
+    const int I = V.blk_I[blk], J = V.blk_J[blk];
+    for (int el = lane; el < 36; el += 32) {
+        const int r = el / 6, c = el - r * 6;
+        double acc = 0;
+        if (I == J) {
+            acc = B.H_cam[36 * (size_t)V.fc_cam[I] + c * 6 + r];
+            if (r == c) acc += lambda;
+        }
+        for (int q = V.blk_ptr[blk]; q < V.blk_ptr[blk + 1]; q++) {
+            const int2 en = V.blk_ent[q];
+            if (en.x >= 0) {
+                const double* W = V.W + 54 * (size_t)en.x;
+                const double* H = pl_hij(B, V, en.y);
+#pragma unroll
+                for (int k = 0; k < 9; k++) acc = fma(-W[k * 6 + r], H[k * 6 + c], acc);
+            } else if (en.x == -1) acc += B.eo_Hij[36 * (size_t)en.y + c * 6 + r];   // rows = vertex i of the edge = block row
+            else acc += B.eo_Hij[36 * (size_t)en.y + r * 6 + c];                       // transposed
+        }
+        V.S[(size_t)(6 * I + r) * V.ld + 6 * J + c] = acc;
+    }
+}
+
+// padding rows/cols of S: identity on the diagonal so that the factorisation runs over full tiles
+__global__ void k_schur_pad(SolveView V) {
+    const int i = V.n + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < V.ld) { V.S[(size_t)i * V.ld + i] = 1.0; V.rhs[i] = 0.0; }
+}
+
+__global__ void k_schur_rhs(BABuffers B, SolveView V) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int I = t / 6, r = t - I * 6;
+    if (I >= V.n_fc) return;
+    double acc = B.b_cam[6 * (size_t)V.fc_cam[I] + r];
+    for (int q = V.cam_pl_ptr[I]; q < V.cam_pl_ptr[I + 1]; q++) {
+        const int e = V.cam_pl_e[q];
+        const double* W = V.W + 54 * (size_t)e;
+        const double* bl = B.b_cube + 9 * (size_t)V.fl_cube[V.pl_cube[e]];
+#pragma unroll
+        for (int k = 0; k < 9; k++) acc = fma(-W[k * 6 + r], bl[k], acc);
+    }
+    V.rhs[6 * I + r] = acc;
+}
+
+// ---- blocked Cholesky, lower, in place, row-major, 32x32 tiles ------------------------------------------------------
+constexpr int NB = 32;
+
+__global__ void __launch_bounds__(NB * NB) k_chol_diag(double* S, int ld, int k0, double* ok_flag) {
+    __shared__ double a[NB][NB + 1];
+    const int r = threadIdx.y, c = threadIdx.x;
+    a[r][c] = S[(size_t)(k0 + r) * ld + k0 + c];
+    __syncthreads();
+    for (int j = 0; j < NB; j++) {
+        if (r == j && c == j) {
+            double d = a[j][j];
+            if (!(d > 0)) { *ok_flag = 0.0; d = 1.0; }
+            a[j][j] = sqrt(d);
+        }
+        __syncthreads();
+        if (c == j && r > j) a[r][j] /= a[j][j];
+        __syncthreads();
+        if (r > j && c > j && c <= r) a[r][c] = fma(-a[r][j], a[c][j], a[r][c]);
+        __syncthreads();
+    }
+    S[(size_t)(k0 + r) * ld + k0 + c] = (c <= r) ? a[r][c] : 0.0;
+}
+
+// rows below the diagonal tile: X L11^T = A21, one thread per row
+__global__ void __launch_bounds__(64) k_chol_panel(double* S, int ld, int k0) {
+    __shared__ double l11[NB][NB + 1];
+    for (int i = threadIdx.x; i < NB * NB; i += blockDim.x) l11[i / NB][i % NB] = S[(size_t)(k0 + i / NB) * ld + k0 + i % NB];
+    __syncthreads();
+    const int row = k0 + NB + blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= ld) return;
+    double x[NB];
+    double* p = S + (size_t)row * ld + k0;
+#pragma unroll
+    for (int c = 0; c < NB; c++) x[c] = p[c];
+#pragma unroll
+    for (int c = 0; c < NB; c++) {
+        double t = x[c];
+#pragma unroll
+        for (int k = 0; k < c; k++) t = fma(-x[k], l11[c][k], t);
+        x[c] = t / l11[c][c];
+    }
+#pragma unroll
+    for (int c = 0; c < NB; c++) p[c] = x[c];
+}
+
+// trailing update of the lower triangle: C(ti, tj) -= P(ti) P(tj)^T for tiles ti >= tj behind the panel
+__global__ void __launch_bounds__(256) k_chol_update(double* S, int ld, int k0) {
+    __shared__ double pa[NB][NB + 1], pb[NB][NB + 1];
+    // linear tile index -> (ti, tj), ti >= tj
+    int t = blockIdx.x, ti = 0;
+    while (t >= ti + 1) { t -= ti + 1; ti++; }
+    const int tj = t;
+    const int r0 = k0 + NB + ti * NB, c0 = k0 + NB + tj * NB;
+    for (int i = threadIdx.x; i < NB * NB; i += 256) {
+        pa[i / NB][i % NB] = S[(size_t)(r0 + i / NB) * ld + k0 + i % NB];
+        pb[i / NB][i % NB] = S[(size_t)(c0 + i / NB) * ld + k0 + i % NB];
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double acc[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+    for (int k = 0; k < NB; k++) {
+        const double a0 = pa[ty][k], a1 = pa[ty + 16][k], b0 = pb[tx][k], b1 = pb[tx + 16][k];
+        acc[0][0] = fma(a0, b0, acc[0][0]); acc[0][1] = fma(a0, b1, acc[0][1]);
+        acc[1][0] = fma(a1, b0, acc[1][0]); acc[1][1] = fma(a1, b1, acc[1][1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int r = r0 + ty + 16 * i, c = c0 + tx + 16 * j;
+            if (c <= r) S[(size_t)r * ld + c] -= acc[i][j];
+        }
+}
+
+// L y = r then L^T x = y; one CTA, in place in `v`
+__global__ void __launch_bounds__(1024) k_trsv(const double* S, int ld, double* v) {
+    __shared__ double xs[NB];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned FULL = 0xffffffffu;
+    for (int k0 = 0; k0 < ld; k0 += NB) {
+        if (tid < 32) {
+            double y = v[k0 + lane];
+            for (int c = 0; c < NB; c++) {
+                const double lcc = S[(size_t)(k0 + c) * ld + k0 + c];
+                const double yc = __shfl_sync(FULL, y, c) / lcc;
+                if (lane == c) y = yc;
+                else if (lane > c) y = fma(-S[(size_t)(k0 + lane) * ld + k0 + c], yc, y);
+            }
+            v[k0 + lane] = y;
+            xs[lane] = y;
+        }
+        __syncthreads();
+        for (int row = k0 + NB + tid; row < ld; row += blockDim.x) {
+            const double* p = S + (size_t)row * ld + k0;
+            double t = v[row];
+#pragma unroll
+            for (int c = 0; c < NB; c++) t = fma(-p[c], xs[c], t);
+            v[row] = t;
+        }
+        __syncthreads();
+    }
+    for (int k0 = ld - NB; k0 >= 0; k0 -= NB) {
+        if (tid < 32) {
+            double x = v[k0 + lane];
+            for (int c = NB - 1; c >= 0; c--) {
+                const double lcc = S[(size_t)(k0 + c) * ld + k0 + c];
+                const double xc = __shfl_sync(FULL, x, c) / lcc;
+                if (lane == c) x = xc;
+                else if (lane < c) x = fma(-S[(size_t)(k0 + c) * ld + k0 + lane], xc, x);
+            }
+            v[k0 + lane] = x;
+            xs[lane] = x;
+        }
+        __syncthreads();
+        for (int row = tid; row < k0; row += blockDim.x) {
+            double t = v[row];
+#pragma unroll
+            for (int c = 0; c < NB; c++) t = fma(-S[(size_t)(k0 + c) * ld + row], xs[c], t);
+            v[row] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// x_l = Ainv (b_l - sum_e H_pl(e)^T x_cam(e)), one thread per (cuboid, row) after a per-cuboid gather
+__global__ void __launch_bounds__(32) k_cube_back(BABuffers B, SolveView V) {
+    const int l = blockIdx.x, lane = threadIdx.x;
+    __shared__ double g[9];
+    if (lane < 9) {
+        double acc = B.b_cube[9 * (size_t)V.fl_cube[l] + lane];
+        for (int q = V.cube_pl_ptr[l]; q < V.cube_pl_ptr[l + 1]; q++) {
+            const int e = V.cube_pl_e[q];
+            const double* H = pl_hij(B, V, e);
+            const double* xc = V.rhs + 6 * (size_t)V.pl_cam[e];
+#pragma unroll
+            for (int r = 0; r < 6; r++) acc = fma(-H[lane * 6 + r], xc[r], acc);
+        }
+        g[lane] = acc;
+    }
+    __syncwarp();
+    if (lane < 9) {
+        const double* Ai = V.Ainv + 81 * (size_t)l;
+        double t = 0;
+#pragma unroll
+        for (int c = 0; c < 9; c++) t = fma(Ai[lane * 9 + c], g[c], t);
+        V.x_cube[9 * (size_t)l + lane] = t;
+    }
+}
+
+__device__ __forceinline__ void se3_store7(const SE3& s, double* v) { v[0] = s.t.x; v[1] = s.t.y; v[2] = s.t.z; v[3] = s.r.x; v[4] = s.r.y; v[5] = s.r.z; v[6] = s.r.w; }
+
+// trial = oplus(current, x); solved == 0 -> x = 0 (the reference's behaviour when the linear solve fails)
+__global__ void k_apply(BABuffers B, SolveView V) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool solved = V.scal[3] != 0.0;
+    if (t < B.n_cam) {
+        SE3 T = se3_from_vec7(B.cams7 + 7 * (size_t)t);
+        const int I = V.cam_col[t];
+        if (I >= 0) {
+            double u[6];
+            for (int k = 0; k < 6; k++) u[k] = solved ? V.rhs[6 * I + k] : 0.0;
+            T = se3_mul(se3_exp(u), T);  // VertexSE3Expmap::oplusImpl
+        }
+        se3_store7(T, V.trial_cams7 + 7 * (size_t)t);
+    } else if (t < B.n_cam + B.n_cube) {
+        const int v = t - B.n_cam;
+        Cube c = cube_from_vec10(B.cubes10 + 10 * (size_t)v);
+        const int l = V.cube_col[v];
+        if (l >= 0) {
+            double u[9];
+            for (int k = 0; k < 9; k++) u[k] = solved ? V.x_cube[9 * (size_t)l + k] : 0.0;
+            c = cube_exp_update(c, u);  // VertexCuboid::oplusImpl
+        }
+        double* o = V.trial_cubes10 + 10 * (size_t)v;
+        se3_store7(c.pose, o);
+        o[7] = c.scale.x; o[8] = c.scale.y; o[9] = c.scale.z;
+    }
+}
+
+// chi2 of every edge at the given estimates (computeActiveErrors + Edge::chi2), one thread per edge
+__global__ void __launch_bounds__(128) k_edge_chi2(BABuffers B, const double* cams7, const double* cubes10, double* out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_all = B.n_ec + B.n_ep + B.n_eo;
+    if (t >= n_all) return;
+    EdgeCtx x;
+    double e[9], chi = 0;
+    if (t < B.n_ec) {
+        const int ee = t;
+        x.meas_cube = cube_from_vec10(B.ec_meas + 10 * (size_t)ee);
+        const SE3 cam = se3_from_vec7(cams7 + 7 * (size_t)B.ec_cam[ee]);
+        const Cube cube = cube_from_vec10(cubes10 + 10 * (size_t)B.ec_cube[ee]);
+        edge_error<EDGE_CUBOID>(x, cam, cube, cam, e);
+        const double* info = B.ec_info + 81 * (size_t)ee;
+        for (int r = 0; r < 9; r++) { double s = 0; for (int k = 0; k < 9; k++) s += info[r * 9 + k] * e[k]; chi += e[r] * s; }
+    } else if (t < B.n_ec + B.n_ep) {
+        const int ee = t - B.n_ec;
+        for (int k = 0; k < 4; k++) x.meas4[k] = B.ep_meas[4 * (size_t)ee + k];
+        x.K = B.ep_K + 9 * (size_t)ee;
+        const SE3 cam = se3_from_vec7(cams7 + 7 * (size_t)B.ep_cam[ee]);
+        const Cube cube = cube_from_vec10(cubes10 + 10 * (size_t)B.ep_cube[ee]);
+        edge_error<EDGE_PROJ>(x, cam, cube, cam, e);
+        const double* info = B.ep_info + 16 * (size_t)ee;
+        for (int r = 0; r < 4; r++) { double s = 0; for (int k = 0; k < 4; k++) s += info[r * 4 + k] * e[k]; chi += e[r] * s; }
+    } else {
+        const int ee = t - B.n_ec - B.n_ep;
+        x.meas_se3 = se3_from_vec7(B.eo_meas + 7 * (size_t)ee);
+        const SE3 ci = se3_from_vec7(cams7 + 7 * (size_t)B.eo_i[ee]), cj = se3_from_vec7(cams7 + 7 * (size_t)B.eo_j[ee]);
+        edge_error<EDGE_ODOM>(x, ci, Cube{}, cj, e);
+        const double* info = B.eo_info + 36 * (size_t)ee;
+        for (int r = 0; r < 6; r++) { double s = 0; for (int k = 0; k < 6; k++) s += info[r * 6 + k] * e[k]; chi += e[r] * s; }
+    }
+    out[t] = chi;
+}
+
+// fixed-order reductions by one warp: out[0] = sum(edge chi2), out[1] = x^T (lambda x + b) + 1e-3
+__global__ void __launch_bounds__(32) k_trial_scalars(BABuffers B, SolveView V, double lambda) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x;
+    double s = 0;
+    const int n_all = B.n_ec + B.n_ep + B.n_eo;
+    for (int i = lane; i < n_all; i += 32) s += V.edge_chi2[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(FULL, s, o);
+    double q = 0;
+    const bool solved = V.scal[3] != 0.0;
+    if (solved) {
+        for (int i = lane; i < 9 * V.n_fl; i += 32) { const double x = V.x_cube[i]; q += x * (lambda * x + B.b_cube[9 * (size_t)V.fl_cube[i / 9] + i % 9]); }
+        for (int i = lane; i < 6 * V.n_fc; i += 32) { const double x = V.rhs[i]; q += x * (lambda * x + B.b_cam[6 * (size_t)V.fc_cam[i / 6] + i % 6]); }
+    }
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_down_sync(FULL, q, o);
+    if (lane == 0) { V.scal[0] = s; V.scal[1] = q + 1e-3; }
+}
+
+__global__ void __launch_bounds__(32) k_max_diag(BABuffers B, SolveView V) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x;
+    double m = 0;
+    for (int i = lane; i < 9 * V.n_fl; i += 32) m = fmax(m, fabs(B.H_cube[81 * (size_t)V.fl_cube[i / 9] + (i % 9) * 10]));
+    for (int i = lane; i < 6 * V.n_fc; i += 32) m = fmax(m, fabs(B.H_cam[36 * (size_t)V.fc_cam[i / 6] + (i % 6) * 7]));
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(FULL, m, o));
+    if (lane == 0) V.scal[2] = m;
+}
+
+__global__ void k_set_flag(double* p, double v) { *p = v; }
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+struct SolveState {
+    bool built = false;
+    SolveView V{};
+    std::vector<void*> allocs;
+};
+
+}  // namespace csb
+
+using namespace csb;
+
+namespace {
+
+#define CSB_TRY(x) do { int rc__ = (x); if (rc__ != CSB_OK) return rc__; } while (0)
+
+template <class T>
+int up(csb_context* c, std::vector<void*>& allocs, const T** out, const std::vector<T>& h) {
+    void* p = nullptr;
+    CSB_CUDA(c, cudaMalloc(&p, std::max<size_t>(h.size(), 1) * sizeof(T)));
+    allocs.push_back(p);
+    if (!h.empty()) CSB_CUDA(c, cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = reinterpret_cast<const T*>(p);
+    return CSB_OK;
+}
+template <class T>
+int al(csb_context* c, std::vector<void*>& allocs, T** out, size_t n) {
+    void* p = nullptr;
+    CSB_CUDA(c, cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    allocs.push_back(p);
+    *out = reinterpret_cast<T*>(p);
+    return CSB_OK;
+}
+
+// Structure of the reduced camera system (what BlockSolver::buildStructure does for Hschur), built from the host copy of the graph.
+int build_solver(csb_context* c) {
+    BAState& s = c->ba;
+    SolveState* st = new SolveState();
+    s.solver = st;
+    SolveView& V = st->V;
+    const HostGraph& g = s.host;
+    std::vector<int> cam_col(s.n_cam, -1), cube_col(s.n_cube, -1), fc_cam, fl_cube;
+    for (int i = 0; i < s.n_cube; i++) if (!g.cube_fixed[i]) { cube_col[i] = (int)fl_cube.size(); fl_cube.push_back(i); }
+    for (int i = 0; i < s.n_cam; i++) if (!g.cam_fixed[i]) { cam_col[i] = (int)fc_cam.size(); fc_cam.push_back(i); }
+    V.n_fc = (int)fc_cam.size(); V.n_fl = (int)fl_cube.size();
+    V.n = 6 * V.n_fc; V.ld = ((V.n + NB - 1) / NB) * NB;
+    if (V.ld == 0) V.ld = NB;
+    std::vector<int> pl_cam, pl_cube, pl_src;
+    for (int e = 0; e < s.n_ec; e++) if (cam_col[g.ec_cam[e]] >= 0 && cube_col[g.ec_cube[e]] >= 0) { pl_cam.push_back(cam_col[g.ec_cam[e]]); pl_cube.push_back(cube_col[g.ec_cube[e]]); pl_src.push_back(e); }
+    for (int e = 0; e < s.n_ep; e++) if (cam_col[g.ep_cam[e]] >= 0 && cube_col[g.ep_cube[e]] >= 0) { pl_cam.push_back(cam_col[g.ep_cam[e]]); pl_cube.push_back(cube_col[g.ep_cube[e]]); pl_src.push_back(-1 - e); }
+    V.n_pl = (int)pl_cam.size();
+    // adjacency of pl edges
+    std::vector<std::vector<int>> cam_pl(V.n_fc), cube_pl(V.n_fl);
+    for (int e = 0; e < V.n_pl; e++) { cam_pl[pl_cam[e]].push_back(e); cube_pl[pl_cube[e]].push_back(e); }
+    auto csr = [](const std::vector<std::vector<int>>& a, std::vector<int>& ptr, std::vector<int>& idx) {
+        ptr.assign(a.size() + 1, 0);
+        for (size_t i = 0; i < a.size(); i++) { ptr[i + 1] = ptr[i] + (int)a[i].size(); idx.insert(idx.end(), a[i].begin(), a[i].end()); }
+    };
+    std::vector<int> cam_pl_ptr, cam_pl_e, cube_pl_ptr, cube_pl_e;
+    csr(cam_pl, cam_pl_ptr, cam_pl_e); csr(cube_pl, cube_pl_ptr, cube_pl_e);
+    // S block entries, keyed by (I, J) with I >= J; order inside a block: cuboid index, then e1, then e2; odometry edges last, in edge order
+    const size_t nb = (size_t)V.n_fc;
+    std::vector<std::vector<int2>> ent(nb * (nb + 1) / 2);
+    auto key = [&](int I, int J) { return (size_t)I * (I + 1) / 2 + J; };
+    for (int l = 0; l < V.n_fl; l++)
+        for (int e1 : cube_pl[l])
+            for (int e2 : cube_pl[l]) {
+                const int I = pl_cam[e1], J = pl_cam[e2];
+                if (I >= J) ent[key(I, J)].push_back(make_int2(e1, e2));
+            }
+    for (int e = 0; e < s.n_eo; e++) {
+        const int ci = cam_col[g.eo_i[e]], cj = cam_col[g.eo_j[e]];
+        if (ci < 0 || cj < 0) continue;
+        if (ci == cj) continue;  // self edges do not occur
+        if (ci > cj) ent[key(ci, cj)].push_back(make_int2(-1, e));
+        else ent[key(cj, ci)].push_back(make_int2(-2, e));
+    }
+    std::vector<int> blk_ptr{0}, blk_I, blk_J;
+    std::vector<int2> blk_ent;
+    for (int I = 0; I < V.n_fc; I++)
+        for (int J = 0; J <= I; J++) {
+            const auto& v = ent[key(I, J)];
+            if (v.empty() && I != J) continue;  // untouched off-diagonal blocks stay zero
+            blk_I.push_back(I); blk_J.push_back(J);
+            blk_ent.insert(blk_ent.end(), v.begin(), v.end());
+            blk_ptr.push_back((int)blk_ent.size());
+        }
+    V.n_blk = (int)blk_I.size();
+    auto& A = st->allocs;
+    CSB_TRY(up(c, A, &V.cam_col, cam_col)); CSB_TRY(up(c, A, &V.cube_col, cube_col)); CSB_TRY(up(c, A, &V.fc_cam, fc_cam)); CSB_TRY(up(c, A, &V.fl_cube, fl_cube));
+    CSB_TRY(up(c, A, &V.pl_cam, pl_cam)); CSB_TRY(up(c, A, &V.pl_cube, pl_cube)); CSB_TRY(up(c, A, &V.pl_src, pl_src));
+    CSB_TRY(up(c, A, &V.blk_ptr, blk_ptr)); CSB_TRY(up(c, A, &V.blk_I, blk_I)); CSB_TRY(up(c, A, &V.blk_J, blk_J)); CSB_TRY(up(c, A, &V.blk_ent, blk_ent));
+    CSB_TRY(up(c, A, &V.cam_pl_ptr, cam_pl_ptr)); CSB_TRY(up(c, A, &V.cam_pl_e, cam_pl_e)); CSB_TRY(up(c, A, &V.cube_pl_ptr, cube_pl_ptr)); CSB_TRY(up(c, A, &V.cube_pl_e, cube_pl_e));
+    CSB_TRY(al(c, A, &V.Ainv, 81 * (size_t)V.n_fl)); CSB_TRY(al(c, A, &V.tl, 9 * (size_t)V.n_fl)); CSB_TRY(al(c, A, &V.W, 54 * (size_t)V.n_pl));
+    CSB_TRY(al(c, A, &V.S, (size_t)V.ld * V.ld)); CSB_TRY(al(c, A, &V.rhs, (size_t)V.ld)); CSB_TRY(al(c, A, &V.x_cube, 9 * (size_t)V.n_fl));
+    CSB_TRY(al(c, A, &V.scal, 8)); CSB_TRY(al(c, A, &V.trial_cams7, 7 * (size_t)s.n_cam)); CSB_TRY(al(c, A, &V.trial_cubes10, 10 * (size_t)s.n_cube));
+    CSB_TRY(al(c, A, &V.edge_chi2, (size_t)(s.n_ec + s.n_ep + s.n_eo)));
+    V.x_cam = V.rhs;
+    st->built = true;
+    return CSB_OK;
+}
+
+}  // namespace
+
+namespace csb {
+void ba_solver_release(BAState& s) {
+    SolveState* st = reinterpret_cast<SolveState*>(s.solver);
+    if (!st) return;
+    for (void* p : st->allocs) cudaFree(p);
+    delete st;
+    s.solver = nullptr;
+}
+}  // namespace csb
+
+extern "C" int csb_ba_optimize(csb_context* c, int iterations, double* cams7_out, double* cubes10_out, csb_ba_optimize_stats* stats) {
+    if (!c || iterations < 0) return CSB_ERR_INVALID;
+    BAState& s = c->ba;
+    if (!s.has_graph || !s.has_estimates) { c->err = "csb_ba_optimize before graph/estimates"; return CSB_ERR_STATE; }
+    CSB_CUDA(c, cudaSetDevice(c->device));
+    if (!s.solver) CSB_TRY(build_solver(c));
+    SolveState* st = reinterpret_cast<SolveState*>(s.solver);
+    SolveView& V = st->V;
+    BABuffers& B = s.B;
+    cudaStream_t sm = c->stream;
+    const int n_edges = s.n_ec + s.n_ep + s.n_eo;
+    // OptimizationAlgorithmLevenberg state (levenberg.cpp:45-58)
+    const double tau = 1e-5, goodUp = 2. / 3., goodLow = 1. / 3.;
+    const int maxTrials = 10;
+    double lambda = -1, ni = 2;
+    int nBad = 0, it_done = 0, trials_total = 0, launches = 0;
+    double chi_final = 0, h_scal[4] = {0, 0, 0, 0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (stats) { CSB_CUDA(c, cudaEventCreate(&ev0)); CSB_CUDA(c, cudaEventCreate(&ev1)); CSB_CUDA(c, cudaEventRecord(ev0, sm)); }
+    const int tiles = V.ld / NB;
+    for (int it = 0; it < iterations; it++) {
+        int nl = 0;
+        CSB_CUDA(c, ba_launch(B, false, sm, &nl));  // computeActiveErrors + buildSystem at the current estimates
+        launches += nl;
+        if (it == 0) { k_max_diag<<<1, 32, 0, sm>>>(B, V); launches++; }
+        double h2[2];
+        CSB_CUDA(c, cudaMemcpyAsync(&h2[0], B.chi2, 8, cudaMemcpyDeviceToHost, sm));
+        CSB_CUDA(c, cudaMemcpyAsync(&h2[1], V.scal + 2, 8, cudaMemcpyDeviceToHost, sm));
+        CSB_CUDA(c, cudaStreamSynchronize(sm));
+        double currentChi = h2[0], tempChi = currentChi;
+        const double iniChi = currentChi;
+        if (it == 0) { lambda = tau * h2[1]; ni = 2; nBad = 0; }
+        double rho = 0;
+        int qmax = 0;
+        do {
+            k_set_flag<<<1, 1, 0, sm>>>(V.scal + 3, 1.0);
+            if (V.n_fl) k_cube_inv<<<(V.n_fl + 31) / 32, 32, 0, sm>>>(B, V, lambda);
+            if (V.n_pl) k_edge_w<<<(V.n_pl * 54 + 127) / 128, 128, 0, sm>>>(B, V);
+            CSB_CUDA(c, cudaMemsetAsync(V.S, 0, sizeof(double) * (size_t)V.ld * V.ld, sm));
+            if (V.n_blk) k_schur_blocks<<<(V.n_blk * 32 + 127) / 128, 128, 0, sm>>>(B, V, lambda);
+            if (V.n_fc) k_schur_rhs<<<(V.n + 127) / 128, 128, 0, sm>>>(B, V);
+            k_schur_pad<<<1, NB, 0, sm>>>(V);
+            launches += 6;
+            for (int k = 0; k < tiles; k++) {
+                const int k0 = k * NB;
+                k_chol_diag<<<1, dim3(NB, NB), 0, sm>>>(V.S, V.ld, k0, V.scal + 3);
+                launches++;
+                const int rest = V.ld - k0 - NB;
+                if (rest > 0) {
+                    k_chol_panel<<<(rest + 63) / 64, 64, 0, sm>>>(V.S, V.ld, k0);
+                    const int tt = rest / NB;
+                    k_chol_update<<<tt * (tt + 1) / 2, 256, 0, sm>>>(V.S, V.ld, k0);
+                    launches += 2;
+                }
+            }
+            k_trsv<<<1, 1024, 0, sm>>>(V.S, V.ld, V.rhs);
+            if (V.n_fl) k_cube_back<<<V.n_fl, 32, 0, sm>>>(B, V);
+            k_apply<<<(s.n_cam + s.n_cube + 127) / 128, 128, 0, sm>>>(B, V);
+            if (n_edges) k_edge_chi2<<<(n_edges + 127) / 128, 128, 0, sm>>>(B, V.trial_cams7, V.trial_cubes10, V.edge_chi2);
+            k_trial_scalars<<<1, 32, 0, sm>>>(B, V, lambda);
+            launches += 5;
+            CSB_CUDA(c, cudaGetLastError());
+            CSB_CUDA(c, cudaMemcpyAsync(h_scal, V.scal, 32, cudaMemcpyDeviceToHost, sm));
+            CSB_CUDA(c, cudaStreamSynchronize(sm));
+            const bool ok2 = h_scal[3] != 0.0;
+            tempChi = ok2 ? h_scal[0] : std::numeric_limits<double>::max();
+            rho = (currentChi - tempChi) / h_scal[1];
+            if (rho > 0 && std::isfinite(tempChi)) {
+                double alpha = 1. - std::pow((2 * rho - 1), 3);
+                alpha = std::min(alpha, goodUp);
+                const double scaleFactor = std::max(goodLow, alpha);
+                lambda *= scaleFactor; ni = 2; currentChi = tempChi;
+                // accept: the trial estimates become the estimates (discardTop)
+                CSB_CUDA(c, cudaMemcpyAsync(const_cast<double*>(B.cams7), V.trial_cams7, 56 * (size_t)s.n_cam, cudaMemcpyDeviceToDevice, sm));
+                CSB_CUDA(c, cudaMemcpyAsync(const_cast<double*>(B.cubes10), V.trial_cubes10, 80 * (size_t)s.n_cube, cudaMemcpyDeviceToDevice, sm));
+            } else {
+                lambda *= ni; ni *= 2;  // reject: estimates untouched (pop)
+            }
+            qmax++; trials_total++;
+        } while (rho < 0 && qmax < maxTrials);
+        it_done++;
+        chi_final = currentChi;
+        if (qmax == maxTrials || rho == 0) break;  // Terminate
+        if ((iniChi - currentChi) * 1e3 < iniChi) nBad++; else nBad = 0;
+        if (nBad >= 3) break;
+    }
+    if (cams7_out && s.n_cam) CSB_CUDA(c, cudaMemcpyAsync(cams7_out, B.cams7, 56 * (size_t)s.n_cam, cudaMemcpyDeviceToHost, sm));
+    if (cubes10_out && s.n_cube) CSB_CUDA(c, cudaMemcpyAsync(cubes10_out, B.cubes10, 80 * (size_t)s.n_cube, cudaMemcpyDeviceToHost, sm));
+    if (stats) CSB_CUDA(c, cudaEventRecord(ev1, sm));
+    CSB_CUDA(c, cudaStreamSynchronize(sm));
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        stats->iterations = it_done; stats->trials = trials_total; stats->n_kernel_launches = launches;
+        stats->chi2 = chi_final; stats->lambda = lambda; stats->schur_dim = V.n;
+        cudaEventElapsedTime(&stats->gpu_ms, ev0, ev1);
+        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    }
+    return CSB_OK;
+}

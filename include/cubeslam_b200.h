@@ -210,6 +210,24 @@ int csb_ba_upload_estimates(csb_context* ctx, const double* cams7, const double*
 int csb_ba_run(csb_context* ctx);
 int csb_ba_download(csb_context* ctx, const csb_ba_output* out);
 
+/* SparseOptimizer::optimize(iterations) with OptimizationAlgorithmLevenberg on the device (replaces
+ * Thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.cpp:61-189 + block_solver.hpp:353-486 + linear_solver_dense.h:65-113
+ * as configured at object_slam/src/main_obj.cpp:512-517, 803).  Works on the estimates uploaded with csb_ba_upload_estimates();
+ * every trial (cuboid elimination, reduced camera system, Cholesky, back-substitution, oplus, chi2) runs on the device, the host
+ * only takes the scalar accept/reject decision.  The optimised estimates stay on the device and are copied to cams7_out /
+ * cubes10_out (either may be NULL). */
+typedef struct csb_ba_optimize_stats {
+    int32_t iterations;        /* outer LM iterations run */
+    int32_t trials;            /* linear solves (lambda trials) over all iterations */
+    int32_t n_kernel_launches;
+    int32_t schur_dim;         /* size of the reduced camera system (6 x free cameras) */
+    double chi2;               /* activeRobustChi2 after the last accepted step */
+    double lambda;
+    float gpu_ms;              /* device time of the whole call */
+    float pad;
+} csb_ba_optimize_stats;
+int csb_ba_optimize(csb_context* ctx, int iterations, double* cams7_out, double* cubes10_out, csb_ba_optimize_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif
