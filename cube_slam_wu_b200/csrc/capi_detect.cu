@@ -195,12 +195,13 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
         d.max_groups = std::max(d.max_groups, ft.n_roll * ft.n_pitch * ft.n_yaw);
         d.max_lines_per_frame = std::max(d.max_lines_per_frame, frames[f].line_end - frames[f].line_begin);
     }
-    d.out_total = 0; d.line_cap_total = 0; d.max_hyp_per_task = 1; d.max_roi_w = 1;
+    d.out_total = 0; d.line_cap_total = 0; d.max_hyp_per_task = 1; d.max_roi_w = 1; d.max_roi_px = 1;
     for (const TaskTab& t : d.ttab) {
         d.out_total = std::max<int64_t>(d.out_total, t.out_offset + t.n_hyp);
         d.line_cap_total = std::max<int64_t>(d.line_cap_total, (int64_t)t.line_cap_offset + (frames[t.frame_id].line_end - frames[t.frame_id].line_begin));
         d.max_hyp_per_task = std::max(d.max_hyp_per_task, t.n_hyp);
         d.max_roi_w = std::max(d.max_roi_w, t.roi_w);
+        d.max_roi_px = std::max(d.max_roi_px, ((t.roi_w + 15) >> 4) * t.roi_h);  // words of the packed edge map
     }
     if (n_tasks) std::memcpy(h_ttab, d.ttab.data(), sizeof(TaskTab) * (size_t)n_tasks);
     // task queue: tasks whose slice arrives first go first; inside a slice the biggest first
@@ -258,7 +259,7 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
     CSB_CUDA(c, d.d_rank_idx.ensure(8 * OT));
     CSB_CUDA(c, d.d_counters.ensure(64));
     if (d.gray_mode) {
-        CSB_CUDA(c, d.d_cmap.ensure((size_t)nm + 64));
+        CSB_CUDA(c, d.d_cmap.ensure(4 * (size_t)nm + 64));
         CSB_CUDA(c, d.d_queue.ensure(4 * (size_t)nm + 64));
         CSB_CUDA(c, d.d_dtmp.ensure(4 * (size_t)nm + 64));
     }
@@ -313,7 +314,7 @@ int csb_detect_run(csb_context* c, int timed) {
         CSB_CUDA(c, cudaMemsetAsync(d.d_counters.p, 0, 64, st));
         if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[6], st));
         if (d.gray_mode) {
-            CSB_CUDA(c, launch_distmaps(d.B, d.d_gray.as<uint8_t>(), d.d_cmap.as<uint8_t>(), d.d_queue.as<int>(), d.d_dtmp.as<unsigned>(), d.d_maps.as<float>(), d.max_roi_w, st));
+            CSB_CUDA(c, launch_distmaps(d.B, d.d_gray.as<uint8_t>(), d.d_cmap.as<uint8_t>(), d.d_queue.as<int>(), d.d_dtmp.as<unsigned>(), d.d_maps.as<float>(), d.max_roi_w, d.max_roi_px, st));
         }
         if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[0], st));
         CSB_CUDA(c, launch_prep_lines(d.B, d.max_lines_per_frame, d.max_groups, st));
@@ -325,7 +326,7 @@ int csb_detect_run(csb_context* c, int timed) {
         if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[3], st));
         CSB_CUDA(c, launch_recover(d.B, st));
         if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[4], st));
-        d.launches_last = 4 + nsel + (d.gray_mode ? 3 : 0);  // prep_lines, vp_support, score, recover + select launches (+ distance maps)
+        d.launches_last = 4 + nsel + (d.gray_mode ? 2 : 0);  // prep_lines, vp_support, score, recover + select launches (+ distance maps)
     } else if (timed) {
         CSB_CUDA(c, cudaEventRecord(d.ev[6], st));
         for (int i = 0; i < 5; i++) CSB_CUDA(c, cudaEventRecord(d.ev[i], st));
@@ -421,7 +422,12 @@ int csb_detect_debug_map(csb_context* c, int task_id, float* dist_map_out, uint8
     if (dist_map_out) CSB_CUDA(c, cudaMemcpy(dist_map_out, d.d_maps.as<float>() + t.map_offset, 4 * (size_t)n, cudaMemcpyDeviceToHost));
     if (edges_out) {
         if (!d.gray_mode) { c->err = "edge maps exist only after csb_detect_upload_gray"; return CSB_ERR_STATE; }
-        CSB_CUDA(c, cudaMemcpy(edges_out, d.d_cmap.as<uint8_t>() + t.map_offset, (size_t)n, cudaMemcpyDeviceToHost));
+        // device layout: 2 bits per pixel, 16 pixels per word, row pitch ceil(w / 16) words (distmap.cu)
+        const int wpr = (t.roi_w + 15) >> 4;
+        std::vector<uint32_t> packed((size_t)wpr * t.roi_h);
+        CSB_CUDA(c, cudaMemcpy(packed.data(), d.d_cmap.as<uint8_t>() + 4 * (size_t)t.map_offset, 4 * packed.size(), cudaMemcpyDeviceToHost));
+        for (int r = 0; r < t.roi_h; r++)
+            for (int col = 0; col < t.roi_w; col++) edges_out[(size_t)r * t.roi_w + col] = (uint8_t)((packed[(size_t)r * wpr + (col >> 4)] >> (2 * (col & 15))) & 3u);
     }
     return CSB_OK;
 }

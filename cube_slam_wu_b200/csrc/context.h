@@ -57,7 +57,7 @@ struct HostBuf {
 struct DetectState {
     bool uploaded = false, ran = false;
     int n_frames = 0, n_boxes = 0, n_lines = 0, n_tasks = 0;
-    int max_groups = 0, max_lines_per_frame = 0, max_hyp_per_task = 0, map_cap_floats = 0, max_roi_w = 0;
+    int max_groups = 0, max_lines_per_frame = 0, max_hyp_per_task = 0, map_cap_floats = 0, max_roi_w = 0, max_roi_px = 0;
     int64_t n_map_floats = 0, out_total = 0, line_cap_total = 0;
     csb_detect_params params{};
     std::vector<csb::TaskTab> ttab;
