@@ -47,7 +47,7 @@ class BAOut(C.Structure):
 
 def build(force=False):
     so = os.path.join(ORACLE_DIR, "liboracle.so")
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle_proposal.cpp", "oracle_ba.cpp", "oracle_math.h", "Makefile")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle_proposal.cpp", "oracle_ba.cpp", "oracle_lsd.cpp", "oracle_math.h", "Makefile")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
     return so
