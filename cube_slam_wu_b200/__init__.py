@@ -81,6 +81,16 @@ class BAOutput(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in BA_OUT_FIELDS]
 
 
+class LsdParams(C.Structure):
+    _fields_ = [("line_length_thres", C.c_float), ("filter", C.c_int32), ("max_lines", C.c_int32), ("reserved", C.c_int32)]
+
+
+class LsdStats(C.Structure):
+    _fields_ = [("n_lines", C.c_int64), ("n_regions", C.c_int64), ("n_region_px", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("scaled_width", C.c_int32), ("scaled_height", C.c_int32), ("n_kernel_launches", C.c_int32), ("reserved", C.c_int32),
+                ("gpu_ms_maps", C.c_float), ("gpu_ms_grow", C.c_float)]
+
+
 def lib():
     """Load the CUDA library; raises if it has not been built (there is no fallback path)."""
     global _LIB
@@ -291,3 +301,67 @@ class Context:
         out, O = self._ba_out(jacobians)
         self._chk(lib().csb_ba_download(self._h, C.byref(O)))
         return out
+
+    # ---- line detection (LSD) ------------------------------------------------------------------
+    def _lsd_params(self, line_length_thres, filter, max_lines):
+        self._lsd_p = LsdParams(float(line_length_thres), int(filter), int(max_lines), 0)
+        return self._lsd_p
+
+    @staticmethod
+    def _lsd_gray(gray):
+        gray = np.ascontiguousarray(gray, np.uint8)
+        if gray.ndim == 2:
+            gray = gray[None]
+        assert gray.ndim == 3
+        return gray
+
+    def lsd_detect_batch(self, gray, line_length_thres=15.0, filter=True, max_lines=4096):
+        """csb_lsd_detect_batch(): gray (n, h, w) uint8 -> list of (k_i, 4) float32 arrays [x1 y1 x2 y2], stats."""
+        gray = self._lsd_gray(gray)
+        n, h, w = gray.shape
+        P = self._lsd_params(line_length_thres, filter, max_lines)
+        lines = np.zeros((n, max_lines, 4), np.float32); cnt = np.zeros(n, np.int32); st = LsdStats()
+        self._chk(lib().csb_lsd_detect_batch(self._h, _p(gray), n, w, h, C.byref(P), _p(lines), _p(cnt), C.byref(st)))
+        return [lines[i, :cnt[i]].copy() for i in range(n)], st
+
+    def lsd_upload(self, gray, line_length_thres=15.0, filter=True, max_lines=4096):
+        gray = self._lsd_gray(gray)
+        n, h, w = gray.shape
+        self._lsd_n = n
+        self._chk(lib().csb_lsd_upload(self._h, _p(gray), n, w, h, C.byref(self._lsd_params(line_length_thres, filter, max_lines))))
+
+    def lsd_run(self, timed=False):
+        self._chk(lib().csb_lsd_run(self._h, int(timed)))
+
+    def lsd_download(self):
+        n, cap = self._lsd_n, self._lsd_p.max_lines
+        lines = np.zeros((n, cap, 4), np.float32); cnt = np.zeros(n, np.int32); st = LsdStats()
+        self._chk(lib().csb_lsd_download(self._h, _p(lines), _p(cnt), C.byref(st)))
+        return [lines[i, :cnt[i]].copy() for i in range(n)], st
+
+    def lsd_debug_maps(self, frame, scaled_shape):
+        H, W = scaled_shape
+        sc = np.zeros((H, W)); mg = np.zeros((H, W)); an = np.zeros((H, W))
+        self._chk(lib().csb_lsd_debug_maps(self._h, int(frame), _p(sc), _p(mg), _p(an)))
+        return sc, mg, an
+
+
+class line_lbd_detect:
+    """Host-side mirror of class line_lbd_detect (reference: line_lbd/include/line_lbd/line_lbd_allclass.h:20-60) for its LSD branch:
+    same member names and meaning (use_LSD, line_length_thres, detect_filter_lines), computing on the GPU through the C ABI."""
+
+    def __init__(self, ctx, numoctaves=1, octaveratio=2.0):
+        if numoctaves != 1:
+            raise CsbError(CSB_ERR_INVALID, "only one octave is supported (every caller in the reference uses one: main_obj.cpp:503, detect_lines.cpp:61)")
+        self._ctx = ctx
+        self.use_LSD = True            # line_lbd_allclass.cpp:125 defaults to False (EDLines), which is not ported
+        self.line_length_thres = 50.0  # line_lbd_allclass.cpp:126; both callers overwrite it with 15
+        self.max_lines = 4096
+
+    def detect_filter_lines(self, gray_img):
+        """line_lbd_allclass.cpp:221-235: gray image(s) -> linesmat_out rows [x1 y1 x2 y2] float32 (one array per frame)."""
+        if not self.use_LSD:
+            raise CsbError(CSB_ERR_INVALID, "use_LSD = false (EDLines) is not implemented on the GPU")
+        single = np.asarray(gray_img).ndim == 2
+        out, _ = self._ctx.lsd_detect_batch(gray_img, self.line_length_thres, True, self.max_lines)
+        return out[0] if single else out

@@ -7,6 +7,7 @@
 
 #include "ba.h"
 #include "csb_internal.h"
+#include "lsd.h"
 #include "proposal.h"
 
 struct DevBuf {
@@ -89,6 +90,7 @@ struct csb_context {
     std::string err;
     DetectState det;
     csb::BAState ba;
+    csb::LsdState* lsd = nullptr;  // created by the first csb_lsd_* call
 };
 
 #define CSB_CUDA(ctx, call)                                                                   \

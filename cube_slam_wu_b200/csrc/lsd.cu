@@ -1,0 +1,999 @@
+// lsd.cu -- LSD line segment detection for a batch of gray frames (SURVEY.md 8 "next" row f-2).
+//
+// Replaces the LSD branch of line_lbd_detect::detect_filter_lines (reference: line_lbd/class/line_lbd_allclass.cpp:130-149, 200-235 ->
+// LSDDetector::detectImpl line_lbd/libs/LSDDetector.cpp:154-293 -> LineSegmentDetectorImpl line_lbd/libs/lsd.cpp:414-1167).  The OpenCV
+// calls inside (convertTo, GaussianBlur 7x7 on CV_64F, resize x0.8 INTER_LINEAR, fastAtan2) are restated from OpenCV's algorithms; see
+// oracle/oracle_lsd.cpp for how each piece is pinned against cv2 4.13.
+//
+//   k_lsd_scale : (tile, frame).  u8 tile + halo -> shared memory; separable 7-tap Gaussian in FP64 with OpenCV's summation order
+//                 (row filter left to right, column filter centre tap then symmetric pairs), bilinear x0.8 down-scaling with float
+//                 coefficients -> `scaled` (double).  HBM streaming: 1 B read per source pixel, 8 B written per scaled pixel.
+//   k_lsd_grad  : (32x8 pixel tile, frame).  ll_angle (lsd.cpp:538-590): 2x2 gradient, norm, fastAtan2 level-line angle; per pixel
+//                 {angle in degrees, cosf(angle), sinf(angle)} (the two terms region_grow adds per accepted pixel, lsd.cpp:679-680,
+//                 evaluated once here with the specified det_sincos), the gradient norm, and a 1-bit "defined" map (warp ballot).
+//   k_lsd_grow  : one warp per frame -- flsd's seed loop (lsd.cpp:474-535) is sequential per frame: seeds are visited in raster order
+//                 and every region depends on the `used` map left by the previous ones.  The `used` and `defined` maps live in shared
+//                 memory as bitmaps (2 x 24 KB for 512x384); seeds are found with ballot/ffs over bitmap words; region_grow tests the
+//                 8 neighbours of a region pixel on 9 lanes at once and replays the reference's sequential accept order (the running
+//                 angle changes after every accepted pixel, so later neighbours are re-tested); the order-dependent FP64 sums of
+//                 region2rect / get_theta / refine are accumulated in region order from per-lane products staged in shared memory;
+//                 reduce_region_radius' swap-with-last removal is done as two ordered compactions that yield the same permutation;
+//                 rect_nfa counts aligned pixels lane-parallel (integer counts, order-free).
+//
+// Arithmetic: FP64, -fmad=false, no libm in anything that decides region membership (det_sincos / fast_atan2f are specified,
+// csb_math-style); log/exp/pow/sinh of the NFA use CUDA's libm (they only feed `>` comparisons against 0 and each other).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#include "context.h"
+
+namespace csb {
+
+constexpr double LSD_PI = 3.1415926535897932384626433832795;
+constexpr double LSD_3_2_PI = (3 * LSD_PI) / 2;
+constexpr double LSD_2PI = 2 * LSD_PI;
+constexpr double LSD_DEG2RAD = LSD_PI / 180;
+constexpr float LSD_NOTDEF_DEG = -1024.f;  // sentinel in the degree map (fastAtan2 returns [0, 360])
+constexpr double LSD_SCALE = 0.8;
+
+struct LsdDims {
+    int w, h;     // source frame
+    int W, H;     // scaled frame
+    int WW;       // bitmap words per scaled row
+    int n_frames;
+};
+
+struct LsdConst {
+    double k[7];       // Gaussian taps (cv::getGaussianKernel(7, 0.6 / 0.8))
+    double inv_scale;  // 1 / 0.8
+    double rho;        // gradient threshold QUANT / sin(prec)
+    double prec, p;    // angle tolerance (rad), its probability
+    double log_nt;
+    int min_reg_size;
+    float length_thres;
+    int filter, max_lines;
+};
+
+struct LsdBuffers {
+    const uint8_t* gray;
+    double* scaled;
+    float4* pix;       // {deg, cosf, sinf, 0}
+    float* deg;        // compact copy of pix.x for the NFA counts
+    double* modgrad;
+    uint32_t* defbits;
+    uint32_t* reg;     // region lists, W*H entries per frame (x | y << 16)
+    uint32_t* tmp;     // scratch of reduce_region_radius, W*H entries per frame
+    float* lines;      // n_frames x max_lines x 4
+    int* n_lines;      // n_frames
+    unsigned long long* stats;  // [0] regions, [1] region pixels
+};
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// specified arithmetic (same sequences as oracle/oracle_lsd.cpp)
+// ---------------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void det_sincos(double x, double& s, double& c) {
+    const double two_over_pi = 6.36619772367581382433e-01, pio2_hi = 1.57079632673412561417e+00, pio2_lo = 6.07710050650619224932e-11;
+    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04,
+                 S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05,
+                 C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    const double kf = floor(x * two_over_pi + 0.5);
+    const int k = (int)kf;
+    double r = x - kf * pio2_hi;
+    r = r - kf * pio2_lo;
+    const double z = r * r;
+    const double sn = r + (z * r) * (S1 + z * (S2 + z * (S3 + z * (S4 + z * (S5 + z * S6)))));
+    const double cs = 1.0 - (0.5 * z - z * (z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))))));
+    switch (k & 3) {
+        case 0: s = sn; c = cs; break;
+        case 1: s = cs; c = -sn; break;
+        case 2: s = -sn; c = -cs; break;
+        default: s = -cs; c = sn; break;
+    }
+}
+
+// cv::fastAtan2, degrees in [0, 360]
+__device__ __forceinline__ float fast_atan2f(float y, float x) {
+    constexpr float p1 = 0.9997878412794807f * (float)(180 / LSD_PI), p3 = -0.3258083974640975f * (float)(180 / LSD_PI),
+                    p5 = 0.1555786518463281f * (float)(180 / LSD_PI), p7 = -0.04432655554792128f * (float)(180 / LSD_PI);
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = ay / (ax + (float)DBL_EPSILON);
+        c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = ax / (ay + (float)DBL_EPSILON);
+        c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * n - 2 - i;
+    return i;
+}
+
+// cv::resize's source column for destination column d (xofs / alpha of resizeGeneric): fraction zeroed when clamped
+__device__ __forceinline__ int resize_src_x(int d, double inv, int n, float& f) {
+    f = (float)((d + 0.5) * inv - 0.5);
+    int s = (int)floorf(f);
+    f -= s;
+    if (s < 0) { f = 0; s = 0; }
+    if (s >= n - 1) { f = 0; s = n - 1; }
+    return s;
+}
+// ... and source row (yofs / beta): rows are clamped when read, the fraction is kept
+__device__ __forceinline__ int resize_src_y(int d, double inv, float& f) {
+    f = (float)((d + 0.5) * inv - 0.5);
+    const int s = (int)floorf(f);
+    f -= s;
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// k_lsd_scale
+// ---------------------------------------------------------------------------------------------------------------------------------
+constexpr int SC_TW = 64, SC_TH = 16, SC_THREADS = 256;
+constexpr int SC_BC = 84, SC_BR = 24;  // blurred tile capacity (source columns / rows feeding one scaled tile)
+constexpr int SC_GP = SC_BC + 8;       // u8 tile pitch
+
+__global__ void __launch_bounds__(SC_THREADS) k_lsd_scale(LsdBuffers B, LsdDims d, LsdConst C) {
+    __shared__ uint8_t g[(SC_BR + 6) * SC_GP];
+    __shared__ double rowf[(SC_BR + 6) * SC_BC];
+    __shared__ double blur[SC_BR * SC_BC];
+    const int tid = threadIdx.x, f = blockIdx.z;
+    const int X0 = blockIdx.x * SC_TW, Y0 = blockIdx.y * SC_TH;
+    const int X1 = min(X0 + SC_TW, d.W) - 1, Y1 = min(Y0 + SC_TH, d.H) - 1;
+    const uint8_t* src = B.gray + (size_t)f * d.w * d.h;
+    float fr;
+    const int sx_lo = resize_src_x(X0, C.inv_scale, d.w, fr);
+    const int sx_hi = min(resize_src_x(X1, C.inv_scale, d.w, fr) + 1, d.w - 1);
+    const int sy_lo = min(max(resize_src_y(Y0, C.inv_scale, fr), 0), d.h - 1);
+    const int sy_hi = min(max(resize_src_y(Y1, C.inv_scale, fr) + 1, 0), d.h - 1);
+    const int nc = sx_hi - sx_lo + 1, nr = sy_hi - sy_lo + 1;  // <= SC_BC, SC_BR
+    // (1) u8 tile: virtual rows sy_lo-3 .. sy_hi+3, virtual columns sx_lo-3 .. sx_hi+3, BORDER_REFLECT_101
+    for (int i = tid; i < (nr + 6) * (nc + 6); i += SC_THREADS) {
+        const int r = i / (nc + 6), c = i - r * (nc + 6);
+        g[r * SC_GP + c] = src[(size_t)reflect101(sy_lo - 3 + r, d.h) * d.w + reflect101(sx_lo - 3 + c, d.w)];
+    }
+    __syncthreads();
+    // (2) row filter, taps summed left to right (cv::RowFilter)
+    for (int i = tid; i < (nr + 6) * nc; i += SC_THREADS) {
+        const int r = i / nc, c = i - r * nc;
+        const uint8_t* s = g + r * SC_GP + c;
+        double acc = C.k[0] * (double)s[0];
+#pragma unroll
+        for (int t = 1; t < 7; t++) acc += C.k[t] * (double)s[t];
+        rowf[r * SC_BC + c] = acc;
+    }
+    __syncthreads();
+    // (3) column filter (cv::SymmColumnFilter): centre tap, then f_k (S[+k] + S[-k])
+    for (int i = tid; i < nr * nc; i += SC_THREADS) {
+        const int r = i / nc, c = i - r * nc;
+        const double* s = rowf + (r + 3) * SC_BC + c;
+        double acc = C.k[3] * s[0];
+#pragma unroll
+        for (int t = 1; t <= 3; t++) acc += C.k[3 + t] * (s[t * SC_BC] + s[-t * SC_BC]);
+        blur[r * SC_BC + c] = acc;
+    }
+    __syncthreads();
+    // (4) bilinear down-scaling (HResizeLinear then VResizeLinear, float coefficients)
+    for (int i = tid; i < SC_TW * SC_TH; i += SC_THREADS) {
+        const int dy = Y0 + i / SC_TW, dx = X0 + (i % SC_TW);
+        if (dx >= d.W || dy >= d.H) continue;
+        float fx, fy;
+        const int sx = resize_src_x(dx, C.inv_scale, d.w, fx);
+        const int sy = resize_src_y(dy, C.inv_scale, fy);
+        const float a1 = fx, a0 = 1.f - fx, b1 = fy, b0 = 1.f - fy;
+        const int y0 = min(max(sy, 0), d.h - 1) - sy_lo, y1 = min(max(sy + 1, 0), d.h - 1) - sy_lo;
+        const double* r0p = blur + y0 * SC_BC + (sx - sx_lo);
+        const double* r1p = blur + y1 * SC_BC + (sx - sx_lo);
+        double r0, r1;
+        if (sx + 1 < d.w) {
+            r0 = r0p[0] * (double)a0 + r0p[1] * (double)a1;
+            r1 = r1p[0] * (double)a0 + r1p[1] * (double)a1;
+        } else {
+            r0 = r0p[0];
+            r1 = r1p[0];
+        }
+        B.scaled[((size_t)f * d.H + dy) * d.W + dx] = r0 * (double)b0 + r1 * (double)b1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// k_lsd_grad (ll_angle, lsd.cpp:538-590)
+// ---------------------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_lsd_grad(LsdBuffers B, LsdDims d, LsdConst C) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
+    const bool in = x < d.W && y < d.H;
+    const size_t fo = (size_t)f * d.W * d.H;
+    float deg = LSD_NOTDEF_DEG, cv = 0.f, sv = 0.f;
+    double mg = 0.0;
+    bool def = false;
+    if (in && x < d.W - 1 && y < d.H - 1) {
+        const double* S = B.scaled + fo + (size_t)y * d.W + x;
+        const double a = S[0], b = S[1], c = S[d.W], e = S[d.W + 1];
+        const double DA = e - a, BC = b - c;
+        const double gx = DA + BC, gy = DA - BC;
+        const double norm = sqrt((gx * gx + gy * gy) / 4);
+        mg = norm;
+        if (norm > C.rho) {
+            def = true;
+            deg = fast_atan2f((float)gx, (float)(-gy));
+            const double ang = (double)deg * LSD_DEG2RAD;
+            double s, c2;
+            det_sincos((double)(float)ang, s, c2);
+            cv = (float)c2;
+            sv = (float)s;
+        }
+    }
+    if (in) {
+        B.pix[fo + (size_t)y * d.W + x] = make_float4(deg, cv, sv, 0.f);
+        B.deg[fo + (size_t)y * d.W + x] = deg;
+        B.modgrad[fo + (size_t)y * d.W + x] = mg;
+    }
+    const unsigned bits = __ballot_sync(0xffffffffu, def);
+    if (threadIdx.x == 0 && y < d.H) B.defbits[(size_t)f * d.H * d.WW + (size_t)y * d.WW + blockIdx.x] = bits;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// k_lsd_grow
+// ---------------------------------------------------------------------------------------------------------------------------------
+struct LRect {
+    double x1, y1, x2, y2, width, x, y, theta, dx, dy, prec, p;
+};
+
+__device__ __forceinline__ double l_distSq(double x1, double y1, double x2, double y2) { return (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1); }
+__device__ __forceinline__ double l_dist(double x1, double y1, double x2, double y2) { return sqrt(l_distSq(x1, y1, x2, y2)); }
+__device__ __forceinline__ double l_angle_diff_signed(double a, double b) {
+    double diff = a - b;
+    while (diff <= -LSD_PI) diff += LSD_2PI;
+    while (diff > LSD_PI) diff -= LSD_2PI;
+    return diff;
+}
+__device__ __forceinline__ bool l_double_equal(double a, double b) {
+    if (a == b) return true;
+    const double abs_diff = fabs(a - b), aa = fabs(a), bb = fabs(b);
+    double abs_max = (aa > bb) ? aa : bb;
+    if (abs_max < DBL_MIN) abs_max = DBL_MIN;
+    return (abs_diff / abs_max) <= (100.0 * DBL_EPSILON);
+}
+// lsd.cpp:1151-1167 on a defined pixel whose angle is deg degrees
+__device__ __forceinline__ bool l_aligned_deg(float deg, double theta, double prec) {
+    const double a = (double)deg * LSD_DEG2RAD;
+    double n_theta = theta - a;
+    if (n_theta < 0) n_theta = -n_theta;
+    if (n_theta > LSD_3_2_PI) {
+        n_theta -= LSD_2PI;
+        if (n_theta < 0) n_theta = -n_theta;
+    }
+    return n_theta <= prec;
+}
+__device__ double l_log_gamma(double x) {
+    if (x > 15.0) return 0.918938533204673 + (x - 0.5) * log(x) - x + 0.5 * x * log(x * sinh(1 / x) + 1 / (810.0 * pow(x, 6.0)));
+    const double q[7] = {75122.6331530, 80916.6278952, 36308.2951477, 8687.24529705, 1168.92649479, 83.8676043424, 2.50662827511};
+    double a = (x + 0.5) * log(x + 5.5) - (x + 5.5);
+    double b = 0;
+    for (int n = 0; n < 7; ++n) {
+        a -= log(x + double(n));
+        b += q[n] * pow(x, double(n));
+    }
+    return a + log(b);
+}
+// lsd.cpp:1100-1149 (the first term is n + 1, not log_gamma(n + 1), in the reference's copy)
+__device__ __noinline__ double l_nfa(int n, int k, double p, double LOG_NT) {
+    if (n == 0 || k == 0) return -LOG_NT;
+    if (n == k) return -LOG_NT - double(n) * log10(p);
+    const double p_term = p / (1 - p);
+    const double log1term = (double(n) + 1) - l_log_gamma(double(k) + 1) - l_log_gamma(double(n - k) + 1) + double(k) * log(p) +
+                            double(n - k) * log(1.0 - p);
+    double term = exp(log1term);
+    if (l_double_equal(term, 0)) {
+        if (k > n * p) return -log1term / 2.30258509299404568402 - LOG_NT;
+        return -LOG_NT;
+    }
+    double bin_tail = term;
+    const double tolerance = 0.1;
+    for (int i = k + 1; i <= n; ++i) {
+        const double bin_term = double(n - i + 1) / double(i);
+        const double mult_term = bin_term * p_term;
+        term *= mult_term;
+        bin_tail += term;
+        if (bin_term < 1) {
+            const double err = term * ((1 - pow(mult_term, double(n - i + 1))) / (1 - mult_term) - 1);
+            if (err < tolerance * fabs(-log10(bin_tail) - LOG_NT) * bin_tail) break;
+        }
+    }
+    return -log10(bin_tail) - LOG_NT;
+}
+
+struct Grow {
+    const float4* pix;
+    const float* deg;
+    const double* mg;
+    uint32_t* reg;
+    uint32_t* tmp;
+    uint32_t* U;        // shared: used bitmap
+    const uint32_t* D;  // shared: defined bitmap
+    double* sc;         // shared: 3 x 32 doubles
+    int W, H, WW, lane;
+    double LOG_NT;
+    unsigned long long n_regions, n_px;
+
+    __device__ __forceinline__ void clear_used(int px, int py) { atomicAnd(&U[py * WW + (px >> 5)], ~(1u << (px & 31))); }
+
+    // lsd.cpp:637-688.  Returns the region size; the region is reg[0 .. size).
+    __device__ __noinline__ int region_grow(int sx, int sy, double prec, double& reg_angle_out) {
+        if (lane == 0) {
+            reg[0] = (uint32_t)sx | ((uint32_t)sy << 16);
+            U[sy * WW + (sx >> 5)] |= 1u << (sx & 31);
+        }
+        int n = 1;
+        double reg_angle = (double)pix[(size_t)sy * W + sx].x * LSD_DEG2RAD;
+        double s0, c0;
+        det_sincos(reg_angle, s0, c0);
+        float sumdx = (float)c0, sumdy = (float)s0;
+        const int ox = lane % 3 - 1, oy = lane / 3 - 1;
+        __syncwarp();
+        for (int i = 0; i < n; ++i) {
+            const uint32_t q = reg[i];
+            const int xx = (int)(q & 0xffffu) + ox, yy = (int)(q >> 16) + oy;
+            const bool inb = lane < 9 && xx >= 0 && xx < W && yy >= 0 && yy < H;
+            const int word = inb ? yy * WW + (xx >> 5) : 0;
+            const unsigned bit = 1u << (xx & 31);
+            const bool cand = inb && (D[word] & bit) && !(U[word] & bit);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cand) v = pix[(size_t)yy * W + xx];
+            unsigned m = __ballot_sync(0xffffffffu, cand);
+            while (m) {
+                const bool al = cand && l_aligned_deg(v.x, reg_angle, prec);
+                const unsigned am = __ballot_sync(0xffffffffu, al) & m;
+                if (!am) break;
+                const int l = __ffs(am) - 1;
+                if (lane == l) {
+                    U[word] |= bit;
+                    reg[n] = (uint32_t)xx | ((uint32_t)yy << 16);
+                }
+                sumdx += __shfl_sync(0xffffffffu, v.y, l);
+                sumdy += __shfl_sync(0xffffffffu, v.z, l);
+                reg_angle = (double)fast_atan2f(sumdy, sumdx) * LSD_DEG2RAD;
+                ++n;
+                m &= ~((2u << l) - 1u);
+            }
+            __syncwarp();
+        }
+        reg_angle_out = reg_angle;
+        return n;
+    }
+
+    // lsd.cpp:690-746 + get_theta :748-784
+    __device__ __noinline__ void region2rect(int n, double reg_angle, double prec, double p, LRect& rec) {
+        double x = 0, y = 0, sum = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int idx = base + lane, cnt = min(32, n - base);
+            if (idx < n) {
+                const uint32_t q = reg[idx];
+                const int px = q & 0xffffu, py = q >> 16;
+                const double w = mg[(size_t)py * W + px];
+                sc[lane] = double(px) * w;
+                sc[32 + lane] = double(py) * w;
+                sc[64 + lane] = w;
+            }
+            __syncwarp();
+            for (int j = 0; j < cnt; j++) {
+                x += sc[j];
+                y += sc[32 + j];
+                sum += sc[64 + j];
+            }
+            __syncwarp();
+        }
+        x /= sum;
+        y /= sum;
+        double Ixx = 0.0, Iyy = 0.0, Ixy = 0.0;
+        for (int base = 0; base < n; base += 32) {
+            const int idx = base + lane, cnt = min(32, n - base);
+            if (idx < n) {
+                const uint32_t q = reg[idx];
+                const int px = q & 0xffffu, py = q >> 16;
+                const double w = mg[(size_t)py * W + px];
+                const double ddx = double(px) - x, ddy = double(py) - y;
+                sc[lane] = ddy * ddy * w;
+                sc[32 + lane] = ddx * ddx * w;
+                sc[64 + lane] = ddx * ddy * w;
+            }
+            __syncwarp();
+            for (int j = 0; j < cnt; j++) {
+                Ixx += sc[j];
+                Iyy += sc[32 + j];
+                Ixy -= sc[64 + j];
+            }
+            __syncwarp();
+        }
+        const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
+        double theta = (fabs(Ixx) > fabs(Iyy)) ? double(fast_atan2f(float(lambda - Ixx), float(Ixy))) : double(fast_atan2f(float(Ixy), float(lambda - Iyy)));
+        theta *= LSD_DEG2RAD;
+        if (fabs(l_angle_diff_signed(theta, reg_angle)) > prec) theta += LSD_PI;
+        double dx, dy;
+        det_sincos(theta, dy, dx);
+        double l_min = 0, l_max = 0, w_min = 0, w_max = 0;  // the reference's running min / max from 0 (order-free)
+        for (int idx = lane; idx < n; idx += 32) {
+            const uint32_t q = reg[idx];
+            const double regdx = double(q & 0xffffu) - x, regdy = double(q >> 16) - y;
+            const double l = regdx * dx + regdy * dy;
+            const double w = -regdx * dy + regdy * dx;
+            l_max = fmax(l_max, l);
+            l_min = fmin(l_min, l);
+            w_max = fmax(w_max, w);
+            w_min = fmin(w_min, w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            l_max = fmax(l_max, __shfl_xor_sync(0xffffffffu, l_max, o));
+            l_min = fmin(l_min, __shfl_xor_sync(0xffffffffu, l_min, o));
+            w_max = fmax(w_max, __shfl_xor_sync(0xffffffffu, w_max, o));
+            w_min = fmin(w_min, __shfl_xor_sync(0xffffffffu, w_min, o));
+        }
+        rec.x1 = x + l_min * dx;
+        rec.y1 = y + l_min * dy;
+        rec.x2 = x + l_max * dx;
+        rec.y2 = y + l_max * dy;
+        rec.width = w_max - w_min;
+        rec.x = x;
+        rec.y = y;
+        rec.theta = theta;
+        rec.dx = dx;
+        rec.dy = dy;
+        rec.prec = prec;
+        rec.p = p;
+        if (rec.width < 1.0) rec.width = 1.0;
+    }
+
+    // lsd.cpp:834-871.  The reference removes far points one by one with swap(reg[i], reg[size - 1]); the resulting order is: kept points
+    // stay, holes among the first m = #kept slots (ascending) are filled by the kept points of slots >= m in descending slot order.
+    __device__ __noinline__ bool reduce_region_radius(int& n, double reg_angle, double prec, double p, LRect& rec, double density, double density_th) {
+        const uint32_t q0 = reg[0];
+        const double xc = double(q0 & 0xffffu), yc = double(q0 >> 16);
+        const double radSq1 = l_distSq(xc, yc, rec.x1, rec.y1), radSq2 = l_distSq(xc, yc, rec.x2, rec.y2);
+        double radSq = radSq1 > radSq2 ? radSq1 : radSq2;
+        while (density < density_th) {
+            radSq *= 0.75 * 0.75;
+            int m = 0;
+            for (int base = 0; base < n; base += 32) {
+                const int idx = base + lane;
+                bool keep = false;
+                if (idx < n) {
+                    const uint32_t q = reg[idx];
+                    const int px = q & 0xffffu, py = q >> 16;
+                    keep = !(l_distSq(xc, yc, double(px), double(py)) > radSq);
+                    if (!keep) clear_used(px, py);
+                }
+                m += __popc(__ballot_sync(0xffffffffu, keep));
+            }
+            if (m != n) {
+                int r = 0;
+                for (int top = n - 1; top >= m; top -= 32) {  // kept points of slots >= m, descending
+                    const int pos = top - lane;
+                    bool keep = false;
+                    uint32_t q = 0;
+                    if (pos >= m) {
+                        q = reg[pos];
+                        keep = !(l_distSq(xc, yc, double(q & 0xffffu), double(q >> 16)) > radSq);
+                    }
+                    const unsigned b = __ballot_sync(0xffffffffu, keep);
+                    if (keep) tmp[r + __popc(b & ((1u << lane) - 1u))] = q;
+                    r += __popc(b);
+                }
+                __syncwarp();
+                r = 0;
+                for (int base = 0; base < m; base += 32) {  // holes of slots < m, ascending
+                    const int idx = base + lane;
+                    bool far = false;
+                    if (idx < m) {
+                        const uint32_t q = reg[idx];
+                        far = l_distSq(xc, yc, double(q & 0xffffu), double(q >> 16)) > radSq;
+                    }
+                    const unsigned b = __ballot_sync(0xffffffffu, far);
+                    if (far) reg[idx] = tmp[r + __popc(b & ((1u << lane) - 1u))];
+                    r += __popc(b);
+                }
+                __syncwarp();
+            }
+            n = m;
+            if (n < 2) return false;
+            region2rect(n, reg_angle, prec, p, rec);
+            density = double(n) / (l_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+        }
+        return true;
+    }
+
+    // lsd.cpp:786-832
+    __device__ __noinline__ bool refine(int& n, double reg_angle, double prec, double p, LRect& rec, double density_th) {
+        double density = double(n) / (l_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+        if (density >= density_th) return true;
+        const uint32_t q0 = reg[0];
+        const int x0 = q0 & 0xffffu, y0 = q0 >> 16;
+        const double xc = double(x0), yc = double(y0);
+        const double ang_c = (double)pix[(size_t)y0 * W + x0].x * LSD_DEG2RAD;
+        double sum = 0, s_sum = 0;
+        int cnt = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int idx = base + lane;
+            bool near = false;
+            if (idx < n) {
+                const uint32_t q = reg[idx];
+                const int px = q & 0xffffu, py = q >> 16;
+                clear_used(px, py);
+                if (l_dist(xc, yc, double(px), double(py)) < rec.width) {
+                    near = true;
+                    sc[lane] = l_angle_diff_signed((double)pix[(size_t)py * W + px].x * LSD_DEG2RAD, ang_c);
+                }
+            }
+            unsigned m = __ballot_sync(0xffffffffu, near);
+            while (m) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1;
+                const double d = sc[l];
+                sum += d;
+                s_sum += d * d;
+                ++cnt;
+            }
+            __syncwarp();
+        }
+        const double mean_angle = sum / double(cnt);
+        const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / double(cnt) + mean_angle * mean_angle);
+        n = region_grow(x0, y0, tau, reg_angle);
+        n_px += n;
+        if (n < 2) return false;
+        region2rect(n, reg_angle, prec, p, rec);
+        density = double(n) / (l_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+        if (density < density_th) return reduce_region_radius(n, reg_angle, prec, p, rec, density, density_th);
+        return true;
+    }
+
+    // lsd.cpp:977-1098.  Integer-division slopes and the tailp->p.x comparisons are the reference's; since every step is an integer the
+    // scan-line bounds of row y have a closed form, so rows can be counted in any order.
+    __device__ __noinline__ double rect_nfa(const LRect& rec) {
+        const double half_width = rec.width / 2.0;
+        const double dyhw = rec.dy * half_width, dxhw = rec.dx * half_width;
+        int ex[4], ey[4];
+        ex[0] = int(rec.x1 - dyhw); ey[0] = int(rec.y1 + dxhw);
+        ex[1] = int(rec.x2 - dyhw); ey[1] = int(rec.y2 + dxhw);
+        ex[2] = int(rec.x2 + dyhw); ey[2] = int(rec.y2 - dxhw);
+        ex[3] = int(rec.x1 + dyhw); ey[3] = int(rec.y1 - dxhw);
+#define LSD_CSWAP(a, b)                                                              \
+    if (ex[b] < ex[a] || (ex[b] == ex[a] && ey[b] < ey[a])) {                        \
+        int t_ = ex[a]; ex[a] = ex[b]; ex[b] = t_; t_ = ey[a]; ey[a] = ey[b]; ey[b] = t_; \
+    }
+        LSD_CSWAP(0, 1) LSD_CSWAP(2, 3) LSD_CSWAP(0, 2) LSD_CSWAP(1, 3) LSD_CSWAP(1, 2)
+#undef LSD_CSWAP
+        int mi = 0, miy = ey[0], mix = ex[0], may = ey[0];
+#pragma unroll
+        for (int i = 1; i < 4; i++) {
+            if (miy > ey[i]) { mi = i; miy = ey[i]; mix = ex[i]; }
+            if (may < ey[i]) may = ey[i];
+        }
+        unsigned taken = 1u << mi;
+        int lx_ = 0, ly_ = 0, li = -1;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (!(taken >> i & 1u)) {
+                if (li < 0 || lx_ > ex[i]) { li = i; lx_ = ex[i]; ly_ = ey[i]; }
+            }
+        taken |= 1u << li;
+        int rx_ = 0, ry_ = 0, ri = -1;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (!(taken >> i & 1u)) {
+                if (ri < 0 || rx_ < ex[i]) { ri = i; rx_ = ex[i]; ry_ = ey[i]; }
+            }
+        taken |= 1u << ri;
+        int tx_ = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (!(taken >> i & 1u)) tx_ = ex[i];
+        const int flstep = (miy != ly_) ? (mix - lx_) / (miy - ly_) : 0;
+        const int slstep = (ly_ != tx_) ? (lx_ - tx_) / (ly_ - tx_) : 0;
+        const int frstep = (miy != ry_) ? (mix - rx_) / (miy - ry_) : 0;
+        const int srstep = (ry_ != tx_) ? (rx_ - tx_) / (ry_ - tx_) : 0;
+        const int y0 = max(miy, 0), y1 = min(may, H - 1);
+        int total = 0, alg = 0;
+        const double theta = rec.theta, prec = rec.prec;
+        const int rows = y1 - y0 + 1;
+        if (rows >= 16) {  // one lane per row
+            for (int y = y0 + lane; y <= y1; y += 32) {
+                const long long c = y - y0;
+                const long long cfl = min(max((long long)ly_ - y0, 0ll), c), cfr = min(max((long long)ry_ - y0, 0ll), c);
+                const int xl = max((int)(mix + cfl * flstep + (c - cfl) * slstep), 0);
+                const int xr = min((int)(mix + cfr * frstep + (c - cfr) * srstep), W - 1);
+                if (xr >= xl) total += xr - xl + 1;
+                const float* row = deg + (size_t)y * W;
+#pragma unroll 4
+                for (int x = xl; x <= xr; x++) {
+                    const float a = row[x];
+                    if (a != LSD_NOTDEF_DEG && l_aligned_deg(a, theta, prec)) ++alg;
+                }
+            }
+        } else {
+            for (int y = y0; y <= y1; y++) {
+                const long long c = y - y0;
+                const long long cfl = min(max((long long)ly_ - y0, 0ll), c), cfr = min(max((long long)ry_ - y0, 0ll), c);
+                const int xl = max((int)(mix + cfl * flstep + (c - cfl) * slstep), 0);
+                const int xr = min((int)(mix + cfr * frstep + (c - cfr) * srstep), W - 1);
+                if (lane == 0 && xr >= xl) total += xr - xl + 1;
+                const float* row = deg + (size_t)y * W;
+                for (int x = xl + lane; x <= xr; x += 32) {
+                    const float a = row[x];
+                    if (a != LSD_NOTDEF_DEG && l_aligned_deg(a, theta, prec)) ++alg;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            total += __shfl_xor_sync(0xffffffffu, total, o);
+            alg += __shfl_xor_sync(0xffffffffu, alg, o);
+        }
+        return l_nfa(total, alg, rec.p, LOG_NT);
+    }
+
+    // lsd.cpp:873-975
+    __device__ __noinline__ double rect_improve(LRect& rec) {
+        const double LOG_EPS = 0, delta = 0.5, delta_2 = delta / 2.0;
+        double log_nfa = rect_nfa(rec);
+        if (log_nfa > LOG_EPS) return log_nfa;
+        LRect r = rec;
+        for (int n = 0; n < 5; ++n) {
+            r.p /= 2;
+            r.prec = r.p * LSD_PI;
+            const double v = rect_nfa(r);
+            if (v > log_nfa) { log_nfa = v; rec = r; }
+        }
+        if (log_nfa > LOG_EPS) return log_nfa;
+        for (int pass = 0; pass < 3; pass++) {  // reduce width; reduce one side; reduce the other side
+            r = rec;
+            for (int n = 0; n < 5; ++n)
+                if ((r.width - delta) >= 0.5) {
+                    if (pass == 1) {
+                        r.x1 += -r.dy * delta_2; r.y1 += r.dx * delta_2; r.x2 += -r.dy * delta_2; r.y2 += r.dx * delta_2;
+                    } else if (pass == 2) {
+                        r.x1 -= -r.dy * delta_2; r.y1 -= r.dx * delta_2; r.x2 -= -r.dy * delta_2; r.y2 -= r.dx * delta_2;
+                    }
+                    r.width -= delta;
+                    const double v = rect_nfa(r);
+                    if (v > log_nfa) { rec = r; log_nfa = v; }
+                }
+            if (log_nfa > LOG_EPS) return log_nfa;
+        }
+        r = rec;
+        for (int n = 0; n < 5; ++n)
+            if ((r.width - delta) >= 0.5) {
+                r.p /= 2;
+                r.prec = r.p * LSD_PI;
+                const double v = rect_nfa(r);
+                if (v > log_nfa) { rec = r; log_nfa = v; }
+            }
+        return log_nfa;
+    }
+};
+
+__global__ void __launch_bounds__(32) k_lsd_grow(LsdBuffers B, LsdDims d, LsdConst C) {
+    extern __shared__ __align__(16) unsigned char lsd_smem[];
+    const int f = blockIdx.x, lane = threadIdx.x;
+    const int nw = d.H * d.WW;
+    Grow G;
+    G.sc = reinterpret_cast<double*>(lsd_smem);
+    G.U = reinterpret_cast<uint32_t*>(lsd_smem + 96 * sizeof(double));
+    uint32_t* Dm = G.U + nw;
+    G.D = Dm;
+    const size_t fo = (size_t)f * d.W * d.H;
+    G.pix = B.pix + fo;
+    G.deg = B.deg + fo;
+    G.mg = B.modgrad + fo;
+    G.reg = B.reg + fo;
+    G.tmp = B.tmp + fo;
+    G.W = d.W; G.H = d.H; G.WW = d.WW; G.lane = lane;
+    G.LOG_NT = C.log_nt;
+    G.n_regions = 0; G.n_px = 0;
+    const uint32_t* dsrc = B.defbits + (size_t)f * nw;
+    for (int i = lane; i < nw; i += 32) {
+        G.U[i] = 0;
+        Dm[i] = dsrc[i];
+    }
+    __syncwarp();
+    float* lines = B.lines + (size_t)f * C.max_lines * 4;
+    int n_out = 0;
+    for (int wbase = 0; wbase < nw; wbase += 32) {
+        const int widx = wbase + lane;
+        unsigned nz = __ballot_sync(0xffffffffu, widx < nw && (Dm[widx] & ~G.U[widx]) != 0);
+        while (nz) {
+            const int l = __ffs(nz) - 1, w = wbase + l;
+            const int wy = w / d.WW, wx0 = (w - wy * d.WW) * 32;
+            int lastbit = -1;
+            while (true) {
+                unsigned cand = Dm[w] & ~G.U[w];
+                if (lastbit >= 0) cand &= ~((2u << lastbit) - 1u);
+                if (!cand) break;
+                const int b = __ffs(cand) - 1;
+                lastbit = b;
+                const int sx = wx0 + b, sy = wy;
+                // ---- one seed (lsd.cpp:478-534)
+                double reg_angle;
+                int n = G.region_grow(sx, sy, C.prec, reg_angle);
+                G.n_regions++;
+                G.n_px += n;
+                if (n < C.min_reg_size) continue;
+                LRect rec;
+                G.region2rect(n, reg_angle, C.prec, C.p, rec);
+                if (!G.refine(n, reg_angle, C.prec, C.p, rec, 0.7)) continue;
+                const double log_nfa = G.rect_improve(rec);
+                if (log_nfa <= 0) continue;
+                rec.x1 += 0.5; rec.y1 += 0.5; rec.x2 += 0.5; rec.y2 += 0.5;
+                rec.x1 /= LSD_SCALE; rec.y1 /= LSD_SCALE; rec.x2 /= LSD_SCALE; rec.y2 /= LSD_SCALE;
+                float e0 = float(rec.x1), e1 = float(rec.y1), e2 = float(rec.x2), e3 = float(rec.y2);
+                if (C.filter) {
+                    // LSDDetector.cpp:80-101, 219-232 (octaveScale = 1), line_lbd_allclass.cpp:206
+                    const int w_ = d.w, h_ = d.h;
+                    if (e0 < 0) e0 = 0;
+                    if (e0 >= w_) e0 = (float)w_ - 1.0f;
+                    if (e2 < 0) e2 = 0;
+                    if (e2 >= w_) e2 = (float)w_ - 1.0f;
+                    if (e1 < 0) e1 = 0;
+                    if (e1 >= h_) e1 = (float)h_ - 1.0f;
+                    if (e3 < 0) e3 = 0;
+                    if (e3 >= h_) e3 = (float)h_ - 1.0f;
+                    const float thr = 10;
+                    if (((e0 < thr) && (e2 < thr)) || ((e0 > w_ - thr) && (e2 > w_ - thr)) || ((e1 < thr) && (e3 < thr)) ||
+                        ((e1 > h_ - thr) && (e3 > h_ - thr)))
+                        continue;
+                    const double ddx = double(e0 - e2), ddy = double(e1 - e3);
+                    const float len = (float)sqrt(ddx * ddx + ddy * ddy);
+                    if (!(len > C.length_thres)) continue;
+                }
+                if (lane == 0 && n_out < C.max_lines) {
+                    float4* o = reinterpret_cast<float4*>(lines) + n_out;
+                    *o = make_float4(e0, e1, e2, e3);
+                }
+                ++n_out;
+            }
+            __syncwarp();
+            nz = __ballot_sync(0xffffffffu, widx < nw && lane > l && (Dm[widx] & ~G.U[widx]) != 0);
+        }
+    }
+    if (lane == 0) {
+        B.n_lines[f] = n_out;
+        atomicAdd(&B.stats[0], G.n_regions);
+        atomicAdd(&B.stats[1], G.n_px);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------------------
+struct LsdState {
+    bool uploaded = false, ran = false, timed_last = false;
+    LsdDims d{};
+    LsdConst C{};
+    csb_lsd_params params{};
+    DevBuf d_gray, d_scaled, d_pix, d_deg, d_mg, d_def, d_reg, d_tmp, d_lines, d_nlines, d_stats;
+    HostBuf h_gray, h_out;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    size_t grow_smem = 0;
+    int64_t h2d_bytes = 0, d2h_bytes = 0;
+    int launches_last = 0;
+};
+
+void lsd_release(LsdState*& s) {
+    if (!s) return;
+    DevBuf* bufs[] = {&s->d_gray, &s->d_scaled, &s->d_pix, &s->d_deg, &s->d_mg, &s->d_def, &s->d_reg, &s->d_tmp, &s->d_lines, &s->d_nlines, &s->d_stats};
+    for (DevBuf* b : bufs) b->release();
+    s->h_gray.release();
+    s->h_out.release();
+    for (auto& e : s->ev)
+        if (e) cudaEventDestroy(e);
+    delete s;
+    s = nullptr;
+}
+
+static LsdBuffers lsd_buffers(LsdState& s) {
+    LsdBuffers B{};
+    B.gray = s.d_gray.as<uint8_t>();
+    B.scaled = s.d_scaled.as<double>();
+    B.pix = s.d_pix.as<float4>();
+    B.deg = s.d_deg.as<float>();
+    B.modgrad = s.d_mg.as<double>();
+    B.defbits = s.d_def.as<uint32_t>();
+    B.reg = s.d_reg.as<uint32_t>();
+    B.tmp = s.d_tmp.as<uint32_t>();
+    B.lines = s.d_lines.as<float>();
+    B.n_lines = s.d_nlines.as<int>();
+    B.stats = s.d_stats.as<unsigned long long>();
+    return B;
+}
+
+}  // namespace csb
+
+using namespace csb;
+
+static int lsd_prepare(csb_context* c, int n_frames, int width, int height, const csb_lsd_params* params) {
+    if (!c || !params || n_frames <= 0 || width < 8 || height < 8 || width > 65535 || height > 65535 || params->max_lines <= 0) return CSB_ERR_INVALID;
+    CSB_CUDA(c, cudaSetDevice(c->device));
+    if (!c->lsd) {
+        c->lsd = new LsdState();
+        for (auto& e : c->lsd->ev) CSB_CUDA(c, cudaEventCreate(&e));
+    }
+    LsdState& s = *c->lsd;
+    s.uploaded = false;
+    s.ran = false;
+    s.params = *params;
+    LsdDims& d = s.d;
+    d.w = width;
+    d.h = height;
+    d.W = (int)std::lrint(width * LSD_SCALE);   // cvRound (lsd.cpp:459 -> cv::resize dsize)
+    d.H = (int)std::lrint(height * LSD_SCALE);
+    d.WW = (d.W + 31) / 32;
+    d.n_frames = n_frames;
+    LsdConst& C = s.C;
+    {   // cv::getGaussianKernel(7, sigma, CV_64F) with sigma = SIGMA_SCALE / SCALE (lsd.cpp:453-457); ksize = 1 + 2 ceil(sigma sqrt(2 * 3 ln 10)) = 7
+        const double sigma = 0.6 / 0.8, scale2X = -0.5 / (sigma * sigma);
+        double sum = 0;
+        for (int i = 0; i < 7; i++) {
+            const double x = i - 3.0;
+            C.k[i] = std::exp(scale2X * x * x);
+            sum += C.k[i];
+        }
+        sum = 1. / sum;
+        for (int i = 0; i < 7; i++) C.k[i] *= sum;
+    }
+    C.inv_scale = 1.0 / LSD_SCALE;
+    C.prec = LSD_PI * 22.5 / 180;
+    C.p = 22.5 / 180;
+    C.rho = 2.0 / std::sin(C.prec);
+    C.log_nt = 5 * (std::log10(double(d.W)) + std::log10(double(d.H))) / 2 + std::log10(11.0);
+    C.min_reg_size = int(-C.log_nt / std::log10(C.p));
+    C.length_thres = params->line_length_thres;
+    C.filter = params->filter;
+    C.max_lines = params->max_lines;
+    s.grow_smem = 96 * sizeof(double) + 2 * (size_t)d.H * d.WW * sizeof(uint32_t);
+    if (s.grow_smem > (size_t)c->max_smem_optin) {
+        c->err = "csb_lsd: frame too large for the shared-memory used/defined bitmaps";
+        return CSB_ERR_CAPACITY;
+    }
+    const size_t npx = (size_t)d.W * d.H * n_frames;
+    CSB_CUDA(c, s.d_gray.ensure((size_t)width * height * n_frames));
+    CSB_CUDA(c, s.d_scaled.ensure(npx * 8));
+    CSB_CUDA(c, s.d_pix.ensure(npx * 16));
+    CSB_CUDA(c, s.d_deg.ensure(npx * 4));
+    CSB_CUDA(c, s.d_mg.ensure(npx * 8));
+    CSB_CUDA(c, s.d_def.ensure((size_t)d.H * d.WW * n_frames * 4));
+    CSB_CUDA(c, s.d_reg.ensure(npx * 4));
+    CSB_CUDA(c, s.d_tmp.ensure(npx * 4));
+    CSB_CUDA(c, s.d_lines.ensure((size_t)n_frames * params->max_lines * 16));
+    CSB_CUDA(c, s.d_nlines.ensure((size_t)n_frames * 4));
+    CSB_CUDA(c, s.d_stats.ensure(64));
+    CSB_CUDA(c, cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.grow_smem));
+    return CSB_OK;
+}
+
+extern "C" {
+
+int csb_lsd_upload(csb_context* c, const uint8_t* gray, int n_frames, int width, int height, const csb_lsd_params* params) {
+    if (!gray) return CSB_ERR_INVALID;
+    int rc = lsd_prepare(c, n_frames, width, height, params);
+    if (rc != CSB_OK) return rc;
+    LsdState& s = *c->lsd;
+    const size_t bytes = (size_t)width * height * n_frames;
+    CSB_CUDA(c, s.h_gray.ensure(bytes));
+    std::memcpy(s.h_gray.p, gray, bytes);
+    CSB_CUDA(c, cudaMemcpyAsync(s.d_gray.p, s.h_gray.p, bytes, cudaMemcpyHostToDevice, c->stream));
+    s.h2d_bytes = (int64_t)bytes;
+    s.uploaded = true;
+    return CSB_OK;
+}
+
+int csb_lsd_run(csb_context* c, int timed) {
+    if (!c || !c->lsd || !c->lsd->uploaded) {
+        if (c) c->err = "csb_lsd_run before csb_lsd_upload";
+        return CSB_ERR_STATE;
+    }
+    LsdState& s = *c->lsd;
+    CSB_CUDA(c, cudaSetDevice(c->device));
+    const LsdDims& d = s.d;
+    LsdBuffers B = lsd_buffers(s);
+    cudaStream_t st = c->stream;
+    CSB_CUDA(c, cudaMemsetAsync(s.d_stats.p, 0, 64, st));
+    if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[0], st));
+    k_lsd_scale<<<dim3((d.W + SC_TW - 1) / SC_TW, (d.H + SC_TH - 1) / SC_TH, d.n_frames), SC_THREADS, 0, st>>>(B, d, s.C);
+    k_lsd_grad<<<dim3(d.WW, (d.H + 7) / 8, d.n_frames), dim3(32, 8), 0, st>>>(B, d, s.C);
+    if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[1], st));
+    k_lsd_grow<<<d.n_frames, 32, s.grow_smem, st>>>(B, d, s.C);
+    if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[2], st));
+    CSB_CUDA(c, cudaGetLastError());
+    s.launches_last = 3;
+    s.timed_last = timed != 0;
+    s.ran = true;
+    return CSB_OK;
+}
+
+int csb_lsd_download(csb_context* c, float* lines_out, int32_t* n_lines_out, csb_lsd_stats* stats) {
+    if (!c || !c->lsd || !c->lsd->ran) {
+        if (c) c->err = "csb_lsd_download before csb_lsd_run";
+        return CSB_ERR_STATE;
+    }
+    LsdState& s = *c->lsd;
+    CSB_CUDA(c, cudaSetDevice(c->device));
+    const size_t lb = (size_t)s.d.n_frames * s.params.max_lines * 16, nb = (size_t)s.d.n_frames * 4;
+    CSB_CUDA(c, s.h_out.ensure(lb + nb + 64));
+    char* h = s.h_out.as<char>();
+    CSB_CUDA(c, cudaMemcpyAsync(h, s.d_lines.p, lb, cudaMemcpyDeviceToHost, c->stream));
+    CSB_CUDA(c, cudaMemcpyAsync(h + lb, s.d_nlines.p, nb, cudaMemcpyDeviceToHost, c->stream));
+    CSB_CUDA(c, cudaMemcpyAsync(h + lb + nb, s.d_stats.p, 64, cudaMemcpyDeviceToHost, c->stream));
+    CSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    s.d2h_bytes = (int64_t)(lb + nb + 64);
+    const int32_t* nl = reinterpret_cast<const int32_t*>(h + lb);
+    const unsigned long long* st = reinterpret_cast<const unsigned long long*>(h + lb + nb);
+    bool overflow = false;
+    int64_t total = 0;
+    for (int f = 0; f < s.d.n_frames; f++) {
+        overflow |= nl[f] > s.params.max_lines;
+        total += std::min(nl[f], s.params.max_lines);
+    }
+    if (lines_out) std::memcpy(lines_out, h, lb);
+    if (n_lines_out) std::memcpy(n_lines_out, nl, nb);
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        stats->n_lines = total;
+        stats->n_regions = (int64_t)st[0];
+        stats->n_region_px = (int64_t)st[1];
+        stats->h2d_bytes = s.h2d_bytes;
+        stats->d2h_bytes = s.d2h_bytes;
+        stats->scaled_width = s.d.W;
+        stats->scaled_height = s.d.H;
+        stats->n_kernel_launches = s.launches_last;
+        if (s.timed_last) {
+            cudaEventElapsedTime(&stats->gpu_ms_maps, s.ev[0], s.ev[1]);
+            cudaEventElapsedTime(&stats->gpu_ms_grow, s.ev[1], s.ev[2]);
+        }
+    }
+    if (overflow) {
+        c->err = "csb_lsd: more segments than max_lines in at least one frame";
+        return CSB_ERR_CAPACITY;
+    }
+    return CSB_OK;
+}
+
+int csb_lsd_detect_batch(csb_context* c, const uint8_t* gray, int n_frames, int width, int height, const csb_lsd_params* params, float* lines_out,
+                         int32_t* n_lines_out, csb_lsd_stats* stats) {
+    int rc = csb_lsd_upload(c, gray, n_frames, width, height, params);
+    if (rc != CSB_OK) return rc;
+    rc = csb_lsd_run(c, stats != nullptr);
+    if (rc != CSB_OK) return rc;
+    return csb_lsd_download(c, lines_out, n_lines_out, stats);
+}
+
+int csb_lsd_debug_maps(csb_context* c, int frame, double* scaled_out, double* modgrad_out, double* angles_out) {
+    if (!c || !c->lsd || !c->lsd->ran) return CSB_ERR_STATE;
+    LsdState& s = *c->lsd;
+    if (frame < 0 || frame >= s.d.n_frames) return CSB_ERR_INVALID;
+    CSB_CUDA(c, cudaSetDevice(c->device));
+    CSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    const size_t n = (size_t)s.d.W * s.d.H, off = n * frame;
+    if (scaled_out) CSB_CUDA(c, cudaMemcpy(scaled_out, s.d_scaled.as<double>() + off, n * 8, cudaMemcpyDeviceToHost));
+    if (modgrad_out) CSB_CUDA(c, cudaMemcpy(modgrad_out, s.d_mg.as<double>() + off, n * 8, cudaMemcpyDeviceToHost));
+    if (angles_out) {
+        std::vector<float> deg(n);
+        CSB_CUDA(c, cudaMemcpy(deg.data(), s.d_deg.as<float>() + off, n * 4, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; i++) angles_out[i] = deg[i] == LSD_NOTDEF_DEG ? -1024.0 : (double)deg[i] * LSD_DEG2RAD;
+    }
+    return CSB_OK;
+}
+
+}  // extern "C"

@@ -240,3 +240,34 @@ def dist_map_for_roi_reference(gray, left, top, width, height, return_edges=Fals
     finally:
         cv2.ipp.setUseIPP(ipp)
     return (dm, edges) if return_edges else dm
+
+
+def make_lsd_frames(n_frames, img_w=640, img_h=480, seed=20260927, n_polys=10, n_lines=25, noise_sigma=3.0, texture=0.0):
+    """Synthetic gray frames for the line detector (BASELINE config #3: 640x480): filled quadrilaterals and thick line segments on a
+    shaded background, blurred by a small PSF, plus white sensor noise (and optionally band-limited texture).  uint8 (n, h, w)."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    out = np.zeros((n_frames, img_h, img_w), np.uint8)
+    yy, xx = np.mgrid[0:img_h, 0:img_w]
+    for f in range(n_frames):
+        gx, gy = rng.uniform(-0.05, 0.05, 2)
+        img = np.clip(rng.uniform(60, 160) + gx * (xx - img_w / 2) + gy * (yy - img_h / 2), 0, 255).astype(np.uint8)
+        for _ in range(n_polys):
+            cx, cy = rng.uniform(0, img_w), rng.uniform(0, img_h)
+            sz = rng.uniform(20, 160, 2)
+            ang = rng.uniform(0, np.pi)
+            c, s = np.cos(ang), np.sin(ang)
+            base = np.array([[-1, -1], [1, -1], [1, 1], [-1, 1]], np.float64) * sz * 0.5 * rng.uniform(0.6, 1.0, (4, 2))
+            pts = np.c_[cx + base[:, 0] * c - base[:, 1] * s, cy + base[:, 0] * s + base[:, 1] * c]
+            cv2.fillPoly(img, [np.round(pts).astype(np.int32)], int(rng.integers(0, 256)), lineType=cv2.LINE_AA)
+        for _ in range(n_lines):
+            p1 = (int(rng.integers(0, img_w)), int(rng.integers(0, img_h)))
+            ln, ang = rng.uniform(15, 250), rng.uniform(0, 2 * np.pi)
+            p2 = (int(p1[0] + ln * np.cos(ang)), int(p1[1] + ln * np.sin(ang)))
+            cv2.line(img, p1, p2, int(rng.integers(0, 256)), int(rng.integers(1, 6)), lineType=cv2.LINE_AA)
+        img = cv2.GaussianBlur(img, (0, 0), 0.8).astype(np.float64)
+        if texture > 0:
+            img += cv2.GaussianBlur(rng.normal(0, 1, img.shape), (0, 0), 2.0) * texture * 6.0
+        img += rng.normal(0, noise_sigma, img.shape)
+        out[f] = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    return out

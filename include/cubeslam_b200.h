@@ -228,6 +228,45 @@ typedef struct csb_ba_optimize_stats {
 } csb_ba_optimize_stats;
 int csb_ba_optimize(csb_context* ctx, int iterations, double* cams7_out, double* cubes10_out, csb_ba_optimize_stats* stats);
 
+/* ------------------------------------------------------------------------------------------------
+ * Line detection: the LSD branch of line_lbd_detect::detect_filter_lines
+ * ------------------------------------------------------------------------------------------------
+ * Replaces, for a batch of equally sized 8-bit gray frames, what
+ *   line_lbd_detect::detect_filter_lines(const cv::Mat& gray_img, cv::Mat& linesmat_out)   line_lbd/class/line_lbd_allclass.cpp:221-235
+ * does with use_LSD = true (line_lbd/launch/line_detect.launch:9): LSDDetector::detectImpl (line_lbd/libs/LSDDetector.cpp:154-293, one
+ * octave) -> LineSegmentDetectorImpl::detect with LSD_REFINE_ADV and the default parameters (line_lbd/libs/lsd.cpp:414-1167:
+ * Gaussian blur + 0.8 down-scaling, level-line angles, region growing in raster seed order, rectangle fit, refinement, NFA search)
+ * -> border clamp / border filter (LSDDetector.cpp:80-101, 206-232) -> length filter (line_lbd_allclass.cpp:200-208).
+ * Output rows are linesmat_out's: float32 [x1 y1 x2 y2] in image coordinates, in the reference's order (keylines_to_mat, :28-38). */
+typedef struct csb_lsd_params {
+    float line_length_thres; /* line_lbd_detect::line_length_thres; both callers set 15 (main_obj.cpp:505, detect_lines.cpp:66) */
+    int32_t filter;          /* 1: detect_filter_lines output; 0: every segment LineSegmentDetectorImpl::detect returns */
+    int32_t max_lines;       /* capacity (rows) per frame of lines_out */
+    int32_t reserved;
+} csb_lsd_params;
+
+typedef struct csb_lsd_stats {
+    int64_t n_lines;        /* segments written over the whole batch */
+    int64_t n_regions;      /* seeds that started a region (region_grow calls from flsd) */
+    int64_t n_region_px;    /* pixels accepted by those calls and by the re-growing of refine() */
+    int64_t h2d_bytes, d2h_bytes;
+    int32_t scaled_width, scaled_height;
+    int32_t n_kernel_launches, reserved;
+    float gpu_ms_maps, gpu_ms_grow; /* CUDA-event times of the last timed run: streaming kernels / region kernel */
+} csb_lsd_stats;
+
+/* Host buffers in and out: gray = n_frames x height x width bytes; lines_out = n_frames x max_lines x 4 floats; n_lines_out[n_frames].
+ * Returns CSB_ERR_CAPACITY (after filling what fits) if any frame produced more than max_lines segments. */
+int csb_lsd_detect_batch(csb_context* ctx, const uint8_t* gray, int n_frames, int width, int height, const csb_lsd_params* params,
+                         float* lines_out, int32_t* n_lines_out, csb_lsd_stats* stats);
+/* Device-resident variant: upload once, run any number of times (asynchronous on the context stream), download. */
+int csb_lsd_upload(csb_context* ctx, const uint8_t* gray, int n_frames, int width, int height, const csb_lsd_params* params);
+int csb_lsd_run(csb_context* ctx, int timed);
+int csb_lsd_download(csb_context* ctx, float* lines_out, int32_t* n_lines_out, csb_lsd_stats* stats);
+/* Parity/debug: per-pixel maps of one frame after a run (scaled_width x scaled_height doubles each, any pointer may be NULL):
+ * the blurred + down-scaled image, the gradient norm, the level-line angle in radians (-1024 = undefined). */
+int csb_lsd_debug_maps(csb_context* ctx, int frame, double* scaled_out, double* modgrad_out, double* angles_out);
+
 #ifdef __cplusplus
 }
 #endif

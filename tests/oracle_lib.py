@@ -64,6 +64,8 @@ def lib():
         L.orc_ba_linearize.restype = C.c_double
         L.orc_det_atan2.restype = C.c_double
         L.orc_det_atan2.argtypes = [C.c_double, C.c_double]
+        L.orc_lsd_fast_atan2.restype = C.c_float
+        L.orc_lsd_fast_atan2.argtypes = [C.c_float, C.c_float]
         _LIB = L
     return _LIB
 
@@ -198,3 +200,30 @@ def se3_log(a7):
 
 def se3_exp(u6):
     o = _v(7); lib().orc_se3_exp(_p(np.ascontiguousarray(u6, np.float64)), _p(o)); return o
+
+
+# ---- LSD line detector (oracle/oracle_lsd.cpp) ------------------------------------------------------------------------------------
+def lsd_gauss_kernel():
+    k = np.zeros(7); lib().orc_lsd_gauss_kernel(_p(k)); return k
+
+
+def lsd_maps(gray, gauss7=None):
+    """scaled image, gradient norm, level-line angle (-1024 = undefined) as the reference's double pipeline computes them."""
+    gray = np.ascontiguousarray(gray, np.uint8); h, w = gray.shape
+    W, H = int(np.rint(w * 0.8)), int(np.rint(h * 0.8))
+    sc = np.zeros((H, W)); mg = np.zeros((H, W)); an = np.zeros((H, W)); sw = C.c_int(); sh = C.c_int()
+    lib().orc_lsd_maps(_p(gray), w, h, _p(gauss7), _p(sc), _p(mg), _p(an), C.byref(sw), C.byref(sh))
+    assert (sw.value, sh.value) == (W, H)
+    return sc, mg, an
+
+
+def lsd_detect(gray, seed_order=0, libm_trig=0, refine=2, mode=1, length_thres=15.0, gauss7=None, scaled=None, cap=20000, details=False):
+    """seed_order 0 = reference (raster), 1 = cv2 4.x; mode 1 = detect_filter_lines output, 0 = raw LSD segments."""
+    gray = np.ascontiguousarray(gray, np.uint8); h, w = gray.shape
+    out = np.zeros((cap, 4), np.float32); det = np.zeros((cap, 12))
+    if scaled is not None:
+        scaled = np.ascontiguousarray(scaled, np.float64)
+    n = lib().orc_lsd_detect(_p(gray), w, h, _p(gauss7), _p(scaled), int(seed_order), int(libm_trig), int(refine), int(mode), C.c_float(length_thres),
+                             _p(out), _p(det), cap)
+    assert 0 <= n <= cap
+    return (out[:n].copy(), det[:n].copy()) if details else out[:n].copy()
