@@ -82,13 +82,13 @@ class BAOutput(C.Structure):
 
 
 class LsdParams(C.Structure):
-    _fields_ = [("line_length_thres", C.c_float), ("filter", C.c_int32), ("max_lines", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("line_length_thres", C.c_float), ("filter", C.c_int32), ("max_lines", C.c_int32), ("unit_link_deg", C.c_int32)]
 
 
 class LsdStats(C.Structure):
     _fields_ = [("n_lines", C.c_int64), ("n_regions", C.c_int64), ("n_region_px", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("scaled_width", C.c_int32), ("scaled_height", C.c_int32), ("n_kernel_launches", C.c_int32), ("reserved", C.c_int32),
-                ("gpu_ms_maps", C.c_float), ("gpu_ms_grow", C.c_float)]
+                ("gpu_ms_maps", C.c_float), ("gpu_ms_grow", C.c_float), ("grow_cycles", C.c_int64 * 5), ("n_merge_rounds", C.c_int64), ("n_unit_conflicts", C.c_int64)]
 
 
 def lib():
@@ -303,8 +303,8 @@ class Context:
         return out
 
     # ---- line detection (LSD) ------------------------------------------------------------------
-    def _lsd_params(self, line_length_thres, filter, max_lines):
-        self._lsd_p = LsdParams(float(line_length_thres), int(filter), int(max_lines), 0)
+    def _lsd_params(self, line_length_thres, filter, max_lines, unit_link_deg=0):
+        self._lsd_p = LsdParams(float(line_length_thres), int(filter), int(max_lines), int(unit_link_deg))
         return self._lsd_p
 
     @staticmethod
@@ -315,20 +315,20 @@ class Context:
         assert gray.ndim == 3
         return gray
 
-    def lsd_detect_batch(self, gray, line_length_thres=15.0, filter=True, max_lines=4096):
+    def lsd_detect_batch(self, gray, line_length_thres=15.0, filter=True, max_lines=4096, unit_link_deg=0):
         """csb_lsd_detect_batch(): gray (n, h, w) uint8 -> list of (k_i, 4) float32 arrays [x1 y1 x2 y2], stats."""
         gray = self._lsd_gray(gray)
         n, h, w = gray.shape
-        P = self._lsd_params(line_length_thres, filter, max_lines)
+        P = self._lsd_params(line_length_thres, filter, max_lines, unit_link_deg)
         lines = np.zeros((n, max_lines, 4), np.float32); cnt = np.zeros(n, np.int32); st = LsdStats()
         self._chk(lib().csb_lsd_detect_batch(self._h, _p(gray), n, w, h, C.byref(P), _p(lines), _p(cnt), C.byref(st)))
         return [lines[i, :cnt[i]].copy() for i in range(n)], st
 
-    def lsd_upload(self, gray, line_length_thres=15.0, filter=True, max_lines=4096):
+    def lsd_upload(self, gray, line_length_thres=15.0, filter=True, max_lines=4096, unit_link_deg=0):
         gray = self._lsd_gray(gray)
         n, h, w = gray.shape
         self._lsd_n = n
-        self._chk(lib().csb_lsd_upload(self._h, _p(gray), n, w, h, C.byref(self._lsd_params(line_length_thres, filter, max_lines))))
+        self._chk(lib().csb_lsd_upload(self._h, _p(gray), n, w, h, C.byref(self._lsd_params(line_length_thres, filter, max_lines, unit_link_deg))))
 
     def lsd_run(self, timed=False):
         self._chk(lib().csb_lsd_run(self._h, int(timed)))

@@ -11,9 +11,13 @@
 //   k_lsd_grad  : (32x8 pixel tile, frame).  ll_angle (lsd.cpp:538-590): 2x2 gradient, norm, fastAtan2 level-line angle; per pixel
 //                 {angle in degrees, cosf(angle), sinf(angle)} (the two terms region_grow adds per accepted pixel, lsd.cpp:679-680,
 //                 evaluated once here with the specified det_sincos), the gradient norm, and a 1-bit "defined" map (warp ballot).
-//   k_lsd_grow  : one warp per frame -- flsd's seed loop (lsd.cpp:474-535) is sequential per frame: seeds are visited in raster order
-//                 and every region depends on the `used` map left by the previous ones.  The `used` and `defined` maps live in shared
-//                 memory as bitmaps (2 x 24 KB for 512x384); seeds are found with ballot/ffs over bitmap words; region_grow tests the
+//   k_lsd_merge / _flatten / _complist : connected components of the "defined" mask (union-find, root = first pixel in raster order).
+//   k_lsd_grow  : one CTA per frame, one warp per connected component (dynamic queue, big components first).  flsd's seed loop
+//                 (lsd.cpp:474-535) visits seeds in raster order and every region depends on the `used` map left by the previous
+//                 ones -- but only inside one component, because regions only ever add defined 8-neighbours; so components run
+//                 concurrently and the segments are put back into seed order at the end.  The `used` and `defined` maps live in shared
+//                 memory as bitmaps (2 x 24 KB for 512x384, atomicOr/atomicAnd: words are shared between components); a warp first
+//                 lists its component's pixels in raster order (label scan of the bounding box), then walks that list; region_grow tests the
 //                 8 neighbours of a region pixel on 9 lanes at once and replays the reference's sequential accept order (the running
 //                 angle changes after every accepted pixel, so later neighbours are re-tested); the order-dependent FP64 sums of
 //                 region2rect / get_theta / refine are accumulated in region order from per-lane products staged in shared memory;
@@ -40,6 +44,7 @@ constexpr double LSD_2PI = 2 * LSD_PI;
 constexpr double LSD_DEG2RAD = LSD_PI / 180;
 constexpr float LSD_NOTDEF_DEG = -1024.f;  // sentinel in the degree map (fastAtan2 returns [0, 360])
 constexpr double LSD_SCALE = 0.8;
+constexpr int LSD_RING = 512;
 
 struct LsdDims {
     int w, h;     // source frame
@@ -62,15 +67,31 @@ struct LsdConst {
 struct LsdBuffers {
     const uint8_t* gray;
     double* scaled;
-    float4* pix;       // {deg, cosf, sinf, 0}
-    float* deg;        // compact copy of pix.x for the NFA counts
+    float4* pix;       // {deg, cosf, sinf, unit label as int bits}
+    float* deg;        // compact copy of pix.x for the NFA counts and the labelling
     double* modgrad;
     uint32_t* defbits;
-    uint32_t* reg;     // region lists, W*H entries per frame (x | y << 16)
-    uint32_t* tmp;     // scratch of reduce_region_radius, W*H entries per frame
+    // work arenas, W*H entries per frame each.  Arena A serves the units of the first round, arena B the merged units of later rounds.
+    uint32_t *regA, *tmpA, *lstA, *regB, *tmpB, *lstB;  // region list (x | y << 16), scratch of reduce_region_radius, a unit's pixels in raster order
+    int* label;        // unit label of every pixel: root = smallest pixel index of its unit; -1 = undefined
+    int* csize;        // per root pixel: unit size, min x, max x, max y (aggregated into the leader when units are merged)
+    int* cminx;
+    int* cmaxx;
+    int* cmaxy;
+    int* cflag;        // per root pixel: bit 0 = some pixel of the unit touches a defined pixel of another unit
+    int* cgrp;         // per root pixel: union-find parent over units (merging of interacting units)
+    int* cmark;        // per root pixel: round in which the root became the leader of a merged unit
+    int* units;        // n_frames x W*H: roots of the first-round units, big ones from the front, small ones from the back
+    int* units2;       // n_frames x W*H: leaders of the merged units of the current round
+    int* viol;         // n_frames x 2 x W*H: (unit leader, foreign root) pairs recorded in the current round
+    int* ncomp;        // n_frames x 4: [0] big units, [1] small units
+    float4* stage;     // n_frames x stage_cap segments in completion order ...
+    int* stage_key;    // ... the pixel index of the seed each one grew from (the reference's output order; -1 = discarded) ...
+    int* stage_owner;  // ... and the root of the unit that produced it
     float* lines;      // n_frames x max_lines x 4
     int* n_lines;      // n_frames
-    unsigned long long* stats;  // [0] regions, [1] region pixels
+    unsigned long long* stats;  // [0] regions, [1] region pixels, [2..5] SM cycles per phase, [6] SM cycles of the whole seed loop (summed over warps), [7] merge rounds, [8] violations
+    int stage_cap;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------------------
@@ -241,9 +262,138 @@ __global__ void __launch_bounds__(256) k_lsd_grad(LsdBuffers B, LsdDims d, LsdCo
         B.pix[fo + (size_t)y * d.W + x] = make_float4(deg, cv, sv, 0.f);
         B.deg[fo + (size_t)y * d.W + x] = deg;
         B.modgrad[fo + (size_t)y * d.W + x] = mg;
+        const size_t pi = fo + (size_t)y * d.W + x;
+        B.label[pi] = def ? y * d.W + x : -1;
+        if (def) {
+            B.csize[pi] = 0;
+            B.cminx[pi] = 0x7fffffff;
+            B.cmaxx[pi] = -1;
+            B.cmaxy[pi] = -1;
+            B.cflag[pi] = 0;
+            B.cmark[pi] = 0;
+            B.cgrp[pi] = y * d.W + x;
+        }
     }
     const unsigned bits = __ballot_sync(0xffffffffu, def);
     if (threadIdx.x == 0 && y < d.H) B.defbits[(size_t)f * d.H * d.WW + (size_t)y * d.WW + blockIdx.x] = bits;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Units of independent work.  region_grow (lsd.cpp:637-688) only ever adds DEFINED 8-neighbours that are aligned with the running
+// region angle, and the `used` state of a pixel is only read and written by regions that test it.  The defined pixels are therefore
+// partitioned into "units": connected sets under the relation "8-adjacent, both defined, level-line angles within LSD_LINK_DEG of
+// each other" (a straight edge is one unit; at a corner or a crossing the angle jumps and the units split).  A unit is processed in
+// isolation by one warp, seeds in raster order, and is VALID iff none of its regions ever finds a pixel of another unit aligned --
+// whatever that pixel's used state -- because then neither side can observe the other.  A unit that does find one records the pair
+// and stops; interacting units are merged (union-find over unit roots) and the merged unit is redone, round after round, until every
+// unit is valid; the result is then exactly the reference's sequential one.  Units smaller than min_reg_size that touch no other unit
+// are whole connected components that cannot yield a segment (lsd.cpp:489) and are skipped.
+//   k_lsd_merge   : union-find with atomicMin (root = smallest pixel index) over the W / NW / N / NE neighbours
+//   k_lsd_flatten : label <- root (also into pix.w); per-root size and bounding box (warp-aggregated atomics)
+//   k_lsd_contact : per-root flag "touches another unit"
+//   k_lsd_units   : roots of the first-round units, big ones first (they bound the frame's critical path)
+// ---------------------------------------------------------------------------------------------------------------------------------
+constexpr float LSD_LINK_DEG = 45.f;  // default; csb_lsd_params::unit_link_deg overrides it (tests use small values to force merge rounds)
+
+__device__ __forceinline__ int ccl_find(const int* L, int a) {
+    int r = L[a];
+    while (r != a) {
+        a = r;
+        r = L[a];
+    }
+    return a;
+}
+__device__ __forceinline__ void ccl_union(int* L, int a, int b) {
+    while (true) {
+        a = ccl_find(L, a);
+        b = ccl_find(L, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }
+        const int old = atomicMin(&L[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+__device__ __forceinline__ bool lsd_linked(float a, float b, float link_deg) {  // both defined
+    float dd = fabsf(a - b);
+    if (dd > 180.f) dd = 360.f - dd;
+    return dd <= link_deg;
+}
+
+__global__ void __launch_bounds__(256) k_lsd_merge(LsdBuffers B, LsdDims d, float link_deg) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
+    if (x >= d.W || y >= d.H) return;
+    const size_t fo = (size_t)f * d.W * d.H;
+    int* L = B.label + fo;
+    const float* A = B.deg + fo;
+    const int p = y * d.W + x;
+    const float a = A[p];
+    if (a == LSD_NOTDEF_DEG) return;
+    if (x > 0 && A[p - 1] != LSD_NOTDEF_DEG && lsd_linked(a, A[p - 1], link_deg)) ccl_union(L, p, p - 1);
+    if (y > 0) {
+        const int q = p - d.W;
+        if (x > 0 && A[q - 1] != LSD_NOTDEF_DEG && lsd_linked(a, A[q - 1], link_deg)) ccl_union(L, p, q - 1);
+        if (A[q] != LSD_NOTDEF_DEG && lsd_linked(a, A[q], link_deg)) ccl_union(L, p, q);
+        if (x + 1 < d.W && A[q + 1] != LSD_NOTDEF_DEG && lsd_linked(a, A[q + 1], link_deg)) ccl_union(L, p, q + 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_lsd_flatten(LsdBuffers B, LsdDims d) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
+    const size_t fo = (size_t)f * d.W * d.H;
+    int* L = B.label + fo;
+    int r = -1;
+    if (x < d.W && y < d.H) {
+        const int p = y * d.W + x;
+        if (L[p] >= 0) {
+            r = ccl_find(L, p);
+            L[p] = r;
+            B.pix[fo + p].w = __int_as_float(r);
+        }
+    }
+    const unsigned act = __ballot_sync(0xffffffffu, r >= 0);
+    if (r < 0) return;
+    const unsigned grp = __match_any_sync(act, r);
+    const int mn = __reduce_min_sync(grp, x), mx = __reduce_max_sync(grp, x);
+    if ((int)(threadIdx.x) == __ffs(grp) - 1) {
+        atomicAdd(&B.csize[fo + r], __popc(grp));
+        atomicMin(&B.cminx[fo + r], mn);
+        atomicMax(&B.cmaxx[fo + r], mx);
+        atomicMax(&B.cmaxy[fo + r], y);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_lsd_contact(LsdBuffers B, LsdDims d) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
+    if (x >= d.W || y >= d.H) return;
+    const size_t fo = (size_t)f * d.W * d.H;
+    const int* L = B.label + fo;
+    const int p = y * d.W + x, r = L[p];
+    if (r < 0) return;
+    bool touch = false;
+    for (int dy = -1; dy <= 1; dy++)
+        for (int dx = -1; dx <= 1; dx++) {
+            const int xx = x + dx, yy = y + dy;
+            if (xx < 0 || xx >= d.W || yy < 0 || yy >= d.H) continue;
+            const int l = L[yy * d.W + xx];
+            touch |= l >= 0 && l != r;
+        }
+    if (touch) B.cflag[fo + r] = 1;
+}
+
+constexpr int LSD_BIG_UNIT = 128;
+
+__global__ void __launch_bounds__(256) k_lsd_units(LsdBuffers B, LsdDims d, int min_reg_size) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
+    if (x >= d.W || y >= d.H) return;
+    const size_t fo = (size_t)f * d.W * d.H;
+    const int p = y * d.W + x;
+    if (B.label[fo + p] != p) return;
+    const int size = B.csize[fo + p];
+    if (size < min_reg_size && !B.cflag[fo + p]) return;
+    int* nc = B.ncomp + 4 * f;
+    const int slot = size >= LSD_BIG_UNIT ? atomicAdd(&nc[0], 1) : d.W * d.H - 1 - atomicAdd(&nc[1], 1);
+    B.units[fo + slot] = p;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------
@@ -321,22 +471,83 @@ struct Grow {
     const float4* pix;
     const float* deg;
     const double* mg;
+    const int* cgrp;    // union-find parents over unit roots (merged units)
     uint32_t* reg;
     uint32_t* tmp;
     uint32_t* U;        // shared: used bitmap
     const uint32_t* D;  // shared: defined bitmap
     double* sc;         // shared: 3 x 32 doubles
+    uint32_t* ring;     // shared: the last LSD_RING queue entries of the region being grown
     int W, H, WW, lane;
+    int leader;         // root of the unit being processed
+    int mode;           // 0: first-round unit (foreign <=> label != leader); 1: merged unit (find(label) != leader); 2: whole frame (nothing is foreign)
+    int foreign_root;   // set when a region found a pixel of another unit aligned: the unit must be merged with that one and redone
     double LOG_NT;
     unsigned long long n_regions, n_px;
 
     __device__ __forceinline__ void clear_used(int px, int py) { atomicAnd(&U[py * WW + (px >> 5)], ~(1u << (px & 31))); }
+    __device__ __forceinline__ bool is_foreign(int lbl) const {
+        if (mode == 0) return lbl != leader;
+        if (mode == 1) return lbl != leader && ccl_find(cgrp, lbl) != leader;
+        return false;
+    }
 
-    // lsd.cpp:637-688.  Returns the region size; the region is reg[0 .. size).
+    // lsd.cpp:637-688.  Returns the region size (the region is reg[0 .. size)), or -1 if a pixel of another unit was found aligned.
+    // The queue head is read from a shared-memory ring (the last LSD_RING entries; older ones from global memory), and the neighbour
+    // records of queue entries i, i+1, i+2 are loaded ahead of time into three register sets (software pipeline, unrolled by three so
+    // that consuming one set never waits for the loads of the others).  Every defined neighbour is loaded: its record carries the
+    // label that tells own pixels (candidates while unused) from foreign ones (tested whatever their used state: finding one aligned
+    // invalidates the unit).
+    __device__ __forceinline__ uint32_t queue_at(int j, int n) const { return (n - j <= LSD_RING) ? ring[j & (LSD_RING - 1)] : reg[j]; }
+
+#define LSD_ISSUE(S, J)                                                                                         \
+    if (!have##S && (J) < n) {                                                                                  \
+        const uint32_t q_ = queue_at((J), n);                                                                   \
+        const int xx_ = (int)(q_ & 0xffffu) + ox, yy_ = (int)(q_ >> 16) + oy;                                  \
+        const bool inb_ = lane < 9 && xx_ >= 0 && xx_ < W && yy_ >= 0 && yy_ < H;                              \
+        word##S = inb_ ? yy_ * WW + (xx_ >> 5) : 0;                                                             \
+        bit##S = 1u << (xx_ & 31);                                                                              \
+        pos##S = (uint32_t)xx_ | ((uint32_t)yy_ << 16);                                                         \
+        def##S = inb_ && (D[word##S] & bit##S);                                                                 \
+        if (def##S) v##S = pix[(size_t)yy_ * W + xx_];                                                          \
+        have##S = true;                                                                                         \
+    }
+#define LSD_PROCESS(S)                                                                                          \
+    {                                                                                                           \
+        const bool frn_ = def##S && is_foreign(__float_as_int(v##S.w));                                         \
+        const bool cand_ = def##S && (frn_ || !(U[word##S] & bit##S));                                          \
+        unsigned m_ = __ballot_sync(0xffffffffu, cand_);                                                        \
+        while (m_) {                                                                                            \
+            const bool al_ = cand_ && l_aligned_deg(v##S.x, reg_angle, prec);                                   \
+            const unsigned am_ = __ballot_sync(0xffffffffu, al_) & m_;                                          \
+            if (!am_) break;                                                                                    \
+            const int l_ = __ffs(am_) - 1;                                                                      \
+            if (__shfl_sync(0xffffffffu, (int)frn_, l_)) {                                                      \
+                foreign_root = __shfl_sync(0xffffffffu, __float_as_int(v##S.w), l_);                            \
+                break;                                                                                          \
+            }                                                                                                   \
+            if (lane == l_) {                                                                                   \
+                atomicOr(&U[word##S], bit##S);                                                                  \
+                reg[n] = pos##S;                                                                                \
+                ring[n & (LSD_RING - 1)] = pos##S;                                                              \
+            }                                                                                                   \
+            sumdx += __shfl_sync(0xffffffffu, v##S.y, l_);                                                      \
+            sumdy += __shfl_sync(0xffffffffu, v##S.z, l_);                                                      \
+            reg_angle = (double)fast_atan2f(sumdy, sumdx) * LSD_DEG2RAD;                                        \
+            ++n;                                                                                                \
+            m_ &= ~((2u << l_) - 1u);                                                                           \
+        }                                                                                                       \
+        have##S = false;                                                                                        \
+        __syncwarp();                                                                                           \
+        if (foreign_root >= 0) return -1;                                                                       \
+    }
+
     __device__ __noinline__ int region_grow(int sx, int sy, double prec, double& reg_angle_out) {
         if (lane == 0) {
-            reg[0] = (uint32_t)sx | ((uint32_t)sy << 16);
-            U[sy * WW + (sx >> 5)] |= 1u << (sx & 31);
+            const uint32_t q = (uint32_t)sx | ((uint32_t)sy << 16);
+            reg[0] = q;
+            ring[0] = q;
+            atomicOr(&U[sy * WW + (sx >> 5)], 1u << (sx & 31));
         }
         int n = 1;
         double reg_angle = (double)pix[(size_t)sy * W + sx].x * LSD_DEG2RAD;
@@ -344,37 +555,28 @@ struct Grow {
         det_sincos(reg_angle, s0, c0);
         float sumdx = (float)c0, sumdy = (float)s0;
         const int ox = lane % 3 - 1, oy = lane / 3 - 1;
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0;
+        bool have0 = false, have1 = false, have2 = false, def0 = false, def1 = false, def2 = false;
+        int word0 = 0, word1 = 0, word2 = 0;
+        unsigned bit0 = 0, bit1 = 0, bit2 = 0;
+        uint32_t pos0 = 0, pos1 = 0, pos2 = 0;
         __syncwarp();
-        for (int i = 0; i < n; ++i) {
-            const uint32_t q = reg[i];
-            const int xx = (int)(q & 0xffffu) + ox, yy = (int)(q >> 16) + oy;
-            const bool inb = lane < 9 && xx >= 0 && xx < W && yy >= 0 && yy < H;
-            const int word = inb ? yy * WW + (xx >> 5) : 0;
-            const unsigned bit = 1u << (xx & 31);
-            const bool cand = inb && (D[word] & bit) && !(U[word] & bit);
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (cand) v = pix[(size_t)yy * W + xx];
-            unsigned m = __ballot_sync(0xffffffffu, cand);
-            while (m) {
-                const bool al = cand && l_aligned_deg(v.x, reg_angle, prec);
-                const unsigned am = __ballot_sync(0xffffffffu, al) & m;
-                if (!am) break;
-                const int l = __ffs(am) - 1;
-                if (lane == l) {
-                    U[word] |= bit;
-                    reg[n] = (uint32_t)xx | ((uint32_t)yy << 16);
-                }
-                sumdx += __shfl_sync(0xffffffffu, v.y, l);
-                sumdy += __shfl_sync(0xffffffffu, v.z, l);
-                reg_angle = (double)fast_atan2f(sumdy, sumdx) * LSD_DEG2RAD;
-                ++n;
-                m &= ~((2u << l) - 1u);
-            }
-            __syncwarp();
+        for (int i = 0;; i += 3) {
+            LSD_ISSUE(0, i) LSD_ISSUE(1, i + 1) LSD_ISSUE(2, i + 2)
+            if (i >= n) break;
+            LSD_PROCESS(0)
+            LSD_ISSUE(1, i + 1) LSD_ISSUE(2, i + 2) LSD_ISSUE(0, i + 3)
+            if (i + 1 >= n) break;
+            LSD_PROCESS(1)
+            LSD_ISSUE(2, i + 2) LSD_ISSUE(0, i + 3) LSD_ISSUE(1, i + 4)
+            if (i + 2 >= n) break;
+            LSD_PROCESS(2)
         }
         reg_angle_out = reg_angle;
         return n;
     }
+#undef LSD_ISSUE
+#undef LSD_PROCESS
 
     // lsd.cpp:690-746 + get_theta :748-784
     __device__ __noinline__ void region2rect(int n, double reg_angle, double prec, double p, LRect& rec) {
@@ -552,8 +754,8 @@ struct Grow {
         const double mean_angle = sum / double(cnt);
         const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / double(cnt) + mean_angle * mean_angle);
         n = region_grow(x0, y0, tau, reg_angle);
+        if (n < 2) return false;  // also the foreign-pixel exit (n = -1; the caller checks foreign_root)
         n_px += n;
-        if (n < 2) return false;
         region2rect(n, reg_angle, prec, p, rec);
         density = double(n) / (l_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
         if (density < density_th) return reduce_region_radius(n, reg_angle, prec, p, rec, density, density_th);
@@ -685,94 +887,232 @@ struct Grow {
     }
 };
 
-__global__ void __launch_bounds__(32) k_lsd_grow(LsdBuffers B, LsdDims d, LsdConst C) {
+constexpr int LSD_WARPS = 8;  // 8 warps x <=128 registers: two CTAs (frames) per SM
+constexpr int LSD_WARP_SMEM = 96 * sizeof(double) + LSD_RING * sizeof(uint32_t);  // per warp: staging of the ordered sums + queue ring
+constexpr int LSD_MAX_ROUNDS = 12;  // merge rounds before the rest of the frame is redone as one unit
+
+__global__ void __launch_bounds__(LSD_WARPS * 32, 2) k_lsd_grow(LsdBuffers B, LsdDims d, LsdConst C) {
     extern __shared__ __align__(16) unsigned char lsd_smem[];
-    const int f = blockIdx.x, lane = threadIdx.x;
-    const int nw = d.H * d.WW;
+    __shared__ int s_next, s_nout, s_nviol, s_nunits, s_alloc;
+    const int f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nw = d.H * d.WW, npx = d.W * d.H;
     Grow G;
-    G.sc = reinterpret_cast<double*>(lsd_smem);
-    G.U = reinterpret_cast<uint32_t*>(lsd_smem + 96 * sizeof(double));
+    G.sc = reinterpret_cast<double*>(lsd_smem + (size_t)warp * LSD_WARP_SMEM);
+    G.ring = reinterpret_cast<uint32_t*>(G.sc + 96);
+    G.U = reinterpret_cast<uint32_t*>(lsd_smem + (size_t)LSD_WARPS * LSD_WARP_SMEM);
     uint32_t* Dm = G.U + nw;
     G.D = Dm;
-    const size_t fo = (size_t)f * d.W * d.H;
+    const size_t fo = (size_t)f * npx;
     G.pix = B.pix + fo;
     G.deg = B.deg + fo;
     G.mg = B.modgrad + fo;
-    G.reg = B.reg + fo;
-    G.tmp = B.tmp + fo;
+    int* cgrp = B.cgrp + fo;
+    G.cgrp = cgrp;
     G.W = d.W; G.H = d.H; G.WW = d.WW; G.lane = lane;
     G.LOG_NT = C.log_nt;
     G.n_regions = 0; G.n_px = 0;
     const uint32_t* dsrc = B.defbits + (size_t)f * nw;
-    for (int i = lane; i < nw; i += 32) {
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) {
         G.U[i] = 0;
         Dm[i] = dsrc[i];
     }
-    __syncwarp();
-    float* lines = B.lines + (size_t)f * C.max_lines * 4;
-    int n_out = 0;
-    for (int wbase = 0; wbase < nw; wbase += 32) {
-        const int widx = wbase + lane;
-        unsigned nz = __ballot_sync(0xffffffffu, widx < nw && (Dm[widx] & ~G.U[widx]) != 0);
-        while (nz) {
-            const int l = __ffs(nz) - 1, w = wbase + l;
-            const int wy = w / d.WW, wx0 = (w - wy * d.WW) * 32;
-            int lastbit = -1;
-            while (true) {
-                unsigned cand = Dm[w] & ~G.U[w];
-                if (lastbit >= 0) cand &= ~((2u << lastbit) - 1u);
-                if (!cand) break;
-                const int b = __ffs(cand) - 1;
-                lastbit = b;
-                const int sx = wx0 + b, sy = wy;
-                // ---- one seed (lsd.cpp:478-534)
-                double reg_angle;
-                int n = G.region_grow(sx, sy, C.prec, reg_angle);
-                G.n_regions++;
-                G.n_px += n;
-                if (n < C.min_reg_size) continue;
-                LRect rec;
-                G.region2rect(n, reg_angle, C.prec, C.p, rec);
-                if (!G.refine(n, reg_angle, C.prec, C.p, rec, 0.7)) continue;
-                const double log_nfa = G.rect_improve(rec);
-                if (log_nfa <= 0) continue;
-                rec.x1 += 0.5; rec.y1 += 0.5; rec.x2 += 0.5; rec.y2 += 0.5;
-                rec.x1 /= LSD_SCALE; rec.y1 /= LSD_SCALE; rec.x2 /= LSD_SCALE; rec.y2 /= LSD_SCALE;
-                float e0 = float(rec.x1), e1 = float(rec.y1), e2 = float(rec.x2), e3 = float(rec.y2);
-                if (C.filter) {
-                    // LSDDetector.cpp:80-101, 219-232 (octaveScale = 1), line_lbd_allclass.cpp:206
-                    const int w_ = d.w, h_ = d.h;
-                    if (e0 < 0) e0 = 0;
-                    if (e0 >= w_) e0 = (float)w_ - 1.0f;
-                    if (e2 < 0) e2 = 0;
-                    if (e2 >= w_) e2 = (float)w_ - 1.0f;
-                    if (e1 < 0) e1 = 0;
-                    if (e1 >= h_) e1 = (float)h_ - 1.0f;
-                    if (e3 < 0) e3 = 0;
-                    if (e3 >= h_) e3 = (float)h_ - 1.0f;
-                    const float thr = 10;
-                    if (((e0 < thr) && (e2 < thr)) || ((e0 > w_ - thr) && (e2 > w_ - thr)) || ((e1 < thr) && (e3 < thr)) ||
-                        ((e1 > h_ - thr) && (e3 > h_ - thr)))
-                        continue;
-                    const double ddx = double(e0 - e2), ddy = double(e1 - e3);
-                    const float len = (float)sqrt(ddx * ddx + ddy * ddy);
-                    if (!(len > C.length_thres)) continue;
+    const int n_big = B.ncomp[4 * f], n_small = B.ncomp[4 * f + 1];
+    if (threadIdx.x == 0) { s_next = 0; s_nout = 0; s_nviol = 0; s_alloc = 0; s_nunits = n_big + n_small; }
+    __syncthreads();
+    const int* L = B.label + fo;
+    int *csize = B.csize + fo, *cminx = B.cminx + fo, *cmaxx = B.cmaxx + fo, *cmaxy = B.cmaxy + fo, *cmark = B.cmark + fo;
+    const int* units = B.units + fo;
+    int* units2 = B.units2 + fo;
+    int* viol = B.viol + 2 * fo;
+    float4* stage = B.stage + (size_t)f * B.stage_cap;
+    int* stage_key = B.stage_key + (size_t)f * B.stage_cap;
+    int* stage_owner = B.stage_owner + (size_t)f * B.stage_cap;
+    long long cyc[4] = {0, 0, 0, 0};  // region_grow, region2rect, refine (with re-growing), rect_improve
+    const long long t_begin = clock64();
+    int round = 0;
+    for (;; round++) {
+        const int n_units = s_nunits;
+        const int mode = round == 0 ? 0 : (round <= LSD_MAX_ROUNDS ? 1 : 2);
+        uint32_t *regX = round == 0 ? B.regA : B.regB, *tmpX = round == 0 ? B.tmpA : B.tmpB, *lstX = round == 0 ? B.lstA : B.lstB;
+        while (true) {
+            int ci = 0;
+            if (lane == 0) ci = atomicAdd(&s_next, 1);
+            ci = __shfl_sync(0xffffffffu, ci, 0);
+            if (ci >= n_units) break;
+            const int root = mode == 0 ? units[ci < n_big ? ci : npx - 1 - (ci - n_big)] : (mode == 1 ? units2[ci] : 0);
+            int usize, minx, maxx, y0, maxy;
+            if (mode == 2) { usize = npx; minx = 0; maxx = d.W - 1; y0 = 0; maxy = d.H - 1; }
+            else { usize = csize[root]; minx = cminx[root]; maxx = cmaxx[root]; y0 = root / d.W; maxy = cmaxy[root]; }
+            int off = 0;
+            if (lane == 0) off = atomicAdd(&s_alloc, usize);
+            off = __shfl_sync(0xffffffffu, off, 0);
+            G.reg = regX + fo + off;
+            G.tmp = tmpX + fo + off;
+            uint32_t* lst = lstX + fo + off;
+            G.leader = root;
+            G.mode = mode;
+            G.foreign_root = -1;
+            // (1) the unit's pixels in raster order: scan its bounding box for the label.  A merged unit starts from a clean used map.
+            int cnt = 0;
+            for (int y = y0; y <= maxy && cnt < usize; y++)
+                for (int xb = minx & ~31; xb <= maxx; xb += 32) {
+                    const int x = xb + lane;
+                    bool mine = false;
+                    if (x <= maxx) {
+                        const int lbl = L[(size_t)y * d.W + x];
+                        mine = mode == 0 ? lbl == root : (lbl >= 0 && (mode == 2 || lbl == root || ccl_find(cgrp, lbl) == root));
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, mine);
+                    if (mine) {
+                        lst[cnt + __popc(m & ((1u << lane) - 1u))] = (uint32_t)x | ((uint32_t)y << 16);
+                        if (mode != 0) G.clear_used(x, y);
+                    }
+                    cnt += __popc(m);
                 }
-                if (lane == 0 && n_out < C.max_lines) {
-                    float4* o = reinterpret_cast<float4*>(lines) + n_out;
-                    *o = make_float4(e0, e1, e2, e3);
-                }
-                ++n_out;
-            }
             __syncwarp();
-            nz = __ballot_sync(0xffffffffu, widx < nw && lane > l && (Dm[widx] & ~G.U[widx]) != 0);
+            // (2) flsd's seed loop (lsd.cpp:474-535) over this unit
+            for (int base = 0; base < cnt && G.foreign_root < 0; base += 32) {
+                const int idx = base + lane;
+                const uint32_t q = idx < cnt ? lst[idx] : 0u;
+                const int qx = q & 0xffffu, qy = q >> 16;
+                unsigned todo = 0xffffffffu;
+                while (G.foreign_root < 0) {
+                    const bool unused = idx < cnt && !(G.U[qy * d.WW + (qx >> 5)] & (1u << (qx & 31)));
+                    const unsigned m = __ballot_sync(0xffffffffu, unused) & todo;
+                    if (!m) break;
+                    const int l = __ffs(m) - 1;
+                    todo = ~((2u << l) - 1u);
+                    const int sx = __shfl_sync(0xffffffffu, qx, l), sy = __shfl_sync(0xffffffffu, qy, l);
+                    // ---- one seed (lsd.cpp:478-534)
+                    double reg_angle;
+                    long long t0 = clock64();
+                    int n = G.region_grow(sx, sy, C.prec, reg_angle);
+                    long long t1 = clock64();
+                    cyc[0] += t1 - t0;
+                    if (n < 0) break;
+                    G.n_regions++;
+                    G.n_px += n;
+                    if (n < C.min_reg_size) continue;
+                    LRect rec;
+                    G.region2rect(n, reg_angle, C.prec, C.p, rec);
+                    t0 = clock64();
+                    cyc[1] += t0 - t1;
+                    const bool ok = G.refine(n, reg_angle, C.prec, C.p, rec, 0.7);
+                    t1 = clock64();
+                    cyc[2] += t1 - t0;
+                    if (!ok) continue;  // (or a foreign pixel: the loop condition ends the unit)
+                    const double log_nfa = G.rect_improve(rec);
+                    cyc[3] += clock64() - t1;
+                    if (log_nfa <= 0) continue;
+                    rec.x1 += 0.5; rec.y1 += 0.5; rec.x2 += 0.5; rec.y2 += 0.5;
+                    rec.x1 /= LSD_SCALE; rec.y1 /= LSD_SCALE; rec.x2 /= LSD_SCALE; rec.y2 /= LSD_SCALE;
+                    float e0 = float(rec.x1), e1 = float(rec.y1), e2 = float(rec.x2), e3 = float(rec.y2);
+                    if (C.filter) {
+                        // LSDDetector.cpp:80-101, 219-232 (octaveScale = 1), line_lbd_allclass.cpp:206
+                        const int w_ = d.w, h_ = d.h;
+                        if (e0 < 0) e0 = 0;
+                        if (e0 >= w_) e0 = (float)w_ - 1.0f;
+                        if (e2 < 0) e2 = 0;
+                        if (e2 >= w_) e2 = (float)w_ - 1.0f;
+                        if (e1 < 0) e1 = 0;
+                        if (e1 >= h_) e1 = (float)h_ - 1.0f;
+                        if (e3 < 0) e3 = 0;
+                        if (e3 >= h_) e3 = (float)h_ - 1.0f;
+                        const float thr = 10;
+                        if (((e0 < thr) && (e2 < thr)) || ((e0 > w_ - thr) && (e2 > w_ - thr)) || ((e1 < thr) && (e3 < thr)) ||
+                            ((e1 > h_ - thr) && (e3 > h_ - thr)))
+                            continue;
+                        const double ddx = double(e0 - e2), ddy = double(e1 - e3);
+                        const float len = (float)sqrt(ddx * ddx + ddy * ddy);
+                        if (!(len > C.length_thres)) continue;
+                    }
+                    if (lane == 0) {
+                        const int slot = atomicAdd(&s_nout, 1);
+                        if (slot < B.stage_cap) {
+                            stage[slot] = make_float4(e0, e1, e2, e3);
+                            stage_key[slot] = sy * d.W + sx;
+                            stage_owner[slot] = root;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            if (G.foreign_root >= 0 && lane == 0) {  // one pair per unit and round
+                const int k = atomicAdd(&s_nviol, 1);
+                viol[2 * k] = root;
+                viol[2 * k + 1] = G.foreign_root;
+            }
         }
+        __syncthreads();
+        const int nv = s_nviol;
+        __syncthreads();  // everybody has read the count before thread 0 resets it
+        if (nv == 0) break;
+        // ---- merge the interacting units (one thread: the lists are short), then redo the merged ones in the next round
+        if (threadIdx.x == 0) {
+            int k = 0;
+            if (round + 1 > LSD_MAX_ROUNDS) {
+                k = 1;  // last resort: the whole frame as one unit, processed sequentially by one warp
+            } else {
+                for (int v = 0; v < nv; v++) {
+                    int ra = ccl_find(cgrp, viol[2 * v]), rb = ccl_find(cgrp, viol[2 * v + 1]);
+                    if (ra == rb) continue;
+                    if (ra > rb) { const int t = ra; ra = rb; rb = t; }
+                    cgrp[rb] = ra;
+                    csize[ra] += csize[rb];
+                    cminx[ra] = min(cminx[ra], cminx[rb]);
+                    cmaxx[ra] = max(cmaxx[ra], cmaxx[rb]);
+                    cmaxy[ra] = max(cmaxy[ra], cmaxy[rb]);
+                }
+                for (int v = 0; v < nv; v++) {
+                    const int r = ccl_find(cgrp, viol[2 * v]);
+                    if (cmark[r] != round + 1) {
+                        cmark[r] = round + 1;
+                        units2[k++] = r;
+                    }
+                }
+            }
+            s_nunits = k;
+            s_next = 0;
+            s_nviol = 0;
+            s_alloc = 0;
+            atomicAdd(&B.stats[7], 1ull);
+            atomicAdd(&B.stats[8], (unsigned long long)nv);
+        }
+        __syncthreads();
+        // segments of units that are being redone are dropped
+        const int n_st = min(s_nout, B.stage_cap);
+        const bool all = round + 1 > LSD_MAX_ROUNDS;
+        for (int i = threadIdx.x; i < n_st; i += blockDim.x)
+            if (stage_key[i] >= 0 && (all || cmark[ccl_find(cgrp, stage_owner[i])] == round + 1)) stage_key[i] = -1;
+        __syncthreads();
     }
     if (lane == 0) {
-        B.n_lines[f] = n_out;
         atomicAdd(&B.stats[0], G.n_regions);
         atomicAdd(&B.stats[1], G.n_px);
+        for (int i = 0; i < 4; i++) atomicAdd(&B.stats[2 + i], (unsigned long long)cyc[i]);
+        atomicAdd(&B.stats[6], (unsigned long long)(clock64() - t_begin));
     }
+    // (3) the reference pushes segments in seed order (lsd.cpp:523): rank every kept segment by its seed's pixel index
+    const int n_raw = s_nout, n_st = min(n_raw, B.stage_cap);
+    float4* lines = reinterpret_cast<float4*>(B.lines) + (size_t)f * C.max_lines;
+    __shared__ int s_kept;
+    if (threadIdx.x == 0) s_kept = 0;
+    __syncthreads();
+    int kept = 0;
+    for (int i = threadIdx.x; i < n_st; i += blockDim.x) {
+        const int key = stage_key[i];
+        if (key < 0) continue;
+        int rank = 0;
+        for (int j = 0; j < n_st; j++) {
+            const int kj = stage_key[j];
+            rank += kj >= 0 && kj < key;
+        }
+        if (rank < C.max_lines) lines[rank] = stage[i];
+        kept++;
+    }
+    if (kept) atomicAdd(&s_kept, kept);
+    __syncthreads();
+    if (threadIdx.x == 0) B.n_lines[f] = n_raw > B.stage_cap ? 0x7fffffff : s_kept;  // staging overflow is reported as a capacity error
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------
@@ -783,7 +1123,8 @@ struct LsdState {
     LsdDims d{};
     LsdConst C{};
     csb_lsd_params params{};
-    DevBuf d_gray, d_scaled, d_pix, d_deg, d_mg, d_def, d_reg, d_tmp, d_lines, d_nlines, d_stats;
+    DevBuf d_gray, d_scaled, d_pix, d_deg, d_mg, d_def, d_arena, d_roots, d_ncomp, d_stage, d_stage_key, d_stage_owner, d_lines, d_nlines, d_stats;
+    int stage_cap = 0;
     HostBuf h_gray, h_out;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     size_t grow_smem = 0;
@@ -793,7 +1134,8 @@ struct LsdState {
 
 void lsd_release(LsdState*& s) {
     if (!s) return;
-    DevBuf* bufs[] = {&s->d_gray, &s->d_scaled, &s->d_pix, &s->d_deg, &s->d_mg, &s->d_def, &s->d_reg, &s->d_tmp, &s->d_lines, &s->d_nlines, &s->d_stats};
+    DevBuf* bufs[] = {&s->d_gray, &s->d_scaled, &s->d_pix, &s->d_deg, &s->d_mg, &s->d_def, &s->d_arena, &s->d_roots, &s->d_ncomp, &s->d_stage,
+                      &s->d_stage_key, &s->d_stage_owner, &s->d_lines, &s->d_nlines, &s->d_stats};
     for (DevBuf* b : bufs) b->release();
     s->h_gray.release();
     s->h_out.release();
@@ -811,8 +1153,17 @@ static LsdBuffers lsd_buffers(LsdState& s) {
     B.deg = s.d_deg.as<float>();
     B.modgrad = s.d_mg.as<double>();
     B.defbits = s.d_def.as<uint32_t>();
-    B.reg = s.d_reg.as<uint32_t>();
-    B.tmp = s.d_tmp.as<uint32_t>();
+    const size_t npx = (size_t)s.d.W * s.d.H * s.d.n_frames;
+    uint32_t* ar = s.d_arena.as<uint32_t>();  // 6 work arenas
+    B.regA = ar; B.tmpA = ar + npx; B.lstA = ar + 2 * npx; B.regB = ar + 3 * npx; B.tmpB = ar + 4 * npx; B.lstB = ar + 5 * npx;
+    int* ro = s.d_roots.as<int>();            // 12 per-pixel int arrays (viol counts twice)
+    B.label = ro; B.csize = ro + npx; B.cminx = ro + 2 * npx; B.cmaxx = ro + 3 * npx; B.cmaxy = ro + 4 * npx; B.cflag = ro + 5 * npx;
+    B.cgrp = ro + 6 * npx; B.cmark = ro + 7 * npx; B.units = ro + 8 * npx; B.units2 = ro + 9 * npx; B.viol = ro + 10 * npx;
+    B.ncomp = s.d_ncomp.as<int>();
+    B.stage = s.d_stage.as<float4>();
+    B.stage_key = s.d_stage_key.as<int>();
+    B.stage_owner = s.d_stage_owner.as<int>();
+    B.stage_cap = s.stage_cap;
     B.lines = s.d_lines.as<float>();
     B.n_lines = s.d_nlines.as<int>();
     B.stats = s.d_stats.as<unsigned long long>();
@@ -862,7 +1213,8 @@ static int lsd_prepare(csb_context* c, int n_frames, int width, int height, cons
     C.length_thres = params->line_length_thres;
     C.filter = params->filter;
     C.max_lines = params->max_lines;
-    s.grow_smem = 96 * sizeof(double) + 2 * (size_t)d.H * d.WW * sizeof(uint32_t);
+    s.grow_smem = (size_t)LSD_WARPS * LSD_WARP_SMEM + 2 * (size_t)d.H * d.WW * sizeof(uint32_t);
+    s.stage_cap = std::max((d.W * d.H) / 4, params->max_lines);
     if (s.grow_smem > (size_t)c->max_smem_optin) {
         c->err = "csb_lsd: frame too large for the shared-memory used/defined bitmaps";
         return CSB_ERR_CAPACITY;
@@ -874,11 +1226,15 @@ static int lsd_prepare(csb_context* c, int n_frames, int width, int height, cons
     CSB_CUDA(c, s.d_deg.ensure(npx * 4));
     CSB_CUDA(c, s.d_mg.ensure(npx * 8));
     CSB_CUDA(c, s.d_def.ensure((size_t)d.H * d.WW * n_frames * 4));
-    CSB_CUDA(c, s.d_reg.ensure(npx * 4));
-    CSB_CUDA(c, s.d_tmp.ensure(npx * 4));
+    CSB_CUDA(c, s.d_arena.ensure(npx * 4 * 6));
+    CSB_CUDA(c, s.d_roots.ensure(npx * 4 * 12));
+    CSB_CUDA(c, s.d_ncomp.ensure((size_t)n_frames * 16));
+    CSB_CUDA(c, s.d_stage.ensure((size_t)n_frames * s.stage_cap * 16));
+    CSB_CUDA(c, s.d_stage_key.ensure((size_t)n_frames * s.stage_cap * 4));
+    CSB_CUDA(c, s.d_stage_owner.ensure((size_t)n_frames * s.stage_cap * 4));
     CSB_CUDA(c, s.d_lines.ensure((size_t)n_frames * params->max_lines * 16));
     CSB_CUDA(c, s.d_nlines.ensure((size_t)n_frames * 4));
-    CSB_CUDA(c, s.d_stats.ensure(64));
+    CSB_CUDA(c, s.d_stats.ensure(128));
     CSB_CUDA(c, cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.grow_smem));
     return CSB_OK;
 }
@@ -909,15 +1265,21 @@ int csb_lsd_run(csb_context* c, int timed) {
     const LsdDims& d = s.d;
     LsdBuffers B = lsd_buffers(s);
     cudaStream_t st = c->stream;
-    CSB_CUDA(c, cudaMemsetAsync(s.d_stats.p, 0, 64, st));
+    CSB_CUDA(c, cudaMemsetAsync(s.d_stats.p, 0, 128, st));
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[0], st));
     k_lsd_scale<<<dim3((d.W + SC_TW - 1) / SC_TW, (d.H + SC_TH - 1) / SC_TH, d.n_frames), SC_THREADS, 0, st>>>(B, d, s.C);
-    k_lsd_grad<<<dim3(d.WW, (d.H + 7) / 8, d.n_frames), dim3(32, 8), 0, st>>>(B, d, s.C);
+    const dim3 pg(d.WW, (d.H + 7) / 8, d.n_frames), pb(32, 8);
+    k_lsd_grad<<<pg, pb, 0, st>>>(B, d, s.C);
+    CSB_CUDA(c, cudaMemsetAsync(s.d_ncomp.p, 0, (size_t)d.n_frames * 16, st));
+    k_lsd_merge<<<pg, pb, 0, st>>>(B, d, s.params.unit_link_deg > 0 ? (float)s.params.unit_link_deg : LSD_LINK_DEG);
+    k_lsd_flatten<<<pg, pb, 0, st>>>(B, d);
+    k_lsd_contact<<<pg, pb, 0, st>>>(B, d);
+    k_lsd_units<<<pg, pb, 0, st>>>(B, d, s.C.min_reg_size);
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[1], st));
-    k_lsd_grow<<<d.n_frames, 32, s.grow_smem, st>>>(B, d, s.C);
+    k_lsd_grow<<<d.n_frames, LSD_WARPS * 32, s.grow_smem, st>>>(B, d, s.C);
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[2], st));
     CSB_CUDA(c, cudaGetLastError());
-    s.launches_last = 3;
+    s.launches_last = 7;
     s.timed_last = timed != 0;
     s.ran = true;
     return CSB_OK;
@@ -931,13 +1293,13 @@ int csb_lsd_download(csb_context* c, float* lines_out, int32_t* n_lines_out, csb
     LsdState& s = *c->lsd;
     CSB_CUDA(c, cudaSetDevice(c->device));
     const size_t lb = (size_t)s.d.n_frames * s.params.max_lines * 16, nb = (size_t)s.d.n_frames * 4;
-    CSB_CUDA(c, s.h_out.ensure(lb + nb + 64));
+    CSB_CUDA(c, s.h_out.ensure(lb + nb + 128));
     char* h = s.h_out.as<char>();
     CSB_CUDA(c, cudaMemcpyAsync(h, s.d_lines.p, lb, cudaMemcpyDeviceToHost, c->stream));
     CSB_CUDA(c, cudaMemcpyAsync(h + lb, s.d_nlines.p, nb, cudaMemcpyDeviceToHost, c->stream));
-    CSB_CUDA(c, cudaMemcpyAsync(h + lb + nb, s.d_stats.p, 64, cudaMemcpyDeviceToHost, c->stream));
+    CSB_CUDA(c, cudaMemcpyAsync(h + lb + nb, s.d_stats.p, 128, cudaMemcpyDeviceToHost, c->stream));
     CSB_CUDA(c, cudaStreamSynchronize(c->stream));
-    s.d2h_bytes = (int64_t)(lb + nb + 64);
+    s.d2h_bytes = (int64_t)(lb + nb + 128);
     const int32_t* nl = reinterpret_cast<const int32_t*>(h + lb);
     const unsigned long long* st = reinterpret_cast<const unsigned long long*>(h + lb + nb);
     bool overflow = false;
@@ -958,6 +1320,9 @@ int csb_lsd_download(csb_context* c, float* lines_out, int32_t* n_lines_out, csb
         stats->scaled_width = s.d.W;
         stats->scaled_height = s.d.H;
         stats->n_kernel_launches = s.launches_last;
+        for (int i = 0; i < 5; i++) stats->grow_cycles[i] = (int64_t)st[2 + i];
+        stats->n_merge_rounds = (int64_t)st[7];
+        stats->n_unit_conflicts = (int64_t)st[8];
         if (s.timed_last) {
             cudaEventElapsedTime(&stats->gpu_ms_maps, s.ev[0], s.ev[1]);
             cudaEventElapsedTime(&stats->gpu_ms_grow, s.ev[1], s.ev[2]);

@@ -242,17 +242,20 @@ typedef struct csb_lsd_params {
     float line_length_thres; /* line_lbd_detect::line_length_thres; both callers set 15 (main_obj.cpp:505, detect_lines.cpp:66) */
     int32_t filter;          /* 1: detect_filter_lines output; 0: every segment LineSegmentDetectorImpl::detect returns */
     int32_t max_lines;       /* capacity (rows) per frame of lines_out */
-    int32_t reserved;
+    int32_t unit_link_deg;   /* 0 = default (45).  Tuning/test knob of the work partition only: the result does not depend on it */
 } csb_lsd_params;
 
 typedef struct csb_lsd_stats {
     int64_t n_lines;        /* segments written over the whole batch */
-    int64_t n_regions;      /* seeds that started a region (region_grow calls from flsd) */
-    int64_t n_region_px;    /* pixels accepted by those calls and by the re-growing of refine() */
+    int64_t n_regions;      /* seeds that started a region (region_grow calls from flsd; units that cannot yield a segment are skipped) */
+    int64_t n_region_px;    /* pixels accepted by those calls and by the re-growing of refine(), redone units included */
     int64_t h2d_bytes, d2h_bytes;
     int32_t scaled_width, scaled_height;
     int32_t n_kernel_launches, reserved;
     float gpu_ms_maps, gpu_ms_grow; /* CUDA-event times of the last timed run: streaming kernels / region kernel */
+    int64_t grow_cycles[5];         /* SM cycles summed over warps: region_grow, region2rect, refine, rect_improve, whole seed loop */
+    int64_t n_merge_rounds;         /* frames x rounds in which interacting units had to be merged and redone (0 = first partition valid) */
+    int64_t n_unit_conflicts;       /* units that found a pixel of another unit aligned */
 } csb_lsd_stats;
 
 /* Host buffers in and out: gray = n_frames x height x width bytes; lines_out = n_frames x max_lines x 4 floats; n_lines_out[n_frames].

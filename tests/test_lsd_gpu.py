@@ -12,6 +12,7 @@ pytestmark = pytest.mark.gpu
 
 def _check(ctx, oracle, frames, **kw):
     lines, st = ctx.lsd_detect_batch(frames, **kw)
+    kw.pop("unit_link_deg", None)
     mode = 1 if kw.get("filter", True) else 0
     thr = kw.get("line_length_thres", 15.0)
     worst = 0.0
@@ -97,3 +98,15 @@ def test_class_mirror_and_rerun(ctx, csb, oracle):
     ctx.lsd_run(); l1, _ = ctx.lsd_download()
     ctx.lsd_run(); l2, _ = ctx.lsd_download()  # the used map is rebuilt on every run
     assert all(np.array_equal(x, y) for x, y in zip(l1, l2)) and all(np.array_equal(x, y) for x, y in zip(l1, a))
+
+
+@pytest.mark.parametrize("link_deg", [3, 8, 20])
+def test_unit_partition_does_not_change_the_result(ctx, csb, oracle, link_deg):
+    """The work partition (units = pixels linked by similar level-line angles) is validated at run time: units whose regions find a pixel
+    of another unit aligned are merged and redone.  A tiny link angle fragments every edge and forces many merge rounds (up to the
+    whole-frame fallback); the segments must not change."""
+    from cube_slam_wu_b200 import synth
+    frames = np.concatenate([synth.make_lsd_frames(2, 640, 480, seed=31), synth.make_lsd_frames(2, 640, 480, seed=32, texture=1.0, noise_sigma=6.0)])
+    lines, st, worst = _check(ctx, oracle, frames, unit_link_deg=link_deg)
+    assert st.n_merge_rounds > 0 and st.n_unit_conflicts > 0
+    print("link %d deg: %d merge rounds, %d conflicts, max diff %g" % (link_deg, st.n_merge_rounds, st.n_unit_conflicts, worst))
