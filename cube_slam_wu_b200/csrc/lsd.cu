@@ -429,6 +429,15 @@ __device__ __forceinline__ bool l_aligned_deg(float deg, double theta, double pr
     }
     return n_theta <= prec;
 }
+// The same decision as l_aligned_deg((deg), (double)reg_deg * DEG2RAD, prec), taken in float degrees when it is not within 1e-3 degrees
+// of a threshold (the FP64 expressions are accurate to 1e-13 degrees, the float difference to 4e-5).
+__device__ __forceinline__ bool l_aligned_fast(float deg, float reg_deg, float prec_deg, double prec) {
+    float dd = fabsf(reg_deg - deg);
+    const bool wrap = dd > 270.f;
+    const float d2 = wrap ? fabsf(dd - 360.f) : dd;
+    if (fabsf(d2 - prec_deg) > 1e-3f && fabsf(dd - 270.f) > 1e-3f) return d2 < prec_deg;
+    return l_aligned_deg(deg, (double)reg_deg * LSD_DEG2RAD, prec);
+}
 __device__ double l_log_gamma(double x) {
     if (x > 15.0) return 0.918938533204673 + (x - 0.5) * log(x) - x + 0.5 * x * log(x * sinh(1 / x) + 1 / (810.0 * pow(x, 6.0)));
     const double q[7] = {75122.6331530, 80916.6278952, 36308.2951477, 8687.24529705, 1168.92649479, 83.8676043424, 2.50662827511};
@@ -518,7 +527,7 @@ struct Grow {
         const bool cand_ = def##S && (frn_ || !(U[word##S] & bit##S));                                          \
         unsigned m_ = __ballot_sync(0xffffffffu, cand_);                                                        \
         while (m_) {                                                                                            \
-            const bool al_ = cand_ && l_aligned_deg(v##S.x, reg_angle, prec);                                   \
+            const bool al_ = cand_ && l_aligned_fast(v##S.x, reg_deg, prec_deg, prec);                          \
             const unsigned am_ = __ballot_sync(0xffffffffu, al_) & m_;                                          \
             if (!am_) break;                                                                                    \
             const int l_ = __ffs(am_) - 1;                                                                      \
@@ -533,7 +542,7 @@ struct Grow {
             }                                                                                                   \
             sumdx += __shfl_sync(0xffffffffu, v##S.y, l_);                                                      \
             sumdy += __shfl_sync(0xffffffffu, v##S.z, l_);                                                      \
-            reg_angle = (double)fast_atan2f(sumdy, sumdx) * LSD_DEG2RAD;                                        \
+            reg_deg = fast_atan2f(sumdy, sumdx);                                                                \
             ++n;                                                                                                \
             m_ &= ~((2u << l_) - 1u);                                                                           \
         }                                                                                                       \
@@ -542,7 +551,7 @@ struct Grow {
         if (foreign_root >= 0) return -1;                                                                       \
     }
 
-    __device__ __noinline__ int region_grow(int sx, int sy, double prec, double& reg_angle_out) {
+    __device__ __forceinline__ int region_grow(int sx, int sy, double prec, double& reg_angle_out) {
         if (lane == 0) {
             const uint32_t q = (uint32_t)sx | ((uint32_t)sy << 16);
             reg[0] = q;
@@ -550,9 +559,10 @@ struct Grow {
             atomicOr(&U[sy * WW + (sx >> 5)], 1u << (sx & 31));
         }
         int n = 1;
-        double reg_angle = (double)pix[(size_t)sy * W + sx].x * LSD_DEG2RAD;
+        float reg_deg = pix[(size_t)sy * W + sx].x;  // the region angle is always a fastAtan2 value: degrees in float, radians = deg * (pi / 180) in double
+        const float prec_deg = (float)(prec * (180.0 / LSD_PI));
         double s0, c0;
-        det_sincos(reg_angle, s0, c0);
+        det_sincos((double)reg_deg * LSD_DEG2RAD, s0, c0);
         float sumdx = (float)c0, sumdy = (float)s0;
         const int ox = lane % 3 - 1, oy = lane / 3 - 1;
         float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0;
@@ -572,14 +582,14 @@ struct Grow {
             if (i + 2 >= n) break;
             LSD_PROCESS(2)
         }
-        reg_angle_out = reg_angle;
+        reg_angle_out = (double)reg_deg * LSD_DEG2RAD;
         return n;
     }
 #undef LSD_ISSUE
 #undef LSD_PROCESS
 
     // lsd.cpp:690-746 + get_theta :748-784
-    __device__ __noinline__ void region2rect(int n, double reg_angle, double prec, double p, LRect& rec) {
+    __device__ __forceinline__ void region2rect(int n, double reg_angle, double prec, double p, LRect& rec) {
         double x = 0, y = 0, sum = 0;
         for (int base = 0; base < n; base += 32) {
             const int idx = base + lane, cnt = min(32, n - base);
@@ -662,7 +672,7 @@ struct Grow {
 
     // lsd.cpp:834-871.  The reference removes far points one by one with swap(reg[i], reg[size - 1]); the resulting order is: kept points
     // stay, holes among the first m = #kept slots (ascending) are filled by the kept points of slots >= m in descending slot order.
-    __device__ __noinline__ bool reduce_region_radius(int& n, double reg_angle, double prec, double p, LRect& rec, double density, double density_th) {
+    __device__ __forceinline__ bool reduce_region_radius(int& n, double reg_angle, double prec, double p, LRect& rec, double density, double density_th) {
         const uint32_t q0 = reg[0];
         const double xc = double(q0 & 0xffffu), yc = double(q0 >> 16);
         const double radSq1 = l_distSq(xc, yc, rec.x1, rec.y1), radSq2 = l_distSq(xc, yc, rec.x2, rec.y2);
@@ -719,7 +729,7 @@ struct Grow {
     }
 
     // lsd.cpp:786-832
-    __device__ __noinline__ bool refine(int& n, double reg_angle, double prec, double p, LRect& rec, double density_th) {
+    __device__ __forceinline__ bool refine(int& n, double reg_angle, double prec, double p, LRect& rec, double density_th) {
         double density = double(n) / (l_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
         if (density >= density_th) return true;
         const uint32_t q0 = reg[0];
@@ -764,7 +774,7 @@ struct Grow {
 
     // lsd.cpp:977-1098.  Integer-division slopes and the tailp->p.x comparisons are the reference's; since every step is an integer the
     // scan-line bounds of row y have a closed form, so rows can be counted in any order.
-    __device__ __noinline__ double rect_nfa(const LRect& rec) {
+    __device__ __forceinline__ double rect_nfa(const LRect& rec) {
         const double half_width = rec.width / 2.0;
         const double dyhw = rec.dy * half_width, dxhw = rec.dx * half_width;
         int ex[4], ey[4];
@@ -848,7 +858,7 @@ struct Grow {
     }
 
     // lsd.cpp:873-975
-    __device__ __noinline__ double rect_improve(LRect& rec) {
+    __device__ __forceinline__ double rect_improve(LRect& rec) {
         const double LOG_EPS = 0, delta = 0.5, delta_2 = delta / 2.0;
         double log_nfa = rect_nfa(rec);
         if (log_nfa > LOG_EPS) return log_nfa;
