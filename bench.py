@@ -39,6 +39,9 @@ FRAMES_PER_GPU = 64
 BOXES_PER_FRAME = 8
 ALGO_BYTES_PER_PROPOSAL = 550.0   # SURVEY.md 8d contract figure: 596 B (config 1) / 508 B (config 2), 0.55 KB mean
 ALGO_BYTES_PER_EDGE = 1856.0      # EdgeSE3Cuboid, fused (Jacobian not materialised)
+LSD_FRAMES, LSD_W, LSD_H = 256, 640, 480  # BASELINE config #3
+# streaming stages of the line detector: 1 B read per source pixel, then the reference's two FP64 maps (gradient norm + level-line angle) per scaled pixel
+LSD_ALGO_BYTES_PER_FRAME = LSD_W * LSD_H + 16.0 * round(LSD_W * 0.8) * round(LSD_H * 0.8)
 
 
 def workload_config(n_gpus):
@@ -394,6 +397,46 @@ def run_ours(args, rank, local_rank, world):
         except Exception as e:  # the headline line must still print
             out["ba"] = {"error": str(e)}
 
+        # ---- line detector (BASELINE config #3): 256 synthetic 640x480 frames, LSD branch of line_lbd_detect::detect_filter_lines
+        lsd_frames = None
+        try:
+            base = synth.make_lsd_frames(32, LSD_W, LSD_H, seed=20260927)
+            lsd_frames = np.ascontiguousarray(np.concatenate([base] * (LSD_FRAMES // 32)))
+            with torch.cuda.stream(stream):
+                ctx.lsd_upload(lsd_frames)
+                for _ in range(2):
+                    ctx.lsd_run()
+                torch.cuda.synchronize()
+                reps, maps_ms, grow_ms = 5, [], []
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                tot_ms = 0.0
+                for _ in range(reps):
+                    flush.zero_()
+                    a.record(stream)
+                    ctx.lsd_run(timed=True)
+                    b.record(stream)
+                    _, lst = ctx.lsd_download()
+                    tot_ms += a.elapsed_time(b)
+                    maps_ms.append(lst.gpu_ms_maps); grow_ms.append(lst.gpu_ms_grow)
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    _, lst = ctx.lsd_detect_batch(lsd_frames)
+                call_ms = 1e3 * (time.perf_counter() - t0) / 3
+            m_ms = float(np.mean(maps_ms))
+            lsd_ach = LSD_ALGO_BYTES_PER_FRAME * LSD_FRAMES / (m_ms * 1e-3) / 1e9
+            out["lsd"] = {"metric": "lsd_frames_per_sec", "value": LSD_FRAMES / (tot_ms / reps * 1e-3), "unit": "frames/s",
+                          "config": "config#3: %d synthetic %dx%d frames (32 distinct, tiled), LSD_REFINE_ADV, detect_filter_lines with line_length_thres 15; resident, L2 flushed between runs" % (LSD_FRAMES, LSD_W, LSD_H),
+                          "ms_per_batch": tot_ms / reps, "kernel_ms": {"maps (scale, gradient, labelling)": m_ms, "grow (regions, rectangles, NFA)": float(np.mean(grow_ms))},
+                          "segments": int(lst.n_lines), "regions": int(lst.n_regions), "region_px": int(lst.n_region_px), "merge_rounds": int(lst.n_merge_rounds),
+                          "e2e": {"value": LSD_FRAMES / (call_ms * 1e-3), "unit": "frames/s", "ms_per_call": call_ms, "h2d_bytes_per_step": int(lst.h2d_bytes),
+                                  "d2h_bytes_per_step": int(lst.d2h_bytes), "mode": "one blocking csb_lsd_detect_batch() with host buffers"},
+                          "roofline": {"kernel": "streaming stages (k_lsd_scale .. k_lsd_units)", "bound": "hbm", "achieved": lsd_ach, "peak": peak, "unit": "GB/s",
+                                       "frac": lsd_ach / peak, "traffic": None, "algorithmic_bytes_per_launch": LSD_ALGO_BYTES_PER_FRAME * LSD_FRAMES,
+                                       "note": "the region kernel that follows is sequential per work unit (latency bound), see DESIGN.md 3c"},
+                          "gpu_launches": int(lst.n_kernel_launches)}
+        except Exception as e:
+            out["lsd"] = {"error": str(e)}
+
         # ---- CPU baseline: oracle port, one thread (the reference is single-threaded), bounded sample
         if world == 1:
             try:
@@ -418,6 +461,12 @@ def run_ours(args, rank, local_rank, world):
                         _, _, oit, ochi = O.ba_optimize(g["cams7"], g["cam_fixed"], g["cubes10"], g["cube_fixed"], E, 5)
                         out["ba"]["optimize"]["cpu_baseline"] = {"ms": 1e3 * (time.perf_counter() - t0), "iterations": int(oit), "chi2": float(ochi), "cores": 1,
                                                                  "kind": "port", "sample": "the same 5 LM iterations, dense LDL^T of the full system"}
+                if lsd_frames is not None and "value" in out.get("lsd", {}):
+                    t0 = time.perf_counter(); r = 0
+                    while time.perf_counter() - t0 < 3.0:
+                        O.lsd_detect(lsd_frames[r % 32]); r += 1
+                    out["lsd"]["cpu_baseline"] = {"value": r / (time.perf_counter() - t0), "unit": "frames/s", "cores": 1, "kind": "port",
+                                                  "sample": "%d frames of the same batch, single thread like the reference" % r}
             except Exception as e:
                 out["cpu_baseline"] = {"error": str(e)}
         print(json.dumps(out), flush=True)  # flush: under torchrun stdout is a block-buffered pipe/file

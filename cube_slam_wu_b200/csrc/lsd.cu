@@ -502,55 +502,11 @@ struct Grow {
     }
 
     // lsd.cpp:637-688.  Returns the region size (the region is reg[0 .. size)), or -1 if a pixel of another unit was found aligned.
-    // The queue head is read from a shared-memory ring (the last LSD_RING entries; older ones from global memory), and the neighbour
-    // records of queue entries i, i+1, i+2 are loaded ahead of time into three register sets (software pipeline, unrolled by three so
-    // that consuming one set never waits for the loads of the others).  Every defined neighbour is loaded: its record carries the
-    // label that tells own pixels (candidates while unused) from foreign ones (tested whatever their used state: finding one aligned
-    // invalidates the unit).
-    __device__ __forceinline__ uint32_t queue_at(int j, int n) const { return (n - j <= LSD_RING) ? ring[j & (LSD_RING - 1)] : reg[j]; }
-
-#define LSD_ISSUE(S, J)                                                                                         \
-    if (!have##S && (J) < n) {                                                                                  \
-        const uint32_t q_ = queue_at((J), n);                                                                   \
-        const int xx_ = (int)(q_ & 0xffffu) + ox, yy_ = (int)(q_ >> 16) + oy;                                  \
-        const bool inb_ = lane < 9 && xx_ >= 0 && xx_ < W && yy_ >= 0 && yy_ < H;                              \
-        word##S = inb_ ? yy_ * WW + (xx_ >> 5) : 0;                                                             \
-        bit##S = 1u << (xx_ & 31);                                                                              \
-        pos##S = (uint32_t)xx_ | ((uint32_t)yy_ << 16);                                                         \
-        def##S = inb_ && (D[word##S] & bit##S);                                                                 \
-        if (def##S) v##S = pix[(size_t)yy_ * W + xx_];                                                          \
-        have##S = true;                                                                                         \
-    }
-#define LSD_PROCESS(S)                                                                                          \
-    {                                                                                                           \
-        const bool frn_ = def##S && is_foreign(__float_as_int(v##S.w));                                         \
-        const bool cand_ = def##S && (frn_ || !(U[word##S] & bit##S));                                          \
-        unsigned m_ = __ballot_sync(0xffffffffu, cand_);                                                        \
-        while (m_) {                                                                                            \
-            const bool al_ = cand_ && l_aligned_fast(v##S.x, reg_deg, prec_deg, prec);                          \
-            const unsigned am_ = __ballot_sync(0xffffffffu, al_) & m_;                                          \
-            if (!am_) break;                                                                                    \
-            const int l_ = __ffs(am_) - 1;                                                                      \
-            if (__shfl_sync(0xffffffffu, (int)frn_, l_)) {                                                      \
-                foreign_root = __shfl_sync(0xffffffffu, __float_as_int(v##S.w), l_);                            \
-                break;                                                                                          \
-            }                                                                                                   \
-            if (lane == l_) {                                                                                   \
-                atomicOr(&U[word##S], bit##S);                                                                  \
-                reg[n] = pos##S;                                                                                \
-                ring[n & (LSD_RING - 1)] = pos##S;                                                              \
-            }                                                                                                   \
-            sumdx += __shfl_sync(0xffffffffu, v##S.y, l_);                                                      \
-            sumdy += __shfl_sync(0xffffffffu, v##S.z, l_);                                                      \
-            reg_deg = fast_atan2f(sumdy, sumdx);                                                                \
-            ++n;                                                                                                \
-            m_ &= ~((2u << l_) - 1u);                                                                           \
-        }                                                                                                       \
-        have##S = false;                                                                                        \
-        __syncwarp();                                                                                           \
-        if (foreign_root >= 0) return -1;                                                                       \
-    }
-
+    // The queue head is read from a shared-memory ring (the last LSD_RING entries; older ones from global memory).  Lanes 0..8 hold the
+    // 3x3 neighbourhood of the entry being expanded; every defined neighbour is loaded: its record carries the label that tells own
+    // pixels (candidates while unused) from foreign ones (tested whatever their used state: finding one aligned invalidates the unit).
+    // The accept loop replays the reference's order: the first aligned lane is accepted, the running angle is updated, the lanes after
+    // it are tested again with the new angle.
     __device__ __forceinline__ int region_grow(int sx, int sy, double prec, double& reg_angle_out) {
         if (lane == 0) {
             const uint32_t q = (uint32_t)sx | ((uint32_t)sy << 16);
@@ -565,28 +521,46 @@ struct Grow {
         det_sincos((double)reg_deg * LSD_DEG2RAD, s0, c0);
         float sumdx = (float)c0, sumdy = (float)s0;
         const int ox = lane % 3 - 1, oy = lane / 3 - 1;
-        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0;
-        bool have0 = false, have1 = false, have2 = false, def0 = false, def1 = false, def2 = false;
-        int word0 = 0, word1 = 0, word2 = 0;
-        unsigned bit0 = 0, bit1 = 0, bit2 = 0;
-        uint32_t pos0 = 0, pos1 = 0, pos2 = 0;
         __syncwarp();
-        for (int i = 0;; i += 3) {
-            LSD_ISSUE(0, i) LSD_ISSUE(1, i + 1) LSD_ISSUE(2, i + 2)
-            if (i >= n) break;
-            LSD_PROCESS(0)
-            LSD_ISSUE(1, i + 1) LSD_ISSUE(2, i + 2) LSD_ISSUE(0, i + 3)
-            if (i + 1 >= n) break;
-            LSD_PROCESS(1)
-            LSD_ISSUE(2, i + 2) LSD_ISSUE(0, i + 3) LSD_ISSUE(1, i + 4)
-            if (i + 2 >= n) break;
-            LSD_PROCESS(2)
+        for (int i = 0; i < n; ++i) {
+            const uint32_t q = (n - i <= LSD_RING) ? ring[i & (LSD_RING - 1)] : reg[i];
+            const int xx = (int)(q & 0xffffu) + ox, yy = (int)(q >> 16) + oy;
+            const bool inb = lane < 9 && xx >= 0 && xx < W && yy >= 0 && yy < H;
+            const int word = inb ? yy * WW + (xx >> 5) : 0;
+            const unsigned bit = 1u << (xx & 31);
+            const bool def = inb && (D[word] & bit);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (def) v = pix[(size_t)yy * W + xx];
+            const bool frn = def && is_foreign(__float_as_int(v.w));
+            const bool cand = def && (frn || !(U[word] & bit));
+            unsigned m = __ballot_sync(0xffffffffu, cand);
+            while (m) {
+                const bool al = cand && l_aligned_fast(v.x, reg_deg, prec_deg, prec);
+                const unsigned am = __ballot_sync(0xffffffffu, al) & m;
+                if (!am) break;
+                const int l = __ffs(am) - 1;
+                if (__shfl_sync(0xffffffffu, (int)frn, l)) {
+                    foreign_root = __shfl_sync(0xffffffffu, __float_as_int(v.w), l);
+                    break;
+                }
+                if (lane == l) {
+                    const uint32_t pos = (uint32_t)xx | ((uint32_t)yy << 16);
+                    atomicOr(&U[word], bit);
+                    reg[n] = pos;
+                    ring[n & (LSD_RING - 1)] = pos;
+                }
+                sumdx += __shfl_sync(0xffffffffu, v.y, l);
+                sumdy += __shfl_sync(0xffffffffu, v.z, l);
+                reg_deg = fast_atan2f(sumdy, sumdx);
+                ++n;
+                m &= ~((2u << l) - 1u);
+            }
+            __syncwarp();
+            if (foreign_root >= 0) return -1;
         }
         reg_angle_out = (double)reg_deg * LSD_DEG2RAD;
         return n;
     }
-#undef LSD_ISSUE
-#undef LSD_PROCESS
 
     // lsd.cpp:690-746 + get_theta :748-784
     __device__ __forceinline__ void region2rect(int n, double reg_angle, double prec, double p, LRect& rec) {
@@ -670,68 +644,56 @@ struct Grow {
         if (rec.width < 1.0) rec.width = 1.0;
     }
 
-    // lsd.cpp:834-871.  The reference removes far points one by one with swap(reg[i], reg[size - 1]); the resulting order is: kept points
-    // stay, holes among the first m = #kept slots (ascending) are filled by the kept points of slots >= m in descending slot order.
-    __device__ __forceinline__ bool reduce_region_radius(int& n, double reg_angle, double prec, double p, LRect& rec, double density, double density_th) {
-        const uint32_t q0 = reg[0];
-        const double xc = double(q0 & 0xffffu), yc = double(q0 >> 16);
-        const double radSq1 = l_distSq(xc, yc, rec.x1, rec.y1), radSq2 = l_distSq(xc, yc, rec.x2, rec.y2);
-        double radSq = radSq1 > radSq2 ? radSq1 : radSq2;
-        while (density < density_th) {
-            radSq *= 0.75 * 0.75;
-            int m = 0;
-            for (int base = 0; base < n; base += 32) {
-                const int idx = base + lane;
-                bool keep = false;
-                if (idx < n) {
-                    const uint32_t q = reg[idx];
-                    const int px = q & 0xffffu, py = q >> 16;
-                    keep = !(l_distSq(xc, yc, double(px), double(py)) > radSq);
-                    if (!keep) clear_used(px, py);
-                }
-                m += __popc(__ballot_sync(0xffffffffu, keep));
+    // One pass of the loop of reduce_region_radius (lsd.cpp:845-868): drop the points farther than sqrt(radSq) from the seed.  The
+    // reference removes them one by one with swap(reg[i], reg[size - 1]); the resulting order is: kept points stay, holes among the
+    // first m = #kept slots (ascending) are filled by the kept points of slots >= m in descending slot order.  Returns the new size.
+    __device__ __forceinline__ int reduce_step(int n, double xc, double yc, double radSq) {
+        int m = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int idx = base + lane;
+            bool keep = false;
+            if (idx < n) {
+                const uint32_t q = reg[idx];
+                const int px = q & 0xffffu, py = q >> 16;
+                keep = !(l_distSq(xc, yc, double(px), double(py)) > radSq);
+                if (!keep) clear_used(px, py);
             }
-            if (m != n) {
-                int r = 0;
-                for (int top = n - 1; top >= m; top -= 32) {  // kept points of slots >= m, descending
-                    const int pos = top - lane;
-                    bool keep = false;
-                    uint32_t q = 0;
-                    if (pos >= m) {
-                        q = reg[pos];
-                        keep = !(l_distSq(xc, yc, double(q & 0xffffu), double(q >> 16)) > radSq);
-                    }
-                    const unsigned b = __ballot_sync(0xffffffffu, keep);
-                    if (keep) tmp[r + __popc(b & ((1u << lane) - 1u))] = q;
-                    r += __popc(b);
-                }
-                __syncwarp();
-                r = 0;
-                for (int base = 0; base < m; base += 32) {  // holes of slots < m, ascending
-                    const int idx = base + lane;
-                    bool far = false;
-                    if (idx < m) {
-                        const uint32_t q = reg[idx];
-                        far = l_distSq(xc, yc, double(q & 0xffffu), double(q >> 16)) > radSq;
-                    }
-                    const unsigned b = __ballot_sync(0xffffffffu, far);
-                    if (far) reg[idx] = tmp[r + __popc(b & ((1u << lane) - 1u))];
-                    r += __popc(b);
-                }
-                __syncwarp();
-            }
-            n = m;
-            if (n < 2) return false;
-            region2rect(n, reg_angle, prec, p, rec);
-            density = double(n) / (l_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+            m += __popc(__ballot_sync(0xffffffffu, keep));
         }
-        return true;
+        if (m != n) {
+            int r = 0;
+            for (int top = n - 1; top >= m; top -= 32) {  // kept points of slots >= m, descending
+                const int pos = top - lane;
+                bool keep = false;
+                uint32_t q = 0;
+                if (pos >= m) {
+                    q = reg[pos];
+                    keep = !(l_distSq(xc, yc, double(q & 0xffffu), double(q >> 16)) > radSq);
+                }
+                const unsigned b = __ballot_sync(0xffffffffu, keep);
+                if (keep) tmp[r + __popc(b & ((1u << lane) - 1u))] = q;
+                r += __popc(b);
+            }
+            __syncwarp();
+            r = 0;
+            for (int base = 0; base < m; base += 32) {  // holes of slots < m, ascending
+                const int idx = base + lane;
+                bool far = false;
+                if (idx < m) {
+                    const uint32_t q = reg[idx];
+                    far = l_distSq(xc, yc, double(q & 0xffffu), double(q >> 16)) > radSq;
+                }
+                const unsigned b = __ballot_sync(0xffffffffu, far);
+                if (far) reg[idx] = tmp[r + __popc(b & ((1u << lane) - 1u))];
+                r += __popc(b);
+            }
+            __syncwarp();
+        }
+        return m;
     }
 
-    // lsd.cpp:786-832
-    __device__ __forceinline__ bool refine(int& n, double reg_angle, double prec, double p, LRect& rec, double density_th) {
-        double density = double(n) / (l_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
-        if (density >= density_th) return true;
+    // First half of refine() (lsd.cpp:794-813): release the region and derive the tighter tolerance tau from the angle spread near the seed.
+    __device__ __forceinline__ double tau_step(int n, double width) {
         const uint32_t q0 = reg[0];
         const int x0 = q0 & 0xffffu, y0 = q0 >> 16;
         const double xc = double(x0), yc = double(y0);
@@ -745,7 +707,7 @@ struct Grow {
                 const uint32_t q = reg[idx];
                 const int px = q & 0xffffu, py = q >> 16;
                 clear_used(px, py);
-                if (l_dist(xc, yc, double(px), double(py)) < rec.width) {
+                if (l_dist(xc, yc, double(px), double(py)) < width) {
                     near = true;
                     sc[lane] = l_angle_diff_signed((double)pix[(size_t)py * W + px].x * LSD_DEG2RAD, ang_c);
                 }
@@ -762,14 +724,7 @@ struct Grow {
             __syncwarp();
         }
         const double mean_angle = sum / double(cnt);
-        const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / double(cnt) + mean_angle * mean_angle);
-        n = region_grow(x0, y0, tau, reg_angle);
-        if (n < 2) return false;  // also the foreign-pixel exit (n = -1; the caller checks foreign_root)
-        n_px += n;
-        region2rect(n, reg_angle, prec, p, rec);
-        density = double(n) / (l_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
-        if (density < density_th) return reduce_region_radius(n, reg_angle, prec, p, rec, density, density_th);
-        return true;
+        return 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / double(cnt) + mean_angle * mean_angle);
     }
 
     // lsd.cpp:977-1098.  Integer-division slopes and the tailp->p.x comparisons are the reference's; since every step is an integer the
@@ -857,42 +812,39 @@ struct Grow {
         return l_nfa(total, alg, rec.p, LOG_NT);
     }
 
-    // lsd.cpp:873-975
+    // lsd.cpp:873-975 as one loop (a single rect_nfa call site keeps the code small): trial 0 is the rectangle itself, then five
+    // stages of five trials each -- finer precision, narrower, one side in, the other side in, finer precision again.
     __device__ __forceinline__ double rect_improve(LRect& rec) {
         const double LOG_EPS = 0, delta = 0.5, delta_2 = delta / 2.0;
-        double log_nfa = rect_nfa(rec);
-        if (log_nfa > LOG_EPS) return log_nfa;
+        double log_nfa = -DBL_MAX;
         LRect r = rec;
-        for (int n = 0; n < 5; ++n) {
-            r.p /= 2;
-            r.prec = r.p * LSD_PI;
-            const double v = rect_nfa(r);
-            if (v > log_nfa) { log_nfa = v; rec = r; }
-        }
-        if (log_nfa > LOG_EPS) return log_nfa;
-        for (int pass = 0; pass < 3; pass++) {  // reduce width; reduce one side; reduce the other side
-            r = rec;
-            for (int n = 0; n < 5; ++n)
-                if ((r.width - delta) >= 0.5) {
-                    if (pass == 1) {
-                        r.x1 += -r.dy * delta_2; r.y1 += r.dx * delta_2; r.x2 += -r.dy * delta_2; r.y2 += r.dx * delta_2;
-                    } else if (pass == 2) {
-                        r.x1 -= -r.dy * delta_2; r.y1 -= r.dx * delta_2; r.x2 -= -r.dy * delta_2; r.y2 -= r.dx * delta_2;
-                    }
-                    r.width -= delta;
-                    const double v = rect_nfa(r);
-                    if (v > log_nfa) { rec = r; log_nfa = v; }
-                }
-            if (log_nfa > LOG_EPS) return log_nfa;
-        }
-        r = rec;
-        for (int n = 0; n < 5; ++n)
-            if ((r.width - delta) >= 0.5) {
+        for (int t = 0; t <= 25; ++t) {
+            const int stage = t == 0 ? -1 : (t - 1) / 5;
+            if (t > 0 && (t - 1) % 5 == 0) {  // a new stage starts from the best rectangle so far, unless it is already meaningful
+                if (log_nfa > LOG_EPS) return log_nfa;
+                r = rec;
+            }
+            if (stage == 0) {
                 r.p /= 2;
                 r.prec = r.p * LSD_PI;
-                const double v = rect_nfa(r);
-                if (v > log_nfa) { rec = r; log_nfa = v; }
+            } else if (stage > 0) {
+                if (!((r.width - delta) >= 0.5)) continue;
+                if (stage == 2) {
+                    r.x1 += -r.dy * delta_2; r.y1 += r.dx * delta_2; r.x2 += -r.dy * delta_2; r.y2 += r.dx * delta_2;
+                } else if (stage == 3) {
+                    r.x1 -= -r.dy * delta_2; r.y1 -= r.dx * delta_2; r.x2 -= -r.dy * delta_2; r.y2 -= r.dx * delta_2;
+                }
+                if (stage == 4) {
+                    r.p /= 2;
+                    r.prec = r.p * LSD_PI;
+                } else {
+                    r.width -= delta;
+                }
             }
+            const double v = rect_nfa(r);
+            if (t == 0) log_nfa = v;
+            else if (v > log_nfa) { log_nfa = v; rec = r; }
+        }
         return log_nfa;
     }
 };
@@ -993,26 +945,53 @@ __global__ void __launch_bounds__(LSD_WARPS * 32, 2) k_lsd_grow(LsdBuffers B, Ls
                     const int l = __ffs(m) - 1;
                     todo = ~((2u << l) - 1u);
                     const int sx = __shfl_sync(0xffffffffu, qx, l), sy = __shfl_sync(0xffffffffu, qy, l);
-                    // ---- one seed (lsd.cpp:478-534)
-                    double reg_angle;
-                    long long t0 = clock64();
-                    int n = G.region_grow(sx, sy, C.prec, reg_angle);
-                    long long t1 = clock64();
-                    cyc[0] += t1 - t0;
-                    if (n < 0) break;
-                    G.n_regions++;
-                    G.n_px += n;
-                    if (n < C.min_reg_size) continue;
+                    // ---- one seed (lsd.cpp:478-534 with refine :786-832 and reduce_region_radius :834-871 unrolled into one loop, so
+                    //      that region_grow and region2rect have a single call site each)
                     LRect rec;
-                    G.region2rect(n, reg_angle, C.prec, C.p, rec);
+                    double reg_angle = 0, tol = C.prec, radSq = 0, xc = 0, yc = 0;
+                    int n = 0, attempt = 0;
+                    bool reducing = false, good = false;
+                    long long t0 = clock64();
+                    while (true) {
+                        if (!reducing) {
+                            n = G.region_grow(sx, sy, tol, reg_angle);
+                            const long long t1 = clock64();
+                            cyc[attempt == 0 ? 0 : 2] += t1 - t0;
+                            t0 = t1;
+                            if (n < 0) break;  // a foreign pixel: the unit ends here
+                            if (attempt == 0) G.n_regions++;
+                            G.n_px += n;
+                            if (n < (attempt == 0 ? C.min_reg_size : 2)) break;
+                        } else {
+                            radSq *= 0.75 * 0.75;
+                            n = G.reduce_step(n, xc, yc, radSq);
+                            if (n < 2) break;
+                        }
+                        G.region2rect(n, reg_angle, C.prec, C.p, rec);
+                        const double density = double(n) / (l_dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+                        long long t1 = clock64();
+                        cyc[attempt == 0 ? 1 : 2] += t1 - t0;
+                        t0 = t1;
+                        if (density >= 0.7) { good = true; break; }
+                        if (attempt == 0) {  // refine(): try a tighter angle tolerance first
+                            tol = G.tau_step(n, rec.width);
+                            attempt = 1;
+                        } else if (!reducing) {  // then shrink the region around the seed
+                            const uint32_t q0 = G.reg[0];
+                            xc = double(q0 & 0xffffu); yc = double(q0 >> 16);
+                            const double radSq1 = l_distSq(xc, yc, rec.x1, rec.y1), radSq2 = l_distSq(xc, yc, rec.x2, rec.y2);
+                            radSq = radSq1 > radSq2 ? radSq1 : radSq2;
+                            reducing = true;
+                        }
+                        t1 = clock64();
+                        cyc[2] += t1 - t0;
+                        t0 = t1;
+                    }
+                    if (n < 0) break;
+                    if (!good) continue;
                     t0 = clock64();
-                    cyc[1] += t0 - t1;
-                    const bool ok = G.refine(n, reg_angle, C.prec, C.p, rec, 0.7);
-                    t1 = clock64();
-                    cyc[2] += t1 - t0;
-                    if (!ok) continue;  // (or a foreign pixel: the loop condition ends the unit)
                     const double log_nfa = G.rect_improve(rec);
-                    cyc[3] += clock64() - t1;
+                    cyc[3] += clock64() - t0;
                     if (log_nfa <= 0) continue;
                     rec.x1 += 0.5; rec.y1 += 0.5; rec.x2 += 0.5; rec.y2 += 0.5;
                     rec.x1 /= LSD_SCALE; rec.y1 /= LSD_SCALE; rec.x2 /= LSD_SCALE; rec.y2 /= LSD_SCALE;
