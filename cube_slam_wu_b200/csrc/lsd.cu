@@ -49,7 +49,6 @@ constexpr int LSD_RING = 512;
 struct LsdDims {
     int w, h;     // source frame
     int W, H;     // scaled frame
-    int WW;       // bitmap words per scaled row
     int n_frames;
 };
 
@@ -67,10 +66,9 @@ struct LsdConst {
 struct LsdBuffers {
     const uint8_t* gray;
     double* scaled;
-    float4* pix;       // {deg, cosf, sinf, unit label as int bits}
+    float4* pix;       // {deg, cosf, sinf, (unit label << 9 | defined-neighbour mask) as int bits}; mask bit k <-> neighbour (k / 3 - 1, k % 3 - 1)
     float* deg;        // compact copy of pix.x for the NFA counts and the labelling
     double* modgrad;
-    uint32_t* defbits;
     // work arenas, W*H entries per frame each.  Arena A serves the units of the first round, arena B the merged units of later rounds.
     uint32_t *regA, *tmpA, *lstA, *regB, *tmpB, *lstB;  // region list (x | y << 16), scratch of reduce_region_radius, a unit's pixels in raster order
     int* label;        // unit label of every pixel: root = smallest pixel index of its unit; -1 = undefined
@@ -274,8 +272,6 @@ __global__ void __launch_bounds__(256) k_lsd_grad(LsdBuffers B, LsdDims d, LsdCo
             B.cgrp[pi] = y * d.W + x;
         }
     }
-    const unsigned bits = __ballot_sync(0xffffffffu, def);
-    if (threadIdx.x == 0 && y < d.H) B.defbits[(size_t)f * d.H * d.WW + (size_t)y * d.WW + blockIdx.x] = bits;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------
@@ -348,7 +344,12 @@ __global__ void __launch_bounds__(256) k_lsd_flatten(LsdBuffers B, LsdDims d) {
         if (L[p] >= 0) {
             r = ccl_find(L, p);
             L[p] = r;
-            B.pix[fo + p].w = __int_as_float(r);
+            unsigned mask = 0;  // defined 8-neighbours (a negative label never turns non-negative or back while labels are flattened)
+            for (int k = 0; k < 9; k++) {
+                const int xx = x + k % 3 - 1, yy = y + k / 3 - 1;
+                if (k != 4 && xx >= 0 && xx < d.W && yy >= 0 && yy < d.H && L[yy * d.W + xx] >= 0) mask |= 1u << k;
+            }
+            B.pix[fo + p].w = __uint_as_float(((unsigned)r << 9) | mask);
         }
     }
     const unsigned act = __ballot_sync(0xffffffffu, r >= 0);
@@ -476,25 +477,32 @@ __device__ __noinline__ double l_nfa(int n, int k, double p, double LOG_NT) {
     return -log10(bin_tail) - LOG_NT;
 }
 
+// explicit shared-window accesses (generic pointers into dynamic shared memory cost a window-base computation per access)
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void atoms_or(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void atoms_and(uint32_t a, uint32_t v) { asm volatile("red.shared.and.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 struct Grow {
     const float4* pix;
     const float* deg;
     const double* mg;
     const int* cgrp;    // union-find parents over unit roots (merged units)
-    uint32_t* reg;
+    uint32_t* reg;      // region list: pixel indices (y * W + x)
     uint32_t* tmp;
-    uint32_t* U;        // shared: used bitmap
-    const uint32_t* D;  // shared: defined bitmap
+    uint32_t U;         // shared address of the used bitmap: bit i <-> pixel index i
+    uint32_t ring;      // shared address of the last LSD_RING queue entries (pixel index | defined-neighbour mask << 23)
     double* sc;         // shared: 3 x 32 doubles
-    uint32_t* ring;     // shared: the last LSD_RING queue entries of the region being grown
-    int W, H, WW, lane;
+    int W, H, lane;
     int leader;         // root of the unit being processed
     int mode;           // 0: first-round unit (foreign <=> label != leader); 1: merged unit (find(label) != leader); 2: whole frame (nothing is foreign)
     int foreign_root;   // set when a region found a pixel of another unit aligned: the unit must be merged with that one and redone
     double LOG_NT;
     unsigned long long n_regions, n_px;
 
-    __device__ __forceinline__ void clear_used(int px, int py) { atomicAnd(&U[py * WW + (px >> 5)], ~(1u << (px & 31))); }
+    __device__ __forceinline__ bool used(int idx) const { return (lds32(U + 4u * (unsigned)(idx >> 5)) >> (idx & 31)) & 1u; }
+    __device__ __forceinline__ void set_used(int idx) const { atoms_or(U + 4u * (unsigned)(idx >> 5), 1u << (idx & 31)); }
+    __device__ __forceinline__ void clear_used(int idx) const { atoms_and(U + 4u * (unsigned)(idx >> 5), ~(1u << (idx & 31))); }
     __device__ __forceinline__ bool is_foreign(int lbl) const {
         if (mode == 0) return lbl != leader;
         if (mode == 1) return lbl != leader && ccl_find(cgrp, lbl) != leader;
@@ -502,37 +510,42 @@ struct Grow {
     }
 
     // lsd.cpp:637-688.  Returns the region size (the region is reg[0 .. size)), or -1 if a pixel of another unit was found aligned.
-    // The queue head is read from a shared-memory ring (the last LSD_RING entries; older ones from global memory).  Lanes 0..8 hold the
-    // 3x3 neighbourhood of the entry being expanded; every defined neighbour is loaded: its record carries the label that tells own
-    // pixels (candidates while unused) from foreign ones (tested whatever their used state: finding one aligned invalidates the unit).
-    // The accept loop replays the reference's order: the first aligned lane is accepted, the running angle is updated, the lanes after
-    // it are tested again with the new angle.
-    __device__ __forceinline__ int region_grow(int sx, int sy, double prec, double& reg_angle_out) {
+    // A queue entry is a pixel index plus the mask of its defined 8-neighbours (precomputed per pixel, so the expansion needs neither
+    // bounds tests nor a "defined" lookup); the queue head is read from a shared-memory ring (the last LSD_RING entries; older ones are
+    // rebuilt from the region list).  Lanes 0..8 hold the 3x3 neighbourhood of the entry being expanded; every defined neighbour is
+    // loaded: its record carries the label that tells own pixels (candidates while unused) from foreign ones (tested whatever their used
+    // state: finding one aligned invalidates the unit).  The accept loop replays the reference's order: the first aligned lane is
+    // accepted, the running angle is updated, the lanes after it are tested again with the new angle.
+    __device__ __forceinline__ int region_grow(int seed, double prec, double& reg_angle_out) {
+        const float4 vs = pix[seed];
         if (lane == 0) {
-            const uint32_t q = (uint32_t)sx | ((uint32_t)sy << 16);
-            reg[0] = q;
-            ring[0] = q;
-            atomicOr(&U[sy * WW + (sx >> 5)], 1u << (sx & 31));
+            reg[0] = (uint32_t)seed;
+            sts32(ring, (uint32_t)seed | (__float_as_uint(vs.w) << 23));
+            set_used(seed);
         }
         int n = 1;
-        float reg_deg = pix[(size_t)sy * W + sx].x;  // the region angle is always a fastAtan2 value: degrees in float, radians = deg * (pi / 180) in double
+        float reg_deg = vs.x;  // the region angle is always a fastAtan2 value: degrees in float, radians = deg * (pi / 180) in double
         const float prec_deg = (float)(prec * (180.0 / LSD_PI));
         double s0, c0;
         det_sincos((double)reg_deg * LSD_DEG2RAD, s0, c0);
         float sumdx = (float)c0, sumdy = (float)s0;
-        const int ox = lane % 3 - 1, oy = lane / 3 - 1;
+        const int off = (lane / 3 - 1) * W + (lane % 3 - 1);
+        const uint32_t lanebit = lane < 9 ? 1u << (23 + lane) : 0u;
         __syncwarp();
         for (int i = 0; i < n; ++i) {
-            const uint32_t q = (n - i <= LSD_RING) ? ring[i & (LSD_RING - 1)] : reg[i];
-            const int xx = (int)(q & 0xffffu) + ox, yy = (int)(q >> 16) + oy;
-            const bool inb = lane < 9 && xx >= 0 && xx < W && yy >= 0 && yy < H;
-            const int word = inb ? yy * WW + (xx >> 5) : 0;
-            const unsigned bit = 1u << (xx & 31);
-            const bool def = inb && (D[word] & bit);
+            uint32_t e;
+            if (n - i <= LSD_RING) e = lds32(ring + 4u * (unsigned)(i & (LSD_RING - 1)));
+            else {
+                const uint32_t r = reg[i];
+                e = r | (__float_as_uint(pix[r].w) << 23);
+            }
+            const bool def = e & lanebit;
+            const int idx = (int)(e & 0x7fffffu) + off;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (def) v = pix[(size_t)yy * W + xx];
-            const bool frn = def && is_foreign(__float_as_int(v.w));
-            const bool cand = def && (frn || !(U[word] & bit));
+            if (def) v = pix[idx];
+            const uint32_t wv = __float_as_uint(v.w);
+            const bool frn = def && is_foreign((int)(wv >> 9));
+            const bool cand = def && (frn || !used(idx));
             unsigned m = __ballot_sync(0xffffffffu, cand);
             while (m) {
                 const bool al = cand && l_aligned_fast(v.x, reg_deg, prec_deg, prec);
@@ -540,14 +553,13 @@ struct Grow {
                 if (!am) break;
                 const int l = __ffs(am) - 1;
                 if (__shfl_sync(0xffffffffu, (int)frn, l)) {
-                    foreign_root = __shfl_sync(0xffffffffu, __float_as_int(v.w), l);
+                    foreign_root = (int)(__shfl_sync(0xffffffffu, wv, l) >> 9);
                     break;
                 }
                 if (lane == l) {
-                    const uint32_t pos = (uint32_t)xx | ((uint32_t)yy << 16);
-                    atomicOr(&U[word], bit);
-                    reg[n] = pos;
-                    ring[n & (LSD_RING - 1)] = pos;
+                    set_used(idx);
+                    reg[n] = (uint32_t)idx;
+                    sts32(ring + 4u * (unsigned)(n & (LSD_RING - 1)), (uint32_t)idx | (wv << 23));
                 }
                 sumdx += __shfl_sync(0xffffffffu, v.y, l);
                 sumdy += __shfl_sync(0xffffffffu, v.z, l);
@@ -568,9 +580,9 @@ struct Grow {
         for (int base = 0; base < n; base += 32) {
             const int idx = base + lane, cnt = min(32, n - base);
             if (idx < n) {
-                const uint32_t q = reg[idx];
-                const int px = q & 0xffffu, py = q >> 16;
-                const double w = mg[(size_t)py * W + px];
+                const int q = (int)reg[idx];
+                const int py = q / W, px = q - py * W;
+                const double w = mg[q];
                 sc[lane] = double(px) * w;
                 sc[32 + lane] = double(py) * w;
                 sc[64 + lane] = w;
@@ -589,9 +601,9 @@ struct Grow {
         for (int base = 0; base < n; base += 32) {
             const int idx = base + lane, cnt = min(32, n - base);
             if (idx < n) {
-                const uint32_t q = reg[idx];
-                const int px = q & 0xffffu, py = q >> 16;
-                const double w = mg[(size_t)py * W + px];
+                const int q = (int)reg[idx];
+                const int py = q / W, px = q - py * W;
+                const double w = mg[q];
                 const double ddx = double(px) - x, ddy = double(py) - y;
                 sc[lane] = ddy * ddy * w;
                 sc[32 + lane] = ddx * ddx * w;
@@ -613,8 +625,9 @@ struct Grow {
         det_sincos(theta, dy, dx);
         double l_min = 0, l_max = 0, w_min = 0, w_max = 0;  // the reference's running min / max from 0 (order-free)
         for (int idx = lane; idx < n; idx += 32) {
-            const uint32_t q = reg[idx];
-            const double regdx = double(q & 0xffffu) - x, regdy = double(q >> 16) - y;
+            const int q = (int)reg[idx];
+            const int py = q / W, px = q - py * W;
+            const double regdx = double(px) - x, regdy = double(py) - y;
             const double l = regdx * dx + regdy * dy;
             const double w = -regdx * dy + regdy * dx;
             l_max = fmax(l_max, l);
@@ -653,10 +666,10 @@ struct Grow {
             const int idx = base + lane;
             bool keep = false;
             if (idx < n) {
-                const uint32_t q = reg[idx];
-                const int px = q & 0xffffu, py = q >> 16;
+                const int q = (int)reg[idx];
+                const int py = q / W, px = q - py * W;
                 keep = !(l_distSq(xc, yc, double(px), double(py)) > radSq);
-                if (!keep) clear_used(px, py);
+                if (!keep) clear_used(q);
             }
             m += __popc(__ballot_sync(0xffffffffu, keep));
         }
@@ -668,7 +681,7 @@ struct Grow {
                 uint32_t q = 0;
                 if (pos >= m) {
                     q = reg[pos];
-                    keep = !(l_distSq(xc, yc, double(q & 0xffffu), double(q >> 16)) > radSq);
+                    keep = !(l_distSq(xc, yc, double((int)q % W), double((int)q / W)) > radSq);
                 }
                 const unsigned b = __ballot_sync(0xffffffffu, keep);
                 if (keep) tmp[r + __popc(b & ((1u << lane) - 1u))] = q;
@@ -680,8 +693,8 @@ struct Grow {
                 const int idx = base + lane;
                 bool far = false;
                 if (idx < m) {
-                    const uint32_t q = reg[idx];
-                    far = l_distSq(xc, yc, double(q & 0xffffu), double(q >> 16)) > radSq;
+                    const int q = (int)reg[idx];
+                    far = l_distSq(xc, yc, double(q % W), double(q / W)) > radSq;
                 }
                 const unsigned b = __ballot_sync(0xffffffffu, far);
                 if (far) reg[idx] = tmp[r + __popc(b & ((1u << lane) - 1u))];
@@ -694,22 +707,21 @@ struct Grow {
 
     // First half of refine() (lsd.cpp:794-813): release the region and derive the tighter tolerance tau from the angle spread near the seed.
     __device__ __forceinline__ double tau_step(int n, double width) {
-        const uint32_t q0 = reg[0];
-        const int x0 = q0 & 0xffffu, y0 = q0 >> 16;
-        const double xc = double(x0), yc = double(y0);
-        const double ang_c = (double)pix[(size_t)y0 * W + x0].x * LSD_DEG2RAD;
+        const int q0 = (int)reg[0];
+        const double xc = double(q0 % W), yc = double(q0 / W);
+        const double ang_c = (double)deg[q0] * LSD_DEG2RAD;
         double sum = 0, s_sum = 0;
         int cnt = 0;
         for (int base = 0; base < n; base += 32) {
             const int idx = base + lane;
             bool near = false;
             if (idx < n) {
-                const uint32_t q = reg[idx];
-                const int px = q & 0xffffu, py = q >> 16;
-                clear_used(px, py);
+                const int q = (int)reg[idx];
+                const int py = q / W, px = q - py * W;
+                clear_used(q);
                 if (l_dist(xc, yc, double(px), double(py)) < width) {
                     near = true;
-                    sc[lane] = l_angle_diff_signed((double)pix[(size_t)py * W + px].x * LSD_DEG2RAD, ang_c);
+                    sc[lane] = l_angle_diff_signed((double)deg[q] * LSD_DEG2RAD, ang_c);
                 }
             }
             unsigned m = __ballot_sync(0xffffffffu, near);
@@ -857,27 +869,22 @@ __global__ void __launch_bounds__(LSD_WARPS * 32, 2) k_lsd_grow(LsdBuffers B, Ls
     extern __shared__ __align__(16) unsigned char lsd_smem[];
     __shared__ int s_next, s_nout, s_nviol, s_nunits, s_alloc;
     const int f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nw = d.H * d.WW, npx = d.W * d.H;
+    const int npx = d.W * d.H, nw = (npx + 31) / 32;
     Grow G;
     G.sc = reinterpret_cast<double*>(lsd_smem + (size_t)warp * LSD_WARP_SMEM);
-    G.ring = reinterpret_cast<uint32_t*>(G.sc + 96);
-    G.U = reinterpret_cast<uint32_t*>(lsd_smem + (size_t)LSD_WARPS * LSD_WARP_SMEM);
-    uint32_t* Dm = G.U + nw;
-    G.D = Dm;
+    G.ring = (uint32_t)__cvta_generic_to_shared(G.sc + 96);
+    uint32_t* Ubits = reinterpret_cast<uint32_t*>(lsd_smem + (size_t)LSD_WARPS * LSD_WARP_SMEM);
+    G.U = (uint32_t)__cvta_generic_to_shared(Ubits);
     const size_t fo = (size_t)f * npx;
     G.pix = B.pix + fo;
     G.deg = B.deg + fo;
     G.mg = B.modgrad + fo;
     int* cgrp = B.cgrp + fo;
     G.cgrp = cgrp;
-    G.W = d.W; G.H = d.H; G.WW = d.WW; G.lane = lane;
+    G.W = d.W; G.H = d.H; G.lane = lane;
     G.LOG_NT = C.log_nt;
     G.n_regions = 0; G.n_px = 0;
-    const uint32_t* dsrc = B.defbits + (size_t)f * nw;
-    for (int i = threadIdx.x; i < nw; i += blockDim.x) {
-        G.U[i] = 0;
-        Dm[i] = dsrc[i];
-    }
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) Ubits[i] = 0;
     const int n_big = B.ncomp[4 * f], n_small = B.ncomp[4 * f + 1];
     if (threadIdx.x == 0) { s_next = 0; s_nout = 0; s_nviol = 0; s_alloc = 0; s_nunits = n_big + n_small; }
     __syncthreads();
@@ -917,34 +924,38 @@ __global__ void __launch_bounds__(LSD_WARPS * 32, 2) k_lsd_grow(LsdBuffers B, Ls
             // (1) the unit's pixels in raster order: scan its bounding box for the label.  A merged unit starts from a clean used map.
             int cnt = 0;
             for (int y = y0; y <= maxy && cnt < usize; y++)
-                for (int xb = minx & ~31; xb <= maxx; xb += 32) {
-                    const int x = xb + lane;
-                    bool mine = false;
-                    if (x <= maxx) {
-                        const int lbl = L[(size_t)y * d.W + x];
-                        mine = mode == 0 ? lbl == root : (lbl >= 0 && (mode == 2 || lbl == root || ccl_find(cgrp, lbl) == root));
+                for (int xb = minx & ~31; xb <= maxx; xb += 128) {
+                    int lbl[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {  // four independent loads in flight
+                        const int x = xb + 32 * k + lane;
+                        lbl[k] = x <= maxx ? L[y * d.W + x] : -1;
                     }
-                    const unsigned m = __ballot_sync(0xffffffffu, mine);
-                    if (mine) {
-                        lst[cnt + __popc(m & ((1u << lane) - 1u))] = (uint32_t)x | ((uint32_t)y << 16);
-                        if (mode != 0) G.clear_used(x, y);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const bool mine = mode == 0 ? lbl[k] == root : (lbl[k] >= 0 && (mode == 2 || lbl[k] == root || ccl_find(cgrp, lbl[k]) == root));
+                        const unsigned m = __ballot_sync(0xffffffffu, mine);
+                        if (mine) {
+                            const int pi = y * d.W + xb + 32 * k + lane;
+                            lst[cnt + __popc(m & ((1u << lane) - 1u))] = (uint32_t)pi;
+                            if (mode != 0) G.clear_used(pi);
+                        }
+                        cnt += __popc(m);
                     }
-                    cnt += __popc(m);
                 }
             __syncwarp();
             // (2) flsd's seed loop (lsd.cpp:474-535) over this unit
             for (int base = 0; base < cnt && G.foreign_root < 0; base += 32) {
                 const int idx = base + lane;
-                const uint32_t q = idx < cnt ? lst[idx] : 0u;
-                const int qx = q & 0xffffu, qy = q >> 16;
+                const int q = idx < cnt ? (int)lst[idx] : 0;
                 unsigned todo = 0xffffffffu;
                 while (G.foreign_root < 0) {
-                    const bool unused = idx < cnt && !(G.U[qy * d.WW + (qx >> 5)] & (1u << (qx & 31)));
+                    const bool unused = idx < cnt && !G.used(q);
                     const unsigned m = __ballot_sync(0xffffffffu, unused) & todo;
                     if (!m) break;
                     const int l = __ffs(m) - 1;
                     todo = ~((2u << l) - 1u);
-                    const int sx = __shfl_sync(0xffffffffu, qx, l), sy = __shfl_sync(0xffffffffu, qy, l);
+                    const int seed = __shfl_sync(0xffffffffu, q, l);
                     // ---- one seed (lsd.cpp:478-534 with refine :786-832 and reduce_region_radius :834-871 unrolled into one loop, so
                     //      that region_grow and region2rect have a single call site each)
                     LRect rec;
@@ -954,7 +965,7 @@ __global__ void __launch_bounds__(LSD_WARPS * 32, 2) k_lsd_grow(LsdBuffers B, Ls
                     long long t0 = clock64();
                     while (true) {
                         if (!reducing) {
-                            n = G.region_grow(sx, sy, tol, reg_angle);
+                            n = G.region_grow(seed, tol, reg_angle);
                             const long long t1 = clock64();
                             cyc[attempt == 0 ? 0 : 2] += t1 - t0;
                             t0 = t1;
@@ -977,8 +988,7 @@ __global__ void __launch_bounds__(LSD_WARPS * 32, 2) k_lsd_grow(LsdBuffers B, Ls
                             tol = G.tau_step(n, rec.width);
                             attempt = 1;
                         } else if (!reducing) {  // then shrink the region around the seed
-                            const uint32_t q0 = G.reg[0];
-                            xc = double(q0 & 0xffffu); yc = double(q0 >> 16);
+                            xc = double(seed % d.W); yc = double(seed / d.W);
                             const double radSq1 = l_distSq(xc, yc, rec.x1, rec.y1), radSq2 = l_distSq(xc, yc, rec.x2, rec.y2);
                             radSq = radSq1 > radSq2 ? radSq1 : radSq2;
                             reducing = true;
@@ -1019,7 +1029,7 @@ __global__ void __launch_bounds__(LSD_WARPS * 32, 2) k_lsd_grow(LsdBuffers B, Ls
                         const int slot = atomicAdd(&s_nout, 1);
                         if (slot < B.stage_cap) {
                             stage[slot] = make_float4(e0, e1, e2, e3);
-                            stage_key[slot] = sy * d.W + sx;
+                            stage_key[slot] = seed;
                             stage_owner[slot] = root;
                         }
                     }
@@ -1112,7 +1122,7 @@ struct LsdState {
     LsdDims d{};
     LsdConst C{};
     csb_lsd_params params{};
-    DevBuf d_gray, d_scaled, d_pix, d_deg, d_mg, d_def, d_arena, d_roots, d_ncomp, d_stage, d_stage_key, d_stage_owner, d_lines, d_nlines, d_stats;
+    DevBuf d_gray, d_scaled, d_pix, d_deg, d_mg, d_arena, d_roots, d_ncomp, d_stage, d_stage_key, d_stage_owner, d_lines, d_nlines, d_stats;
     int stage_cap = 0;
     HostBuf h_gray, h_out;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -1123,7 +1133,7 @@ struct LsdState {
 
 void lsd_release(LsdState*& s) {
     if (!s) return;
-    DevBuf* bufs[] = {&s->d_gray, &s->d_scaled, &s->d_pix, &s->d_deg, &s->d_mg, &s->d_def, &s->d_arena, &s->d_roots, &s->d_ncomp, &s->d_stage,
+    DevBuf* bufs[] = {&s->d_gray, &s->d_scaled, &s->d_pix, &s->d_deg, &s->d_mg, &s->d_arena, &s->d_roots, &s->d_ncomp, &s->d_stage,
                       &s->d_stage_key, &s->d_stage_owner, &s->d_lines, &s->d_nlines, &s->d_stats};
     for (DevBuf* b : bufs) b->release();
     s->h_gray.release();
@@ -1141,7 +1151,6 @@ static LsdBuffers lsd_buffers(LsdState& s) {
     B.pix = s.d_pix.as<float4>();
     B.deg = s.d_deg.as<float>();
     B.modgrad = s.d_mg.as<double>();
-    B.defbits = s.d_def.as<uint32_t>();
     const size_t npx = (size_t)s.d.W * s.d.H * s.d.n_frames;
     uint32_t* ar = s.d_arena.as<uint32_t>();  // 6 work arenas
     B.regA = ar; B.tmpA = ar + npx; B.lstA = ar + 2 * npx; B.regB = ar + 3 * npx; B.tmpB = ar + 4 * npx; B.lstB = ar + 5 * npx;
@@ -1164,7 +1173,7 @@ static LsdBuffers lsd_buffers(LsdState& s) {
 using namespace csb;
 
 static int lsd_prepare(csb_context* c, int n_frames, int width, int height, const csb_lsd_params* params) {
-    if (!c || !params || n_frames <= 0 || width < 8 || height < 8 || width > 65535 || height > 65535 || params->max_lines <= 0) return CSB_ERR_INVALID;
+    if (!c || !params || n_frames <= 0 || width < 8 || height < 8 || (int64_t)width * height > (1 << 23) || params->max_lines <= 0) return CSB_ERR_INVALID;
     CSB_CUDA(c, cudaSetDevice(c->device));
     if (!c->lsd) {
         c->lsd = new LsdState();
@@ -1179,7 +1188,6 @@ static int lsd_prepare(csb_context* c, int n_frames, int width, int height, cons
     d.h = height;
     d.W = (int)std::lrint(width * LSD_SCALE);   // cvRound (lsd.cpp:459 -> cv::resize dsize)
     d.H = (int)std::lrint(height * LSD_SCALE);
-    d.WW = (d.W + 31) / 32;
     d.n_frames = n_frames;
     LsdConst& C = s.C;
     {   // cv::getGaussianKernel(7, sigma, CV_64F) with sigma = SIGMA_SCALE / SCALE (lsd.cpp:453-457); ksize = 1 + 2 ceil(sigma sqrt(2 * 3 ln 10)) = 7
@@ -1202,7 +1210,7 @@ static int lsd_prepare(csb_context* c, int n_frames, int width, int height, cons
     C.length_thres = params->line_length_thres;
     C.filter = params->filter;
     C.max_lines = params->max_lines;
-    s.grow_smem = (size_t)LSD_WARPS * LSD_WARP_SMEM + 2 * (size_t)d.H * d.WW * sizeof(uint32_t);
+    s.grow_smem = (size_t)LSD_WARPS * LSD_WARP_SMEM + (size_t)((d.W * d.H + 31) / 32) * sizeof(uint32_t);
     s.stage_cap = std::max((d.W * d.H) / 4, params->max_lines);
     if (s.grow_smem > (size_t)c->max_smem_optin) {
         c->err = "csb_lsd: frame too large for the shared-memory used/defined bitmaps";
@@ -1214,7 +1222,6 @@ static int lsd_prepare(csb_context* c, int n_frames, int width, int height, cons
     CSB_CUDA(c, s.d_pix.ensure(npx * 16));
     CSB_CUDA(c, s.d_deg.ensure(npx * 4));
     CSB_CUDA(c, s.d_mg.ensure(npx * 8));
-    CSB_CUDA(c, s.d_def.ensure((size_t)d.H * d.WW * n_frames * 4));
     CSB_CUDA(c, s.d_arena.ensure(npx * 4 * 6));
     CSB_CUDA(c, s.d_roots.ensure(npx * 4 * 12));
     CSB_CUDA(c, s.d_ncomp.ensure((size_t)n_frames * 16));
@@ -1257,7 +1264,7 @@ int csb_lsd_run(csb_context* c, int timed) {
     CSB_CUDA(c, cudaMemsetAsync(s.d_stats.p, 0, 128, st));
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[0], st));
     k_lsd_scale<<<dim3((d.W + SC_TW - 1) / SC_TW, (d.H + SC_TH - 1) / SC_TH, d.n_frames), SC_THREADS, 0, st>>>(B, d, s.C);
-    const dim3 pg(d.WW, (d.H + 7) / 8, d.n_frames), pb(32, 8);
+    const dim3 pg((d.W + 31) / 32, (d.H + 7) / 8, d.n_frames), pb(32, 8);
     k_lsd_grad<<<pg, pb, 0, st>>>(B, d, s.C);
     CSB_CUDA(c, cudaMemsetAsync(s.d_ncomp.p, 0, (size_t)d.n_frames * 16, st));
     k_lsd_merge<<<pg, pb, 0, st>>>(B, d, s.params.unit_link_deg > 0 ? (float)s.params.unit_link_deg : LSD_LINK_DEG);
