@@ -401,7 +401,8 @@ def run_ours(args, rank, local_rank, world):
         lsd_frames = None
         try:
             base = synth.make_lsd_frames(32, LSD_W, LSD_H, seed=20260927)
-            lsd_frames = np.ascontiguousarray(np.concatenate([base] * (LSD_FRAMES // 32)))
+            t_lsd, lsd_frames = pinned(np.concatenate([base] * (LSD_FRAMES // 32)))
+            keep.append(t_lsd)
             with torch.cuda.stream(stream):
                 ctx.lsd_upload(lsd_frames)
                 for _ in range(2):
@@ -429,7 +430,7 @@ def run_ours(args, rank, local_rank, world):
                           "ms_per_batch": tot_ms / reps, "kernel_ms": {"maps (scale, gradient, labelling)": m_ms, "grow (regions, rectangles, NFA)": float(np.mean(grow_ms))},
                           "segments": int(lst.n_lines), "regions": int(lst.n_regions), "region_px": int(lst.n_region_px), "merge_rounds": int(lst.n_merge_rounds),
                           "e2e": {"value": LSD_FRAMES / (call_ms * 1e-3), "unit": "frames/s", "ms_per_call": call_ms, "h2d_bytes_per_step": int(lst.h2d_bytes),
-                                  "d2h_bytes_per_step": int(lst.d2h_bytes), "mode": "one blocking csb_lsd_detect_batch() with host buffers"},
+                                  "d2h_bytes_per_step": int(lst.d2h_bytes), "mode": "one blocking csb_lsd_detect_batch() with pinned host buffers"},
                           "roofline": {"kernel": "streaming stages (k_lsd_scale .. k_lsd_units)", "bound": "hbm", "achieved": lsd_ach, "peak": peak, "unit": "GB/s",
                                        "frac": lsd_ach / peak, "traffic": None, "algorithmic_bytes_per_launch": LSD_ALGO_BYTES_PER_FRAME * LSD_FRAMES,
                                        "note": "the region kernel that follows is sequential per work unit (latency bound), see DESIGN.md 3c"},

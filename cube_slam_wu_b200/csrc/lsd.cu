@@ -1243,9 +1243,16 @@ int csb_lsd_upload(csb_context* c, const uint8_t* gray, int n_frames, int width,
     if (rc != CSB_OK) return rc;
     LsdState& s = *c->lsd;
     const size_t bytes = (size_t)width * height * n_frames;
-    CSB_CUDA(c, s.h_gray.ensure(bytes));
-    std::memcpy(s.h_gray.p, gray, bytes);
-    CSB_CUDA(c, cudaMemcpyAsync(s.d_gray.p, s.h_gray.p, bytes, cudaMemcpyHostToDevice, c->stream));
+    cudaPointerAttributes pa{};
+    const bool pinned = cudaPointerGetAttributes(&pa, gray) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();  // an unregistered pageable pointer is not an error here
+    if (pinned) {  // caller-pinned frames go straight to the device (the caller keeps them alive until the next synchronising call)
+        CSB_CUDA(c, cudaMemcpyAsync(s.d_gray.p, gray, bytes, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        CSB_CUDA(c, s.h_gray.ensure(bytes));
+        std::memcpy(s.h_gray.p, gray, bytes);
+        CSB_CUDA(c, cudaMemcpyAsync(s.d_gray.p, s.h_gray.p, bytes, cudaMemcpyHostToDevice, c->stream));
+    }
     s.h2d_bytes = (int64_t)bytes;
     s.uploaded = true;
     return CSB_OK;
@@ -1291,11 +1298,16 @@ int csb_lsd_download(csb_context* c, float* lines_out, int32_t* n_lines_out, csb
     const size_t lb = (size_t)s.d.n_frames * s.params.max_lines * 16, nb = (size_t)s.d.n_frames * 4;
     CSB_CUDA(c, s.h_out.ensure(lb + nb + 128));
     char* h = s.h_out.as<char>();
-    CSB_CUDA(c, cudaMemcpyAsync(h, s.d_lines.p, lb, cudaMemcpyDeviceToHost, c->stream));
+    // counts first, then only the rows that are in use (the per-frame capacity is usually far larger than the segment count)
     CSB_CUDA(c, cudaMemcpyAsync(h + lb, s.d_nlines.p, nb, cudaMemcpyDeviceToHost, c->stream));
     CSB_CUDA(c, cudaMemcpyAsync(h + lb + nb, s.d_stats.p, 128, cudaMemcpyDeviceToHost, c->stream));
     CSB_CUDA(c, cudaStreamSynchronize(c->stream));
-    s.d2h_bytes = (int64_t)(lb + nb + 128);
+    int rows = 0;
+    for (int f = 0; f < s.d.n_frames; f++) rows = std::max(rows, std::min(reinterpret_cast<const int32_t*>(h + lb)[f], s.params.max_lines));
+    const size_t pitch = (size_t)s.params.max_lines * 16;
+    if (rows > 0) CSB_CUDA(c, cudaMemcpy2DAsync(h, pitch, s.d_lines.p, pitch, (size_t)rows * 16, s.d.n_frames, cudaMemcpyDeviceToHost, c->stream));
+    CSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    s.d2h_bytes = (int64_t)((size_t)rows * 16 * s.d.n_frames + nb + 128);
     const int32_t* nl = reinterpret_cast<const int32_t*>(h + lb);
     const unsigned long long* st = reinterpret_cast<const unsigned long long*>(h + lb + nb);
     bool overflow = false;
@@ -1304,7 +1316,9 @@ int csb_lsd_download(csb_context* c, float* lines_out, int32_t* n_lines_out, csb
         overflow |= nl[f] > s.params.max_lines;
         total += std::min(nl[f], s.params.max_lines);
     }
-    if (lines_out) std::memcpy(lines_out, h, lb);
+    if (lines_out)
+        for (int f = 0; f < s.d.n_frames; f++)
+            std::memcpy(reinterpret_cast<char*>(lines_out) + f * pitch, h + f * pitch, (size_t)std::min(nl[f], s.params.max_lines) * 16);
     if (n_lines_out) std::memcpy(n_lines_out, nl, nb);
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));

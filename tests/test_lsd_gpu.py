@@ -110,3 +110,15 @@ def test_unit_partition_does_not_change_the_result(ctx, csb, oracle, link_deg):
     lines, st, worst = _check(ctx, oracle, frames, unit_link_deg=link_deg)
     assert st.n_merge_rounds > 0 and st.n_unit_conflicts > 0
     print("link %d deg: %d merge rounds, %d conflicts, max diff %g" % (link_deg, st.n_merge_rounds, st.n_unit_conflicts, worst))
+
+
+def test_reference_golden_vector_on_gpu(ctx, csb, oracle):
+    """The reference's own LSD output for its bundled demo image (tests/golden/lsd_demo.npz, see test_lsd_oracle.py): the GPU path
+    reproduces the oracle bit for bit and hence the file (271 segments, same order, 6 printed digits but for one segment at 7e-4 px)."""
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lsd_demo.npz"))
+    frames = np.ascontiguousarray(d["gray"][None])
+    lines, st, worst = _check(ctx, oracle, frames)
+    ref = d["ref_lines"]
+    assert lines[0].shape == ref.shape
+    assert np.abs(lines[0].astype(np.float64) - ref).max() < 2e-3
