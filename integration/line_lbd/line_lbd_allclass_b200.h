@@ -1,0 +1,53 @@
+// line_lbd_allclass_b200.h -- drop-in for the LSD branch of class line_lbd_detect
+// (reference: line_lbd/include/line_lbd/line_lbd_allclass.h:20-60, line_lbd/class/line_lbd_allclass.cpp:130-149, 200-235).
+//
+// Same class name, same public members the callers touch (use_LSD, line_length_thres; object_slam/src/main_obj.cpp:503-505,
+// line_lbd/src/detect_lines.cpp:61-66) and the same detect_filter_lines(const cv::Mat&, cv::Mat&) signature; the work is done by
+// csb_lsd_detect_batch() of libcubeslam_b200.so.  NOT compiled in the build container (no OpenCV headers there); it only uses the C ABI,
+// which the test-suite exercises through ctypes.  use_LSD = false (EDLines) is not ported: keep the reference's class for that.
+#pragma once
+#include <opencv2/core.hpp>
+
+#include <stdexcept>
+#include <vector>
+
+#include "cubeslam_b200.h"
+
+class line_lbd_detect {
+public:
+    line_lbd_detect(int numoctaves = 1, float octaveratio = 2.0) : numoctaves_(numoctaves), octaveratio_(octaveratio) {
+        if (numoctaves != 1) throw std::runtime_error("line_lbd_detect (B200): one octave only, as every caller in the reference uses");
+        if (csb_create(&ctx_, 0) != CSB_OK) throw std::runtime_error("line_lbd_detect (B200): no usable CUDA device (there is no CPU fallback)");
+    }
+    ~line_lbd_detect() { csb_destroy(ctx_); }
+    line_lbd_detect(const line_lbd_detect&) = delete;
+    line_lbd_detect& operator=(const line_lbd_detect&) = delete;
+
+    bool use_LSD = true;            // line_lbd_allclass.h:32 (the reference defaults to false = EDLines)
+    float line_length_thres = 50;   // line_lbd_allclass.h:35, :126; both callers set 15
+
+    // line_lbd_allclass.cpp:221-235: gray image in, n x 4 CV_32F [x1 y1 x2 y2] out (keylines_to_mat, :28-38)
+    void detect_filter_lines(const cv::Mat& gray_img, cv::Mat& linesmat_out) {
+        if (!use_LSD) throw std::runtime_error("line_lbd_detect (B200): use_LSD = false is not implemented");
+        if (gray_img.type() != CV_8UC1) throw std::runtime_error("Error, depth image!= 0");  // LSDDetector.cpp:163-164
+        cv::Mat gray = gray_img.isContinuous() ? gray_img : gray_img.clone();
+        csb_lsd_params p{line_length_thres, 1, max_lines_, 0};
+        lines_.resize((size_t)max_lines_ * 4);
+        int32_t n = 0;
+        int rc = csb_lsd_detect_batch(ctx_, gray.data, 1, gray.cols, gray.rows, &p, lines_.data(), &n, nullptr);
+        if (rc == CSB_ERR_CAPACITY) {  // more segments than rows: grow once and repeat
+            max_lines_ *= 4;
+            return detect_filter_lines(gray_img, linesmat_out);
+        }
+        if (rc != CSB_OK) throw std::runtime_error(csb_last_error(ctx_));
+        linesmat_out.create(n, 4, CV_32FC1);
+        if (n) std::memcpy(linesmat_out.data, lines_.data(), (size_t)n * 16);
+    }
+
+private:
+    int numoctaves_;
+    float octaveratio_;
+    csb_context* ctx_ = nullptr;
+    int max_lines_ = 4096;
+    std::vector<float> lines_;
+};

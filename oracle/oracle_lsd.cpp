@@ -14,13 +14,19 @@
 //   cv::fastAtan2                               the degree-7 float polynomial of core/src/mathfuncs_core
 //   cv::LineIterator                            only its pixel count, which does not reach the output matrix -> not restated
 //
-// How it is pinned (tests/test_lsd_oracle.py, fixtures tests/golden/lsd_cv2.npz made by tests/golden/make_lsd_golden.py): python cv2 4.13
-// ships the same LSD (cv2.createLineSegmentDetector(LSD_REFINE_ADV)); the one algorithmic difference is the order in which seed pixels
-// are visited -- cv2 4.x visits them by descending bin of the quantised gradient norm, the reference's copy walks `list[i]` in raster order because its
-// bin "sort" only relinks ->next pointers it never follows (lsd.cpp:478-481 vs :618-634).  seed_order = 1 reproduces cv2 4.13 (bins of
-// descending gradient norm, raster order inside a bin) and is compared segment by segment with cv2's output; seed_order = 0 is the reference's order.
+// How it is pinned (tests/test_lsd_oracle.py; fixtures tests/golden/lsd_demo.npz + lsd_cv2.npz made by tests/golden/make_lsd_golden.py):
+//  (1) the reference's OWN golden vector: detect_3d_cuboid/data/edge_detection/LSD/0000_edge.txt holds the 271 segments the reference's
+//      line_lbd node wrote for the bundled image detect_3d_cuboid/data/0000_rgb_raw.jpg.  This restatement reproduces the file: 271
+//      segments in the same order, 1082 of 1084 coordinates equal to the 6 printed digits, the worst 7e-4 px off (author's OpenCV and JPEG
+//      decoder vs cv2 4.13).  The file pins everything at once -- front end, seed order, region growing, refinement, the NFA search with
+//      the reference copy's quirks (integer-division scan-line slopes, `n + 1` instead of log_gamma(n + 1)), border and length filters.
+//  (2) cv2 4.13, which ships a newer revision of the same detector (cv2.createLineSegmentDetector): it visits seeds by descending bin of
+//      the quantised gradient norm (raster order inside a bin) where the reference's copy walks `list[i]` in raster order (its bin "sort"
+//      only relinks ->next pointers it never follows, lsd.cpp:478-481 vs :618-634), runs its front end on the u8 image, and has a
+//      repaired NFA.  seed_order = 1 + cv2's own scaled image as input reproduce cv2's LSD_REFINE_NONE and LSD_REFINE_STD outputs bit
+//      for bit (everything up to and including refine()); the CV_64F blur + resize and fastAtan2 are compared with cv2's directly.
 //
-// Specified arithmetic shared with the device path (csrc/lsd_dev.cuh): the running region angle sums cosf/sinf of every accepted
+// Specified arithmetic shared with the device path (csrc/lsd.cu): the running region angle sums cosf/sinf of every accepted
 // pixel in FLOAT (lsd.cpp:679-680), so a 1-ulp libm difference changes which pixels join a region.  Both sides therefore use det_sincos()
 // (Cody-Waite reduction + the fdlibm kernel polynomials, plain IEEE double operations, rounded once to float) instead of libm;
 // libm_trig = 1 selects the literal libm calls.
