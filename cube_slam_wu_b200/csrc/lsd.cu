@@ -739,9 +739,25 @@ struct Grow {
         return 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / double(cnt) + mean_angle * mean_angle);
     }
 
+};
+
+// Everything after refine(): the NFA search over rectangle variants and the output filters.  None of it touches the used map, so a
+// finished rectangle can be handed to any warp of the CTA (job queue in k_lsd_grow); the producing warp goes on growing regions.
+struct NfaCtx {
+    const float* deg;
+    int W, H, w, h, lane;
+    double LOG_NT;
+    int filter;
+    float length_thres;
+    float4* stage;
+    int* stage_key;
+    int* stage_owner;
+    int stage_cap;
+    int* nout;  // shared counter of staged segments
+
     // lsd.cpp:977-1098.  Integer-division slopes and the tailp->p.x comparisons are the reference's; since every step is an integer the
     // scan-line bounds of row y have a closed form, so rows can be counted in any order.
-    __device__ __forceinline__ double rect_nfa(const LRect& rec) {
+    __device__ __forceinline__ double rect_nfa(const LRect& rec) const {
         const double half_width = rec.width / 2.0;
         const double dyhw = rec.dy * half_width, dxhw = rec.dx * half_width;
         int ex[4], ey[4];
@@ -826,7 +842,7 @@ struct Grow {
 
     // lsd.cpp:873-975 as one loop (a single rect_nfa call site keeps the code small): trial 0 is the rectangle itself, then five
     // stages of five trials each -- finer precision, narrower, one side in, the other side in, finer precision again.
-    __device__ __forceinline__ double rect_improve(LRect& rec) {
+    __device__ __forceinline__ double rect_improve(LRect& rec) const {
         const double LOG_EPS = 0, delta = 0.5, delta_2 = delta / 2.0;
         double log_nfa = -DBL_MAX;
         LRect r = rec;
@@ -859,6 +875,47 @@ struct Grow {
         }
         return log_nfa;
     }
+
+    // rect_improve (lsd.cpp:500-504), the +0.5 / rescale (:509-519), the LSDDetector / line_lbd filters, staging
+    __device__ __noinline__ void finish(LRect rec, int seed, int owner) const {
+        const double log_nfa = rect_improve(rec);
+        if (log_nfa <= 0) return;
+        rec.x1 += 0.5; rec.y1 += 0.5; rec.x2 += 0.5; rec.y2 += 0.5;
+        rec.x1 /= LSD_SCALE; rec.y1 /= LSD_SCALE; rec.x2 /= LSD_SCALE; rec.y2 /= LSD_SCALE;
+        float e0 = float(rec.x1), e1 = float(rec.y1), e2 = float(rec.x2), e3 = float(rec.y2);
+        if (filter) {
+            // LSDDetector.cpp:80-101, 219-232 (octaveScale = 1), line_lbd_allclass.cpp:206
+            const int w_ = w, h_ = h;
+            if (e0 < 0) e0 = 0;
+            if (e0 >= w_) e0 = (float)w_ - 1.0f;
+            if (e2 < 0) e2 = 0;
+            if (e2 >= w_) e2 = (float)w_ - 1.0f;
+            if (e1 < 0) e1 = 0;
+            if (e1 >= h_) e1 = (float)h_ - 1.0f;
+            if (e3 < 0) e3 = 0;
+            if (e3 >= h_) e3 = (float)h_ - 1.0f;
+            const float thr = 10;
+            if (((e0 < thr) && (e2 < thr)) || ((e0 > w_ - thr) && (e2 > w_ - thr)) || ((e1 < thr) && (e3 < thr)) || ((e1 > h_ - thr) && (e3 > h_ - thr)))
+                return;
+            const double ddx = double(e0 - e2), ddy = double(e1 - e3);
+            const float len = (float)sqrt(ddx * ddx + ddy * ddy);
+            if (!(len > length_thres)) return;
+        }
+        if (lane == 0) {
+            const int slot = atomicAdd(nout, 1);
+            if (slot < stage_cap) {
+                stage[slot] = make_float4(e0, e1, e2, e3);
+                stage_key[slot] = seed;
+                stage_owner[slot] = owner;
+            }
+        }
+    }
+};
+
+constexpr int LSD_JOBQ = 32;  // finished rectangles waiting for their NFA search
+struct NfaJob {
+    double r[12];
+    int seed, owner;
 };
 
 constexpr int LSD_WARPS = 8;  // 8 warps x <=128 registers: two CTAs (frames) per SM
@@ -867,7 +924,9 @@ constexpr int LSD_MAX_ROUNDS = 12;  // merge rounds before the rest of the frame
 
 __global__ void __launch_bounds__(LSD_WARPS * 32, 2) k_lsd_grow(LsdBuffers B, LsdDims d, LsdConst C) {
     extern __shared__ __align__(16) unsigned char lsd_smem[];
-    __shared__ int s_next, s_nout, s_nviol, s_nunits, s_alloc;
+    __shared__ int s_next, s_nout, s_nviol, s_nunits, s_alloc, s_qtail, s_qhead, s_qdone, s_active;
+    __shared__ NfaJob s_job[LSD_JOBQ];
+    __shared__ int s_job_ready[LSD_JOBQ];
     const int f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int npx = d.W * d.H, nw = (npx + 31) / 32;
     Grow G;
@@ -886,7 +945,8 @@ __global__ void __launch_bounds__(LSD_WARPS * 32, 2) k_lsd_grow(LsdBuffers B, Ls
     G.n_regions = 0; G.n_px = 0;
     for (int i = threadIdx.x; i < nw; i += blockDim.x) Ubits[i] = 0;
     const int n_big = B.ncomp[4 * f], n_small = B.ncomp[4 * f + 1];
-    if (threadIdx.x == 0) { s_next = 0; s_nout = 0; s_nviol = 0; s_alloc = 0; s_nunits = n_big + n_small; }
+    if (threadIdx.x == 0) { s_next = 0; s_nout = 0; s_nviol = 0; s_alloc = 0; s_nunits = n_big + n_small; s_qtail = 0; s_qhead = 0; s_qdone = 0; s_active = LSD_WARPS; }
+    if (threadIdx.x < LSD_JOBQ) s_job_ready[threadIdx.x] = 0;
     __syncthreads();
     const int* L = B.label + fo;
     int *csize = B.csize + fo, *cminx = B.cminx + fo, *cmaxx = B.cmaxx + fo, *cmaxy = B.cmaxy + fo, *cmark = B.cmark + fo;
@@ -896,6 +956,9 @@ __global__ void __launch_bounds__(LSD_WARPS * 32, 2) k_lsd_grow(LsdBuffers B, Ls
     float4* stage = B.stage + (size_t)f * B.stage_cap;
     int* stage_key = B.stage_key + (size_t)f * B.stage_cap;
     int* stage_owner = B.stage_owner + (size_t)f * B.stage_cap;
+    NfaCtx N;
+    N.deg = G.deg; N.W = d.W; N.H = d.H; N.w = d.w; N.h = d.h; N.lane = lane; N.LOG_NT = C.log_nt; N.filter = C.filter; N.length_thres = C.length_thres;
+    N.stage = stage; N.stage_key = stage_key; N.stage_owner = stage_owner; N.stage_cap = B.stage_cap; N.nout = &s_nout;
     long long cyc[4] = {0, 0, 0, 0};  // region_grow, region2rect, refine (with re-growing), rect_improve
     const long long t_begin = clock64();
     int round = 0;
@@ -999,39 +1062,27 @@ __global__ void __launch_bounds__(LSD_WARPS * 32, 2) k_lsd_grow(LsdBuffers B, Ls
                     }
                     if (n < 0) break;
                     if (!good) continue;
-                    t0 = clock64();
-                    const double log_nfa = G.rect_improve(rec);
-                    cyc[3] += clock64() - t0;
-                    if (log_nfa <= 0) continue;
-                    rec.x1 += 0.5; rec.y1 += 0.5; rec.x2 += 0.5; rec.y2 += 0.5;
-                    rec.x1 /= LSD_SCALE; rec.y1 /= LSD_SCALE; rec.x2 /= LSD_SCALE; rec.y2 /= LSD_SCALE;
-                    float e0 = float(rec.x1), e1 = float(rec.y1), e2 = float(rec.x2), e3 = float(rec.y2);
-                    if (C.filter) {
-                        // LSDDetector.cpp:80-101, 219-232 (octaveScale = 1), line_lbd_allclass.cpp:206
-                        const int w_ = d.w, h_ = d.h;
-                        if (e0 < 0) e0 = 0;
-                        if (e0 >= w_) e0 = (float)w_ - 1.0f;
-                        if (e2 < 0) e2 = 0;
-                        if (e2 >= w_) e2 = (float)w_ - 1.0f;
-                        if (e1 < 0) e1 = 0;
-                        if (e1 >= h_) e1 = (float)h_ - 1.0f;
-                        if (e3 < 0) e3 = 0;
-                        if (e3 >= h_) e3 = (float)h_ - 1.0f;
-                        const float thr = 10;
-                        if (((e0 < thr) && (e2 < thr)) || ((e0 > w_ - thr) && (e2 > w_ - thr)) || ((e1 < thr) && (e3 < thr)) ||
-                            ((e1 > h_ - thr) && (e3 > h_ - thr)))
-                            continue;
-                        const double ddx = double(e0 - e2), ddy = double(e1 - e3);
-                        const float len = (float)sqrt(ddx * ddx + ddy * ddy);
-                        if (!(len > C.length_thres)) continue;
-                    }
+                    // ---- hand the rectangle to whichever warp is free (the NFA search does not touch the used map); keep it when the queue is full
+                    int ticket = -1;
                     if (lane == 0) {
-                        const int slot = atomicAdd(&s_nout, 1);
-                        if (slot < B.stage_cap) {
-                            stage[slot] = make_float4(e0, e1, e2, e3);
-                            stage_key[slot] = seed;
-                            stage_owner[slot] = root;
+                        const int tl = *(volatile int*)&s_qtail, dn = *(volatile int*)&s_qdone;
+                        if (tl - dn < LSD_JOBQ - 2 * LSD_WARPS) ticket = atomicAdd(&s_qtail, 1);
+                    }
+                    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+                    if (ticket >= 0) {
+                        NfaJob& jb = s_job[ticket % LSD_JOBQ];
+                        const double rv[12] = {rec.x1, rec.y1, rec.x2, rec.y2, rec.width, rec.x, rec.y, rec.theta, rec.dx, rec.dy, rec.prec, rec.p};
+                        if (lane < 12) jb.r[lane] = rv[lane];
+                        if (lane == 12) { jb.seed = seed; jb.owner = root; }
+                        __syncwarp();
+                        if (lane == 0) {
+                            __threadfence_block();
+                            *(volatile int*)&s_job_ready[ticket % LSD_JOBQ] = ticket + 1;
                         }
+                    } else {
+                        t0 = clock64();
+                        N.finish(rec, seed, root);
+                        cyc[3] += clock64() - t0;
                     }
                 }
                 __syncwarp();
@@ -1041,6 +1092,33 @@ __global__ void __launch_bounds__(LSD_WARPS * 32, 2) k_lsd_grow(LsdBuffers B, Ls
                 viol[2 * k] = root;
                 viol[2 * k + 1] = G.foreign_root;
             }
+        }
+        // ---- no unit left for this warp: serve the rectangle queue until every warp is here and the queue is empty
+        if (lane == 0) atomicSub(&s_active, 1);
+        while (true) {
+            int h = -1;
+            if (lane == 0) {
+                const int act = *(volatile int*)&s_active;  // read before the queue: a producer pushes before it retires
+                const int hd = *(volatile int*)&s_qhead, tl = *(volatile int*)&s_qtail;
+                if (hd < tl) h = atomicCAS(&s_qhead, hd, hd + 1) == hd ? hd : -2;
+                else if (act == 0) h = -3;
+            }
+            h = __shfl_sync(0xffffffffu, h, 0);
+            if (h == -3) break;
+            if (h < 0) { __nanosleep(200); continue; }
+            const int slot = h % LSD_JOBQ;
+            if (lane == 0) while (*(volatile int*)&s_job_ready[slot] != h + 1) __nanosleep(50);
+            __syncwarp();
+            const NfaJob& jb = s_job[slot];
+            LRect rec;
+            rec.x1 = jb.r[0]; rec.y1 = jb.r[1]; rec.x2 = jb.r[2]; rec.y2 = jb.r[3]; rec.width = jb.r[4]; rec.x = jb.r[5]; rec.y = jb.r[6];
+            rec.theta = jb.r[7]; rec.dx = jb.r[8]; rec.dy = jb.r[9]; rec.prec = jb.r[10]; rec.p = jb.r[11];
+            const int jseed = jb.seed, jowner = jb.owner;
+            __syncwarp();
+            if (lane == 0) atomicAdd(&s_qdone, 1);
+            const long long t0 = clock64();
+            N.finish(rec, jseed, jowner);
+            cyc[3] += clock64() - t0;
         }
         __syncthreads();
         const int nv = s_nviol;
@@ -1074,6 +1152,7 @@ __global__ void __launch_bounds__(LSD_WARPS * 32, 2) k_lsd_grow(LsdBuffers B, Ls
             s_next = 0;
             s_nviol = 0;
             s_alloc = 0;
+            s_active = LSD_WARPS;
             atomicAdd(&B.stats[7], 1ull);
             atomicAdd(&B.stats[8], (unsigned long long)nv);
         }
