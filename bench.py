@@ -12,8 +12,9 @@ computes them).  A "scored proposal" is a hypothesis that passes all geometric c
 
 value : inputs resident in HBM, kernels only (prep_lines, score, select, rank, observe [+ NCCL allgather of the
         observation records when N > 1]); CUDA events per step on the launching stream, L2 flushed between steps.
-e2e   : the same metric through csb_detect_batch() with pinned HOST buffers: H2D of frames/boxes/lines/distance maps,
-        the kernels, D2H of the cuboid records, all inside the timed region.
+e2e   : the same metric through the C ABI with pinned HOST buffers, gray frames in (csb_detect_upload_gray / run / download, two contexts
+        pipelined): H2D of frames/boxes/lines/gray images, Canny + distance transform + the scoring kernels, D2H of the cuboid records,
+        all inside the timed region.  e2e_other: the same from caller-computed distance maps, and single blocking calls.
 Multi-GPU: frames shard across ranks (weak scaling, fixed 64 frames per GPU), no data-path collective except the final
 allgather of 128-byte observation records.
 """
@@ -323,9 +324,11 @@ def run_ours(args, rank, local_rank, world):
             r["gpu_ms_distmap"] = float(stx.gpu_ms_distmap)
         return r
 
-    e2e = e2e_pipelined("maps")
+    # headline e2e: gray frames in, cuboids out -- what the reference's detect_cuboid(rgb_img, ...) covers (Canny + distance transform are
+    # inside it, box_proposal_detail.cpp:320-327); the variant that takes caller-computed distance maps is kept next to it
+    e2e = e2e_pipelined("gray")
     e2e_extra = {}
-    for name, fn, mode in (("pipelined_gray", e2e_pipelined, "gray"), ("single_call", e2e_single, "maps"), ("single_call_gray", e2e_single, "gray")):
+    for name, fn, mode in (("pipelined_maps", e2e_pipelined, "maps"), ("single_call", e2e_single, "maps"), ("single_call_gray", e2e_single, "gray")):
         try:
             e2e_extra[name] = fn(mode)
         except Exception as e:
