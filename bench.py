@@ -383,6 +383,23 @@ def run_ours(args, rank, local_rank, world):
             out["ba"] = {"metric": "ba_edges_linearised_per_sec", "value": n_edges / (ba_ms * 1e-3), "unit": "edges/s", "edges": n_edges,
                          "ms_per_linearisation": ba_ms, "config": "config#4: 200 keyframes, 50 cuboids, 4000 EdgeSE3Cuboid + 199 EdgeSE3Expmap, 200 back-to-back linearisations (L2-resident; launch/FP64 bound)",
                          "roofline": {"bound": "hbm", "achieved": ba_ach, "peak": peak, "unit": "GB/s", "frac": ba_ach / peak, "traffic": None}}
+            try:  # closed-form Jacobians (row f-4): same 200 back-to-back linearisations
+                ctx.ba_set_jacobian_mode(True)
+                with torch.cuda.stream(stream):
+                    for _ in range(5):
+                        ctx.ba_run()
+                    torch.cuda.synchronize()
+                    a.record(stream)
+                    for _ in range(reps):
+                        ctx.ba_run()
+                    b.record(stream)
+                    torch.cuda.synchronize()
+                ba_ms_a = a.elapsed_time(b) / reps
+                out["ba"]["analytic_jacobians"] = {"value": n_edges / (ba_ms_a * 1e-3), "unit": "edges/s", "ms_per_linearisation": ba_ms_a}
+            except Exception as e:
+                out["ba"]["analytic_jacobians"] = {"error": str(e)}
+            finally:
+                ctx.ba_set_jacobian_mode(False)
             # Levenberg-Marquardt on the device (row f-3): 5 outer iterations from the same initial estimates, best of 3
             try:
                 best = None

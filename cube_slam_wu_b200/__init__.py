@@ -287,6 +287,10 @@ class Context:
         cams7 = np.ascontiguousarray(cams7, np.float64); cubes10 = np.ascontiguousarray(cubes10, np.float64)
         self._chk(lib().csb_ba_upload_estimates(self._h, _p(cams7), _p(cubes10)))
 
+    def ba_set_jacobian_mode(self, analytic):
+        """csb_ba_set_jacobian_mode(): False = central differences like the reference (default), True = closed form."""
+        self._chk(lib().csb_ba_set_jacobian_mode(self._h, 1 if analytic else 0))
+
     def ba_run(self):
         self._chk(lib().csb_ba_run(self._h))
 

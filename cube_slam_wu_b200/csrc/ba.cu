@@ -28,7 +28,13 @@ namespace csb {
 
 constexpr int LIN_THREADS = 128;  // 8 edges per CTA
 
-template <int TYPE>
+// ANALYTIC: the Jacobian columns of EdgeSE3Cuboid / EdgeSE3Expmap in closed form instead of the reference's 30
+// residual evaluations.  With Delta = (Twc M R_k)^-1 C (k = the yaw variant min_log_error picks) and xi = log(Delta) = e[0:6]:
+//   camera   T <- exp(d) T      : Delta <- exp(Ad_A d) Delta,  A = (M R_k)^-1     =>  de/dd = [ Jl^-1(xi) Ad_A ; 0 ]
+//   cuboid   C <- C exp(d[0:6]) : Delta <- Delta exp(d)                           =>  de/dd = blockdiag( Jl^-1(-xi), I_3 )
+//   odometry e = log(M Ti Tj^-1): de/ddi = Jl^-1(xi) Ad_M,  de/ddj = -Jl^-1(-xi)
+// EdgeSE3CuboidProj keeps central differences.  Validated against the numeric Jacobians (tests/test_ba_gpu.py).
+template <int TYPE, bool ANALYTIC>
 __global__ void __launch_bounds__(LIN_THREADS) k_linearize(BABuffers B, int n_edges, int64_t rec_base, int chi_base, double* Ji_out, double* Jj_out) {
     constexpr int D = EdgeDims<TYPE>::D, Di = EdgeDims<TYPE>::Di, Dj = EdgeDims<TYPE>::Dj, REC = EdgeDims<TYPE>::REC;
     const int tid = blockIdx.x * LIN_THREADS + threadIdx.x;
@@ -67,7 +73,47 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(BABuffers B, int n_ed
 #pragma unroll
     for (int k = 0; k < D; k++) J[k] = 0;
     const double delta = 1e-9, scalar = 1.0 / (2 * delta);
-    if (active) {
+    if (active && ANALYTIC && TYPE != EDGE_PROJ) {
+        double e0[D];
+        SE3 A;  // the fixed left factor of Delta
+        if (TYPE == EDGE_CUBOID) {
+            Cube esti;
+            esti.pose = se3_mul(se3_inverse(x.cam), x.meas_cube.pose);
+            esti.scale = x.meas_cube.scale;
+            SE3 best;
+            cube_min_log_error_k(x.cube, esti, e0, best);  // best = Twc M R_k
+            A = se3_mul(se3_inverse(best), se3_inverse(x.cam));  // (M R_k)^-1 = best^-1 Twc
+        } else {
+            edge_error<TYPE>(x, x.cam, x.cube, x.cam2, e0);
+            A = x.meas_se3;
+        }
+        if (c == 15) {
+#pragma unroll
+            for (int k = 0; k < D; k++) J[k] = e0[k];
+        } else if (c < Di) {
+            if (i_free) {
+                double col[6], o[6];
+                se3_adjoint_col(A, c, col);
+                se3_jl_inv_apply(e0, col, o);
+#pragma unroll
+                for (int k = 0; k < 6; k++) J[k] = o[k];
+            }
+        } else if (c < Di + Dj) {
+            if (j_free) {
+                const int dd = c - Di;
+                if (dd < 6) {
+                    double mxi[6], col[6], o[6];
+#pragma unroll
+                    for (int k = 0; k < 6; k++) { mxi[k] = -e0[k]; col[k] = (k == dd) ? 1.0 : 0.0; }
+                    se3_jl_inv_apply(mxi, col, o);
+#pragma unroll
+                    for (int k = 0; k < 6; k++) J[k] = (TYPE == EDGE_ODOM) ? -o[k] : o[k];
+                } else if (TYPE == EDGE_CUBOID) {
+                    J[dd] = 1.0;  // scale rows: e[6:9] = scale - (swapped) measured scale
+                }
+            }
+        }
+    } else if (active) {
         if (c == 15) {
             edge_error<TYPE>(x, x.cam, x.cube, x.cam2, J);  // J holds the error vector on lane 15
         } else if (c < Di) {
@@ -210,12 +256,20 @@ __global__ void __launch_bounds__(32) k_chi2(const double* edge_chi2, int n, dou
     if (threadIdx.x == 0) *out = s;
 }
 
-cudaError_t ba_launch(const BABuffers& B, bool want_J, cudaStream_t st, int* n_launches) {
+cudaError_t ba_launch(const BABuffers& B, bool want_J, cudaStream_t st, int* n_launches, bool analytic) {
     int L = 0;
     auto grid = [](int n_edges) { return (n_edges * 16 + LIN_THREADS - 1) / LIN_THREADS; };
-    if (B.n_ec) { k_linearize<EDGE_CUBOID><<<grid(B.n_ec), LIN_THREADS, 0, st>>>(B, B.n_ec, 0, 0, want_J ? B.ec_Ji : nullptr, want_J ? B.ec_Jj : nullptr); L++; }
-    if (B.n_ep) { k_linearize<EDGE_PROJ><<<grid(B.n_ep), LIN_THREADS, 0, st>>>(B, B.n_ep, (int64_t)132 * B.n_ec, B.n_ec, want_J ? B.ep_Ji : nullptr, want_J ? B.ep_Jj : nullptr); L++; }
-    if (B.n_eo) { k_linearize<EDGE_ODOM><<<grid(B.n_eo), LIN_THREADS, 0, st>>>(B, B.n_eo, (int64_t)132 * (B.n_ec + B.n_ep), B.n_ec + B.n_ep, want_J ? B.eo_Ji : nullptr, want_J ? B.eo_Jj : nullptr); L++; }
+    if (B.n_ec) {
+        if (analytic) k_linearize<EDGE_CUBOID, true><<<grid(B.n_ec), LIN_THREADS, 0, st>>>(B, B.n_ec, 0, 0, want_J ? B.ec_Ji : nullptr, want_J ? B.ec_Jj : nullptr);
+        else k_linearize<EDGE_CUBOID, false><<<grid(B.n_ec), LIN_THREADS, 0, st>>>(B, B.n_ec, 0, 0, want_J ? B.ec_Ji : nullptr, want_J ? B.ec_Jj : nullptr);
+        L++;
+    }
+    if (B.n_ep) { k_linearize<EDGE_PROJ, false><<<grid(B.n_ep), LIN_THREADS, 0, st>>>(B, B.n_ep, (int64_t)132 * B.n_ec, B.n_ec, want_J ? B.ep_Ji : nullptr, want_J ? B.ep_Jj : nullptr); L++; }
+    if (B.n_eo) {
+        if (analytic) k_linearize<EDGE_ODOM, true><<<grid(B.n_eo), LIN_THREADS, 0, st>>>(B, B.n_eo, (int64_t)132 * (B.n_ec + B.n_ep), B.n_ec + B.n_ep, want_J ? B.eo_Ji : nullptr, want_J ? B.eo_Jj : nullptr);
+        else k_linearize<EDGE_ODOM, false><<<grid(B.n_eo), LIN_THREADS, 0, st>>>(B, B.n_eo, (int64_t)132 * (B.n_ec + B.n_ep), B.n_ec + B.n_ep, want_J ? B.eo_Ji : nullptr, want_J ? B.eo_Jj : nullptr);
+        L++;
+    }
     if (B.n_cam) { k_gather<<<(B.n_cam * 32 + 127) / 128, 128, 0, st>>>(B, B.n_cam, 6, B.cam_adj_ptr, B.cam_adj_H, B.cam_adj_b, B.H_cam, B.b_cam); L++; }
     if (B.n_cube) { k_gather<<<(B.n_cube * 32 + 127) / 128, 128, 0, st>>>(B, B.n_cube, 9, B.cube_adj_ptr, B.cube_adj_H, B.cube_adj_b, B.H_cube, B.b_cube); L++; }
     k_chi2<<<1, 32, 0, st>>>(B.edge_chi2, B.n_ec + B.n_ep + B.n_eo, B.chi2); L++;
@@ -354,8 +408,14 @@ static int ba_run_impl(csb_context* c, bool want_J) {
     BAState& s = c->ba;
     if (!s.has_graph || !s.has_estimates) { c->err = "csb_ba_run before graph/estimates"; return CSB_ERR_STATE; }
     CSB_CUDA(c, cudaSetDevice(c->device));
-    CSB_CUDA(c, ba_launch(s.B, want_J, c->stream, &s.launches_last));
+    CSB_CUDA(c, ba_launch(s.B, want_J, c->stream, &s.launches_last, s.analytic));
     s.ran = true;
+    return CSB_OK;
+}
+
+int csb_ba_set_jacobian_mode(csb_context* c, int mode) {
+    if (!c || (mode != CSB_BA_JACOBIAN_NUMERIC && mode != CSB_BA_JACOBIAN_ANALYTIC)) return CSB_ERR_INVALID;
+    c->ba.analytic = mode == CSB_BA_JACOBIAN_ANALYTIC;
     return CSB_OK;
 }
 

@@ -36,6 +36,7 @@ struct HostGraph {
 
 struct BAState {
     bool has_graph = false, has_estimates = false, ran = false;
+    bool analytic = false;  // csb_ba_set_jacobian_mode
     HostGraph host;
     void* solver = nullptr;  // SolveState of ba_solve.cu
     int n_cam = 0, n_cube = 0, n_ec = 0, n_ep = 0, n_eo = 0;
@@ -46,6 +47,6 @@ struct BAState {
 
 void ba_release(BAState& s);
 void ba_solver_release(BAState& s);
-cudaError_t ba_launch(const BABuffers& B, bool want_jacobians, cudaStream_t st, int* n_launches);
+cudaError_t ba_launch(const BABuffers& B, bool want_jacobians, cudaStream_t st, int* n_launches, bool analytic);
 
 }  // namespace csb

@@ -48,6 +48,80 @@ __device__ __forceinline__ void cube_min_log_error(const Cube& self, const Cube&
         }
     }
 }
+// the same, also reporting which of the four yaw variants won and the measurement pose it was compared with (analytic Jacobians)
+__device__ __forceinline__ void cube_min_log_error_k(const Cube& self, const Cube& newone, double* res, SE3& best_pose) {
+    double best_n = 0;
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) {
+        double yaw_angle = (double)(i - 1) * M_PI / 2.0;
+        Cube rc;
+        SE3 rot = se3_make(Quat{cos(yaw_angle * 0.5), 0, 0, sin(yaw_angle * 0.5)}, V3{0, 0, 0});
+        rc.pose = se3_mul(newone.pose, rot);
+        rc.scale = newone.scale;
+        if ((yaw_angle == M_PI / 2.0) || (yaw_angle == -M_PI / 2.0) || (yaw_angle == 3 * M_PI / 2.0)) { double t = rc.scale.x; rc.scale.x = rc.scale.y; rc.scale.y = t; }
+        double e[9];
+        cube_log_error(self, rc, e);
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 9; k++) s += e[k] * e[k];
+        double n = sqrt(s);
+        if (i == 0 || n < best_n) {
+            best_n = n;
+            best_pose = rc.pose;
+#pragma unroll
+            for (int k = 0; k < 9; k++) res[k] = e[k];
+        }
+    }
+}
+
+// ---- closed-form derivatives of the SE(3) logarithm ----------------------------------------------------------
+// g2o orders a tangent vector as [omega (rotation); upsilon (translation)] (se3quat.h:230-323).  For xi = log(T):
+//   log(exp(eps) T) = xi + Jl^-1(xi) eps + O(eps^2),   log(T exp(eps)) = xi + Jl^-1(-xi) eps + O(eps^2)
+//   Jl^-1(xi) = [ J^-1 0 ; -J^-1 Q J^-1  J^-1 ]  with J the SO(3) left Jacobian of omega and Q(upsilon, omega) as in Barfoot,
+//   "State Estimation for Robotics", eq. 7.86 (there in [rho; phi] order).  se3_jl_inv_apply returns Jl^-1(xi) v.
+__device__ __forceinline__ M3 m3_add(const M3& a, const M3& b, double sb) { M3 r; for (int i = 0; i < 9; i++) r.m[i] = a.m[i] + sb * b.m[i]; return r; }
+__device__ __forceinline__ void se3_jl_inv_apply(const double* xi, const double* v, double* out) {
+    const V3 w{xi[0], xi[1], xi[2]}, u{xi[3], xi[4], xi[5]};
+    const M3 W = skew(w), P = skew(u);
+    const double th2 = w.x * w.x + w.y * w.y + w.z * w.z, th = sqrt(th2);
+    const M3 WW = mul(W, W), WP = mul(W, P), PW = mul(P, W), WPW = mul(WP, W);
+    M3 Ji, Q;
+    const M3 t1 = m3_add(m3_add(WP, PW, 1.0), WPW, 1.0);                       // WP + PW + WPW
+    const M3 t2 = m3_add(m3_add(mul(WW, P), mul(P, WW), 1.0), WPW, -3.0);      // WWP + PWW - 3 WPW
+    const M3 t3 = m3_add(mul(WPW, W), mul(W, WPW), 1.0);                        // WPWW + WWPW
+    if (th < 1e-4) {
+        Ji = m3_add(m3_add(identity3(), W, -0.5), WW, 1.0 / 12.0);
+        Q = m3_add(m3_add(m3_add(M3{{0, 0, 0, 0, 0, 0, 0, 0, 0}}, P, 0.5), t1, 1.0 / 6.0), t2, -1.0 / 24.0);
+    } else {
+        const double half = 0.5 * th, cot = half / tan(half);
+        // J^-1 = cot I + (1 - cot) a a^T - (theta / 2) a^  with a = w / theta;  a a^T = I + a^ a^
+        Ji = m3_add(m3_add(identity3(), WW, (1.0 - cot) / th2), W, -0.5);
+        const double sn = sin(th), cs = cos(th);
+        const double c1 = (th - sn) / (th2 * th);
+        const double c2 = (1.0 - 0.5 * th2 - cs) / (th2 * th2);
+        const double c3 = 0.5 * (c2 - 3.0 * (th - sn - th2 * th / 6.0) / (th2 * th2 * th));
+        Q = m3_add(m3_add(m3_add(m3_add(M3{{0, 0, 0, 0, 0, 0, 0, 0, 0}}, P, 0.5), t1, c1), t2, -c2), t3, -c3);
+    }
+    const V3 a = mul(Ji, V3{v[0], v[1], v[2]});
+    const V3 b = mul(Ji, V3{v[3], v[4], v[5]});
+    const V3 qa = mul(Ji, mul(Q, a));
+    out[0] = a.x; out[1] = a.y; out[2] = a.z;
+    out[3] = b.x - qa.x; out[4] = b.y - qa.y; out[5] = b.z - qa.z;
+}
+// column c of Ad_T = [ R 0 ; t^ R  R ]  (T exp(x) T^-1 = exp(Ad_T x))
+__device__ __forceinline__ void se3_adjoint_col(const SE3& T, int c, double* col) {
+    const M3 R = quat_to_rot(T.r);
+    if (c < 3) {
+        const V3 r{R.m[c], R.m[3 + c], R.m[6 + c]};
+        const V3 tr = cross(T.t, r);
+        col[0] = r.x; col[1] = r.y; col[2] = r.z; col[3] = tr.x; col[4] = tr.y; col[5] = tr.z;
+    } else {
+        const int k = c - 3;
+        col[0] = col[1] = col[2] = 0.0;
+        col[3] = R.m[k]; col[4] = R.m[3 + k]; col[5] = R.m[6 + k];
+    }
+}
+
 // projectOntoImageBbox :156-197
 __device__ __forceinline__ void cube_project_bbox(const Cube& c, const SE3& Tcw, const double* K, double* out) {
     const M3 R = quat_to_rot(c.pose.r);

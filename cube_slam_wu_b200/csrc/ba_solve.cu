@@ -542,7 +542,7 @@ extern "C" int csb_ba_optimize(csb_context* c, int iterations, double* cams7_out
     const int tiles = V.ld / NB;
     for (int it = 0; it < iterations; it++) {
         int nl = 0;
-        CSB_CUDA(c, ba_launch(B, false, sm, &nl));  // computeActiveErrors + buildSystem at the current estimates
+        CSB_CUDA(c, ba_launch(B, false, sm, &nl, c->ba.analytic));  // computeActiveErrors + buildSystem at the current estimates
         launches += nl;
         if (it == 0) { k_max_diag<<<1, 32, 0, sm>>>(B, V); launches++; }
         double h2[2];

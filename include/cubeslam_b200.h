@@ -210,6 +210,15 @@ int csb_ba_upload_estimates(csb_context* ctx, const double* cams7, const double*
 int csb_ba_run(csb_context* ctx);
 int csb_ba_download(csb_context* ctx, const csb_ba_output* out);
 
+/* How the Jacobians of EdgeSE3Cuboid and EdgeSE3Expmap are obtained.  NUMERIC (default) is the reference's own
+ * definition: BaseBinaryEdge::linearizeOplus, central differences with delta = 1e-9 (base_binary_edge.hpp:130-205; upstream's exact
+ * linearizeOplus is commented out, types_six_dof_expmap.h:141).  ANALYTIC evaluates the closed form (derivative of the SE(3) logarithm,
+ * the yaw variant chosen by cuboid::min_log_error held fixed); it agrees with NUMERIC to the latter's round-off (~1e-7 relative).
+ * EdgeSE3CuboidProj always uses central differences.  Applies to csb_ba_linearize / csb_ba_run / csb_ba_optimize. */
+#define CSB_BA_JACOBIAN_NUMERIC 0
+#define CSB_BA_JACOBIAN_ANALYTIC 1
+int csb_ba_set_jacobian_mode(csb_context* ctx, int mode);
+
 /* SparseOptimizer::optimize(iterations) with OptimizationAlgorithmLevenberg on the device (replaces
  * Thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.cpp:61-189 + block_solver.hpp:353-486 + linear_solver_dense.h:65-113
  * as configured at object_slam/src/main_obj.cpp:512-517, 803).  Works on the estimates uploaded with csb_ba_upload_estimates();

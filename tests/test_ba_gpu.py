@@ -131,3 +131,50 @@ def tum_graph(d, optimise_each_frame=True):
     return dict(cams7=np.array(cams), cubes10=cube.reshape(1, 10), cam_fixed=np.array(fixed, np.int32), cube_fixed=np.zeros(1, np.int32),
                 ec=(np.array(ec[0], np.int32), np.array(ec[1], np.int32), np.array(ec[2]), np.array(ec[3])), ep=None,
                 eo=(np.array(eo[0], np.int32), np.array(eo[1], np.int32), np.array(eo[2]).reshape(-1, 7), np.array(eo[3]).reshape(-1, 36)))
+
+
+def test_analytic_jacobians_match_numeric(ctx):
+    """closed-form Jacobians of EdgeSE3Cuboid / EdgeSE3Expmap (csb_ba_set_jacobian_mode) against the reference's
+    definition, the delta = 1e-9 central differences (oracle, base_binary_edge.hpp:130-205).  Bar: 1e-4 relative to the block scale
+    (north star); the numeric Jacobians themselves carry ~1e-7 of round-off.  Residuals and chi2 do not depend on the mode."""
+    from cube_slam_wu_b200 import synth
+    for g in (synth.make_ba_graph(n_cam=12, n_cube=3, obs_per_cube=6, seed=4), synth.make_ba_graph()):
+        ctx.ba_set_graph(g["cam_fixed"], g["cube_fixed"], ec=g["ec"], ep=g["ep"], eo=g["eo"])
+        E = O.ba_edges(ec=g["ec"], ep=g["ep"], eo=g["eo"])
+        ora = O.ba_linearize(g["cams7"], g["cam_fixed"], g["cubes10"], g["cube_fixed"], E)
+        try:
+            ctx.ba_set_jacobian_mode(True)
+            ana = ctx.ba_linearize(g["cams7"], g["cubes10"], jacobians=True)
+        finally:
+            ctx.ba_set_jacobian_mode(False)
+        num = ctx.ba_linearize(g["cams7"], g["cubes10"], jacobians=True)
+        worst = 0.0
+        for k in ("ec_err", "eo_err"):
+            assert np.array_equal(ana[k], num[k])
+        for k in ("ec_Ji", "ec_Jj", "eo_Ji", "eo_Jj", "H_cam", "b_cam", "H_cube", "b_cube", "ec_Hij", "eo_Hij"):
+            scale = max(1.0, np.abs(ora[k]).max())
+            d = np.abs(ana[k] - ora[k]).max() / scale
+            assert d <= H.TOL_NORTH_STAR, "%s: analytic vs the reference's numeric Jacobians differ by %g of the block scale" % (k, d)
+            worst = max(worst, d)
+        assert worst <= 5e-6, worst  # observed ~3e-7: the round-off of the central differences
+        # fixed vertices: untouched in both modes
+        assert np.all(ana["H_cam"][0] == 0) and np.all(ana["b_cam"][0] == 0)
+        print("analytic vs numeric Jacobians: worst %.3g of the block scale" % worst)
+
+
+def test_analytic_mode_optimizes_to_the_same_point(ctx):
+    from cube_slam_wu_b200 import synth
+    g = synth.make_ba_graph(n_cam=40, n_cube=8, obs_per_cube=20, seed=9)
+    ctx.ba_set_graph(g["cam_fixed"], g["cube_fixed"], ec=g["ec"], ep=g["ep"], eo=g["eo"])
+    res = []
+    for analytic in (False, True):
+        try:
+            ctx.ba_set_jacobian_mode(analytic)
+            ctx.ba_upload_estimates(g["cams7"], g["cubes10"])
+            res.append(ctx.ba_optimize(5))
+        finally:
+            ctx.ba_set_jacobian_mode(False)
+    (c0, q0, s0), (c1, q1, s1) = res
+    assert s0.iterations == s1.iterations
+    assert abs(s0.chi2 - s1.chi2) <= 1e-5 * max(1.0, s0.chi2)
+    assert np.abs(c0 - c1).max() < 1e-5 and np.abs(q0 - q1).max() < 1e-5
