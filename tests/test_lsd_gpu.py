@@ -122,3 +122,15 @@ def test_reference_golden_vector_on_gpu(ctx, csb, oracle):
     ref = d["ref_lines"]
     assert lines[0].shape == ref.shape
     assert np.abs(lines[0].astype(np.float64) - ref).max() < 2e-3
+
+
+def test_full_hd_frame_and_tiny_frames(ctx, csb, oracle):
+    from cube_slam_wu_b200 import synth
+    big = synth.make_lsd_frames(1, 1920, 1080, seed=51, n_polys=30, n_lines=60)
+    lines, st, worst = _check(ctx, oracle, big)   # used bitmap = 166 KB of shared memory
+    assert st.n_lines > 200
+    for (w, h) in ((8, 8), (9, 33), (40, 8)):
+        tiny = np.random.default_rng(w * h).integers(0, 256, (2, h, w)).astype(np.uint8)
+        _check(ctx, oracle, tiny, filter=False)
+    with pytest.raises(csb.CsbError):
+        ctx.lsd_detect_batch(np.zeros((1, 4, 4), np.uint8))   # below the 8 x 8 minimum
