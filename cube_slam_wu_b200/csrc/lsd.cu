@@ -918,11 +918,14 @@ struct NfaJob {
     int seed, owner;
 };
 
-constexpr int LSD_WARPS = 8;  // 8 warps x <=128 registers: two CTAs (frames) per SM
+// Warps per frame: 8 (two frames per SM; the idle ones serve the rectangle queue) while every frame of the batch fits on the GPU at once,
+// 4 (four frames per SM) for larger batches, where residency -- not the latency of one frame -- sets the throughput.
+constexpr int LSD_WARPS_MAX = 8;
 constexpr int LSD_WARP_SMEM = 96 * sizeof(double) + LSD_RING * sizeof(uint32_t);  // per warp: staging of the ordered sums + queue ring
 constexpr int LSD_MAX_ROUNDS = 12;  // merge rounds before the rest of the frame is redone as one unit
 
-__global__ void __launch_bounds__(LSD_WARPS * 32, 2) k_lsd_grow(LsdBuffers B, LsdDims d, LsdConst C) {
+template <int LSD_WARPS>
+__global__ void __launch_bounds__(LSD_WARPS * 32, 512 / (LSD_WARPS * 32)) k_lsd_grow(LsdBuffers B, LsdDims d, LsdConst C) {
     extern __shared__ __align__(16) unsigned char lsd_smem[];
     __shared__ int s_next, s_nout, s_nviol, s_nunits, s_alloc, s_qtail, s_qhead, s_qdone, s_active;
     __shared__ NfaJob s_job[LSD_JOBQ];
@@ -1066,7 +1069,7 @@ __global__ void __launch_bounds__(LSD_WARPS * 32, 2) k_lsd_grow(LsdBuffers B, Ls
                     int ticket = -1;
                     if (lane == 0) {
                         const int tl = *(volatile int*)&s_qtail, dn = *(volatile int*)&s_qdone;
-                        if (tl - dn < LSD_JOBQ - 2 * LSD_WARPS) ticket = atomicAdd(&s_qtail, 1);
+                        if (tl - dn < LSD_JOBQ - 2 * LSD_WARPS_MAX) ticket = atomicAdd(&s_qtail, 1);
                     }
                     ticket = __shfl_sync(0xffffffffu, ticket, 0);
                     if (ticket >= 0) {
@@ -1289,7 +1292,7 @@ static int lsd_prepare(csb_context* c, int n_frames, int width, int height, cons
     C.length_thres = params->line_length_thres;
     C.filter = params->filter;
     C.max_lines = params->max_lines;
-    s.grow_smem = (size_t)LSD_WARPS * LSD_WARP_SMEM + (size_t)((d.W * d.H + 31) / 32) * sizeof(uint32_t);
+    s.grow_smem = (size_t)LSD_WARPS_MAX * LSD_WARP_SMEM + (size_t)((d.W * d.H + 31) / 32) * sizeof(uint32_t);
     s.stage_cap = std::max((d.W * d.H) / 4, params->max_lines);
     if (s.grow_smem > (size_t)c->max_smem_optin) {
         c->err = "csb_lsd: frame too large for the shared-memory used/defined bitmaps";
@@ -1310,7 +1313,8 @@ static int lsd_prepare(csb_context* c, int n_frames, int width, int height, cons
     CSB_CUDA(c, s.d_lines.ensure((size_t)n_frames * params->max_lines * 16));
     CSB_CUDA(c, s.d_nlines.ensure((size_t)n_frames * 4));
     CSB_CUDA(c, s.d_stats.ensure(128));
-    CSB_CUDA(c, cudaFuncSetAttribute(k_lsd_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.grow_smem));
+    CSB_CUDA(c, cudaFuncSetAttribute(k_lsd_grow<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.grow_smem));
+    CSB_CUDA(c, cudaFuncSetAttribute(k_lsd_grow<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.grow_smem));
     return CSB_OK;
 }
 
@@ -1358,7 +1362,9 @@ int csb_lsd_run(csb_context* c, int timed) {
     k_lsd_contact<<<pg, pb, 0, st>>>(B, d);
     k_lsd_units<<<pg, pb, 0, st>>>(B, d, s.C.min_reg_size);
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[1], st));
-    k_lsd_grow<<<d.n_frames, LSD_WARPS * 32, s.grow_smem, st>>>(B, d, s.C);
+    const size_t ubytes = (size_t)((d.W * d.H + 31) / 32) * sizeof(uint32_t);
+    if (d.n_frames <= 2 * c->num_sms) k_lsd_grow<8><<<d.n_frames, 256, 8 * LSD_WARP_SMEM + ubytes, st>>>(B, d, s.C);
+    else k_lsd_grow<4><<<d.n_frames, 128, 4 * LSD_WARP_SMEM + ubytes, st>>>(B, d, s.C);
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[2], st));
     CSB_CUDA(c, cudaGetLastError());
     s.launches_last = 7;
