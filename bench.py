@@ -10,8 +10,9 @@ configurations, synthetic inputs (seeded; distance maps by cv2.Canny + cv2.dista
 computes them).  A "scored proposal" is a hypothesis that passes all geometric checks and receives both scores
 (a row of all_configs_error_one_objH); the enumerated-hypothesis rate is reported next to it.
 
-value : inputs resident in HBM, kernels only (prep_lines, score, select, rank, observe [+ NCCL allgather of the
-        observation records when N > 1]); CUDA events per step on the launching stream, L2 flushed between steps.
+value : inputs resident in HBM, kernels only (prep_lines, vp_support, score, select, recover, rank, observe [+ NCCL allgather of the
+        observation records when N > 1]); K steps issued round-robin over 4 contexts (streams) with their own resident inputs, timed
+        on the device between one start and one end event.  `serial` holds the one-step-at-a-time latency (L2 flushed).
 e2e   : the same metric through the C ABI with pinned HOST buffers, gray frames in (csb_detect_upload_gray / run / download, two contexts
         pipelined): H2D of frames/boxes/lines/gray images, Canny + distance transform + the scoring kernels, D2H of the cuboid records,
         all inside the timed region.  e2e_other: the same from caller-computed distance maps, and single blocking calls.
@@ -40,6 +41,8 @@ FRAMES_PER_GPU = 64
 BOXES_PER_FRAME = 8
 ALGO_BYTES_PER_PROPOSAL = 550.0   # SURVEY.md 8d contract figure: 596 B (config 1) / 508 B (config 2), 0.55 KB mean
 ALGO_BYTES_PER_EDGE = 1856.0      # EdgeSE3Cuboid, fused (Jacobian not materialised)
+E2E_DEPTH = 4       # contexts (streams) the end-to-end pipeline keeps in flight
+VALUE_DEPTH = 4     # contexts (streams) with resident inputs used round-robin for `value`
 LSD_FRAMES, LSD_W, LSD_H = 256, 640, 480  # BASELINE config #3
 # streaming stages of the line detector: 1 B read per source pixel, then the reference's two FP64 maps (gradient norm + level-line angle) per scaled pixel
 LSD_ALGO_BYTES_PER_FRAME = LSD_W * LSD_H + 16.0 * round(LSD_W * 0.8) * round(LSD_H * 0.8)
@@ -49,7 +52,8 @@ def workload_config(n_gpus):
     return {"workload": "config#2 batched proposal scoring: %d KITTI-shape frames x %d boxes per GPU, roll/pitch sampling on, both configs"
                         % (FRAMES_PER_GPU, BOXES_PER_FRAME),
             "frames_per_gpu": FRAMES_PER_GPU, "boxes_per_frame": BOXES_PER_FRAME, "img": "1242x375", "sharding": "frames over %d GPU(s)" % n_gpus,
-            "l2": "256 MiB buffer written between timed steps (flush), excluded from the timed region"}
+            "contexts_in_flight": VALUE_DEPTH,
+            "l2": "steps alternate over %d resident copies of the inputs (%d x 70 MB > 126 MB L2); the single-stream latency figures flush a 256 MiB buffer between steps" % (VALUE_DEPTH, VALUE_DEPTH)}
 
 
 def measured_peaks():
@@ -107,7 +111,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
-                "window": "warm-up + timed steps (under load)"}
+                "window": "warm-up + timed regions of value / serial / e2e (under load)"}
 
 
 def build_batch(rank):
@@ -218,19 +222,60 @@ def run_ours(args, rank, local_rank, world):
         if world > 1:
             dist.all_gather_into_tensor(obs_all, obs)
 
+    # (1) throughput ("value"): VALUE_DEPTH contexts, each with its own stream and its own resident copy of the batch (D x 70 MB > L2, so
+    #     consecutive steps never find their inputs in L2); step i runs on context i % D, so the latency-bound kernels of one step
+    #     (line merging, selection replay, ranking) overlap with the scoring kernel of another.  Device-timed: one start event that every
+    #     stream waits for, one end event after all streams have joined.
+    D = max(1, int(os.environ.get("CSB_VALUE_DEPTH", VALUE_DEPTH)))
+    streams = [stream] + [torch.cuda.Stream() for _ in range(D - 1)]
+    ctxs = [ctx] + [csb.Context(local_rank, stream=s_.cuda_stream) for s_ in streams[1:]]
+    for c_ in ctxs[1:]:
+        c_.detect_upload(frames, boxes, lines, tasks, n_tasks, maps, n_map, params)
+    obs_d = [obs] + [torch.zeros_like(obs) for _ in range(D - 1)]
+    obs_all_d = [obs_all] + [torch.zeros_like(obs_all) if world > 1 else None for _ in range(D - 1)]
+
+    def step_d(i):
+        k = i % D
+        with torch.cuda.stream(streams[k]):
+            ctxs[k].detect_run(timed=False)
+            rc = L.csb_detect_observations_device(ctxs[k]._h, C.c_void_p(obs_d[k].data_ptr()))
+            assert rc == 0
+            if world > 1:
+                dist.all_gather_into_tensor(obs_all_d[k], obs_d[k])
+
+    sampler.mark_begin()
+    for i in range(max(args.warmup, D)):
+        step_d(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev_start.record(streams[0])
+    for s_ in streams[1:]:
+        s_.wait_event(ev_start)
+    for i in range(args.steps):
+        step_d(i)
+    for s_ in streams[1:]:
+        e_ = torch.cuda.Event()
+        e_.record(s_)
+        streams[0].wait_event(e_)
+    ev_end.record(streams[0])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    ms_total = ev_start.elapsed_time(ev_end)
+    for c_ in ctxs[1:]:
+        c_.close()
+
+    # (2) latency of one step, serialised on one stream with the L2 flushed in between: per-kernel CUDA events (roofline of k_score)
+    n_lat = min(args.steps, 10)
     with torch.cuda.stream(stream):
-        sampler.mark_begin()
-        for _ in range(args.warmup):
-            flush.zero_()
-            step(False)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_lat)]
         score_ms = []
-        t_wall0 = time.perf_counter()
-        for i in range(args.steps):
+        for i in range(n_lat):
             flush.zero_()
             ev[i][0].record(stream)
             step(True)
@@ -239,12 +284,7 @@ def run_ours(args, rank, local_rank, world):
             cub, ncub, st = ctx.detect_download()
             score_ms.append((st.gpu_ms_prep, st.gpu_ms_score, st.gpu_ms_select, st.gpu_ms_rank, st.gpu_ms_recover))
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t_wall = time.perf_counter() - t_wall0
-        sampler.mark_end()
-        clocks = sampler.stop()
-    ms_total = sum(a.elapsed_time(b) for a, b in ev)
+    serial_ms = sum(a.elapsed_time(b) for a, b in ev) / n_lat
     n_scored, n_enum = int(st.n_scored), int(st.n_enumerated)
     t = torch.tensor([ms_total, float(n_scored), float(n_enum)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -264,7 +304,8 @@ def run_ours(args, rank, local_rank, world):
     e2e_warm = args.warmup + 10  # PCIe link / pinned-path warm-up on top of the requested W (untimed)
     tg, gray = pinned(np.concatenate([im.ravel() for im in batch["images"]]).astype(np.uint8))
     keep.append(tg)
-    pipe_ctx = [csb.Context(local_rank), csb.Context(local_rank)]
+    depth = max(2, int(os.environ.get("CSB_E2E_DEPTH", E2E_DEPTH)))
+    pipe_ctx = [csb.Context(local_rank) for _ in range(depth)]
 
     def reduce_time(total_s, scored):
         tt = torch.tensor([total_s, float(scored)], dtype=torch.float64, device="cuda")
@@ -282,25 +323,30 @@ def run_ours(args, rank, local_rank, world):
                 c.detect_upload(frames, boxes, lines, tasks, n_tasks, maps, n_map, params)
             c.detect_run(timed=False)
         stx = None
-        for i in range(e2e_warm):
-            submit(pipe_ctx[i % 2])
-            if i >= 1:
-                pipe_ctx[(i - 1) % 2].detect_download()
-        pipe_ctx[(e2e_warm - 1) % 2].detect_download()
+        D = depth
+
+        def run(n_steps):
+            # step i is submitted to context i % D; before a context is reused its previous step (i - D) is downloaded, so D - 1 steps
+            # are in flight behind the one being submitted and every step's results are read back exactly once
+            st_last = None
+            for i in range(n_steps):
+                if i >= D:
+                    _, _, st_last = pipe_ctx[i % D].detect_download()
+                submit(pipe_ctx[i % D])
+            for i in range(max(n_steps - D, 0), n_steps):
+                _, _, st_last = pipe_ctx[i % D].detect_download()
+            return st_last
+        run(e2e_warm)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        for i in range(args.steps):
-            submit(pipe_ctx[i % 2])
-            if i >= 1:
-                _, _, stx = pipe_ctx[(i - 1) % 2].detect_download()
-        _, _, stx = pipe_ctx[(args.steps - 1) % 2].detect_download()
+        stx = run(args.steps)
         torch.cuda.synchronize()
         total = time.perf_counter() - t0
         total, scored = reduce_time(total, stx.n_scored)
         return {"value": scored * args.steps / total, "unit": UNIT, "h2d_bytes_per_step": int(stx.h2d_bytes), "d2h_bytes_per_step": int(stx.d2h_bytes),
-                "ms_per_step": 1e3 * total / args.steps, "mode": "pipelined, 2 contexts (upload+run of step i+1 queued while step i computes), inputs: " +
+                "ms_per_step": 1e3 * total / args.steps, "mode": "pipelined, %d contexts (upload+run of the next steps queued while a step computes), inputs: " % D +
                 ("gray frames (Canny + distance transform on the GPU)" if mode == "gray" else "caller-computed distance maps")}
 
     def e2e_single(mode):
@@ -334,6 +380,8 @@ def run_ours(args, rank, local_rank, world):
         except Exception as e:
             e2e_extra[name] = {"error": str(e)}
     del pipe_ctx
+    sampler.mark_end()  # the sampled window covers the timed regions of value, serial and e2e (all under load)
+    clocks = sampler.stop()
 
     out = None
     if rank == 0:
@@ -359,6 +407,8 @@ def run_ours(args, rank, local_rank, world):
                "scored_per_step_per_gpu": n_scored, "enumerated_per_step_per_gpu": n_enum,
                "kernel_ms": {"prep_lines": float(np.mean([s[0] for s in score_ms])), "score": k_ms, "select": float(np.mean([s[2] for s in score_ms])),
                              "recover": float(np.mean([s[4] for s in score_ms])), "rank": float(np.mean([s[3] for s in score_ms]))},
+               "serial": {"ms_per_step": serial_ms, "value": n_scored / (serial_ms * 1e-3), "unit": UNIT,
+                          "note": "one step at a time on one stream, L2 flushed between steps (rank 0)"},
                "wall_s_timed_region": t_wall}
 
         # ---- secondary metric: BA edges linearised per second (config #4), resident, back to back
