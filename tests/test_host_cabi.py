@@ -72,3 +72,29 @@ def test_no_cpu_fallback(csb):
     with pytest.raises(csb.CsbError) as e:
         csb.Context(0)
     assert e.value.code == csb.CSB_ERR_CUDA
+
+
+def test_null_context_is_rejected_everywhere(csb):
+    """Entry points added for the line detector and the Jacobian mode: a NULL context is an argument error, not a crash, with or without a GPU."""
+    L = csb.lib()
+    p = csb.LsdParams(15.0, 1, 16, 0)
+    img = np.zeros((1, 16, 16), np.uint8)
+    out = np.zeros((1, 16, 4), np.float32); n = np.zeros(1, np.int32)
+    assert L.csb_lsd_detect_batch(None, img.ctypes.data_as(C.c_void_p), 1, 16, 16, C.byref(p), out.ctypes.data_as(C.c_void_p), n.ctypes.data_as(C.c_void_p), None) == csb.CSB_ERR_INVALID
+    assert L.csb_lsd_upload(None, img.ctypes.data_as(C.c_void_p), 1, 16, 16, C.byref(p)) == csb.CSB_ERR_INVALID
+    assert L.csb_lsd_run(None, 0) == csb.CSB_ERR_STATE
+    assert L.csb_lsd_download(None, None, None, None) == csb.CSB_ERR_STATE
+    assert L.csb_ba_set_jacobian_mode(None, 1) == csb.CSB_ERR_INVALID
+    assert C.sizeof(csb.LsdParams) == 16 and C.sizeof(csb.LsdStats) == 5 * 8 + 4 * 4 + 2 * 4 + 7 * 8
+
+
+def test_line_lbd_mirror_refuses_unported_modes(csb):
+    class _Ctx:  # no device needed: the checks happen before any call into the library
+        pass
+    with pytest.raises(csb.CsbError):
+        csb.line_lbd_detect(_Ctx(), numoctaves=2)
+    d = csb.line_lbd_detect(_Ctx())
+    assert d.use_LSD is True and d.line_length_thres == 50.0  # the reference's default threshold (line_lbd_allclass.cpp:126)
+    d.use_LSD = False
+    with pytest.raises(csb.CsbError):
+        d.detect_filter_lines(np.zeros((8, 8), np.uint8))
