@@ -11,7 +11,7 @@ computes them).  A "scored proposal" is a hypothesis that passes all geometric c
 (a row of all_configs_error_one_objH); the enumerated-hypothesis rate is reported next to it.
 
 value : inputs resident in HBM, kernels only (prep_lines, vp_support, score, select, recover, rank, observe [+ NCCL allgather of the
-        observation records when N > 1]); K steps issued round-robin over 4 contexts (streams) with their own resident inputs, timed
+        observation records when N > 1]); K steps issued round-robin over 6 contexts (streams) with their own resident inputs, timed
         on the device between one start and one end event.  `serial` holds the one-step-at-a-time latency (L2 flushed).
 e2e   : the same metric through the C ABI with pinned HOST buffers, gray frames in (csb_detect_upload_gray / run / download, two contexts
         pipelined): H2D of frames/boxes/lines/gray images, Canny + distance transform + the scoring kernels, D2H of the cuboid records,
@@ -41,8 +41,8 @@ FRAMES_PER_GPU = 64
 BOXES_PER_FRAME = 8
 ALGO_BYTES_PER_PROPOSAL = 550.0   # SURVEY.md 8d contract figure: 596 B (config 1) / 508 B (config 2), 0.55 KB mean
 ALGO_BYTES_PER_EDGE = 1856.0      # EdgeSE3Cuboid, fused (Jacobian not materialised)
-E2E_DEPTH = 4       # contexts (streams) the end-to-end pipeline keeps in flight
-VALUE_DEPTH = 4     # contexts (streams) with resident inputs used round-robin for `value`
+E2E_DEPTH = 6       # contexts (streams) the end-to-end pipeline keeps in flight
+VALUE_DEPTH = 6     # contexts (streams) with resident inputs used round-robin for `value`
 LSD_FRAMES, LSD_W, LSD_H = 256, 640, 480  # BASELINE config #3
 # streaming stages of the line detector: 1 B read per source pixel, then the reference's two FP64 maps (gradient norm + level-line angle) per scaled pixel
 LSD_ALGO_BYTES_PER_FRAME = LSD_W * LSD_H + 16.0 * round(LSD_W * 0.8) * round(LSD_H * 0.8)

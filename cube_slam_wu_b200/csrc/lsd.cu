@@ -8,21 +8,27 @@
 //   k_lsd_scale : (tile, frame).  u8 tile + halo -> shared memory; separable 7-tap Gaussian in FP64 with OpenCV's summation order
 //                 (row filter left to right, column filter centre tap then symmetric pairs), bilinear x0.8 down-scaling with float
 //                 coefficients -> `scaled` (double).  HBM streaming: 1 B read per source pixel, 8 B written per scaled pixel.
-//   k_lsd_grad  : (32x8 pixel tile, frame).  ll_angle (lsd.cpp:538-590): 2x2 gradient, norm, fastAtan2 level-line angle; per pixel
-//                 {angle in degrees, cosf(angle), sinf(angle)} (the two terms region_grow adds per accepted pixel, lsd.cpp:679-680,
-//                 evaluated once here with the specified det_sincos), the gradient norm, and a 1-bit "defined" map (warp ballot).
-//   k_lsd_merge / _flatten / _complist : connected components of the "defined" mask (union-find, root = first pixel in raster order).
-//   k_lsd_grow  : one CTA per frame, one warp per connected component (dynamic queue, big components first).  flsd's seed loop
-//                 (lsd.cpp:474-535) visits seeds in raster order and every region depends on the `used` map left by the previous
-//                 ones -- but only inside one component, because regions only ever add defined 8-neighbours; so components run
-//                 concurrently and the segments are put back into seed order at the end.  The `used` and `defined` maps live in shared
-//                 memory as bitmaps (2 x 24 KB for 512x384, atomicOr/atomicAnd: words are shared between components); a warp first
-//                 lists its component's pixels in raster order (label scan of the bounding box), then walks that list; region_grow tests the
-//                 8 neighbours of a region pixel on 9 lanes at once and replays the reference's sequential accept order (the running
-//                 angle changes after every accepted pixel, so later neighbours are re-tested); the order-dependent FP64 sums of
-//                 region2rect / get_theta / refine are accumulated in region order from per-lane products staged in shared memory;
+//   k_lsd_grad  : (32x8 pixel tile, frame).  ll_angle (lsd.cpp:538-590): 2x2 gradient, norm, fastAtan2 level-line angle; per pixel a
+//                 16-byte record {angle in degrees, cosf(angle), sinf(angle), label slot} (the two terms region_grow adds per accepted
+//                 pixel, lsd.cpp:679-680, evaluated once here with the specified det_sincos), the gradient norm, a compact angle copy.
+//   k_lsd_merge / _flatten / _contact / _units : the work partition -- "units" = defined pixels linked by 8-adjacency and similar
+//                 level-line angles (union-find, root = first pixel in raster order), their sizes / bounding boxes, the
+//                 defined-neighbour mask of every pixel, the unit list (see the comment above k_lsd_merge for why units are independent
+//                 and how that is checked at run time).
+//   k_lsd_grow  : one CTA per frame (8 warps, or 4 for batches beyond the GPU's residency), one warp per unit (dynamic queue, big
+//                 units first).  flsd's seed loop (lsd.cpp:474-535) visits seeds in raster order and every region depends on the
+//                 `used` map left by the previous ones -- but only inside one unit; units run concurrently and the segments are put back
+//                 into seed order at the end.  The `used` map lives in shared memory as a bitmap (24 KB for 512x384; red.or / red.and:
+//                 words are shared between units).  A warp first lists its unit's pixels in raster order (label scan of the bounding
+//                 box), then walks that list.  region_grow expands one queue entry at a time: lanes 0..8 hold its 3x3 neighbourhood
+//                 (defined-neighbour mask from the entry itself, so no bounds tests), the first aligned lane is accepted, the running
+//                 angle is updated, the later lanes are tested again -- the reference's sequential order.  The order-dependent FP64 sums
+//                 of region2rect / get_theta / refine are accumulated in region order from per-lane products staged in shared memory;
 //                 reduce_region_radius' swap-with-last removal is done as two ordered compactions that yield the same permutation;
-//                 rect_nfa counts aligned pixels lane-parallel (integer counts, order-free).
+//                 rect_nfa counts aligned pixels lane-parallel (closed-form scan-line bounds, integer counts).  One seed is a small state
+//                 machine with a single call site per building block, which keeps the kernel inside the instruction cache.  Finished
+//                 rectangles go through a shared-memory job queue: warps without a unit run the NFA search (rect_improve), which does
+//                 not touch the used map.
 //
 // Arithmetic: FP64, -fmad=false, no libm in anything that decides region membership (det_sincos / fast_atan2f are specified,
 // csb_math-style); log/exp/pow/sinh of the NFA use CUDA's libm (they only feed `>` comparisons against 0 and each other).
