@@ -494,6 +494,11 @@ def run_ours(args, rank, local_rank, world):
                     _, lst = ctx.lsd_detect_batch(lsd_frames)
                 call_ms = 1e3 * (time.perf_counter() - t0) / 3
             m_ms = float(np.mean(maps_ms))
+            lsd_traffic = None
+            try:
+                lsd_traffic = json.load(open(os.path.join(ROOT, "profiles", "lsd_traffic.json"))).get("dram_bytes_per_launch")
+            except Exception:
+                pass
             lsd_ach = LSD_ALGO_BYTES_PER_FRAME * LSD_FRAMES / (m_ms * 1e-3) / 1e9
             out["lsd"] = {"metric": "lsd_frames_per_sec", "value": LSD_FRAMES / (tot_ms / reps * 1e-3), "unit": "frames/s",
                           "config": "config#3: %d synthetic %dx%d frames (32 distinct, tiled), LSD_REFINE_ADV, detect_filter_lines with line_length_thres 15; resident, L2 flushed between runs" % (LSD_FRAMES, LSD_W, LSD_H),
@@ -502,7 +507,7 @@ def run_ours(args, rank, local_rank, world):
                           "e2e": {"value": LSD_FRAMES / (call_ms * 1e-3), "unit": "frames/s", "ms_per_call": call_ms, "h2d_bytes_per_step": int(lst.h2d_bytes),
                                   "d2h_bytes_per_step": int(lst.d2h_bytes), "mode": "one blocking csb_lsd_detect_batch() with pinned host buffers"},
                           "roofline": {"kernel": "streaming stages (k_lsd_scale .. k_lsd_units)", "bound": "hbm", "achieved": lsd_ach, "peak": peak, "unit": "GB/s",
-                                       "frac": lsd_ach / peak, "traffic": None, "algorithmic_bytes_per_launch": LSD_ALGO_BYTES_PER_FRAME * LSD_FRAMES,
+                                       "frac": lsd_ach / peak, "traffic": lsd_traffic, "algorithmic_bytes_per_launch": LSD_ALGO_BYTES_PER_FRAME * LSD_FRAMES,
                                        "note": "the region kernel that follows is sequential per work unit (latency bound), see DESIGN.md 3c"},
                           "gpu_launches": int(lst.n_kernel_launches)}
         except Exception as e:
