@@ -682,10 +682,8 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_CTAS_PER_SM) k_score(Dete
             V2 c[8];
             construct_corners<false>(geo, s_vp + 6 * group, (double)(tt.top_x0 + top * tt.top_step), cfg, c);
             const double total_angle_diff = box_edge_alignment_angle_error(s_sup + 6 * group, c, cfg);
-            V2 cs[8];
-#pragma unroll
-            for (int q = 0; q < 8; q++) cs[q] = V2{c[q].x - geo.roi_l, c[q].y - geo.roi_t};
-            const double sum_dist = map_smem ? box_edge_sum_dists<true>(s_map, tt.roi_h, tt.roi_w, cs, cfg) : box_edge_sum_dists<false>(gmap, tt.roi_h, tt.roi_w, cs, cfg);
+            const double sum_dist = map_smem ? box_edge_sum_dists<true>(s_map, tt.roi_h, tt.roi_w, c, geo.roi_l, geo.roi_t, cfg)
+                                             : box_edge_sum_dists<false>(gmap, tt.roi_h, tt.roi_w, c, geo.roi_l, geo.roi_t, cfg);
             const size_t o = (size_t)tt.out_offset + i;
             B.p_dist[o] = sum_dist / tt.diag;
             B.p_angle[o] = total_angle_diff;

@@ -26,10 +26,13 @@ __device__ __forceinline__ float edge_samples(float sum_dist, const float* __res
 }
 
 // box_edge_sum_dists, object_3d_util.cpp:622-667 with the visible-edge tables of box_proposal_detail.cpp:646, 663
+// c: corners in image coordinates; (ox, oy) = ROI origin.  The reference shifts all eight corners first (box_proposal_detail.cpp:634-636);
+// shifting the two corners of an edge when the edge is sampled gives the same values and keeps only one corner set live.
 template <bool SMEM>
-__device__ __forceinline__ double box_edge_sum_dists(const float* __restrict__ map, int rows, int cols, const V2* c, int config_id) {
+__device__ __forceinline__ double box_edge_sum_dists(const float* __restrict__ map, int rows, int cols, const V2* cc, double ox, double oy, int config_id) {
     const int last = rows * cols - 1;
     float s = 0;
+    struct Sh { const V2* c; double ox, oy; __device__ __forceinline__ V2 operator[](int i) const { return V2{c[i].x - ox, c[i].y - oy}; } } c{cc, ox, oy};
     s = edge_samples<SMEM, 0>(s, map, cols, last, c[0], c[1]);
     s = edge_samples<SMEM, 0>(s, map, cols, last, c[1], c[2]);
     s = edge_samples<SMEM, 0>(s, map, cols, last, c[2], c[3]);
