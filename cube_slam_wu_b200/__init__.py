@@ -216,6 +216,12 @@ class Context:
         self._chk(lib().csb_detect_debug_score_phases(self._h, _p(out), int(reset)))
         return out
 
+    def debug_atan2(self, y, x):
+        y = np.ascontiguousarray(y, np.float64); x = np.ascontiguousarray(x, np.float64)
+        out = np.zeros_like(y); nf = C.c_int()
+        self._chk(lib().csb_detect_debug_atan2(self._h, _p(y), _p(x), _p(out), int(y.size), C.byref(nf)))
+        return out, nf.value
+
     def detect_upload(self, frames, boxes, lines, tasks, n_tasks, dist_maps, n_map_floats, params):
         self._nb, self._kmax = boxes.shape[0], params.max_cuboid_num
         self._chk(lib().csb_detect_upload(*self._args(frames, boxes, lines, tasks, n_tasks, dist_maps, n_map_floats, params)))

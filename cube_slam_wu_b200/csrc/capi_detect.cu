@@ -400,6 +400,28 @@ int csb_detect_batch_gray(csb_context* c, const csb_frame* frames, int n_frames,
     return csb_detect_download(c, cuboids_out, n_cuboids_out, stats);
 }
 
+int csb_detect_debug_atan2(csb_context* c, const double* y, const double* x, double* out, int n, int* n_fallback) {
+    if (!c || !y || !x || !out || n < 0 || n % 6 != 0) return CSB_ERR_INVALID;
+    CSB_CUDA(c, cudaSetDevice(c->device));
+    double* d = nullptr;
+    int* df = nullptr;
+    CSB_CUDA(c, cudaMalloc(&d, (size_t)3 * n * sizeof(double) + 64));
+    CSB_CUDA(c, cudaMalloc(&df, sizeof(int)));
+    cudaMemsetAsync(df, 0, sizeof(int), c->stream);
+    cudaMemcpyAsync(d, y, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(d + n, x, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream);
+    cudaError_t e = launch_debug_atan2(d, d + n, d + 2 * (size_t)n, n / 6, df, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + 2 * (size_t)n, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream);
+    int nf = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&nf, df, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    cudaFree(df);
+    if (n_fallback) *n_fallback = nf;
+    CSB_CUDA(c, e);
+    return CSB_OK;
+}
+
 int csb_detect_debug_score_phases(csb_context* c, uint64_t* cycles8, int reset) {  // 12 entries, see the header
     if (!c || !cycles8) return CSB_ERR_INVALID;
     CSB_CUDA(c, cudaSetDevice(c->device));

@@ -255,6 +255,66 @@ CSB_HD double det_atan2(double y, double x) {
     return (z - pi_lo) - pi;
 }
 
+// Six det_atan2 evaluations at once, for operands that take det_atan2's generic path (finite, non-zero, |y/x| in [2^-29, 2^66), no
+// exponent shortcut): the same operations in the same order per element, but with the interval choice of det_atan expressed as
+// selects of (numerator, denominator) feeding ONE division, so that the six dependency chains are independent straight-line code the
+// compiler can interleave.  Returns false (and computes nothing) if any element needs one of det_atan2's special paths; the caller then
+// falls back to det_atan2 element by element.  Bit-identical to det_atan2 (tests/test_proposal_gpu.py::test_batched_atan2).
+#if defined(__CUDACC__)
+__device__ __forceinline__ bool det_atan2_x6(const double* y, const double* x, double* out) {
+    const double atanhi[4] = {4.63647609000806093515e-01, 7.85398163397448278999e-01, 9.82793723247329054082e-01, 1.57079632679489655800e+00};
+    const double atanlo[4] = {2.26987774529616870924e-17, 3.06161699786838301793e-17, 1.39033110312309984516e-17, 6.12323399573676603587e-17};
+    const double aT[11] = {3.33333333333329318027e-01, -1.99999999998764832476e-01, 1.42857142725034663711e-01, -1.11111104054623557880e-01,
+                           9.09088713343650656196e-02, -7.69187620504482999495e-02, 6.66107313738753120669e-02, -5.83357013379057348645e-02,
+                           4.97687799461593236017e-02, -3.65315727442169155270e-02, 1.62858201153657823623e-02};
+    const double pi = 3.1415926535897931160E+00, pi_lo = 1.2246467991473531772E-16;
+    bool ok = true;
+    double q[6];
+    int m[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        const unsigned hx = (unsigned)__double2hiint(x[i]), lx = (unsigned)__double2loint(x[i]);
+        const unsigned hy = (unsigned)__double2hiint(y[i]), ly = (unsigned)__double2loint(y[i]);
+        const unsigned ix = hx & 0x7fffffffu, iy = hy & 0x7fffffffu;
+        m[i] = (int)((hy >> 31) & 1u) | (int)((hx >> 30) & 2u);
+        const int k = ((int)iy - (int)ix) >> 20;
+        // NaN / inf (exponent all ones), zeros, and the exponent shortcuts of det_atan2
+        ok = ok && (ix < 0x7ff00000u) && (iy < 0x7ff00000u) && ((ix | lx) != 0) && ((iy | ly) != 0) && (k <= 60) && (k >= -60);
+    }
+    if (!ok) return false;
+#pragma unroll
+    for (int i = 0; i < 6; i++) q[i] = fabs(y[i] / x[i]);
+    double num[6], den[6], hi[6], lo[6];
+    bool small[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        const unsigned ixq = (unsigned)__double2hiint(q[i]) & 0x7fffffffu;
+        ok = ok && (ixq < 0x44100000u) && (ixq >= 0x3e200000u);
+        const double v = q[i];
+        small[i] = ixq < 0x3fdc0000u;
+        const bool i0 = !small[i] && ixq < 0x3fe60000u, i1 = !small[i] && !i0 && ixq < 0x3ff30000u, i2 = !small[i] && !i0 && !i1 && ixq < 0x40038000u;
+        num[i] = small[i] ? v : i0 ? (2.0 * v - 1.0) : i1 ? (v - 1.0) : i2 ? (v - 1.5) : -1.0;
+        den[i] = small[i] ? 1.0 : i0 ? (2.0 + v) : i1 ? (v + 1.0) : i2 ? (1.0 + 1.5 * v) : v;
+        hi[i] = i0 ? atanhi[0] : i1 ? atanhi[1] : i2 ? atanhi[2] : atanhi[3];
+        lo[i] = i0 ? atanlo[0] : i1 ? atanlo[1] : i2 ? atanlo[2] : atanlo[3];
+    }
+    if (!ok) return false;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        const double xr = num[i] / den[i];  // den == 1 in the small interval: xr == q exactly
+        const double z = xr * xr;
+        const double w = z * z;
+        const double s1 = z * (aT[0] + w * (aT[2] + w * (aT[4] + w * (aT[6] + w * (aT[8] + w * aT[10])))));
+        const double s2 = w * (aT[1] + w * (aT[3] + w * (aT[5] + w * (aT[7] + w * aT[9]))));
+        const double p = xr * (s1 + s2);
+        const double zz = small[i] ? (xr - p) : (hi[i] - ((p - lo[i]) - xr));
+        const double r2 = pi - (zz - pi_lo), r3 = (zz - pi_lo) - pi;
+        out[i] = (m[i] == 0) ? zz : (m[i] == 1) ? -zz : (m[i] == 2) ? r2 : r3;
+    }
+    return true;
+}
+#endif
+
 // ---- SE(3), g2o se3quat.h ---------------------------------------------------------------------
 CSB_HD void se3_normalize(SE3& s) {  // :346-351
     if (s.r.w < 0) { s.r.w = -s.r.w; s.r.x = -s.r.x; s.r.y = -s.r.y; s.r.z = -s.r.z; }

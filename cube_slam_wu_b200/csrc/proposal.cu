@@ -1059,6 +1059,27 @@ __global__ void __launch_bounds__(32) k_rank(DetectBuffers B) {
 }
 
 // debug: recompute the 2x8 corners of every valid proposal of one task
+// parity probe of det_atan2_x6: thread t evaluates elements [6t, 6t + 6) the way box_edge_alignment_angle_error does
+__global__ void k_debug_atan2(const double* y, const double* x, double* out, int n6, int* n_fallback) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n6) return;
+    double yy[6], xx[6], o[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) { yy[i] = y[6 * t + i]; xx[i] = x[6 * t + i]; }
+    if (!det_atan2_x6(yy, xx, o)) {
+        atomicAdd(n_fallback, 1);
+#pragma unroll
+        for (int i = 0; i < 6; i++) o[i] = det_atan2(yy[i], xx[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) out[6 * t + i] = o[i];
+}
+cudaError_t launch_debug_atan2(const double* y, const double* x, double* out, int n6, int* n_fallback, cudaStream_t st) {
+    if (n6 == 0) return cudaSuccess;
+    k_debug_atan2<<<(n6 + 127) / 128, 128, 0, st>>>(y, x, out, n6, n_fallback);
+    return cudaGetLastError();
+}
+
 __global__ void k_debug_corners(DetectBuffers B, int task, double* out) {
     const TaskTab tt = B.ttab[task];
     const FrameTab& ft = B.ftab[tt.frame_id];

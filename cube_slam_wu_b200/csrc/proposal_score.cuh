@@ -51,9 +51,9 @@ __device__ __forceinline__ double box_edge_sum_dists(const float* __restrict__ m
     return (double)s;
 }
 
-// one box edge against the (<=2) supporting line angles of its VP, object_3d_util.cpp:696-715
-__device__ __forceinline__ double edge_angle_diff(V2 a, V2 b, double v0, double v1) {
-    double box_edge_angle = normalize_to_pi(det_atan2(b.y - a.y, b.x - a.x));
+// one box edge (its angle already evaluated) against the (<=2) supporting line angles of its VP, object_3d_util.cpp:696-715
+__device__ __forceinline__ double edge_angle_diff(double raw_atan2, double v0, double v1) {
+    double box_edge_angle = normalize_to_pi(raw_atan2);
     double angle_diff_temp = 100;
     if (!isnan(v0)) {
         double temp = fabs(box_edge_angle - v0);
@@ -67,26 +67,37 @@ __device__ __forceinline__ double edge_angle_diff(V2 a, V2 b, double v0, double 
     }
     return angle_diff_temp;
 }
-// box_edge_alignment_angle_error, object_3d_util.cpp:670-723 with the tables of box_proposal_detail.cpp:651, 665
+// box_edge_alignment_angle_error, object_3d_util.cpp:670-723 with the tables of box_proposal_detail.cpp:651, 665.
+// The six edge angles are evaluated together (det_atan2_x6: six independent chains instead of six calls one after the other);
+// operands on one of det_atan2's special paths make the whole proposal take the scalar route.
 __device__ __forceinline__ double box_edge_alignment_angle_error(const double* sup /*6*/, const V2* c, int config_id) {
     const double not_found_penalty = 30.0 / 180.0 * M_PI * 2;
+    // VP 1: edges (1,2) and (8,5) | (3,4);  VP 2: edges (4,1) and (5,6);  VP 3: edges (4,8)|(3,5) and (2,6)
+    double dy[6], dx[6], ang[6];
+    dy[0] = c[1].y - c[0].y; dx[0] = c[1].x - c[0].x;
+    dy[1] = config_id == 1 ? c[4].y - c[7].y : c[3].y - c[2].y; dx[1] = config_id == 1 ? c[4].x - c[7].x : c[3].x - c[2].x;
+    dy[2] = c[0].y - c[3].y; dx[2] = c[0].x - c[3].x;
+    dy[3] = c[5].y - c[4].y; dx[3] = c[5].x - c[4].x;
+    dy[4] = config_id == 1 ? c[7].y - c[3].y : c[4].y - c[2].y; dx[4] = config_id == 1 ? c[7].x - c[3].x : c[4].x - c[2].x;
+    dy[5] = c[5].y - c[1].y; dx[5] = c[5].x - c[1].x;
+    if (!det_atan2_x6(dy, dx, ang)) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) ang[i] = det_atan2(dy[i], dx[i]);
+    }
     double total = 0;
-    // VP 1: edges (1,2) and (8,5) | (3,4)
     if (!isnan(sup[0]) || !isnan(sup[1])) {
-        total = total + edge_angle_diff(c[0], c[1], sup[0], sup[1]);
-        total = total + (config_id == 1 ? edge_angle_diff(c[7], c[4], sup[0], sup[1]) : edge_angle_diff(c[2], c[3], sup[0], sup[1]));
+        total = total + edge_angle_diff(ang[0], sup[0], sup[1]);
+        total = total + edge_angle_diff(ang[1], sup[0], sup[1]);
     } else
         total = total + not_found_penalty;
-    // VP 2: edges (4,1) and (5,6)
     if (!isnan(sup[2]) || !isnan(sup[3])) {
-        total = total + edge_angle_diff(c[3], c[0], sup[2], sup[3]);
-        total = total + edge_angle_diff(c[4], c[5], sup[2], sup[3]);
+        total = total + edge_angle_diff(ang[2], sup[2], sup[3]);
+        total = total + edge_angle_diff(ang[3], sup[2], sup[3]);
     } else
         total = total + not_found_penalty;
-    // VP 3: edges (4,8)|(3,5) and (2,6)
     if (!isnan(sup[4]) || !isnan(sup[5])) {
-        total = total + (config_id == 1 ? edge_angle_diff(c[3], c[7], sup[4], sup[5]) : edge_angle_diff(c[2], c[4], sup[4], sup[5]));
-        total = total + edge_angle_diff(c[1], c[5], sup[4], sup[5]);
+        total = total + edge_angle_diff(ang[4], sup[4], sup[5]);
+        total = total + edge_angle_diff(ang[5], sup[4], sup[5]);
     } else
         total = total + not_found_penalty;
     return total;

@@ -147,6 +147,9 @@ int csb_detect_debug_map(csb_context* ctx, int task_id, float* dist_map_out, uin
  * [4] prefix sums, [5] wait for the distance map, [6] scoring, [7] exit; [8..10] VP-support units decided by the float / double /
  * exact tier, [11] unused.  The buffer holds 12 entries. */
 int csb_detect_debug_score_phases(csb_context* ctx, uint64_t* cycles12, int reset);
+/* Parity/debug: the six-at-a-time atan2 of the scoring kernel (groups of six operands, n a multiple of 6) with its scalar fallback;
+ * n_fallback (optional) receives the number of groups that took the fallback.  Must equal the scalar det_atan2 bit for bit. */
+int csb_detect_debug_atan2(csb_context* ctx, const double* y, const double* x, double* out, int n, int* n_fallback);
 
 /* Per-box observation records for camera-object graph assembly (object_slam/src/main_obj.cpp:643-679, :732): the best
  * cuboid of each 2D box as a g2o::cuboid measurement in the local camera frame.  Writes n_boxes x 16 doubles into a

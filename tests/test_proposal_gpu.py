@@ -171,3 +171,26 @@ def test_api_errors(ctx, csb):
     with pytest.raises(csb.CsbError):
         c2.detect_run()  # before upload
     c2.close()
+
+
+def test_batched_atan2(ctx, csb, oracle):
+    """det_atan2_x6 (six edge angles of a proposal evaluated as independent straight-line chains) against the scalar det_atan2 of the
+    oracle: identical bits, including groups that contain operands of the special paths (zeros, huge ratios, infinities)."""
+    L = oracle.lib()
+    rng = np.random.default_rng(7)
+    n = 6 * 20000
+    y = np.concatenate([rng.normal(0, 50, n // 2), rng.uniform(-1e-3, 1e-3, n // 4), rng.normal(0, 1e5, n // 4)])
+    x = np.concatenate([rng.normal(0, 50, n // 2), rng.normal(0, 1, n // 4), rng.uniform(-1, 1, n // 4)])
+    # interval boundaries of the argument reduction and special operands
+    for i, q in enumerate([0.4375, 0.6875, 1.1875, 2.4375, 2.0 ** -29, 2.0 ** 66, 1.0, 0.0, np.inf, 1e-320]):
+        y[6 * i] = q; x[6 * i] = 1.0
+        y[6 * i + 1] = np.nextafter(q, 0) if np.isfinite(q) else q; x[6 * i + 1] = -1.0
+        y[6 * i + 2] = -q; x[6 * i + 2] = np.nextafter(1.0, 2)
+    y[6 * 30] = 1.0; x[6 * 30] = 0.0
+    y[6 * 31] = 1e200; x[6 * 31] = -1e-200
+    out, n_fallback = ctx.debug_atan2(y, x)
+    ref = np.array([L.orc_det_atan2(float(a), float(b)) for a, b in zip(y, x)])
+    same = (out == ref) | (np.isnan(out) & np.isnan(ref))
+    assert same.all(), "%d of %d differ, e.g. %r" % (int((~same).sum()), n, (y[~same][0], x[~same][0], out[~same][0], ref[~same][0]))
+    assert np.array_equal(np.signbit(out), np.signbit(ref))
+    assert 5 <= n_fallback < 200   # the special operands take the scalar route, the bulk does not
