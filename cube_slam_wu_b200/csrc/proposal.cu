@@ -598,10 +598,12 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_CTAS_PER_SM) k_score(Dete
         const int map_floats = tt.roi_w * tt.roi_h;
         const bool map_smem = map_floats <= map_cap_floats;
         const float* gmap = B.maps + tt.map_offset;
+        // a map larger than the shared-memory budget: its first rows (as many whole rows as fit) are staged, the rest is gathered from L2
+        const int smem_floats = map_smem ? map_floats : (map_cap_floats / tt.roi_w) * tt.roi_w;
 
         // (a)
-        if (map_smem && tid == 0) {
-            uint32_t bytes = ((uint32_t)map_floats * 4u + 15u) & ~15u;
+        if (smem_floats > 0 && tid == 0) {
+            uint32_t bytes = map_smem ? (((uint32_t)map_floats * 4u + 15u) & ~15u) : (((uint32_t)smem_floats * 4u) & ~15u);
             fence_proxy_async();  // previous task's generic reads of s_map are ordered before the async write
             mbar_expect_tx(&s_bar, bytes);
             tma_bulk_g2s(s_map, gmap, bytes, &s_bar);
@@ -667,7 +669,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_CTAS_PER_SM) k_score(Dete
         __syncthreads();
         // (f) phase 2
         SCORE_PHASE(4);  // prefix
-        if (map_smem) { mbar_wait(&s_bar, bar_parity); bar_parity ^= 1; }
+        if (smem_floats > 0) { mbar_wait(&s_bar, bar_parity); bar_parity ^= 1; }
         SCORE_PHASE(5);  // wait for the map
         for (int i = tid; i < n_valid; i += SCORE_THREADS) {
             // word containing the i-th set bit: last w with s_wpre[w] <= i
@@ -682,8 +684,9 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_CTAS_PER_SM) k_score(Dete
             V2 c[8];
             construct_corners<false>(geo, s_vp + 6 * group, (double)(tt.top_x0 + top * tt.top_step), cfg, c);
             const double total_angle_diff = box_edge_alignment_angle_error(s_sup + 6 * group, c, cfg);
-            const double sum_dist = map_smem ? box_edge_sum_dists<true>(s_map, tt.roi_h, tt.roi_w, c, geo.roi_l, geo.roi_t, cfg)
-                                             : box_edge_sum_dists<false>(gmap, tt.roi_h, tt.roi_w, c, geo.roi_l, geo.roi_t, cfg);
+            // (the bulk copy of a partial map is rounded down to 16 bytes: up to three floats short of smem_floats)
+            const double sum_dist = map_smem ? box_edge_sum_dists<1>(s_map, gmap, 0, tt.roi_h, tt.roi_w, c, geo.roi_l, geo.roi_t, cfg)
+                                             : box_edge_sum_dists<2>(s_map, gmap, smem_floats & ~3, tt.roi_h, tt.roi_w, c, geo.roi_l, geo.roi_t, cfg);
             const size_t o = (size_t)tt.out_offset + i;
             B.p_dist[o] = sum_dist / tt.diag;
             B.p_angle[o] = total_angle_diff;

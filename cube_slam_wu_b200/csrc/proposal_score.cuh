@@ -8,16 +8,22 @@ __constant__ double c_t[11] = {0 / 10.0, 1 / 10.0, 2 / 10.0, 3 / 10.0, 4 / 10.0,
 __constant__ double c_1mt[11] = {1 - 0 / 10.0, 1 - 1 / 10.0, 1 - 2 / 10.0, 1 - 3 / 10.0, 1 - 4 / 10.0, 1 - 5 / 10.0,
                                  1 - 6 / 10.0, 1 - 7 / 10.0, 1 - 8 / 10.0, 1 - 9 / 10.0, 1 - 10 / 10.0};
 
-// 11 samples along one box edge, object_3d_util.cpp:642-664.  WEIGHT: 0 none, 1 x1.5 (edges 4,5 of config 2), 2 x2 (edge 6)
-template <bool SMEM, int WEIGHT>
-__device__ __forceinline__ float edge_samples(float sum_dist, const float* __restrict__ map, int cols, int last, V2 c1, V2 c2) {
+// 11 samples along one box edge, object_3d_util.cpp:642-664.  WEIGHT: 0 none, 1 x1.5 (edges 4,5 of config 2), 2 x2 (edge 6).
+// MODE: 1 = the whole distance map is in shared memory; 2 = its first n_smem floats (whole rows) are, the rest is gathered from
+// global memory (maps larger than the shared-memory budget); 0 = global memory only.
+template <int MODE, int WEIGHT>
+__device__ __forceinline__ float edge_samples(float sum_dist, const float* __restrict__ smap, const float* __restrict__ gmap, int n_smem, int cols, int last,
+                                              V2 c1, V2 c2) {
 #pragma unroll 4
     for (int k = 0; k < 11; k++) {
         double sx = c_t[k] * c1.x + c_1mt[k] * c2.x;
         double sy = c_t[k] * c1.y + c_1mt[k] * c2.y;
         int li = __double2int_rz(sy) * cols + __double2int_rz(sx);
         li = max(0, min(li, last));  // defined behaviour for samples on the ROI's right/bottom bound (reference: UB)
-        float d1 = SMEM ? map[li] : __ldg(map + li);
+        float d1;
+        if (MODE == 1) d1 = smap[li];
+        else if (MODE == 2) d1 = (li < n_smem) ? smap[li] : __ldg(gmap + li);
+        else d1 = __ldg(gmap + li);
         if (WEIGHT == 1) d1 = (float)((double)d1 * 3.0 / 2.0);
         if (WEIGHT == 2) d1 = (float)((double)d1 * 2.0);
         sum_dist = sum_dist + d1;
@@ -28,26 +34,20 @@ __device__ __forceinline__ float edge_samples(float sum_dist, const float* __res
 // box_edge_sum_dists, object_3d_util.cpp:622-667 with the visible-edge tables of box_proposal_detail.cpp:646, 663
 // c: corners in image coordinates; (ox, oy) = ROI origin.  The reference shifts all eight corners first (box_proposal_detail.cpp:634-636);
 // shifting the two corners of an edge when the edge is sampled gives the same values and keeps only one corner set live.
-template <bool SMEM>
-__device__ __forceinline__ double box_edge_sum_dists(const float* __restrict__ map, int rows, int cols, const V2* cc, double ox, double oy, int config_id) {
+template <int MODE>
+__device__ __forceinline__ double box_edge_sum_dists(const float* __restrict__ smap, const float* __restrict__ gmap, int n_smem, int rows, int cols, const V2* cc,
+                                                     double ox, double oy, int config_id) {
     const int last = rows * cols - 1;
     float s = 0;
     struct Sh { const V2* c; double ox, oy; __device__ __forceinline__ V2 operator[](int i) const { return V2{c[i].x - ox, c[i].y - oy}; } } c{cc, ox, oy};
-    s = edge_samples<SMEM, 0>(s, map, cols, last, c[0], c[1]);
-    s = edge_samples<SMEM, 0>(s, map, cols, last, c[1], c[2]);
-    s = edge_samples<SMEM, 0>(s, map, cols, last, c[2], c[3]);
-    s = edge_samples<SMEM, 0>(s, map, cols, last, c[3], c[0]);
+#define CSB_EDGE(W, A, B) s = edge_samples<MODE, W>(s, smap, gmap, n_smem, cols, last, c[A], c[B]);
+    CSB_EDGE(0, 0, 1) CSB_EDGE(0, 1, 2) CSB_EDGE(0, 2, 3) CSB_EDGE(0, 3, 0)
     if (config_id == 1) {
-        s = edge_samples<SMEM, 0>(s, map, cols, last, c[1], c[5]);
-        s = edge_samples<SMEM, 0>(s, map, cols, last, c[2], c[4]);
-        s = edge_samples<SMEM, 0>(s, map, cols, last, c[3], c[7]);
-        s = edge_samples<SMEM, 0>(s, map, cols, last, c[4], c[7]);
-        s = edge_samples<SMEM, 0>(s, map, cols, last, c[4], c[5]);
+        CSB_EDGE(0, 1, 5) CSB_EDGE(0, 2, 4) CSB_EDGE(0, 3, 7) CSB_EDGE(0, 4, 7) CSB_EDGE(0, 4, 5)
     } else {
-        s = edge_samples<SMEM, 1>(s, map, cols, last, c[1], c[5]);
-        s = edge_samples<SMEM, 1>(s, map, cols, last, c[2], c[4]);
-        s = edge_samples<SMEM, 2>(s, map, cols, last, c[4], c[5]);
+        CSB_EDGE(1, 1, 5) CSB_EDGE(1, 2, 4) CSB_EDGE(2, 4, 5)
     }
+#undef CSB_EDGE
     return (double)s;
 }
 
