@@ -68,7 +68,7 @@ cudaError_t score_phase_cycles(unsigned long long* out12, bool reset) {
 }
 
 constexpr int SCORE_CTAS_PER_SM = 1;  // 2 x 256 threads was measured slower (maps no longer fit shared memory, coarser tail)
-constexpr int SCORE_THREADS = 768;  // 24 warps at 80 registers (136 B of spills) beat 16 warps at 124: 0.245 vs 0.256 ms (640: 0.259, 896: 0.248, 1024: 0.249)
+constexpr int SCORE_THREADS = 768;  // 24 warps at 80 registers (some spills) beat 16 warps at 124 and 28 / 32 warps with more spills (bench value: 640 -> 0.275, 768 -> 0.269, 896 -> 0.269 ms per step)
 constexpr int LINE_SMEM_CAP = 256;
 constexpr int SUBW = 8;  // lanes per VP-support unit
 
