@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_CTAS_PER_SM) k_score(Dete
     unsigned* s_mask = reinterpret_cast<unsigned*>(s_sup + 6 * (size_t)groups_cap);
     int* s_wpre = reinterpret_cast<int*>(s_mask + words_cap);  // words_cap + 1 entries
     __shared__ uint64_t s_bar;
-    __shared__ int s_task;
+    __shared__ int s_task, s_chunk;
     __shared__ int s_w[SCORE_THREADS / 32];
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -620,6 +620,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_CTAS_PER_SM) k_score(Dete
             const double* sup = B.vp_sup + (size_t)task * B.sup_stride;
             for (int i = tid; i < 6 * n_groups; i += SCORE_THREADS) s_sup[i] = sup[i];
         }
+        if (tid == 0) s_chunk = 0;
         SCORE_PHASE(1);
         __syncthreads();
         SCORE_PHASE(2);  // VP support
@@ -630,8 +631,13 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_CTAS_PER_SM) k_score(Dete
         // one thread per (group, top sample): corner 2 once, then both configurations; hypothesis id = 2 * pair + (cfg - 1), so a
         // warp's 32 pairs fill two mask words (bits interleaved: even = configuration 1, odd = configuration 2)
         const int n_pairs_gt = n_hyp >> 1;
-        for (int base = 0; base < n_pairs_gt; base += SCORE_THREADS) {
-            const int p = base + tid;
+        // warps fetch chunks of 32 pairs from a shared counter: the cost of a pair depends on where the cascade rejects it
+        while (true) {
+            int cb = 0;
+            if (lane == 0) cb = atomicAdd(&s_chunk, 32);
+            cb = __shfl_sync(FULL, cb, 0);
+            if (cb >= n_pairs_gt) break;
+            const int p = cb + lane;
             bool v1 = false, v2 = false;
             if (p < n_pairs_gt) {
                 const int group = p / tt.n_top, top = p - group * tt.n_top;
@@ -650,7 +656,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_CTAS_PER_SM) k_score(Dete
                 unsigned x = (lane == 0) ? (b1 & 0xffffu) : (b1 >> 16), y = (lane == 0) ? (b2 & 0xffffu) : (b2 >> 16);
                 x = (x | (x << 8)) & 0x00ff00ffu; x = (x | (x << 4)) & 0x0f0f0f0fu; x = (x | (x << 2)) & 0x33333333u; x = (x | (x << 1)) & 0x55555555u;
                 y = (y | (y << 8)) & 0x00ff00ffu; y = (y | (y << 4)) & 0x0f0f0f0fu; y = (y | (y << 2)) & 0x33333333u; y = (y | (y << 1)) & 0x55555555u;
-                const int w = ((base + (tid & ~31)) >> 4) + lane;  // first hypothesis of the warp = 2 * pair -> word (2 * pair) / 32
+                const int w = (cb >> 4) + lane;  // first hypothesis of the chunk = 2 * pair -> word (2 * pair) / 32
                 if (w < n_words) s_mask[w] = x | (y << 1);
             }
         }
