@@ -141,6 +141,14 @@ struct LSD {
     std::vector<double> scaled, angles, modgrad;
     std::vector<uint8_t> used;
     double LOG_NT = 0;
+    // speculation study (orc_lsd_spec_sim): when rec is set, every used-flag whose value can matter is logged as read, every change as
+    // written (with the old value, so that a speculative seed can be rolled back)
+    struct Rec { std::vector<int> reads; std::vector<std::pair<int, uint8_t>> writes; };
+    Rec* rec = nullptr;
+    void set_used(int a, uint8_t v) {
+        if (rec) rec->writes.push_back({a, used[a]});
+        used[a] = v;
+    }
 
     void sincosd(double x, double* s, double* c) const {
         if (libm_trig) { *s = std::sin(x); *c = std::cos(x); }
@@ -206,7 +214,7 @@ struct LSD {
         double s0, c0;
         sincosd(reg_angle, &s0, &c0);
         float sumdx = float(c0), sumdy = float(s0);
-        used[addr] = 1;
+        set_used(addr, 1);
         for (int i = 0; i < reg_size; ++i) {
             const int px = reg[i].x, py = reg[i].y;
             int xx_min = std::max(px - 1, 0), xx_max = std::min(px + 1, W - 1);
@@ -214,8 +222,11 @@ struct LSD {
             for (int yy = yy_min; yy <= yy_max; ++yy) {
                 int c_addr = xx_min + yy * W;
                 for (int xx = xx_min; xx <= xx_max; ++xx, ++c_addr) {
-                    if (used[c_addr] != 1 && isAligned(c_addr, reg_angle, prec)) {
-                        used[c_addr] = 1;
+                    // (the alignment test comes first here: same result, and only aligned pixels' used flags influence the region)
+                    const bool al = isAligned(c_addr, reg_angle, prec);
+                    if (al && rec) rec->reads.push_back(c_addr);
+                    if (al && used[c_addr] != 1) {
+                        set_used(c_addr, 1);
                         RegionPoint& rp = reg[reg_size];
                         rp.x = xx;
                         rp.y = yy;
@@ -299,7 +310,7 @@ struct LSD {
             radSq *= 0.75 * 0.75;
             for (int i = 0; i < reg_size; ++i) {
                 if (distSq(xc, yc, double(reg[i].x), double(reg[i].y)) > radSq) {
-                    used[reg[i].x + reg[i].y * W] = 0;
+                    set_used(reg[i].x + reg[i].y * W, 0);
                     std::swap(reg[i], reg[reg_size - 1]);
                     --reg_size;
                     --i;
@@ -321,7 +332,7 @@ struct LSD {
         double sum = 0, s_sum = 0;
         int n = 0;
         for (int i = 0; i < reg_size; ++i) {
-            used[reg[i].x + reg[i].y * W] = 0;
+            set_used(reg[i].x + reg[i].y * W, 0);
             if (dist(xc, yc, reg[i].x, reg[i].y) < rec.width) {
                 double ang_d = angle_diff_signed(reg[i].angle, ang_c);
                 sum += ang_d;
@@ -687,6 +698,103 @@ int orc_lsd_detect(const uint8_t* gray, int w, int h, const double* gauss7, cons
             }
         }
         ++n_out;
+    }
+    return n_out;
+}
+
+
+// Study for the next optimisation step of the GPU path: can consecutive seeds be processed speculatively in parallel?
+// Seeds are taken K at a time in raster order; each one is processed from the state at the start of the wave while its reads (used
+// flags of aligned pixels) and writes are logged, then rolled back; they commit in order, and a seed is valid iff nothing it read or
+// wrote was written by a seed committed before it in the same wave -- then it behaves exactly as in the sequential order.  The wave
+// ends at the first invalid seed.  Returns the number of segments (identical to orc_lsd_detect by construction; the caller checks) and
+// fills stats: [0] seeds processed sequentially, [1] waves, [2] speculative seed executions, [3] work of the committed seeds
+// (logged reads + writes), [4] sum over waves of the largest work in the wave (the parallel critical path), [5] total speculative work.
+int orc_lsd_spec_sim(const uint8_t* gray, int w, int h, int K, float* lines_out, int cap, double* stats) {
+    const double SCALE = 0.8, ANG_TH = 22.5, LOG_EPS = 0, DENSITY_TH = 0.7;
+    double k7[7];
+    orc_lsd_gauss_kernel(k7);
+    LSD L;
+    {
+        std::vector<double> blur;
+        gaussian_blur7(gray, w, h, k7, blur);
+        resize_linear(blur, w, h, SCALE, L.scaled, L.W, L.H);
+    }
+    const double prec = CV_PI_ * ANG_TH / 180, p = ANG_TH / 180, rho = 2.0 / std::sin(prec);
+    L.ll_angle(rho);
+    const int W = L.W, H = L.H;
+    L.LOG_NT = 5 * (std::log10(double(W)) + std::log10(double(H))) / 2 + std::log10(11.0);
+    const int min_reg_size = int(-L.LOG_NT / std::log10(p));
+    L.used.assign((size_t)W * H, 0);
+    std::vector<RegionPoint> reg((size_t)W * H);
+    struct Spec { int seed; LSD::Rec rec; std::vector<std::pair<int, uint8_t>> finals; bool line; float e[4]; };
+    auto run_seed = [&](int adx, Spec& S) {
+        S.seed = adx;
+        S.line = false;
+        S.rec.reads.clear();
+        S.rec.writes.clear();
+        L.rec = &S.rec;
+        S.rec.reads.push_back(adx);
+        int reg_size;
+        double reg_angle;
+        L.region_grow(adx % W, adx / W, reg, reg_size, reg_angle, prec);
+        if (reg_size >= min_reg_size) {
+            Rect rec;
+            L.region2rect(reg, reg_size, reg_angle, prec, p, rec);
+            if (L.refine(reg, reg_size, reg_angle, prec, p, rec, DENSITY_TH)) {
+                const double log_nfa = L.rect_improve(rec, LOG_EPS);
+                if (log_nfa > LOG_EPS) {
+                    rec.x1 += 0.5; rec.y1 += 0.5; rec.x2 += 0.5; rec.y2 += 0.5;
+                    rec.x1 /= SCALE; rec.y1 /= SCALE; rec.x2 /= SCALE; rec.y2 /= SCALE;
+                    S.e[0] = float(rec.x1); S.e[1] = float(rec.y1); S.e[2] = float(rec.x2); S.e[3] = float(rec.y2);
+                    S.line = true;
+                }
+            }
+        }
+        L.rec = nullptr;
+        // final values of everything written, then roll back
+        S.finals.clear();
+        for (auto& wv : S.rec.writes) S.finals.push_back({wv.first, L.used[wv.first]});
+        for (size_t i = S.rec.writes.size(); i-- > 0;) L.used[S.rec.writes[i].first] = S.rec.writes[i].second;
+    };
+    std::vector<Spec> wave(K);
+    std::vector<int> mark((size_t)W * H, -1);
+    for (int i = 0; i < 6; i++) stats[i] = 0;
+    int n_out = 0, pos = 0, wave_id = 0;
+    const int N = W * H;
+    while (pos < N) {
+        int n = 0;
+        for (int j = pos; j < N && n < K; j++)
+            if (L.used[j] == 0 && L.angles[j] != NOTDEF) { run_seed(j, wave[n]); n++; }
+        if (n == 0) break;
+        double wmax = 0;
+        for (int k = 0; k < n; k++) {
+            const double wk = double(wave[k].rec.reads.size() + wave[k].rec.writes.size());
+            wmax = std::max(wmax, wk);
+            stats[5] += wk;
+        }
+        stats[2] += n;
+        stats[1] += 1;
+        stats[4] += wmax;
+        int committed = 0;
+        for (int k = 0; k < n; k++) {
+            bool ok = true;
+            if (k > 0) {
+                for (int a : wave[k].rec.reads) if (mark[a] == wave_id) { ok = false; break; }
+                if (ok) for (auto& wv : wave[k].rec.writes) if (mark[wv.first] == wave_id) { ok = false; break; }
+            }
+            if (!ok) break;
+            for (auto& fv : wave[k].finals) { L.used[fv.first] = fv.second; mark[fv.first] = wave_id; }
+            if (wave[k].line) {
+                if (n_out < cap) std::memcpy(lines_out + 4 * (size_t)n_out, wave[k].e, 16);
+                ++n_out;
+            }
+            stats[3] += double(wave[k].rec.reads.size() + wave[k].rec.writes.size());
+            stats[0] += 1;
+            committed++;
+        }
+        pos = wave[committed - 1].seed + 1;
+        wave_id++;
     }
     return n_out;
 }

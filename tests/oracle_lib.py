@@ -227,3 +227,11 @@ def lsd_detect(gray, seed_order=0, libm_trig=0, refine=2, mode=1, length_thres=1
                              _p(out), _p(det), cap)
     assert 0 <= n <= cap
     return (out[:n].copy(), det[:n].copy()) if details else out[:n].copy()
+
+
+def lsd_spec_sim(gray, K):
+    """orc_lsd_spec_sim: wave-speculative seed processing (study, see oracle/oracle_lsd.cpp).  Returns (segments, stats[6])."""
+    gray = np.ascontiguousarray(gray, np.uint8); h, w = gray.shape
+    out = np.zeros((20000, 4), np.float32); st = np.zeros(6)
+    n = lib().orc_lsd_spec_sim(_p(gray), w, h, int(K), _p(out), 20000, _p(st))
+    return out[:n].copy(), st
