@@ -506,7 +506,7 @@ def run_ours(args, rank, local_rank, world):
                           "segments": int(lst.n_lines), "regions": int(lst.n_regions), "region_px": int(lst.n_region_px), "merge_rounds": int(lst.n_merge_rounds),
                           "e2e": {"value": LSD_FRAMES / (call_ms * 1e-3), "unit": "frames/s", "ms_per_call": call_ms, "h2d_bytes_per_step": int(lst.h2d_bytes),
                                   "d2h_bytes_per_step": int(lst.d2h_bytes), "mode": "one blocking csb_lsd_detect_batch() with pinned host buffers"},
-                          "roofline": {"kernel": "streaming stages (k_lsd_scale .. k_lsd_units)", "bound": "hbm", "achieved": lsd_ach, "peak": peak, "unit": "GB/s",
+                          "roofline": {"kernel": "streaming stages (k_lsd_maps .. k_lsd_units)", "bound": "hbm", "achieved": lsd_ach, "peak": peak, "unit": "GB/s",
                                        "frac": lsd_ach / peak, "traffic": lsd_traffic, "algorithmic_bytes_per_launch": LSD_ALGO_BYTES_PER_FRAME * LSD_FRAMES,
                                        "note": "the region kernel that follows is sequential per work unit (latency bound), see DESIGN.md 3c"},
                           "gpu_launches": int(lst.n_kernel_launches)}

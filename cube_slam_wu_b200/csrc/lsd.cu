@@ -5,12 +5,12 @@
 // calls inside (convertTo, GaussianBlur 7x7 on CV_64F, resize x0.8 INTER_LINEAR, fastAtan2) are restated from OpenCV's algorithms; see
 // oracle/oracle_lsd.cpp for how each piece is pinned against cv2 4.13.
 //
-//   k_lsd_scale : (tile, frame).  u8 tile + halo -> shared memory; separable 7-tap Gaussian in FP64 with OpenCV's summation order
-//                 (row filter left to right, column filter centre tap then symmetric pairs), bilinear x0.8 down-scaling with float
-//                 coefficients -> `scaled` (double).  HBM streaming: 1 B read per source pixel, 8 B written per scaled pixel.
-//   k_lsd_grad  : (32x8 pixel tile, frame).  ll_angle (lsd.cpp:538-590): 2x2 gradient, norm, fastAtan2 level-line angle; per pixel a
-//                 16-byte record {angle in degrees, cosf(angle), sinf(angle), label slot} (the two terms region_grow adds per accepted
-//                 pixel, lsd.cpp:679-680, evaluated once here with the specified det_sincos), the gradient norm, a compact angle copy.
+//   k_lsd_maps  : (64x16 tile of the scaled frame, frame).  u8 tile + halo -> shared memory; separable 7-tap Gaussian in FP64 with
+//                 OpenCV's summation order (row filter left to right, column filter centre tap then symmetric pairs); bilinear x0.8
+//                 down-scaling with float coefficients into a shared-memory tile; ll_angle (lsd.cpp:538-590) on that tile: 2x2 gradient,
+//                 norm, fastAtan2 level-line angle.  Per pixel: a 16-byte record {angle in degrees, cosf(angle), sinf(angle), label slot}
+//                 (the two terms region_grow adds per accepted pixel, lsd.cpp:679-680, evaluated once here with the specified
+//                 det_sincos), the gradient norm, a compact angle copy, the initial label; the scaled image is also kept (debug API).
 //   k_lsd_merge / _flatten / _contact / _units : the work partition -- "units" = defined pixels linked by 8-adjacency and similar
 //                 level-line angles (union-find, root = first pixel in raster order), their sizes / bounding boxes, the
 //                 defined-neighbour mask of every pixel, the unit list (see the comment above k_lsd_merge for why units are independent
@@ -166,19 +166,23 @@ __device__ __forceinline__ int resize_src_y(int d, double inv, float& f) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------
-// k_lsd_scale
+// k_lsd_maps (cv::GaussianBlur + cv::resize of flsd, lsd.cpp:449-460, and ll_angle, :538-590)
 // ---------------------------------------------------------------------------------------------------------------------------------
 constexpr int SC_TW = 64, SC_TH = 16, SC_THREADS = 256;
-constexpr int SC_BC = 84, SC_BR = 24;  // blurred tile capacity (source columns / rows feeding one scaled tile)
+constexpr int SC_BC = 88, SC_BR = 26;  // blurred tile capacity: source columns / rows feeding (SC_TW + 1) x (SC_TH + 1) scaled pixels
 constexpr int SC_GP = SC_BC + 8;       // u8 tile pitch
+constexpr int SC_SP = SC_TW + 1;       // scaled tile pitch
 
-__global__ void __launch_bounds__(SC_THREADS) k_lsd_scale(LsdBuffers B, LsdDims d, LsdConst C) {
+// One CTA per 64 x 16 tile of the scaled frame: u8 tile -> row filter -> column filter -> bilinear x0.8 -> (SC_TW + 1) x (SC_TH + 1)
+// scaled pixels in shared memory -> the 2x2 gradient of ll_angle -> per-pixel outputs.  Thread (tx, ty) = (tid & 31, tid >> 5) strides a
+// tile stage by 32 columns and 8 rows, so no stage needs a division.
+__global__ void __launch_bounds__(SC_THREADS) k_lsd_maps(LsdBuffers B, LsdDims d, LsdConst C) {
     __shared__ uint8_t g[(SC_BR + 6) * SC_GP];
-    __shared__ double rowf[(SC_BR + 6) * SC_BC];
+    __shared__ double rowf[(SC_BR + 6) * SC_BC];  // re-used for the scaled tile once the column filter is done
     __shared__ double blur[SC_BR * SC_BC];
-    const int tid = threadIdx.x, f = blockIdx.z;
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5, f = blockIdx.z;
     const int X0 = blockIdx.x * SC_TW, Y0 = blockIdx.y * SC_TH;
-    const int X1 = min(X0 + SC_TW, d.W) - 1, Y1 = min(Y0 + SC_TH, d.H) - 1;
+    const int X1 = min(X0 + SC_TW, d.W - 1), Y1 = min(Y0 + SC_TH, d.H - 1);  // one scaled column / row beyond the tile for the gradient
     const uint8_t* src = B.gray + (size_t)f * d.w * d.h;
     float fr;
     const int sx_lo = resize_src_x(X0, C.inv_scale, d.w, fr);
@@ -187,95 +191,102 @@ __global__ void __launch_bounds__(SC_THREADS) k_lsd_scale(LsdBuffers B, LsdDims 
     const int sy_hi = min(max(resize_src_y(Y1, C.inv_scale, fr) + 1, 0), d.h - 1);
     const int nc = sx_hi - sx_lo + 1, nr = sy_hi - sy_lo + 1;  // <= SC_BC, SC_BR
     // (1) u8 tile: virtual rows sy_lo-3 .. sy_hi+3, virtual columns sx_lo-3 .. sx_hi+3, BORDER_REFLECT_101
-    for (int i = tid; i < (nr + 6) * (nc + 6); i += SC_THREADS) {
-        const int r = i / (nc + 6), c = i - r * (nc + 6);
-        g[r * SC_GP + c] = src[(size_t)reflect101(sy_lo - 3 + r, d.h) * d.w + reflect101(sx_lo - 3 + c, d.w)];
+    for (int r = ty; r < nr + 6; r += 8) {
+        const uint8_t* row = src + (size_t)reflect101(sy_lo - 3 + r, d.h) * d.w;
+        for (int c = tx; c < nc + 6; c += 32) g[r * SC_GP + c] = row[reflect101(sx_lo - 3 + c, d.w)];
     }
     __syncthreads();
     // (2) row filter, taps summed left to right (cv::RowFilter)
-    for (int i = tid; i < (nr + 6) * nc; i += SC_THREADS) {
-        const int r = i / nc, c = i - r * nc;
-        const uint8_t* s = g + r * SC_GP + c;
-        double acc = C.k[0] * (double)s[0];
+    for (int r = ty; r < nr + 6; r += 8)
+        for (int c = tx; c < nc; c += 32) {
+            const uint8_t* s = g + r * SC_GP + c;
+            double acc = C.k[0] * (double)s[0];
 #pragma unroll
-        for (int t = 1; t < 7; t++) acc += C.k[t] * (double)s[t];
-        rowf[r * SC_BC + c] = acc;
-    }
+            for (int t = 1; t < 7; t++) acc += C.k[t] * (double)s[t];
+            rowf[r * SC_BC + c] = acc;
+        }
     __syncthreads();
     // (3) column filter (cv::SymmColumnFilter): centre tap, then f_k (S[+k] + S[-k])
-    for (int i = tid; i < nr * nc; i += SC_THREADS) {
-        const int r = i / nc, c = i - r * nc;
-        const double* s = rowf + (r + 3) * SC_BC + c;
-        double acc = C.k[3] * s[0];
+    for (int r = ty; r < nr; r += 8)
+        for (int c = tx; c < nc; c += 32) {
+            const double* s = rowf + (r + 3) * SC_BC + c;
+            double acc = C.k[3] * s[0];
 #pragma unroll
-        for (int t = 1; t <= 3; t++) acc += C.k[3 + t] * (s[t * SC_BC] + s[-t * SC_BC]);
-        blur[r * SC_BC + c] = acc;
+            for (int t = 1; t <= 3; t++) acc += C.k[3 + t] * (s[t * SC_BC] + s[-t * SC_BC]);
+            blur[r * SC_BC + c] = acc;
+        }
+    __syncthreads();
+    // (4) bilinear down-scaling (HResizeLinear then VResizeLinear, float coefficients) of scaled rows Y0 .. Y1, columns X0 .. X1
+    double* sc = rowf;
+    for (int yy = ty; yy <= Y1 - Y0; yy += 8) {
+        const int dy = Y0 + yy;
+        float fy;
+        const int sy = resize_src_y(dy, C.inv_scale, fy);
+        const float b1 = fy, b0 = 1.f - fy;
+        const int y0 = min(max(sy, 0), d.h - 1) - sy_lo, y1 = min(max(sy + 1, 0), d.h - 1) - sy_lo;
+        for (int xx = tx; xx <= X1 - X0; xx += 32) {
+            const int dx = X0 + xx;
+            float fx;
+            const int sx = resize_src_x(dx, C.inv_scale, d.w, fx);
+            const float a1 = fx, a0 = 1.f - fx;
+            const double* r0p = blur + y0 * SC_BC + (sx - sx_lo);
+            const double* r1p = blur + y1 * SC_BC + (sx - sx_lo);
+            double r0, r1;
+            if (sx + 1 < d.w) {
+                r0 = r0p[0] * (double)a0 + r0p[1] * (double)a1;
+                r1 = r1p[0] * (double)a0 + r1p[1] * (double)a1;
+            } else {
+                r0 = r0p[0];
+                r1 = r1p[0];
+            }
+            const double v = r0 * (double)b0 + r1 * (double)b1;
+            sc[yy * SC_SP + xx] = v;
+            if (xx < SC_TW && yy < SC_TH) B.scaled[((size_t)f * d.H + dy) * d.W + dx] = v;  // kept for csb_lsd_debug_maps
+        }
     }
     __syncthreads();
-    // (4) bilinear down-scaling (HResizeLinear then VResizeLinear, float coefficients)
-    for (int i = tid; i < SC_TW * SC_TH; i += SC_THREADS) {
-        const int dy = Y0 + i / SC_TW, dx = X0 + (i % SC_TW);
-        if (dx >= d.W || dy >= d.H) continue;
-        float fx, fy;
-        const int sx = resize_src_x(dx, C.inv_scale, d.w, fx);
-        const int sy = resize_src_y(dy, C.inv_scale, fy);
-        const float a1 = fx, a0 = 1.f - fx, b1 = fy, b0 = 1.f - fy;
-        const int y0 = min(max(sy, 0), d.h - 1) - sy_lo, y1 = min(max(sy + 1, 0), d.h - 1) - sy_lo;
-        const double* r0p = blur + y0 * SC_BC + (sx - sx_lo);
-        const double* r1p = blur + y1 * SC_BC + (sx - sx_lo);
-        double r0, r1;
-        if (sx + 1 < d.w) {
-            r0 = r0p[0] * (double)a0 + r0p[1] * (double)a1;
-            r1 = r1p[0] * (double)a0 + r1p[1] * (double)a1;
-        } else {
-            r0 = r0p[0];
-            r1 = r1p[0];
-        }
-        B.scaled[((size_t)f * d.H + dy) * d.W + dx] = r0 * (double)b0 + r1 * (double)b1;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------------------
-// k_lsd_grad (ll_angle, lsd.cpp:538-590)
-// ---------------------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_lsd_grad(LsdBuffers B, LsdDims d, LsdConst C) {
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
-    const bool in = x < d.W && y < d.H;
+    // (5) ll_angle (lsd.cpp:538-590): 2x2 gradient, norm, fastAtan2 level-line angle; the records region_grow reads
     const size_t fo = (size_t)f * d.W * d.H;
-    float deg = LSD_NOTDEF_DEG, cv = 0.f, sv = 0.f;
-    double mg = 0.0;
-    bool def = false;
-    if (in && x < d.W - 1 && y < d.H - 1) {
-        const double* S = B.scaled + fo + (size_t)y * d.W + x;
-        const double a = S[0], b = S[1], c = S[d.W], e = S[d.W + 1];
-        const double DA = e - a, BC = b - c;
-        const double gx = DA + BC, gy = DA - BC;
-        const double norm = sqrt((gx * gx + gy * gy) / 4);
-        mg = norm;
-        if (norm > C.rho) {
-            def = true;
-            deg = fast_atan2f((float)gx, (float)(-gy));
-            const double ang = (double)deg * LSD_DEG2RAD;
-            double s, c2;
-            det_sincos((double)(float)ang, s, c2);
-            cv = (float)c2;
-            sv = (float)s;
-        }
-    }
-    if (in) {
-        B.pix[fo + (size_t)y * d.W + x] = make_float4(deg, cv, sv, 0.f);
-        B.deg[fo + (size_t)y * d.W + x] = deg;
-        B.modgrad[fo + (size_t)y * d.W + x] = mg;
-        const size_t pi = fo + (size_t)y * d.W + x;
-        B.label[pi] = def ? y * d.W + x : -1;
-        if (def) {
-            B.csize[pi] = 0;
-            B.cminx[pi] = 0x7fffffff;
-            B.cmaxx[pi] = -1;
-            B.cmaxy[pi] = -1;
-            B.cflag[pi] = 0;
-            B.cmark[pi] = 0;
-            B.cgrp[pi] = y * d.W + x;
+    for (int yy = ty; yy < SC_TH; yy += 8) {
+        const int y = Y0 + yy;
+        if (y >= d.H) break;
+        for (int xx = tx; xx < SC_TW; xx += 32) {
+            const int x = X0 + xx;
+            if (x >= d.W) break;
+            float deg = LSD_NOTDEF_DEG, cv = 0.f, sv = 0.f;
+            double mg = 0.0;
+            bool def = false;
+            if (x < d.W - 1 && y < d.H - 1) {
+                const double* S = sc + yy * SC_SP + xx;
+                const double a = S[0], b = S[1], c = S[SC_SP], e = S[SC_SP + 1];
+                const double DA = e - a, BC = b - c;
+                const double gx = DA + BC, gy = DA - BC;
+                const double norm = sqrt((gx * gx + gy * gy) / 4);
+                mg = norm;
+                if (norm > C.rho) {
+                    def = true;
+                    deg = fast_atan2f((float)gx, (float)(-gy));
+                    const double ang = (double)deg * LSD_DEG2RAD;
+                    double s, c2;
+                    det_sincos((double)(float)ang, s, c2);
+                    cv = (float)c2;
+                    sv = (float)s;
+                }
+            }
+            const size_t pi = fo + (size_t)y * d.W + x;
+            B.pix[pi] = make_float4(deg, cv, sv, 0.f);
+            B.deg[pi] = deg;
+            B.modgrad[pi] = mg;
+            B.label[pi] = def ? y * d.W + x : -1;
+            if (def) {
+                B.csize[pi] = 0;
+                B.cminx[pi] = 0x7fffffff;
+                B.cmaxx[pi] = -1;
+                B.cmaxy[pi] = -1;
+                B.cflag[pi] = 0;
+                B.cmark[pi] = 0;
+                B.cgrp[pi] = y * d.W + x;
+            }
         }
     }
 }
@@ -1359,9 +1370,8 @@ int csb_lsd_run(csb_context* c, int timed) {
     cudaStream_t st = c->stream;
     CSB_CUDA(c, cudaMemsetAsync(s.d_stats.p, 0, 128, st));
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[0], st));
-    k_lsd_scale<<<dim3((d.W + SC_TW - 1) / SC_TW, (d.H + SC_TH - 1) / SC_TH, d.n_frames), SC_THREADS, 0, st>>>(B, d, s.C);
+    k_lsd_maps<<<dim3((d.W + SC_TW - 1) / SC_TW, (d.H + SC_TH - 1) / SC_TH, d.n_frames), SC_THREADS, 0, st>>>(B, d, s.C);
     const dim3 pg((d.W + 31) / 32, (d.H + 7) / 8, d.n_frames), pb(32, 8);
-    k_lsd_grad<<<pg, pb, 0, st>>>(B, d, s.C);
     CSB_CUDA(c, cudaMemsetAsync(s.d_ncomp.p, 0, (size_t)d.n_frames * 16, st));
     k_lsd_merge<<<pg, pb, 0, st>>>(B, d, s.params.unit_link_deg > 0 ? (float)s.params.unit_link_deg : LSD_LINK_DEG);
     k_lsd_flatten<<<pg, pb, 0, st>>>(B, d);
@@ -1373,7 +1383,7 @@ int csb_lsd_run(csb_context* c, int timed) {
     else k_lsd_grow<4><<<d.n_frames, 128, 4 * LSD_WARP_SMEM + ubytes, st>>>(B, d, s.C);
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[2], st));
     CSB_CUDA(c, cudaGetLastError());
-    s.launches_last = 7;
+    s.launches_last = 6;
     s.timed_last = timed != 0;
     s.ran = true;
     return CSB_OK;
