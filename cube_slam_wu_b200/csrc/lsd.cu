@@ -15,7 +15,7 @@
 //                 level-line angles (union-find, root = first pixel in raster order), their sizes / bounding boxes, the
 //                 defined-neighbour mask of every pixel, the unit list (see the comment above k_lsd_merge for why units are independent
 //                 and how that is checked at run time).
-//   k_lsd_grow  : one CTA per frame (8 warps, or 4 for batches beyond the GPU's residency), one warp per unit (dynamic queue, big
+//   k_lsd_grow  : one CTA per frame (4 warps, four frames per SM), one warp per unit (dynamic queue, big
 //                 units first).  flsd's seed loop (lsd.cpp:474-535) visits seeds in raster order and every region depends on the
 //                 `used` map left by the previous ones -- but only inside one unit; units run concurrently and the segments are put back
 //                 into seed order at the end.  The `used` map lives in shared memory as a bitmap (24 KB for 512x384; red.or / red.and:
@@ -935,9 +935,9 @@ struct NfaJob {
     int seed, owner;
 };
 
-// Warps per frame: 8 (two frames per SM; the idle ones serve the rectangle queue) while every frame of the batch fits on the GPU at once,
-// 4 (four frames per SM) for larger batches, where residency -- not the latency of one frame -- sets the throughput.
-constexpr int LSD_WARPS_MAX = 8;
+// Warps per frame.  Four (four frames per SM) measured best at every batch size: 15.5 ms vs 16.5 ms with eight at 256 frames (the
+// extra warps mostly poll the rectangle queue), and twice the residency for large batches; two was slower (36 vs 33 ms at 1024 frames).
+constexpr int LSD_WARPS_MAX = 4;
 constexpr int LSD_WARP_SMEM = 96 * sizeof(double) + LSD_RING * sizeof(uint32_t);  // per warp: staging of the ordered sums + queue ring
 constexpr int LSD_MAX_ROUNDS = 12;  // merge rounds before the rest of the frame is redone as one unit
 
@@ -1330,8 +1330,7 @@ static int lsd_prepare(csb_context* c, int n_frames, int width, int height, cons
     CSB_CUDA(c, s.d_lines.ensure((size_t)n_frames * params->max_lines * 16));
     CSB_CUDA(c, s.d_nlines.ensure((size_t)n_frames * 4));
     CSB_CUDA(c, s.d_stats.ensure(128));
-    CSB_CUDA(c, cudaFuncSetAttribute(k_lsd_grow<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.grow_smem));
-    CSB_CUDA(c, cudaFuncSetAttribute(k_lsd_grow<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.grow_smem));
+    CSB_CUDA(c, cudaFuncSetAttribute(k_lsd_grow<LSD_WARPS_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.grow_smem));
     return CSB_OK;
 }
 
@@ -1378,9 +1377,7 @@ int csb_lsd_run(csb_context* c, int timed) {
     k_lsd_contact<<<pg, pb, 0, st>>>(B, d);
     k_lsd_units<<<pg, pb, 0, st>>>(B, d, s.C.min_reg_size);
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[1], st));
-    const size_t ubytes = (size_t)((d.W * d.H + 31) / 32) * sizeof(uint32_t);
-    if (d.n_frames <= 2 * c->num_sms) k_lsd_grow<8><<<d.n_frames, 256, 8 * LSD_WARP_SMEM + ubytes, st>>>(B, d, s.C);
-    else k_lsd_grow<4><<<d.n_frames, 128, 4 * LSD_WARP_SMEM + ubytes, st>>>(B, d, s.C);
+    k_lsd_grow<LSD_WARPS_MAX><<<d.n_frames, 32 * LSD_WARPS_MAX, s.grow_smem, st>>>(B, d, s.C);
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[2], st));
     CSB_CUDA(c, cudaGetLastError());
     s.launches_last = 6;
