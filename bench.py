@@ -513,6 +513,41 @@ def run_ours(args, rank, local_rank, world):
         except Exception as e:
             out["lsd"] = {"error": str(e)}
 
+        # ---- line descriptors (the LBD half of config #3): descriptors of the segments the detector left on the device
+        try:
+            if "value" in out.get("lsd", {}):
+                with torch.cuda.stream(stream):
+                    for _ in range(2):
+                        ctx.lbd_run_on_lsd()
+                    torch.cuda.synchronize()
+                    reps, g_ms, d_ms = 5, [], []
+                    for _ in range(reps):
+                        flush.zero_()
+                        ctx.lbd_run_on_lsd(timed=True)
+                        bst = ctx.lbd_download()["stats"]
+                        g_ms.append(bst.gpu_ms_grad); d_ms.append(bst.gpu_ms_describe)
+                    t0 = time.perf_counter()
+                    for _ in range(3):
+                        ctx.lsd_upload(lsd_frames); ctx.lsd_run(); ctx.lbd_run_on_lsd()
+                        _, lst2 = ctx.lsd_download(); bout = ctx.lbd_download()
+                    chain_ms = 1e3 * (time.perf_counter() - t0) / 3
+                gm, dm = float(np.mean(g_ms)), float(np.mean(d_ms))
+                grad_bytes = 5.0 * LSD_W * LSD_H * LSD_FRAMES  # 1 B read + one 4-byte {dx, dy} record written per pixel
+                out["lsd"]["lbd"] = {"metric": "lbd_descriptors_per_sec", "value": bst.n_lines / ((gm + dm) * 1e-3), "unit": "descriptors/s",
+                                     "config": "descriptors (32 bytes) of the %d segments of the same batch, read in place from the detector's device buffers; L2 flushed between runs" % bst.n_lines,
+                                     "kernel_ms": {"grad (blur 5x5 + Sobel)": gm, "describe (prefix + descriptors)": dm},
+                                     "samples": int(bst.n_samples), "gsamples_per_s": bst.n_samples / (dm * 1e-3) / 1e9,
+                                     "lsd_plus_lbd_frames_per_s": LSD_FRAMES / ((out["lsd"]["ms_per_batch"] + gm + dm) * 1e-3),
+                                     "e2e": {"value": LSD_FRAMES / (chain_ms * 1e-3), "unit": "frames/s", "ms_per_call": chain_ms,
+                                             "h2d_bytes_per_step": int(lst2.h2d_bytes), "d2h_bytes_per_step": int(lst2.d2h_bytes + bout["stats"].d2h_bytes),
+                                             "mode": "detect_descrip_lines: frames up, LSD, LBD on the resident segments, segments + descriptors down (pinned host buffers)"},
+                                     "roofline": {"kernel": "k_lbd_grad4", "bound": "hbm", "achieved": grad_bytes / (gm * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                                  "frac": grad_bytes / (gm * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": grad_bytes,
+                                                  "note": "k_lbd_describe gathers 4 B per sample from L1/L2 (the gradient records of a frame's lines stay cached)"},
+                                     "gpu_launches": int(bst.n_kernel_launches)}
+        except Exception as e:
+            out.setdefault("lsd", {})["lbd"] = {"error": str(e)}
+
         # ---- CPU baseline: oracle port, one thread (the reference is single-threaded), bounded sample
         if world == 1:
             try:
@@ -543,6 +578,13 @@ def run_ours(args, rank, local_rank, world):
                         O.lsd_detect(lsd_frames[r % 32]); r += 1
                     out["lsd"]["cpu_baseline"] = {"value": r / (time.perf_counter() - t0), "unit": "frames/s", "cores": 1, "kind": "port",
                                                   "sample": "%d frames of the same batch, single thread like the reference" % r}
+                    if "value" in out["lsd"].get("lbd", {}):
+                        segs = [O.lsd_detect(lsd_frames[i]) for i in range(4)]
+                        t0 = time.perf_counter(); r = 0; nd = 0
+                        while time.perf_counter() - t0 < 2.0:
+                            O.lbd_describe(lsd_frames[r % 4], segs[r % 4]); nd += len(segs[r % 4]); r += 1
+                        out["lsd"]["lbd"]["cpu_baseline"] = {"value": nd / (time.perf_counter() - t0), "unit": "descriptors/s", "cores": 1, "kind": "port",
+                                                             "sample": "%d frames (blur + Sobel + descriptors of their segments), single thread" % r}
             except Exception as e:
                 out["cpu_baseline"] = {"error": str(e)}
         print(json.dumps(out), flush=True)  # flush: under torchrun stdout is a block-buffered pipe/file

@@ -91,6 +91,11 @@ class LsdStats(C.Structure):
                 ("gpu_ms_maps", C.c_float), ("gpu_ms_grow", C.c_float), ("grow_cycles", C.c_int64 * 5), ("n_merge_rounds", C.c_int64), ("n_unit_conflicts", C.c_int64)]
 
 
+class LbdStats(C.Structure):
+    _fields_ = [("n_lines", C.c_int64), ("n_samples", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("n_kernel_launches", C.c_int32), ("reserved", C.c_int32), ("gpu_ms_grad", C.c_float), ("gpu_ms_describe", C.c_float)]
+
+
 def lib():
     """Load the CUDA library; raises if it has not been built (there is no fallback path)."""
     global _LIB
@@ -355,6 +360,78 @@ class Context:
         self._chk(lib().csb_lsd_debug_maps(self._h, int(frame), _p(sc), _p(mg), _p(an)))
         return sc, mg, an
 
+    # ---- line descriptors (LBD) ----------------------------------------------------------------
+    @staticmethod
+    def _lbd_pack(lines_per_frame):
+        off = np.zeros(len(lines_per_frame) + 1, np.int32)
+        for i, l in enumerate(lines_per_frame):
+            off[i + 1] = off[i] + len(l)
+        flat = np.zeros((max(int(off[-1]), 1), 4), np.float32)
+        for i, l in enumerate(lines_per_frame):
+            if len(l):
+                flat[off[i]:off[i + 1]] = np.asarray(l, np.float32).reshape(-1, 4)
+        return flat, off
+
+    @staticmethod
+    def _lbd_split(arr, cnt):
+        out, o = [], 0
+        for k in cnt:
+            out.append(arr[o:o + k].copy()); o += k
+        return out
+
+    def lbd_describe_batch(self, gray, lines_per_frame, want_float=False):
+        """csb_lbd_describe_batch(): gray (n, h, w) uint8 + per-frame (k_i, 4) float32 line arrays -> per-frame (k_i, 32) uint8 descriptors
+        (and (k_i, 72) float32 ones with want_float), stats."""
+        gray = self._lsd_gray(gray)
+        n, h, w = gray.shape
+        assert len(lines_per_frame) == n
+        flat, off = self._lbd_pack(lines_per_frame)
+        total = int(off[-1])
+        d32 = np.zeros((max(total, 1), 32), np.uint8); d72 = np.zeros((max(total, 1), 72), np.float32) if want_float else None
+        st = LbdStats()
+        self._chk(lib().csb_lbd_describe_batch(self._h, _p(gray), n, w, h, _p(flat), _p(off), _p(d32), _p(d72), C.byref(st)))
+        cnt = np.diff(off)
+        if want_float:
+            return self._lbd_split(d32[:total], cnt), self._lbd_split(d72[:total], cnt), st
+        return self._lbd_split(d32[:total], cnt), st
+
+    def lbd_upload(self, gray, lines_per_frame, want_float=False):
+        gray = self._lsd_gray(gray)
+        n, h, w = gray.shape
+        flat, off = self._lbd_pack(lines_per_frame)
+        self._lbd_cap = int(off[-1])
+        self._lbd_n = n
+        self._chk(lib().csb_lbd_upload(self._h, _p(gray), n, w, h, _p(flat), _p(off), int(want_float)))
+
+    def lbd_run(self, timed=False):
+        self._chk(lib().csb_lbd_run(self._h, int(timed)))
+
+    def lbd_run_on_lsd(self, want_float=False, timed=False):
+        """csb_lbd_run_on_lsd(): descriptors of the segments the last lsd_run() left on the device."""
+        self._lbd_cap = self._lsd_n * self._lsd_p.max_lines
+        self._lbd_n = self._lsd_n
+        self._chk(lib().csb_lbd_run_on_lsd(self._h, int(want_float), int(timed)))
+
+    def lbd_download(self, want_float=False, keylines=False):
+        cap = max(self._lbd_cap, 1)
+        d32 = np.zeros((cap, 32), np.uint8)
+        d72 = np.zeros((cap, 72), np.float32) if want_float else None
+        kl = np.zeros((cap, 4), np.float32) if keylines else None
+        cnt = np.zeros(self._lbd_n, np.int32); st = LbdStats()
+        self._chk(lib().csb_lbd_download(self._h, _p(d32), _p(d72), _p(kl), _p(cnt), C.c_int64(cap), C.byref(st)))
+        out = {"desc": self._lbd_split(d32, cnt), "stats": st, "n_lines": cnt}
+        if want_float:
+            out["desc_float"] = self._lbd_split(d72, cnt)
+        if keylines:
+            out["keylines"] = self._lbd_split(kl, cnt)
+        return out
+
+    def lbd_debug_gradients(self, frame, shape):
+        h, w = shape
+        dx = np.zeros((h, w), np.int16); dy = np.zeros((h, w), np.int16)
+        self._chk(lib().csb_lbd_debug_gradients(self._h, int(frame), _p(dx), _p(dy)))
+        return dx, dy
+
 
 class line_lbd_detect:
     """Host-side mirror of class line_lbd_detect (reference: line_lbd/include/line_lbd/line_lbd_allclass.h:20-60) for its LSD branch:
@@ -375,3 +452,17 @@ class line_lbd_detect:
         single = np.asarray(gray_img).ndim == 2
         out, _ = self._ctx.lsd_detect_batch(gray_img, self.line_length_thres, True, self.max_lines)
         return out[0] if single else out
+
+    def detect_descrip_lines(self, gray_img):
+        """line_lbd_allclass.cpp:263-281 (the KeyLine overload: octave 0, lineLength > line_length_thres): gray image(s) -> (lines rows
+        [x1 y1 x2 y2] float32, line_descrips rows of 32 bytes); the segments stay on the device between the two stages."""
+        if not self.use_LSD:
+            raise CsbError(CSB_ERR_INVALID, "use_LSD = false (EDLines) is not implemented on the GPU")
+        single = np.asarray(gray_img).ndim == 2
+        c = self._ctx
+        c.lsd_upload(gray_img, self.line_length_thres, True, self.max_lines)
+        c.lsd_run()
+        c.lbd_run_on_lsd()
+        lines, _ = c.lsd_download()
+        desc = c.lbd_download()["desc"]
+        return (lines[0], desc[0]) if single else (lines, desc)

@@ -54,6 +54,7 @@ void csb_destroy(csb_context* c) {
         if (d.ev[i]) cudaEventDestroy(d.ev[i]);
     ba_release(c->ba);
     lsd_release(c->lsd);
+    lbd_release(c->lbd);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->h_epoch) cudaFreeHost(c->h_epoch);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);

@@ -7,6 +7,7 @@
 
 #include "ba.h"
 #include "csb_internal.h"
+#include "lbd.h"
 #include "lsd.h"
 #include "proposal.h"
 
@@ -91,6 +92,7 @@ struct csb_context {
     DetectState det;
     csb::BAState ba;
     csb::LsdState* lsd = nullptr;  // created by the first csb_lsd_* call
+    csb::LbdState* lbd = nullptr;  // created by the first csb_lbd_* call
 };
 
 #define CSB_CUDA(ctx, call)                                                                   \

@@ -1243,6 +1243,15 @@ void lsd_release(LsdState*& s) {
     s = nullptr;
 }
 
+bool lsd_view(LsdState* s, LsdView& v) {
+    if (!s || !s->ran) return false;
+    v.gray = s->d_gray.as<uint8_t>();
+    v.lines = s->d_lines.as<float>();
+    v.n_lines = s->d_nlines.as<int>();
+    v.w = s->d.w; v.h = s->d.h; v.n_frames = s->d.n_frames; v.max_lines = s->params.max_lines;
+    return true;
+}
+
 static LsdBuffers lsd_buffers(LsdState& s) {
     LsdBuffers B{};
     B.gray = s.d_gray.as<uint8_t>();

@@ -282,6 +282,44 @@ int csb_lsd_download(csb_context* ctx, float* lines_out, int32_t* n_lines_out, c
  * the blurred + down-scaled image, the gradient norm, the level-line angle in radians (-1024 = undefined). */
 int csb_lsd_debug_maps(csb_context* ctx, int frame, double* scaled_out, double* modgrad_out, double* angles_out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Line descriptors (BASELINE config #3): the LBD half of line_lbd_detect::detect_descrip_lines
+ * ------------------------------------------------------------------------------------------------
+ * Replaces, for a batch of equally sized 8-bit gray frames and their line segments, what
+ *   line_lbd_detect::detect_descrip_lines(gray_img, lines_mat, line_descrips)             line_lbd/class/line_lbd_allclass.cpp:239-281
+ * does after the detector: lbd->compute(gray_img, keylines, descrips) = BinaryDescriptor::computeImpl (line_lbd/libs/binary_descriptor.cpp:
+ * 607-794): Gaussian blur 5x5 + Sobel (:347-402), computeLBD (:1150-1512), binaryConversion (:405-417, 766-773), with the key-line fields
+ * (numOfPixels, angle) filled as LSDDetector::detectImpl does (line_lbd/libs/LSDDetector.cpp:80-101, 239-245).  One octave.
+ * Output rows are line_descrips': 32 bytes per line (CV_8UC1, returnFloatDescr = false) and, on request, the 72 floats behind them
+ * (returnFloatDescr = true), one row per input line, frame after frame.  A frame without lines yields no rows (computeImpl returns early).
+ * Not provided: line_lbd_detect::get_line_descriptors (its mat_to_keylines reads KeyLine fields before setting them) and the matcher. */
+typedef struct csb_lbd_stats {
+    int64_t n_lines;    /* descriptors computed */
+    int64_t n_samples;  /* gradient samples gathered: 63 rows x numOfPixels per line */
+    int64_t h2d_bytes, d2h_bytes;
+    int32_t n_kernel_launches, reserved;
+    float gpu_ms_grad, gpu_ms_describe; /* CUDA-event times of the last timed run: blur + Sobel / prefix + descriptors */
+} csb_lbd_stats;
+
+/* Host buffers in and out.  lines = float32 [x1 y1 x2 y2] rows of all frames back to back; line_offsets[n_frames + 1] = first row of each
+ * frame (line_offsets[0] is the base); desc_out = rows x 32 bytes; desc_float_out = rows x 72 floats or NULL. */
+int csb_lbd_describe_batch(csb_context* ctx, const uint8_t* gray, int n_frames, int width, int height, const float* lines,
+                           const int32_t* line_offsets, uint8_t* desc_out, float* desc_float_out, csb_lbd_stats* stats);
+/* Device-resident variant. */
+int csb_lbd_upload(csb_context* ctx, const uint8_t* gray, int n_frames, int width, int height, const float* lines, const int32_t* line_offsets,
+                   int want_float);
+int csb_lbd_run(csb_context* ctx, int timed);
+/* detect_descrip_lines without a host round trip: descriptors of the segments the last csb_lsd_run of this context left on the device
+ * (its frames and its segment table are read in place).  With csb_lsd_params.filter = 1 the rows are those of the KeyLine overload
+ * (line_lbd_allclass.cpp:263-281: octave 0, lineLength > line_length_thres); a descriptor does not depend on the other lines. */
+int csb_lbd_run_on_lsd(csb_context* ctx, int want_float, int timed);
+/* Rows of all frames back to back (n_lines_out[f] rows for frame f; any pointer may be NULL).  keylines_out = rows x 4 floats
+ * {angle, numOfPixels, lineLength, 0}.  CSB_ERR_CAPACITY if the batch holds more than capacity_rows lines (nothing is copied). */
+int csb_lbd_download(csb_context* ctx, uint8_t* desc_out, float* desc_float_out, float* keylines_out, int32_t* n_lines_out,
+                     int64_t capacity_rows, csb_lbd_stats* stats);
+/* Parity/debug: the int16 Sobel images of one frame after a run (width x height each). */
+int csb_lbd_debug_gradients(csb_context* ctx, int frame, int16_t* dx_out, int16_t* dy_out);
+
 #ifdef __cplusplus
 }
 #endif

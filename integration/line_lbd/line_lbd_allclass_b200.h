@@ -1,13 +1,14 @@
 // line_lbd_allclass_b200.h -- drop-in for the LSD branch of class line_lbd_detect
-// (reference: line_lbd/include/line_lbd/line_lbd_allclass.h:20-60, line_lbd/class/line_lbd_allclass.cpp:130-149, 200-235).
+// (reference: line_lbd/include/line_lbd/line_lbd_allclass.h:20-60, line_lbd/class/line_lbd_allclass.cpp:130-149, 200-281).
 //
 // Same class name, same public members the callers touch (use_LSD, line_length_thres; object_slam/src/main_obj.cpp:503-505,
-// line_lbd/src/detect_lines.cpp:61-66) and the same detect_filter_lines(const cv::Mat&, cv::Mat&) signature; the work is done by
-// csb_lsd_detect_batch() of libcubeslam_b200.so.  NOT compiled in the build container (no OpenCV headers there); it only uses the C ABI,
+// line_lbd/src/detect_lines.cpp:61-66) and the same detect_filter_lines(const cv::Mat&, cv::Mat&) /
+// detect_descrip_lines(const cv::Mat&, cv::Mat&, cv::Mat&) signatures; the work is done by csb_lsd_* / csb_lbd_* of libcubeslam_b200.so.  NOT compiled in the build container (no OpenCV headers there); it only uses the C ABI,
 // which the test-suite exercises through ctypes.  use_LSD = false (EDLines) is not ported: keep the reference's class for that.
 #pragma once
 #include <opencv2/core.hpp>
 
+#include <cstring>
 #include <stdexcept>
 #include <vector>
 
@@ -42,6 +43,34 @@ public:
         if (rc != CSB_OK) throw std::runtime_error(csb_last_error(ctx_));
         linesmat_out.create(n, 4, CV_32FC1);
         if (n) std::memcpy(linesmat_out.data, lines_.data(), (size_t)n * 16);
+    }
+
+    // line_lbd_allclass.cpp:239-260: lines and their 32-byte LBD descriptors (lbd->compute on the detector's key lines, octave 0).
+    // The segments never leave the device between the two stages.  The reference's Mat overload describes every key line the detector
+    // returns (no length filter): line_length_thres is not applied here either (csb_lsd_params.line_length_thres = -1).
+    void detect_descrip_lines(const cv::Mat& gray_img, cv::Mat& lines_mat, cv::Mat& line_descrips) {
+        if (!use_LSD) throw std::runtime_error("line_lbd_detect (B200): use_LSD = false is not implemented");
+        if (gray_img.type() != CV_8UC1) throw std::runtime_error("Error, depth image!= 0");
+        cv::Mat gray = gray_img.isContinuous() ? gray_img : gray_img.clone();
+        csb_lsd_params p{-1.0f, 1, max_lines_, 0};
+        int rc = csb_lsd_upload(ctx_, gray.data, 1, gray.cols, gray.rows, &p);
+        if (rc == CSB_OK) rc = csb_lsd_run(ctx_, 0);
+        if (rc == CSB_OK) rc = csb_lbd_run_on_lsd(ctx_, /*want_float=*/0, 0);
+        lines_.resize((size_t)max_lines_ * 4);
+        int32_t n = 0;
+        if (rc == CSB_OK) rc = csb_lsd_download(ctx_, lines_.data(), &n, nullptr);
+        if (rc == CSB_ERR_CAPACITY) {
+            max_lines_ *= 4;
+            return detect_descrip_lines(gray_img, lines_mat, line_descrips);
+        }
+        if (rc != CSB_OK) throw std::runtime_error(csb_last_error(ctx_));
+        lines_mat.create(n, 4, CV_32FC1);
+        line_descrips.create(n, 32, CV_8UC1);
+        if (n) {
+            std::memcpy(lines_mat.data, lines_.data(), (size_t)n * 16);
+            rc = csb_lbd_download(ctx_, line_descrips.data, nullptr, nullptr, nullptr, n, nullptr);
+            if (rc != CSB_OK) throw std::runtime_error(csb_last_error(ctx_));
+        }
     }
 
 private:

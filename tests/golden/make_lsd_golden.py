@@ -3,6 +3,9 @@
   lsd_demo.npz : the reference's own golden vector for the line detector.  gray = cv2 decode + BGR2GRAY of
                  detect_3d_cuboid/data/0000_rgb_raw.jpg; ref_lines = detect_3d_cuboid/data/edge_detection/LSD/0000_edge.txt, the 271 segments the
                  reference's line_lbd node (LSD branch, line_length_thres 15) wrote for that image (6 significant digits).
+  lsd_407.npz  : a second golden vector of the reference: gray = cv2 decode + BGR2GRAY of line_lbd/data/407.jpg (the image of
+                 line_lbd/launch/line_detect.launch:5, use_LSD_algorithm = true); ref_lines = line_lbd/data/saved_edges.txt, the 295 segments the
+                 node wrote for it (line_lbd/src/detect_lines.cpp:94-103).
   lsd_cv2.npz  : pins of the third-party (OpenCV) arithmetic against cv2 4.13 on synthetic frames:
                  * gauss7            cv2.getGaussianKernel(7, 0.6 / 0.8)
                  * atan_y/x/deg      cv2.fastAtan2 samples
@@ -34,6 +37,9 @@ def main():
     gray = cv2.cvtColor(cv2.imread(REF + "0000_rgb_raw.jpg", 1), cv2.COLOR_BGR2GRAY)
     ref = np.loadtxt(REF + "edge_detection/LSD/0000_edge.txt")
     np.savez_compressed(os.path.join(HERE, "lsd_demo.npz"), gray=gray, ref_lines=ref)
+    gray2 = cv2.cvtColor(cv2.imread("/root/reference/line_lbd/data/407.jpg", 1), cv2.COLOR_BGR2GRAY)
+    ref2 = np.loadtxt("/root/reference/line_lbd/data/saved_edges.txt")
+    np.savez_compressed(os.path.join(HERE, "lsd_407.npz"), gray=gray2, ref_lines=ref2)
 
     out = {"gauss7": cv2.getGaussianKernel(7, 0.6 / 0.8, cv2.CV_64F).ravel()}
     rng = np.random.default_rng(1)

@@ -47,7 +47,7 @@ class BAOut(C.Structure):
 
 def build(force=False):
     so = os.path.join(ORACLE_DIR, "liboracle.so")
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle_proposal.cpp", "oracle_ba.cpp", "oracle_lsd.cpp", "oracle_math.h", "Makefile")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle_proposal.cpp", "oracle_ba.cpp", "oracle_lsd.cpp", "oracle_lbd.cpp", "oracle_math.h", "Makefile")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
     return so
@@ -235,3 +235,31 @@ def lsd_spec_sim(gray, K):
     out = np.zeros((20000, 4), np.float32); st = np.zeros(6)
     n = lib().orc_lsd_spec_sim(_p(gray), w, h, int(K), _p(out), 20000, _p(st))
     return out[:n].copy(), st
+
+
+# ---- LBD line descriptor (oracle/oracle_lbd.cpp) -----------------------------------------------------------------------------------
+def lbd_gradients(gray):
+    """blurred frame (u8) and the int16 Sobel images BinaryDescriptor::computeSobel produces."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    b = np.zeros((h, w), np.uint8); dx = np.zeros((h, w), np.int16); dy = np.zeros((h, w), np.int16)
+    lib().orc_lbd_gradients(_p(gray), w, h, _p(b), _p(dx), _p(dy))
+    return b, dx, dy
+
+
+def lbd_weights():
+    g = np.zeros(63, np.float32); l = np.zeros(21, np.float32)
+    lib().orc_lbd_weights(_p(g), _p(l))
+    return g, l
+
+
+def lbd_describe(gray, lines, libm_trig=0):
+    """72-float and 32-byte LBD descriptors of `lines` (n x 4 float32) + key-line fields {angle, numOfPixels, lineLength}."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    lines = np.ascontiguousarray(lines, np.float32).reshape(-1, 4)
+    h, w = gray.shape
+    n = len(lines)
+    d72 = np.zeros((n, 72), np.float32); d32 = np.zeros((n, 32), np.uint8); kl = np.zeros((n, 3), np.float32)
+    if n:
+        lib().orc_lbd_describe(_p(gray), w, h, _p(lines), n, int(libm_trig), _p(d72), _p(d32), _p(kl))
+    return d72, d32, kl

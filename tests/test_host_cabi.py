@@ -88,6 +88,20 @@ def test_null_context_is_rejected_everywhere(csb):
     assert C.sizeof(csb.LsdParams) == 16 and C.sizeof(csb.LsdStats) == 5 * 8 + 4 * 4 + 2 * 4 + 7 * 8
 
 
+def test_null_context_lbd(csb):
+    """The descriptor entry points: NULL context / call-order errors are reported, not crashes, with or without a GPU."""
+    L = csb.lib()
+    img = np.zeros((1, 16, 16), np.uint8); ln = np.zeros((1, 4), np.float32); off = np.array([0, 1], np.int32); d = np.zeros((1, 32), np.uint8)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert L.csb_lbd_describe_batch(None, vp(img), 1, 16, 16, vp(ln), vp(off), vp(d), None, None) == csb.CSB_ERR_INVALID
+    assert L.csb_lbd_upload(None, vp(img), 1, 16, 16, vp(ln), vp(off), 0) == csb.CSB_ERR_INVALID
+    assert L.csb_lbd_run(None, 0) == csb.CSB_ERR_STATE
+    assert L.csb_lbd_run_on_lsd(None, 0, 0) == csb.CSB_ERR_INVALID
+    assert L.csb_lbd_download(None, None, None, None, None, C.c_int64(0), None) == csb.CSB_ERR_STATE
+    assert L.csb_lbd_debug_gradients(None, 0, None, None) == csb.CSB_ERR_STATE
+    assert C.sizeof(csb.LbdStats) == 4 * 8 + 2 * 4 + 2 * 4
+
+
 def test_line_lbd_mirror_refuses_unported_modes(csb):
     class _Ctx:  # no device needed: the checks happen before any call into the library
         pass
@@ -98,3 +112,5 @@ def test_line_lbd_mirror_refuses_unported_modes(csb):
     d.use_LSD = False
     with pytest.raises(csb.CsbError):
         d.detect_filter_lines(np.zeros((8, 8), np.uint8))
+    with pytest.raises(csb.CsbError):
+        d.detect_descrip_lines(np.zeros((8, 8), np.uint8))

@@ -124,6 +124,24 @@ def test_reference_golden_vector_on_gpu(ctx, csb, oracle):
     assert np.abs(lines[0].astype(np.float64) - ref).max() < 2e-3
 
 
+def test_second_reference_golden_vector_on_gpu(ctx, csb, oracle):
+    """line_lbd/data/saved_edges.txt (295 segments of line_lbd/data/407.jpg, 640 x 479; tests/golden/lsd_407.npz) through the GPU path, and the
+    descriptors of those segments against the descriptor oracle (detect_descrip_lines on a real image)."""
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lsd_407.npz"))
+    frames = np.ascontiguousarray(d["gray"][None])
+    lines, st, worst = _check(ctx, oracle, frames)
+    ref = d["ref_lines"]
+    assert lines[0].shape == ref.shape
+    assert np.abs(lines[0].astype(np.float64) - ref).max() < 2e-3
+    det = csb.line_lbd_detect(ctx)
+    det.line_length_thres = 15.0
+    l2, desc = det.detect_descrip_lines(frames[0])
+    assert np.array_equal(l2, lines[0])
+    _, r32, _ = oracle.lbd_describe(frames[0], l2)
+    assert np.array_equal(desc, r32)
+
+
 def test_full_hd_frame_and_tiny_frames(ctx, csb, oracle):
     from cube_slam_wu_b200 import synth
     big = synth.make_lsd_frames(1, 1920, 1080, seed=51, n_polys=30, n_lines=60)
