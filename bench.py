@@ -548,6 +548,16 @@ def run_ours(args, rank, local_rank, world):
         except Exception as e:
             out.setdefault("lsd", {})["lbd"] = {"error": str(e)}
 
+        # ---- BASELINE config #5 (single-GPU share; tools/config5.py is the torchrun-able version): 10k frames through the gray-frame entry,
+        #      observation records collected on the device, host graph assembly, one linearisation of the 10k-camera graph
+        if world == 1:
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import config5
+                out["config5"] = config5.run(10000, E2E_DEPTH, ctx=ctx)
+            except Exception as e:
+                out["config5"] = {"error": str(e)}
+
         # ---- CPU baseline: oracle port, one thread (the reference is single-threaded), bounded sample
         if world == 1:
             try:

@@ -40,3 +40,28 @@ def test_lsd_lines_feed_the_proposal_stage(ctx, csb, oracle):
     s = H.compare_with_oracle(ctx, csb, batch, p, cub, ncub, ora)
     assert st.n_scored == s["n_scored"]
     print("pipeline: %d segments -> %d scored proposals, max float diff %g" % (off, st.n_scored, s["max_float_diff"]))
+
+
+def test_config5_frames_to_graph(ctx, csb, oracle):
+    """BASELINE config #5 at a small size (tools/config5.py): frames -> proposal kernels -> observation records -> host graph assembly
+    (main_obj.cpp:738-803) -> csb_ba_set_graph + linearisation, against the oracle's linearisation of the same graph."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import config5
+    out = config5.run(n_frames_total=192, depth=2, ctx=ctx, keep=True)
+    g, lin, rec = out["_graph"], out["_lin"], out["_records"]
+    assert out["frames"] == 192 and out["graph"]["cameras"] == 192 and out["graph"]["edges_odometry"] == 191
+    n_valid = int((rec[..., 2] == 1).sum())
+    assert out["graph"]["edges_cuboid"] == n_valid and n_valid > 192      # most of the 8 boxes of a frame yield a cuboid
+    assert 1 <= out["graph"]["landmarks"] <= 8
+    # the three passes over the same 64 frames give the same records
+    assert np.array_equal(rec[0, 0, :, 2:], rec[0, 1, :, 2:]) and np.array_equal(rec[0, 0, :, 2:], rec[0, 2, :, 2:])
+    E = oracle.ba_edges(ec=g["ec"], ep=None, eo=g["eo"])
+    ref = oracle.ba_linearize(g["cams7"], g["cam_fixed"], g["cubes10"], g["cube_fixed"], E)
+    for k in ("ec_err", "eo_err"):
+        assert np.abs(lin[k] - ref[k]).max() <= 1e-9 * max(1.0, np.abs(ref[k]).max()), k
+    for k in ("H_cam", "H_cube", "b_cam", "b_cube", "ec_Hij"):
+        d = np.abs(lin[k] - ref[k]).max() / max(1.0, np.abs(ref[k]).max())
+        assert d <= 1e-4, "%s differs by %g" % (k, d)
+    assert np.isfinite(out["chi2"]) and out["chi2"] > 0 and out["edges_per_s"]["numeric"] > 0
