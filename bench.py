@@ -532,6 +532,11 @@ def run_ours(args, rank, local_rank, world):
                         _, lst2 = ctx.lsd_download(); bout = ctx.lbd_download()
                     chain_ms = 1e3 * (time.perf_counter() - t0) / 3
                 gm, dm = float(np.mean(g_ms)), float(np.mean(d_ms))
+                lbd_traffic = None
+                try:
+                    lbd_traffic = json.load(open(os.path.join(ROOT, "profiles", "lbd_traffic.json"))).get("dram_bytes_per_launch")
+                except Exception:
+                    pass
                 grad_bytes = 5.0 * LSD_W * LSD_H * LSD_FRAMES  # 1 B read + one 4-byte {dx, dy} record written per pixel
                 out["lsd"]["lbd"] = {"metric": "lbd_descriptors_per_sec", "value": bst.n_lines / ((gm + dm) * 1e-3), "unit": "descriptors/s",
                                      "config": "descriptors (32 bytes) of the %d segments of the same batch, read in place from the detector's device buffers; L2 flushed between runs" % bst.n_lines,
@@ -542,7 +547,7 @@ def run_ours(args, rank, local_rank, world):
                                              "h2d_bytes_per_step": int(lst2.h2d_bytes), "d2h_bytes_per_step": int(lst2.d2h_bytes + bout["stats"].d2h_bytes),
                                              "mode": "detect_descrip_lines: frames up, LSD, LBD on the resident segments, segments + descriptors down (pinned host buffers)"},
                                      "roofline": {"kernel": "k_lbd_grad4", "bound": "hbm", "achieved": grad_bytes / (gm * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                                  "frac": grad_bytes / (gm * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": grad_bytes,
+                                                  "frac": grad_bytes / (gm * 1e-3) / 1e9 / peak, "traffic": lbd_traffic, "algorithmic_bytes_per_launch": grad_bytes,
                                                   "note": "k_lbd_describe gathers 4 B per sample from L1/L2 (the gradient records of a frame's lines stay cached)"},
                                      "gpu_launches": int(bst.n_kernel_launches)}
         except Exception as e:

@@ -6,8 +6,8 @@ the local camera frame x y z qx qy qz qw sx sy sz, normalized_error, 0), gathere
 
   * one VertexSE3Expmap per frame holding the world->camera pose, the first one fixed (:753-762);
   * one VertexCuboid per landmark, initialised from its first valid observation: cube_local_meas.transform_from(Twc) (:745-751;
-    g2o_Object.h:134-140).  The reference's data set has a single landmark; here box k of a frame observes landmark k (the synthetic
-    generator's convention -- data association is not part of the reference);
+    g2o_Object.h:134-140).  The reference's data set has a single landmark; here column 1 of a record names the landmark (data
+    association is the caller's: it is not part of the reference);
   * one EdgeSE3Cuboid per valid record, information diag((2 meas_quality)^2) (:766-781);
   * one EdgeSE3Expmap between consecutive frames, information I6 (:786-799); its measurement is T_j T_i^-1 of the given poses.
 
@@ -74,8 +74,8 @@ def pose7_from_matrix(T):
 
 
 def assemble_graph(records, cams_wc7, n_landmarks):
-    """records: (n, 16) observation records whose column 0 already holds the GLOBAL frame index (row of cams_wc7) and whose box index
-    modulo n_landmarks (column 1) names the landmark.  cams_wc7: (n_frames, 7) camera-to-world poses.  Returns the dict of arrays
+    """records: (n, 16) observation records whose column 0 already holds the GLOBAL frame index (row of cams_wc7) and whose column 1
+    holds the landmark index (taken modulo n_landmarks).  cams_wc7: (n_frames, 7) camera-to-world poses.  Returns the dict of arrays
     Context.ba_set_graph / ba_linearize take, plus 'landmark_seen'."""
     records = np.asarray(records, np.float64).reshape(-1, 16)
     cams_wc7 = np.asarray(cams_wc7, np.float64).reshape(-1, 7)
@@ -94,17 +94,11 @@ def assemble_graph(records, cams_wc7, n_landmarks):
     cubes[:, 6] = 1.0
     cubes[:, 7:10] = 1.0
     seen = np.zeros(n_landmarks, bool)
-    first = {}
-    for i, l in enumerate(lm):                     # first occurrence per landmark (n_landmarks is small; stops early)
-        if l not in first:
-            first[l] = i
-            if len(first) == n_landmarks:
-                break
-    for l, i in first.items():
-        g = se3_mul(cams_wc7[frame[i]], meas[i, :7])   # cuboid::transform_from: pose = Twc * local pose, scale unchanged
-        cubes[l, :7] = g
-        cubes[l, 7:10] = meas[i, 7:10]
-        seen[l] = True
+    if len(lm):
+        ul, fi = np.unique(lm, return_index=True)  # first occurrence per landmark in frame order
+        cubes[ul, :7] = se3_mul(cams_wc7[frame[fi]], meas[fi, :7])   # cuboid::transform_from: pose = Twc * local pose, scale unchanged
+        cubes[ul, 7:10] = meas[fi, 7:10]
+        seen[ul] = True
     info = np.zeros((len(rec), 81))
     info[:, ::10] = ((2.0 * q) ** 2)[:, None]
     ec = (frame.astype(np.int32), lm.astype(np.int32), np.ascontiguousarray(meas), info)

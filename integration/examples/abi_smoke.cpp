@@ -2,7 +2,7 @@
 //
 //   g++ -std=c++17 -I include integration/examples/abi_smoke.cpp cube_slam_wu_b200/libcubeslam_b200.so -Wl,-rpath,$PWD/cube_slam_wu_b200 -o abi_smoke
 //
-// Draws one synthetic gray frame, runs the line detector (csb_lsd_detect_batch), feeds the segments and the gray frame to the cuboid
+// Draws one synthetic gray frame, runs the line detector (csb_lsd_detect_batch) and the line descriptors (csb_lbd_*), feeds the segments and the gray frame to the cuboid
 // proposal path (csb_detect_plan + csb_detect_batch_gray), then linearises a two-camera / one-cuboid graph in both Jacobian modes
 // (csb_ba_set_graph / csb_ba_linearize).  Exit code 0 = every call returned CSB_OK and the results are sane; 77 = no CUDA device
 // (there is no CPU fallback: csb_create fails); anything else = failure.
@@ -57,6 +57,17 @@ int main() {
     CHECK(csb_lsd_detect_batch(ctx, gray.data(), 1, W, H, &lp, seg.data(), &n_seg, &ls));
     std::printf("abi_smoke: %d line segments (%lld regions grown, %d kernel launches)\n", n_seg, (long long)ls.n_regions, ls.n_kernel_launches);
     if (n_seg < 8) return 2;
+
+    // ---- line_lbd_detect::detect_descrip_lines: descriptors of those segments, read in place on the device; the same rows again through
+    //      the host-buffer entry point must give the same bytes
+    csb_lbd_stats bs{};
+    std::vector<uint8_t> desc((size_t)n_seg * 32), desc2((size_t)n_seg * 32);
+    CHECK(csb_lbd_run_on_lsd(ctx, 0, 0));
+    CHECK(csb_lbd_download(ctx, desc.data(), nullptr, nullptr, nullptr, n_seg, &bs));
+    const int32_t off[2] = {0, n_seg};
+    CHECK(csb_lbd_describe_batch(ctx, gray.data(), 1, W, H, seg.data(), off, desc2.data(), nullptr, nullptr));
+    std::printf("abi_smoke: %lld LBD descriptors (%lld gradient samples)\n", (long long)bs.n_lines, (long long)bs.n_samples);
+    if (bs.n_lines != n_seg || std::memcmp(desc.data(), desc2.data(), desc.size()) != 0) return 6;
 
     // ---- detect_3d_cuboid::detect_cuboid
     csb_detect_params dp{1, 1, 1, 0, 1, 0, 1.0, 3.0};

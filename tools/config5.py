@@ -88,13 +88,16 @@ def run(n_frames_total=10000, depth=6, ctx=None, keep=False):
         step_base = (np.arange(world)[:, None] * S + np.arange(S)[None, :]) * F
         has_frame = rec[..., 0] >= 0
         rec[..., 0] = np.where(has_frame, rec[..., 0] + step_base[:, :, None], -1)
-        rec[..., 1] = rec[..., 1] % BPF  # box k of a frame observes landmark k (synthetic convention)
+        # data association (not part of the reference, whose data set has one object): every 2D box of a rank's 64 distinct frames is its own
+        # landmark, observed again each time the rank reuses the frame -> world x 512 landmarks of degree S, consistent measurements
+        rec[..., 1] = rec[..., 1] + (np.arange(world) * n_boxes)[:, None, None]
+        n_landmarks = world * n_boxes
         poses = []
         for r in range(world):
             b = batch if r == 0 else bench.build_batch(r)
             poses.append(np.array([graph.pose7_from_matrix(T) for T in b["T"]]))
         cams_wc = np.concatenate([np.tile(poses[r], (S, 1)) for r in range(world)])
-        g = graph.assemble_graph(rec.reshape(-1, 16), cams_wc, BPF)
+        g = graph.assemble_graph(rec.reshape(-1, 16), cams_wc, n_landmarks)
         t_assemble = time.perf_counter() - t0
         own = ctx is None
         if own:
