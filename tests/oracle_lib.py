@@ -47,7 +47,7 @@ class BAOut(C.Structure):
 
 def build(force=False):
     so = os.path.join(ORACLE_DIR, "liboracle.so")
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle_proposal.cpp", "oracle_ba.cpp", "oracle_lsd.cpp", "oracle_lbd.cpp", "oracle_math.h", "Makefile")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle_proposal.cpp", "oracle_ba.cpp", "oracle_lsd.cpp", "oracle_lbd.cpp", "oracle_edlines.cpp", "oracle_math.h", "Makefile")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
     return so
@@ -263,3 +263,32 @@ def lbd_describe(gray, lines, libm_trig=0):
     if n:
         lib().orc_lbd_describe(_p(gray), w, h, _p(lines), n, int(libm_trig), _p(d72), _p(d32), _p(kl))
     return d72, d32, kl
+
+
+# ---- EDLines line detector (oracle/oracle_edlines.cpp; no GPU path yet) -------------------------------------------------------------
+def edlines_maps(gray, anchor_cap=400000):
+    """thresholded gradient map (int16), direction map (255 / 0), anchors (n, 2) [x, y] in the reference's scan order."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    g = np.zeros((h, w), np.int16); d = np.zeros((h, w), np.uint8); a = np.zeros((anchor_cap, 2), np.uint32)
+    n = lib().orc_edlines_maps(_p(gray), w, h, _p(g), _p(d), _p(a), anchor_cap)
+    return g, d, a[:max(n, 0)].astype(np.int64)
+
+
+def edlines_chains(gray):
+    """edge chains of EDLineDetector::EdgeDrawing: list of (k_i, 2) [x, y] arrays."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    cap = w * h
+    xy = np.zeros((cap, 2), np.uint32); sid = np.zeros(cap // 16 + 2, np.uint32); npx = C.c_int()
+    n = lib().orc_edlines_chains(_p(gray), w, h, _p(xy), cap, _p(sid), len(sid) - 1, C.byref(npx))
+    return [xy[sid[i]:sid[i + 1]].astype(np.int64) for i in range(max(n, 0))]
+
+
+def edlines_detect(gray, filter=True, length_thres=15.0, cap=20000):
+    """key lines (n, 4) float32 [x1 y1 x2 y2] and (n, 3) {direction, numOfPixels, lineLength}."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    out = np.zeros((cap, 4), np.float32); ex = np.zeros((cap, 3), np.float32)
+    n = lib().orc_edlines_detect(_p(gray), w, h, int(filter), C.c_float(length_thres), _p(out), _p(ex), cap)
+    return out[:max(n, 0)].copy(), ex[:max(n, 0)].copy()
