@@ -96,6 +96,12 @@ class LbdStats(C.Structure):
                 ("n_kernel_launches", C.c_int32), ("reserved", C.c_int32), ("gpu_ms_grad", C.c_float), ("gpu_ms_describe", C.c_float)]
 
 
+class EdlinesStats(C.Structure):
+    _fields_ = [("n_lines", C.c_int64), ("n_anchors", C.c_int64), ("n_chain_px", C.c_int64), ("n_chains", C.c_int64), ("h2d_bytes", C.c_int64),
+                ("d2h_bytes", C.c_int64), ("n_kernel_launches", C.c_int32), ("n_frames_failed", C.c_int32),
+                ("gpu_ms_maps", C.c_float), ("gpu_ms_draw", C.c_float), ("gpu_ms_fit", C.c_float), ("reserved", C.c_float)]
+
+
 def lib():
     """Load the CUDA library; raises if it has not been built (there is no fallback path)."""
     global _LIB
@@ -360,6 +366,16 @@ class Context:
         self._chk(lib().csb_lsd_debug_maps(self._h, int(frame), _p(sc), _p(mg), _p(an)))
         return sc, mg, an
 
+    # ---- line detection (EDLines, use_LSD = false) ----------------------------------------------
+    def edlines_detect_batch(self, gray, line_length_thres=15.0, filter=True, max_lines=4096):
+        """csb_edlines_detect_batch(): gray (n, h, w) uint8 -> list of (k_i, 4) float32 arrays [x1 y1 x2 y2], stats."""
+        gray = self._lsd_gray(gray)
+        n, h, w = gray.shape
+        P = LsdParams(float(line_length_thres), int(filter), int(max_lines), 0)
+        lines = np.zeros((n, max_lines, 4), np.float32); cnt = np.zeros(n, np.int32); st = EdlinesStats()
+        self._chk(lib().csb_edlines_detect_batch(self._h, _p(gray), n, w, h, C.byref(P), _p(lines), _p(cnt), C.byref(st)))
+        return [lines[i, :cnt[i]].copy() for i in range(n)], st
+
     # ---- line descriptors (LBD) ----------------------------------------------------------------
     @staticmethod
     def _lbd_pack(lines_per_frame):
@@ -441,15 +457,21 @@ class line_lbd_detect:
         if numoctaves != 1:
             raise CsbError(CSB_ERR_INVALID, "only one octave is supported (every caller in the reference uses one: main_obj.cpp:503, detect_lines.cpp:61)")
         self._ctx = ctx
-        self.use_LSD = True            # line_lbd_allclass.cpp:125 defaults to False (EDLines), which is not ported
+        self.use_LSD = True            # line_lbd_allclass.cpp:125 defaults to False (EDLines)
         self.line_length_thres = 50.0  # line_lbd_allclass.cpp:126; both callers overwrite it with 15
         self.max_lines = 4096
+        # use_LSD = False runs csb_edlines_* -- whose kernels had not been run on hardware when round 1 ended (the device code is validated
+        # on the host, tests/test_edlines_emul.py), so it has to be switched on explicitly until tests/test_zz_edlines_gpu.py has been seen green
+        self.allow_unvalidated_edlines = False
 
     def detect_filter_lines(self, gray_img):
         """line_lbd_allclass.cpp:221-235: gray image(s) -> linesmat_out rows [x1 y1 x2 y2] float32 (one array per frame)."""
-        if not self.use_LSD:
-            raise CsbError(CSB_ERR_INVALID, "use_LSD = false (EDLines) is not implemented on the GPU")
         single = np.asarray(gray_img).ndim == 2
+        if not self.use_LSD:
+            if not self.allow_unvalidated_edlines:
+                raise CsbError(CSB_ERR_INVALID, "use_LSD = false (EDLines): the GPU path awaits its first hardware validation; set allow_unvalidated_edlines")
+            out, _ = self._ctx.edlines_detect_batch(gray_img, self.line_length_thres, True, self.max_lines)
+            return out[0] if single else out
         out, _ = self._ctx.lsd_detect_batch(gray_img, self.line_length_thres, True, self.max_lines)
         return out[0] if single else out
 
@@ -457,7 +479,7 @@ class line_lbd_detect:
         """line_lbd_allclass.cpp:263-281 (the KeyLine overload: octave 0, lineLength > line_length_thres): gray image(s) -> (lines rows
         [x1 y1 x2 y2] float32, line_descrips rows of 32 bytes); the segments stay on the device between the two stages."""
         if not self.use_LSD:
-            raise CsbError(CSB_ERR_INVALID, "use_LSD = false (EDLines) is not implemented on the GPU")
+            raise CsbError(CSB_ERR_INVALID, "detect_descrip_lines with use_LSD = false (EDLines key lines) is not implemented on the GPU")
         single = np.asarray(gray_img).ndim == 2
         c = self._ctx
         c.lsd_upload(gray_img, self.line_length_thres, True, self.max_lines)

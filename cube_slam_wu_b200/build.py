@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libcubeslam_b200.so")
 
-CU_SOURCES = ["proposal.cu", "capi_detect.cu", "ba.cu", "ba_solve.cu", "observe.cu", "distmap.cu", "lsd.cu", "lbd.cu"]
+CU_SOURCES = ["proposal.cu", "capi_detect.cu", "ba.cu", "ba_solve.cu", "observe.cu", "distmap.cu", "lsd.cu", "lbd.cu", "edlines.cu"]
 CPP_SOURCES = ["host_plan.cpp"]
 
 NVCC_FLAGS = [

@@ -55,6 +55,7 @@ void csb_destroy(csb_context* c) {
     ba_release(c->ba);
     lsd_release(c->lsd);
     lbd_release(c->lbd);
+    edlines_release(c->edlines);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->h_epoch) cudaFreeHost(c->h_epoch);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);

@@ -7,6 +7,7 @@
 
 #include "ba.h"
 #include "csb_internal.h"
+#include "edlines.h"
 #include "lbd.h"
 #include "lsd.h"
 #include "proposal.h"
@@ -93,6 +94,7 @@ struct csb_context {
     csb::BAState ba;
     csb::LsdState* lsd = nullptr;  // created by the first csb_lsd_* call
     csb::LbdState* lbd = nullptr;  // created by the first csb_lbd_* call
+    csb::EdState* edlines = nullptr;  // created by the first csb_edlines_* call
 };
 
 #define CSB_CUDA(ctx, call)                                                                   \

@@ -1,0 +1,254 @@
+// edlines.cu -- EDLines line detection on the GPU: the use_LSD = false branch of line_lbd_detect::detect_filter_lines
+// (line_lbd/class/line_lbd_allclass.cpp:130-149, 200-235; what object_slam selects, main_obj.cpp:503-505).  SURVEY.md 8 "next" row f-2.
+//
+// The algorithm lives in edlines_dev.cuh as one-thread-per-item functions (see there for the reference lines and for why: the same source
+// is executed on the host by tests/test_edlines_emul.py, bit for bit against oracle/oracle_edlines.cpp); this file holds the kernel
+// wrappers, the device workspaces and the C ABI.
+//
+//   lbd_launch_grad  (lbd.cu)  blur 5x5 + Sobel -> {dx, dy}                                 HBM / issue bound, shared with the LBD descriptor
+//   k_ed_pixel       thread per pixel: packed gradient + direction map                     HBM bound (4 B read, 2 B written per pixel)
+//   k_ed_anchor      thread per 32 anchor candidates: one word of the column-major bitmap  L2 bound
+//   k_ed_draw        one thread per frame: smart routing, edge chains                      latency bound (sequential by construction; frames run
+//                                                                                          side by side, one warp slot each)
+//   k_ed_fit         thread per chain: least-squares segments, validation, end points      latency bound, chains in parallel
+//   k_ed_emit        one thread per frame: ordered compaction, end-point order, length filter
+//
+// First version: correctness first (the drawing stage uses one lane of a warp per frame).  STATUS: the device code is validated on the host;
+// the kernels below had not run on hardware when this was written (tests/test_zz_edlines_gpu.py runs them in a child process).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "context.h"
+#include "edlines.h"
+#include "edlines_dev.cuh"
+#include "lbd.h"
+
+namespace csb {
+
+__global__ void __launch_bounds__(256) k_ed_pixel(EdBuffers B, EdDims d, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ed_pixel(B, d, i);
+}
+
+__global__ void __launch_bounds__(128) k_ed_anchor(EdBuffers B, EdDims d) {
+    const int word = blockIdx.x * blockDim.x + threadIdx.x, frame = blockIdx.y;
+    if (word >= d.anchor_words) return;
+    const int n_cand = d.nxc * d.nyc;
+    uint32_t bits = 0;
+    for (int b = 0; b < 32; b++) {
+        const int item = word * 32 + b;
+        if (item < n_cand && ed_anchor(B, d, frame, item)) bits |= 1u << b;
+    }
+    B.anchors[(size_t)frame * d.anchor_words + word] = bits;
+}
+
+__global__ void __launch_bounds__(32) k_ed_draw(EdBuffers B, EdDims d) {
+    if (threadIdx.x == 0) ed_draw(B, d, blockIdx.x);
+}
+
+__global__ void __launch_bounds__(64) k_ed_fit(EdBuffers B, EdDims d) {
+    const int chain = blockIdx.x * blockDim.x + threadIdx.x, frame = blockIdx.y;
+    if (chain < B.n_chains[frame]) ed_fit(B, d, frame, chain);
+}
+
+__global__ void __launch_bounds__(32) k_ed_emit(EdBuffers B, EdDims d, int filter, float length_thres, int max_lines) {
+    if (threadIdx.x == 0) ed_emit(B, d, blockIdx.x, filter, length_thres, max_lines);
+}
+
+struct EdState {
+    bool uploaded = false, ran = false, timed_last = false;
+    EdDims d{};
+    csb_lsd_params params{};
+    DevBuf d_gray, d_grad, d_gd, d_anchors, d_edge, d_part1, d_part2, d_chain, d_line, d_sid, d_nch, d_stage, d_lines, d_nlines, d_stats;
+    HostBuf h_gray, h_out;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t h2d_bytes = 0, d2h_bytes = 0;
+    int launches_last = 0;
+};
+
+void edlines_release(EdState*& s) {
+    if (!s) return;
+    DevBuf* bufs[] = {&s->d_gray, &s->d_grad, &s->d_gd, &s->d_anchors, &s->d_edge, &s->d_part1, &s->d_part2, &s->d_chain, &s->d_line,
+                      &s->d_sid, &s->d_nch, &s->d_stage, &s->d_lines, &s->d_nlines, &s->d_stats};
+    for (DevBuf* b : bufs) b->release();
+    s->h_gray.release();
+    s->h_out.release();
+    for (auto& e : s->ev)
+        if (e) cudaEventDestroy(e);
+    delete s;
+    s = nullptr;
+}
+
+static EdBuffers ed_buffers(EdState& s) {
+    EdBuffers B{};
+    B.grad = s.d_grad.as<short2>();
+    B.gd = s.d_gd.as<uint16_t>();
+    B.anchors = s.d_anchors.as<uint32_t>();
+    B.edge = s.d_edge.as<uint32_t>();
+    B.part1 = s.d_part1.as<ushort2>();
+    B.part2 = s.d_part2.as<ushort2>();
+    B.chain_px = s.d_chain.as<ushort2>();
+    B.line_px = s.d_line.as<ushort2>();
+    B.chain_sid = s.d_sid.as<int>();
+    B.n_chains = s.d_nch.as<int>();
+    B.stage = s.d_stage.as<EdLine>();
+    B.lines = s.d_lines.as<float>();
+    B.n_lines = s.d_nlines.as<int>();
+    B.stats = s.d_stats.as<unsigned long long>();
+    return B;
+}
+
+}  // namespace csb
+
+using namespace csb;
+
+extern "C" {
+
+int csb_edlines_upload(csb_context* c, const uint8_t* gray, int n_frames, int width, int height, const csb_lsd_params* params) {
+    if (!c || !gray || !params || n_frames <= 0 || width < 8 || height < 8 || width > 32767 || height > 32767 || (int64_t)width * height > (1 << 24) ||
+        params->max_lines <= 0)
+        return CSB_ERR_INVALID;
+    CSB_CUDA(c, cudaSetDevice(c->device));
+    if (!c->edlines) {
+        c->edlines = new EdState();
+        for (auto& e : c->edlines->ev) CSB_CUDA(c, cudaEventCreate(&e));
+    }
+    EdState& s = *c->edlines;
+    s.uploaded = false;
+    s.ran = false;
+    s.params = *params;
+    s.d = ed_make_dims(width, height, n_frames);
+    const EdDims& d = s.d;
+    const size_t npx = (size_t)width * height * n_frames, nf = (size_t)n_frames;
+    CSB_CUDA(c, s.d_gray.ensure(npx));
+    CSB_CUDA(c, s.d_grad.ensure(npx * 4));
+    CSB_CUDA(c, s.d_gd.ensure(npx * 2));
+    CSB_CUDA(c, s.d_anchors.ensure(nf * d.anchor_words * 4));
+    CSB_CUDA(c, s.d_edge.ensure(nf * d.edge_words * 4));
+    CSB_CUDA(c, s.d_part1.ensure(nf * std::max(d.part_cap, 1) * 4));
+    CSB_CUDA(c, s.d_part2.ensure(nf * std::max(d.part_cap, 1) * 4));
+    CSB_CUDA(c, s.d_chain.ensure(nf * std::max(d.chain_cap, 1) * 4));
+    CSB_CUDA(c, s.d_line.ensure(nf * std::max(d.chain_cap, 1) * 4));
+    CSB_CUDA(c, s.d_sid.ensure(nf * (d.max_edges + 2) * 4));
+    CSB_CUDA(c, s.d_nch.ensure(nf * 4));
+    CSB_CUDA(c, s.d_stage.ensure(nf * d.stage_cap * sizeof(EdLine)));
+    CSB_CUDA(c, s.d_lines.ensure(nf * params->max_lines * 16));
+    CSB_CUDA(c, s.d_nlines.ensure(nf * 4));
+    CSB_CUDA(c, s.d_stats.ensure(64));
+    cudaPointerAttributes pa{};
+    const bool pinned = cudaPointerGetAttributes(&pa, gray) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {
+        CSB_CUDA(c, cudaMemcpyAsync(s.d_gray.p, gray, npx, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        CSB_CUDA(c, cudaStreamSynchronize(c->stream));  // the staging buffer may still feed an earlier upload
+        CSB_CUDA(c, s.h_gray.ensure(npx));
+        std::memcpy(s.h_gray.p, gray, npx);
+        CSB_CUDA(c, cudaMemcpyAsync(s.d_gray.p, s.h_gray.p, npx, cudaMemcpyHostToDevice, c->stream));
+    }
+    s.h2d_bytes = (int64_t)npx;
+    s.uploaded = true;
+    return CSB_OK;
+}
+
+int csb_edlines_run(csb_context* c, int timed) {
+    if (!c || !c->edlines || !c->edlines->uploaded) {
+        if (c) c->err = "csb_edlines_run before csb_edlines_upload";
+        return CSB_ERR_STATE;
+    }
+    EdState& s = *c->edlines;
+    CSB_CUDA(c, cudaSetDevice(c->device));
+    const EdDims& d = s.d;
+    EdBuffers B = ed_buffers(s);
+    cudaStream_t st = c->stream;
+    const size_t npx = (size_t)d.w * d.h * d.n_frames;
+    CSB_CUDA(c, cudaMemsetAsync(s.d_stats.p, 0, 64, st));
+    CSB_CUDA(c, cudaMemsetAsync(s.d_edge.p, 0, (size_t)d.n_frames * d.edge_words * 4, st));
+    if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[0], st));
+    lbd_launch_grad(s.d_gray.as<uint8_t>(), s.d_grad.as<short2>(), d.w, d.h, d.n_frames, st);
+    k_ed_pixel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(B, d, npx);
+    k_ed_anchor<<<dim3((d.anchor_words + 127) / 128, d.n_frames), 128, 0, st>>>(B, d);
+    if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[1], st));
+    k_ed_draw<<<d.n_frames, 32, 0, st>>>(B, d);
+    if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[2], st));
+    k_ed_fit<<<dim3((d.max_edges + 1 + 63) / 64, d.n_frames), 64, 0, st>>>(B, d);
+    k_ed_emit<<<d.n_frames, 32, 0, st>>>(B, d, s.params.filter, s.params.line_length_thres, s.params.max_lines);
+    if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[3], st));
+    CSB_CUDA(c, cudaGetLastError());
+    s.launches_last = 6;
+    s.timed_last = timed != 0;
+    s.ran = true;
+    return CSB_OK;
+}
+
+int csb_edlines_download(csb_context* c, float* lines_out, int32_t* n_lines_out, csb_edlines_stats* stats) {
+    if (!c || !c->edlines || !c->edlines->ran) {
+        if (c) c->err = "csb_edlines_download before csb_edlines_run";
+        return CSB_ERR_STATE;
+    }
+    EdState& s = *c->edlines;
+    CSB_CUDA(c, cudaSetDevice(c->device));
+    const int nf = s.d.n_frames, cap = s.params.max_lines;
+    const size_t lb = (size_t)nf * cap * 16, nb = (size_t)nf * 4;
+    CSB_CUDA(c, s.h_out.ensure(lb + 2 * nb + 64));
+    char* h = s.h_out.as<char>();
+    CSB_CUDA(c, cudaMemcpyAsync(h + lb, s.d_nlines.p, nb, cudaMemcpyDeviceToHost, c->stream));
+    CSB_CUDA(c, cudaMemcpyAsync(h + lb + nb, s.d_nch.p, nb, cudaMemcpyDeviceToHost, c->stream));
+    CSB_CUDA(c, cudaMemcpyAsync(h + lb + 2 * nb, s.d_stats.p, 64, cudaMemcpyDeviceToHost, c->stream));
+    CSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    const int32_t* nl = reinterpret_cast<const int32_t*>(h + lb);
+    const int32_t* nch = reinterpret_cast<const int32_t*>(h + lb + nb);
+    int rows = 0;
+    for (int f = 0; f < nf; f++) rows = std::max(rows, std::min(nl[f], cap));
+    const size_t pitch = (size_t)cap * 16;
+    if (rows > 0) CSB_CUDA(c, cudaMemcpy2DAsync(h, pitch, s.d_lines.p, pitch, (size_t)rows * 16, nf, cudaMemcpyDeviceToHost, c->stream));
+    CSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    s.d2h_bytes = (int64_t)((size_t)rows * 16 * nf + 2 * nb + 64);
+    bool overflow = false;
+    int64_t total = 0;
+    int failed = 0;
+    for (int f = 0; f < nf; f++) {
+        overflow |= nl[f] > cap;
+        total += std::min(nl[f], cap);
+        failed += nch[f] < 0;
+    }
+    if (lines_out)
+        for (int f = 0; f < nf; f++) std::memcpy(reinterpret_cast<char*>(lines_out) + f * pitch, h + f * pitch, (size_t)std::min(nl[f], cap) * 16);
+    if (n_lines_out) std::memcpy(n_lines_out, nl, nb);
+    if (stats) {
+        const unsigned long long* st = reinterpret_cast<const unsigned long long*>(h + lb + 2 * nb);
+        std::memset(stats, 0, sizeof(*stats));
+        stats->n_lines = total;
+        stats->n_anchors = (int64_t)st[0];
+        stats->n_chain_px = (int64_t)st[1];
+        stats->n_chains = (int64_t)st[2];
+        stats->h2d_bytes = s.h2d_bytes;
+        stats->d2h_bytes = s.d2h_bytes;
+        stats->n_kernel_launches = s.launches_last;
+        stats->n_frames_failed = failed;
+        if (s.timed_last) {
+            cudaEventElapsedTime(&stats->gpu_ms_maps, s.ev[0], s.ev[1]);
+            cudaEventElapsedTime(&stats->gpu_ms_draw, s.ev[1], s.ev[2]);
+            cudaEventElapsedTime(&stats->gpu_ms_fit, s.ev[2], s.ev[3]);
+        }
+    }
+    if (overflow) {
+        c->err = "csb_edlines: more segments than max_lines in at least one frame";
+        return CSB_ERR_CAPACITY;
+    }
+    return CSB_OK;
+}
+
+int csb_edlines_detect_batch(csb_context* c, const uint8_t* gray, int n_frames, int width, int height, const csb_lsd_params* params, float* lines_out,
+                             int32_t* n_lines_out, csb_edlines_stats* stats) {
+    int rc = csb_edlines_upload(c, gray, n_frames, width, height, params);
+    if (rc != CSB_OK) return rc;
+    rc = csb_edlines_run(c, stats != nullptr);
+    if (rc != CSB_OK) return rc;
+    return csb_edlines_download(c, lines_out, n_lines_out, stats);
+}
+
+}  // extern "C"

@@ -424,6 +424,13 @@ struct LbdState {
     const int* src_counts = nullptr;
 };
 
+void lbd_launch_grad(const uint8_t* gray, short2* grad, int w, int h, int n_frames, cudaStream_t st) {
+    if (w % 4 == 0)
+        k_lbd_grad4<<<dim3((w + L4_TW - 1) / L4_TW, (h + L4_TH - 1) / L4_TH, n_frames), L4_THREADS, 0, st>>>(gray, grad, w, h);
+    else
+        k_lbd_grad<<<dim3((w + LG_TW - 1) / LG_TW, (h + LG_TH - 1) / LG_TH, n_frames), LG_THREADS, 0, st>>>(gray, grad, w, h);
+}
+
 void lbd_release(LbdState*& s) {
     if (!s) return;
     DevBuf* bufs[] = {&s->d_gray, &s->d_lines, &s->d_counts, &s->d_prefix, &s->d_grad, &s->d_desc, &s->d_descf, &s->d_keyl, &s->d_ctr};
@@ -486,10 +493,7 @@ static int lbd_outputs(csb_context* c, LbdState& s) {
 static int lbd_launch(csb_context* c, LbdState& s, int timed) {
     cudaStream_t st = c->stream;
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[0], st));
-    if (s.w % 4 == 0)
-        k_lbd_grad4<<<dim3((s.w + L4_TW - 1) / L4_TW, (s.h + L4_TH - 1) / L4_TH, s.n_frames), L4_THREADS, 0, st>>>(s.src_gray, s.d_grad.as<short2>(), s.w, s.h);
-    else
-        k_lbd_grad<<<dim3((s.w + LG_TW - 1) / LG_TW, (s.h + LG_TH - 1) / LG_TH, s.n_frames), LG_THREADS, 0, st>>>(s.src_gray, s.d_grad.as<short2>(), s.w, s.h);
+    lbd_launch_grad(s.src_gray, s.d_grad.as<short2>(), s.w, s.h, s.n_frames, st);
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[1], st));
     k_lbd_prefix<<<1, 1024, 0, st>>>(s.src_counts, s.n_frames, s.stride, s.d_prefix.as<int>(), s.d_ctr.as<unsigned long long>());
     LbdArgs A{};

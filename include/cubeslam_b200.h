@@ -320,6 +320,31 @@ int csb_lbd_download(csb_context* ctx, uint8_t* desc_out, float* desc_float_out,
 /* Parity/debug: the int16 Sobel images of one frame after a run (width x height each). */
 int csb_lbd_debug_gradients(csb_context* ctx, int frame, int16_t* dx_out, int16_t* dy_out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Line detection, EDLines branch: line_lbd_detect::detect_filter_lines with use_LSD = false
+ * ------------------------------------------------------------------------------------------------
+ * What object_slam selects (object_slam/src/main_obj.cpp:503-505): BinaryDescriptor::detect (line_lbd/libs/binary_descriptor.cpp:486-590,
+ * one octave) -> OctaveKeyLines (:796-1148: GaussianBlur 5x5, EDline, end-point order) -> EDLineDetector::EdgeDrawing (:1583-2380) /
+ * EDline (:2383-2630) / LineValidation_ (:2793-2873) with the constructor's parameters (:1515-1525: gradient threshold 80, anchor
+ * threshold 8, scan interval 2, minimum line length 15, fit error 1.6) -> filter_lines (line_lbd_allclass.cpp:200-208).
+ * Same output rows as csb_lsd_*: float32 [x1 y1 x2 y2] (startPoint, endPoint), in the reference's order.  Takes csb_lsd_params
+ * (line_length_thres, filter: 1 = octave 0 and lineLength > line_length_thres, 0 = every key line; max_lines; unit_link_deg unused).
+ * STATUS: the device code (csrc/edlines_dev.cuh) is executed on the host against the oracle by the CPU tests; see DESIGN.md 3e. */
+typedef struct csb_edlines_stats {
+    int64_t n_lines;     /* segments written over the whole batch */
+    int64_t n_anchors, n_chain_px, n_chains;
+    int64_t h2d_bytes, d2h_bytes;
+    int32_t n_kernel_launches;
+    int32_t n_frames_failed; /* frames that hit EdgeDrawing's capacity errors (the reference prints "Line Detection not finished": no lines) */
+    float gpu_ms_maps, gpu_ms_draw, gpu_ms_fit, reserved;
+} csb_edlines_stats;
+
+int csb_edlines_detect_batch(csb_context* ctx, const uint8_t* gray, int n_frames, int width, int height, const csb_lsd_params* params,
+                             float* lines_out, int32_t* n_lines_out, csb_edlines_stats* stats);
+int csb_edlines_upload(csb_context* ctx, const uint8_t* gray, int n_frames, int width, int height, const csb_lsd_params* params);
+int csb_edlines_run(csb_context* ctx, int timed);
+int csb_edlines_download(csb_context* ctx, float* lines_out, int32_t* n_lines_out, csb_edlines_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

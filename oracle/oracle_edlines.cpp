@@ -29,6 +29,8 @@
 #include <cstring>
 #include <vector>
 
+#include "oracle_math.h"
+
 extern "C" void orc_lbd_gradients(const uint8_t* gray, int w, int h, uint8_t* blur_out, int16_t* dx_out, int16_t* dy_out);  // oracle_lbd.cpp
 
 namespace {
@@ -40,6 +42,11 @@ constexpr short GRADIENT_THRESHOLD = 80;
 constexpr int ANCHOR_THRESHOLD = 8, SCAN_INTERVALS = 2, MIN_LINE_LEN = 15;
 constexpr double LINE_FIT_ERR_THRESHOLD = 1.6;
 constexpr double MLN10 = 2.30258509299404568402;
+
+// Specified arithmetic (shared with csrc/edlines_dev.cuh): LineValidation_ calls libm atan2 per chain pixel and for the line direction; both
+// sides use det_atan2 (oracle_math.h / csb_math.cuh) unless g_libm_trig selects the literal libm call.
+int g_libm_trig = 0;
+inline double sp_atan2(double y, double x) { return g_libm_trig ? std::atan2(y, x) : orc::det_atan2(y, x); }
 
 struct Maps {
     int w = 0, h = 0;
@@ -286,14 +293,14 @@ struct Detector {
             const int index = ys[offsetS + i] * m.w + xs[offsetS + i];
             meanGX += m.dx[index];
             meanGY += m.dy[index];
-            pointDirection.push_back(std::atan2(-(double)m.dx[index], (double)m.dy[index]));
+            pointDirection.push_back(sp_atan2(-(double)m.dx[index], (double)m.dy[index]));
         }
         const double dx = std::fabs(lineEqu[1]), dy = std::fabs(lineEqu[0]);
         if (meanGX == 0 && meanGY == 0) return false;
-        if (meanGX > 0 && meanGY >= 0) direction = (float)std::atan2(-dy, dx);
-        if (meanGX <= 0 && meanGY > 0) direction = (float)std::atan2(dy, dx);
-        if (meanGX < 0 && meanGY <= 0) direction = (float)std::atan2(dy, -dx);
-        if (meanGX >= 0 && meanGY < 0) direction = (float)std::atan2(-dy, -dx);
+        if (meanGX > 0 && meanGY >= 0) direction = (float)sp_atan2(-dy, dx);
+        if (meanGX <= 0 && meanGY > 0) direction = (float)sp_atan2(dy, dx);
+        if (meanGX < 0 && meanGY <= 0) direction = (float)sp_atan2(dy, -dx);
+        if (meanGX >= 0 && meanGY < 0) direction = (float)sp_atan2(-dy, -dx);
         if (std::fabs(direction) < 0.15 || M_PI - std::fabs(direction) < 0.15) {
             if (std::fabs(lineEqu[2]) < 10 || std::fabs((double)(unsigned)m.h - std::fabs(lineEqu[2])) < 10) return false;
         }
@@ -386,6 +393,8 @@ struct Detector {
 }  // namespace
 
 extern "C" {
+
+void orc_edlines_set_libm_trig(int on) { g_libm_trig = on; }
 
 // gradient map (thresholded, / 4), direction map (255 / 0) and the anchors in scan order (x0 y0 x1 y1 ...); returns the anchor count
 int orc_edlines_maps(const uint8_t* gray, int w, int h, int16_t* g_out, uint8_t* dir_out, uint32_t* anchors_out, int anchor_cap) {

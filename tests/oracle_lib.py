@@ -285,8 +285,9 @@ def edlines_chains(gray):
     return [xy[sid[i]:sid[i + 1]].astype(np.int64) for i in range(max(n, 0))]
 
 
-def edlines_detect(gray, filter=True, length_thres=15.0, cap=20000):
+def edlines_detect(gray, filter=True, length_thres=15.0, cap=20000, libm_trig=False):
     """key lines (n, 4) float32 [x1 y1 x2 y2] and (n, 3) {direction, numOfPixels, lineLength}."""
+    lib().orc_edlines_set_libm_trig(int(libm_trig))
     gray = np.ascontiguousarray(gray, np.uint8)
     h, w = gray.shape
     out = np.zeros((cap, 4), np.float32); ex = np.zeros((cap, 3), np.float32)

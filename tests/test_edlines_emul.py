@@ -1,0 +1,69 @@
+"""CPU execution of the EDLines device code (cube_slam_wu_b200/csrc/edlines_dev.cuh) against the oracle (oracle/oracle_edlines.cpp).
+
+The EDLines stages are one-thread-per-item functions without shared memory or synchronisation; tests/emul/edlines_emul.cpp compiles the
+same header with g++ and loops over the items, so these tests execute the code the CUDA kernels wrap -- bit for bit against the oracle --
+without a GPU.  (The kernels' launch glue is covered by tests/test_edlines_gpu.py on a B200.)"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CUDA_INC = "/usr/local/cuda/include"
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    if not os.path.exists(os.path.join(CUDA_INC, "vector_types.h")):
+        pytest.skip("CUDA headers not found")
+    so = str(tmp_path_factory.mktemp("emul") / "libedlines_emul.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-I", CUDA_INC,
+                           os.path.join(HERE, "emul", "edlines_emul.cpp"), "-o", so])
+    return C.CDLL(so)
+
+
+def _run(emul, oracle, gray, filter=True, thres=15.0, cap=20000):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    _, dx, dy = oracle.lbd_gradients(gray)
+    out = np.zeros((cap, 4), np.float32); st = np.zeros(4, np.int64); nch = C.c_int()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    n = emul.emul_edlines_detect(vp(dx), vp(dy), w, h, int(filter), C.c_float(thres), vp(out), cap, vp(st), C.byref(nch))
+    return out[:n].copy(), st, nch.value
+
+
+def _same(a, b):
+    return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_device_code_matches_oracle_on_synthetic_frames(emul, oracle):
+    from cube_slam_wu_b200 import synth
+    total = 0
+    for (w, h, seed, kw) in ((640, 480, 3, {}), (641, 479, 4, dict(texture=1.0, noise_sigma=5.0)), (1242, 375, 5, {}), (97, 61, 6, {})):
+        gray = synth.make_lsd_frames(1, w, h, seed=seed, **kw)[0]
+        for filt, thr in ((True, 15.0), (False, 0.0), (True, 50.0)):
+            got, st, nch = _run(emul, oracle, gray, filt, thr)
+            ref, _ = oracle.edlines_detect(gray, filter=filt, length_thres=thr)
+            assert _same(got, ref), "%dx%d filter=%s: %d vs %d lines" % (w, h, filt, len(got), len(ref))
+        chains = oracle.edlines_chains(gray)
+        _, _, anchors = oracle.edlines_maps(gray)
+        assert nch == len(chains) and st[2] == len(chains) and st[1] == sum(len(c) for c in chains) and st[0] == len(anchors)
+        total += len(ref)
+    assert total > 50
+
+
+def test_device_code_on_the_reference_image_and_noise(emul, oracle):
+    d = np.load(os.path.join(HERE, "golden", "lsd_407.npz"))
+    got, st, nch = _run(emul, oracle, d["gray"])
+    ref, _ = oracle.edlines_detect(d["gray"])
+    assert _same(got, ref) and len(ref) > 100
+    rng = np.random.default_rng(1)
+    noise = rng.integers(0, 256, (120, 160), dtype=np.uint8)     # anchors everywhere, thousands of short walks
+    got, st, nch = _run(emul, oracle, noise, False, 0.0)
+    ref, _ = oracle.edlines_detect(noise, filter=False)
+    assert _same(got, ref)
+    flat = np.full((40, 60), 77, np.uint8)
+    got, st, nch = _run(emul, oracle, flat)
+    assert len(got) == 0 and nch == 0

@@ -79,9 +79,11 @@ def test_segments_are_consistent(oracle):
     # a longer threshold keeps a subset
     long_lines, _ = oracle.edlines_detect(gray, length_thres=50.0)
     assert 0 < len(long_lines) < len(lines)
-    # deterministic
+    # deterministic; the specified atan2 and libm's give the same segments here (they differ by <= 1 ulp and only feed comparisons / one float)
     again, _ = oracle.edlines_detect(gray)
     assert np.array_equal(again, lines)
+    lit, lit_extra = oracle.edlines_detect(gray, libm_trig=True)
+    assert np.array_equal(lit, lines) and np.abs(lit_extra[:, 0] - extra[:, 0]).max() <= 2.4e-7
 
 
 def test_reference_image_edlines_vs_lsd(oracle):

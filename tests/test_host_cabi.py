@@ -100,6 +100,12 @@ def test_null_context_lbd(csb):
     assert L.csb_lbd_download(None, None, None, None, None, C.c_int64(0), None) == csb.CSB_ERR_STATE
     assert L.csb_lbd_debug_gradients(None, 0, None, None) == csb.CSB_ERR_STATE
     assert C.sizeof(csb.LbdStats) == 4 * 8 + 2 * 4 + 2 * 4
+    p = csb.LsdParams(15.0, 1, 16, 0)
+    assert L.csb_edlines_detect_batch(None, vp(img), 1, 16, 16, C.byref(p), None, None, None) == csb.CSB_ERR_INVALID
+    assert L.csb_edlines_upload(None, vp(img), 1, 16, 16, C.byref(p)) == csb.CSB_ERR_INVALID
+    assert L.csb_edlines_run(None, 0) == csb.CSB_ERR_STATE
+    assert L.csb_edlines_download(None, None, None, None) == csb.CSB_ERR_STATE
+    assert C.sizeof(csb.EdlinesStats) == 6 * 8 + 2 * 4 + 4 * 4
 
 
 def test_line_lbd_mirror_refuses_unported_modes(csb):
