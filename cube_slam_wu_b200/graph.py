@@ -73,6 +73,19 @@ def pose7_from_matrix(T):
     return np.concatenate([T[:3, 3], rot_to_quat(T[:3, :3])])
 
 
+def globalise_records(rec, frames_per_step, boxes_per_rank):
+    """rec: (world, steps, boxes_per_rank, 16) records as gathered over the ranks (rank-major), every rank having pushed `steps` passes over
+    its own `frames_per_step` frames.  Rewrites, in place, column 0 to the global frame index ((rank * steps + step) * frames_per_step + local
+    frame; -1 stays -1) and column 1 to the global landmark index (rank * boxes_per_rank + box: every 2D box of a rank's frames is its own
+    landmark, observed again at every pass).  Returns (records as (n, 16), number of landmarks)."""
+    world, steps = rec.shape[0], rec.shape[1]
+    step_base = (np.arange(world)[:, None] * steps + np.arange(steps)[None, :]) * frames_per_step
+    has_frame = rec[..., 0] >= 0
+    rec[..., 0] = np.where(has_frame, rec[..., 0] + step_base[:, :, None], -1)
+    rec[..., 1] = rec[..., 1] + (np.arange(world) * boxes_per_rank)[:, None, None]
+    return rec.reshape(-1, 16), world * boxes_per_rank
+
+
 def assemble_graph(records, cams_wc7, n_landmarks):
     """records: (n, 16) observation records whose column 0 already holds the GLOBAL frame index (row of cams_wc7) and whose column 1
     holds the landmark index (taken modulo n_landmarks).  cams_wc7: (n_frames, 7) camera-to-world poses.  Returns the dict of arrays

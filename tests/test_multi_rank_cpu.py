@@ -72,3 +72,75 @@ def test_two_rank_observation_allgather(tmp_path):
     qn = np.linalg.norm(allr[valid][:, 7:11], axis=1)
     assert np.allclose(qn, 1.0, atol=1e-9)                    # unit quaternions in the gathered measurements
     assert np.all((allr[valid][:, 3] >= 0.25) & (allr[valid][:, 3] <= 0.75))  # meas_quality = (1 - err + 0.5)/2, err in [0,1]
+
+
+def _records_from_oracle(batch, res, rank_tag=None):
+    """observation records (layout of csrc/observe.cu) of one rank's batch, produced by the oracle"""
+    import ctypes as C
+    nb = len(batch["boxes"])
+    rec = np.zeros((nb, 16))
+    for f, R in enumerate(res):
+        b0, b1 = batch["box_ranges"][f]
+        for b in range(b1 - b0):
+            rec[b0 + b, 0] = f; rec[b0 + b, 1] = b0 + b
+            if len(R.boxes[b]["sorted"]):
+                c = R.boxes[b]["raw"][R.boxes[b]["sorted"][0]]
+                q = C.c_double(); loc = np.zeros(10)
+                O.lib().orc_observation((C.c_double * 3)(*c.pos), C.c_double(c.rotY), (C.c_double * 3)(*c.scale), C.c_double(c.normalized_error),
+                                        C.c_double(c.camera_roll_delta), C.c_double(c.camera_pitch_delta),
+                                        np.ascontiguousarray(batch["T"][f]).ctypes.data_as(C.c_void_p), 1, C.byref(q), loc.ctypes.data_as(C.c_void_p))
+                rec[b0 + b, 2] = 1; rec[b0 + b, 3] = q.value; rec[b0 + b, 4:14] = loc; rec[b0 + b, 14] = c.normalized_error
+    return rec
+
+
+def _worker_config5(rank, world, port, q):
+    """BASELINE config #5's exchange and graph assembly (tools/config5.py) with two ranks on the CPU: every rank makes `S` passes over its own
+    frames, the records are exchanged with ONE all_gather, rank 0 globalises the indices, assembles the graph and linearises it (oracle)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import helpers as H
+    from cube_slam_wu_b200 import graph, synth
+    F, BPF, S = 2, 3, 2
+    batch = synth.make_kitti_batch(F, boxes_per_frame=BPF, seed=20260925 + rank)
+    P = type("P", (), dict(consider_config_1=1, consider_config_2=1, whether_sample_cam_roll_pitch=1, whether_sample_bbox_height=0, max_cuboid_num=1,
+                           nominal_skew_ratio=1.0, max_cut_skew=3.0))
+    rec1 = _records_from_oracle(batch, H.run_oracle(batch, P, leak=0))
+    n_boxes = len(rec1)
+    mine = torch.from_numpy(np.stack([rec1] * S).ravel().copy())          # S passes over the same frames
+    allr = torch.zeros(world * mine.numel(), dtype=torch.float64)
+    dist.all_gather_into_tensor(allr, mine)
+    poses_mine = torch.from_numpy(np.array([graph.pose7_from_matrix(T) for T in batch["T"]]).ravel().copy())
+    poses_all = torch.zeros(world * poses_mine.numel(), dtype=torch.float64)
+    dist.all_gather_into_tensor(poses_all, poses_mine)                    # the test's way to know the other rank's camera poses
+    if rank == 0:
+        rec = allr.numpy().reshape(world, S, n_boxes, 16).copy()
+        flat, n_lm = graph.globalise_records(rec, F, n_boxes)
+        poses = poses_all.numpy().reshape(world, F, 7)
+        cams_wc = np.concatenate([np.tile(poses[r], (S, 1)) for r in range(world)])
+        g = graph.assemble_graph(flat, cams_wc, n_lm)
+        E = O.ba_edges(ec=g["ec"], ep=None, eo=g["eo"])
+        lin = O.ba_linearize(g["cams7"], g["cam_fixed"], g["cubes10"], g["cube_fixed"], E)
+        out = dict(n_cam=len(g["cams7"]), n_lm=n_lm, seen=int(g["landmark_seen"].sum()), n_ec=len(g["ec"][0]), n_eo=len(g["eo"][0]),
+                   valid=int((rec[..., 2] == 1).sum()), ec_cam=g["ec"][0], ec_cube=g["ec"][1], max_err=float(np.abs(lin["ec_err"]).max()),
+                   max_odo=float(np.abs(lin["eo_err"]).max()), frames=flat[:, 0].copy(), valid_mask=flat[:, 2].copy(), n_boxes=n_boxes)
+        np.save(os.environ["CSB_TEST_OUT"], np.array([out], dtype=object), allow_pickle=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_config5_graph_assembly(tmp_path):
+    port = _free_port()
+    out = str(tmp_path / "c5.npy")
+    os.environ["CSB_TEST_OUT"] = out
+    mp.spawn(_worker_config5, args=(2, port, None), nprocs=2, join=True)
+    d = np.load(out, allow_pickle=True)[0]
+    F, S, world = 2, 2, 2
+    assert d["n_cam"] == world * S * F and d["n_eo"] == d["n_cam"] - 1
+    assert d["n_lm"] == world * d["n_boxes"] and d["n_ec"] == d["valid"] and d["valid"] >= 8
+    assert d["seen"] == d["valid"] // S                                  # every landmark is observed once per pass
+    # rank 1's records landed on rank 1's cameras and landmarks
+    assert set(np.unique(d["frames"][d["valid_mask"] == 1])) <= set(range(world * S * F))
+    r1 = d["ec_cam"] >= S * F
+    assert r1.any() and (d["ec_cube"][r1] >= d["n_boxes"]).all() and (d["ec_cube"][~r1] < d["n_boxes"]).all()
+    # consistent measurements: landmarks initialised from their first observation and re-observed from the same pose
+    assert d["max_err"] < 1e-9 and d["max_odo"] < 1e-9

@@ -84,20 +84,15 @@ def run(n_frames_total=10000, depth=6, ctx=None, keep=False):
     out = None
     if rank == 0:
         t0 = time.perf_counter()
-        # global frame index of a record: ((rank * S + step) * F + local frame); every rank reuses its own 64 frames
-        step_base = (np.arange(world)[:, None] * S + np.arange(S)[None, :]) * F
-        has_frame = rec[..., 0] >= 0
-        rec[..., 0] = np.where(has_frame, rec[..., 0] + step_base[:, :, None], -1)
-        # data association (not part of the reference, whose data set has one object): every 2D box of a rank's 64 distinct frames is its own
-        # landmark, observed again each time the rank reuses the frame -> world x 512 landmarks of degree S, consistent measurements
-        rec[..., 1] = rec[..., 1] + (np.arange(world) * n_boxes)[:, None, None]
-        n_landmarks = world * n_boxes
+        # global frame / landmark indices (graph.globalise_records): every rank reuses its own 64 frames; data association is not part of the
+        # reference (its data set has one object): every 2D box of a rank's frames is its own landmark, observed again at every pass
+        flat, n_landmarks = graph.globalise_records(rec, F, n_boxes)
         poses = []
         for r in range(world):
             b = batch if r == 0 else bench.build_batch(r)
             poses.append(np.array([graph.pose7_from_matrix(T) for T in b["T"]]))
         cams_wc = np.concatenate([np.tile(poses[r], (S, 1)) for r in range(world)])
-        g = graph.assemble_graph(rec.reshape(-1, 16), cams_wc, n_landmarks)
+        g = graph.assemble_graph(flat, cams_wc, n_landmarks)
         t_assemble = time.perf_counter() - t0
         own = ctx is None
         if own:
