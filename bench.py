@@ -48,6 +48,41 @@ LSD_FRAMES, LSD_W, LSD_H = 256, 640, 480  # BASELINE config #3
 LSD_ALGO_BYTES_PER_FRAME = LSD_W * LSD_H + 16.0 * round(LSD_W * 0.8) * round(LSD_H * 0.8)
 
 
+EDLINES_CHILD = r'''
+import sys, os, json, time
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import numpy as np
+import cube_slam_wu_b200 as csb
+from cube_slam_wu_b200 import synth
+import oracle_lib as O
+base = synth.make_lsd_frames(32, %(w)d, %(h)d, seed=20260927)
+frames = np.ascontiguousarray(np.concatenate([base] * (%(n)d // 32)))
+ctx = csb.Context(0)
+ctx.edlines_detect_batch(frames)
+ms = []
+for _ in range(3):
+    lines, st = ctx.edlines_detect_batch(frames)
+    ms.append((st.gpu_ms_maps, st.gpu_ms_draw, st.gpu_ms_fit))
+ok = True
+for f in range(4):
+    ref, _ = O.edlines_detect(frames[f])
+    ok = ok and lines[f].shape == ref.shape and np.array_equal(lines[f].view(np.uint32), ref.view(np.uint32))
+t0 = time.perf_counter(); r = 0
+while time.perf_counter() - t0 < 1.0:
+    O.edlines_detect(frames[r %% 32]); r += 1
+cpu = r / (time.perf_counter() - t0)
+m = np.mean(np.array(ms), axis=0)
+print(json.dumps({"metric": "edlines_frames_per_sec", "value": %(n)d / (float(m.sum()) * 1e-3), "unit": "frames/s",
+                  "config": "%(n)d synthetic %(w)dx%(h)d frames, EDLines branch of detect_filter_lines (line_length_thres 15), resident kernels",
+                  "kernel_ms": {"maps (blur, Sobel, gradient map, anchors)": float(m[0]), "draw (smart routing)": float(m[1]), "fit (segments, validation, emit)": float(m[2])},
+                  "segments": int(st.n_lines), "chains": int(st.n_chains), "chain_px": int(st.n_chain_px), "frames_failed": int(st.n_frames_failed),
+                  "bit_identical_to_oracle_on_4_frames": bool(ok), "gpu_launches": int(st.n_kernel_launches),
+                  "cpu_baseline": {"value": cpu, "unit": "frames/s", "cores": 1, "kind": "port", "sample": "%%d frames, single thread" %% r},
+                  "note": "first hardware run of these kernels happens in this child process (DESIGN.md 3e)"}))
+ctx.close()
+'''
+
+
 def workload_config(n_gpus):
     return {"workload": "config#2 batched proposal scoring: %d KITTI-shape frames x %d boxes per GPU, roll/pitch sampling on, both configs"
                         % (FRAMES_PER_GPU, BOXES_PER_FRAME),
@@ -602,6 +637,19 @@ def run_ours(args, rank, local_rank, world):
                                                              "sample": "%d frames (blur + Sobel + descriptors of their segments), single thread" % r}
             except Exception as e:
                 out["cpu_baseline"] = {"error": str(e)}
+        # ---- EDLines (use_LSD = false): its kernels had not run on hardware when round 1 ended, so this section runs them in a
+        #      CHILD process (own CUDA context, time limit) and checks four frames against the oracle there; whatever happens, the line prints
+        if world == 1:
+            try:
+                code = EDLINES_CHILD % {"root": ROOT, "n": LSD_FRAMES, "w": LSD_W, "h": LSD_H}
+                r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=180)
+                last = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
+                if r.returncode == 0 and last:
+                    out["lsd"]["edlines"] = json.loads(last[-1])
+                else:
+                    out["lsd"]["edlines"] = {"error": (r.stdout + r.stderr)[-600:]}
+            except Exception as e:
+                out.setdefault("lsd", {})["edlines"] = {"error": str(e)}
         print(json.dumps(out), flush=True)  # flush: under torchrun stdout is a block-buffered pipe/file
         sys.stdout.flush()
     ctx.close()
