@@ -287,4 +287,34 @@ int orc_lbd_describe(const uint8_t* gray, int w, int h, const float* lines, int 
     return n;
 }
 
+// Descriptors for key lines whose fields come from a detector other than LSDDetector (EDLines: OctaveKeyLines fills direction =
+// lineDirection_, numOfPixels = the pixel count of the fitted chain segment, and the end points as projected, unclamped;
+// binary_descriptor.cpp:1045-1140).  fields: n x 2 float {direction, numOfPixels}.
+int orc_lbd_describe_keylines(const uint8_t* gray, int w, int h, const float* lines, const float* fields, int n, int libm_trig, float* desc72_out,
+                              uint8_t* desc32_out) {
+    if (n <= 0) return 0;
+    std::vector<int16_t> dx((size_t)w * h), dy((size_t)w * h);
+    orc_lbd_gradients(gray, w, h, nullptr, dx.data(), dy.data());
+    const Weights wt;
+    for (int i = 0; i < n; i++) {
+        KeyLine kl;
+        kl.sx = lines[4 * (size_t)i]; kl.sy = lines[4 * (size_t)i + 1]; kl.ex = lines[4 * (size_t)i + 2]; kl.ey = lines[4 * (size_t)i + 3];
+        kl.angle = fields[2 * (size_t)i];
+        kl.num_px = (int)fields[2 * (size_t)i + 1];
+        kl.length = 0;
+        float des[72];
+        compute_lbd(kl, dx.data(), dy.data(), w, h, libm_trig, wt, des);
+        if (desc72_out) std::memcpy(desc72_out + 72 * (size_t)i, des, sizeof des);
+        if (desc32_out)
+            for (int c = 0; c < 32; c++) {
+                const float *f1 = des + 8 * COMB[c][0], *f2 = des + 8 * COMB[c][1];
+                unsigned r = 0;
+                for (int k = 0; k < 8; k++)
+                    if (f1[k] > f2[k]) r += 1u << k;
+                desc32_out[32 * (size_t)i + c] = (uint8_t)r;
+            }
+    }
+    return n;
+}
+
 }  // extern "C"

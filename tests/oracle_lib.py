@@ -293,3 +293,16 @@ def edlines_detect(gray, filter=True, length_thres=15.0, cap=20000, libm_trig=Fa
     out = np.zeros((cap, 4), np.float32); ex = np.zeros((cap, 3), np.float32)
     n = lib().orc_edlines_detect(_p(gray), w, h, int(filter), C.c_float(length_thres), _p(out), _p(ex), cap)
     return out[:max(n, 0)].copy(), ex[:max(n, 0)].copy()
+
+
+def lbd_describe_keylines(gray, lines, direction, num_px, libm_trig=0):
+    """LBD descriptors of key lines with detector-supplied fields (EDLines: direction = lineDirection_, numOfPixels = chain-segment pixels)."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    lines = np.ascontiguousarray(lines, np.float32).reshape(-1, 4)
+    fields = np.ascontiguousarray(np.stack([np.asarray(direction, np.float32), np.asarray(num_px, np.float32)], axis=1), np.float32)
+    h, w = gray.shape
+    n = len(lines)
+    d72 = np.zeros((n, 72), np.float32); d32 = np.zeros((n, 32), np.uint8)
+    if n:
+        lib().orc_lbd_describe_keylines(_p(gray), w, h, _p(lines), _p(fields), n, int(libm_trig), _p(d72), _p(d32))
+    return d72, d32

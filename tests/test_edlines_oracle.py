@@ -113,3 +113,25 @@ def test_tiny_and_flat_frames(oracle):
     rng = np.random.default_rng(0)
     noise = rng.integers(0, 256, (33, 47), dtype=np.uint8)
     oracle.edlines_detect(noise, filter=False)   # must not crash on a frame full of anchors
+
+
+def test_edlines_keylines_feed_the_descriptor_oracle(oracle):
+    """detect_descrip_lines with use_LSD = false: the EDLines key lines (direction = lineDirection_, numOfPixels = chain-segment pixels) go
+    through computeLBD unchanged.  Checked here on the CPU only (the GPU descriptor kernel takes LSD-style key lines so far): unit-norm
+    descriptors, and -- for a line whose EDLines fields coincide with the LSD recipe's -- the same descriptor as the LSD-style entry point."""
+    d = np.load(os.path.join(GOLD, "lsd_407.npz"))
+    lines, extra = oracle.edlines_detect(d["gray"])
+    d72, d32 = oracle.lbd_describe_keylines(d["gray"], lines, extra[:, 0], extra[:, 1])
+    ok = ~np.isnan(d72).any(axis=1)
+    assert ok.mean() > 0.95
+    assert np.allclose(np.linalg.norm(d72[ok].astype(np.float64), axis=1), 1.0, atol=1e-5)
+    assert len(np.unique(d32, axis=0)) > 0.9 * len(d32)
+    # the LSD-style entry point derives angle = atan2(dy, dx) and numOfPixels = max(|dx|, |dy|) + 1 from the end points: where those agree with
+    # the EDLines fields the two entry points must give the same bits
+    r72, r32, kl = oracle.lbd_describe(d["gray"], lines)
+    same_fields = (kl[:, 0] == extra[:, 0]) & (kl[:, 1] == extra[:, 1])
+    if same_fields.any():
+        assert np.array_equal(d32[same_fields], r32[same_fields])
+    # a good part of the lines differ in numOfPixels (chain pixels vs LineIterator count; 29 % on this image), which is why the EDLines chain
+    # needs the detector's fields
+    assert (kl[:, 1] != extra[:, 1]).mean() > 0.1
