@@ -376,6 +376,25 @@ class Context:
         self._chk(lib().csb_edlines_detect_batch(self._h, _p(gray), n, w, h, C.byref(P), _p(lines), _p(cnt), C.byref(st)))
         return [lines[i, :cnt[i]].copy() for i in range(n)], st
 
+    def edlines_detect_describe_batch(self, gray, line_length_thres=15.0, filter=True, max_lines=4096, want_float=False):
+        """csb_edlines_upload / run / describe / download*: lines and their LBD descriptors (detect_descrip_lines with use_LSD = false)."""
+        gray = self._lsd_gray(gray)
+        n, h, w = gray.shape
+        P = LsdParams(float(line_length_thres), int(filter), int(max_lines), 0)
+        self._chk(lib().csb_edlines_upload(self._h, _p(gray), n, w, h, C.byref(P)))
+        self._chk(lib().csb_edlines_run(self._h, 0))
+        self._chk(lib().csb_edlines_describe(self._h, int(want_float)))
+        lines = np.zeros((n, max_lines, 4), np.float32); cnt = np.zeros(n, np.int32); st = EdlinesStats()
+        self._chk(lib().csb_edlines_download(self._h, _p(lines), _p(cnt), C.byref(st)))
+        total = int(cnt.sum())
+        d32 = np.zeros((max(total, 1), 32), np.uint8); d72 = np.zeros((max(total, 1), 72), np.float32) if want_float else None
+        cnt2 = np.zeros(n, np.int32)
+        self._chk(lib().csb_edlines_download_descriptors(self._h, _p(d32), _p(d72), _p(cnt2), C.c_int64(max(total, 1))))
+        out = {"lines": [lines[i, :cnt[i]].copy() for i in range(n)], "desc": self._lbd_split(d32[:total], cnt), "stats": st}
+        if want_float:
+            out["desc_float"] = self._lbd_split(d72[:total], cnt)
+        return out
+
     # ---- line descriptors (LBD) ----------------------------------------------------------------
     @staticmethod
     def _lbd_pack(lines_per_frame):
@@ -478,10 +497,13 @@ class line_lbd_detect:
     def detect_descrip_lines(self, gray_img):
         """line_lbd_allclass.cpp:263-281 (the KeyLine overload: octave 0, lineLength > line_length_thres): gray image(s) -> (lines rows
         [x1 y1 x2 y2] float32, line_descrips rows of 32 bytes); the segments stay on the device between the two stages."""
-        if not self.use_LSD:
-            raise CsbError(CSB_ERR_INVALID, "detect_descrip_lines with use_LSD = false (EDLines key lines) is not implemented on the GPU")
         single = np.asarray(gray_img).ndim == 2
         c = self._ctx
+        if not self.use_LSD:
+            if not self.allow_unvalidated_edlines:
+                raise CsbError(CSB_ERR_INVALID, "use_LSD = false (EDLines): the GPU path awaits its first hardware validation; set allow_unvalidated_edlines")
+            out = c.edlines_detect_describe_batch(gray_img, self.line_length_thres, True, self.max_lines)
+            return (out["lines"][0], out["desc"][0]) if single else (out["lines"], out["desc"])
         c.lsd_upload(gray_img, self.line_length_thres, True, self.max_lines)
         c.lsd_run()
         c.lbd_run_on_lsd()

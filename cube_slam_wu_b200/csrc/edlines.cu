@@ -25,6 +25,7 @@
 #include "edlines.h"
 #include "edlines_dev.cuh"
 #include "lbd.h"
+#include "lbd_dev.cuh"
 
 namespace csb {
 
@@ -58,11 +59,23 @@ __global__ void __launch_bounds__(32) k_ed_emit(EdBuffers B, EdDims d, int filte
     if (threadIdx.x == 0) ed_emit(B, d, blockIdx.x, filter, length_thres, max_lines);
 }
 
+// detect_descrip_lines with use_LSD = false: one thread per emitted key line (lbd_dev.cuh); weights = {gaussCoefG_[63], gaussCoefL_[21]}
+__global__ void __launch_bounds__(64) k_lbdk_line(EdBuffers B, EdDims d, int max_lines, const float* weights, uint8_t* desc, float* descf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, frame = blockIdx.y;
+    if (i >= min(B.n_lines[frame], max_lines)) return;
+    const size_t row = (size_t)frame * max_lines + i;
+    const float2 k = B.keyl[row];
+    lbdk_line(B.grad + (size_t)frame * d.w * d.h, d.w, d.h, B.lines + 4 * row, k.x, (int)k.y, weights, weights + LBDK_ROWS, descf ? descf + 72 * row : nullptr,
+              desc + 32 * row);
+}
+
 struct EdState {
     bool uploaded = false, ran = false, timed_last = false;
     EdDims d{};
     csb_lsd_params params{};
-    DevBuf d_gray, d_grad, d_gd, d_anchors, d_edge, d_part1, d_part2, d_chain, d_line, d_sid, d_nch, d_stage, d_lines, d_nlines, d_stats;
+    DevBuf d_gray, d_grad, d_gd, d_anchors, d_edge, d_part1, d_part2, d_chain, d_line, d_sid, d_nch, d_stage, d_lines, d_nlines, d_stats, d_keyl, d_weights,
+        d_desc, d_descf;
+    bool weights_set = false, described = false, desc_float = false;
     HostBuf h_gray, h_out;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int64_t h2d_bytes = 0, d2h_bytes = 0;
@@ -72,7 +85,7 @@ struct EdState {
 void edlines_release(EdState*& s) {
     if (!s) return;
     DevBuf* bufs[] = {&s->d_gray, &s->d_grad, &s->d_gd, &s->d_anchors, &s->d_edge, &s->d_part1, &s->d_part2, &s->d_chain, &s->d_line,
-                      &s->d_sid, &s->d_nch, &s->d_stage, &s->d_lines, &s->d_nlines, &s->d_stats};
+                      &s->d_sid, &s->d_nch, &s->d_stage, &s->d_lines, &s->d_nlines, &s->d_stats, &s->d_keyl, &s->d_weights, &s->d_desc, &s->d_descf};
     for (DevBuf* b : bufs) b->release();
     s->h_gray.release();
     s->h_out.release();
@@ -96,6 +109,7 @@ static EdBuffers ed_buffers(EdState& s) {
     B.n_chains = s.d_nch.as<int>();
     B.stage = s.d_stage.as<EdLine>();
     B.lines = s.d_lines.as<float>();
+    B.keyl = s.d_keyl.as<float2>();
     B.n_lines = s.d_nlines.as<int>();
     B.stats = s.d_stats.as<unsigned long long>();
     return B;
@@ -119,6 +133,7 @@ int csb_edlines_upload(csb_context* c, const uint8_t* gray, int n_frames, int wi
     EdState& s = *c->edlines;
     s.uploaded = false;
     s.ran = false;
+    s.described = false;
     s.params = *params;
     s.d = ed_make_dims(width, height, n_frames);
     const EdDims& d = s.d;
@@ -136,6 +151,7 @@ int csb_edlines_upload(csb_context* c, const uint8_t* gray, int n_frames, int wi
     CSB_CUDA(c, s.d_nch.ensure(nf * 4));
     CSB_CUDA(c, s.d_stage.ensure(nf * d.stage_cap * sizeof(EdLine)));
     CSB_CUDA(c, s.d_lines.ensure(nf * params->max_lines * 16));
+    CSB_CUDA(c, s.d_keyl.ensure(nf * params->max_lines * 8));
     CSB_CUDA(c, s.d_nlines.ensure(nf * 4));
     CSB_CUDA(c, s.d_stats.ensure(64));
     cudaPointerAttributes pa{};
@@ -181,6 +197,7 @@ int csb_edlines_run(csb_context* c, int timed) {
     s.launches_last = 6;
     s.timed_last = timed != 0;
     s.ran = true;
+    s.described = false;
     return CSB_OK;
 }
 
@@ -239,6 +256,78 @@ int csb_edlines_download(csb_context* c, float* lines_out, int32_t* n_lines_out,
         c->err = "csb_edlines: more segments than max_lines in at least one frame";
         return CSB_ERR_CAPACITY;
     }
+    return CSB_OK;
+}
+
+int csb_edlines_describe(csb_context* c, int want_float) {
+    if (!c || !c->edlines || !c->edlines->ran) {
+        if (c) c->err = "csb_edlines_describe before csb_edlines_run";
+        return CSB_ERR_STATE;
+    }
+    EdState& s = *c->edlines;
+    CSB_CUDA(c, cudaSetDevice(c->device));
+    const size_t rows = (size_t)s.d.n_frames * s.params.max_lines;
+    if (!s.weights_set) {
+        float wts[LBDK_ROWS + 3 * LBDK_BAND_W];
+        lbdk_weights(wts, wts + LBDK_ROWS);
+        CSB_CUDA(c, s.d_weights.ensure(sizeof wts));
+        CSB_CUDA(c, cudaMemcpyAsync(s.d_weights.p, wts, sizeof wts, cudaMemcpyHostToDevice, c->stream));
+        CSB_CUDA(c, cudaStreamSynchronize(c->stream));  // wts lives on this stack frame
+        s.weights_set = true;
+    }
+    CSB_CUDA(c, s.d_desc.ensure(rows * 32));
+    if (want_float) CSB_CUDA(c, s.d_descf.ensure(rows * 72 * 4));
+    EdBuffers B = ed_buffers(s);
+    k_lbdk_line<<<dim3((s.params.max_lines + 63) / 64, s.d.n_frames), 64, 0, c->stream>>>(B, s.d, s.params.max_lines, s.d_weights.as<float>(), s.d_desc.as<uint8_t>(),
+                                                                                           want_float ? s.d_descf.as<float>() : nullptr);
+    CSB_CUDA(c, cudaGetLastError());
+    s.described = true;
+    s.desc_float = want_float != 0;
+    return CSB_OK;
+}
+
+int csb_edlines_download_descriptors(csb_context* c, uint8_t* desc_out, float* desc_float_out, int32_t* n_lines_out, int64_t capacity_rows) {
+    if (!c || !c->edlines || !c->edlines->described) {
+        if (c) c->err = "csb_edlines_download_descriptors before csb_edlines_describe";
+        return CSB_ERR_STATE;
+    }
+    EdState& s = *c->edlines;
+    if (desc_float_out && !s.desc_float) {
+        c->err = "csb_edlines_download_descriptors: float descriptors were not requested";
+        return CSB_ERR_STATE;
+    }
+    CSB_CUDA(c, cudaSetDevice(c->device));
+    const int nf = s.d.n_frames, cap = s.params.max_lines;
+    std::vector<int32_t> nl(nf);
+    CSB_CUDA(c, cudaMemcpyAsync(nl.data(), s.d_nlines.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, c->stream));
+    CSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    int64_t total = 0;
+    int rows = 0;
+    for (int f = 0; f < nf; f++) { nl[f] = std::min(nl[f], cap); total += nl[f]; rows = std::max(rows, nl[f]); }
+    if (n_lines_out) std::memcpy(n_lines_out, nl.data(), (size_t)nf * 4);
+    if (total > capacity_rows) {
+        c->err = "csb_edlines_download_descriptors: more lines than capacity_rows";
+        return CSB_ERR_CAPACITY;
+    }
+    if (rows == 0) return CSB_OK;
+    auto pull = [&](const void* dev, size_t rb, void* out) -> cudaError_t {
+        if (!out) return cudaSuccess;
+        cudaError_t e = s.h_out.ensure((size_t)rows * nf * rb);
+        if (e != cudaSuccess) return e;
+        char* h = s.h_out.as<char>();
+        e = cudaMemcpy2DAsync(h, (size_t)rows * rb, dev, (size_t)cap * rb, (size_t)rows * rb, nf, cudaMemcpyDeviceToHost, c->stream);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) return e;
+        size_t o = 0;
+        for (int f = 0; f < nf; f++) {
+            std::memcpy(reinterpret_cast<char*>(out) + o, h + (size_t)f * rows * rb, (size_t)nl[f] * rb);
+            o += (size_t)nl[f] * rb;
+        }
+        return cudaSuccess;
+    };
+    CSB_CUDA(c, pull(s.d_desc.p, 32, desc_out));
+    CSB_CUDA(c, pull(s.d_descf.p, 288, desc_float_out));
     return CSB_OK;
 }
 

@@ -81,6 +81,7 @@ struct EdBuffers {
     int* n_chains;            // n_frames (-1: the reference's capacity error)
     EdLine* stage;            // n_frames x stage_cap
     float* lines;             // n_frames x max_lines x 4
+    float2* keyl;             // n_frames x max_lines {lineDirection_, numOfPixels} of the emitted lines (optional: the descriptor stage reads it)
     int* n_lines;             // n_frames
     unsigned long long* stats;  // [0] anchors, [1] chain pixels, [2] chains, [3] staged lines
 };
@@ -474,6 +475,7 @@ CSB_HD void ed_emit(const EdBuffers& B, const EdDims& d, int frame, int filter, 
                 float* o = out + 4 * (size_t)n_out;
                 if (change) { o[0] = ex; o[1] = ey; o[2] = sx; o[3] = sy; }
                 else { o[0] = sx; o[1] = sy; o[2] = ex; o[3] = ey; }
+                if (B.keyl) B.keyl[(size_t)frame * max_lines + n_out] = make_float2(L.direction, (float)L.n_px);
             }
             n_out++;
         }

@@ -344,6 +344,12 @@ int csb_edlines_detect_batch(csb_context* ctx, const uint8_t* gray, int n_frames
 int csb_edlines_upload(csb_context* ctx, const uint8_t* gray, int n_frames, int width, int height, const csb_lsd_params* params);
 int csb_edlines_run(csb_context* ctx, int timed);
 int csb_edlines_download(csb_context* ctx, float* lines_out, int32_t* n_lines_out, csb_edlines_stats* stats);
+/* detect_descrip_lines with use_LSD = false (line_lbd_allclass.cpp:239-281): LBD descriptors of the key lines of the last csb_edlines_run,
+ * computed on the device from the detector's own fields (direction = lineDirection_, numOfPixels = pixels of the fitted chain segment,
+ * end points as projected; binary_descriptor.cpp:1045-1140, 1150-1512).  Rows of all frames back to back (n_lines_out[f] rows for frame f):
+ * 32 bytes per line, 72 floats on request. */
+int csb_edlines_describe(csb_context* ctx, int want_float);
+int csb_edlines_download_descriptors(csb_context* ctx, uint8_t* desc_out, float* desc_float_out, int32_t* n_lines_out, int64_t capacity_rows);
 
 #ifdef __cplusplus
 }

@@ -12,11 +12,13 @@
 #include <vector>
 
 #include "../../cube_slam_wu_b200/csrc/edlines_dev.cuh"
+#include "../../cube_slam_wu_b200/csrc/lbd_dev.cuh"
 
 using namespace csb;
 
+// desc32_out (n x 32 bytes) / desc72_out (n x 72 floats) optional: detect_descrip_lines with use_LSD = false (lbd_dev.cuh on the emitted key lines)
 extern "C" int emul_edlines_detect(const int16_t* dx, const int16_t* dy, int w, int h, int filter, float length_thres, float* lines_out, int max_lines,
-                                   long long* stats4, int* n_chains_out) {
+                                   long long* stats4, int* n_chains_out, uint8_t* desc32_out, float* desc72_out) {
     const EdDims d = ed_make_dims(w, h, 1);
     const size_t npx = (size_t)w * h;
     std::vector<short2> grad(npx);
@@ -27,12 +29,13 @@ extern "C" int emul_edlines_detect(const int16_t* dx, const int16_t* dy, int w, 
     std::vector<int> sid(d.max_edges + 2, 0);
     std::vector<EdLine> stage(d.stage_cap);
     std::vector<float> lines((size_t)max_lines * 4, 0.f);
+    std::vector<float2> keyl((size_t)max_lines);
     int n_chains = 0, n_lines = 0;
     unsigned long long stats[4] = {0, 0, 0, 0};
     EdBuffers B{};
     B.grad = grad.data(); B.gd = gd.data(); B.anchors = anchors.data(); B.edge = edge.data(); B.part1 = p1.data(); B.part2 = p2.data();
     B.chain_px = chain.data(); B.line_px = line.data(); B.chain_sid = sid.data(); B.n_chains = &n_chains; B.stage = stage.data();
-    B.lines = lines.data(); B.n_lines = &n_lines; B.stats = stats;
+    B.lines = lines.data(); B.keyl = keyl.data(); B.n_lines = &n_lines; B.stats = stats;
     for (size_t i = 0; i < npx; i++) ed_pixel(B, d, i);                         // k_ed_pixel
     for (int c = 0; c < d.nxc * d.nyc; c++)                                     // k_ed_anchor
         if (ed_anchor(B, d, 0, c)) anchors[c >> 5] |= 1u << (c & 31);
@@ -41,6 +44,13 @@ extern "C" int emul_edlines_detect(const int16_t* dx, const int16_t* dy, int w, 
     ed_emit(B, d, 0, filter, length_thres, max_lines);                          // k_ed_emit
     const int n = n_lines < max_lines ? n_lines : max_lines;
     if (lines_out && n > 0) std::memcpy(lines_out, lines.data(), (size_t)n * 16);
+    if (desc32_out && n > 0) {
+        float G[LBDK_ROWS], L[3 * LBDK_BAND_W];
+        lbdk_weights(G, L);
+        for (int i = 0; i < n; i++)                                             // k_lbdk_line: item = line
+            lbdk_line(grad.data(), w, h, lines.data() + 4 * (size_t)i, keyl[i].x, (int)keyl[i].y, G, L, desc72_out ? desc72_out + 72 * (size_t)i : nullptr,
+                      desc32_out + 32 * (size_t)i);
+    }
     if (stats4) for (int i = 0; i < 4; i++) stats4[i] = (long long)stats[i];
     if (n_chains_out) *n_chains_out = n_chains;
     return n_lines;

@@ -24,13 +24,17 @@ def emul(tmp_path_factory):
     return C.CDLL(so)
 
 
-def _run(emul, oracle, gray, filter=True, thres=15.0, cap=20000):
+def _run(emul, oracle, gray, filter=True, thres=15.0, cap=20000, descriptors=False):
     gray = np.ascontiguousarray(gray, np.uint8)
     h, w = gray.shape
     _, dx, dy = oracle.lbd_gradients(gray)
     out = np.zeros((cap, 4), np.float32); st = np.zeros(4, np.int64); nch = C.c_int()
+    d32 = np.zeros((cap, 32), np.uint8); d72 = np.zeros((cap, 72), np.float32)
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    n = emul.emul_edlines_detect(vp(dx), vp(dy), w, h, int(filter), C.c_float(thres), vp(out), cap, vp(st), C.byref(nch))
+    n = emul.emul_edlines_detect(vp(dx), vp(dy), w, h, int(filter), C.c_float(thres), vp(out), cap, vp(st), C.byref(nch),
+                                 vp(d32) if descriptors else None, vp(d72) if descriptors else None)
+    if descriptors:
+        return out[:n].copy(), d32[:n].copy(), d72[:n].copy()
     return out[:n].copy(), st, nch.value
 
 
@@ -67,3 +71,21 @@ def test_device_code_on_the_reference_image_and_noise(emul, oracle):
     flat = np.full((40, 60), 77, np.uint8)
     got, st, nch = _run(emul, oracle, flat)
     assert len(got) == 0 and nch == 0
+
+
+def test_descriptor_device_code_matches_oracle(emul, oracle):
+    """detect_descrip_lines with use_LSD = false: EDLines key lines (direction, chain-segment pixel count, projected end points) through the
+    one-thread-per-item descriptor code (csrc/lbd_dev.cuh) against orc_lbd_describe_keylines -- 72 floats and 32 bytes, bit for bit."""
+    from cube_slam_wu_b200 import synth
+    frames = [synth.make_lsd_frames(1, 640, 480, seed=3)[0], synth.make_lsd_frames(1, 333, 251, seed=8, texture=1.0, noise_sigma=4.0)[0],
+              np.load(os.path.join(HERE, "golden", "lsd_407.npz"))["gray"]]
+    total = 0
+    for gray in frames:
+        lines, d32, d72 = _run(emul, oracle, gray, descriptors=True)
+        ref_lines, extra = oracle.edlines_detect(gray)
+        assert _same(lines, ref_lines)
+        r72, r32 = oracle.lbd_describe_keylines(gray, ref_lines, extra[:, 0], extra[:, 1])
+        assert np.array_equal(d32, r32)
+        assert np.array_equal(np.isnan(d72), np.isnan(r72)) and np.array_equal(np.nan_to_num(d72).view(np.uint32), np.nan_to_num(r72).view(np.uint32))
+        total += len(ref_lines)
+    assert total > 200

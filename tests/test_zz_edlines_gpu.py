@@ -38,6 +38,19 @@ for (n, w, h, seed, kw) in ((5, 640, 480, 3, {}), (2, 641, 479, 4, dict(texture=
         total += n_ref
     chains = [O.edlines_chains(fr) for fr in frames]
     assert st.n_chains == sum(len(c) for c in chains) and st.n_chain_px == sum(sum(len(x) for x in c) for c in chains)
+# detect_descrip_lines with use_LSD = false: descriptors of the key lines, from the detector's own fields (csb_edlines_describe)
+frames = synth.make_lsd_frames(3, 640, 480, seed=9)
+out = ctx.edlines_detect_describe_batch(frames, want_float=True)
+n_desc = 0
+for f in range(3):
+    ref, extra = O.edlines_detect(frames[f])
+    assert np.array_equal(out["lines"][f].view(np.uint32), ref.view(np.uint32))
+    r72, r32 = O.lbd_describe_keylines(frames[f], ref, extra[:, 0], extra[:, 1])
+    assert np.array_equal(out["desc"][f], r32), "frame %%d: binary descriptors differ" %% f
+    g72 = out["desc_float"][f]
+    assert np.array_equal(np.isnan(g72), np.isnan(r72)) and np.array_equal(np.nan_to_num(g72).view(np.uint32), np.nan_to_num(r72).view(np.uint32))
+    n_desc += len(ref)
+assert n_desc > 50
 d = np.load(os.path.join(%(root)r, "tests", "golden", "lsd_407.npz"))
 lines, st = ctx.edlines_detect_batch(d["gray"][None])
 ref, _ = O.edlines_detect(d["gray"])
@@ -47,8 +60,8 @@ base = synth.make_lsd_frames(32, 640, 480, seed=20260927)
 big = np.ascontiguousarray(np.concatenate([base] * 8))
 ctx.edlines_detect_batch(big)
 lines, st = ctx.edlines_detect_batch(big)
-print("EDLINES_GPU_OK %%d segments checked; 256 frames 640x480: maps %%.3f ms, draw %%.3f ms, fit %%.3f ms, %%d segments" %% (
-    total, st.gpu_ms_maps, st.gpu_ms_draw, st.gpu_ms_fit, st.n_lines))
+print("EDLINES_GPU_OK %%d segments + %%d descriptors checked; 256 frames 640x480: maps %%.3f ms, draw %%.3f ms, fit %%.3f ms, %%d segments" %% (
+    total, n_desc, st.gpu_ms_maps, st.gpu_ms_draw, st.gpu_ms_fit, st.n_lines))
 ctx.close()
 '''
 
