@@ -12,9 +12,11 @@
 // Parameters as the reference's constructor sets them (:1515-1525): gradient threshold 80, anchor threshold 8, scan interval 2,
 // minimum line length 15, line-fit error 1.6.
 //
-// This oracle exists ahead of a GPU port (SURVEY.md 8 f-2 names EDLines; DESIGN.md 7 lists it as not ported): it fixes the semantics the
-// port will be held to.  PARITY UNPINNED: the reference ships no EDLines output, does not compile here, and cv2 4.13 has no EDLines;
-// the OpenCV arithmetic underneath (blur, Sobel) is the same pinned code as oracle_lbd.cpp (orc_lbd_gradients).
+// PARITY STATUS: PINNED through the reference's own committed outputs.  The reference ships no EDLines segment file, but its object_slam
+// node ran this detector (main_obj.cpp:504) to produce output_obj_poses.txt / output_cam_poses.txt, and tests/test_reference_replay.py
+// reproduces those files to their printed digits for the first 28 frames with this oracle feeding the cuboid proposals -- with the LSD
+// branch instead, the landmark history leaves the committed one at the second frame: the best proposal of a frame depends on the exact
+// line table.  The OpenCV arithmetic underneath (blur, Sobel) is the same cv2-pinned code as oracle_lbd.cpp (orc_lbd_gradients).
 //
 // Quirks of the reference that are kept because they decide which pixels join a chain:
 //   * the routing compares neighbours through `(unsigned char) pgImg[...]` (:1746-1748 ...): gradient values above 255 would wrap

@@ -8,10 +8,9 @@
 // translation units are compiled with -O2 -ffp-contract=off so that +,-,*,/,sqrt
 // are single correctly-rounded IEEE-754 operations (no FMA contraction).
 //
-// PARITY STATUS: "parity unpinned" by the reference for the scored path as a whole
-// (the reference has no tests and cannot be compiled here: no Eigen/OpenCV/ROS).
-// Pinned pieces: the ray_plane_interact worked example printed in
-// detect_3d_cuboid/src/object_3d_util.cpp:884-905 (see tests/test_oracle_golden.py).
+// PARITY STATUS: pinned through its users -- the online-mode replay of the reference's own TUM sequence against its committed output
+// files (tests/test_reference_replay.py; see oracle_proposal.cpp / oracle_ba.cpp) and the ray_plane_interact worked example printed in
+// detect_3d_cuboid/src/object_3d_util.cpp:884-905 (tests/test_oracle_golden.py).
 #pragma once
 #include <cmath>
 #include <cstring>

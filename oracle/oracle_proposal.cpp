@@ -8,8 +8,12 @@
 // OpenCV in the reference (box_proposal_detail.cpp:320-327) and are INPUTS here: the caller
 // supplies one float32 distance map per (box, height-sample) task, in orc_plan() order.
 //
-// PARITY STATUS: "parity unpinned" -- the reference has no tests/golden vectors for this
-// path and does not compile here (needs Eigen, OpenCV, ROS).  What is pinned:
+// PARITY STATUS: PINNED against outputs of the reference itself.  The reference has no tests and does not compile here (needs Eigen,
+// OpenCV, ROS), but it commits what its object_slam node wrote in online mode for the bundled TUM sequence
+// (object_slam/data/output_obj_poses.txt, output_cam_poses.txt), and tests/test_reference_replay.py re-runs that mode with this file
+// (after oracle_edlines.cpp + cv2 Canny / distance transform, before oracle_ba.cpp): the landmark pose after each of the first 28 frames
+// comes out to the files' printed digits, frame 0 being a single detect_cuboid() result, frames 1.. with camera roll / pitch sampling on.
+// Also pinned:
 //   * ray_plane_interact worked example, object_3d_util.cpp:884-905 (tests/test_oracle_golden.py)
 //   * enumeration counts on the bundled demo (320/111, 6400/1799)
 // Defined-by-oracle behaviour where the reference has UB: dist_map.at<float>(r,c) is

@@ -1,0 +1,127 @@
+"""Replay of the reference's object_slam node in ONLINE mode (object_slam/src/main_obj.cpp:479-841, online_detect_mode = true) on its bundled TUM
+sequence, with the stages supplied by a backend (the CPU oracles, or the GPU library through the C ABI).  TEST INFRASTRUCTURE.
+
+Per frame (main_obj.cpp):  constant-velocity pose prediction (:545-558) -> line_lbd_detect::detect_filter_lines with use_LSD = false and
+line_length_thres 15 (:503-505, 596) -> detect_cuboid on the YOLO box with the FIRST frame's pose as transToWolrd, roll / pitch sampling on for
+every frame but the first, nominal_skew_ratio 2 (:494, 612-618) -> measurement in the camera frame with the sampled roll / pitch applied
+(:643-679) -> graph: camera vertex (first fixed), EdgeSE3Cuboid with information (2 meas_quality)^2, EdgeSE3Expmap odometry (:738-799) ->
+optimize(5) (:803) -> the landmark estimate after every frame = one row of output_obj_poses.txt, the final camera poses = output_cam_poses.txt."""
+import os
+
+import cv2
+import numpy as np
+
+import oracle_lib as O
+from cube_slam_wu_b200 import graph, synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+K_TUM = np.array([[535.4, 0, 320.1], [0, 539.2, 247.6], [0, 0, 1.0]])   # main_obj.cpp:484-486
+
+
+def load_sequence():
+    d = np.load(os.path.join(GOLD, "tum_online.npz"))
+    ba = np.load(os.path.join(GOLD, "tum_ba.npz"))
+    frames = []
+    for f in range(len(d["jpeg_off"]) - 1):
+        img = cv2.imdecode(d["jpeg"][d["jpeg_off"][f]:d["jpeg_off"][f + 1]], 1)
+        frames.append(cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))          # detect_filter_lines / detect_cuboid convert BGR -> gray themselves
+    boxes = []
+    for f in range(len(frames)):
+        b = d["boxes"][d["boxes"][:, 0] == f][:, 1:].copy()
+        b[:, :2] -= 1                                                  # "change matlab coordinate to c++" (:608)
+        boxes.append(b)
+    return frames, boxes, ba["truth"], ba["out_obj"], ba["out_cam"]
+
+
+def pose_mat(v7):
+    x, y, z, qx, qy, qz, qw = v7
+    R = np.array([[1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw)],
+                  [2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw)],
+                  [2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)]])
+    T = np.eye(4); T[:3, :3] = R; T[:3, 3] = [x, y, z]
+    return T
+
+
+def quat_to_euler_zyx(q):  # matrix_utils.cpp:38-51; q = x y z w
+    qx, qy, qz, qw = q
+    return (np.arctan2(2 * (qw * qx + qy * qz), 1 - 2 * (qx * qx + qy * qy)), np.arcsin(2 * (qw * qy - qz * qx)),
+            np.arctan2(2 * (qw * qz + qx * qy), 1 - 2 * (qy * qy + qz * qz)))
+
+
+class OracleBackend:
+    """every stage from the CPU oracles (distance maps: cv2, the reference's own calls box_proposal_detail.cpp:320-327)"""
+
+    def __init__(self, use_lsd=False):
+        self.use_lsd = use_lsd
+
+    def lines(self, gray):
+        return (O.lsd_detect(gray) if self.use_lsd else O.edlines_detect(gray)[0]).astype(np.float64)
+
+    def best_cuboid(self, gray, T0, box, lines, sample):
+        H, W = gray.shape
+        tasks = O.plan(box, W, H)
+        maps = [cv2.distanceTransform(255 - cv2.Canny(np.ascontiguousarray(gray[t.top:t.top + t.height, t.left:t.left + t.width]), 80, 200),
+                                      cv2.DIST_L2, 3).astype(np.float32) for t in tasks]
+        P = O.default_params(whether_sample_cam_roll_pitch=int(sample), nominal_skew_ratio=2.0)
+        R = O.detect_frame(K_TUM, T0, W, H, box, lines, maps, P)
+        b = R.boxes[0]
+        if not len(b["sorted"]):
+            return None
+        c = b["raw"][b["sorted"][0]]
+        return dict(pos=np.array(c.pos), rotY=c.rotY, scale=np.array(c.scale), err=c.normalized_error, droll=c.camera_roll_delta, dpitch=c.camera_pitch_delta)
+
+    def optimize(self, cams, fixed, cube, ec, eo):
+        E = O.ba_edges(ec=(ec[0], ec[1], np.array(ec[2]), np.array(ec[3])),
+                       eo=(eo[0], eo[1], np.array(eo[2]).reshape(-1, 7), np.array(eo[3]).reshape(-1, 36)) if len(eo[0]) else None)
+        c2, q2, _, _ = O.ba_optimize(np.array(cams), fixed, cube.reshape(1, 10), [0], E, 5)
+        return c2, q2[0]
+
+
+def run(backend, frames, boxes, truth, n_frames=None):
+    cv2.setNumThreads(1)
+    try:
+        cv2.ipp.setUseIPP(False)
+    except Exception:
+        pass
+    N = len(frames) if n_frames is None else n_frames
+    ident = np.array([0, 0, 0, 0, 0, 0, 1.0])
+    Twc0 = O.se3_mul(truth[0, 1:8], ident)            # g2o::SE3Quat(Vector7d) keeps w >= 0
+    T0 = pose_mat(Twc0)
+    eul0 = quat_to_euler_zyx(Twc0[3:7])               # detect_cuboid_obj.cam_pose_raw.euler_angle after set_cam_pose(transToWolrd)
+    cams, fixed, ec, eo, cube, hist, n_lines = [], [], ([], [], [], []), ([], [], [], []), None, [], []
+    for f in range(N):
+        odom = ident.copy()
+        if f == 0:
+            Twc = Twc0
+        else:
+            prev = cams[f - 1]
+            if f > 1:
+                odom = O.se3_mul(prev, O.se3_inverse(cams[f - 2]))
+            Twc = O.se3_inverse(O.se3_mul(odom, prev))
+        gray, box = frames[f], boxes[f]
+        lines = backend.lines(gray)
+        n_lines.append(len(lines))
+        sample = f != 0
+        best = backend.best_cuboid(gray, T0, box, lines, sample) if len(box) else None   # transToWolrd is the first frame's pose either way
+        if best is not None:
+            cg = O.cuboid_from_minimal([best["pos"][0], best["pos"][1], best["pos"][2], 0, 0, best["rotY"], best["scale"][0], best["scale"][1], best["scale"][2]])
+            meas = O.cuboid_transform_to(cg, Twc)
+            if sample:
+                Rn = np.asarray(synth.euler_zyx_to_rot(eul0[0] + best["droll"], eul0[1] + best["dpitch"], eul0[2]))
+                Tn = np.eye(4); Tn[:3, :3] = Rn; Tn[:3, 3] = T0[:3, 3]
+                meas = O.cuboid_transform_to(cg, graph.pose7_from_matrix(Tn))
+            q = (1 - best["err"] + 0.5) / 2
+        if f == 0:
+            cube = O.cuboid_transform_from(meas, Twc)
+        cams.append(O.se3_inverse(Twc)); fixed.append(1 if f == 0 else 0)
+        if best is not None:
+            ec[0].append(f); ec[1].append(0); ec[2].append(meas); ec[3].append((np.eye(9) * (2 * q) ** 2).ravel())
+        if f > 0:
+            eo[0].append(f - 1); eo[1].append(f); eo[2].append(odom); eo[3].append(np.eye(6).ravel())
+        c2, cube = backend.optimize(cams, fixed, cube, ec, eo)
+        cams = [c2[i] for i in range(f + 1)]
+        hist.append(cube.copy())
+    hist = np.array(hist)
+    obj9 = np.concatenate([hist[:, :3], np.zeros((len(hist), 2)), 2 * np.arctan2(hist[:, 5:6], hist[:, 6:7]), hist[:, 7:10]], axis=1)  # x y z . . yaw scale
+    Twc = np.array([O.se3_inverse(c) for c in cams])
+    return dict(obj=obj9, cube10=hist, Twc=Twc, n_lines=np.array(n_lines))
