@@ -77,6 +77,45 @@ class OracleBackend:
         return c2, q2[0]
 
 
+class GpuBackend:
+    """every stage from libcubeslam_b200.so through the C ABI: csb_edlines_detect_batch (or csb_lsd_detect_batch), csb_detect_batch_gray
+    (Canny + distance transform + proposals on the GPU), csb_ba_set_graph + csb_ba_optimize (LM on the device)"""
+
+    def __init__(self, ctx, csb, use_lsd=False):
+        self.ctx, self.csb, self.use_lsd = ctx, csb, use_lsd
+
+    def lines(self, gray):
+        if self.use_lsd:
+            out, _ = self.ctx.lsd_detect_batch(gray[None], 15.0, True)
+        else:
+            out, _ = self.ctx.edlines_detect_batch(gray[None], 15.0, True)
+        return np.ascontiguousarray(out[0].astype(np.float64)).reshape(-1, 4)
+
+    def best_cuboid(self, gray, T0, box, lines, sample):
+        csb, ctx = self.csb, self.ctx
+        H, W = gray.shape
+        params = csb.DetectParams.default(whether_sample_cam_roll_pitch=int(sample), nominal_skew_ratio=2.0)
+        frames = csb.make_frames([K_TUM], [T0], W, H, [(0, len(box))], [(0, len(lines))])
+        boxes = np.ascontiguousarray(box, np.float64).reshape(-1, 5)
+        lines = np.ascontiguousarray(lines, np.float64).reshape(-1, 4) if len(lines) else np.zeros((0, 4))
+        tasks, n_tasks, n_map = csb.detect_plan(frames, boxes, params)
+        cub, ncub, _ = ctx.detect_batch_gray(frames, boxes, lines, tasks, n_tasks, np.ascontiguousarray(gray.ravel(), np.uint8), params)
+        if ncub[0] < 1:
+            return None
+        c = cub[0]
+        return dict(pos=np.array(c.pos[:]), rotY=c.rotY, scale=np.array(c.scale[:]), err=c.normalized_error, droll=c.camera_roll_delta,
+                    dpitch=c.camera_pitch_delta)
+
+    def optimize(self, cams, fixed, cube, ec, eo):
+        ctx = self.ctx
+        ecs = (np.array(ec[0], np.int32), np.array(ec[1], np.int32), np.array(ec[2]).reshape(-1, 10), np.array(ec[3]).reshape(-1, 81)) if len(ec[0]) else None
+        eos = (np.array(eo[0], np.int32), np.array(eo[1], np.int32), np.array(eo[2]).reshape(-1, 7), np.array(eo[3]).reshape(-1, 36)) if len(eo[0]) else None
+        ctx.ba_set_graph(np.array(fixed, np.int32), np.zeros(1, np.int32), ec=ecs, ep=None, eo=eos)
+        ctx.ba_upload_estimates(np.array(cams), cube.reshape(1, 10))
+        c2, q2, _ = ctx.ba_optimize(5)
+        return c2, q2[0]
+
+
 def run(backend, frames, boxes, truth, n_frames=None):
     cv2.setNumThreads(1)
     try:
