@@ -52,3 +52,82 @@ def test_replay_discriminates(seq):
     dscale = np.abs(r["obj"][:, 6:9] - out_obj[:12, 6:9]).max(axis=1)
     assert dscale[0] < 5e-5          # frame 0: both detectors lead to the same best proposal
     assert dscale[1:].max() > 2e-3
+
+
+class _FakeCtx:
+    """Stands in for cube_slam_wu_b200.Context in replay.GpuBackend: same method names and argument conventions, computing with the oracles.
+    What it checks is the glue of the GPU replay (argument packing, call order) without a GPU -- the real Context is exercised on the B200 by
+    tests/test_zz_edlines_gpu.py."""
+
+    def __init__(self, csb):
+        self.csb = csb
+        self.calls = []
+
+    def lsd_detect_batch(self, gray, line_length_thres=15.0, filter=True, max_lines=4096):
+        self.calls.append("lsd")
+        assert gray.ndim == 3 and gray.dtype == np.uint8
+        return [replay.O.lsd_detect(g, length_thres=line_length_thres) for g in gray], None
+
+    def edlines_detect_batch(self, gray, line_length_thres=15.0, filter=True, max_lines=4096):
+        self.calls.append("edlines")
+        assert gray.ndim == 3 and gray.dtype == np.uint8
+        return [replay.O.edlines_detect(g, filter=filter, length_thres=line_length_thres)[0] for g in gray], None
+
+    def detect_batch_gray(self, frames, boxes, lines, tasks, n_tasks, gray, params, want_stats=True):
+        import cv2
+        self.calls.append("detect")
+        assert len(frames) == 1 and boxes.dtype == np.float64 and lines.dtype == np.float64 and gray.dtype == np.uint8 and gray.ndim == 1
+        fr = frames[0]
+        W, H = fr.img_width, fr.img_height
+        assert gray.size == W * H and (fr.box_begin, fr.box_end) == (0, len(boxes)) and (fr.line_begin, fr.line_end) == (0, len(lines))
+        K = np.array(fr.Kalib[:]).reshape(3, 3)
+        T = np.array(fr.transToWolrd[:]).reshape(4, 4)
+        img = gray.reshape(H, W)
+        maps = []
+        for i in range(n_tasks):
+            t = tasks[i]
+            roi = np.ascontiguousarray(img[t.roi_top:t.roi_top + t.roi_height, t.roi_left:t.roi_left + t.roi_width])
+            maps.append(cv2.distanceTransform(255 - cv2.Canny(roi, 80, 200), cv2.DIST_L2, 3).astype(np.float32))
+        P = replay.O.default_params(whether_sample_cam_roll_pitch=params.whether_sample_cam_roll_pitch, nominal_skew_ratio=params.nominal_skew_ratio)
+        R = replay.O.detect_frame(K, T, W, H, boxes, lines, maps, P)
+        cub, ncub = [], np.zeros(len(boxes), np.int32)
+        for b, bx in enumerate(R.boxes):
+            if len(bx["sorted"]):
+                cub.append(bx["raw"][bx["sorted"][0]]); ncub[b] = 1
+            else:
+                cub.append(None)
+        return cub, ncub, None
+
+    def ba_set_graph(self, cam_fixed, cube_fixed, ec=None, ep=None, eo=None):
+        self.calls.append("set_graph")
+        self.g = (np.asarray(cam_fixed), np.asarray(cube_fixed), ec, eo)
+
+    def ba_upload_estimates(self, cams7, cubes10):
+        self.calls.append("upload")
+        assert cams7.shape == (len(self.g[0]), 7) and cubes10.shape == (len(self.g[1]), 10)
+        self.est = (cams7, cubes10)
+
+    def ba_optimize(self, iterations):
+        self.calls.append("optimize")
+        cam_fixed, cube_fixed, ec, eo = self.g
+        E = replay.O.ba_edges(ec=ec, ep=None, eo=eo)
+        c2, q2, _, _ = replay.O.ba_optimize(self.est[0], cam_fixed, self.est[1], cube_fixed, E, iterations)
+        return c2, q2, None
+
+
+def test_gpu_backend_glue_with_a_fake_context(seq, csb):
+    """replay.GpuBackend (the C-ABI call sequence of the GPU replay) driven through a stand-in context that computes with the oracles: it must
+    give exactly the oracle backend's result, which checks the packing of frames / boxes / lines / gray buffers, the planner call and the
+    order of the BA calls on the CPU.  (csb.make_frames and csb.detect_plan are the real host-side functions of the library.)"""
+    frames, boxes, truth, out_obj, out_cam = seq
+    n = 24   # includes frames without a box
+    ref = replay.run(replay.OracleBackend(), frames, boxes, truth, n_frames=n)
+    fake = _FakeCtx(csb)
+    got = replay.run(replay.GpuBackend(fake, csb), frames, boxes, truth, n_frames=n)
+    assert np.array_equal(got["n_lines"], ref["n_lines"])
+    assert np.array_equal(got["cube10"], ref["cube10"]) and np.array_equal(got["Twc"], ref["Twc"])
+    assert fake.calls[:5] == ["edlines", "detect", "set_graph", "upload", "optimize"]
+    assert fake.calls.count("detect") == sum(1 for b in boxes[:n] if len(b)) < n   # frames without a YOLO box skip detect_cuboid
+    fake2 = _FakeCtx(csb)
+    replay.run(replay.GpuBackend(fake2, csb, use_lsd=True), frames, boxes, truth, n_frames=3)
+    assert fake2.calls[0] == "lsd"
