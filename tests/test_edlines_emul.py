@@ -89,3 +89,34 @@ def test_descriptor_device_code_matches_oracle(emul, oracle):
         assert np.array_equal(np.isnan(d72), np.isnan(r72)) and np.array_equal(np.nan_to_num(d72).view(np.uint32), np.nan_to_num(r72).view(np.uint32))
         total += len(ref_lines)
     assert total > 200
+
+
+def test_device_code_fuzz(emul, oracle):
+    """random sizes and contents (synthetic scenes, textured + noisy scenes, contrast-stretched smooth noise, white noise): segments and
+    descriptors from the device code stay bit-identical to the oracle's"""
+    import cv2
+    from cube_slam_wu_b200 import synth
+    rng = np.random.default_rng(123)
+    total = 0
+    for it in range(16):
+        w = int(rng.integers(40, 700)); h = int(rng.integers(40, 500))
+        kind = it % 4
+        if kind == 0:
+            gray = synth.make_lsd_frames(1, w, h, seed=1000 + it)[0]
+        elif kind == 1:
+            gray = synth.make_lsd_frames(1, w, h, seed=1000 + it, texture=float(rng.uniform(0.5, 2)), noise_sigma=float(rng.uniform(2, 12)))[0]
+        elif kind == 2:
+            g = cv2.GaussianBlur(rng.normal(128, 60, (h, w)), (0, 0), float(rng.uniform(1, 4)))
+            gray = np.clip((g - 128) * float(rng.uniform(2, 8)) + 128, 0, 255).astype(np.uint8)
+        else:
+            gray = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        filt = bool(it % 2)
+        lines, d32, d72 = _run(emul, oracle, gray, filt, 15.0, descriptors=True)
+        ref, extra = oracle.edlines_detect(gray, filter=filt, length_thres=15.0)
+        assert _same(lines, ref), "case %d (%dx%d, kind %d)" % (it, w, h, kind)
+        if len(ref):
+            r72, r32 = oracle.lbd_describe_keylines(gray, ref, extra[:, 0], extra[:, 1])
+            assert np.array_equal(d32, r32)
+            assert np.array_equal(np.isnan(d72), np.isnan(r72)) and np.array_equal(np.nan_to_num(d72).view(np.uint32), np.nan_to_num(r72).view(np.uint32))
+        total += len(ref)
+    assert total > 200
