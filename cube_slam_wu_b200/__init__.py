@@ -176,6 +176,10 @@ class Context:
         if rc != CSB_OK:
             raise CsbError(rc, (lib().csb_last_error(self._h) or b"").decode())
 
+    def set_blur_generation(self, generation):
+        """csb_set_blur_generation(): 4 (default) = OpenCV 4.x taps of the 8-bit 5x5 Gaussian in front of LBD / EDLines, 3 = OpenCV <= 3.4.0's."""
+        self._chk(lib().csb_set_blur_generation(self._h, int(generation)))
+
     def synchronize(self):
         self._chk(lib().csb_synchronize(self._h))
 

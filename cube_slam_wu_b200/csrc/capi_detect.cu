@@ -72,6 +72,12 @@ int csb_set_stream(csb_context* c, void* s) {
     return CSB_OK;
 }
 
+int csb_set_blur_generation(csb_context* c, int generation) {
+    if (!c || (generation != 3 && generation != 4)) return CSB_ERR_INVALID;
+    c->blur_generation = generation;
+    return CSB_OK;
+}
+
 int csb_synchronize(csb_context* c) {
     if (!c) return CSB_ERR_INVALID;
     CSB_CUDA(c, cudaStreamSynchronize(c->stream));

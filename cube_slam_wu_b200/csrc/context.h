@@ -95,6 +95,7 @@ struct csb_context {
     csb::LsdState* lsd = nullptr;  // created by the first csb_lsd_* call
     csb::LbdState* lbd = nullptr;  // created by the first csb_lbd_* call
     csb::EdState* edlines = nullptr;  // created by the first csb_edlines_* call
+    int blur_generation = 4;          // csb_set_blur_generation: integer taps of the 8-bit 5x5 Gaussian of the LBD / EDLines front end
 };
 
 #define CSB_CUDA(ctx, call)                                                                   \

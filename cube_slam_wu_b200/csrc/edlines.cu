@@ -184,7 +184,7 @@ int csb_edlines_run(csb_context* c, int timed) {
     CSB_CUDA(c, cudaMemsetAsync(s.d_stats.p, 0, 64, st));
     CSB_CUDA(c, cudaMemsetAsync(s.d_edge.p, 0, (size_t)d.n_frames * d.edge_words * 4, st));
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[0], st));
-    lbd_launch_grad(s.d_gray.as<uint8_t>(), s.d_grad.as<short2>(), d.w, d.h, d.n_frames, st);
+    lbd_launch_grad(s.d_gray.as<uint8_t>(), s.d_grad.as<short2>(), d.w, d.h, d.n_frames, st, c->blur_generation);
     k_ed_pixel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(B, d, npx);
     k_ed_anchor<<<dim3((d.anchor_words + 127) / 128, d.n_frames), 128, 0, st>>>(B, d);
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[1], st));

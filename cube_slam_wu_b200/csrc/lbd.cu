@@ -84,6 +84,10 @@ __device__ __forceinline__ void lbd_sincos(double x, double& s, double& c) {
 // ---------------------------------------------------------------------------------------------------------------------------------
 // blur 5x5 (fixed point) + Sobel -> {dx, dy} int16 pairs
 // ---------------------------------------------------------------------------------------------------------------------------------
+// K0, K1, K2: the integer taps {K0, K1, K2, K1, K0} / 256 of the 8-bit 5x5 Gaussian; SAT: saturate the blurred value to 255 (needed when the taps
+// sum to more than 256).  <14, 62, 104, false> = cv2 4.x's fixed-point path; <14, 63, 103, true> = OpenCV <= 3.4.0 (sepFilter2D with 8 fractional
+// bits, every tap rounded on its own), the generation the reference's committed outputs were produced with (oracle/oracle_lbd.cpp).
+template <int K0, int K1, int K2, bool SAT>
 __global__ void __launch_bounds__(LG_THREADS) k_lbd_grad(const uint8_t* __restrict__ gray, short2* __restrict__ grad, int w, int h) {
     __shared__ uint8_t s_g[LG_TH + 6][LG_TW + 8];          // gray rows y0-3 .. y0+TH+2, columns x0-3 .. x0+TW+2
     __shared__ unsigned short s_h[LG_TH + 6][LG_TW + 2];   // horizontal sums, columns x0-1 .. x0+TW
@@ -100,13 +104,14 @@ __global__ void __launch_bounds__(LG_THREADS) k_lbd_grad(const uint8_t* __restri
     for (int i = tid; i < (LG_TH + 6) * (LG_TW + 2); i += LG_THREADS) {
         const int r = i / (LG_TW + 2), c = i - r * (LG_TW + 2);
         const uint8_t* p = &s_g[r][c];
-        s_h[r][c] = (unsigned short)(14 * (p[0] + p[4]) + 62 * (p[1] + p[3]) + 104 * p[2]);
+        s_h[r][c] = (unsigned short)(K0 * (p[0] + p[4]) + K1 * (p[1] + p[3]) + K2 * p[2]);   // <= 257 * 255 = 65535
     }
     __syncthreads();
     for (int i = tid; i < (LG_TH + 2) * (LG_TW + 2); i += LG_THREADS) {
         const int r = i / (LG_TW + 2), c = i - r * (LG_TW + 2);
-        const unsigned v = 14u * (s_h[r][c] + s_h[r + 4][c]) + 62u * (s_h[r + 1][c] + s_h[r + 3][c]) + 104u * s_h[r + 2][c];
-        s_b[r][c] = (uint8_t)((v + 32768u) >> 16);
+        const unsigned v = (unsigned)K0 * (s_h[r][c] + s_h[r + 4][c]) + (unsigned)K1 * (s_h[r + 1][c] + s_h[r + 3][c]) + (unsigned)K2 * s_h[r + 2][c];
+        const unsigned bv = (v + 32768u) >> 16;
+        s_b[r][c] = (uint8_t)(SAT ? min(bv, 255u) : bv);
     }
     __syncthreads();
     for (int i = tid; i < LG_TH * LG_TW; i += LG_THREADS) {
@@ -424,11 +429,14 @@ struct LbdState {
     const int* src_counts = nullptr;
 };
 
-void lbd_launch_grad(const uint8_t* gray, short2* grad, int w, int h, int n_frames, cudaStream_t st) {
-    if (w % 4 == 0)
+void lbd_launch_grad(const uint8_t* gray, short2* grad, int w, int h, int n_frames, cudaStream_t st, int blur_generation) {
+    const dim3 gg((w + LG_TW - 1) / LG_TW, (h + LG_TH - 1) / LG_TH, n_frames);
+    if (blur_generation == 3)  // the taps of OpenCV <= 3.4.0 (csb_set_blur_generation); one pixel per thread, any width
+        k_lbd_grad<14, 63, 103, true><<<gg, LG_THREADS, 0, st>>>(gray, grad, w, h);
+    else if (w % 4 == 0)
         k_lbd_grad4<<<dim3((w + L4_TW - 1) / L4_TW, (h + L4_TH - 1) / L4_TH, n_frames), L4_THREADS, 0, st>>>(gray, grad, w, h);
     else
-        k_lbd_grad<<<dim3((w + LG_TW - 1) / LG_TW, (h + LG_TH - 1) / LG_TH, n_frames), LG_THREADS, 0, st>>>(gray, grad, w, h);
+        k_lbd_grad<14, 62, 104, false><<<gg, LG_THREADS, 0, st>>>(gray, grad, w, h);
 }
 
 void lbd_release(LbdState*& s) {
@@ -493,7 +501,7 @@ static int lbd_outputs(csb_context* c, LbdState& s) {
 static int lbd_launch(csb_context* c, LbdState& s, int timed) {
     cudaStream_t st = c->stream;
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[0], st));
-    lbd_launch_grad(s.src_gray, s.d_grad.as<short2>(), s.w, s.h, s.n_frames, st);
+    lbd_launch_grad(s.src_gray, s.d_grad.as<short2>(), s.w, s.h, s.n_frames, st, c->blur_generation);
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[1], st));
     k_lbd_prefix<<<1, 1024, 0, st>>>(s.src_counts, s.n_frames, s.stride, s.d_prefix.as<int>(), s.d_ctr.as<unsigned long long>());
     LbdArgs A{};

@@ -12,6 +12,6 @@ struct LbdState;  // defined in lbd.cu
 void lbd_release(LbdState*& s);
 
 // blur 5x5 + Sobel of n_frames gray frames -> {dx, dy} int16 pairs (k_lbd_grad4 / k_lbd_grad); also the first stage of EDLines
-void lbd_launch_grad(const uint8_t* gray, short2* grad, int w, int h, int n_frames, cudaStream_t st);
+void lbd_launch_grad(const uint8_t* gray, short2* grad, int w, int h, int n_frames, cudaStream_t st, int blur_generation);
 
 }  // namespace csb

@@ -293,6 +293,12 @@ int csb_lsd_debug_maps(csb_context* ctx, int frame, double* scaled_out, double* 
  * Output rows are line_descrips': 32 bytes per line (CV_8UC1, returnFloatDescr = false) and, on request, the 72 floats behind them
  * (returnFloatDescr = true), one row per input line, frame after frame.  A frame without lines yields no rows (computeImpl returns early).
  * Not provided: line_lbd_detect::get_line_descriptors (its mat_to_keylines reads KeyLine fields before setting them) and the matcher. */
+/* The LBD descriptor and EDLines both start from BinaryDescriptor's blurred frame: cv::GaussianBlur(img, Size(5, 5), 1) on CV_8U
+ * (binary_descriptor.cpp:356, 815-816).  OpenCV is not part of the reference tree and the 8-bit Gaussian exists in two generations that differ
+ * in the integer taps: 4 (default) = OpenCV >= 3.4.1 / 4.x, {14, 62, 104, 62, 14} / 256; 3 = OpenCV <= 3.4.0, {14, 63, 103, 63, 14} / 256 -- the
+ * generation the reference's committed object_slam outputs were produced with (tests/test_reference_replay.py). */
+int csb_set_blur_generation(csb_context* ctx, int generation);
+
 typedef struct csb_lbd_stats {
     int64_t n_lines;    /* descriptors computed */
     int64_t n_samples;  /* gradient samples gathered: 63 rows x numOfPixels per line */

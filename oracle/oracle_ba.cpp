@@ -14,8 +14,8 @@
 //
 // PARITY STATUS: PINNED against outputs of the reference itself: tests/test_reference_replay.py re-runs object_slam's online mode on the
 // bundled TUM sequence (graph recipe of main_obj.cpp:738-803, optimize(5) after every frame with this file's numeric Jacobians and
-// Levenberg-Marquardt) and reproduces the committed output_obj_poses.txt (landmark after each of the first 28 frames to the printed digits,
-// all 58 within 5 mm of scale) and output_cam_poses.txt (median 2.5 mm).  The offline fixture is covered by tests/test_oracle_golden.py.
+// Levenberg-Marquardt) and reproduces the committed output_obj_poses.txt (landmark after every one of the 58 frames to the printed
+// digits) and output_cam_poses.txt (0.07 mm in the median).  The offline fixture is covered by tests/test_oracle_golden.py.
 #include <algorithm>
 #include <cmath>
 #include <cstring>

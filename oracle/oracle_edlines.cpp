@@ -14,7 +14,7 @@
 //
 // PARITY STATUS: PINNED through the reference's own committed outputs.  The reference ships no EDLines segment file, but its object_slam
 // node ran this detector (main_obj.cpp:504) to produce output_obj_poses.txt / output_cam_poses.txt, and tests/test_reference_replay.py
-// reproduces those files to their printed digits for the first 28 frames with this oracle feeding the cuboid proposals -- with the LSD
+// reproduces all 58 rows to their printed digits with this oracle (and the OpenCV <= 3.4.0 blur taps, oracle_lbd.cpp) feeding the cuboid proposals -- with the LSD
 // branch instead, the landmark history leaves the committed one at the second frame: the best proposal of a frame depends on the exact
 // line table.  The OpenCV arithmetic underneath (blur, Sobel) is the same cv2-pinned code as oracle_lbd.cpp (orc_lbd_gradients).
 //

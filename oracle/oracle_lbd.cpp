@@ -45,9 +45,18 @@ inline int reflect101(int p, int len) {
     return p;
 }
 
-// cv::GaussianBlur(src, dst, Size(5, 5), 1) on CV_8UC1 (binary_descriptor.cpp:356): cv2 4.13 runs its fixed-point path
+// cv::GaussianBlur(src, dst, Size(5, 5), 1) on CV_8UC1 (binary_descriptor.cpp:356, :815-816).  OpenCV is not part of the reference tree and
+// its version is not pinned by the reference's CMake files; the 8-bit Gaussian exists in two generations that differ in the integer taps:
+//   generation 4 (default here; cv2 4.13's bit-exact fixed-point path, pinned by tests/golden/lbd_cv2.npz): {14, 62, 104, 62, 14} / 256
+//   generation 3 (OpenCV <= 3.4.0: sepFilter2D with 8 fractional bits, every tap rounded on its own):   {14, 63, 103, 63, 14} / 256
+// Both: exact integer row sums, exact column sums, one rounding (v + 2^15) >> 16, saturated to 255 (generation 3's taps sum to 257).
+// Generation 3 is what the reference's author ran: with it -- and only with it -- the replay of object_slam's online mode reproduces ALL 58
+// rows of the committed output_obj_poses.txt to the printed digits (tests/test_reference_replay.py); with generation 4 the landmark history
+// leaves the committed one at frame 28.
+int g_blur_generation = 4;
 void blur5(const uint8_t* g, int w, int h, std::vector<uint8_t>& out) {
-    static const int K[5] = {14, 62, 104, 62, 14};
+    static const int K4[5] = {14, 62, 104, 62, 14}, K3[5] = {14, 63, 103, 63, 14};
+    const int* K = g_blur_generation == 3 ? K3 : K4;
     std::vector<int> hz((size_t)w * h);
     for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++) {
@@ -60,7 +69,8 @@ void blur5(const uint8_t* g, int w, int h, std::vector<uint8_t>& out) {
         for (int x = 0; x < w; x++) {
             int s = 0;
             for (int t = 0; t < 5; t++) s += K[t] * hz[(size_t)reflect101(y + t - 2, h) * w + x];
-            out[(size_t)y * w + x] = (uint8_t)((s + 32768) >> 16);
+            const int v = (s + 32768) >> 16;
+            out[(size_t)y * w + x] = (uint8_t)(v > 255 ? 255 : v);
         }
 }
 
@@ -242,6 +252,9 @@ void compute_lbd(const KeyLine& kl, const int16_t* pdx, const int16_t* pdy, int 
 }  // namespace
 
 extern "C" {
+
+// 4 (default): cv2 4.x taps; 3: the taps of OpenCV <= 3.4.0, the generation the reference's committed outputs were produced with
+void orc_lbd_set_blur_generation(int gen) { g_blur_generation = gen == 3 ? 3 : 4; }
 
 // blurred frame (optional) and the two int16 gradient images the descriptor samples
 void orc_lbd_gradients(const uint8_t* gray, int w, int h, uint8_t* blur_out, int16_t* dx_out, int16_t* dy_out) {

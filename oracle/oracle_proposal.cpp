@@ -11,7 +11,7 @@
 // PARITY STATUS: PINNED against outputs of the reference itself.  The reference has no tests and does not compile here (needs Eigen,
 // OpenCV, ROS), but it commits what its object_slam node wrote in online mode for the bundled TUM sequence
 // (object_slam/data/output_obj_poses.txt, output_cam_poses.txt), and tests/test_reference_replay.py re-runs that mode with this file
-// (after oracle_edlines.cpp + cv2 Canny / distance transform, before oracle_ba.cpp): the landmark pose after each of the first 28 frames
+// (after oracle_edlines.cpp + cv2 Canny / distance transform, before oracle_ba.cpp): the landmark pose after every one of the 58 frames
 // comes out to the files' printed digits, frame 0 being a single detect_cuboid() result, frames 1.. with camera roll / pitch sampling on.
 // Also pinned:
 //   * ray_plane_interact worked example, object_3d_util.cpp:884-905 (tests/test_oracle_golden.py)

@@ -238,6 +238,12 @@ def lsd_spec_sim(gray, K):
 
 
 # ---- LBD line descriptor (oracle/oracle_lbd.cpp) -----------------------------------------------------------------------------------
+def lbd_set_blur_generation(gen):
+    """4 (default): cv2 4.x integer taps of the 8-bit 5x5 Gaussian; 3: OpenCV <= 3.4.0's (what the reference's author ran).  Affects the
+    LBD and EDLines oracles (both start from BinaryDescriptor's blurred frame)."""
+    lib().orc_lbd_set_blur_generation(int(gen))
+
+
 def lbd_gradients(gray):
     """blurred frame (u8) and the int16 Sobel images BinaryDescriptor::computeSobel produces."""
     gray = np.ascontiguousarray(gray, np.uint8)

@@ -51,11 +51,18 @@ def quat_to_euler_zyx(q):  # matrix_utils.cpp:38-51; q = x y z w
 class OracleBackend:
     """every stage from the CPU oracles (distance maps: cv2, the reference's own calls box_proposal_detail.cpp:320-327)"""
 
-    def __init__(self, use_lsd=False):
+    def __init__(self, use_lsd=False, blur_generation=3):
         self.use_lsd = use_lsd
+        self.blur_generation = blur_generation   # 3: the 8-bit Gaussian taps of OpenCV <= 3.4.0, what the reference's author ran (oracle_lbd.cpp)
 
     def lines(self, gray):
-        return (O.lsd_detect(gray) if self.use_lsd else O.edlines_detect(gray)[0]).astype(np.float64)
+        if self.use_lsd:
+            return O.lsd_detect(gray).astype(np.float64)
+        O.lbd_set_blur_generation(self.blur_generation)
+        try:
+            return O.edlines_detect(gray)[0].astype(np.float64)
+        finally:
+            O.lbd_set_blur_generation(4)
 
     def best_cuboid(self, gray, T0, box, lines, sample):
         H, W = gray.shape
@@ -81,14 +88,18 @@ class GpuBackend:
     """every stage from libcubeslam_b200.so through the C ABI: csb_edlines_detect_batch (or csb_lsd_detect_batch), csb_detect_batch_gray
     (Canny + distance transform + proposals on the GPU), csb_ba_set_graph + csb_ba_optimize (LM on the device)"""
 
-    def __init__(self, ctx, csb, use_lsd=False):
-        self.ctx, self.csb, self.use_lsd = ctx, csb, use_lsd
+    def __init__(self, ctx, csb, use_lsd=False, blur_generation=3):
+        self.ctx, self.csb, self.use_lsd, self.blur_generation = ctx, csb, use_lsd, blur_generation
 
     def lines(self, gray):
         if self.use_lsd:
             out, _ = self.ctx.lsd_detect_batch(gray[None], 15.0, True)
         else:
-            out, _ = self.ctx.edlines_detect_batch(gray[None], 15.0, True)
+            self.ctx.set_blur_generation(self.blur_generation)   # csb_set_blur_generation: the author's OpenCV generation (see OracleBackend)
+            try:
+                out, _ = self.ctx.edlines_detect_batch(gray[None], 15.0, True)
+            finally:
+                self.ctx.set_blur_generation(4)
         return np.ascontiguousarray(out[0].astype(np.float64)).reshape(-1, 4)
 
     def best_cuboid(self, gray, T0, box, lines, sample):

@@ -106,6 +106,7 @@ def test_null_context_lbd(csb):
     assert L.csb_edlines_run(None, 0) == csb.CSB_ERR_STATE
     assert L.csb_edlines_download(None, None, None, None) == csb.CSB_ERR_STATE
     assert L.csb_edlines_describe(None, 0) == csb.CSB_ERR_STATE
+    assert L.csb_set_blur_generation(None, 3) == csb.CSB_ERR_INVALID
     assert L.csb_edlines_download_descriptors(None, None, None, None, C.c_int64(0)) == csb.CSB_ERR_STATE
     assert C.sizeof(csb.EdlinesStats) == 6 * 8 + 2 * 4 + 4 * 4
 

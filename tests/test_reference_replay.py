@@ -3,9 +3,10 @@
 output_obj_poses.txt / output_cam_poses.txt (object_slam/data/) are what the reference's node wrote in online mode for the 58 frames in
 object_slam/data/raw_imgs with the boxes in filter_2d_obj_txts.  tests/replay.py re-runs that mode with the CPU oracles -- EDLines line
 detection, cv2 Canny + distance transform, the cuboid proposal sweep / scoring / ranking / 3D recovery, the measurement and graph recipe, five
-Levenberg-Marquardt iterations with the numeric Jacobians after every frame -- and reproduces the files: the landmark pose after each of the
-first 28 frames to the printed digits (a single differently ranked proposal anywhere in those frames would show), every later frame within
-5 mm of scale, the camera track within millimetres (median).  This is the pin of the EDLines, proposal and BA oracles."""
+Levenberg-Marquardt iterations with the numeric Jacobians after every frame -- and reproduces the files: the landmark pose after EVERY ONE of
+the 58 frames to the printed digits (a single differently ranked proposal in any frame would show), the camera track to 0.07 mm in the median.  This is
+the pin of the EDLines, proposal and BA oracles.  It needs the 8-bit Gaussian of the OpenCV generation the author ran (<= 3.4.0:
+integer taps {14, 63, 103, 63, 14}); with cv2 4.x's taps {14, 62, 104, 62, 14} the history leaves the committed one at frame 28."""
 import numpy as np
 import pytest
 
@@ -31,17 +32,23 @@ def test_online_mode_reproduces_the_reference_output_files(seq):
     dscale = np.abs(obj[:, 6:9] - out_obj[:, 6:9]).max(axis=1)
     # frame 0 is a single detection moved to the world frame: the whole proposal path against one committed row
     assert dpos[0] < 5e-5 and dyaw[0] < 5e-5 and dscale[0] < 5e-5
-    # the first 28 frames: the files' printed precision (6 significant digits)
-    assert dpos[:28].max() < 5e-5 and dyaw[:28].max() < 1e-4 and dscale[:28].max() < 1e-4, (dpos[:28].max(), dyaw[:28].max(), dscale[:28].max())
-    # later frames: one frame's best proposal differs from the author's run (their OpenCV / JPEG decoder are not ours); the optimised landmark
-    # stays within 5 mm of scale and 0.1 mm of position of the committed history
-    assert dpos.max() < 1e-4 and dyaw.max() < 2e-3 and dscale.max() < 6e-3, (dpos.max(), dyaw.max(), dscale.max())
+    # all 58 frames: the files' printed precision (6 significant digits)
+    assert dpos.max() < 5e-5 and dyaw.max() < 1e-4 and dscale.max() < 1e-4, (dpos.max(), dyaw.max(), dscale.max())
     dcam = np.linalg.norm(r["Twc"][:, :3] - out_cam[:, 1:4], axis=1)
-    assert np.median(dcam) < 5e-3 and dcam.max() < 0.1, (np.median(dcam), dcam.max())
-    # and the track is as close to ground truth as the committed one
-    e_ours = np.linalg.norm(r["Twc"][:, :3] - truth[:, 1:4], axis=1).mean()
-    e_ref = np.linalg.norm(out_cam[:, 1:4] - truth[:, 1:4], axis=1).mean()
-    assert abs(e_ours - e_ref) < 0.01
+    # the camera track: 0.07 mm in the median; up to 3 mm around the frames without a detection, which only the odometry edges hold (there the
+    # result depends on the linear solver: Eigen's LDLT in the reference, a plain LDL^T here)
+    assert np.median(dcam) < 2e-4 and dcam.max() < 5e-3, (np.median(dcam), dcam.max())
+    dq = np.minimum(np.abs(r["Twc"][:, 3:7] - out_cam[:, 4:8]).max(axis=1), np.abs(r["Twc"][:, 3:7] + out_cam[:, 4:8]).max(axis=1))
+    assert dq.max() < 1e-3, dq.max()
+
+
+def test_the_opencv_generation_of_the_blur_matters(seq):
+    """With cv2 4.x's taps of the 8-bit 5x5 Gaussian (what the GPU gradient kernel and the cv2 fixtures use by default) the EDLines line tables
+    differ slightly and one frame's ranking changes: the history follows the committed one for 28 frames and stays within 5 mm afterwards."""
+    frames, boxes, truth, out_obj, out_cam = seq
+    r = replay.run(replay.OracleBackend(blur_generation=4), frames, boxes, truth)
+    dscale = np.abs(r["obj"][:, 6:9] - out_obj[:, 6:9]).max(axis=1)
+    assert dscale[:28].max() < 1e-4 and 1e-3 < dscale.max() < 6e-3
 
 
 def test_replay_discriminates(seq):
@@ -62,6 +69,10 @@ class _FakeCtx:
     def __init__(self, csb):
         self.csb = csb
         self.calls = []
+
+    def set_blur_generation(self, generation):
+        self.calls.append("blur%d" % generation)
+        replay.O.lbd_set_blur_generation(generation)
 
     def lsd_detect_batch(self, gray, line_length_thres=15.0, filter=True, max_lines=4096):
         self.calls.append("lsd")
@@ -126,7 +137,7 @@ def test_gpu_backend_glue_with_a_fake_context(seq, csb):
     got = replay.run(replay.GpuBackend(fake, csb), frames, boxes, truth, n_frames=n)
     assert np.array_equal(got["n_lines"], ref["n_lines"])
     assert np.array_equal(got["cube10"], ref["cube10"]) and np.array_equal(got["Twc"], ref["Twc"])
-    assert fake.calls[:5] == ["edlines", "detect", "set_graph", "upload", "optimize"]
+    assert fake.calls[:7] == ["blur3", "edlines", "blur4", "detect", "set_graph", "upload", "optimize"]
     assert fake.calls.count("detect") == sum(1 for b in boxes[:n] if len(b)) < n   # frames without a YOLO box skip detect_cuboid
     fake2 = _FakeCtx(csb)
     replay.run(replay.GpuBackend(fake2, csb, use_lsd=True), frames, boxes, truth, n_frames=3)

@@ -38,6 +38,22 @@ for (n, w, h, seed, kw) in ((5, 640, 480, 3, {}), (2, 641, 479, 4, dict(texture=
         total += n_ref
     chains = [O.edlines_chains(fr) for fr in frames]
     assert st.n_chains == sum(len(c) for c in chains) and st.n_chain_px == sum(sum(len(x) for x in c) for c in chains)
+# csb_set_blur_generation(3): the 8-bit Gaussian taps of OpenCV <= 3.4.0 in front of LBD / EDLines (gradient images bit-exact, segments identical)
+frames = synth.make_lsd_frames(2, 333, 251, seed=31, texture=1.0, noise_sigma=4.0)
+frames[0, 20:80, 30:120] = 255          # a saturated patch: the generation-3 taps sum to 257
+ctx.set_blur_generation(3); O.lbd_set_blur_generation(3)
+try:
+    ctx.lbd_upload(frames, [np.zeros((0, 4), np.float32)] * 2); ctx.lbd_run()
+    for f in range(2):
+        dx, dy = ctx.lbd_debug_gradients(f, (251, 333))
+        _, rdx, rdy = O.lbd_gradients(frames[f])
+        assert np.array_equal(dx, rdx) and np.array_equal(dy, rdy), "generation-3 gradients differ"
+    lines, st = ctx.edlines_detect_batch(frames)
+    for f in range(2):
+        ref, _ = O.edlines_detect(frames[f])
+        assert np.array_equal(lines[f].view(np.uint32), ref.view(np.uint32)), "generation-3 segments differ"
+finally:
+    ctx.set_blur_generation(4); O.lbd_set_blur_generation(4)
 # detect_descrip_lines with use_LSD = false: descriptors of the key lines, from the detector's own fields (csb_edlines_describe)
 frames = synth.make_lsd_frames(3, 640, 480, seed=9)
 out = ctx.edlines_detect_describe_batch(frames, want_float=True)
@@ -96,7 +112,7 @@ assert d_obj < 1e-4 and d_cam < 1e-4, (d_obj, d_cam)           # same best propo
 if not %(lsd)d:
     dpos = np.linalg.norm(gpu["obj"][:, :3] - out_obj[:, :3], axis=1)
     dscale = np.abs(gpu["obj"][:, 6:9] - out_obj[:, 6:9]).max(axis=1)
-    assert dpos[:28].max() < 1e-4 and dscale[:28].max() < 2e-4 and dscale.max() < 6e-3, (dpos[:28].max(), dscale[:28].max(), dscale.max())
+    assert dpos.max() < 1e-4 and dscale.max() < 2e-4, (dpos.max(), dscale.max())   # all 58 rows of output_obj_poses.txt, printed precision
 print("REPLAY_GPU_OK lsd=%(lsd)d: GPU vs oracle replay: landmark %%.2e, cameras %%.2e" %% (d_obj, d_cam))
 ctx.close()
 '''
@@ -125,7 +141,7 @@ def test_online_mode_replay_through_the_c_abi_lsd_lines(tmp_path):
 
 def test_online_mode_replay_through_the_c_abi_edlines(tmp_path):
     """The same with the EDLines kernels (first hardware run pending, see above), which is the detector the reference's committed output files
-    were produced with: the GPU replay must then also reproduce output_obj_poses.txt to the printed digits for the first 28 frames."""
+    were produced with: the GPU replay must then also reproduce all 58 rows of output_obj_poses.txt to the printed digits."""
     ok, tail = _replay_child(tmp_path, 0)
     if not ok:
         pytest.xfail("GPU replay with the EDLines kernels (first hardware run):\n" + tail)
