@@ -35,8 +35,8 @@ def test_online_mode_reproduces_the_reference_output_files(seq):
     # all 58 frames: the files' printed precision (6 significant digits)
     assert dpos.max() < 5e-5 and dyaw.max() < 1e-4 and dscale.max() < 1e-4, (dpos.max(), dyaw.max(), dscale.max())
     dcam = np.linalg.norm(r["Twc"][:, :3] - out_cam[:, 1:4], axis=1)
-    # the camera track: 0.07 mm in the median; up to 3 mm around the frames without a detection, which only the odometry edges hold (there the
-    # result depends on the linear solver: Eigen's LDLT in the reference, a plain LDL^T here)
+    # the camera track: 0.07 mm in the median, up to 3 mm around frame 49 (not the linear solver: a pivoted LDL^T like Eigen's gives the same
+    # numbers; a late frame's measurement evidently differs from the author's without moving the 50-observation landmark by 1e-4)
     assert np.median(dcam) < 2e-4 and dcam.max() < 5e-3, (np.median(dcam), dcam.max())
     dq = np.minimum(np.abs(r["Twc"][:, 3:7] - out_cam[:, 4:8]).max(axis=1), np.abs(r["Twc"][:, 3:7] + out_cam[:, 4:8]).max(axis=1))
     assert dq.max() < 1e-3, dq.max()
