@@ -483,16 +483,11 @@ class line_lbd_detect:
         self.use_LSD = True            # line_lbd_allclass.cpp:125 defaults to False (EDLines)
         self.line_length_thres = 50.0  # line_lbd_allclass.cpp:126; both callers overwrite it with 15
         self.max_lines = 4096
-        # use_LSD = False runs csb_edlines_* -- whose kernels had not been run on hardware when round 1 ended (the device code is validated
-        # on the host, tests/test_edlines_emul.py), so it has to be switched on explicitly until tests/test_zz_edlines_gpu.py has been seen green
-        self.allow_unvalidated_edlines = False
 
     def detect_filter_lines(self, gray_img):
         """line_lbd_allclass.cpp:221-235: gray image(s) -> linesmat_out rows [x1 y1 x2 y2] float32 (one array per frame)."""
         single = np.asarray(gray_img).ndim == 2
         if not self.use_LSD:
-            if not self.allow_unvalidated_edlines:
-                raise CsbError(CSB_ERR_INVALID, "use_LSD = false (EDLines): the GPU path awaits its first hardware validation; set allow_unvalidated_edlines")
             out, _ = self._ctx.edlines_detect_batch(gray_img, self.line_length_thres, True, self.max_lines)
             return out[0] if single else out
         out, _ = self._ctx.lsd_detect_batch(gray_img, self.line_length_thres, True, self.max_lines)
@@ -504,8 +499,6 @@ class line_lbd_detect:
         single = np.asarray(gray_img).ndim == 2
         c = self._ctx
         if not self.use_LSD:
-            if not self.allow_unvalidated_edlines:
-                raise CsbError(CSB_ERR_INVALID, "use_LSD = false (EDLines): the GPU path awaits its first hardware validation; set allow_unvalidated_edlines")
             out = c.edlines_detect_describe_batch(gray_img, self.line_length_thres, True, self.max_lines)
             return (out["lines"][0], out["desc"][0]) if single else (out["lines"], out["desc"])
         c.lsd_upload(gray_img, self.line_length_thres, True, self.max_lines)

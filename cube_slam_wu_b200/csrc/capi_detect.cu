@@ -4,6 +4,8 @@
 // (detect_3d_cuboid/include/detect_3d_cuboid/detect_3d_cuboid.h:81-92).  No CPU fallback: if CUDA is not usable every
 // computing entry point returns CSB_ERR_CUDA.
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -11,6 +13,16 @@
 #include "host_plan.h"
 
 using namespace csb;
+
+// process-wide epoch of the chunked distance-map upload (csb_detect_batch): see detect_upload_impl
+static std::atomic<unsigned> g_stream_epoch{0};
+
+// k_score polls flags that a second stream writes while it runs; with a single hardware queue (CUDA_DEVICE_MAX_CONNECTIONS=1) the copies
+// could be queued behind the kernel that waits for them, so the streamed upload is only used when the queues are independent.
+static bool copy_engine_is_concurrent() {
+    const char* e = std::getenv("CUDA_DEVICE_MAX_CONNECTIONS");
+    return !(e && std::atoi(e) <= 1);
+}
 
 extern "C" {
 
@@ -50,6 +62,7 @@ void csb_destroy(csb_context* c) {
     for (DevBuf* b : bufs) b->release();
     d.h_tables.release(); d.h_results.release();
     if (d.ev_tables) cudaEventDestroy(d.ev_tables);
+    if (d.ev_order) cudaEventDestroy(d.ev_order);
     for (int i = 0; i < 7; i++)
         if (d.ev[i]) cudaEventDestroy(d.ev[i]);
     ba_release(c->ba);
@@ -138,15 +151,24 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
         if (gray_total) CSB_CUDA(c, cudaMemcpyAsync(d.d_gray.p, gray, (size_t)gray_total, cudaMemcpyHostToDevice, st));
     } else if (n_map_floats > 0) {
         CSB_CUDA(c, d.d_maps.ensure(4 * (size_t)n_map_floats + 64));
-        if (stream_maps && n_map_floats >= (1 << 18)) {
+        if (stream_maps && n_map_floats >= (1 << 18) && copy_engine_is_concurrent()) {
             // csb_detect_batch: equal slices on the copy stream, each followed by its flag word (same stream => ordered).  k_score starts
             // right away and a task waits for the slice that holds the END of its map (slices complete in order).
             streaming = true;
             n_chunks = CSB_MAX_CHUNKS;
-            CSB_CUDA(c, d.d_flags.ensure(4 * CSB_MAX_CHUNKS));
+            if (!d.d_flags.p) {
+                // a fresh (possibly recycled) block: no flag may carry a value that a later epoch could equal
+                CSB_CUDA(c, d.d_flags.ensure(4 * CSB_MAX_CHUNKS));
+                CSB_CUDA(c, cudaMemset(d.d_flags.p, 0, 4 * CSB_MAX_CHUNKS));
+            }
             CSB_CUDA(c, cudaStreamSynchronize(c->copy_stream));  // nothing may still be reading the epoch word
-            d.epoch++;
+            // epochs are unique per process (not per context), never 0: a flag left behind by a destroyed context cannot match
+            do { d.epoch = g_stream_epoch.fetch_add(1) + 1; } while (d.epoch == 0);
             *c->h_epoch = d.epoch;
+            // the copies below overwrite d_maps: earlier work on the compute stream (a csb_detect_run that was never downloaded) may still read it
+            if (!d.ev_order) CSB_CUDA(c, cudaEventCreateWithFlags(&d.ev_order, cudaEventDisableTiming));
+            CSB_CUDA(c, cudaEventRecord(d.ev_order, st));
+            CSB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, d.ev_order, 0));
             int64_t b0 = 0;
             for (int k = 0; k < n_chunks; k++) {
                 const int64_t b1 = (k == n_chunks - 1) ? n_map_floats : ((n_map_floats * (k + 1) / n_chunks) & ~(int64_t)3);

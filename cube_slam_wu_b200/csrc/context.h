@@ -74,6 +74,7 @@ struct DetectState {
     HostBuf h_tables, h_results;
     size_t res_off_ncub = 0, res_off_nvalid = 0, res_off_nkeep = 0, res_bytes = 0;
     cudaEvent_t ev_tables = nullptr;  // h_tables consumed by the device
+    cudaEvent_t ev_order = nullptr;   // compute stream -> copy stream ordering of the streamed map upload
     bool gray_mode = false;
     unsigned epoch = 0;
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -119,6 +119,8 @@ int plan_tasks(const csb_frame* frames, int n_frames, const double* boxes, int n
     for (int f = 0; f < n_frames; f++) {
         const csb_frame& fr = frames[f];
         if (fr.box_begin < 0 || fr.box_end > n_boxes || fr.box_begin > fr.box_end) return CSB_ERR_INVALID;
+        // frames own disjoint, ascending box ranges: a box's tasks must be contiguous (box -> task prefix sums, k_rank, k_observe)
+        if (f > 0 && fr.box_begin < frames[f - 1].box_end) return CSB_ERR_INVALID;
         int n_groups = 0;
         int rc = frame_group_count(fr, p, &n_groups);
         if (rc != CSB_OK) return rc;

@@ -960,7 +960,7 @@ __global__ void __launch_bounds__(32) k_rank(DetectBuffers B) {
         while (slot >= B.n_keep[t]) { slot -= B.n_keep[t]; t++; }
         j = slot;
     };
-    int* ridx = (t1 > t0) ? B.rank_idx + (size_t)B.ttab[t0].out_offset : nullptr;  // scratch: >= S slots
+    int* ridx = (t1 > t0) ? B.rank_idx + 2 * (size_t)B.ttab[t0].out_offset : nullptr;  // scratch: 2 x the box's capacity (ridx[M] | win[M], M <= S <= capacity)
     // compact the ok slots (ordered) and count them
     int M = 0;
     for (int s0 = 0; s0 < S; s0 += 32) {
@@ -977,7 +977,7 @@ __global__ void __launch_bounds__(32) k_rank(DetectBuffers B) {
     if (k == 0) return;
     auto score_of_slot = [&](int s) { int t, j; locate(s, t, j); return B.cand_score[(size_t)B.ttab[t].out_offset + j]; };
     // winners[w] = rank index (position in ridx) of the w-th best
-    int* win = ridx + M;  // scratch behind the compacted list (capacity n_hyp >= 2 * S)
+    int* win = ridx + M;  // scratch behind the compacted list
     if (k == 1) {
         // partial_sort(idx, idx+1, end): start with element 0, replace by every later strictly smaller one.  That is the first
         // index of the minimum over the non-NaN scores -- unless score[0] is NaN, which nothing can replace.
