@@ -118,8 +118,14 @@ def test_line_lbd_mirror_refuses_unported_modes(csb):
         csb.line_lbd_detect(_Ctx(), numoctaves=2)
     d = csb.line_lbd_detect(_Ctx())
     assert d.use_LSD is True and d.line_length_thres == 50.0  # the reference's default threshold (line_lbd_allclass.cpp:126)
+    # use_LSD = False (EDLines, what object_slam selects) routes to csb_edlines_*: exercised on the GPU by tests/test_edlines_gpu.py
+    calls = []
+    ctx = _Ctx()
+    ctx.edlines_detect_batch = lambda g, thr, filt, cap: (calls.append(("edlines", thr, filt)) or ([np.zeros((0, 4), np.float32)], None))
+    ctx.lsd_detect_batch = lambda g, thr, filt, cap: (calls.append(("lsd", thr, filt)) or ([np.zeros((0, 4), np.float32)], None))
+    d = csb.line_lbd_detect(ctx)
+    d.line_length_thres = 15.0
+    d.detect_filter_lines(np.zeros((8, 8), np.uint8))
     d.use_LSD = False
-    with pytest.raises(csb.CsbError):
-        d.detect_filter_lines(np.zeros((8, 8), np.uint8))
-    with pytest.raises(csb.CsbError):
-        d.detect_descrip_lines(np.zeros((8, 8), np.uint8))
+    d.detect_filter_lines(np.zeros((8, 8), np.uint8))
+    assert calls == [("lsd", 15.0, True), ("edlines", 15.0, True)]
