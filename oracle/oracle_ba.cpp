@@ -212,8 +212,10 @@ void err_odom(const SE3& T1, const SE3& T2, const SE3& C, double e[6]) {
 // VertexSE3Expmap::oplusImpl, types_six_dof_expmap.h:73-76
 SE3 cam_oplus(const SE3& T, const double u[6]) { return se3_exp(u) * T; }
 
-const double kDelta = 1e-9;
-const double kScalar = 1.0 / (2 * kDelta);
+// delta = 1e-9 is the reference's (base_binary_edge.hpp:147).  Test knob (orc_ba_set_delta): a larger step gives central differences whose
+// round-off is far below the reference's (1e-16 / delta), i.e. an independent, accurate Jacobian to hold the closed-form ones against.
+double kDelta = 1e-9;
+double kScalar = 1.0 / (2 * kDelta);
 
 // Generic numeric Jacobian (base_binary_edge.hpp:130-205).  f(vi, vj, err) evaluates the residual.
 template <int D, int Di, int Dj, class VI, class VJ, class F, class OI, class OJ>
@@ -524,6 +526,8 @@ static void bind_edges(Graph& g, const orc_ba_edges* E) {
     g.n_ep = E->n_ep; g.ep_cam = E->ep_cam; g.ep_cube = E->ep_cube; g.ep_meas = E->ep_meas4; g.ep_info = E->ep_info16; g.ep_K = E->ep_K9;
     g.n_eo = E->n_eo; g.eo_i = E->eo_i; g.eo_j = E->eo_j; g.eo_meas = E->eo_meas7; g.eo_info = E->eo_info36;
 }
+
+void orc_ba_set_delta(double delta) { kDelta = delta; kScalar = 1.0 / (2 * kDelta); }
 
 // One computeActiveErrors + buildSystem pass.  Any output pointer may be NULL.  Returns chi2.
 double orc_ba_linearize(int n_cam, const double* cams7, const int* cam_fixed, int n_cube, const double* cubes10, const int* cube_fixed,

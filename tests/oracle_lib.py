@@ -162,6 +162,11 @@ def ba_linearize(cams7, cam_fixed, cubes10, cube_fixed, E, n_threads=1):
     return out
 
 
+def ba_set_delta(delta=1e-9):
+    """step of the central differences (reference: 1e-9, base_binary_edge.hpp:147); test knob, see oracle_ba.cpp"""
+    lib().orc_ba_set_delta(C.c_double(delta))
+
+
 def ba_optimize(cams7, cam_fixed, cubes10, cube_fixed, E, iterations):
     cams7 = np.array(cams7, np.float64).reshape(-1, 7).copy(); cubes10 = np.array(cubes10, np.float64).reshape(-1, 10).copy()
     cam_fixed = np.ascontiguousarray(cam_fixed, np.int32); cube_fixed = np.ascontiguousarray(cube_fixed, np.int32)
