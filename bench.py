@@ -48,41 +48,6 @@ LSD_FRAMES, LSD_W, LSD_H = 256, 640, 480  # BASELINE config #3
 LSD_ALGO_BYTES_PER_FRAME = LSD_W * LSD_H + 16.0 * round(LSD_W * 0.8) * round(LSD_H * 0.8)
 
 
-EDLINES_CHILD = r'''
-import sys, os, json, time
-sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
-import numpy as np
-import cube_slam_wu_b200 as csb
-from cube_slam_wu_b200 import synth
-import oracle_lib as O
-base = synth.make_lsd_frames(32, %(w)d, %(h)d, seed=20260927)
-frames = np.ascontiguousarray(np.concatenate([base] * (%(n)d // 32)))
-ctx = csb.Context(0)
-ctx.edlines_detect_batch(frames)
-ms = []
-for _ in range(3):
-    lines, st = ctx.edlines_detect_batch(frames)
-    ms.append((st.gpu_ms_maps, st.gpu_ms_draw, st.gpu_ms_fit))
-ok = True
-for f in range(4):
-    ref, _ = O.edlines_detect(frames[f])
-    ok = ok and lines[f].shape == ref.shape and np.array_equal(lines[f].view(np.uint32), ref.view(np.uint32))
-t0 = time.perf_counter(); r = 0
-while time.perf_counter() - t0 < 1.0:
-    O.edlines_detect(frames[r %% 32]); r += 1
-cpu = r / (time.perf_counter() - t0)
-m = np.mean(np.array(ms), axis=0)
-print(json.dumps({"metric": "edlines_frames_per_sec", "value": %(n)d / (float(m.sum()) * 1e-3), "unit": "frames/s",
-                  "config": "%(n)d synthetic %(w)dx%(h)d frames, EDLines branch of detect_filter_lines (line_length_thres 15), resident kernels",
-                  "kernel_ms": {"maps (blur, Sobel, gradient map, anchors)": float(m[0]), "draw (smart routing)": float(m[1]), "fit (segments, validation, emit)": float(m[2])},
-                  "segments": int(st.n_lines), "chains": int(st.n_chains), "chain_px": int(st.n_chain_px), "frames_failed": int(st.n_frames_failed),
-                  "bit_identical_to_oracle_on_4_frames": bool(ok), "gpu_launches": int(st.n_kernel_launches),
-                  "cpu_baseline": {"value": cpu, "unit": "frames/s", "cores": 1, "kind": "port", "sample": "%%d frames, single thread" %% r},
-                  "note": "first hardware run of these kernels happens in this child process (DESIGN.md 3e)"}))
-ctx.close()
-'''
-
-
 def workload_config(n_gpus):
     return {"workload": "config#2 batched proposal scoring: %d KITTI-shape frames x %d boxes per GPU, roll/pitch sampling on, both configs"
                         % (FRAMES_PER_GPU, BOXES_PER_FRAME),
@@ -154,6 +119,41 @@ def build_batch(rank):
     return synth.make_kitti_batch(FRAMES_PER_GPU, boxes_per_frame=BOXES_PER_FRAME, seed=20260925 + rank)
 
 
+def divergence_from_literal_reference(batch, tasks, n_tasks, cub, ncub, n_threads):
+    """The product ranks with a SPECIFIED atan2 and without the reference's cam_pose state leak; the literal reference calls libm
+    atan2 and leaks.  How many of the step's boxes get a different best proposal from the literal variant (oracle, libm_atan2 = 1,
+    leak_cam_state = 1), and how far the cuboids of the other boxes are apart."""
+    import ctypes as C
+    import oracle_lib as O
+    inp = oracle_batch_inputs(batch)
+    L = O.lib()
+    P = O.default_params(leak_cam_state=1, libm_atan2=1)
+    n_box = len(batch["boxes"])
+    best = (O.Cuboid * n_box)()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    L.orc_detect_batch(inp["n_frames"], p(inp["K"]), p(inp["T"]), inp["img_w"], inp["img_h"], p(inp["boxes"]), p(inp["box_off"]), p(inp["lines"]),
+                       p(inp["line_off"]), p(inp["maps"]), p(inp["map_off"]), C.byref(P), int(n_threads), best, None)
+    first_task = {}
+    for i in range(n_tasks):
+        first_task.setdefault(tasks[i].frame_id, i)
+    n_diff, worst = 0, 0.0
+    for f, (b0, b1) in enumerate(batch["box_ranges"]):
+        for b in range(b0, b1):
+            oc, gc = best[b], cub[b]
+            if (oc.task_id < 0) != (ncub[b] < 1):
+                n_diff += 1
+            elif oc.task_id >= 0:
+                if gc.task_id - first_task[f] != oc.task_id or gc.raw_cube_ind != oc.raw_cube_ind:
+                    n_diff += 1
+                else:
+                    for name in ("pos", "scale"):
+                        worst = max(worst, float(np.abs(np.array(getattr(gc, name)) - np.array(getattr(oc, name))).max()))
+                    for name in ("rotY", "normalized_error", "edge_distance_error", "edge_angle_error"):
+                        worst = max(worst, abs(getattr(gc, name) - getattr(oc, name)))
+    return {"boxes": n_box, "boxes_with_a_different_top1_proposal": n_diff, "max_abs_diff_of_the_other_cuboids": worst,
+            "note": "GPU (specified atan2, no state leak) against the oracle in literal mode (libm atan2, cam_pose leak): near-ties of the 2/3 selection flip (DESIGN.md 2)"}
+
+
 def oracle_batch_inputs(batch):
     """Pack the batch for orc_detect_batch (oracle plan order, unpadded maps)."""
     import oracle_lib as O
@@ -214,19 +214,18 @@ def run_reference(args, rank, world):
 
 
 def pinned(a):
-    import torch
-    t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    return t, t.numpy()
+    from cube_slam_wu_b200 import pipeline
+    return pipeline.pinned(a)
 
 
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
     import cube_slam_wu_b200 as csb
-    from cube_slam_wu_b200 import synth
-    import helpers as H
+    from cube_slam_wu_b200 import pipeline, synth
 
     torch.cuda.set_device(local_rank)
+    numa_cpus = pipeline.bind_to_gpu_numa_node(local_rank)  # pinned staging buffers are first-touched on the GPU's NUMA node
     sampler = ClockSampler(local_rank)
     sampler.start()  # early: nvidia-smi start-up latency; rows are filtered to the under-load window later
     if world > 1:
@@ -236,7 +235,7 @@ def run_ours(args, rank, local_rank, world):
     params = csb.DetectParams.default()
 
     batch = build_batch(rank)
-    frames, boxes, lines, tasks, n_tasks, maps, n_map = H.gpu_inputs(csb, batch, params)
+    frames, boxes, lines, tasks, n_tasks, maps, n_map = pipeline.pack_inputs(csb, batch, params)
     keep = []
     tb, boxes = pinned(boxes); tl, lines = pinned(lines); tm, maps = pinned(maps)
     keep += [tb, tl, tm]
@@ -245,7 +244,6 @@ def run_ours(args, rank, local_rank, world):
     # ---- device-resident timing ("value")
     ctx.detect_upload(frames, boxes, lines, tasks, n_tasks, maps, n_map, params)
     obs = torch.zeros(n_boxes * 16, dtype=torch.float64, device="cuda")
-    obs_all = torch.zeros(world * n_boxes * 16, dtype=torch.float64, device="cuda") if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     L = csb.lib()
     import ctypes as C
@@ -254,8 +252,6 @@ def run_ours(args, rank, local_rank, world):
         ctx.detect_run(timed=timed)
         rc = L.csb_detect_observations_device(ctx._h, C.c_void_p(obs.data_ptr()))
         assert rc == 0
-        if world > 1:
-            dist.all_gather_into_tensor(obs_all, obs)
 
     # (1) throughput ("value"): VALUE_DEPTH contexts, each with its own stream and its own resident copy of the batch (D x 70 MB > L2, so
     #     consecutive steps never find their inputs in L2); step i runs on context i % D, so the latency-bound kernels of one step
@@ -266,17 +262,18 @@ def run_ours(args, rank, local_rank, world):
     ctxs = [ctx] + [csb.Context(local_rank, stream=s_.cuda_stream) for s_ in streams[1:]]
     for c_ in ctxs[1:]:
         c_.detect_upload(frames, boxes, lines, tasks, n_tasks, maps, n_map, params)
-    obs_d = [obs] + [torch.zeros_like(obs) for _ in range(D - 1)]
-    obs_all_d = [obs_all] + [torch.zeros_like(obs_all) if world > 1 else None for _ in range(D - 1)]
+    # observation records of all K timed steps live in ONE device buffer; the ranks exchange it with ONE all_gather after the last step
+    # (inside the timed region): the north star's "allgather only to assemble the global camera-object graph"
+    n_slots = max(args.steps, args.warmup, D)
+    obs_steps = torch.zeros(n_slots, n_boxes * 16, dtype=torch.float64, device="cuda")
+    obs_steps_all = torch.zeros(world, args.steps * n_boxes * 16, dtype=torch.float64, device="cuda") if world > 1 else None
 
     def step_d(i):
         k = i % D
         with torch.cuda.stream(streams[k]):
             ctxs[k].detect_run(timed=False)
-            rc = L.csb_detect_observations_device(ctxs[k]._h, C.c_void_p(obs_d[k].data_ptr()))
+            rc = L.csb_detect_observations_device(ctxs[k]._h, C.c_void_p(obs_steps[i % n_slots].data_ptr()))
             assert rc == 0
-            if world > 1:
-                dist.all_gather_into_tensor(obs_all_d[k], obs_d[k])
 
     sampler.mark_begin()
     for i in range(max(args.warmup, D)):
@@ -296,6 +293,9 @@ def run_ours(args, rank, local_rank, world):
         e_ = torch.cuda.Event()
         e_.record(s_)
         streams[0].wait_event(e_)
+    if world > 1:
+        with torch.cuda.stream(streams[0]):
+            dist.all_gather_into_tensor(obs_steps_all.view(-1), obs_steps[:args.steps].view(-1))
     ev_end.record(streams[0])
     torch.cuda.synchronize()
     if world > 1:
@@ -405,9 +405,39 @@ def run_ours(args, rank, local_rank, world):
             r["gpu_ms_distmap"] = float(stx.gpu_ms_distmap)
         return r
 
+    def h2d_only(gather):
+        """Upload of one step's inputs alone (tables + gray frames: ROI segments fetched by kernel, or whole frames by the copy engine), all
+        ranks at once, pipelined over the same contexts: the host->device ceiling of the e2e figure."""
+        for c in pipe_ctx:
+            c.set_option(csb.CSB_OPT_GRAY_GATHER, int(gather))
+        def run(n):
+            for i in range(n):
+                c = pipe_ctx[i % depth]
+                if i >= depth:
+                    c.synchronize()
+                c.detect_upload_gray(frames, boxes, lines, tasks, n_tasks, gray, params)
+            for c in pipe_ctx:
+                c.synchronize()
+        run(2 * depth)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        run(args.steps)
+        total, _ = reduce_time(time.perf_counter() - t0, 0)
+        for c in pipe_ctx:
+            c.set_option(csb.CSB_OPT_GRAY_GATHER, 1)
+        return 1e3 * total / args.steps
+
     # headline e2e: gray frames in, cuboids out -- what the reference's detect_cuboid(rgb_img, ...) covers (Canny + distance transform are
     # inside it, box_proposal_detail.cpp:320-327); the variant that takes caller-computed distance maps is kept next to it
     e2e = e2e_pipelined("gray")
+    try:
+        e2e["h2d_only_ms_per_step"] = {"roi_segments_by_kernel": h2d_only(True), "whole_frames_by_copy_engine": h2d_only(False),
+                                       "note": "upload alone, all ranks at once (max over ranks): the host->device ceiling of ms_per_step"}
+        e2e["host_cpus_bound_to"] = "%d CPUs local to the GPU (NVML)" % len(numa_cpus) if numa_cpus else "not bound"
+    except Exception as ex:
+        e2e["h2d_only_ms_per_step"] = {"error": str(ex)}
     e2e_extra = {}
     for name, fn, mode in (("pipelined_maps", e2e_pipelined, "maps"), ("single_call", e2e_single, "maps"), ("single_call_gray", e2e_single, "gray")):
         try:
@@ -417,6 +447,15 @@ def run_ours(args, rank, local_rank, world):
     del pipe_ctx
     sampler.mark_end()  # the sampled window covers the timed regions of value, serial and e2e (all under load)
     clocks = sampler.stop()
+
+    # ---- BASELINE config #5 at this N: 10k frames sharded over the ranks, ONE allgather of the observation records, graph build +
+    #      linearisation on rank 0 (cube_slam_wu_b200.pipeline.run_config5; every rank takes part)
+    try:
+        config5 = pipeline.run_config5(10000, E2E_DEPTH, ctx=ctx)
+    except Exception as ex:
+        config5 = {"error": str(ex)}
+    # the last timed step's cuboids (rank 0), for the literal-reference divergence count below
+    cub_last, ncub_last, _ = ctx.detect_batch(frames, boxes, lines, tasks, n_tasks, maps, n_map, params, want_stats=False) if rank == 0 else (None, None, None)
 
     out = None
     if rank == 0:
@@ -574,6 +613,7 @@ def run_ours(args, rank, local_rank, world):
                     pass
                 grad_bytes = 5.0 * LSD_W * LSD_H * LSD_FRAMES  # 1 B read + one 4-byte {dx, dy} record written per pixel
                 out["lsd"]["lbd"] = {"metric": "lbd_descriptors_per_sec", "value": bst.n_lines / ((gm + dm) * 1e-3), "unit": "descriptors/s",
+                                     "parity": "unpinned (GPU == oracle bit for bit; the oracle's descriptor values have no reference output to be held against, DESIGN.md 3d)",
                                      "config": "descriptors (32 bytes) of the %d segments of the same batch, read in place from the detector's device buffers; L2 flushed between runs" % bst.n_lines,
                                      "kernel_ms": {"grad (blur 5x5 + Sobel)": gm, "describe (prefix + descriptors)": dm},
                                      "samples": int(bst.n_samples), "gsamples_per_s": bst.n_samples / (dm * 1e-3) / 1e9,
@@ -588,15 +628,7 @@ def run_ours(args, rank, local_rank, world):
         except Exception as e:
             out.setdefault("lsd", {})["lbd"] = {"error": str(e)}
 
-        # ---- BASELINE config #5 (single-GPU share; tools/config5.py is the torchrun-able version): 10k frames through the gray-frame entry,
-        #      observation records collected on the device, host graph assembly, one linearisation of the 10k-camera graph
-        if world == 1:
-            try:
-                sys.path.insert(0, os.path.join(ROOT, "tools"))
-                import config5
-                out["config5"] = config5.run(10000, E2E_DEPTH, ctx=ctx)
-            except Exception as e:
-                out["config5"] = {"error": str(e)}
+        out["config5"] = config5
 
         # ---- CPU baseline: oracle port, one thread (the reference is single-threaded), bounded sample
         if world == 1:
@@ -610,6 +642,10 @@ def run_ours(args, rank, local_rank, world):
                     tot += dt; reps += 1
                 out["cpu_baseline"] = {"value": n * reps / tot, "unit": UNIT, "cores": 1, "kind": "port",
                                        "sample": "%d repeats of the full step (%d frames x %d boxes), single thread like the reference" % (reps, FRAMES_PER_GPU, BOXES_PER_FRAME)}
+                try:
+                    out["parity_vs_literal_reference"] = divergence_from_literal_reference(batch, tasks, n_tasks, cub_last, ncub_last, os.cpu_count() or 1)
+                except Exception as e:
+                    out["parity_vs_literal_reference"] = {"error": str(e)}
                 if "ba" in out and "value" in out["ba"]:
                     E = O.ba_edges(ec=g["ec"], ep=g["ep"], eo=g["eo"])
                     t0 = time.perf_counter(); r = 0
@@ -637,17 +673,32 @@ def run_ours(args, rank, local_rank, world):
                                                              "sample": "%d frames (blur + Sobel + descriptors of their segments), single thread" % r}
             except Exception as e:
                 out["cpu_baseline"] = {"error": str(e)}
-        # ---- EDLines (use_LSD = false): its kernels had not run on hardware when round 1 ended, so this section runs them in a
-        #      CHILD process (own CUDA context, time limit) and checks four frames against the oracle there; whatever happens, the line prints
-        if world == 1:
+        # ---- EDLines (use_LSD = false, what object_slam selects): the same 256-frame batch through csb_edlines_*
+        if world == 1 and lsd_frames is not None:
             try:
-                code = EDLINES_CHILD % {"root": ROOT, "n": LSD_FRAMES, "w": LSD_W, "h": LSD_H}
-                r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=180)
-                last = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
-                if r.returncode == 0 and last:
-                    out["lsd"]["edlines"] = json.loads(last[-1])
-                else:
-                    out["lsd"]["edlines"] = {"error": (r.stdout + r.stderr)[-600:]}
+                import oracle_lib as O
+                ctx.edlines_detect_batch(lsd_frames)
+                ms = []
+                for _ in range(3):
+                    flush.zero_()
+                    ed_lines, est = ctx.edlines_detect_batch(lsd_frames)
+                    ms.append((est.gpu_ms_maps, est.gpu_ms_draw, est.gpu_ms_fit))
+                ok = True
+                for f in range(4):
+                    ref, _ = O.edlines_detect(lsd_frames[f])
+                    ok = ok and ed_lines[f].shape == ref.shape and np.array_equal(ed_lines[f].view(np.uint32), ref.view(np.uint32))
+                t0 = time.perf_counter(); r = 0
+                while time.perf_counter() - t0 < 1.0:
+                    O.edlines_detect(lsd_frames[r % 32]); r += 1
+                cpu = r / (time.perf_counter() - t0)
+                m = np.mean(np.array(ms), axis=0)
+                out.setdefault("lsd", {})["edlines"] = {
+                    "metric": "edlines_frames_per_sec", "value": LSD_FRAMES / (float(m.sum()) * 1e-3), "unit": "frames/s",
+                    "config": "%d synthetic %dx%d frames, EDLines branch of detect_filter_lines (line_length_thres 15), resident kernels" % (LSD_FRAMES, LSD_W, LSD_H),
+                    "kernel_ms": {"maps (blur, Sobel, gradient map, anchors)": float(m[0]), "draw (smart routing)": float(m[1]), "fit (segments, validation, emit)": float(m[2])},
+                    "segments": int(est.n_lines), "chains": int(est.n_chains), "chain_px": int(est.n_chain_px), "frames_failed": int(est.n_frames_failed),
+                    "bit_identical_to_oracle_on_4_frames": bool(ok), "gpu_launches": int(est.n_kernel_launches),
+                    "cpu_baseline": {"value": cpu, "unit": "frames/s", "cores": 1, "kind": "port", "sample": "%d frames, single thread" % r}}
             except Exception as e:
                 out.setdefault("lsd", {})["edlines"] = {"error": str(e)}
         print(json.dumps(out), flush=True)  # flush: under torchrun stdout is a block-buffered pipe/file

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_PKG, "libcubeslam_b200.so")
 _LIB = None
 
 CSB_OK, CSB_ERR_INVALID, CSB_ERR_CUDA, CSB_ERR_CAPACITY, CSB_ERR_STATE = 0, -1, -2, -3, -4
+CSB_OPT_GRAY_GATHER = 1
 
 
 class CsbError(RuntimeError):
@@ -179,6 +180,10 @@ class Context:
     def set_blur_generation(self, generation):
         """csb_set_blur_generation(): 4 (default) = OpenCV 4.x taps of the 8-bit 5x5 Gaussian in front of LBD / EDLines, 3 = OpenCV <= 3.4.0's."""
         self._chk(lib().csb_set_blur_generation(self._h, int(generation)))
+
+    def set_option(self, option, value):
+        """csb_set_option(): CSB_OPT_GRAY_GATHER (1) = fetch only the ROI segments of pinned gray frames (default on)."""
+        self._chk(lib().csb_set_option(self._h, int(option), int(value)))
 
     def synchronize(self):
         self._chk(lib().csb_synchronize(self._h))

@@ -58,7 +58,7 @@ void csb_destroy(csb_context* c) {
     DetectState& d = c->det;
     DevBuf* bufs[] = {&d.d_tables, &d.d_results, &d.d_maps, &d.d_ml_seg, &d.d_ml_ang, &d.d_ml_mid, &d.d_n_merged, &d.d_vp_sup,
                       &d.d_p_dist, &d.d_p_angle, &d.d_p_hyp, &d.d_keep, &d.d_norm, &d.d_cand_score, &d.d_cand_ok,
-                      &d.d_sel_idx, &d.d_sel_flag, &d.d_sel_heap, &d.d_rank_idx, &d.d_counters, &d.d_dbg, &d.d_gray, &d.d_cmap, &d.d_queue, &d.d_dtmp, &d.d_flags};
+                      &d.d_sel_idx, &d.d_sel_flag, &d.d_sel_heap, &d.d_rank_idx, &d.d_counters, &d.d_dbg, &d.d_gray, &d.d_cmap, &d.d_queue, &d.d_dtmp, &d.d_flags, &d.d_segbits};
     for (DevBuf* b : bufs) b->release();
     d.h_tables.release(); d.h_results.release();
     if (d.ev_tables) cudaEventDestroy(d.ev_tables);
@@ -89,6 +89,13 @@ int csb_set_blur_generation(csb_context* c, int generation) {
     if (!c || (generation != 3 && generation != 4)) return CSB_ERR_INVALID;
     c->blur_generation = generation;
     return CSB_OK;
+}
+
+int csb_set_option(csb_context* c, int option, int value) {
+    if (!c) return CSB_ERR_INVALID;
+    if (option == CSB_OPT_GRAY_GATHER) { c->det.gray_gather_enabled = value != 0; return CSB_OK; }
+    c->err = "csb_set_option: unknown option";
+    return CSB_ERR_INVALID;
 }
 
 int csb_synchronize(csb_context* c) {
@@ -148,7 +155,16 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
         // gray frames are packed back to back (img_height x img_width bytes each)
         if (n_gray_bytes != gray_total) { c->err = "csb_detect_upload_gray: n_gray_bytes != sum of img_width*img_height"; return CSB_ERR_INVALID; }
         CSB_CUDA(c, d.d_gray.ensure((size_t)gray_total + 64));
-        if (gray_total) CSB_CUDA(c, cudaMemcpyAsync(d.d_gray.p, gray, (size_t)gray_total, cudaMemcpyHostToDevice, st));
+        // Pinned (device-mapped) caller memory: the frames are not copied as a whole -- once the task table is on the device, a kernel
+        // fetches the 512-byte segments the ROIs touch straight from the caller's buffer (launch_gray_gather below).  Pageable memory
+        // goes through the copy engine as one block.
+        d.gray_mapped = nullptr;
+        if (gray_total && d.gray_gather_enabled && ((uintptr_t)gray & 15) == 0) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, gray) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) d.gray_mapped = (const uint8_t*)at.devicePointer;
+            else cudaGetLastError();
+        }
+        if (gray_total && !d.gray_mapped) CSB_CUDA(c, cudaMemcpyAsync(d.d_gray.p, gray, (size_t)gray_total, cudaMemcpyHostToDevice, st));
     } else if (n_map_floats > 0) {
         CSB_CUDA(c, d.d_maps.ensure(4 * (size_t)n_map_floats + 64));
         if (stream_maps && n_map_floats >= (1 << 18) && copy_engine_is_concurrent()) {
@@ -268,7 +284,8 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
     d.res_off_ncub = align256(sizeof(csb_cuboid) * NB * kmax);
     d.res_off_nvalid = align256(d.res_off_ncub + 4 * NB);
     d.res_off_nkeep = align256(d.res_off_nvalid + 4 * NT);
-    d.res_bytes = align256(d.res_off_nkeep + 4 * NT);
+    d.res_off_misc = align256(d.res_off_nkeep + 4 * NT);  // [0]: 512-byte segments fetched by the gray gather
+    d.res_bytes = align256(d.res_off_misc + 64);
     CSB_CUDA(c, d.d_results.ensure(d.res_bytes));
     CSB_CUDA(c, d.h_results.ensure(d.res_bytes));
     if (d.gray_mode || n_map_floats <= 0) CSB_CUDA(c, d.d_maps.ensure(4 * (size_t)nm + 64));
@@ -294,7 +311,7 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
         CSB_CUDA(c, d.d_queue.ensure(4 * (size_t)nm + 64));
         CSB_CUDA(c, d.d_dtmp.ensure(4 * (size_t)nm + 64));
     }
-    d.h2d_bytes = (int64_t)(tab_bytes + (d.gray_mode ? (size_t)gray_total : 4 * (size_t)nm) + (streaming ? 4 * (size_t)n_chunks : 0));
+    d.h2d_bytes = (int64_t)(tab_bytes + (d.gray_mode ? (d.gray_mapped ? (size_t)0 : (size_t)gray_total) : 4 * (size_t)nm) + (streaming ? 4 * (size_t)n_chunks : 0));
 
     DetectBuffers& B = d.B;
     char* db = d.d_tables.as<char>();
@@ -317,6 +334,16 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
     B.dc.max_cuboid_num = kmax; B.dc.whether_sample_cam_roll_pitch = params->whether_sample_cam_roll_pitch;
     B.dc.nominal_skew_ratio = params->nominal_skew_ratio; B.dc.max_cut_skew = params->max_cut_skew;
     for (int f = 0; f < n_frames; f++) d.ftab[f] = h_ftab[f];  // host copy for the debug entries (h_tables is reused by the next upload)
+    if (d.gray_mode) {
+        int* misc = reinterpret_cast<int*>(dr + d.res_off_misc);
+        CSB_CUDA(c, cudaMemsetAsync(misc, 0, 64, st));
+        if (d.gray_mapped) {
+            const long long whole = gray_total & ~(long long)15;  // the last (partial) 16-byte chunk goes by a plain copy: nothing is read past the caller's buffer
+            CSB_CUDA(c, d.d_segbits.ensure(4 * (size_t)((gray_total / 512 + 64) / 32 + 2)));
+            CSB_CUDA(c, launch_gray_gather(B, d.gray_mapped, d.d_gray.as<uint8_t>(), whole, d.d_segbits.as<unsigned>(), misc, st));
+            if (gray_total > whole) CSB_CUDA(c, cudaMemcpyAsync(d.d_gray.as<uint8_t>() + whole, gray + whole, (size_t)(gray_total - whole), cudaMemcpyHostToDevice, st));
+        }
+    }
     d.uploaded = true;
     return CSB_OK;
 }
@@ -395,7 +422,8 @@ int csb_detect_download(csb_context* c, csb_cuboid* cuboids_out, int32_t* n_cubo
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
         for (int t = 0; t < d.n_tasks; t++) { stats->n_enumerated += d.ttab[t].n_enum; stats->n_scored += nv[t]; stats->n_kept += nk[t]; }
-        stats->h2d_bytes = d.h2d_bytes; stats->d2h_bytes = d2h;
+        stats->h2d_bytes = d.h2d_bytes + (d.gray_mode ? 512 * (int64_t)reinterpret_cast<const int*>(hr + d.res_off_misc)[0] : 0);
+        stats->d2h_bytes = d2h;
         stats->n_kernel_launches = d.launches_last;
         for (const TaskTab& t : d.ttab) stats->n_tasks_smem_map += (t.roi_w * t.roi_h <= d.map_cap_floats) ? 1 : 0;
         if (d.timed_last) {

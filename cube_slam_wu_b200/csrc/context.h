@@ -70,9 +70,11 @@ struct DetectState {
     // d_tables: frame/task/order/box/line tables, one H2D copy from h_tables.  d_results: cuboids | n_cuboids | n_valid | n_keep, one D2H
     // copy into h_results.
     DevBuf d_tables, d_results, d_maps, d_ml_seg, d_ml_ang, d_ml_mid, d_n_merged, d_vp_sup, d_p_dist, d_p_angle, d_p_hyp, d_keep, d_norm, d_cand_score, d_cand_ok,
-        d_sel_idx, d_sel_flag, d_sel_heap, d_rank_idx, d_counters, d_dbg, d_gray, d_cmap, d_queue, d_dtmp, d_flags;
+        d_sel_idx, d_sel_flag, d_sel_heap, d_rank_idx, d_counters, d_dbg, d_gray, d_cmap, d_queue, d_dtmp, d_flags, d_segbits;
     HostBuf h_tables, h_results;
-    size_t res_off_ncub = 0, res_off_nvalid = 0, res_off_nkeep = 0, res_bytes = 0;
+    size_t res_off_ncub = 0, res_off_nvalid = 0, res_off_nkeep = 0, res_off_misc = 0, res_bytes = 0;
+    const uint8_t* gray_mapped = nullptr;  // device alias of the caller's pinned gray buffer (csb_detect_upload_gray), or NULL: copied as a whole
+    bool gray_gather_enabled = true;       // csb_set_option(CSB_OPT_GRAY_GATHER)
     cudaEvent_t ev_tables = nullptr;  // h_tables consumed by the device
     cudaEvent_t ev_order = nullptr;   // compute stream -> copy stream ordering of the streamed map upload
     bool gray_mode = false;

@@ -86,14 +86,18 @@ def globalise_records(rec, frames_per_step, boxes_per_rank):
     return rec.reshape(-1, 16), world * boxes_per_rank
 
 
-def assemble_graph(records, cams_wc7, n_landmarks):
+def assemble_graph(records, cams_wc7, n_landmarks, cams_est_wc7=None):
     """records: (n, 16) observation records whose column 0 already holds the GLOBAL frame index (row of cams_wc7) and whose column 1
-    holds the landmark index (taken modulo n_landmarks).  cams_wc7: (n_frames, 7) camera-to-world poses.  Returns the dict of arrays
-    Context.ba_set_graph / ba_linearize take, plus 'landmark_seen'."""
+    holds the landmark index (taken modulo n_landmarks).  cams_wc7: (n_frames, 7) camera-to-world poses: they give the odometry
+    measurements.  cams_est_wc7 (default: the same poses): the camera ESTIMATES the vertices start from and the landmarks are initialised
+    with (the node uses its current estimate there, main_obj.cpp:745-751).  Returns the dict of arrays Context.ba_set_graph / ba_linearize
+    take, plus 'landmark_seen'."""
     records = np.asarray(records, np.float64).reshape(-1, 16)
-    cams_wc7 = np.asarray(cams_wc7, np.float64).reshape(-1, 7)
+    cams_true = np.asarray(cams_wc7, np.float64).reshape(-1, 7)
+    cams_wc7 = cams_true if cams_est_wc7 is None else np.asarray(cams_est_wc7, np.float64).reshape(-1, 7)
     n_frames = len(cams_wc7)
     cams_cw = se3_inv(cams_wc7)                    # g2o vertices store world -> camera (main_obj.cpp:760)
+    true_cw = se3_inv(cams_true)
     valid = (records[:, 2] == 1) & (records[:, 0] >= 0) & (records[:, 0] < n_frames)
     rec = records[valid]
     order = np.lexsort((rec[:, 1], rec[:, 0]))     # frame after frame, box after box: the order the node adds its edges in
@@ -117,7 +121,7 @@ def assemble_graph(records, cams_wc7, n_landmarks):
     ec = (frame.astype(np.int32), lm.astype(np.int32), np.ascontiguousarray(meas), info)
     if n_frames > 1:
         i0 = np.arange(n_frames - 1, dtype=np.int32)
-        odo = se3_mul(cams_cw[1:], se3_inv(cams_cw[:-1]))     # e = log(M T_i T_j^-1) = 0 for M = T_j T_i^-1 (types_six_dof_expmap.h:90-99)
+        odo = se3_mul(true_cw[1:], se3_inv(true_cw[:-1]))     # e = log(M T_i T_j^-1) = 0 for M = T_j T_i^-1 (types_six_dof_expmap.h:90-99)
         eo = (i0, i0 + 1, np.ascontiguousarray(odo), np.tile(np.eye(6).ravel(), (n_frames - 1, 1)))
     else:
         eo = None

@@ -24,8 +24,9 @@ def euler_zyx_to_rot(roll, pitch, yaw):
 
 
 def make_kitti_batch(n_frames, boxes_per_frame=8, seed=20260925, lines_per_box=30, bg_lines=40, img_w=KITTI_W, img_h=KITTI_H,
-                     box_w=(60, 320), box_h=(50, 200)):
-    """Returns dict(K (F,3,3), T (F,4,4), boxes (F*B,5), lines (M,4), box_ranges, line_ranges, images list of u8 gray)."""
+                     box_w=(60, 320), box_h=(50, 200), poses_only=False):
+    """Returns dict(K (F,3,3), T (F,4,4), boxes (F*B,5), lines (M,4), box_ranges, line_ranges, images list of u8 gray).
+    poses_only: skip the rendering (images = None); K / T / boxes / lines are the same as in the full batch."""
     import cv2
     rng = np.random.default_rng(seed)
     Ks, Ts, boxes, lines, box_ranges, line_ranges, images = [], [], [], [], [], [], []
@@ -73,15 +74,16 @@ def make_kitti_batch(n_frames, boxes_per_frame=8, seed=20260925, lines_per_box=3
             if p[2] < p[0]:
                 p = [p[2], p[3], p[0], p[1]]
             lines.append(p)
-        for p in lines[l0:]:
-            cv2.line(img, (int(round(p[0])), int(round(p[1]))), (int(round(p[2])), int(round(p[3]))), 255, 1)
-        salt = rng.random((img_h, img_w)) < 0.005
-        img[salt] = 255
-        images.append(img)
+        salt = rng.random((img_h, img_w)) < 0.005   # drawn in every mode: the random stream must not depend on poses_only
+        if not poses_only:
+            for p in lines[l0:]:
+                cv2.line(img, (int(round(p[0])), int(round(p[1]))), (int(round(p[2])), int(round(p[3]))), 255, 1)
+            img[salt] = 255
+            images.append(img)
         Ks.append(KITTI_K.copy()); Ts.append(T)
         box_ranges.append((b0, len(boxes))); line_ranges.append((l0, len(lines)))
     return dict(K=np.array(Ks), T=np.array(Ts), boxes=np.array(boxes, np.float64).reshape(-1, 5), lines=np.array(lines, np.float64).reshape(-1, 4),
-                box_ranges=box_ranges, line_ranges=line_ranges, images=images, img_w=img_w, img_h=img_h)
+                box_ranges=box_ranges, line_ranges=line_ranges, images=None if poses_only else images, img_w=img_w, img_h=img_h)
 
 
 def dist_map_for_roi(gray, left, top, width, height):

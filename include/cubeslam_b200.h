@@ -4,9 +4,10 @@
  *
  *  (1) proposal half -- everything inside detect_3d_cuboid::detect_cuboid()
  *      (reference: detect_3d_cuboid/include/detect_3d_cuboid/detect_3d_cuboid.h:74-118,
- *       detect_3d_cuboid/src/box_proposal_detail.cpp:65-861) except cv::Canny + cv::distanceTransform
- *      (box_proposal_detail.cpp:320-327), which stay with the caller: csb_detect_plan() tells the caller
- *      which ROIs need a distance map, csb_detect_batch() consumes them.
+ *       detect_3d_cuboid/src/box_proposal_detail.cpp:65-861).  cv::Canny + cv::distanceTransform
+ *      (box_proposal_detail.cpp:320-327) run on the GPU when the caller hands over the gray frames
+ *      (csb_detect_batch_gray / csb_detect_upload_gray); a caller that computes the distance maps itself
+ *      asks csb_detect_plan() which ROIs need one and passes them to csb_detect_batch().
  *
  *  (2) BA half -- what g2o's BlockSolver::buildSystem() does for the cuboid graph
  *      (reference: object_slam/Thirdparty/g2o/g2o/core/block_solver.hpp:501-560 calling
@@ -42,6 +43,13 @@ const char* csb_last_error(const csb_context* ctx);
 int csb_set_stream(csb_context* ctx, void* cuda_stream);
 int csb_synchronize(csb_context* ctx);
 const char* csb_version(void);
+/* Tuning switches (defaults in brackets).
+ *   CSB_OPT_GRAY_GATHER [1]: csb_detect_upload_gray / csb_detect_batch_gray with a PINNED, 16-byte aligned gray buffer (cudaHostAlloc /
+ *   cudaHostRegister) fetch only the 512-byte segments of the frames that the box ROIs (+ the one-pixel Sobel halo) touch, by a kernel
+ *   reading the caller's buffer over PCIe, instead of copying whole frames with the copy engine; 0 = always copy whole frames.  Results
+ *   are identical either way; pageable buffers are always copied as a whole. */
+#define CSB_OPT_GRAY_GATHER 1
+int csb_set_option(csb_context* ctx, int option, int value);
 
 /* ------------------------------------------------------------------------------------------------
  * Proposal half

@@ -70,3 +70,33 @@ def test_blank_and_single_edge_rois(ctx, csb):
     step = np.full((Hh, W), 20, np.uint8); step[:, W // 2:] = 220
     batch["images"] = [blank, step]
     _run_gray(ctx, csb, batch, csb.DetectParams.default(whether_sample_bbox_height=1))
+
+
+def test_pinned_frames_are_fetched_by_roi_segments(ctx, csb):
+    """csb_detect_upload_gray with a PINNED gray buffer (CSB_OPT_GRAY_GATHER, default on): a kernel fetches only the 512-byte segments the
+    ROIs (+ Sobel halo) touch from the caller's memory.  Same maps, same cuboids as the whole-frame copy; fewer bytes over PCIe."""
+    import torch
+    from cube_slam_wu_b200 import synth
+    batch = synth.make_kitti_batch(5, boxes_per_frame=3, seed=91)
+    p = csb.DetectParams.default()
+    frames = csb.make_frames(batch["K"], batch["T"], batch["img_w"], batch["img_h"], batch["box_ranges"], batch["line_ranges"])
+    boxes = np.ascontiguousarray(batch["boxes"], np.float64).reshape(-1, 5)
+    lines = np.ascontiguousarray(batch["lines"], np.float64).reshape(-1, 4)
+    tasks, n_tasks, n_map = csb.detect_plan(frames, boxes, p)
+    g = _gray(batch)
+    # poison the device frame buffer first: whatever the gather does not fetch must not matter
+    ctx.detect_batch_gray(frames, boxes, lines, tasks, n_tasks, np.full_like(g, 255), p)
+    tg = torch.from_numpy(g).pin_memory()
+    cub1, ncub1, st1 = ctx.detect_batch_gray(frames, boxes, lines, tasks, n_tasks, tg.numpy(), p)
+    for i in range(n_tasks):
+        t = tasks[i]
+        dm, ed = ctx.debug_map(i, t, edges=True)
+        ref_dm, ref_ed = synth.dist_map_for_roi_reference(batch["images"][t.frame_id], t.roi_left, t.roi_top, t.roi_width, t.roi_height, return_edges=True)
+        assert np.array_equal((ed == 2), ref_ed > 0) and np.array_equal(dm, ref_dm), "task %d" % i
+    ctx.set_option(csb.CSB_OPT_GRAY_GATHER, 0)
+    try:
+        cub0, ncub0, st0 = ctx.detect_batch_gray(frames, boxes, lines, tasks, n_tasks, tg.numpy(), p)
+    finally:
+        ctx.set_option(csb.CSB_OPT_GRAY_GATHER, 1)
+    assert np.array_equal(ncub0, ncub1) and bytes(cub0) == bytes(cub1)
+    assert st0.h2d_bytes - st1.h2d_bytes > 0.3 * g.size and st1.h2d_bytes > 0.1 * g.size, (st0.h2d_bytes, st1.h2d_bytes, g.size)

@@ -18,10 +18,8 @@ def _free_port():
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    import bench
     import helpers as H
     from cube_slam_wu_b200 import synth
-    bench.FRAMES_PER_GPU = 2
     batch = synth.make_kitti_batch(2, boxes_per_frame=3, seed=20260925 + rank)
     P = type("P", (), dict(consider_config_1=1, consider_config_2=1, whether_sample_cam_roll_pitch=1, whether_sample_bbox_height=0, max_cuboid_num=1,
                            nominal_skew_ratio=1.0, max_cut_skew=3.0))
@@ -120,7 +118,13 @@ def _worker_config5(rank, world, port, q):
         g = graph.assemble_graph(flat, cams_wc, n_lm)
         E = O.ba_edges(ec=g["ec"], ep=None, eo=g["eo"])
         lin = O.ba_linearize(g["cams7"], g["cam_fixed"], g["cubes10"], g["cube_fixed"], E)
-        out = dict(n_cam=len(g["cams7"]), n_lm=n_lm, seen=int(g["landmark_seen"].sum()), n_ec=len(g["ec"][0]), n_eo=len(g["eo"][0]),
+        # the same with perturbed camera ESTIMATES (what pipeline.run_config5 builds): the re-observations disagree
+        from cube_slam_wu_b200 import pipeline
+        g2 = graph.assemble_graph(flat, cams_wc, n_lm, cams_est_wc7=pipeline.perturb_poses(cams_wc, 0.02, 0.005, 7))
+        lin2 = O.ba_linearize(g2["cams7"], g2["cam_fixed"], g2["cubes10"], g2["cube_fixed"], O.ba_edges(ec=g2["ec"], ep=None, eo=g2["eo"]))
+        out = dict(chi2_noisy=float(lin2["chi2"]), b_noisy=float(np.abs(lin2["b_cam"]).max()), cam0_same=bool(np.array_equal(g2["cams7"][0], g["cams7"][0])),
+                   odo_same=bool(np.array_equal(g2["eo"][2], g["eo"][2])),
+                   n_cam=len(g["cams7"]), n_lm=n_lm, seen=int(g["landmark_seen"].sum()), n_ec=len(g["ec"][0]), n_eo=len(g["eo"][0]),
                    valid=int((rec[..., 2] == 1).sum()), ec_cam=g["ec"][0], ec_cube=g["ec"][1], max_err=float(np.abs(lin["ec_err"]).max()),
                    max_odo=float(np.abs(lin["eo_err"]).max()), frames=flat[:, 0].copy(), valid_mask=flat[:, 2].copy(), n_boxes=n_boxes)
         np.save(os.environ["CSB_TEST_OUT"], np.array([out], dtype=object), allow_pickle=True)
@@ -144,3 +148,5 @@ def test_two_rank_config5_graph_assembly(tmp_path):
     assert r1.any() and (d["ec_cube"][r1] >= d["n_boxes"]).all() and (d["ec_cube"][~r1] < d["n_boxes"]).all()
     # consistent measurements: landmarks initialised from their first observation and re-observed from the same pose
     assert d["max_err"] < 1e-9 and d["max_odo"] < 1e-9
+    # perturbed estimates: first camera exact (fixed vertex), odometry measurements from the true poses, chi2 and the right-hand side not zero
+    assert d["cam0_same"] and d["odo_same"] and d["chi2_noisy"] > 1e-3 and d["b_noisy"] > 1e-3
