@@ -284,7 +284,7 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
     d.res_off_ncub = align256(sizeof(csb_cuboid) * NB * kmax);
     d.res_off_nvalid = align256(d.res_off_ncub + 4 * NB);
     d.res_off_nkeep = align256(d.res_off_nvalid + 4 * NT);
-    d.res_off_misc = align256(d.res_off_nkeep + 4 * NT);  // [0]: 512-byte segments fetched by the gray gather
+    d.res_off_misc = align256(d.res_off_nkeep + 4 * NT);  // [0]: 128-byte segments fetched by the gray gather
     d.res_bytes = align256(d.res_off_misc + 64);
     CSB_CUDA(c, d.d_results.ensure(d.res_bytes));
     CSB_CUDA(c, d.h_results.ensure(d.res_bytes));
@@ -293,7 +293,7 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
     CSB_CUDA(c, d.d_ml_ang.ensure(8 * LT));
     CSB_CUDA(c, d.d_ml_mid.ensure(16 * LT));
     CSB_CUDA(c, d.d_n_merged.ensure(4 * NT));
-    CSB_CUDA(c, d.d_vp_sup.ensure(48 * NT * (size_t)std::max(d.max_groups, 1)));
+    CSB_CUDA(c, d.d_vp_sup.ensure(96 * NT * (size_t)std::max(d.max_groups, 1)));
     CSB_CUDA(c, d.d_p_dist.ensure(8 * OT));
     CSB_CUDA(c, d.d_p_angle.ensure(8 * OT));
     CSB_CUDA(c, d.d_p_hyp.ensure(4 * OT));
@@ -320,7 +320,7 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
     B.task_order = reinterpret_cast<const int*>(db + off_order); B.box_task_begin = reinterpret_cast<const int*>(db + off_box);
     B.lines = reinterpret_cast<const double*>(db + off_lines); B.maps = d.d_maps.as<float>(); B.n_tasks = n_tasks; B.pad = 0;
     B.ml_seg = d.d_ml_seg.as<double>(); B.ml_ang = d.d_ml_ang.as<double>(); B.ml_mid = d.d_ml_mid.as<double>(); B.n_merged = d.d_n_merged.as<int>();
-    B.vp_sup = d.d_vp_sup.as<double>(); B.sup_stride = 6 * (long long)std::max(d.max_groups, 1);
+    B.vp_sup = d.d_vp_sup.as<double>(); B.sup_stride = 12 * (long long)std::max(d.max_groups, 1);
     B.p_dist = d.d_p_dist.as<double>(); B.p_angle = d.d_p_angle.as<double>(); B.p_hyp = d.d_p_hyp.as<int>();
     B.n_valid = reinterpret_cast<int*>(dr + d.res_off_nvalid);
     B.keep = d.d_keep.as<int>(); B.norm_score = d.d_norm.as<double>(); B.n_keep = reinterpret_cast<int*>(dr + d.res_off_nkeep);
@@ -339,8 +339,8 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
         CSB_CUDA(c, cudaMemsetAsync(misc, 0, 64, st));
         if (d.gray_mapped) {
             const long long whole = gray_total & ~(long long)15;  // the last (partial) 16-byte chunk goes by a plain copy: nothing is read past the caller's buffer
-            CSB_CUDA(c, d.d_segbits.ensure(4 * (size_t)((gray_total / 512 + 64) / 32 + 2)));
-            CSB_CUDA(c, launch_gray_gather(B, d.gray_mapped, d.d_gray.as<uint8_t>(), whole, d.d_segbits.as<unsigned>(), misc, st));
+            CSB_CUDA(c, d.d_segbits.ensure(4 * (size_t)((gray_total / 128 + 64) / 32 + 2)));
+            CSB_CUDA(c, launch_gray_gather(B, d.gray_mapped, d.d_gray.as<uint8_t>(), whole, d.d_segbits.as<unsigned>(), misc, c->num_sms, st));
             if (gray_total > whole) CSB_CUDA(c, cudaMemcpyAsync(d.d_gray.as<uint8_t>() + whole, gray + whole, (size_t)(gray_total - whole), cudaMemcpyHostToDevice, st));
         }
     }
@@ -422,7 +422,7 @@ int csb_detect_download(csb_context* c, csb_cuboid* cuboids_out, int32_t* n_cubo
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
         for (int t = 0; t < d.n_tasks; t++) { stats->n_enumerated += d.ttab[t].n_enum; stats->n_scored += nv[t]; stats->n_kept += nk[t]; }
-        stats->h2d_bytes = d.h2d_bytes + (d.gray_mode ? 512 * (int64_t)reinterpret_cast<const int*>(hr + d.res_off_misc)[0] : 0);
+        stats->h2d_bytes = d.h2d_bytes + (d.gray_mode ? 128 * (int64_t)reinterpret_cast<const int*>(hr + d.res_off_misc)[0] : 0);
         stats->d2h_bytes = d2h;
         stats->n_kernel_launches = d.launches_last;
         for (const TaskTab& t : d.ttab) stats->n_tasks_smem_map += (t.roi_w * t.roi_h <= d.map_cap_floats) ? 1 : 0;

@@ -373,13 +373,15 @@ __global__ void __launch_bounds__(DT_THREADS) k_dist3x3(DetectBuffers B, const u
 }
 
 // ---- gray-frame upload without the copy engine: only what the ROIs read -----------------------------------------------------------
-// The packed gray frames of a batch are one linear byte array, cut into 512-byte segments (one warp x 16 bytes).  k_gray_mark sets
+// The packed gray frames of a batch are one linear byte array, cut into 128-byte segments (8 lanes x 16 bytes).  k_gray_mark sets
 // the bit of every segment that holds a pixel of some task's ROI or of its one-pixel Sobel halo (clamped to the image); k_gray_gather
 // copies the marked segments from the caller's pinned (device-mapped) buffer into the device frame buffer -- SM-initiated PCIe reads
-// run at the copy engine's rate (measured: 50 GB/s against 55), so the upload shrinks with the share of the frames the boxes cover
-// (config #2: 8 boxes cover about 45 % of a 1242x375 frame).  Everything outside the marked segments is never read by k_canny
-// in a way that reaches a result (magnitudes outside the ROI count as 0).
-constexpr int GSEG = 512;
+// run at the copy engine's rate (measured: 50 GB/s against 55), so the upload shrinks with the share of the frames the boxes cover.
+// Everything outside the marked segments is never read by k_canny in a way that reaches a result (magnitudes outside the ROI count as 0).
+// The gather is a persistent kernel of small CTAs (64 threads, <= 32 registers, no shared memory) so that it finds room next to the
+// one-CTA-per-SM scoring kernel of another context and the transfer overlaps compute the way a copy-engine transfer would.
+constexpr int GSEG = 128;
+constexpr int GG_THREADS = 64;
 
 __global__ void __launch_bounds__(128) k_gray_mark(DetectBuffers B, unsigned* seg_bits) {
     const int task = blockIdx.x;
@@ -389,50 +391,57 @@ __global__ void __launch_bounds__(128) k_gray_mark(DetectBuffers B, unsigned* se
     const int y0 = max(t.roi_top - 1, 0), y1 = min(t.roi_top + t.roi_h, IH - 1);      // inclusive
     const int x0 = max(t.roi_left - 1, 0), x1 = min(t.roi_left + t.roi_w, IW - 1);
     for (int y = y0 + threadIdx.x; y <= y1; y += blockDim.x) {
-        const long long a = ft.gray_offset + (long long)y * IW + x0, b = ft.gray_offset + (long long)y * IW + x1;
-        for (long long sgm = a / GSEG; sgm <= b / GSEG; sgm++) atomicOr(seg_bits + (sgm >> 5), 1u << (sgm & 31));
+        const long long a = (ft.gray_offset + (long long)y * IW + x0) / GSEG, b = (ft.gray_offset + (long long)y * IW + x1) / GSEG;
+        // consecutive segments of one row: set whole runs of bits per bitmap word
+        for (long long w = a >> 5; w <= (b >> 5); w++) {
+            const int lo = (w == (a >> 5)) ? (int)(a & 31) : 0, hi = (w == (b >> 5)) ? (int)(b & 31) : 31;
+            const unsigned m = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+            if ((seg_bits[w] & m) != m) atomicOr(seg_bits + w, m);
+        }
     }
 }
 
-// one warp per 32 segments (one word of the bitmap): four segment loads in flight per lane
-__global__ void __launch_bounds__(256) k_gray_gather(const uint4* __restrict__ src, uint4* __restrict__ dst, const unsigned* __restrict__ seg_bits, int n_words,
-                                                      long long n_chunks16, int* n_segments_out) {
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= n_words) return;
-    unsigned m = seg_bits[w];
-    if (lane == 0 && m) atomicAdd(n_segments_out, __popc(m));
-    while (m) {
-        uint4 v[4];
-        long long o[4];
-        int n = 0;
+// Each warp walks bitmap words (32 segments = 4 KB of frame); a load instruction moves four segments (lane / 8 = segment, lane % 8 = chunk),
+// two load instructions are in flight per lane before the stores.
+__global__ void __launch_bounds__(GG_THREADS, 8) k_gray_gather(const uint4* __restrict__ src, uint4* __restrict__ dst, const unsigned* __restrict__ seg_bits, int n_words,
+                                                             long long n_chunks16, int* n_segments_out) {
+    const int lane = threadIdx.x & 31, sub = lane >> 3, ch = lane & 7;
+    const int warp = (blockIdx.x * GG_THREADS + threadIdx.x) >> 5, n_warps = (gridDim.x * GG_THREADS) >> 5;
+    int n_mine = 0;
+    for (int w = warp; w < n_words; w += n_warps) {
+        unsigned m = seg_bits[w];
+        n_mine += __popc(m);
+        while (m) {
+            long long o[2];
+            uint4 v[2];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            o[k] = -1;
-            if (m) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                o[k] = ((long long)w * 32 + b) * (GSEG / 16) + lane;
-                if (o[k] >= n_chunks16) o[k] = -1;  // tail of the buffer (rounded up to whole 16-byte chunks by the caller)
-                n++;
+            for (int k = 0; k < 2; k++) {
+                // the (sub + 1)-th set bit of m, then drop up to four bits
+                const unsigned b = __fns(m, 0, sub + 1);
+                o[k] = (b < 32u) ? ((long long)w * 32 + b) * (GSEG / 16) + ch : -1;
+                if (o[k] >= n_chunks16) o[k] = -1;
+#pragma unroll
+                for (int q = 0; q < 4; q++) m &= m - 1;
+                if (o[k] >= 0) v[k] = src[o[k]];
             }
-            if (o[k] >= 0) v[k] = src[o[k]];
-        }
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (o[k] >= 0) dst[o[k]] = v[k];
+            for (int k = 0; k < 2; k++)
+                if (o[k] >= 0) dst[o[k]] = v[k];
+        }
     }
+    if (lane == 0 && n_mine) atomicAdd(n_segments_out, n_mine);
 }
 
 cudaError_t launch_gray_gather(const DetectBuffers& B, const uint8_t* gray_host_mapped, uint8_t* gray_dev, long long n_bytes, unsigned* seg_bits, int* n_segments_out,
-                               cudaStream_t st) {
+                               int num_sms, cudaStream_t st) {
     if (B.n_tasks == 0 || n_bytes <= 0) return cudaSuccess;
     const long long n_seg = (n_bytes + GSEG - 1) / GSEG;
     const int n_words = (int)((n_seg + 31) / 32);
     cudaError_t e = cudaMemsetAsync(seg_bits, 0, 4 * (size_t)n_words, st);
     if (e != cudaSuccess) return e;
     k_gray_mark<<<B.n_tasks, 128, 0, st>>>(B, seg_bits);
-    k_gray_gather<<<(n_words * 32 + 255) / 256, 256, 0, st>>>(reinterpret_cast<const uint4*>(gray_host_mapped), reinterpret_cast<uint4*>(gray_dev), seg_bits, n_words,
-                                                              (n_bytes + 15) / 16, n_segments_out);
+    k_gray_gather<<<2 * num_sms, GG_THREADS, 0, st>>>(reinterpret_cast<const uint4*>(gray_host_mapped), reinterpret_cast<uint4*>(gray_dev), seg_bits, n_words,
+                                                     n_bytes / 16, n_segments_out);
     return cudaGetLastError();
 }
 

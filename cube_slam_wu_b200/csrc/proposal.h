@@ -22,7 +22,7 @@ struct DetectBuffers {
     double* ml_ang;
     double* ml_mid;  // 2 per merged line
     int* n_merged;
-    double* vp_sup;      // 6 doubles per (task, group): VP-support angles low/top of vp1, vp2, vp3; task stride sup_stride
+    double* vp_sup;      // 12 doubles per (task, group): vanishing points 1..3 (x, y) | VP-support angles low/top of vp1, vp2, vp3; task stride sup_stride
     long long sup_stride;
     // k_score outputs (compacted valid proposals in enumeration order)
     double* p_dist;
@@ -59,7 +59,7 @@ cudaError_t launch_recover(const DetectBuffers& B, cudaStream_t st);
 cudaError_t launch_rank(const DetectBuffers& B, int n_boxes, cudaStream_t st);
 cudaError_t launch_distmaps(const DetectBuffers& B, const uint8_t* gray, uint8_t* cmap, int* queue, unsigned* dtmp, float* maps, int max_roi_w, int max_pm_words, cudaStream_t st);
 cudaError_t launch_gray_gather(const DetectBuffers& B, const uint8_t* gray_host_mapped, uint8_t* gray_dev, long long n_bytes, unsigned* seg_bits, int* n_segments_out,
-                               cudaStream_t st);
+                               int num_sms, cudaStream_t st);
 cudaError_t score_phase_cycles(unsigned long long* out12, bool reset);
 cudaError_t launch_debug_atan2(const double* y, const double* x, double* out, int n6, int* n_fallback, cudaStream_t st);
 cudaError_t launch_debug_corners(const DetectBuffers& B, int task, int n_valid, double* out, cudaStream_t st);

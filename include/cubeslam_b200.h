@@ -45,7 +45,7 @@ int csb_synchronize(csb_context* ctx);
 const char* csb_version(void);
 /* Tuning switches (defaults in brackets).
  *   CSB_OPT_GRAY_GATHER [1]: csb_detect_upload_gray / csb_detect_batch_gray with a PINNED, 16-byte aligned gray buffer (cudaHostAlloc /
- *   cudaHostRegister) fetch only the 512-byte segments of the frames that the box ROIs (+ the one-pixel Sobel halo) touch, by a kernel
+ *   cudaHostRegister) fetch only the 128-byte segments of the frames that the box ROIs (+ the one-pixel Sobel halo) touch, by a kernel
  *   reading the caller's buffer over PCIe, instead of copying whole frames with the copy engine; 0 = always copy whole frames.  Results
  *   are identical either way; pageable buffers are always copied as a whole. */
 #define CSB_OPT_GRAY_GATHER 1
@@ -150,9 +150,10 @@ int csb_detect_batch_gray(csb_context* ctx, const csb_frame* frames, int n_frame
                           const csb_detect_params* params, csb_cuboid* cuboids_out, int32_t* n_cuboids_out, csb_detect_stats* stats);
 /* Parity/debug: the distance map (and, in gray mode, the 0/1/2 Canny map: 2 = edge) of one task after a run. */
 int csb_detect_debug_map(csb_context* ctx, int task_id, float* dist_map_out, uint8_t* edges_out, int capacity);
-/* Profiling/debug: SM cycles spent per phase of the scoring kernel (thread 0 of every CTA, summed over CTAs and tasks) since the last
- * reset: [0] task fetch / chunk wait, [1] line tables + vanishing points, [2] VP support, [3] corner construction + rejection,
- * [4] prefix sums, [5] wait for the distance map, [6] scoring, [7] exit; [8..10] VP-support units decided by the float / double /
+/* Profiling/debug, only in a library built with -DCSB_SCORE_PHASES (otherwise CSB_ERR_CUDA, "not supported"): SM cycles spent per phase
+ * of the scoring kernel (thread 0 of every CTA, summed over CTAs and tasks) since the last reset: [0] task fetch / chunk wait, [1] tables
+ * (vanishing points, VP-support angles), [2] stage 1 of the rejection cascade (corners 2 - 4), [3] prefix sums, [4] stage 2 (corners
+ * 5 - 8), [5] ordered compaction, [6] wait for the distance map, [7] scoring; [8..10] VP-support units decided by the float / double /
  * exact tier, [11] unused.  The buffer holds 12 entries. */
 int csb_detect_debug_score_phases(csb_context* ctx, uint64_t* cycles12, int reset);
 /* Parity/debug: the six-at-a-time atan2 of the scoring kernel (groups of six operands, n a multiple of 6) with its scalar fallback;

@@ -70,12 +70,15 @@ def test_config5_frames_to_graph(ctx, csb, oracle):
     for k, tol in (("H_cam", 1e-4), ("eo_Hij", 1e-4), ("b_cam", 1e-4), ("H_cube", 2e-2), ("ec_Hij", 2e-2), ("b_cube", 2e-2)):
         assert rel(lin[k], ref[k]) <= tol, "%s differs by %g" % (k, rel(lin[k], ref[k]))
     # (b) closed-form Jacobians on the device against central differences with delta = 1e-5 in the oracle (round-off 1e-11 instead of 1e-7,
-    # truncation O(delta^2)): every block and both right-hand sides to 1e-6 of the block scale (north star: 1e-4)
+    # truncation O(delta^2)): the camera / cuboid blocks and both right-hand sides to 1e-6 of the block scale (north star: 1e-4).  The
+    # odometry blocks to 5e-5: SE3Quat::log switches to omega = deltaR / 2, V^-1 = I - W/2 + W^2/12 below 4.5 mrad (se3quat.h:238-247); the
+    # derivative of that branch differs from the exact logarithm's by O(theta^2) <= 2e-5, which the central differences see and the
+    # closed form (derivative of the exact logarithm) does not -- these residuals (pose noise of 5 mrad) sit right at the switch.
     oracle.ba_set_delta(1e-5)
     try:
         acc = oracle.ba_linearize(g["cams7"], g["cam_fixed"], g["cubes10"], g["cube_fixed"], E)
     finally:
         oracle.ba_set_delta(1e-9)
-    for k in ("H_cam", "b_cam", "H_cube", "b_cube", "ec_Hij", "eo_Hij"):
-        assert rel(lin_a[k], acc[k]) <= 1e-6, "analytic %s differs by %g" % (k, rel(lin_a[k], acc[k]))
+    for k, tol in (("H_cam", 1e-6), ("b_cam", 1e-6), ("H_cube", 1e-6), ("b_cube", 1e-6), ("ec_Hij", 1e-6), ("eo_Hij", 5e-5)):
+        assert rel(lin_a[k], acc[k]) <= tol, "analytic %s differs by %g" % (k, rel(lin_a[k], acc[k]))
     assert out["edges_per_s"]["numeric"] > 0 and out["allgather_bytes_per_rank"] == 3 * 512 * 128
