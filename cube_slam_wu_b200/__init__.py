@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libcubeslam_b200.so")
+LIB_PATH = os.environ.get("CSB_LIB") or os.path.join(_PKG, "libcubeslam_b200.so")  # CSB_LIB: development override (A/B timing of library builds)
 _LIB = None
 
 CSB_OK, CSB_ERR_INVALID, CSB_ERR_CUDA, CSB_ERR_CAPACITY, CSB_ERR_STATE = 0, -1, -2, -3, -4

@@ -293,7 +293,7 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
     CSB_CUDA(c, d.d_ml_ang.ensure(8 * LT));
     CSB_CUDA(c, d.d_ml_mid.ensure(16 * LT));
     CSB_CUDA(c, d.d_n_merged.ensure(4 * NT));
-    CSB_CUDA(c, d.d_vp_sup.ensure(96 * NT * (size_t)std::max(d.max_groups, 1)));
+    CSB_CUDA(c, d.d_vp_sup.ensure(48 * NT * (size_t)std::max(d.max_groups, 1)));
     CSB_CUDA(c, d.d_p_dist.ensure(8 * OT));
     CSB_CUDA(c, d.d_p_angle.ensure(8 * OT));
     CSB_CUDA(c, d.d_p_hyp.ensure(4 * OT));
@@ -320,7 +320,7 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
     B.task_order = reinterpret_cast<const int*>(db + off_order); B.box_task_begin = reinterpret_cast<const int*>(db + off_box);
     B.lines = reinterpret_cast<const double*>(db + off_lines); B.maps = d.d_maps.as<float>(); B.n_tasks = n_tasks; B.pad = 0;
     B.ml_seg = d.d_ml_seg.as<double>(); B.ml_ang = d.d_ml_ang.as<double>(); B.ml_mid = d.d_ml_mid.as<double>(); B.n_merged = d.d_n_merged.as<int>();
-    B.vp_sup = d.d_vp_sup.as<double>(); B.sup_stride = 12 * (long long)std::max(d.max_groups, 1);
+    B.vp_sup = d.d_vp_sup.as<double>(); B.sup_stride = 6 * (long long)std::max(d.max_groups, 1);
     B.p_dist = d.d_p_dist.as<double>(); B.p_angle = d.d_p_angle.as<double>(); B.p_hyp = d.d_p_hyp.as<int>();
     B.n_valid = reinterpret_cast<int*>(dr + d.res_off_nvalid);
     B.keep = d.d_keep.as<int>(); B.norm_score = d.d_norm.as<double>(); B.n_keep = reinterpret_cast<int*>(dr + d.res_off_nkeep);

@@ -57,10 +57,8 @@ __device__ unsigned long long g_score_phase_cycles[12];  // [8..10]: VP-support 
             t_prev = now__;                                                         \
         }                                                                           \
     } while (0)
-#define SCORE_PHASE_COUNT(idx, n) atomicAdd(&g_score_phase_cycles[idx], (unsigned long long)(n))
 #else
 #define SCORE_PHASE(idx) do { } while (0)
-#define SCORE_PHASE_COUNT(idx, n) do { } while (0)
 #endif
 
 cudaError_t score_phase_cycles(unsigned long long* out12, bool reset) {
@@ -479,7 +477,7 @@ __global__ void __launch_bounds__(VPS_THREADS) k_vp_support(DetectBuffers B, int
         if (tid == 0) s_namb = 0;
     }
     __syncthreads();
-    double* sup = B.vp_sup + (size_t)task * B.sup_stride;  // 12 doubles per group: vanishing points 1..3 (x, y), then low / top angle per VP
+    double* sup = B.vp_sup + (size_t)task * B.sup_stride;
     auto unit_of = [&](int u, int& g, int& vp_id) {
         if (u < 2 * n_groups) { g = u >> 1; vp_id = u & 1; }
         else { g = (u - 2 * n_groups) * n_yaw; vp_id = 2; }
@@ -491,13 +489,9 @@ __global__ void __launch_bounds__(VPS_THREADS) k_vp_support(DetectBuffers B, int
         vx = vp_id == 0 ? vp[0] : (vp_id == 1 ? vp[2] : vp[4]);
         vy = vp_id == 0 ? vp[1] : (vp_id == 1 ? vp[3] : vp[5]);
     };
-    auto store_unit = [&](int g, int vp_id, double vx, double vy, double lo, double tp, int first_lane, int stride) {
-        if (vp_id < 2) {
-            if (first_lane == 0) { sup[12 * g + 2 * vp_id] = vx; sup[12 * g + 2 * vp_id + 1] = vy; sup[12 * g + 6 + 2 * vp_id] = lo; sup[12 * g + 6 + 2 * vp_id + 1] = tp; }
-        } else
-            for (int y = first_lane; y < n_yaw; y += stride) {  // vp3 is shared by the pair's yaw samples
-                sup[12 * (g + y) + 4] = vx; sup[12 * (g + y) + 5] = vy; sup[12 * (g + y) + 10] = lo; sup[12 * (g + y) + 11] = tp;
-            }
+    auto store_unit = [&](int g, int vp_id, double lo, double tp, int first_lane, int stride) {
+        if (vp_id < 2) { if (first_lane == 0) { sup[6 * g + 2 * vp_id] = lo; sup[6 * g + 2 * vp_id + 1] = tp; } }
+        else for (int y = first_lane; y < n_yaw; y += stride) { sup[6 * (g + y) + 4] = lo; sup[6 * (g + y) + 5] = tp; }  // vp3 is shared by the pair's yaw samples
     };
     // sin^2 of the guard-band edges around the 15 / 10 degree thresholds
     const float fl12 = sinf((float)(15.0 / 180.0 * M_PI) - 1e-4f), fh12 = sinf((float)(15.0 / 180.0 * M_PI) + 1e-4f);
@@ -514,7 +508,7 @@ __global__ void __launch_bounds__(VPS_THREADS) k_vp_support(DetectBuffers B, int
             const bool v3 = vp_id == 2;
             const bool ok = vp_support_mixed(vx, vy, v3 ? fl3 * fl3 : fl12 * fl12, v3 ? fh3 * fh3 : fh12 * fh12, v3 ? dl3 * dl3 : dl12 * dl12, v3 ? dh3 * dh3 : dh12 * dh12,
                                              n_lines, k_ang, k_mid, k_cs, k_midf, k_csf, vp_id > 0, lo, tp);
-            if (ok) store_unit(g, vp_id, vx, vy, lo, tp, 0, 1);
+            if (ok) store_unit(g, vp_id, lo, tp, 0, 1);
             else s_amb[atomicAdd(&s_namb, 1)] = u;
         }
     }
@@ -531,13 +525,13 @@ __global__ void __launch_bounds__(VPS_THREADS) k_vp_support(DetectBuffers B, int
         double vx, vy, lo, tp;
         unit_vp(g, vp_id, vx, vy);
         vp_support_unit(active, vx, vy, (vp_id != 2 ? 15.0 : 10.0) / 180.0 * M_PI, (vp_id != 2 ? dh12 * dh12 : dh3 * dh3), n_lines, k_ang, k_mid, lcs, lane, vp_id > 0, lo, tp);
-        if (active) store_unit(g, vp_id, vx, vy, lo, tp, sl, SUBW);
+        if (active) store_unit(g, vp_id, lo, tp, sl, SUBW);
     }
 #ifdef CSB_SCORE_PHASES
     if (tid == 0) {
         const int mine = (n_units - u_begin < VPS_THREADS) ? (n_units - u_begin) : VPS_THREADS;
-        SCORE_PHASE_COUNT(8, mine - n_amb);
-        SCORE_PHASE_COUNT(10, n_amb);
+        atomicAdd(&g_score_phase_cycles[8], (unsigned long long)(mine - n_amb));
+        atomicAdd(&g_score_phase_cycles[10], (unsigned long long)n_amb);
     }
 #endif
 }
@@ -560,64 +554,30 @@ __device__ __forceinline__ int block_excl_scan(int v, int* s_w, int tid, int& to
     return pre + inc - v;
 }
 
-constexpr int SCORE_LIST_CAP = 2048;  // valid proposals staged per scoring pass (8 bytes each); larger tasks are scored in several passes
-
-// i-th set bit (0-based) of a bit array whose per-word exclusive popcount prefix is `pre` (n_words + 1 entries)
-__device__ __forceinline__ int nth_set_bit(const unsigned* words, const int* pre, int n_words, int i) {
-    int lo = 0, hi = n_words - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (pre[mid] <= i) lo = mid; else hi = mid - 1;
-    }
-    return (lo << 5) + (int)__fns(words[lo], 0, i - pre[lo] + 1);
-}
-
-// exclusive prefix of the popcounts of n_words mask words -> pre[0 .. n_words]; returns the total.  All threads of the CTA call it.
-template <int THREADS>
-__device__ __forceinline__ int mask_prefix(const unsigned* words, int n_words, int* pre, int* s_w, int tid) {
-    int total = 0;
-    for (int w0 = 0; w0 < n_words; w0 += THREADS) {
-        const int w = w0 + tid;
-        const int v = (w < n_words) ? __popc(words[w]) : 0;
-        int tot;
-        const int p = block_excl_scan<THREADS>(v, s_w, tid, tot);
-        if (w < n_words) pre[w] = total + p;
-        total += tot;
-    }
-    if (tid == 0) pre[n_words] = total;
-    return total;
-}
-
-// Persistent CTA: loops over tasks handed out by an atomic counter (largest first).  Per task:
-//   (a) TMA bulk copy of the task's distance map into shared memory (lands while (b)-(e) run)
-//   (b) vanishing points per (roll,pitch,yaw) group and the VP-support angles k_vp_support left in global memory -> shared memory
-//   (c) stage 1, one lane per (group, top sample): corner 2, then corners 3 / 4 of both configurations with their tests
-//       (box_proposal_detail.cpp:413-561: 23 % of the pairs and 78 % of the configurations that are left end here) -> bitmask B
-//   (d) stage 2, one lane per SURVIVOR of stage 1 (dense warps: prefix over mask B, i-th set bit): corners 2 .. 4 again without tests,
-//       corners 5 .. 8 with theirs (:563-625) -> bitmask E over the survivors
-//   (e) ordered compaction of E into two lists, one per configuration (entry = hypothesis id + position in enumeration order)
-//   (f) scoring, one lane per valid proposal, warps uniform in the configuration: corners once more without tests, the six edge angles
-//       against the VP-support angles, 99 / 77 distance-map gathers in the reference's summation order; results go to the proposal's
-//       position in enumeration order
-// Warps fetch 32-item chunks of (c), (d) and (f) from shared counters: the cost of an item depends on where the cascade rejects it.
+// Persistent CTA: loops over tasks handed out by an atomic counter (largest first).
+//   (a) TMA bulk copy of the task's distance map into shared memory (lands while (b)-(d) run)
+//   (b) vanishing points per (roll,pitch,yaw) group -> shared memory
+//   (c) VP-support angles of the groups (computed by k_prep_lines) -> shared memory
+//   (d) phase 1: every hypothesis through the corner construction / rejection cascade -> validity bitmask (enumeration order)
+//   (e) prefix sums over the bitmask words: proposal i of the compacted list <-> hypothesis id
+//   (f) phase 2: one thread per surviving proposal (all lanes busy): corners again, 99/77 distance-map gathers, edge-angle error
 __global__ void __launch_bounds__(SCORE_THREADS, SCORE_CTAS_PER_SM) k_score(DetectBuffers B, int groups_cap, int map_cap_floats, int words_cap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_map = reinterpret_cast<float*>(smem_raw);
-    double* s_tab = reinterpret_cast<double*>(smem_raw + (size_t)map_cap_floats * 4);  // 12 doubles per group: 3 vanishing points | 3 x (low, top) support angles
-    int2* s_list = reinterpret_cast<int2*>(s_tab + 12 * (size_t)groups_cap);
-    unsigned* s_mask = reinterpret_cast<unsigned*>(s_list + SCORE_LIST_CAP);  // B: stage-1 survivors, bit = hypothesis id
-    unsigned* s_maskE = s_mask + words_cap;                                  // E: valid, bit = survivor index
-    int* s_wpre = reinterpret_cast<int*>(s_maskE + words_cap);               // words_cap + 1 entries
-    __shared__ uint64_t s_bar, s_bar_tab;
-    __shared__ int s_task, s_chunk[3];
+    double* s_vp = reinterpret_cast<double*>(smem_raw + (size_t)map_cap_floats * 4);
+    double* s_sup = s_vp + 6 * (size_t)groups_cap;
+    unsigned* s_mask = reinterpret_cast<unsigned*>(s_sup + 6 * (size_t)groups_cap);
+    int* s_wpre = reinterpret_cast<int*>(s_mask + words_cap);  // words_cap + 1 entries
+    __shared__ uint64_t s_bar;
+    __shared__ int s_task, s_chunk;
     __shared__ int s_w[SCORE_THREADS / 32];
 
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned FULL = 0xffffffffu;
 
-    if (tid == 0) { mbar_init(&s_bar, 1); mbar_init(&s_bar_tab, 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
     __syncthreads();
-    uint32_t bar_parity = 0, tab_parity = 0;
+    uint32_t bar_parity = 0;
 #ifdef CSB_SCORE_PHASES
     long long t_prev = clock64();
 #endif
@@ -630,14 +590,13 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_CTAS_PER_SM) k_score(Dete
             // a chunk is usable once its flag (copied right after it, same stream) carries the current epoch.
             if (B.ready_flags && sl < B.n_tasks) {
                 const TaskTab& tq = B.ttab[B.task_order[sl]];
-                const long long last = (long long)tq.map_offset + (long long)tq.roi_w * tq.roi_h - 1;
-                int chunk = 0;
-                while (chunk < B.n_chunks - 1 && B.chunk_end[chunk] <= last) chunk++;
-                const volatile unsigned* fl = B.ready_flags + chunk;
+            const long long last = (long long)tq.map_offset + (long long)tq.roi_w * tq.roi_h - 1;
+            int chunk = 0;
+            while (chunk < B.n_chunks - 1 && B.chunk_end[chunk] <= last) chunk++;
+            const volatile unsigned* fl = B.ready_flags + chunk;
                 while (*fl != B.epoch) __nanosleep(256);
                 __threadfence();
             }
-            s_chunk[0] = 0; s_chunk[1] = 0; s_chunk[2] = 0;
         }
         __syncthreads();
         const int slot = s_task;
@@ -655,30 +614,40 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_CTAS_PER_SM) k_score(Dete
         // a map larger than the shared-memory budget: its first rows (as many whole rows as fit) are staged, the rest is gathered from L2
         const int smem_floats = map_smem ? map_floats : (map_cap_floats / tt.roi_w) * tt.roi_w;
 
-        // (a) + (b): both bulk copies are issued by one thread; the tables (vanishing points + support angles, written by k_vp_support)
-        // are needed first, the map only by the scoring passes
-        if (tid == 0) {
-            fence_proxy_async();  // previous task's generic reads of s_tab / s_map are ordered before the async writes
-            const uint32_t tab_bytes = (uint32_t)n_groups * 96u;
-            mbar_expect_tx(&s_bar_tab, tab_bytes);
-            tma_bulk_g2s(s_tab, B.vp_sup + (size_t)task * B.sup_stride, tab_bytes, &s_bar_tab);
-            if (smem_floats > 0) {
-                uint32_t bytes = map_smem ? (((uint32_t)map_floats * 4u + 15u) & ~15u) : (((uint32_t)smem_floats * 4u) & ~15u);
-                mbar_expect_tx(&s_bar, bytes);
-                tma_bulk_g2s(s_map, gmap, bytes, &s_bar);
-            }
+        // (a)
+        if (smem_floats > 0 && tid == 0) {
+            uint32_t bytes = map_smem ? (((uint32_t)map_floats * 4u + 15u) & ~15u) : (((uint32_t)smem_floats * 4u) & ~15u);
+            fence_proxy_async();  // previous task's generic reads of s_map are ordered before the async write
+            mbar_expect_tx(&s_bar, bytes);
+            tma_bulk_g2s(s_map, gmap, bytes, &s_bar);
         }
-        mbar_wait(&s_bar_tab, tab_parity);
-        tab_parity ^= 1;
-        SCORE_PHASE(1);  // tables
+        // (b) vanishing points per group + the VP-support angles k_prep_lines left in global memory
+        for (int g = tid; g < n_groups; g += SCORE_THREADS) {
+            int yaw_id = g % n_yaw, pair = g / n_yaw;
+            double vp[6];
+            vanishing_points(ft.KinvR[pair], ft.cosy[yaw_id], ft.siny[yaw_id], vp);
+#pragma unroll
+            for (int q = 0; q < 6; q++) s_vp[6 * g + q] = vp[q];
+        }
+        {
+            const double* sup = B.vp_sup + (size_t)task * B.sup_stride;
+            for (int i = tid; i < 6 * n_groups; i += SCORE_THREADS) s_sup[i] = sup[i];
+        }
+        if (tid == 0) s_chunk = 0;
+        SCORE_PHASE(1);
+        __syncthreads();
+        SCORE_PHASE(2);  // VP support
 
-        // (c) stage 1 -> mask B.  Hypothesis id = 2 * pair + (cfg - 1): a warp's 32 pairs fill two mask words (bits interleaved)
+        // (d) phase 1 -> validity bitmask
         const int n_hyp = tt.n_hyp;
         const int n_words = (n_hyp + 31) >> 5;
+        // one thread per (group, top sample): corner 2 once, then both configurations; hypothesis id = 2 * pair + (cfg - 1), so a
+        // warp's 32 pairs fill two mask words (bits interleaved: even = configuration 1, odd = configuration 2)
         const int n_pairs_gt = n_hyp >> 1;
+        // warps fetch chunks of 32 pairs from a shared counter: the cost of a pair depends on where the cascade rejects it
         while (true) {
             int cb = 0;
-            if (lane == 0) cb = atomicAdd(&s_chunk[0], 32);
+            if (lane == 0) cb = atomicAdd(&s_chunk, 32);
             cb = __shfl_sync(FULL, cb, 0);
             if (cb >= n_pairs_gt) break;
             const int p = cb + lane;
@@ -687,11 +656,11 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_CTAS_PER_SM) k_score(Dete
                 const int group = p / tt.n_top, top = p - group * tt.n_top;
                 const double c1x = (double)(tt.top_x0 + top * tt.top_step);
                 V2 c2;
-                const int vp1 = construct_corner2(geo, s_tab + 12 * group, c1x, c2);
+                const int vp1 = construct_corner2(geo, s_vp + 6 * group, c1x, c2);
                 if (vp1 > 0) {
-                    V2 c3, c4;
-                    if (tt.cfg_mask & 1) v1 = construct_top<true>(geo, s_tab + 12 * group, c1x, c2, vp1, 1, c3, c4);
-                    if (tt.cfg_mask & 2) v2 = construct_top<true>(geo, s_tab + 12 * group, c1x, c2, vp1, 2, c3, c4);
+                    V2 c[8];
+                    if (tt.cfg_mask & 1) v1 = construct_rest(geo, s_vp + 6 * group, c1x, c2, vp1, 1, c) > 0;
+                    if (tt.cfg_mask & 2) v2 = construct_rest(geo, s_vp + 6 * group, c1x, c2, vp1, 2, c) > 0;
                 }
             }
             const unsigned b1 = __ballot_sync(FULL, v1), b2 = __ballot_sync(FULL, v2);
@@ -705,94 +674,48 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_CTAS_PER_SM) k_score(Dete
             }
         }
         __syncthreads();
-        SCORE_PHASE(2);  // stage 1
-        const int nB = mask_prefix<SCORE_THREADS>(s_mask, n_words, s_wpre, s_w, tid);
-        __syncthreads();
-        SCORE_PHASE(3);  // prefix B
-
-        // (d) stage 2 -> mask E (one word per chunk of 32 survivors)
-        while (true) {
-            int cb = 0;
-            if (lane == 0) cb = atomicAdd(&s_chunk[1], 32);
-            cb = __shfl_sync(FULL, cb, 0);
-            if (cb >= nB) break;
-            const int i = cb + lane;
-            bool ok = false;
-            if (i < nB) {
-                const int h = nth_set_bit(s_mask, s_wpre, n_words, i);
-                int group, top, cfg;
-                decode_hyp(h, tt.n_top, group, top, cfg);
-                const double c1x = (double)(tt.top_x0 + top * tt.top_step);
-                V2 c[8];
-                c[0] = V2{c1x, geo.top};
-                const int vp1 = construct_corner2<false>(geo, s_tab + 12 * group, c1x, c[1]);
-                construct_top<false>(geo, s_tab + 12 * group, c1x, c[1], vp1, cfg, c[2], c[3]);
-                ok = construct_down<true>(geo, s_tab + 12 * group, c);
-            }
-            const unsigned be = __ballot_sync(FULL, ok);
-            if (lane == 0) s_maskE[cb >> 5] = be;
+        SCORE_PHASE(3);  // phase 1
+        // (e) exclusive prefix of the word popcounts
+        int n_valid = 0;
+        for (int w0 = 0; w0 < n_words; w0 += SCORE_THREADS) {
+            const int w = w0 + tid;
+            const int v = (w < n_words) ? __popc(s_mask[w]) : 0;
+            int tot;
+            const int pre = block_excl_scan<SCORE_THREADS>(v, s_w, tid, tot);
+            if (w < n_words) s_wpre[w] = n_valid + pre;
+            n_valid += tot;
         }
         __syncthreads();
-        SCORE_PHASE(4);  // stage 2
-
-        // (e) + (f): ordered compaction of E into per-configuration lists, scored whenever the staging list fills up and at the end
-        int n_valid = 0, n1 = 0, n2 = 0;
-        bool have_map = smem_floats == 0;
-        for (int base = 0; base < nB || base == 0; base += SCORE_THREADS) {
-            const int i = base + tid;
-            const bool bit = i < nB && ((s_maskE[i >> 5] >> (i & 31)) & 1u);
-            int h = 0;
-            if (bit) h = nth_set_bit(s_mask, s_wpre, n_words, i);
-            const int packed = bit ? ((h & 1) ? (1 << 16) : 1) : 0;
-            int tot;
-            const int pre = block_excl_scan<SCORE_THREADS>(packed, s_w, tid, tot);
-            if (bit) {
-                const int rank = n_valid + (pre & 0xffff) + (pre >> 16);
-                if (h & 1) s_list[SCORE_LIST_CAP - 1 - (n2 + (pre >> 16))] = make_int2(h, rank);   // configuration 2: from the back
-                else s_list[n1 + (pre & 0xffff)] = make_int2(h, rank);                           // configuration 1: from the front
+        // (f) phase 2
+        SCORE_PHASE(4);  // prefix
+        if (smem_floats > 0) { mbar_wait(&s_bar, bar_parity); bar_parity ^= 1; }
+        SCORE_PHASE(5);  // wait for the map
+        for (int i = tid; i < n_valid; i += SCORE_THREADS) {
+            // word containing the i-th set bit: last w with s_wpre[w] <= i
+            int lo = 0, hi = n_words - 1;
+            while (lo < hi) {
+                int mid = (lo + hi + 1) >> 1;
+                if (s_wpre[mid] <= i) lo = mid; else hi = mid - 1;
             }
-            n1 += tot & 0xffff; n2 += tot >> 16; n_valid += (tot & 0xffff) + (tot >> 16);
-            const bool last = base + SCORE_THREADS >= nB;
-            if (!last && n1 + n2 + SCORE_THREADS <= SCORE_LIST_CAP) continue;
-            __syncthreads();  // the lists are complete
-            SCORE_PHASE(5);   // compaction
-            if (!have_map) { mbar_wait(&s_bar, bar_parity); bar_parity ^= 1; have_map = true; }
-            SCORE_PHASE(6);   // wait for the map
-            const int ch1 = (n1 + 31) >> 5, ch2 = (n2 + 31) >> 5;
-            while (true) {
-                int q = 0;
-                if (lane == 0) q = atomicAdd(&s_chunk[2], 1);
-                q = __shfl_sync(FULL, q, 0);
-                if (q >= ch1 + ch2) break;
-                const bool second = q >= ch1;  // warp-uniform: the chunk's configuration
-                const int j = (second ? (q - ch1) : q) * 32 + lane;
-                if (j < (second ? n2 : n1)) {
-                    const int2 e = second ? s_list[SCORE_LIST_CAP - 1 - j] : s_list[j];
-                    int group, top, cfg;
-                    decode_hyp(e.x, tt.n_top, group, top, cfg);
-                    V2 c[8];
-                    construct_corners<false>(geo, s_tab + 12 * group, (double)(tt.top_x0 + top * tt.top_step), cfg, c);
-                    const double total_angle_diff = second ? box_edge_alignment_angle_error<2>(s_tab + 12 * group + 6, c) : box_edge_alignment_angle_error<1>(s_tab + 12 * group + 6, c);
-                    // (the bulk copy of a partial map is rounded down to 16 bytes: up to three floats short of smem_floats)
-                    double sum_dist;
-                    if (second) sum_dist = map_smem ? box_edge_sum_dists<1, 2>(s_map, gmap, 0, tt.roi_h, tt.roi_w, c, geo.roi_l, geo.roi_t)
-                                                    : box_edge_sum_dists<2, 2>(s_map, gmap, smem_floats & ~3, tt.roi_h, tt.roi_w, c, geo.roi_l, geo.roi_t);
-                    else sum_dist = map_smem ? box_edge_sum_dists<1, 1>(s_map, gmap, 0, tt.roi_h, tt.roi_w, c, geo.roi_l, geo.roi_t)
-                                             : box_edge_sum_dists<2, 1>(s_map, gmap, smem_floats & ~3, tt.roi_h, tt.roi_w, c, geo.roi_l, geo.roi_t);
-                    const size_t o = (size_t)tt.out_offset + e.y;
-                    B.p_dist[o] = sum_dist / tt.diag;
-                    B.p_angle[o] = total_angle_diff;
-                    B.p_hyp[o] = e.x;
-                }
-            }
-            __syncthreads();  // everyone is done with the lists (and, after the last pass, with the map and the tables)
-            if (tid == 0) s_chunk[2] = 0;
-            n1 = 0; n2 = 0;
-            SCORE_PHASE(7);   // scoring
-            if (last) break;
+            const int h = (lo << 5) + (int)__fns(s_mask[lo], 0, i - s_wpre[lo] + 1);
+            int group, top, cfg;
+            decode_hyp(h, tt.n_top, group, top, cfg);
+            V2 c[8];
+            construct_corners<false>(geo, s_vp + 6 * group, (double)(tt.top_x0 + top * tt.top_step), cfg, c);
+            const double total_angle_diff = box_edge_alignment_angle_error(s_sup + 6 * group, c, cfg);
+            // (the bulk copy of a partial map is rounded down to 16 bytes: up to three floats short of smem_floats)
+            const double sum_dist = map_smem ? box_edge_sum_dists<1>(s_map, gmap, 0, tt.roi_h, tt.roi_w, c, geo.roi_l, geo.roi_t, cfg)
+                                             : box_edge_sum_dists<2>(s_map, gmap, smem_floats & ~3, tt.roi_h, tt.roi_w, c, geo.roi_l, geo.roi_t, cfg);
+            const size_t o = (size_t)tt.out_offset + i;
+            B.p_dist[o] = sum_dist / tt.diag;
+            B.p_angle[o] = total_angle_diff;
+            B.p_hyp[o] = h;
         }
         if (tid == 0) B.n_valid[task] = n_valid;
+        __syncthreads();
+        SCORE_PHASE(6);  // phase 2
     }
+    SCORE_PHASE(7);  // idle tail: exit of this CTA relative to its last task (total kernel time is the slowest CTA)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1197,7 +1120,7 @@ __global__ void k_debug_corners(DetectBuffers B, int task, double* out) {
 // launchers
 // ------------------------------------------------------------------------------------------------
 static size_t score_smem_bytes(int groups_cap, int map_cap_floats, int words_cap) {
-    return (size_t)map_cap_floats * 4 + (size_t)groups_cap * 12 * 8 + (size_t)SCORE_LIST_CAP * 8 + (size_t)(3 * words_cap + 1) * 4 + 64;
+    return (size_t)map_cap_floats * 4 + (size_t)groups_cap * 12 * 8 + (size_t)(2 * words_cap + 1) * 4 + 64;
 }
 
 cudaError_t launch_prep_lines(const DetectBuffers& B, int max_lines_per_frame, int max_groups, cudaStream_t st) {
@@ -1223,9 +1146,7 @@ cudaError_t launch_score(const DetectBuffers& B, int max_groups, int max_hyp_per
     const int words_cap = (max_hyp_per_task + 31) / 32 + 1;
     size_t fixed = score_smem_bytes(groups_cap, 0, words_cap);
     // static __shared__ + slack; with two CTAs per SM each gets half of the SM's 228 KB (1 KB per CTA is reserved by the system)
-    // 4 KB of the SM stay free: the gray-frame gather of another context (k_gray_gather: no shared memory of its own, 1 KB of system
-    // reservation per CTA) must find room next to this one-CTA-per-SM kernel
-    size_t budget = SCORE_CTAS_PER_SM == 1 ? (size_t)max_smem_optin - 1024 - 4096 : (size_t)(228 * 1024) / SCORE_CTAS_PER_SM - 2048;
+    size_t budget = SCORE_CTAS_PER_SM == 1 ? (size_t)max_smem_optin - 1024 : (size_t)(228 * 1024) / SCORE_CTAS_PER_SM - 2048;
     if (fixed + 16 * 1024 > budget) return cudaErrorInvalidValue;
     int map_cap = (int)((budget - fixed) / 4) & ~31;
     size_t smem = score_smem_bytes(groups_cap, map_cap, words_cap);

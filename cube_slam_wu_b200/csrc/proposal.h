@@ -22,7 +22,7 @@ struct DetectBuffers {
     double* ml_ang;
     double* ml_mid;  // 2 per merged line
     int* n_merged;
-    double* vp_sup;      // 12 doubles per (task, group): vanishing points 1..3 (x, y) | VP-support angles low/top of vp1, vp2, vp3; task stride sup_stride
+    double* vp_sup;      // 6 doubles per (task, group): VP-support angles low/top of vp1, vp2, vp3; task stride sup_stride
     long long sup_stride;
     // k_score outputs (compacted valid proposals in enumeration order)
     double* p_dist;

@@ -34,10 +34,9 @@ __device__ __forceinline__ float edge_samples(float sum_dist, const float* __res
 // box_edge_sum_dists, object_3d_util.cpp:622-667 with the visible-edge tables of box_proposal_detail.cpp:646, 663
 // c: corners in image coordinates; (ox, oy) = ROI origin.  The reference shifts all eight corners first (box_proposal_detail.cpp:634-636);
 // shifting the two corners of an edge when the edge is sampled gives the same values and keeps only one corner set live.
-template <int MODE, int CFG>
+template <int MODE>
 __device__ __forceinline__ double box_edge_sum_dists(const float* __restrict__ smap, const float* __restrict__ gmap, int n_smem, int rows, int cols, const V2* cc,
-                                                     double ox, double oy) {
-    constexpr int config_id = CFG;
+                                                     double ox, double oy, int config_id) {
     const int last = rows * cols - 1;
     float s = 0;
     struct Sh { const V2* c; double ox, oy; __device__ __forceinline__ V2 operator[](int i) const { return V2{c[i].x - ox, c[i].y - oy}; } } c{cc, ox, oy};
@@ -71,9 +70,7 @@ __device__ __forceinline__ double edge_angle_diff(double raw_atan2, double v0, d
 // box_edge_alignment_angle_error, object_3d_util.cpp:670-723 with the tables of box_proposal_detail.cpp:651, 665.
 // The six edge angles are evaluated together (det_atan2_x6: six independent chains instead of six calls one after the other);
 // operands on one of det_atan2's special paths make the whole proposal take the scalar route.
-template <int CFG>
-__device__ __forceinline__ double box_edge_alignment_angle_error(const double* sup /*6*/, const V2* c) {
-    constexpr int config_id = CFG;
+__device__ __forceinline__ double box_edge_alignment_angle_error(const double* sup /*6*/, const V2* c, int config_id) {
     const double not_found_penalty = 30.0 / 180.0 * M_PI * 2;
     // VP 1: edges (1,2) and (8,5) | (3,4);  VP 2: edges (4,1) and (5,6);  VP 3: edges (4,8)|(3,5) and (2,6)
     double dy[6], dx[6], ang[6];

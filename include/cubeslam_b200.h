@@ -151,10 +151,9 @@ int csb_detect_batch_gray(csb_context* ctx, const csb_frame* frames, int n_frame
 /* Parity/debug: the distance map (and, in gray mode, the 0/1/2 Canny map: 2 = edge) of one task after a run. */
 int csb_detect_debug_map(csb_context* ctx, int task_id, float* dist_map_out, uint8_t* edges_out, int capacity);
 /* Profiling/debug, only in a library built with -DCSB_SCORE_PHASES (otherwise CSB_ERR_CUDA, "not supported"): SM cycles spent per phase
- * of the scoring kernel (thread 0 of every CTA, summed over CTAs and tasks) since the last reset: [0] task fetch / chunk wait, [1] tables
- * (vanishing points, VP-support angles), [2] stage 1 of the rejection cascade (corners 2 - 4), [3] prefix sums, [4] stage 2 (corners
- * 5 - 8), [5] ordered compaction, [6] wait for the distance map, [7] scoring; [8..10] VP-support units decided by the float / double /
- * exact tier, [11] unused.  The buffer holds 12 entries. */
+ * of the scoring kernel (thread 0 of every CTA, summed over CTAs and tasks) since the last reset: [0] task fetch / chunk wait, [1] line
+ * tables + vanishing points, [2] VP support, [3] corner construction + rejection, [4] prefix sums, [5] wait for the distance map,
+ * [6] scoring, [7] exit; [8..10] VP-support units decided by the float / double / exact tier, [11] unused.  The buffer holds 12 entries. */
 int csb_detect_debug_score_phases(csb_context* ctx, uint64_t* cycles12, int reset);
 /* Parity/debug: the six-at-a-time atan2 of the scoring kernel (groups of six operands, n a multiple of 6) with its scalar fallback;
  * n_fallback (optional) receives the number of groups that took the fallback.  Must equal the scalar det_atan2 bit for bit. */

@@ -24,8 +24,8 @@ for _ in range(reps):
     _, _, st = ctx.detect_download()
     ms.append(st.gpu_ms_score)
 ph = ctx.score_phases(reset=True).astype(np.float64)
-names = ["fetch/wait", "tables", "stage 1 (c2-c4)", "prefix B", "stage 2 (c5-c8)", "compaction", "map wait", "scoring"]
-tot = ph[:8].sum()
+names = ["fetch/wait", "lines+VPs", "VP support", "phase1 corners", "prefix", "map wait", "phase2 score", "exit"]
+tot = ph[:7].sum()
 print("k_score %.3f ms; cycles per CTA per run %.0f (busy) ; 148 CTAs" % (np.mean(ms), tot / reps / 148))
 print("VP-support units per run: float %d, double %d, exact %d" % tuple(int(x / reps) for x in ph[8:11]))
 for n, v in zip(names, ph):
