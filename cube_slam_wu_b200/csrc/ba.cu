@@ -1,10 +1,10 @@
 // ba.cu -- sm_100a kernels + C ABI of the BA half: residuals, central-difference Jacobians and the block normal
 // equations of the camera-cuboid graph (what g2o's BlockSolver::buildSystem() does edge by edge).
 //
-//   k_linearize<TYPE> : half a warp per edge.  Lane c < Di+Dj evaluates the residual at +/-delta along tangent
-//                       direction c of vertex 0 / vertex 1 (the 30 evaluations of BaseBinaryEdge::linearizeOplus,
-//                       base_binary_edge.hpp:130-205, delta = 1e-9) and keeps Jacobian column c in registers; lane 15
-//                       evaluates the unperturbed residual.  The 186-double quadratic form of the edge
+//   k_linearize<TYPE> : a warp per edge.  Lane c < Di+Dj evaluates the residual at +delta along tangent direction c of
+//                       vertex 0 / vertex 1, lane c + 16 at -delta (the 30 evaluations of BaseBinaryEdge::linearizeOplus,
+//                       base_binary_edge.hpp:130-205, delta = 1e-9: one per lane); lane c keeps Jacobian column c in
+//                       registers; lane 15 evaluates the unperturbed residual.  (Closed-form Jacobians: half a warp per edge.)  The 186-double quadratic form of the edge
 //                       (constructQuadraticForm, base_binary_edge.hpp:54-120) is formed with warp shuffles and stored
 //                       as one contiguous record; the off-diagonal block A^T Omega B goes straight to its BSR slot.
 //   k_gather          : one warp per vertex sums the records of its incident edges in g2o's edge order
@@ -37,12 +37,17 @@ constexpr int LIN_THREADS = 128;  // 8 edges per CTA
 template <int TYPE, bool ANALYTIC>
 __global__ void __launch_bounds__(LIN_THREADS) k_linearize(BABuffers B, int n_edges, int64_t rec_base, int chi_base, double* Ji_out, double* Jj_out) {
     constexpr int D = EdgeDims<TYPE>::D, Di = EdgeDims<TYPE>::Di, Dj = EdgeDims<TYPE>::Dj, REC = EdgeDims<TYPE>::REC;
+    // numeric Jacobians: a whole warp per edge -- lane c < 16 evaluates the residual at +delta along tangent c, lane c + 16 at -delta
+    // (one residual evaluation per lane); closed form: half a warp per edge
+    constexpr int LPE = ANALYTIC ? 16 : 32;
     const int tid = blockIdx.x * LIN_THREADS + threadIdx.x;
-    const int e = tid >> 4, c = tid & 15;          // edge, column / role
-    const int lane = threadIdx.x & 31, half_base = lane & 16;
+    const int e = tid / LPE, c = tid & 15;          // edge, column / role
+    const int lane = threadIdx.x & 31, half_base = (LPE == 16) ? (lane & 16) : 0;
+    const bool neg = (LPE == 32) && (lane & 16);    // the -delta half of the warp
     const unsigned FULL = 0xffffffffu;
-    const bool active = e < n_edges;
-    const int ee = active ? e : 0;
+    const bool in_range = e < n_edges;
+    const bool active = in_range && !neg;           // lanes that own a row of the quadratic form / write results
+    const int ee = in_range ? e : 0;
 
     // ---- load
     EdgeCtx x;
@@ -113,45 +118,45 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(BABuffers B, int n_ed
                 }
             }
         }
-    } else if (active) {
+    } else if (in_range) {
+        const double dl = neg ? -delta : delta;
+        double ev[D];
+#pragma unroll
+        for (int k = 0; k < D; k++) ev[k] = 0;
         if (c == 15) {
-            edge_error<TYPE>(x, x.cam, x.cube, x.cam2, J);  // J holds the error vector on lane 15
+            if (!neg) edge_error<TYPE>(x, x.cam, x.cube, x.cam2, ev);  // the error vector, on lane 15
         } else if (c < Di) {
             if (i_free) {
-                double add[6], ep[D], em[D];
+                double add[6];
 #pragma unroll
-                for (int q = 0; q < 6; q++) add[q] = (q == c) ? delta : 0.0;
-                edge_error<TYPE>(x, se3_mul(se3_exp(add), x.cam), x.cube, x.cam2, ep);  // VertexSE3Expmap::oplusImpl: exp(d) * T
-#pragma unroll
-                for (int q = 0; q < 6; q++) add[q] = (q == c) ? -delta : 0.0;
-                edge_error<TYPE>(x, se3_mul(se3_exp(add), x.cam), x.cube, x.cam2, em);
-#pragma unroll
-                for (int k = 0; k < D; k++) J[k] = scalar * (ep[k] - em[k]);
+                for (int q = 0; q < 6; q++) add[q] = (q == c) ? dl : 0.0;
+                edge_error<TYPE>(x, se3_mul(se3_exp(add), x.cam), x.cube, x.cam2, ev);  // VertexSE3Expmap::oplusImpl: exp(d) * T
             }
         } else if (c < Di + Dj) {
             if (j_free) {
                 const int d = c - Di;
-                double ep[D], em[D];
                 if (TYPE == EDGE_ODOM) {
                     double add[6];
 #pragma unroll
-                    for (int q = 0; q < 6; q++) add[q] = (q == d) ? delta : 0.0;
-                    edge_error<TYPE>(x, x.cam, x.cube, se3_mul(se3_exp(add), x.cam2), ep);
-#pragma unroll
-                    for (int q = 0; q < 6; q++) add[q] = (q == d) ? -delta : 0.0;
-                    edge_error<TYPE>(x, x.cam, x.cube, se3_mul(se3_exp(add), x.cam2), em);
+                    for (int q = 0; q < 6; q++) add[q] = (q == d) ? dl : 0.0;
+                    edge_error<TYPE>(x, x.cam, x.cube, se3_mul(se3_exp(add), x.cam2), ev);
                 } else {
                     double add[9];
 #pragma unroll
-                    for (int q = 0; q < 9; q++) add[q] = (q == d) ? delta : 0.0;
-                    edge_error<TYPE>(x, x.cam, cube_exp_update(x.cube, add), x.cam2, ep);  // VertexCuboid::oplusImpl
-#pragma unroll
-                    for (int q = 0; q < 9; q++) add[q] = (q == d) ? -delta : 0.0;
-                    edge_error<TYPE>(x, x.cam, cube_exp_update(x.cube, add), x.cam2, em);
+                    for (int q = 0; q < 9; q++) add[q] = (q == d) ? dl : 0.0;
+                    edge_error<TYPE>(x, x.cam, cube_exp_update(x.cube, add), x.cam2, ev);  // VertexCuboid::oplusImpl
                 }
-#pragma unroll
-                for (int k = 0; k < D; k++) J[k] = scalar * (ep[k] - em[k]);
             }
+        }
+        // central difference (base_binary_edge.hpp:147-160): the -delta evaluation comes from lane + 16
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            const double em = __shfl_down_sync(FULL, ev[k], 16);
+            J[k] = (c == 15) ? ev[k] : scalar * (ev[k] - em);
+        }
+        if (neg) {
+#pragma unroll
+            for (int k = 0; k < D; k++) J[k] = 0;
         }
     }
 
@@ -258,16 +263,16 @@ __global__ void __launch_bounds__(32) k_chi2(const double* edge_chi2, int n, dou
 
 cudaError_t ba_launch(const BABuffers& B, bool want_J, cudaStream_t st, int* n_launches, bool analytic) {
     int L = 0;
-    auto grid = [](int n_edges) { return (n_edges * 16 + LIN_THREADS - 1) / LIN_THREADS; };
+    auto grid = [](int n_edges, int lanes_per_edge) { return (int)(((long long)n_edges * lanes_per_edge + LIN_THREADS - 1) / LIN_THREADS); };
     if (B.n_ec) {
-        if (analytic) k_linearize<EDGE_CUBOID, true><<<grid(B.n_ec), LIN_THREADS, 0, st>>>(B, B.n_ec, 0, 0, want_J ? B.ec_Ji : nullptr, want_J ? B.ec_Jj : nullptr);
-        else k_linearize<EDGE_CUBOID, false><<<grid(B.n_ec), LIN_THREADS, 0, st>>>(B, B.n_ec, 0, 0, want_J ? B.ec_Ji : nullptr, want_J ? B.ec_Jj : nullptr);
+        if (analytic) k_linearize<EDGE_CUBOID, true><<<grid(B.n_ec, 16), LIN_THREADS, 0, st>>>(B, B.n_ec, 0, 0, want_J ? B.ec_Ji : nullptr, want_J ? B.ec_Jj : nullptr);
+        else k_linearize<EDGE_CUBOID, false><<<grid(B.n_ec, 32), LIN_THREADS, 0, st>>>(B, B.n_ec, 0, 0, want_J ? B.ec_Ji : nullptr, want_J ? B.ec_Jj : nullptr);
         L++;
     }
-    if (B.n_ep) { k_linearize<EDGE_PROJ, false><<<grid(B.n_ep), LIN_THREADS, 0, st>>>(B, B.n_ep, (int64_t)132 * B.n_ec, B.n_ec, want_J ? B.ep_Ji : nullptr, want_J ? B.ep_Jj : nullptr); L++; }
+    if (B.n_ep) { k_linearize<EDGE_PROJ, false><<<grid(B.n_ep, 32), LIN_THREADS, 0, st>>>(B, B.n_ep, (int64_t)132 * B.n_ec, B.n_ec, want_J ? B.ep_Ji : nullptr, want_J ? B.ep_Jj : nullptr); L++; }
     if (B.n_eo) {
-        if (analytic) k_linearize<EDGE_ODOM, true><<<grid(B.n_eo), LIN_THREADS, 0, st>>>(B, B.n_eo, (int64_t)132 * (B.n_ec + B.n_ep), B.n_ec + B.n_ep, want_J ? B.eo_Ji : nullptr, want_J ? B.eo_Jj : nullptr);
-        else k_linearize<EDGE_ODOM, false><<<grid(B.n_eo), LIN_THREADS, 0, st>>>(B, B.n_eo, (int64_t)132 * (B.n_ec + B.n_ep), B.n_ec + B.n_ep, want_J ? B.eo_Ji : nullptr, want_J ? B.eo_Jj : nullptr);
+        if (analytic) k_linearize<EDGE_ODOM, true><<<grid(B.n_eo, 16), LIN_THREADS, 0, st>>>(B, B.n_eo, (int64_t)132 * (B.n_ec + B.n_ep), B.n_ec + B.n_ep, want_J ? B.eo_Ji : nullptr, want_J ? B.eo_Jj : nullptr);
+        else k_linearize<EDGE_ODOM, false><<<grid(B.n_eo, 32), LIN_THREADS, 0, st>>>(B, B.n_eo, (int64_t)132 * (B.n_ec + B.n_ep), B.n_ec + B.n_ep, want_J ? B.eo_Ji : nullptr, want_J ? B.eo_Jj : nullptr);
         L++;
     }
     if (B.n_cam) { k_gather<<<(B.n_cam * 32 + 127) / 128, 128, 0, st>>>(B, B.n_cam, 6, B.cam_adj_ptr, B.cam_adj_H, B.cam_adj_b, B.H_cam, B.b_cam); L++; }

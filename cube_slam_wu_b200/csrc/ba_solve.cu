@@ -9,8 +9,7 @@
 //   k_schur_blocks S_IJ = [H_pp + lambda I]_IJ - sum_e1,e2 W_e1 H_pl(e2)^T (+ odometry H_ij), lower block triangle,
 //                  one warp per 6x6 block, contributions gathered in a fixed order (no atomics)
 //   k_schur_rhs    r_I = b_I - sum_e W_e b_l(e)
-//   k_chol_*       blocked right-looking Cholesky of S (32x32 tiles): diagonal tile, panel solve, trailing update
-//   k_trsv         L y = r, L^T x = y (one CTA, 32-wide steps)
+//   k_chol_solve   blocked right-looking Cholesky of S (32x32 tiles) + L y = r, L^T x = y: ONE cooperative kernel with grid barriers
 //   k_cube_back    x_l = (H_ll + lambda I)^-1 (b_l - sum_e H_pl(e)^T x_cam(e))
 //   k_apply        trial estimates = oplus(estimates, x): cameras exp(dx) * T, cuboids pose * exp(dx), scale + ds
 //   k_edge_chi2    chi2 of every edge at the trial estimates (residual only), reduced in a fixed order
@@ -24,6 +23,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <limits>
 #include <vector>
@@ -49,6 +49,8 @@ struct SolveView {
     const int *cube_pl_ptr, *cube_pl_e; // pl edges of every free cuboid, edge order
     double *Ainv, *tl, *W, *S, *rhs, *x_cam, *x_cube, *scal;  // scal: [0] trial chi2, [1] scale, [2] max diag, [3] cholesky ok (1/0)
     double *trial_cams7, *trial_cubes10, *edge_chi2;
+    double* linv;      // inverses of the diagonal Cholesky tiles (ld / 32 tiles of 32 x 32)
+    unsigned* bar;     // grid barrier of k_chol_solve: [0] arrivals, [1] generation
 };
 
 __device__ __forceinline__ const double* pl_hij(const BABuffers& B, const SolveView& V, int e) {
@@ -165,126 +167,219 @@ __global__ void k_schur_rhs(BABuffers B, SolveView V) {
 // ---- blocked Cholesky, lower, in place, row-major, 32x32 tiles ------------------------------------------------------
 constexpr int NB = 32;
 
-__global__ void __launch_bounds__(NB * NB) k_chol_diag(double* S, int ld, int k0, double* ok_flag) {
-    __shared__ double a[NB][NB + 1];
-    const int r = threadIdx.y, c = threadIdx.x;
-    a[r][c] = S[(size_t)(k0 + r) * ld + k0 + c];
+// ---- the whole dense solve S x = r in ONE cooperative kernel --------------------------------------------------------------------
+// Blocked right-looking Cholesky (32 x 32 tiles, lower, in place) followed by the two triangular solves, with grid-wide barriers
+// between the steps instead of one kernel launch per step (config #4: 38 tile columns = 114 launches of the k_chol_* kernels above
+// plus a serial k_trsv became one launch).  Per tile column k:
+//   (1) CTA 0: L_kk = chol(S_kk) in shared memory, and its inverse (a 32 x 32 triangular inverse, one column per lane) -> `linv`
+//   (2) every CTA, rows below the tile: L_ik = S_ik L_kk^-T as a product with the explicit inverse (no dependent chain per row)
+//   (3) every CTA, tiles (i, j) of the trailing lower triangle: S_ij -= L_ik L_jk^T
+// Then L y = r (tile by tile: y_k = L_kk^-1 r_k by CTA 0 with the stored inverses, then every CTA subtracts L_ik y_k from its rows)
+// and L^T x = y backwards.  `linv` keeps the inverse of every diagonal tile (tiles x 32 x 32).
+// The grid barrier is a generation counter in global memory: the kernel is launched with cudaLaunchCooperativeKernel, so all CTAs
+// are resident.
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned n_ctas) {
     __syncthreads();
-    for (int j = 0; j < NB; j++) {
-        if (r == j && c == j) {
-            double d = a[j][j];
-            if (!(d > 0)) { *ok_flag = 0.0; d = 1.0; }
-            a[j][j] = sqrt(d);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        volatile unsigned* gen = bar + 1;
+        const unsigned g = *gen;
+        if (atomicAdd(bar, 1u) == n_ctas - 1) {
+            bar[0] = 0;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        } else {
+            while (*gen == g) { }
         }
-        __syncthreads();
-        if (c == j && r > j) a[r][j] /= a[j][j];
-        __syncthreads();
-        if (r > j && c > j && c <= r) a[r][c] = fma(-a[r][j], a[c][j], a[r][c]);
-        __syncthreads();
+        __threadfence();
     }
-    S[(size_t)(k0 + r) * ld + k0 + c] = (c <= r) ? a[r][c] : 0.0;
+    __syncthreads();
 }
 
-// rows below the diagonal tile: X L11^T = A21, one thread per row
-__global__ void __launch_bounds__(64) k_chol_panel(double* S, int ld, int k0) {
-    __shared__ double l11[NB][NB + 1];
-    for (int i = threadIdx.x; i < NB * NB; i += blockDim.x) l11[i / NB][i % NB] = S[(size_t)(k0 + i / NB) * ld + k0 + i % NB];
-    __syncthreads();
-    const int row = k0 + NB + blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= ld) return;
+constexpr int CF_THREADS = 256;
+#ifdef CSB_CHOL_DEBUG
+#define CHOL_T(i) do { if (cta == 0 && tid == 0) { const long long n__ = clock64(); tacc[i] += n__ - tprev; tprev = n__; } } while (0)
+#else
+#define CHOL_T(i) do { } while (0)
+#endif
+
+// inverse of the lower-triangular tile in shared memory `a` into `b` (row r, column c): one warp, lane = column c of the inverse, forward
+// substitution on e_c with the solution in registers (every index static) and the tile read by broadcast
+__device__ __forceinline__ void tri_inverse_tile(double (*a)[NB + 1], double (*b)[NB + 1], const double* dinv, int lane) {
     double x[NB];
-    double* p = S + (size_t)row * ld + k0;
 #pragma unroll
-    for (int c = 0; c < NB; c++) x[c] = p[c];
+    for (int r = 0; r < NB; r++) {
+        double t0 = (r == lane) ? 1.0 : 0.0, t1 = 0.0;
 #pragma unroll
-    for (int c = 0; c < NB; c++) {
-        double t = x[c];
-#pragma unroll
-        for (int k = 0; k < c; k++) t = fma(-x[k], l11[c][k], t);
-        x[c] = t / l11[c][c];
+        for (int q = 0; q + 1 < r; q += 2) { t0 = fma(-a[r][q], x[q], t0); t1 = fma(-a[r][q + 1], x[q + 1], t1); }
+        if (r & 1) t0 = fma(-a[r][r - 1], x[r - 1], t0);
+        x[r] = (r >= lane) ? (t0 + t1) * dinv[r] : 0.0;
     }
 #pragma unroll
-    for (int c = 0; c < NB; c++) p[c] = x[c];
+    for (int r = 0; r < NB; r++) b[r][lane] = x[r];
 }
 
-// trailing update of the lower triangle: C(ti, tj) -= P(ti) P(tj)^T for tiles ti >= tj behind the panel
-__global__ void __launch_bounds__(256) k_chol_update(double* S, int ld, int k0) {
-    __shared__ double pa[NB][NB + 1], pb[NB][NB + 1];
-    // linear tile index -> (ti, tj), ti >= tj
-    int t = blockIdx.x, ti = 0;
-    while (t >= ti + 1) { t -= ti + 1; ti++; }
-    const int tj = t;
-    const int r0 = k0 + NB + ti * NB, c0 = k0 + NB + tj * NB;
-    for (int i = threadIdx.x; i < NB * NB; i += 256) {
-        pa[i / NB][i % NB] = S[(size_t)(r0 + i / NB) * ld + k0 + i % NB];
-        pb[i / NB][i % NB] = S[(size_t)(c0 + i / NB) * ld + k0 + i % NB];
+__global__ void __launch_bounds__(CF_THREADS) k_chol_solve(double* S, int ld, double* v, double* linv, double* ok_flag, unsigned* bar) {
+    __shared__ double a[NB][NB + 1], b[NB][NB + 1];
+    __shared__ double xs[NB], dinv[NB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles = ld / NB;
+    const unsigned G = gridDim.x;
+    const int cta = blockIdx.x;
+#ifdef CSB_CHOL_DEBUG
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#endif
+    // CTA 0: factor the diagonal tile k0 (already updated) and store L_kk and its inverse
+    // CTA 0: L_kk = chol(S_kk) of the (already updated) diagonal tile in shared memory, all threads on the trailing part of every column,
+    // then its inverse; both go back to global memory
+    auto factor_diag = [&](int k) {
+        const int k0 = k * NB;
+        double* Lk = linv + (size_t)k * NB * NB;
+        __syncthreads();  // the CTA's update of this tile is complete
+        for (int i = tid; i < NB * NB; i += CF_THREADS) a[i / NB][i % NB] = S[(size_t)(k0 + i / NB) * ld + k0 + i % NB];
+        __syncthreads();
+        for (int j = 0; j < NB; j++) {
+            // every thread forms 1 / sqrt(d_jj) itself: one barrier less per column, the column is scaled by a multiplication
+            double d = a[j][j];
+            if (!(d > 0)) { if (tid == 0) *ok_flag = 0.0; d = 1.0; }
+            const double sd = sqrt(d), inv = 1.0 / sd;
+            __syncthreads();  // everyone has read a[j][j] and (previous column) finished the trailing update
+            if (tid == j) { a[j][j] = sd; dinv[j] = inv; }
+            else if (tid > j && tid < NB) a[tid][j] *= inv;
+            __syncthreads();
+            for (int idx = tid; idx < NB * NB; idx += CF_THREADS) {
+                const int r = idx >> 5, c = idx & 31;
+                if (c > j && c <= r) a[r][c] = fma(-a[r][j], a[c][j], a[r][c]);
+            }
+        }
+        __syncthreads();
+        if (warp == 0) tri_inverse_tile(a, b, dinv, lane);
+        __syncthreads();
+        for (int i = tid; i < NB * NB; i += CF_THREADS) {
+            const int r = i / NB, c = i % NB;
+            S[(size_t)(k0 + r) * ld + k0 + c] = (c <= r) ? a[r][c] : 0.0;
+            Lk[i] = b[r][c];
+        }
+        __threadfence();
+    };
+    if (cta == 0) factor_diag(0);
+    CHOL_T(0);
+    grid_barrier(bar, G);
+    CHOL_T(1);
+    for (int k = 0; k < tiles - 1; k++) {
+        const int k0 = k * NB;
+        const double* Lk = linv + (size_t)k * NB * NB;
+        // (2) L_ik = S_ik Linv^T : out[r][c] = sum_q S_ik[r][q] Linv[c][q]   (Linv lower: q <= c); a warp per row, lane = output column
+        {
+            __syncthreads();
+            for (int i = tid; i < NB * NB; i += CF_THREADS) b[i / NB][i % NB] = Lk[i];
+            __syncthreads();
+            const int n_rows = ld - k0 - NB;
+            for (int r = cta * (CF_THREADS / 32) + warp; r < n_rows; r += G * (CF_THREADS / 32)) {
+                double* p = S + (size_t)(k0 + NB + r) * ld + k0;
+                const double mine = p[lane];
+                double acc = 0;
+#pragma unroll
+                for (int q = 0; q < NB; q++) {
+                    const double sv = __shfl_sync(0xffffffffu, mine, q);
+                    acc = fma(sv, (q <= lane) ? b[lane][q] : 0.0, acc);
+                }
+                p[lane] = acc;
+            }
+        }
+        CHOL_T(2);
+        grid_barrier(bar, G);
+        CHOL_T(1);
+        // (3) trailing update, tiles (ti >= tj) behind the panel, strided over the CTAs; CTA 0 takes tile (0, 0) first -- the next diagonal
+        // tile -- and factors it at once, while the other CTAs are still updating
+        {
+            const int tt = tiles - k - 1;
+            const int n_t = tt * (tt + 1) / 2;
+            const int tx = tid & 15, ty = tid >> 4;
+            for (int t = cta; t < n_t; t += G) {
+                int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+                while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+                while (ti * (ti + 1) / 2 > t) ti--;
+                const int tj = t - ti * (ti + 1) / 2;
+                const int r0 = k0 + NB + ti * NB, c0 = k0 + NB + tj * NB;
+                __syncthreads();
+                for (int i = tid; i < NB * NB; i += CF_THREADS) {
+                    a[i / NB][i % NB] = S[(size_t)(r0 + i / NB) * ld + k0 + i % NB];
+                    b[i / NB][i % NB] = S[(size_t)(c0 + i / NB) * ld + k0 + i % NB];
+                }
+                __syncthreads();
+                double acc[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+                for (int q = 0; q < NB; q++) {
+                    const double a0 = a[ty][q], a1 = a[ty + 16][q], b0 = b[tx][q], b1 = b[tx + 16][q];
+                    acc[0][0] = fma(a0, b0, acc[0][0]); acc[0][1] = fma(a0, b1, acc[0][1]);
+                    acc[1][0] = fma(a1, b0, acc[1][0]); acc[1][1] = fma(a1, b1, acc[1][1]);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j2 = 0; j2 < 2; j2++) {
+                        const int r = r0 + ty + 16 * i, c = c0 + tx + 16 * j2;
+                        if (c <= r) S[(size_t)r * ld + c] -= acc[i][j2];
+                    }
+                if (t == 0) { CHOL_T(3); factor_diag(k + 1); CHOL_T(0); }  // (cta == 0)
+            }
+        }
+        CHOL_T(3);
+        grid_barrier(bar, G);
+        CHOL_T(1);
+    }
+    if (cta != 0) return;
+    // ---- the two triangular solves: CTA 0 alone (1.4 M multiply-adds; the lower triangle streams through once per direction)
+    // L y = r, block row by block row: y_i = Linv_ii (r_i - sum_{c < 32 i} L[row][c] y[c]); a warp per row, lanes over the columns (coalesced)
+    for (int k = 0; k < tiles; k++) {
+        const int k0 = k * NB;
+        const double* Lk = linv + (size_t)k * NB * NB;
+        __syncthreads();  // y of the previous block rows is in v
+        for (int rr = warp; rr < NB; rr += CF_THREADS / 32) {
+            const double* p = S + (size_t)(k0 + rr) * ld;
+            double t = 0;
+            for (int c = lane; c < k0; c += 32) t = fma(p[c], v[c], t);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0) xs[rr] = v[k0 + rr] - t;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const double rv = xs[lane];  // y_k = Linv r_k: lane = row
+            double acc = 0;
+#pragma unroll
+            for (int q = 0; q < NB; q++) acc = fma((q <= lane) ? Lk[lane * NB + q] : 0.0, __shfl_sync(0xffffffffu, rv, q), acc);
+            v[k0 + lane] = acc;
+        }
     }
     __syncthreads();
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    double acc[2][2] = {{0, 0}, {0, 0}};
+    CHOL_T(4);
+    // L^T x = y
+    for (int k = tiles - 1; k >= 0; k--) {
+        const int k0 = k * NB;
+        const double* Lk = linv + (size_t)k * NB * NB;
+        __syncthreads();
+        if (warp == 0) {
+            const double yv = v[k0 + lane];  // x_k = Linv^T y_k: lane = row r, sum over q >= r of Linv[q][r] y[q]
+            double acc = 0;
 #pragma unroll
-    for (int k = 0; k < NB; k++) {
-        const double a0 = pa[ty][k], a1 = pa[ty + 16][k], b0 = pb[tx][k], b1 = pb[tx + 16][k];
-        acc[0][0] = fma(a0, b0, acc[0][0]); acc[0][1] = fma(a0, b1, acc[0][1]);
-        acc[1][0] = fma(a1, b0, acc[1][0]); acc[1][1] = fma(a1, b1, acc[1][1]);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; i++)
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int r = r0 + ty + 16 * i, c = c0 + tx + 16 * j;
-            if (c <= r) S[(size_t)r * ld + c] -= acc[i][j];
-        }
-}
-
-// L y = r then L^T x = y; one CTA, in place in `v`
-__global__ void __launch_bounds__(1024) k_trsv(const double* S, int ld, double* v) {
-    __shared__ double xs[NB];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const unsigned FULL = 0xffffffffu;
-    for (int k0 = 0; k0 < ld; k0 += NB) {
-        if (tid < 32) {
-            double y = v[k0 + lane];
-            for (int c = 0; c < NB; c++) {
-                const double lcc = S[(size_t)(k0 + c) * ld + k0 + c];
-                const double yc = __shfl_sync(FULL, y, c) / lcc;
-                if (lane == c) y = yc;
-                else if (lane > c) y = fma(-S[(size_t)(k0 + lane) * ld + k0 + c], yc, y);
-            }
-            v[k0 + lane] = y;
-            xs[lane] = y;
+            for (int q = 0; q < NB; q++) acc = fma((q >= lane) ? Lk[q * NB + lane] : 0.0, __shfl_sync(0xffffffffu, yv, q), acc);
+            v[k0 + lane] = acc;
+            xs[lane] = acc;
         }
         __syncthreads();
-        for (int row = k0 + NB + tid; row < ld; row += blockDim.x) {
-            const double* p = S + (size_t)row * ld + k0;
-            double t = v[row];
-#pragma unroll
-            for (int c = 0; c < NB; c++) t = fma(-p[c], xs[c], t);
-            v[row] = t;
-        }
-        __syncthreads();
-    }
-    for (int k0 = ld - NB; k0 >= 0; k0 -= NB) {
-        if (tid < 32) {
-            double x = v[k0 + lane];
-            for (int c = NB - 1; c >= 0; c--) {
-                const double lcc = S[(size_t)(k0 + c) * ld + k0 + c];
-                const double xc = __shfl_sync(FULL, x, c) / lcc;
-                if (lane == c) x = xc;
-                else if (lane < c) x = fma(-S[(size_t)(k0 + c) * ld + k0 + lane], xc, x);
-            }
-            v[k0 + lane] = x;
-            xs[lane] = x;
-        }
-        __syncthreads();
-        for (int row = tid; row < k0; row += blockDim.x) {
+        for (int row = tid; row < k0; row += CF_THREADS) {
             double t = v[row];
 #pragma unroll
             for (int c = 0; c < NB; c++) t = fma(-S[(size_t)(k0 + c) * ld + row], xs[c], t);
             v[row] = t;
         }
-        __syncthreads();
     }
+    CHOL_T(5);
+#ifdef CSB_CHOL_DEBUG
+    if (tid == 0) printf("k_chol_solve cycles: diag %lld barrier %lld panel %lld update %lld fwd %lld bwd %lld\n", tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5]);
+#endif
 }
 
 // x_l = Ainv (b_l - sum_e H_pl(e)^T x_cam(e)), one thread per (cuboid, row) after a per-cuboid gather
@@ -410,6 +505,7 @@ __global__ void k_set_flag(double* p, double v) { *p = v; }
 // ---- host side ------------------------------------------------------------------------------------------------------
 struct SolveState {
     bool built = false;
+    int chol_ctas = 1;  // grid of the cooperative k_chol_solve: one CTA per SM, all resident
     SolveView V{};
     std::vector<void*> allocs;
 };
@@ -503,7 +599,15 @@ int build_solver(csb_context* c) {
     CSB_TRY(al(c, A, &V.S, (size_t)V.ld * V.ld)); CSB_TRY(al(c, A, &V.rhs, (size_t)V.ld)); CSB_TRY(al(c, A, &V.x_cube, 9 * (size_t)V.n_fl));
     CSB_TRY(al(c, A, &V.scal, 8)); CSB_TRY(al(c, A, &V.trial_cams7, 7 * (size_t)s.n_cam)); CSB_TRY(al(c, A, &V.trial_cubes10, 10 * (size_t)s.n_cube));
     CSB_TRY(al(c, A, &V.edge_chi2, (size_t)(s.n_ec + s.n_ep + s.n_eo)));
+    CSB_TRY(al(c, A, &V.linv, (size_t)V.ld * NB)); CSB_TRY(al(c, A, &V.bar, 4));
+    CSB_CUDA(c, cudaMemset(V.bar, 0, 16));
     V.x_cam = V.rhs;
+    {
+        int per_sm = 0;
+        CSB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chol_solve, CF_THREADS, 0));
+        if (per_sm < 1) { c->err = "k_chol_solve does not fit an SM"; return CSB_ERR_CUDA; }
+        st->chol_ctas = c->num_sms;
+    }
     st->built = true;
     return CSB_OK;
 }
@@ -539,7 +643,6 @@ extern "C" int csb_ba_optimize(csb_context* c, int iterations, double* cams7_out
     double chi_final = 0, h_scal[4] = {0, 0, 0, 0};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (stats) { CSB_CUDA(c, cudaEventCreate(&ev0)); CSB_CUDA(c, cudaEventCreate(&ev1)); CSB_CUDA(c, cudaEventRecord(ev0, sm)); }
-    const int tiles = V.ld / NB;
     for (int it = 0; it < iterations; it++) {
         int nl = 0;
         CSB_CUDA(c, ba_launch(B, false, sm, &nl, c->ba.analytic));  // computeActiveErrors + buildSystem at the current estimates
@@ -563,19 +666,12 @@ extern "C" int csb_ba_optimize(csb_context* c, int iterations, double* cams7_out
             if (V.n_fc) k_schur_rhs<<<(V.n + 127) / 128, 128, 0, sm>>>(B, V);
             k_schur_pad<<<1, NB, 0, sm>>>(V);
             launches += 6;
-            for (int k = 0; k < tiles; k++) {
-                const int k0 = k * NB;
-                k_chol_diag<<<1, dim3(NB, NB), 0, sm>>>(V.S, V.ld, k0, V.scal + 3);
+            {
+                double* a_S = V.S; int a_ld = V.ld; double* a_v = V.rhs; double* a_linv = V.linv; double* a_ok = V.scal + 3; unsigned* a_bar = V.bar;
+                void* args[] = {&a_S, &a_ld, &a_v, &a_linv, &a_ok, &a_bar};
+                CSB_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_chol_solve, dim3(st->chol_ctas), dim3(CF_THREADS), args, 0, sm));
                 launches++;
-                const int rest = V.ld - k0 - NB;
-                if (rest > 0) {
-                    k_chol_panel<<<(rest + 63) / 64, 64, 0, sm>>>(V.S, V.ld, k0);
-                    const int tt = rest / NB;
-                    k_chol_update<<<tt * (tt + 1) / 2, 256, 0, sm>>>(V.S, V.ld, k0);
-                    launches += 2;
-                }
             }
-            k_trsv<<<1, 1024, 0, sm>>>(V.S, V.ld, V.rhs);
             if (V.n_fl) k_cube_back<<<V.n_fl, 32, 0, sm>>>(B, V);
             k_apply<<<(s.n_cam + s.n_cube + 127) / 128, 128, 0, sm>>>(B, V);
             if (n_edges) k_edge_chi2<<<(n_edges + 127) / 128, 128, 0, sm>>>(B, V.trial_cams7, V.trial_cubes10, V.edge_chi2);
