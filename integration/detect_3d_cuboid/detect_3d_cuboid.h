@@ -1,13 +1,17 @@
 // Drop-in replacement for detect_3d_cuboid/include/detect_3d_cuboid/detect_3d_cuboid.h of the reference.
 //
 // Same class names, members, public flags and detect_cuboid() signature (reference header lines 20-41, 59-71, 74-118), so
-// object_slam/src/main_obj.cpp:492-500, 633-669 and detect_3d_cuboid/src/main.cpp:62-72 compile unchanged.  The sweep, scoring,
-// selection and 3D recovery run on the GPU through the C ABI of include/cubeslam_b200.h; cv::Canny + cv::distanceTransform
-// (box_proposal_detail.cpp:320-327) stay here because they are OpenCV, not CubeSLAM code.
+// object_slam/src/main_obj.cpp:492-500, 633-669 and detect_3d_cuboid/src/main.cpp:62-72 compile unchanged.  Everything inside
+// detect_cuboid() -- cv::Canny + cv::distanceTransform per box ROI (box_proposal_detail.cpp:320-327), the sweep, scoring, selection and
+// 3D recovery -- runs on the GPU through csb_detect_batch_gray() of include/cubeslam_b200.h; this header only converts types.
+// box_proposal_detail.cpp drops out of the build: set_calibration / set_cam_pose (:36-56) are defined here.
 //
-// NOT compiled in the build container (needs Eigen + OpenCV, which are absent there); see INTEGRATION.md.
+// Compiled by tests/test_adapters_compile.py against the interface stubs under tests/stubs/ (the build container has no Eigen / OpenCV).
 #pragma once
 
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -58,11 +62,33 @@ public:
     cam_pose_infos cam_pose;
     cam_pose_infos cam_pose_raw;
 
-    detect_3d_cuboid() { csb_create(&ctx_, 0); }
+    // The reference's constructor cannot fail; this one needs a CUDA device (there is no CPU fallback) and says so at once instead of
+    // returning empty ObjectSets later.
+    detect_3d_cuboid() {
+        if (csb_create(&ctx_, 0) != CSB_OK) throw std::runtime_error("detect_3d_cuboid (B200): no usable CUDA device");
+    }
     ~detect_3d_cuboid() { csb_destroy(ctx_); }
+    detect_3d_cuboid(const detect_3d_cuboid&) = delete;
+    detect_3d_cuboid& operator=(const detect_3d_cuboid&) = delete;
 
-    void set_calibration(const Eigen::Matrix3d& Kalib) { cam_pose.Kalib = Kalib; cam_pose.invK = Kalib.inverse(); }
-    void set_cam_pose(const Eigen::Matrix4d& transToWolrd);  // box_proposal_detail.cpp:45-56, unchanged (host)
+    void set_calibration(const Eigen::Matrix3d& Kalib) { cam_pose.Kalib = Kalib; cam_pose.invK = Kalib.inverse(); }  // box_proposal_detail.cpp:36-40
+    // box_proposal_detail.cpp:45-56 with quat_to_euler_zyx (matrix_utils.cpp:38-51) written out
+    void set_cam_pose(const Eigen::Matrix4d& transToWolrd)
+    {
+        cam_pose.transToWolrd = transToWolrd;
+        cam_pose.rotationToWorld = transToWolrd.topLeftCorner<3, 3>();
+        const Eigen::Quaterniond q(cam_pose.rotationToWorld);
+        const double qw = q.w(), qx = q.x(), qy = q.y(), qz = q.z();
+        Eigen::Vector3d euler_angles;
+        euler_angles(0) = atan2(2 * (qw * qx + qy * qz), 1 - 2 * (qx * qx + qy * qy));
+        euler_angles(1) = asin(2 * (qw * qy - qz * qx));
+        euler_angles(2) = atan2(2 * (qw * qz + qx * qy), 1 - 2 * (qy * qy + qz * qz));
+        cam_pose.euler_angle = euler_angles;
+        cam_pose.invR = cam_pose.rotationToWorld.inverse();
+        cam_pose.projectionMatrix = cam_pose.Kalib * transToWolrd.inverse().topRows<3>();  // project world coordinate to camera
+        cam_pose.KinvR = cam_pose.Kalib * cam_pose.invR;
+        cam_pose.camera_yaw = cam_pose.euler_angle(2);
+    }
 
     // Same contract as the reference: all_object_cuboids is resized to the number of boxes; each ObjectSet holds up to
     // max_cuboid_num new-ed cuboids (caller-owned, as in the reference); an empty ObjectSet means "nothing found".
@@ -94,20 +120,13 @@ public:
         if (csb_detect_plan(&fr, 1, boxes.data(), n_boxes, &p, nullptr, 0, &n_tasks, &n_map) != CSB_OK) return;
         std::vector<csb_task> tasks(n_tasks > 0 ? n_tasks : 1);
         csb_detect_plan(&fr, 1, boxes.data(), n_boxes, &p, tasks.data(), n_tasks, &n_tasks, &n_map);
-        std::vector<float> maps((size_t)n_map + 16, 0.f);
-        for (int t = 0; t < n_tasks; t++) {  // box_proposal_detail.cpp:320-327
-            cv::Rect roi(tasks[t].roi_left, tasks[t].roi_top, tasks[t].roi_width, tasks[t].roi_height);
-            cv::Mat im_canny, dist_map;
-            cv::Canny(gray(roi), im_canny, 80, 200);
-            cv::distanceTransform(255 - im_canny, dist_map, CV_DIST_L2, 3);
-            for (int r = 0; r < dist_map.rows; r++)
-                std::memcpy(&maps[tasks[t].map_offset + (size_t)r * dist_map.cols], dist_map.ptr<float>(r), sizeof(float) * dist_map.cols);
-        }
+        if (!gray.isContinuous()) gray = gray.clone();  // the library takes the whole frame, row-major, no padding
         std::vector<csb_cuboid> out((size_t)std::max(1, n_boxes * max_cuboid_num));
         std::vector<int32_t> n_out(std::max(1, n_boxes));
-        if (csb_detect_batch(ctx_, &fr, 1, boxes.data(), n_boxes, lines.data(), n_lines, tasks.data(), n_tasks, maps.data(), n_map, &p, out.data(),
-                             n_out.data(), nullptr) != CSB_OK)
-            return;  // like the reference: no exception, empty ObjectSets
+        // Canny (80, 200) + 3x3 L2 distance transform of every box ROI + the whole proposal path (box_proposal_detail.cpp:143-838) on the GPU
+        if (csb_detect_batch_gray(ctx_, &fr, 1, boxes.data(), n_boxes, lines.data(), n_lines, tasks.data(), n_tasks, gray.data, (int64_t)gray.total(), &p,
+                                  out.data(), n_out.data(), nullptr) != CSB_OK)
+            return;  // like the reference: no exception, empty ObjectSets (csb_last_error(ctx_) holds the reason)
         for (int b = 0; b < n_boxes; b++)
             for (int r = 0; r < n_out[b]; r++) {
                 const csb_cuboid& c = out[(size_t)b * max_cuboid_num + r];

@@ -7,9 +7,14 @@
 // Usage in object_slam/src/main_obj.cpp:512-517 (one changed line):
 //     g2o::BlockSolverX* solver_ptr = new g2o::CuboidBlockSolverB200(linearSolver);
 //
-// NOT compiled in the build container (needs Eigen + the vendored g2o); see INTEGRATION.md.
+// The vendored g2o stays UNPATCHED: the off-diagonal blocks are looked up in the solver's own _Hpp / _Hpl / _Hll (protected members of
+// BlockSolver, the very blocks buildStructure() mapped into the edges, block_solver.hpp:222-249).
+// Compiled by tests/test_adapters_compile.py against the interface stubs under tests/stubs/ (the build container has no Eigen / g2o build).
 #pragma once
 
+#include <algorithm>
+#include <map>
+#include <stdexcept>
 #include <vector>
 
 #include "Thirdparty/g2o/g2o/core/block_solver.h"
@@ -22,7 +27,9 @@ namespace g2o {
 
 class CuboidBlockSolverB200 : public BlockSolverX {
 public:
-    explicit CuboidBlockSolverB200(LinearSolverType* linearSolver) : BlockSolverX(linearSolver) { csb_create(&ctx_, 0); }
+    explicit CuboidBlockSolverB200(LinearSolverType* linearSolver) : BlockSolverX(linearSolver) {
+        if (csb_create(&ctx_, 0) != CSB_OK) throw std::runtime_error("CuboidBlockSolverB200: no usable CUDA device (there is no CPU fallback)");
+    }
     ~CuboidBlockSolverB200() { csb_destroy(ctx_); }
 
     // buildStructure() of the base class allocates Hpp blocks and maps them into vertices (diagonal) and edges (off-diagonal);
@@ -98,8 +105,7 @@ public:
             std::copy(&H_cube_[81 * i], &H_cube_[81 * i] + 81, cubes_[i]->hessianData());
             std::copy(&b_cube_[9 * i], &b_cube_[9 * i] + 9, cubes_[i]->bData());
         }
-        // off-diagonal blocks: the edge holds the mapped block (possibly transposed: base_binary_edge.hpp:207-218).  A small accessor
-        // (friend or public wrapper around _hessian/_hessianTransposed/_hessianRowMajor) has to be added to BaseBinaryEdge for this copy.
+        // off-diagonal blocks: written where buildStructure() mapped them for the edges (block_solver.hpp:222-249)
         for (size_t e = 0; e < ec_.size(); e++) writeOffDiagonal(ec_[e], &ec_Hij_[54 * e], 6, 9);
         for (size_t e = 0; e < ep_.size(); e++) writeOffDiagonal(ep_[e], &ep_Hij_[54 * e], 6, 9);
         for (size_t e = 0; e < eo_.size(); e++) writeOffDiagonal(eo_[e], &eo_Hij_[36 * e], 6, 6);
@@ -111,13 +117,24 @@ public:
     }
 
 private:
-    template <class Edge>
-    static void writeOffDiagonal(Edge* e, const double* blk, int di, int dj)
+    // blk = A^T Omega B of the edge (di x dj, column-major; A belongs to vertex 0).  The block g2o accumulates it into is found the way
+    // buildStructure() allocated it: upper block triangle of _Hpp for two poses (stored transposed when vertex 0 has the larger
+    // hessian index), _Hll for two marginalised vertices, _Hpl (pose row, landmark column) for a mixed pair.
+    void writeOffDiagonal(OptimizableGraph::Edge* e, const double* blk, int di, int dj)
     {
-        double* dst = e->mappedHessianData();          // accessor to add: returns the pointer given to mapHessianMemory()
-        if (!dst) return;                              // a vertex is fixed: no block
-        if (!e->mappedHessianRowMajor()) std::copy(blk, blk + di * dj, dst);
-        else for (int r = 0; r < di; r++) for (int c = 0; c < dj; c++) dst[r * dj + c] = blk[c * di + r];  // transposed block (dj x di, column-major)
+        OptimizableGraph::Vertex* v1 = static_cast<OptimizableGraph::Vertex*>(e->vertex(0));
+        OptimizableGraph::Vertex* v2 = static_cast<OptimizableGraph::Vertex*>(e->vertex(1));
+        int ind1 = v1->hessianIndex(), ind2 = v2->hessianIndex();
+        if (ind1 == -1 || ind2 == -1) return;  // a vertex is fixed: no block
+        bool transposed = ind1 > ind2;
+        if (transposed) std::swap(ind1, ind2);
+        double* dst = 0;
+        if (!v1->marginalized() && !v2->marginalized()) dst = _Hpp->block(ind1, ind2, false)->data();
+        else if (v1->marginalized() && v2->marginalized()) { dst = _Hll->block(ind1 - _numPoses, ind2 - _numPoses, false)->data(); transposed = false; }
+        else if (v1->marginalized()) { dst = _Hpl->block(v2->hessianIndex(), v1->hessianIndex() - _numPoses, false)->data(); transposed = true; }
+        else { dst = _Hpl->block(v1->hessianIndex(), v2->hessianIndex() - _numPoses, false)->data(); transposed = false; }
+        if (!transposed) std::copy(blk, blk + di * dj, dst);                                                  // di x dj, column-major
+        else for (int r = 0; r < di; r++) for (int c = 0; c < dj; c++) dst[r * dj + c] = blk[c * di + r];       // the dj x di transpose, column-major
     }
 
     csb_context* ctx_ = nullptr;
