@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdio>
 
 #include "proposal.h"
 #include "proposal_score.cuh"
@@ -830,11 +831,48 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(DetectBuffers B, int 
         // value vk is inside the heap (lessD == k-1) it is the top (the dropped k-th) and the set is exactly {d < vk}; otherwise
         // which of the tied elements stay depends on the heap -> replay.  With the angle filter off the kept list keeps
         // partial_sort's ORDER (:783-786): replay (it also yields the sorted order).
-        const bool need_emul = angle_active ? (lessD != k - 1) : true;
+        bool need_emul = angle_active ? (lessD != k - 1) : true;
         if (angle_active) {
             for (int i = tid; i < N; i += SELECT_THREADS) flag[i] = ((va[i] < vkA) ? 1 : 0) | ((!need_emul && vd[i] < vk) ? 2 : 0);
         }
         __syncthreads();
+        // Angle filter off, no tie at the boundary (exactly k - 1 distances below the k-th smallest) and no two equal values among them:
+        // std::partial_sort's prefix is then the ONE ascending order of those k - 1 elements, whatever the heap does -- sort them with the
+        // whole CTA (bitonic, keys in the angle array's storage) instead of replaying k sequential heap pops on one warp.  Any duplicate
+        // key sends the task to the literal replay below.
+        if (!angle_active && lessD == k - 1 && N <= n_cap) {
+            int m = 1;
+            while (m < k - 1) m <<= 1;
+            if (m <= n_cap) {
+                unsigned long long* keys = reinterpret_cast<unsigned long long*>(va);
+                if (tid == 0) s_bc[0] = 0;
+                __syncthreads();
+                const unsigned long long kk = ordered_key(vk);  // the same order the radix select counted in: exactly lessD = k - 1 keys are below
+                for (int i = tid; i < N; i += SELECT_THREADS) {
+                    const unsigned long long key = ordered_key(vd[i]);
+                    if (key < kk) { const int pos = atomicAdd(&s_bc[0], 1); keys[pos] = key; ibuf[pos] = i; }
+                }
+                for (int i = k - 1 + tid; i < m; i += SELECT_THREADS) { keys[i] = ~0ull; ibuf[i] = -1; }
+                __syncthreads();
+                for (int size = 2; size <= m; size <<= 1)
+                    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                        for (int t = tid; t < (m >> 1); t += SELECT_THREADS) {
+                            const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1)), hi = lo | stride;
+                            const bool up = (lo & size) == 0;
+                            const unsigned long long a = keys[lo], b = keys[hi];
+                            if ((a > b) == up) { keys[lo] = b; keys[hi] = a; const int ti = ibuf[lo]; ibuf[lo] = ibuf[hi]; ibuf[hi] = ti; }
+                        }
+                        __syncthreads();
+                    }
+                int dup = 0;
+                for (int p = tid; p + 1 < k - 1; p += SELECT_THREADS) dup |= (keys[p] == keys[p + 1]) ? 1 : 0;
+                if (!__syncthreads_or(dup)) {
+                    for (int p = tid; p < k - 1; p += SELECT_THREADS) keep[p] = ibuf[p];
+                    need_emul = false;
+                }
+                __syncthreads();
+            }
+        }
         if (need_emul) {
             // literal libstdc++ __heap_select (+ __sort_heap), warp-cooperative (proposal_dev.cuh); va / ibuf provide the storage
             heap.big = heap.hi + k;
