@@ -50,6 +50,153 @@ __global__ void __launch_bounds__(32) k_ed_draw(EdBuffers B, EdDims d) {
     if (threadIdx.x == 0) ed_draw(B, d, blockIdx.x);
 }
 
+// ---- smart routing, one WARP per frame (the production kernel; k_ed_draw above is the one-thread transcription the host emulation shares) -----
+// The walk is sequential -- every step reads the packed gradient of the pixel and of three neighbours and the `edge` bit, all dependent on
+// the previous step -- so its speed is the latency of those reads.  With the bitmap in global memory every step's read-modify-write
+// invalidates its L1 line and the next step's test goes to L2; here the frame's edge bitmap lives in shared memory (the gradient map is
+// read-only and stays L1-resident around the walk; a shared-memory window for it was measured slower: its reloads cost more than the L1
+// misses they save).  The 32 lanes execute the routing redundantly (identical registers, broadcast reads), lane 0 writes the bitmap,
+// walk pixels are staged in registers (lane n % 32 keeps pixel n) and leave as one coalesced store per 32 steps, and the chain assembly
+// (first part reversed + second part without the anchor) is a coalesced copy by all lanes.  Same results as ed_draw().
+struct EdWindow {
+    const uint16_t* gd;   // the frame's packed gradient map (read-only path: consecutive steps stay inside the same few L1 lines)
+    int W, H;
+};
+__device__ __forceinline__ void edw_ensure(EdWindow&, int, int, int) {}
+__device__ __forceinline__ uint16_t edw_at(const EdWindow& w, int x, int y) { return __ldg(w.gd + (size_t)y * w.W + x); }
+
+// one walk, warp-uniform; returns the pixels written to `out` (global, capacity cap)
+__device__ __forceinline__ int edw_walk(EdWindow& w, uint32_t* edge, unsigned x, unsigned y, int lastDirection, ushort2* out, int cap, EdWalkState& st, int lane) {
+    const int W = w.W, H = w.H;
+    int n = 0;
+    ushort2 mine = make_ushort2(0, 0);
+    while (true) {
+        edw_ensure(w, (int)x, (int)y, lane);
+        const int idx = (int)(y * (unsigned)W + x);
+        const uint16_t cur = edw_at(w, (int)x, (int)y);
+        if (!(ed_g(cur) > 0 && !((edge[idx >> 5] >> (idx & 31)) & 1u))) break;
+        __syncwarp();
+        if (lane == 0) edge[idx >> 5] |= 1u << (idx & 31);
+        if ((n & 31) == lane) mine = make_ushort2((unsigned short)x, (unsigned short)y);
+        n++;
+        if ((n & 31) == 0) { const int o = n - 32 + lane; if (o < cap) out[o] = mine; }
+        __syncwarp();
+        int shouldGo = 0;
+#define EDW_GV(dx, dy) ((unsigned char)ed_g(edw_at(w, (int)x + (dx), (int)y + (dy))))
+        if (ed_horizontal(cur)) {
+            if (lastDirection == ED_UP || lastDirection == ED_DOWN) shouldGo = (x > st.lastX) ? ED_RIGHT : ED_LEFT;
+            st.lastX = x; st.lastY = y;
+            if (lastDirection == ED_RIGHT || shouldGo == ED_RIGHT) {
+                if (x == (unsigned)W - 1 || y == 0 || y == (unsigned)H - 1) break;
+                const unsigned char g1 = EDW_GV(1, -1), g2 = EDW_GV(1, 0), g3 = EDW_GV(1, 1);
+                if (g1 >= g2 && g1 >= g3) { x = x + 1; y = y - 1; }
+                else if (g3 >= g2 && g3 >= g1) { x = x + 1; y = y + 1; }
+                else { x = x + 1; }
+                lastDirection = ED_RIGHT;
+            } else if (lastDirection == ED_LEFT || shouldGo == ED_LEFT) {
+                if (x == 0 || y == 0 || y == (unsigned)H - 1) break;
+                const unsigned char g1 = EDW_GV(-1, -1), g2 = EDW_GV(-1, 0), g3 = EDW_GV(-1, 1);
+                if (g1 >= g2 && g1 >= g3) { x = x - 1; y = y - 1; }
+                else if (g3 >= g2 && g3 >= g1) { x = x - 1; y = y + 1; }
+                else { x = x - 1; }
+                lastDirection = ED_LEFT;
+            }
+        } else {
+            if (lastDirection == ED_RIGHT || lastDirection == ED_LEFT) shouldGo = (y > st.lastY) ? ED_DOWN : ED_UP;
+            st.lastX = x; st.lastY = y;
+            if (lastDirection == ED_DOWN || shouldGo == ED_DOWN) {
+                if (x == 0 || x == (unsigned)W - 1 || y == (unsigned)H - 1) break;
+                const unsigned char g1 = EDW_GV(1, 1), g2 = EDW_GV(0, 1), g3 = EDW_GV(-1, 1);
+                if (g1 >= g2 && g1 >= g3) { x = x + 1; y = y + 1; }
+                else if (g3 >= g2 && g3 >= g1) { x = x - 1; y = y + 1; }
+                else { y = y + 1; }
+                lastDirection = ED_DOWN;
+            } else if (lastDirection == ED_UP || shouldGo == ED_UP) {
+                if (x == 0 || x == (unsigned)W - 1 || y == 0) break;
+                const unsigned char g1 = EDW_GV(1, -1), g2 = EDW_GV(0, -1), g3 = EDW_GV(-1, -1);
+                if (g1 >= g2 && g1 >= g3) { x = x + 1; y = y - 1; }
+                else if (g3 >= g2 && g3 >= g1) { x = x - 1; y = y - 1; }
+                else { y = y - 1; }
+                lastDirection = ED_UP;
+            }
+        }
+#undef EDW_GV
+    }
+    // the staged tail
+    if (n & 31) { const int o = (n & ~31) + lane; if (lane < (n & 31) && o < cap) out[o] = mine; }
+    __syncwarp();
+    return n;
+}
+
+__global__ void __launch_bounds__(32) k_ed_draw_warp(EdBuffers B, EdDims d) {
+    extern __shared__ __align__(16) unsigned char ed_smem[];
+    uint32_t* edge = reinterpret_cast<uint32_t*>(ed_smem);
+    const int frame = blockIdx.x, lane = threadIdx.x;
+    const int W = d.w, H = d.h;
+    const uint32_t* anc = B.anchors + (size_t)frame * d.anchor_words;
+    ushort2* p1 = B.part1 + (size_t)frame * d.part_cap;
+    ushort2* p2 = B.part2 + (size_t)frame * d.part_cap;
+    ushort2* chain = B.chain_px + (size_t)frame * d.chain_cap;
+    int* sid = B.chain_sid + (size_t)frame * (d.max_edges + 2);
+    for (int i = lane; i < d.edge_words; i += 32) edge[i] = 0;
+    EdWindow w{B.gd + (size_t)frame * W * H, W, H};
+    __syncwarp();
+    EdWalkState st{0u, 0u};
+    int n_chains = 0, n_px = 0;
+    long long kept1 = 0, kept2 = 0;
+    bool overflow = false;
+    unsigned long long n_anchor = 0;
+    const int n_cand = d.nxc * d.nyc;
+    for (int w0 = 0; w0 < d.anchor_words; w0 += 32) {
+        // 32 words of the anchor bitmap per load; skip empty stretches at once
+        const uint32_t my_bits = (w0 + lane < d.anchor_words) ? anc[w0 + lane] : 0u;
+        unsigned nonzero = __ballot_sync(0xffffffffu, my_bits != 0);
+        while (nonzero) {
+            const int wl = __ffs(nonzero) - 1;
+            nonzero &= nonzero - 1;
+            uint32_t bits = __shfl_sync(0xffffffffu, my_bits, wl);
+            const int wi = w0 + wl;
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int item = wi * 32 + b;
+                if (item >= n_cand) break;
+                n_anchor++;
+                const int i = item / d.nyc, j = item - i * d.nyc;
+                const unsigned x = 1 + 2 * i, y = 1 + 2 * j;
+                const int idx = (int)(y * (unsigned)W + x);
+                if ((edge[idx >> 5] >> (idx & 31)) & 1u) continue;
+                edw_ensure(w, (int)x, (int)y, lane);
+                const bool horiz = ed_horizontal(edw_at(w, (int)x, (int)y));
+                const int len1 = edw_walk(w, edge, x, y, horiz ? ED_RIGHT : ED_DOWN, p1, d.part_cap, st, lane);
+                __syncwarp();
+                if (lane == 0) edge[idx >> 5] &= ~(1u << (idx & 31));  // the anchor starts the second part too
+                __syncwarp();
+                const int len2 = edw_walk(w, edge, x, y, horiz ? ED_LEFT : ED_UP, p2, d.part_cap, st, lane);
+                if (len1 + len2 < ED_MIN_LINE_LEN + 1) continue;  // short edge: pixels stay marked, chain dropped
+                kept1 += len1; kept2 += len2;
+                if (len1 > d.part_cap || len2 > d.part_cap || n_chains >= d.max_edges + 1 || n_px + len1 + len2 - 1 > d.chain_cap) { overflow = true; continue; }
+                if (lane == 0) sid[n_chains] = n_px;
+                n_chains++;
+                __syncwarp();  // the walk's global stores are visible to the whole warp (same CTA: ordered after the barrier)
+                __threadfence_block();
+                for (int t = lane; t < len1; t += 32) chain[n_px + t] = p1[len1 - 1 - t];
+                for (int t = 1 + lane; t < len2; t += 32) chain[n_px + len1 + t - 1] = p2[t];
+                n_px += len1 + len2 - 1;
+                __syncwarp();
+            }
+        }
+    }
+    if (lane != 0) return;
+    // EdgeDrawing's capacity errors (:2329-2341) abort the detection of the frame ("Line Detection not finished")
+    if (overflow || n_chains > d.max_edges || kept1 > d.part_cap || kept2 > d.part_cap) { B.n_chains[frame] = -1; return; }
+    sid[n_chains] = n_px;
+    B.n_chains[frame] = n_chains;
+    atomicAdd(B.stats + 0, n_anchor);
+    atomicAdd(B.stats + 1, (unsigned long long)n_px);
+    atomicAdd(B.stats + 2, (unsigned long long)n_chains);
+}
+
 __global__ void __launch_bounds__(64) k_ed_fit(EdBuffers B, EdDims d) {
     const int chain = blockIdx.x * blockDim.x + threadIdx.x, frame = blockIdx.y;
     if (chain < B.n_chains[frame]) ed_fit(B, d, frame, chain);
@@ -182,13 +329,23 @@ int csb_edlines_run(csb_context* c, int timed) {
     cudaStream_t st = c->stream;
     const size_t npx = (size_t)d.w * d.h * d.n_frames;
     CSB_CUDA(c, cudaMemsetAsync(s.d_stats.p, 0, 64, st));
-    CSB_CUDA(c, cudaMemsetAsync(s.d_edge.p, 0, (size_t)d.n_frames * d.edge_words * 4, st));
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[0], st));
     lbd_launch_grad(s.d_gray.as<uint8_t>(), s.d_grad.as<short2>(), d.w, d.h, d.n_frames, st, c->blur_generation);
     k_ed_pixel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(B, d, npx);
     k_ed_anchor<<<dim3((d.anchor_words + 127) / 128, d.n_frames), 128, 0, st>>>(B, d);
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[1], st));
-    k_ed_draw<<<d.n_frames, 32, 0, st>>>(B, d);
+    {
+        // the warp-per-frame kernel keeps the frame's edge bitmap in shared memory; a frame whose bitmap does not fit (> ~1.8 Mpx) takes
+        // the one-thread transcription with the bitmap in global memory
+        const size_t smem = 4 * (size_t)((d.edge_words + 3) & ~3);
+        if (smem <= (size_t)c->max_smem_optin - 1024) {
+            CSB_CUDA(c, cudaFuncSetAttribute(k_ed_draw_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_ed_draw_warp<<<d.n_frames, 32, smem, st>>>(B, d);
+        } else {
+            CSB_CUDA(c, cudaMemsetAsync(s.d_edge.p, 0, (size_t)d.n_frames * d.edge_words * 4, st));
+            k_ed_draw<<<d.n_frames, 32, 0, st>>>(B, d);
+        }
+    }
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[2], st));
     k_ed_fit<<<dim3((d.max_edges + 1 + 63) / 64, d.n_frames), 64, 0, st>>>(B, d);
     k_ed_emit<<<d.n_frames, 32, 0, st>>>(B, d, s.params.filter, s.params.line_length_thres, s.params.max_lines);
