@@ -37,7 +37,7 @@ int main(int argc, char** argv)
         // R^-1 R = I, K invR consistent, euler angles of this pose: roll = atan2(R21, R22) (zyx)
         Eigen::Matrix3d I = det.cam_pose.invR * det.cam_pose.rotationToWorld;
         for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) CHECK(std::fabs(I(i, j) - (i == j)) < 1e-12);
-        CHECK(std::fabs(det.cam_pose.euler_angle(0) - std::atan2(T(2, 1), T(2, 2))) < 1e-6);
+        CHECK(std::fabs(det.cam_pose.euler_angle(0) - std::atan2(T(2, 1), T(2, 2))) < 1e-3);   // (the demo pose is rounded to four digits: not exactly orthonormal)
         CHECK(std::fabs(det.cam_pose.camera_yaw - det.cam_pose.euler_angle(2)) == 0);
         Eigen::Matrix<double, 3, 4> P = det.cam_pose.projectionMatrix;
         Eigen::Matrix<double, 4, 1> cam_centre(T(0, 3), T(1, 3), T(2, 3), 1.0);
