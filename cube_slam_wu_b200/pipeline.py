@@ -117,8 +117,16 @@ def run_config5(n_frames_total=10000, depth=6, ctx=None, keep=False, pose_noise=
             c.synchronize()
 
     frames_stage(min(S, 2 * depth), obs)  # warm-up
+    # every rank's camera poses (input metadata of the synthetic frames: 64 x 7 doubles) go to every rank up front; the exchange also
+    # brings up the NCCL communicator, so that the timed all_gather below measures the collective and not its lazy initialisation
+    poses_mine = torch.from_numpy(np.array([graph.pose7_from_matrix(T) for T in batch["T"]])).cuda()
     if world > 1:
+        poses_all_t = torch.empty(world, F, 7, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(poses_all_t.view(-1), poses_mine.view(-1))
         dist.barrier()
+    else:
+        poses_all_t = poses_mine.view(1, F, 7)
+    poses_all = poses_all_t.cpu().numpy()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     frames_stage(S, obs)
@@ -150,11 +158,7 @@ def run_config5(n_frames_total=10000, depth=6, ctx=None, keep=False, pose_noise=
     if rank == 0:
         t0 = time.perf_counter()
         flat, n_landmarks = graph.globalise_records(rec, F, n_boxes)
-        poses = []
-        for r in range(world):
-            b = batch if r == 0 else synth.make_kitti_batch(F, boxes_per_frame=BPF, seed=seed + r, poses_only=True)
-            poses.append(np.array([graph.pose7_from_matrix(T) for T in b["T"]]))
-        cams_true = np.concatenate([np.tile(poses[r], (S, 1)) for r in range(world)])
+        cams_true = np.concatenate([np.tile(poses_all[r], (S, 1)) for r in range(world)])
         cams_est = perturb_poses(cams_true, pose_noise[0], pose_noise[1], seed + 77) if pose_noise else None
         g = graph.assemble_graph(flat, cams_true, n_landmarks, cams_est_wc7=cams_est)
         t_assemble = time.perf_counter() - t0
