@@ -45,6 +45,8 @@ def build(force=False, verbose=False):
     objs = []
     procs = []
     extra = ["-DCSB_SCORE_PHASES"] if os.environ.get("CSB_SCORE_PHASES") == "1" else []  # per-phase cycle counters of k_score (tools/score_phases.py)
+    if os.environ.get("CSB_DM_PHASES") == "1":
+        extra.append("-DCSB_DM_PHASES")  # per-task stage cycles of k_distmap (tools/distmap_phases.py)
     if os.environ.get("CSB_CHOL_DEBUG") == "1":
         extra.append("-DCSB_CHOL_DEBUG")  # k_chol_solve prints its per-phase cycle counts
     for src in CU_SOURCES + CPP_SOURCES:

@@ -248,7 +248,7 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
         d.line_cap_total = std::max<int64_t>(d.line_cap_total, (int64_t)t.line_cap_offset + (frames[t.frame_id].line_end - frames[t.frame_id].line_begin));
         d.max_hyp_per_task = std::max(d.max_hyp_per_task, t.n_hyp);
         d.max_roi_w = std::max(d.max_roi_w, t.roi_w);
-        d.max_roi_px = std::max(d.max_roi_px, ((t.roi_w + 15) >> 4) * t.roi_h);  // words of the packed edge map
+        d.max_roi_px = std::max(d.max_roi_px, (((t.roi_w + 15) >> 4) + 1) * t.roi_h);  // words of the packed edge map, + 1 per row: k_distmap overlays its edge-bit rows and carries
     }
     if (n_tasks) std::memcpy(h_ttab, d.ttab.data(), sizeof(TaskTab) * (size_t)n_tasks);
     // task queue: tasks whose slice arrives first go first; inside a slice the biggest first

@@ -34,342 +34,398 @@
 
 namespace csb {
 
-constexpr int CN_THREADS = 256;
-constexpr int CN_ROWS = 16;
-
-// Sobel 3x3 (cv::Sobel ksize 3, scale 1) at strip position (y, x) of the byte strip g
-__device__ __forceinline__ void sobel_s(const uint8_t* g, int pitch, int y, int x, int& dx, int& dy) {
-    const uint8_t* p = g + (y - 1) * pitch + (x - 1);
-    const int a = p[0], b = p[1], c = p[2];
-    const int d = p[pitch], f = p[pitch + 2];
-    const int q = p[2 * pitch], h = p[2 * pitch + 1], i = p[2 * pitch + 2];
-    dx = (c + 2 * f + i) - (a + 2 * d + q);
-    dy = (q + 2 * h + i) - (a + 2 * b + c);
-}
-
-__global__ void __launch_bounds__(CN_THREADS) k_canny(DetectBuffers B, const uint8_t* gray, uint8_t* cmap, int* queue, int low, int high, int pm_words_cap, int wp_cap) {
-    extern __shared__ __align__(16) unsigned char cn_smem[];
-    const int task = blockIdx.x, tid = threadIdx.x;
-    const int tx = tid & 31, ty = tid >> 5;  // 8 row groups x 32 column groups
-    const TaskTab t = B.ttab[task];
-    const FrameTab& ft = B.ftab[t.frame_id];
-    const uint8_t* img = gray + ft.gray_offset;
-    const int IW = ft.img_w, IH = ft.img_h;
-    const int W = t.roi_w, H = t.roi_h;
-    const int Wp = (W + 15) & ~15, WPR = Wp >> 4;
-    const int GP = wp_cap + 8;   // gray strip pitch (bytes): column index = ROI column + 4
-    const int MP = wp_cap + 8;   // magnitude strip pitch (u16)
-    unsigned* pm = reinterpret_cast<unsigned*>(cn_smem);                                   // packed map, H * WPR words
-    uint8_t* gs = cn_smem + 4 * (size_t)pm_words_cap;                                      // (CN_ROWS + 4) x GP bytes
-    unsigned short* ms = reinterpret_cast<unsigned short*>(gs + (size_t)(CN_ROWS + 4) * GP);  // (CN_ROWS + 2) x MP u16
-    unsigned* gs32 = reinterpret_cast<unsigned*>(gs);
-    unsigned* ms32 = reinterpret_cast<unsigned*>(ms);
-    uint8_t* pm8 = reinterpret_cast<uint8_t*>(pm);
-    __shared__ int s_tail, s_head, s_end;
-    int* q = queue + t.map_offset;
-    const int TG22 = (int)(0.4142135623730950488016887242097 * (1 << 15) + 0.5);
-    if (tid == 0) { s_tail = 0; s_head = 0; }
-    const int G4 = (Wp + 8) >> 2;  // 4-byte groups per gray strip row that are actually used
-    const int NG = Wp >> 2;        // 4-pixel groups per ROI row
-    for (int r0 = 0; r0 < H; r0 += CN_ROWS) {
-        const int rows = min(CN_ROWS, H - r0);
-        __syncthreads();  // previous strip fully consumed
-        // (1) gray strip: strip row sr <-> ROI row r0 - 2 + sr, byte column u <-> ROI column u - 4; BORDER_REPLICATE at the image border
-        for (int sr = ty; sr < rows + 4; sr += 8) {
-            const int y = min(max(t.roi_top + r0 - 2 + sr, 0), IH - 1);
-            const uint8_t* row = img + (size_t)y * IW;
-            for (int g = tx; g < G4; g += 32) {
-                const int x0 = t.roi_left + 4 * g - 4;
-                unsigned w = 0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) w |= (unsigned)row[min(max(x0 + k, 0), IW - 1)] << (8 * k);
-                gs32[(sr * GP >> 2) + g] = w;
-            }
-        }
-        __syncthreads();
-        // (2) L1 gradient magnitude of ROI rows r0 - 1 .. r0 + rows (0 outside the ROI: the zero border of Canny's magnitude buffer);
-        //     strip row mr <-> ROI row r0 - 1 + mr, u16 column index = ROI column + 4
-        for (int mr = ty; mr < rows + 2; mr += 8) {
-            const int r = r0 - 1 + mr;
-            const bool row_in = r >= 0 && r < H;
-            if (tx == 0) { ms32[(mr * MP >> 1) + 0] = 0; ms32[(mr * MP >> 1) + 1] = 0; }  // columns -4 .. -1
-            for (int g = tx; g < NG + 1; g += 32) {
-                unsigned lo = 0, hi = 0;
-                if (row_in && g < NG) {
-                    int s1[6], tt[6];
-                    const unsigned* r0p = gs32 + ((mr + 0) * GP >> 2) + g;  // gray rows r-1, r, r+1 are strip rows mr, mr+1, mr+2
-                    const unsigned* r1p = gs32 + ((mr + 1) * GP >> 2) + g;
-                    const unsigned* r2p = gs32 + ((mr + 2) * GP >> 2) + g;
-                    const unsigned a0 = r0p[0], a1 = r0p[1], a2 = r0p[2], b0 = r1p[0], b1 = r1p[1], b2 = r1p[2], c0w = r2p[0], c1 = r2p[1], c2 = r2p[2];
-#pragma unroll
-                    for (int x = 0; x < 6; x++) {
-                        // window column x <-> ROI column 4g - 1 + x: byte 3 of word g, bytes 0..3 of word g+1, byte 0 of word g+2
-                        const int top = (x == 0) ? (a0 >> 24) : (x == 5) ? (a2 & 255u) : ((a1 >> (8 * (x - 1))) & 255u);
-                        const int mid = (x == 0) ? (b0 >> 24) : (x == 5) ? (b2 & 255u) : ((b1 >> (8 * (x - 1))) & 255u);
-                        const int bot = (x == 0) ? (c0w >> 24) : (x == 5) ? (c2 & 255u) : ((c1 >> (8 * (x - 1))) & 255u);
-                        s1[x] = top + 2 * mid + bot;
-                        tt[x] = bot - top;
-                    }
-                    unsigned m4[4];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int dx = s1[k + 2] - s1[k], dy = tt[k] + 2 * tt[k + 1] + tt[k + 2];
-                        m4[k] = (4 * g + k < W) ? (unsigned)(abs(dx) + abs(dy)) : 0u;
-                    }
-                    lo = m4[0] | (m4[1] << 16); hi = m4[2] | (m4[3] << 16);
-                }
-                const int wi = (mr * MP >> 1) + 2 + 2 * g;  // u16 column 4g + 4
-                ms32[wi] = lo; ms32[wi + 1] = hi;           // g == NG writes the zero columns Wp .. Wp + 3
-            }
-        }
-        __syncthreads();
-        // (3) non-maximum suppression of ROI rows r0 .. r0 + rows - 1; one thread per 4 pixels = one byte of the packed map
-        for (int rr = ty; rr < rows; rr += 8) {
-            const int r = r0 + rr, mr = rr + 1;
-            for (int g = tx; g < NG; g += 32) {
-                // magnitudes of columns 4g - 2 .. 4g + 5 on rows r-1, r, r+1 (u16 columns 4g + 2 .. 4g + 9 -> words 2g + 1 .. 2g + 4)
-                unsigned up[4], md[4], dn[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    up[k] = ms32[((mr - 1) * MP >> 1) + 2 * g + 1 + k];
-                    md[k] = ms32[(mr * MP >> 1) + 2 * g + 1 + k];
-                    dn[k] = ms32[((mr + 1) * MP >> 1) + 2 * g + 1 + k];
-                }
-                auto at = [](const unsigned* w, int x) -> int { return (int)((w[x >> 1] >> (16 * (x & 1))) & 0xffffu); };  // x = column - (4g - 2)
-                unsigned bits = 0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int c = 4 * g + k, x = k + 2;
-                    const int m = at(md, x);
-                    unsigned v = 1;
-                    if (m > low) {  // implies c < W (magnitude 0 beyond the ROI)
-                        int xs, ys;
-                        sobel_s(gs, GP, rr + 2, c + 4, xs, ys);
-                        const int ax = abs(xs), ay = abs(ys) << 15;
-                        const int tg22x = ax * TG22;
-                        bool keep;
-                        if (ay < tg22x) keep = (m > at(md, x - 1)) && (m >= at(md, x + 1));
-                        else {
-                            const int tg67x = tg22x + (ax << 16);
-                            if (ay > tg67x) keep = (m > at(up, x)) && (m >= at(dn, x));
-                            else {
-                                const bool neg = (xs ^ ys) < 0;  // s = -1
-                                const int mu = neg ? at(up, x + 1) : at(up, x - 1), mdn = neg ? at(dn, x - 1) : at(dn, x + 1);
-                                keep = (m > mu) && (m > mdn);
-                            }
-                        }
-                        if (keep) {
-                            v = (m > high) ? 2u : 0u;
-                            if (v == 2u) q[atomicAdd(&s_tail, 1)] = (r << 16) | c;
-                        }
-                    }
-                    bits |= v << (2 * k);
-                }
-                pm8[(size_t)r * (WPR * 4) + g] = (uint8_t)bits;
-            }
-        }
-    }
-    __syncthreads();
-    // (4) hysteresis: breadth-first promotion of weak pixels 8-connected to edge pixels
-    while (true) {
-        if (tid == 0) s_end = s_tail;
-        __syncthreads();
-        const int head = s_head, end = s_end;
-        if (head >= end) break;
-        for (int e = head + tid; e < end; e += CN_THREADS) {
-            const int rc = q[e];
-            const int r = rc >> 16, c = rc & 0xffff;
-#pragma unroll
-            for (int dr = -1; dr <= 1; dr++)
-#pragma unroll
-                for (int dc = -1; dc <= 1; dc++) {
-                    const int rr = r + dr, cc = c + dc;
-                    if ((dr | dc) == 0 || rr < 0 || cc < 0 || rr >= H || cc >= W) continue;
-                    unsigned* w = pm + rr * WPR + (cc >> 4);
-                    const int sh = 2 * (cc & 15);
-                    if (((*w >> sh) & 3u) != 0) continue;
-                    const unsigned old = atomicOr(w, 2u << sh);
-                    if (((old >> sh) & 3u) == 0) q[atomicAdd(&s_tail, 1)] = (rr << 16) | cc;
-                }
-        }
-        __syncthreads();
-        if (tid == 0) s_head = end;
-        __syncthreads();
-    }
-    // (5) packed map -> global
-    unsigned* out = reinterpret_cast<unsigned*>(cmap + 4 * (size_t)t.map_offset);
-    for (int i = tid; i < H * WPR; i += CN_THREADS) out[i] = pm[i];
-}
+constexpr int DM_THREADS = 256;
+constexpr int DM_WARPS = DM_THREADS / 32;
+constexpr int DM_COLS = 120;  // ROI columns a warp produces per row: lanes 1..30 x 4 pixels (lanes 0 and 31 only supply the magnitude halo)
 
 constexpr unsigned DT_HV = 62587u;                 // cvRound(0.955f  * 65536)
 constexpr unsigned DT_DG = 89738u;                 // cvRound(1.3693f * 65536)
 constexpr unsigned DT_MAX = 0xffffffffu - DT_DG;   // DIST_MAX; also used for the border cells (behaves like OpenCV's INIT_DIST0)
-constexpr int DT_WARPS = 4;            // warps per CTA = per task
-constexpr int DT_THREADS = 32 * DT_WARPS;
-constexpr int DT_STRIP = 8;            // rows per TMA strip of the backward pass
 constexpr int DT_INF = 0x3fffffff;     // "no path yet" inside the kernel (32-bit arithmetic); becomes DT_MAX on output
 
-// One CTA (4 warps) per task; thread t owns columns [t*CH, t*CH + CH).  The previous row lives in registers; each row is a
-// min-plus scan:  forward  d[j] = min_{m<=j} (c[m] - a m) + a j,   backward  d[j] = min_{m>=j} (c[m] + a m) - a j
-// (a = DT_HV; c = 0 on edge pixels, else the 3-neighbour minimum over the already finished adjacent row): sequential inside the
-// thread's chunk, warp shuffles across lanes, one shared-memory exchange across the 4 warps; two barriers per row.
-// 32-bit arithmetic: OpenCV saturates unreachable cells at DIST_MAX (~2^32); with at least one edge pixel in the ROI every final
-// value is a real path length (< 2^27 for ROIs up to 1280 px), and saturated cells only ever lose comparisons, so any "infinity"
-// that survives the additions gives the same result.  A ROI without edge pixels ends at DT_INF everywhere -> DIST_MAX, as in OpenCV.
-// The chunk size CH (2 / 3 / 4 / 10 columns per thread) is chosen per task from its ROI width; all classes run in one launch.
-template <int CH>
-__device__ __forceinline__ void dist3x3_cta(const TaskTab& t, const uint8_t* cmap, int* dtmp, float* maps, int tid, int (*s_tot)[DT_WARPS], int (*s_edge)[2 * DT_WARPS],
-                                            unsigned* s_pm, int* s_strip, int buf_stride, uint64_t* s_bar) {
-    const int W = t.roi_w, H = t.roi_h;
-    const int WPR = (W + 15) >> 4;
-    int* tmp = dtmp + t.map_offset;
-    float* out = maps + t.map_offset;
-    const float scale = 1.f / 65536.f;
+// gray bytes (y, x .. x+3) of a frame as one word, BORDER_REPLICATE at the image border, assembled byte by byte: only for words that
+// straddle the left / right image border (everything else goes through two aligned word loads + a funnel shift, see k_distmap)
+__device__ __noinline__ unsigned load_gray4_border(const uint8_t* __restrict__ row, int IW, int x) {
+    unsigned w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) w |= (unsigned)row[min(max(x + k, 0), IW - 1)] << (8 * k);
+    return w;
+}
+
+// 16 bits -> the even bit positions of a word
+__device__ __forceinline__ unsigned spread16(unsigned x) {
+    x &= 0xffffu;
+    x = (x | (x << 8)) & 0x00ff00ffu;
+    x = (x | (x << 4)) & 0x0f0f0f0fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+
+// The two vertical sweeps of the distance transform (see k_distmap), thread = column x = tid + k * DM_THREADS.
+template <int CPT>
+__device__ __forceinline__ void dt_sweeps(int W, int H, int WPE, const unsigned* Sb, int* rowD, int* rowU, int WB, int* __restrict__ tmpD, int* __restrict__ tmpU, int tid) {
     const int HV = (int)DT_HV, DG = (int)DT_DG;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int j0 = tid * CH;
-    const unsigned FULL = 0xffffffffu;
-    {
-        const unsigned* gpm = reinterpret_cast<const unsigned*>(cmap + 4 * (size_t)t.map_offset);
-        for (int i = tid; i < H * WPR; i += DT_THREADS) s_pm[i] = gpm[i];
-    }
-    int prev[CH];
-    // ---- forward pass
+    int dprev[CPT], uprev[CPT];
 #pragma unroll
-    for (int k = 0; k < CH; k++) prev[k] = DT_INF;  // row -1 = border
-    if (tid < 2 * DT_WARPS) { s_edge[0][tid] = DT_INF; s_edge[1][tid] = DT_INF; }
-    __syncthreads();
+    for (int k = 0; k < CPT; k++) { dprev[k] = DT_INF; uprev[k] = DT_INF; }
+    const unsigned* ed = Sb + (tid >> 5);                  // word of column tid in row 0; column tid + 256 k is 8 k words further
+    const unsigned* eu = Sb + (H - 1) * WPE + (tid >> 5);
+    const int sh = tid & 31;
+    int* gd = tmpD + tid;
+    int* gu = tmpU + (size_t)(H - 1) * W + tid;
+    int off_c = 0, off_p = WB;  // row buffers: current / previous parity
     for (int i = 0; i < H; i++) {
-        const int par = i & 1;
-        // neighbours' boundary cells of the previous row: by shuffle inside the warp, through s_edge across warps
-        int pl = __shfl_up_sync(FULL, prev[CH - 1], 1), pr = __shfl_down_sync(FULL, prev[0], 1);
-        if (lane == 0) pl = (warp == 0) ? DT_INF : s_edge[par ^ 1][2 * (warp - 1) + 1];
-        if (lane == 31) pr = (warp == DT_WARPS - 1) ? DT_INF : s_edge[par ^ 1][2 * (warp + 1)];
-        int v[CH];
-        int run = 0x7fffffff;
 #pragma unroll
-        for (int k = 0; k < CH; k++) {
-            const int j = j0 + k;
-            int x = 0x7fffffff;
-            if (j < W) {
-                int c;
-                if (((s_pm[i * WPR + (j >> 4)] >> (2 * (j & 15))) & 3u) == 2u) c = 0;
-                else {
-                    const int ul = (k > 0) ? prev[k - 1] : pl;
-                    const int ur = (j + 1 < W) ? ((k + 1 < CH) ? prev[k + 1] : pr) : DT_INF;
-                    c = min(min(ul + DG, prev[k] + HV), min(ur + DG, DT_INF));
-                }
-                x = c - HV * j;
+        for (int k = 0; k < CPT; k++) {
+            const int x = tid + k * DM_THREADS;
+            if (x < W) {
+                // cell x of the previous row sits at index x + 1 of the row buffer (indices 0 and W + 1 = border, always DT_INF)
+                int d = min(dprev[k] + HV, min(rowD[off_p + x], rowD[off_p + x + 2]) + DG);
+                int u = min(uprev[k] + HV, min(rowU[off_p + x], rowU[off_p + x + 2]) + DG);
+                d = min(d, DT_INF); u = min(u, DT_INF);
+                if ((ed[8 * k] >> sh) & 1u) d = 0;
+                if ((eu[8 * k] >> sh) & 1u) u = 0;
+                dprev[k] = d; uprev[k] = u;
+                rowD[off_c + x + 1] = d; rowU[off_c + x + 1] = u;
+                gd[k * DM_THREADS] = d;
+                gu[k * DM_THREADS] = u;
             }
-            run = min(run, x);
-            v[k] = run;  // inclusive prefix min inside the chunk
         }
-        int inc = run;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc = min(inc, y); }
-        if (lane == 31) s_tot[par][warp] = inc;
-        int excl = __shfl_up_sync(FULL, inc, 1);
-        if (lane == 0) excl = 0x7fffffff;
+        ed += WPE; eu -= WPE; gd += W; gu -= W;
+        off_c ^= WB; off_p ^= WB;
         __syncthreads();
-#pragma unroll
-        for (int w = 0; w < DT_WARPS - 1; w++) if (w < warp) excl = min(excl, s_tot[par][w]);
-        excl = min(excl, DT_INF + HV);  // left border cell (column -1)
-#pragma unroll
-        for (int k = 0; k < CH; k++) {
-            const int j = j0 + k;
-            const int dv = min(min(excl, v[k]) + HV * j, DT_INF);
-            prev[k] = (j < W) ? dv : DT_INF;
-            if (j < W) tmp[(size_t)i * W + j] = dv;
-        }
-        if (lane == 0) s_edge[par][2 * warp] = prev[0];
-        if (lane == 31) s_edge[par][2 * warp + 1] = prev[CH - 1];
-        __syncthreads();
-    }
-    // ---- backward pass: the forward result comes back in strips of DT_STRIP rows (bottom strip first), double buffered.
-    // Strip s covers rows [s*DT_STRIP, min(H, (s+1)*DT_STRIP)); its first int sits at tmp + s*DT_STRIP*W: 16-byte aligned because
-    // map_offset and DT_STRIP*W are multiples of 4 ints.  Byte counts are rounded up to 16 (the map slots are padded to 16 bytes).
-    const int n_strips = (H + DT_STRIP - 1) / DT_STRIP;
-    auto issue = [&](int s, int b) {
-        const int r_lo = s * DT_STRIP, r_hi = min(H, r_lo + DT_STRIP);
-        const uint32_t bytes = ((uint32_t)((r_hi - r_lo) * W) * 4u + 15u) & ~15u;
-        fence_proxy_async();  // generic-proxy reads of this buffer (previous strip) are ordered before the async-proxy write
-        mbar_expect_tx(&s_bar[b], bytes);
-        tma_bulk_g2s(s_strip + b * buf_stride, tmp + (size_t)r_lo * W, bytes, &s_bar[b]);
-    };
-#pragma unroll
-    for (int k = 0; k < CH; k++) prev[k] = DT_INF;  // row H = border
-    if (tid < 2 * DT_WARPS) { s_edge[0][tid] = DT_INF; s_edge[1][tid] = DT_INF; }
-    __threadfence();
-    fence_proxy_async_all();  // this thread's forward stores (generic proxy, global) before the bulk reads of the async proxy
-    __syncthreads();
-    uint32_t ph0 = 0, ph1 = 0;
-    if (tid == 0) issue(n_strips - 1, 0);
-    for (int s = n_strips - 1, it = 0; s >= 0; s--, it++) {
-        const int b = it & 1;
-        if (tid == 0 && s > 0) issue(s - 1, b ^ 1);  // buffer b^1 was released by the trailing barrier of the previous strip
-        if (b == 0) { mbar_wait(&s_bar[0], ph0); ph0 ^= 1; } else { mbar_wait(&s_bar[1], ph1); ph1 ^= 1; }
-        const int r_lo = s * DT_STRIP, r_hi = min(H, r_lo + DT_STRIP);
-        const int* sb = s_strip + b * buf_stride;
-        for (int i = r_hi - 1; i >= r_lo; i--) {
-            const int par = i & 1;
-            int pl = __shfl_up_sync(FULL, prev[CH - 1], 1), pr = __shfl_down_sync(FULL, prev[0], 1);
-            if (lane == 0) pl = (warp == 0) ? DT_INF : s_edge[par ^ 1][2 * (warp - 1) + 1];
-            if (lane == 31) pr = (warp == DT_WARPS - 1) ? DT_INF : s_edge[par ^ 1][2 * (warp + 1)];
-            int v[CH];
-            int run = 0x7fffffff;
-#pragma unroll
-            for (int k = CH - 1; k >= 0; k--) {
-                const int j = j0 + k;
-                int x = 0x7fffffff;
-                if (j < W) {
-                    const int self = sb[(i - r_lo) * W + j];
-                    const int dl = (k > 0) ? prev[k - 1] : pl;
-                    const int dr = (j + 1 < W) ? ((k + 1 < CH) ? prev[k + 1] : pr) : DT_INF;
-                    const int t0 = min(min(self, dr + DG), min(prev[k] + HV, dl + DG));
-                    x = t0 + HV * j;
-                }
-                run = min(run, x);
-                v[k] = run;  // inclusive suffix min inside the chunk
-            }
-            int inc = run;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_down_sync(FULL, inc, o); if (lane + o < 32) inc = min(inc, y); }
-            if (lane == 0) s_tot[par][warp] = inc;
-            int excl = __shfl_down_sync(FULL, inc, 1);
-            if (lane == 31) excl = 0x7fffffff;
-            __syncthreads();
-#pragma unroll
-            for (int w = 1; w < DT_WARPS; w++) if (w > warp) excl = min(excl, s_tot[par][w]);
-            excl = min(excl, DT_INF + HV * W);  // right border cell (column W)
-#pragma unroll
-            for (int k = 0; k < CH; k++) {
-                const int j = j0 + k;
-                const int dv = min(min(excl, v[k]) - HV * j, DT_INF);
-                prev[k] = (j < W) ? dv : DT_INF;
-                if (j < W) out[(size_t)i * W + j] = (float)((dv >= DT_INF) ? DT_MAX : (unsigned)dv) * scale;
-            }
-            if (lane == 0) s_edge[par][2 * warp] = prev[0];
-            if (lane == 31) s_edge[par][2 * warp + 1] = prev[CH - 1];
-            __syncthreads();
-        }
     }
 }
 
-__global__ void __launch_bounds__(DT_THREADS) k_dist3x3(DetectBuffers B, const uint8_t* cmap, int* dtmp, float* maps, int pm_words_cap, int strip_cap) {
-    extern __shared__ __align__(128) unsigned char dt_smem[];
-    __shared__ int s_tot[2][DT_WARPS];
-    __shared__ int s_edge[2][2 * DT_WARPS];
-    __shared__ uint64_t s_bar[2];
-    int* s_strip = reinterpret_cast<int*>(dt_smem);                          // 2 buffers of strip_cap ints (16-byte aligned)
-    unsigned* s_pm = reinterpret_cast<unsigned*>(dt_smem) + 2 * strip_cap;   // packed map
-    const int task = blockIdx.x, tid = threadIdx.x;
+// Row pass of the distance transform, one warp per row: buf[x] = V(x) - a x on entry, dist(x) = min_x' (V(x') + a |x - x'|) on exit.
+// Lane l owns the chunk [l CH, (l + 1) CH): prefix-min of V - a x and suffix-min of V + a x inside the chunk, the lanes' totals
+// combined with shuffles.  Chunk in registers (CH <= CHT):
+template <int CHT>
+__device__ __forceinline__ void row_scan_regs(int* buf, int CH, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    const int HV = (int)DT_HV;
+    const int i0 = lane * CH;
+    int p[CHT];
+    int incP = 0x7fffffff, incQ = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < CHT; k++) {
+        p[k] = (k < CH) ? buf[i0 + k] : DT_INF;   // a missing element can never win a minimum against a real one
+        incP = min(incP, p[k]);
+        incQ = min(incQ, p[k] + 2 * HV * (i0 + k));
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(FULL, incP, o), b = __shfl_down_sync(FULL, incQ, o);
+        if (lane >= o) incP = min(incP, a);
+        if (lane + o < 32) incQ = min(incQ, b);
+    }
+    int runP = __shfl_up_sync(FULL, incP, 1), runQ = __shfl_down_sync(FULL, incQ, 1);
+    if (lane == 0) runP = 0x7fffffff;
+    if (lane == 31) runQ = 0x7fffffff;
+    int f[CHT];
+#pragma unroll
+    for (int k = 0; k < CHT; k++) { runP = min(runP, p[k]); f[k] = runP + HV * (i0 + k); }
+#pragma unroll
+    for (int k = CHT - 1; k >= 0; k--) {
+        runQ = min(runQ, p[k] + 2 * HV * (i0 + k));
+        if (k < CH) buf[i0 + k] = min(f[k], runQ - HV * (i0 + k));
+    }
+}
+// buf[x] = min(Down, Up)(x) - a x for x < 32 CH (DT_INF beyond the row), all global loads of the lane in flight together
+template <int CHT>
+__device__ __forceinline__ void row_load(int* buf, const int* rd, const int* ru, int W, int CH, int lane) {
+    const int HV = (int)DT_HV;
+    int a[CHT], b[CHT];
+#pragma unroll
+    for (int j = 0; j < CHT; j++) {
+        const int x = lane + 32 * j;
+        a[j] = (x < W) ? rd[x] : DT_INF;
+        b[j] = (x < W) ? ru[x] : DT_INF;
+    }
+#pragma unroll
+    for (int j = 0; j < CHT; j++) {
+        const int x = lane + 32 * j;
+        if (j < CH) buf[x] = min(a[j], b[j]) - HV * x;
+    }
+    __syncwarp();
+}
+// any chunk length, through a second shared-memory buffer
+__device__ __forceinline__ void row_scan_smem(int* bufP, int* bufQ, int CH, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    const int HV = (int)DT_HV;
+    const int i0 = lane * CH;
+    int runP = 0x7fffffff, runQ = 0x7fffffff;
+    for (int k = CH - 1; k >= 0; k--) { runQ = min(runQ, bufP[i0 + k] + 2 * HV * (i0 + k)); bufQ[i0 + k] = runQ; }
+    for (int k = 0; k < CH; k++) { runP = min(runP, bufP[i0 + k]); bufP[i0 + k] = runP; }
+    int incP = runP, incQ = runQ;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(FULL, incP, o), b = __shfl_down_sync(FULL, incQ, o);
+        if (lane >= o) incP = min(incP, a);
+        if (lane + o < 32) incQ = min(incQ, b);
+    }
+    int cP = __shfl_up_sync(FULL, incP, 1), cQ = __shfl_down_sync(FULL, incQ, 1);
+    if (lane == 0) cP = 0x7fffffff;
+    if (lane == 31) cQ = 0x7fffffff;
+    for (int k = 0; k < CH; k++) {
+        const int x = i0 + k;
+        bufP[x] = min(min(cP, bufP[x]) + HV * x, min(cQ, bufQ[x]) - HV * x);
+    }
+}
+
+// Per-task stage cycles of k_distmap (thread 0), compiled in only with -DCSB_DM_PHASES (CSB_DM_PHASES=1 python -m cube_slam_wu_b200.build --force;
+// tools/distmap_phases.py reads them through csb_debug_distmap_phases).
+#ifdef CSB_DM_PHASES
+constexpr int DM_PHASE_TASKS = 8192;
+__device__ long long g_dm_phase[DM_PHASE_TASKS][8];
+#define DM_PHASE(idx) do { if (tid == 0 && task < DM_PHASE_TASKS) { const long long now__ = clock64(); g_dm_phase[task][idx] = now__ - t_prev__; t_prev__ = now__; } } while (0)
+#else
+#define DM_PHASE(idx) do { } while (0)
+#endif
+
+// One CTA per task: Canny (Sobel -> L1 magnitude -> non-maximum suppression -> hysteresis) and the 3x3 chamfer distance transform.
+//
+// (1) Sobel + NMS, register sliding window, no shared-memory staging: a warp takes a unit = (120 ROI columns, strip of rows); lane l owns the
+//     four columns 120 wc + 4 (l - 1) .. + 3 and walks down the strip holding two gray rows (6 columns each, packed u16 pairs; the two
+//     outer columns come from the neighbour lanes' words by shuffle), three magnitude rows (4 + the neighbours' adjacent magnitudes) and the
+//     gradients of the middle row.  Column sums / differences are formed on packed pairs with plain integer adds (biased so that no borrow
+//     crosses the halves); the suppression test is branch-free (the candidate density of real frames makes every branch divergent).
+//     Result: one bit per pixel in two planes that stay in shared memory, S = edge (kept, magnitude > high) and Wk = weak candidate
+//     (kept, low < magnitude <= high); two lanes combine their nibbles into one byte per plane.
+// (2) hysteresis = flood fill on the bit planes: S |= dilate3x3(S) & Wk, word-parallel and in place, until nothing changes.
+// (3) distance transform.  OpenCV's two raster passes compute, for every pixel, the exact 3x3 chamfer distance (a, b) to the nearest edge
+//     pixel of the ROI (integer min / + only, so the order of evaluation cannot change a bit).  A shortest chamfer path can always be
+//     taken as vertical / diagonal moves that all go down or all go up, followed by horizontal moves inside the target pixel's row.  So:
+//     Down(y, x) = edge ? 0 : min(Down(y-1, x) + a, Down(y-1, x +- 1) + b) for rows top to bottom and Up(y, x) the same bottom to top --
+//     two independent sweeps run in the same loop, thread = column, ONE barrier per row, no scan inside a row -- then per row
+//     dist(x) = min_x' (V(x') + a |x - x'|) with V = min(Down, Up): a prefix-min of V - a x and a suffix-min of V + a x, one warp per
+//     row (every lane scans a contiguous chunk in shared memory, the lanes' totals are combined with shuffles).  Checked against cv2 on
+//     the CPU (numpy model) before it was written, and bit for bit on the GPU by tests/test_distmap_gpu.py.
+__global__ void __launch_bounds__(DM_THREADS, 4) k_distmap(DetectBuffers B, const uint8_t* __restrict__ gray, uint8_t* cmap, int* queue, int* dtmp, float* maps,
+                                                           int low, int high, int plane_words_cap, int work_ints) {
+    extern __shared__ __align__(16) unsigned char dm_smem[];
+    unsigned* Sb = reinterpret_cast<unsigned*>(dm_smem);                 // edge bits, H * WPE words; the weak plane follows it
+    int* work = reinterpret_cast<int*>(Sb + plane_words_cap);            // sweeps: 2 x 2 row buffers; row pass: 2 buffers per warp
+
+    const int task = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned FULL = 0xffffffffu;
     const TaskTab t = B.ttab[task];
-    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); fence_mbar_init(); }
+    const FrameTab& ft = B.ftab[t.frame_id];
+    const uint8_t* img = gray + ft.gray_offset;
+    const int img_mis = (int)(reinterpret_cast<uintptr_t>(img) & 3);
+    const unsigned* imgA = reinterpret_cast<const unsigned*>(img - img_mis);
+    const int IW = ft.img_w, IH = ft.img_h;
+    const int W = t.roi_w, H = t.roi_h;
+    const int WPE = (W + 31) >> 5, nE = H * WPE, RB = 4 * WPE;  // RB = bytes per plane row
+    unsigned* Wb = Sb + nE;
+    uint8_t* S8 = reinterpret_cast<uint8_t*>(Sb);
+    uint8_t* W8 = reinterpret_cast<uint8_t*>(Wb);
+    const int TG22 = (int)(0.4142135623730950488016887242097 * (1 << 15) + 0.5);
+#ifdef CSB_DM_PHASES
+    long long t_prev__ = clock64();
+    int n_levels__ = 0;
+#endif
+
+    // ---- (1) Sobel, magnitude, non-maximum suppression
+    {
+        const int n_wc = (8 * RB + DM_COLS - 1) / DM_COLS;
+        int n_st = (2 * DM_WARPS) / n_wc;
+        n_st = max(1, min(n_st, (H + 7) >> 3));
+        const int SR = (H + n_st - 1) / n_st;
+        const int n_units = n_wc * n_st;
+        for (int u = warp; u < n_units; u += DM_WARPS) {
+            const int wc = u % n_wc, s = u / n_wc;
+            const int r_begin = s * SR, r_end = min(H, r_begin + SR);
+            if (r_begin >= r_end) continue;  // warp-uniform
+            const int cR = wc * DM_COLS + 4 * (lane - 1);  // first ROI column of this lane
+            const bool need = (cR + 3 >= -1) && (cR <= W);   // columns -1 .. W feed a result
+            bool cin[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) cin[k] = (cR + k >= 0) && (cR + k < W);
+            const int bidx = wc * (DM_COLS / 8) + ((lane - 1) >> 1);  // byte of the plane row that this lane pair fills
+            const bool store_ok = (lane & 1) && lane <= 29 && bidx < RB;
+            const int gx = t.roi_left + cR;
+            const bool fast = gx >= 0 && gx + 3 < IW;  // the lane's four bytes lie inside the image row: two aligned word loads + funnel shift
+            const int goff = gx + img_mis;
+            // the lane's gray word of ROI row rr (issued one row ahead of its use: a row step is one global-load latency otherwise)
+            auto gray_word = [&](int rr) -> unsigned {
+                rr = min(max(rr, -1), H);  // rows outside -1 .. H never reach a result
+                const int yc = min(max(t.roi_top + rr, 0), IH - 1);
+                unsigned w = 0u;
+                if (need) {
+                    if (fast) {
+                        const int off = yc * IW + goff;  // byte offset from the 4-byte aligned base (rows are packed: any alignment)
+                        const unsigned lo = __ldg(imgA + (off >> 2)), hi = __ldg(imgA + (off >> 2) + 1);  // (the frame buffer has 64 bytes of slack)
+                        w = __funnelshift_r(lo, hi, (unsigned)(off & 3) * 8u);
+                    } else
+                        w = load_gray4_border(img + (size_t)yc * IW, IW, gx);
+                }
+                return w;
+            };
+            // word -> three packed pairs: columns (-1, 0), (1, 2), (3, 4) relative to cR
+            auto unpack_row = [&](unsigned w, unsigned& P0, unsigned& P1, unsigned& P2) {
+                const unsigned wl = __shfl_up_sync(FULL, w, 1), wr = __shfl_down_sync(FULL, w, 1);
+                P0 = (wl >> 24) | ((w & 0xffu) << 16);
+                P1 = __byte_perm(w, 0u, 0x4241);
+                P2 = (w >> 24) | ((wr & 0xffu) << 16);
+            };
+            unsigned A0, A1, A2, B0, B1, B2;
+            unpack_row(gray_word(r_begin - 2), A0, A1, A2);
+            unpack_row(gray_word(r_begin - 1), B0, B1, B2);
+            unsigned w_next = gray_word(r_begin);
+            // magnitude rows m - 2 (M0) and m - 1 (M1): index 0 .. 5 = columns cR - 1 .. cR + 4; gradients of row m - 1
+            int M0[6], M1[6], px[4], py[4];
+#pragma unroll
+            for (int j = 0; j < 6; j++) { M0[j] = 0; M1[j] = 0; }
+#pragma unroll
+            for (int k = 0; k < 4; k++) { px[k] = 0; py[k] = 0; }
+            for (int m = r_begin - 1; m <= r_end; m++) {
+                unsigned C0, C1, C2;
+                const unsigned w_cur = w_next;
+                w_next = gray_word(m + 2);
+                unpack_row(w_cur, C0, C1, C2);
+                // Sobel of row m: column sums S = top + 2 mid + bot, differences T = bot - top (+1024 per half)
+                const unsigned S0 = A0 + C0 + 2u * B0, S1 = A1 + C1 + 2u * B1, S2 = A2 + C2 + 2u * B2;
+                const unsigned T0 = C0 - A0 + 0x04000400u, T1 = C1 - A1 + 0x04000400u, T2 = C2 - A2 + 0x04000400u;
+                const unsigned dx01 = S1 - S0 + 0x08000800u, dx23 = S2 - S1 + 0x08000800u;              // dx + 2048
+                const unsigned T01 = __funnelshift_r(T0, T1, 16), T12 = __funnelshift_r(T1, T2, 16);
+                const unsigned dy01 = T0 + 2u * T01 + T1, dy23 = T1 + 2u * T12 + T2;                    // dy + 4096
+                int cx[4], cy[4], M2[6];
+                cx[0] = (int)(dx01 & 0xffffu) - 2048; cx[1] = (int)(dx01 >> 16) - 2048; cx[2] = (int)(dx23 & 0xffffu) - 2048; cx[3] = (int)(dx23 >> 16) - 2048;
+                cy[0] = (int)(dy01 & 0xffffu) - 4096; cy[1] = (int)(dy01 >> 16) - 4096; cy[2] = (int)(dy23 & 0xffffu) - 4096; cy[3] = (int)(dy23 >> 16) - 4096;
+                const bool row_in = m >= 0 && m < H;
+#pragma unroll
+                for (int k = 0; k < 4; k++) M2[k + 1] = (row_in && cin[k]) ? abs(cx[k]) + abs(cy[k]) : 0;  // magnitude 0 outside the ROI
+                M2[0] = __shfl_up_sync(FULL, M2[4], 1);
+                M2[5] = __shfl_down_sync(FULL, M2[1], 1);
+                const int r = m - 1;
+                if (r >= r_begin) {
+                    unsigned sbits = 0, wbits = 0;
+                    const bool cand = (M1[1] > low) || (M1[2] > low) || (M1[3] > low) || (M1[4] > low);
+                    if (__any_sync(FULL, cand)) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int j = k + 1;
+                            const int mg = M1[j];
+                            const int xs = px[k], ys = py[k];
+                            const int ax = abs(xs), ay = abs(ys) << 15;
+                            const int tg22x = ax * TG22;
+                            const int tg67x = tg22x + (ax << 16);
+                            const bool horiz = ay < tg22x, vert = ay > tg67x;
+                            const bool neg = (xs ^ ys) < 0;  // s = -1
+                            int na = neg ? M0[j + 1] : M0[j - 1];
+                            int nb = neg ? M2[j - 1] : M2[j + 1];
+                            na = vert ? M0[j] : na; nb = vert ? M2[j] : nb;
+                            na = horiz ? M1[j - 1] : na; nb = horiz ? M1[j + 1] : nb;
+                            // horizontal / vertical: m > a && m >= b; diagonal: m > a && m > b
+                            const bool diag = !horiz && !vert;
+                            const bool keep = (mg > low) && (mg > na) && (mg + (diag ? 0 : 1) > nb);
+                            const bool strong = keep && (mg > high);
+                            sbits |= (strong ? 1u : 0u) << k;
+                            wbits |= ((keep && !strong) ? 1u : 0u) << k;
+                        }
+                    }
+                    const unsigned mine = sbits | (wbits << 4);
+                    const unsigned other = __shfl_down_sync(FULL, mine, 1);
+                    if (store_ok) {
+                        S8[(size_t)r * RB + bidx] = (uint8_t)((mine & 15u) | ((other & 15u) << 4));
+                        W8[(size_t)r * RB + bidx] = (uint8_t)((mine >> 4) | (other & 0xf0u));
+                    }
+                }
+                A0 = B0; A1 = B1; A2 = B2; B0 = C0; B1 = C1; B2 = C2;
+#pragma unroll
+                for (int j = 0; j < 6; j++) { M0[j] = M1[j]; M1[j] = M2[j]; }
+#pragma unroll
+                for (int k = 0; k < 4; k++) { px[k] = cx[k]; py[k] = cy[k]; }
+            }
+        }
+    }
     __syncthreads();
-    if (t.roi_w <= DT_THREADS * 2) dist3x3_cta<2>(t, cmap, dtmp, maps, tid, s_tot, s_edge, s_pm, s_strip, strip_cap, s_bar);
-    else if (t.roi_w <= DT_THREADS * 3) dist3x3_cta<3>(t, cmap, dtmp, maps, tid, s_tot, s_edge, s_pm, s_strip, strip_cap, s_bar);
-    else if (t.roi_w <= DT_THREADS * 4) dist3x3_cta<4>(t, cmap, dtmp, maps, tid, s_tot, s_edge, s_pm, s_strip, strip_cap, s_bar);
-    else dist3x3_cta<10>(t, cmap, dtmp, maps, tid, s_tot, s_edge, s_pm, s_strip, strip_cap, s_bar);
+    DM_PHASE(0);
+    // ---- (2) hysteresis: weak pixels 8-connected (through weak pixels) to an edge pixel become edge pixels.  In place: a word only ever
+    //      gains bits, a stale neighbour word just postpones a promotion to the next round.
+    while (true) {
+        int changed = 0;
+        for (int idx = tid; idx < nE; idx += DM_THREADS) {
+            const unsigned wk = Wb[idx];
+            if (wk == 0u) continue;
+            const int y = idx / WPE, w = idx - y * WPE;
+            unsigned acc = 0;
+#pragma unroll
+            for (int dy = -1; dy <= 1; dy++) {
+                const int yy = y + dy;
+                if (yy < 0 || yy >= H) continue;
+                const unsigned* row = Sb + yy * WPE;
+                const unsigned c = row[w], l = (w > 0) ? row[w - 1] : 0u, rr = (w + 1 < WPE) ? row[w + 1] : 0u;
+                acc |= c | (c << 1) | (c >> 1) | (l >> 31) | (rr << 31);
+            }
+            const unsigned nw = acc & wk;
+            if (nw) { Sb[idx] |= nw; Wb[idx] = wk & ~nw; changed = 1; }
+        }
+#ifdef CSB_DM_PHASES
+        n_levels__++;
+#endif
+        if (!__syncthreads_or(changed)) break;
+    }
+    DM_PHASE(1);
+    // packed 2-bit map -> global (csb_detect_debug_map reads it): 0 weak candidate, 1 no edge, 2 edge; 16 pixels per word
+    {
+        const int WPR = (W + 15) >> 4;
+        unsigned* out = reinterpret_cast<unsigned*>(cmap + 4 * (size_t)t.map_offset);
+        for (int i = tid; i < H * WPR; i += DM_THREADS) {
+            const int y = i / WPR, w = i - y * WPR;
+            const unsigned sw = Sb[y * WPE + (w >> 1)] >> (16 * (w & 1)), ww = Wb[y * WPE + (w >> 1)] >> (16 * (w & 1));
+            out[i] = spread16(~(sw | ww)) | (spread16(sw) << 1);
+        }
+    }
+    // ---- (3) distance transform: vertical sweeps
+    const int WB = W + 2;
+    int* rowD = work;            // 2 x WB
+    int* rowU = work + 2 * WB;   // 2 x WB
+    for (int i = tid; i < 2 * WB; i += DM_THREADS) { rowD[i] = DT_INF; rowU[i] = DT_INF; }
+    __syncthreads();
+    DM_PHASE(2);
+    int* tmpD = dtmp + t.map_offset;
+    int* tmpU = queue + t.map_offset;
+    if (W <= DM_THREADS) dt_sweeps<1>(W, H, WPE, Sb, rowD, rowU, WB, tmpD, tmpU, tid);
+    else if (W <= 2 * DM_THREADS) dt_sweeps<2>(W, H, WPE, Sb, rowD, rowU, WB, tmpD, tmpU, tid);
+    else if (W <= 3 * DM_THREADS) dt_sweeps<3>(W, H, WPE, Sb, rowD, rowU, WB, tmpD, tmpU, tid);
+    else dt_sweeps<5>(W, H, WPE, Sb, rowD, rowU, WB, tmpD, tmpU, tid);
+    DM_PHASE(3);
+    // ---- row pass (the sweeps end with a barrier: the block's global writes are visible to all its threads).
+    // Scaled like OpenCV: (float)(unsigned) * 2^-16; unreachable -> DIST_MAX.
+    {
+        const int HV = (int)DT_HV;
+        const int CH = ((W + 31) >> 5) | 1;   // odd chunk length: conflict-free shared-memory access at stride CH
+        const int WP = 32 * CH;
+        int* buf = work + warp * 2 * WP;
+        float* out = maps + t.map_offset;
+        const float scale = 1.f / 65536.f;
+        for (int y = warp; y < H; y += DM_WARPS) {
+            const int* rd = tmpD + (size_t)y * W;
+            const int* ru = tmpU + (size_t)y * W;
+            if (CH <= 5) { row_load<5>(buf, rd, ru, W, CH, lane); row_scan_regs<5>(buf, CH, lane); }
+            else if (CH <= 9) { row_load<9>(buf, rd, ru, W, CH, lane); row_scan_regs<9>(buf, CH, lane); }
+            else if (CH <= 13) { row_load<13>(buf, rd, ru, W, CH, lane); row_scan_regs<13>(buf, CH, lane); }
+            else {
+                for (int x = lane; x < WP; x += 32) buf[x] = ((x < W) ? min(rd[x], ru[x]) : DT_INF) - HV * x;
+                __syncwarp();
+                row_scan_smem(buf, buf + WP, CH, lane);
+            }
+            __syncwarp();
+            float* o = out + (size_t)y * W;
+            for (int x = lane; x < W; x += 32) {
+                const int v = buf[x];
+                o[x] = (float)((v >= DT_INF) ? DT_MAX : (unsigned)v) * scale;
+            }
+            __syncwarp();
+        }
+    }
+    DM_PHASE(4);
+#ifdef CSB_DM_PHASES
+    if (tid == 0 && task < DM_PHASE_TASKS) { g_dm_phase[task][5] = n_levels__; g_dm_phase[task][6] = 0; g_dm_phase[task][7] = (long long)W << 32 | H; }
+#endif
 }
 
 // ---- gray-frame upload without the copy engine: only what the ROIs read -----------------------------------------------------------
@@ -447,21 +503,23 @@ cudaError_t launch_gray_gather(const DetectBuffers& B, const uint8_t* gray_host_
 
 cudaError_t launch_distmaps(const DetectBuffers& B, const uint8_t* gray, uint8_t* cmap, int* queue, unsigned* dtmp, float* maps, int max_roi_w, int max_pm_words, cudaStream_t st) {
     if (B.n_tasks == 0) return cudaSuccess;
-    if (max_roi_w > DT_THREADS * 10) return cudaErrorInvalidValue;  // ROI wider than 1280 px
-    const int wp_cap = (max_roi_w + 15) & ~15;
-    const int pm_cap = (max_pm_words + 3) & ~3;
-    const size_t smem_c = 4 * (size_t)pm_cap + (size_t)(CN_ROWS + 4) * (wp_cap + 8) + 2 * (size_t)(CN_ROWS + 2) * (wp_cap + 8);
-    if (smem_c > 200 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(k_canny, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
+    if (max_roi_w > DM_THREADS * 5) return cudaErrorInvalidValue;  // ROI wider than 1280 px
+    const int plane_cap = (max_pm_words + 3) & ~3;  // >= 2 * H * ceil(W / 32) words for every task (capi_detect.cu)
+    const int wp = 32 * (((max_roi_w + 31) >> 5) | 1);
+    const int work_ints = 2 * DM_WARPS * wp;  // >= 4 * (W + 2)
+    const size_t smem = 4 * (size_t)plane_cap + 4 * (size_t)work_ints;
+    if (smem > 220 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(k_distmap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_canny<<<B.n_tasks, CN_THREADS, smem_c, st>>>(B, gray, cmap, queue, 80, 200, pm_cap, wp_cap);
-    const int strip_cap = (DT_STRIP * max_roi_w + 3) & ~3;
-    const size_t smem_d = 4 * (size_t)(2 * strip_cap + pm_cap);
-    if (smem_d > 200 * 1024) return cudaErrorInvalidValue;
-    e = cudaFuncSetAttribute(k_dist3x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d);
-    if (e != cudaSuccess) return e;
-    k_dist3x3<<<B.n_tasks, DT_THREADS, smem_d, st>>>(B, cmap, reinterpret_cast<int*>(dtmp), maps, pm_cap, strip_cap);
+    k_distmap<<<B.n_tasks, DM_THREADS, smem, st>>>(B, gray, cmap, queue, reinterpret_cast<int*>(dtmp), maps, 80, 200, plane_cap, work_ints);
     return cudaGetLastError();
 }
 
 }  // namespace csb
+
+#ifdef CSB_DM_PHASES
+extern "C" int csb_debug_distmap_phases(long long* out, int n_tasks) {
+    if (n_tasks > csb::DM_PHASE_TASKS) n_tasks = csb::DM_PHASE_TASKS;
+    return (int)cudaMemcpyFromSymbol(out, csb::g_dm_phase, sizeof(long long) * 8 * (size_t)n_tasks);
+}
+#endif
