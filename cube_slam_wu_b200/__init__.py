@@ -75,7 +75,13 @@ BA_OUT_FIELDS = ("ec_err", "ec_Ji", "ec_Jj", "ep_err", "ep_Ji", "ep_Jj", "eo_err
 
 class BAOptimizeStats(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("trials", C.c_int32), ("n_kernel_launches", C.c_int32), ("schur_dim", C.c_int32),
-                ("chi2", C.c_double), ("lambda_", C.c_double), ("gpu_ms", C.c_float), ("pad", C.c_float)]
+                ("chi2", C.c_double), ("lambda_", C.c_double), ("gpu_ms", C.c_float), ("n_launches", C.c_int32)]
+
+
+class BAFrame(C.Structure):
+    _fields_ = [("cam7", C.c_void_p), ("cam_fixed", C.c_int32), ("n_new_cubes", C.c_int32), ("new_cubes10", C.c_void_p), ("new_cube_fixed", C.c_void_p),
+                ("n_ec", C.c_int32), ("ec_cube", C.c_void_p), ("ec_meas", C.c_void_p), ("ec_info", C.c_void_p),
+                ("n_eo", C.c_int32), ("eo_cam_i", C.c_void_p), ("eo_meas", C.c_void_p), ("eo_info", C.c_void_p)]
 
 
 class BAOutput(C.Structure):
@@ -290,6 +296,28 @@ class Context:
             g.n_eo = len(eo[0]); g.eo_cam_i = arr(eo[0], np.int32); g.eo_cam_j = arr(eo[1], np.int32); g.eo_meas = arr(eo[2], np.float64); g.eo_info = arr(eo[3], np.float64)
         self._chk(lib().csb_ba_set_graph(self._h, C.byref(g)))
         self._ba_dims = (g.n_cam, g.n_cube, g.n_ec, g.n_ep, g.n_eo)
+
+    def ba_add_frame(self, cam7, cam_fixed=False, new_cubes10=None, new_cube_fixed=None, ec=None, eo=None):
+        """csb_ba_add_frame(): one more camera with its edges.  ec=(cube,meas10,info81)  eo=(cam_i,meas7,info36).  Returns the camera index."""
+        keep = []
+
+        def arr(a, dt):
+            a = np.ascontiguousarray(a, dt); keep.append(a); return a.ctypes.data_as(C.c_void_p)
+        f = BAFrame()
+        f.cam7 = arr(cam7, np.float64); f.cam_fixed = int(bool(cam_fixed))
+        if new_cubes10 is not None and len(new_cubes10):
+            f.n_new_cubes = len(new_cubes10); f.new_cubes10 = arr(new_cubes10, np.float64)
+            f.new_cube_fixed = arr(new_cube_fixed if new_cube_fixed is not None else np.zeros(len(new_cubes10)), np.int32)
+        if ec is not None and len(ec[0]):
+            f.n_ec = len(ec[0]); f.ec_cube = arr(ec[0], np.int32); f.ec_meas = arr(ec[1], np.float64); f.ec_info = arr(ec[2], np.float64)
+        if eo is not None and len(eo[0]):
+            f.n_eo = len(eo[0]); f.eo_cam_i = arr(eo[0], np.int32); f.eo_meas = arr(eo[1], np.float64); f.eo_info = arr(eo[2], np.float64)
+        idx = C.c_int32(-1)
+        self._chk(lib().csb_ba_add_frame(self._h, C.byref(f), C.byref(idx)))
+        nc, nq, nec, nep, neo = self._ba_dims
+        self._ba_dims = (nc + 1, nq + f.n_new_cubes, nec + f.n_ec, nep, neo + f.n_eo)
+        self._ba_n_cam, self._ba_n_cube = self._ba_dims[0], self._ba_dims[1]
+        return idx.value
 
     def _ba_out(self, jacobians):
         nc, nq, nec, nep, neo = self._ba_dims

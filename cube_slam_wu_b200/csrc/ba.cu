@@ -286,114 +286,205 @@ void ba_release(BAState& s) {
     ba_solver_release(s);
     for (void* p : s.allocs) cudaFree(p);
     s.allocs.clear();
-    s.has_graph = s.has_estimates = s.ran = false;
+    for (GrowBuf& g : s.dev) { if (g.p) cudaFree(g.p); g.p = nullptr; g.cap = 0; }
+    s.host = HostGraph();
+    s.n_cam = s.n_cube = s.n_ec = s.n_ep = s.n_eo = 0;
+    s.has_graph = s.has_estimates = s.ran = s.have_J = false;
 }
 
 }  // namespace csb
 
 using namespace csb;
 
-namespace {
-template <class T>
-int dev_alloc(csb_context* c, T** out, size_t count) {
-    void* p = nullptr;
-    CSB_CUDA(c, cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
-    c->ba.allocs.push_back(p);
-    *out = reinterpret_cast<T*>(p);
-    return CSB_OK;
-}
-template <class T>
-int dev_upload(csb_context* c, const T** out, const T* host, size_t count) {
-    T* p = nullptr;
-    int rc = dev_alloc(c, &p, count);
-    if (rc != CSB_OK) return rc;
-    if (count) CSB_CUDA(c, cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
-    *out = p;
-    return CSB_OK;
-}
-}  // namespace
-
 #define CSB_TRY(x) do { int rc__ = (x); if (rc__ != CSB_OK) return rc__; } while (0)
+
+namespace {
+
+enum {
+    G_CAM_FIXED, G_CUBE_FIXED, G_EC_CAM, G_EC_CUBE, G_EC_MEAS, G_EC_INFO, G_EP_CAM, G_EP_CUBE, G_EP_MEAS, G_EP_INFO, G_EP_K, G_EO_I, G_EO_J, G_EO_MEAS, G_EO_INFO,
+    G_CAM_ADJ_PTR, G_CAM_ADJ_H, G_CAM_ADJ_B, G_CUBE_ADJ_PTR, G_CUBE_ADJ_H, G_CUBE_ADJ_B, G_CAMS7, G_CUBES10, G_EC_ERR, G_EP_ERR, G_EO_ERR, G_EC_JI, G_EC_JJ, G_EP_JI,
+    G_EP_JJ, G_EO_JI, G_EO_JJ, G_EC_HIJ, G_EP_HIJ, G_EO_HIJ, G_CONTRIB, G_EDGE_CHI2, G_H_CAM, G_B_CAM, G_H_CUBE, G_B_CUBE, G_CHI2, G_COUNT
+};
+static_assert(G_COUNT <= BA_MAX_BUFS, "BA_MAX_BUFS");
+
+// capacity >= bytes; the first `keep` bytes survive a reallocation (geometric growth: appending a frame rarely reallocates)
+int ensure(csb_context* c, int slot, size_t bytes, size_t keep) {
+    GrowBuf& g = c->ba.dev[slot];
+    if (g.p && bytes <= g.cap) return CSB_OK;
+    const size_t ncap = std::max<size_t>(std::max<size_t>(bytes, 2 * g.cap), 256);
+    void* np = nullptr;
+    CSB_CUDA(c, cudaMalloc(&np, ncap));
+    if (g.p) {
+        if (keep) CSB_CUDA(c, cudaMemcpyAsync(np, g.p, keep, cudaMemcpyDeviceToDevice, c->stream));
+        CSB_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(g.p);
+    }
+    g.p = np; g.cap = ncap;
+    return CSB_OK;
+}
+// device copy of a host vector whose first n_old elements are already there
+template <class T>
+int sync_tail(csb_context* c, int slot, const std::vector<T>& h, size_t n_old) {
+    CSB_TRY(ensure(c, slot, h.size() * sizeof(T), n_old * sizeof(T)));
+    if (h.size() > n_old)
+        CSB_CUDA(c, cudaMemcpyAsync(reinterpret_cast<T*>(c->ba.dev[slot].p) + n_old, h.data() + n_old, (h.size() - n_old) * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    return CSB_OK;
+}
+template <class T>
+int sync_all(csb_context* c, int slot, const std::vector<T>& h) { return sync_tail(c, slot, h, 0); }
+
+struct Counts { int n_cam, n_cube, n_ec, n_ep, n_eo; };
+
+// Brings the device state in line with c->ba.host after vertices / edges were appended (old = what the device already holds):
+// tails of the topology / measurement arrays, the per-vertex adjacency (rebuilt: the record offsets of the later edge types move when
+// an edge is inserted), the work buffers; the estimates of the existing vertices are preserved.
+int sync_device(csb_context* c, const Counts& old) {
+    BAState& s = c->ba;
+    const HostGraph& h = s.host;
+    const int n_cam = (int)h.cam_fixed.size(), n_cube = (int)h.cube_fixed.size(), n_ec = (int)h.ec_cam.size(), n_ep = (int)h.ep_cam.size(), n_eo = (int)h.eo_i.size();
+    CSB_TRY(sync_tail(c, G_CAM_FIXED, h.cam_fixed, old.n_cam)); CSB_TRY(sync_tail(c, G_CUBE_FIXED, h.cube_fixed, old.n_cube));
+    CSB_TRY(sync_tail(c, G_EC_CAM, h.ec_cam, old.n_ec)); CSB_TRY(sync_tail(c, G_EC_CUBE, h.ec_cube, old.n_ec));
+    CSB_TRY(sync_tail(c, G_EC_MEAS, h.ec_meas, (size_t)old.n_ec * 10)); CSB_TRY(sync_tail(c, G_EC_INFO, h.ec_info, (size_t)old.n_ec * 81));
+    CSB_TRY(sync_tail(c, G_EP_CAM, h.ep_cam, old.n_ep)); CSB_TRY(sync_tail(c, G_EP_CUBE, h.ep_cube, old.n_ep));
+    CSB_TRY(sync_tail(c, G_EP_MEAS, h.ep_meas, (size_t)old.n_ep * 4)); CSB_TRY(sync_tail(c, G_EP_INFO, h.ep_info, (size_t)old.n_ep * 16));
+    CSB_TRY(sync_tail(c, G_EP_K, h.ep_K, (size_t)old.n_ep * 9));
+    CSB_TRY(sync_tail(c, G_EO_I, h.eo_i, old.n_eo)); CSB_TRY(sync_tail(c, G_EO_J, h.eo_j, old.n_eo));
+    CSB_TRY(sync_tail(c, G_EO_MEAS, h.eo_meas, (size_t)old.n_eo * 7)); CSB_TRY(sync_tail(c, G_EO_INFO, h.eo_info, (size_t)old.n_eo * 36));
+
+    // buildStructure(): per-vertex adjacency in edge order ec, ep, eo (block_solver.hpp:142-295 allocates the blocks;
+    // sparse_optimizer.cpp:482-487 fixes the edge order) -- counting sort, flat arrays
+    {
+        std::vector<int> cam_ptr(n_cam + 1, 0), cube_ptr(n_cube + 1, 0);
+        for (int e = 0; e < n_ec; e++) { cam_ptr[h.ec_cam[e] + 1]++; cube_ptr[h.ec_cube[e] + 1]++; }
+        for (int e = 0; e < n_ep; e++) { cam_ptr[h.ep_cam[e] + 1]++; cube_ptr[h.ep_cube[e] + 1]++; }
+        for (int e = 0; e < n_eo; e++) { cam_ptr[h.eo_i[e] + 1]++; cam_ptr[h.eo_j[e] + 1]++; }
+        for (int v = 0; v < n_cam; v++) cam_ptr[v + 1] += cam_ptr[v];
+        for (int v = 0; v < n_cube; v++) cube_ptr[v + 1] += cube_ptr[v];
+        std::vector<int64_t> cam_H(cam_ptr[n_cam]), cam_b(cam_ptr[n_cam]), cube_H(cube_ptr[n_cube]), cube_b(cube_ptr[n_cube]);
+        std::vector<int> cam_at(cam_ptr.begin(), cam_ptr.end() - 1), cube_at(cube_ptr.begin(), cube_ptr.end() - 1);
+        auto put = [](std::vector<int>& at, std::vector<int64_t>& H, std::vector<int64_t>& b, int v, int64_t oh, int64_t ob) { const int k = at[v]++; H[k] = oh; b[k] = ob; };
+        for (int e = 0; e < n_ec; e++) {
+            const int64_t r = (int64_t)132 * e;
+            put(cam_at, cam_H, cam_b, h.ec_cam[e], r, r + 36); put(cube_at, cube_H, cube_b, h.ec_cube[e], r + 42, r + 42 + 81);
+        }
+        for (int e = 0; e < n_ep; e++) {
+            const int64_t r = (int64_t)132 * (n_ec + e);
+            put(cam_at, cam_H, cam_b, h.ep_cam[e], r, r + 36); put(cube_at, cube_H, cube_b, h.ep_cube[e], r + 42, r + 42 + 81);
+        }
+        for (int e = 0; e < n_eo; e++) {
+            const int64_t r = (int64_t)132 * (n_ec + n_ep) + (int64_t)84 * e;
+            put(cam_at, cam_H, cam_b, h.eo_i[e], r, r + 36); put(cam_at, cam_H, cam_b, h.eo_j[e], r + 42, r + 42 + 36);
+        }
+        CSB_TRY(sync_all(c, G_CAM_ADJ_PTR, cam_ptr)); CSB_TRY(sync_all(c, G_CAM_ADJ_H, cam_H)); CSB_TRY(sync_all(c, G_CAM_ADJ_B, cam_b));
+        CSB_TRY(sync_all(c, G_CUBE_ADJ_PTR, cube_ptr)); CSB_TRY(sync_all(c, G_CUBE_ADJ_H, cube_H)); CSB_TRY(sync_all(c, G_CUBE_ADJ_B, cube_b));
+        CSB_CUDA(c, cudaStreamSynchronize(c->stream));  // the host vectors go out of scope
+    }
+    CSB_TRY(ensure(c, G_CAMS7, 56 * (size_t)n_cam, 56 * (size_t)old.n_cam)); CSB_TRY(ensure(c, G_CUBES10, 80 * (size_t)n_cube, 80 * (size_t)old.n_cube));
+    auto work = [&](int slot, size_t n_doubles) { return ensure(c, slot, 8 * n_doubles, 0); };
+    CSB_TRY(work(G_EC_ERR, (size_t)n_ec * 9)); CSB_TRY(work(G_EP_ERR, (size_t)n_ep * 4)); CSB_TRY(work(G_EO_ERR, (size_t)n_eo * 6));
+    CSB_TRY(work(G_EC_JI, (size_t)n_ec * 54)); CSB_TRY(work(G_EC_JJ, (size_t)n_ec * 81)); CSB_TRY(work(G_EP_JI, (size_t)n_ep * 24)); CSB_TRY(work(G_EP_JJ, (size_t)n_ep * 36));
+    CSB_TRY(work(G_EO_JI, (size_t)n_eo * 36)); CSB_TRY(work(G_EO_JJ, (size_t)n_eo * 36));
+    CSB_TRY(work(G_EC_HIJ, (size_t)n_ec * 54)); CSB_TRY(work(G_EP_HIJ, (size_t)n_ep * 54)); CSB_TRY(work(G_EO_HIJ, (size_t)n_eo * 36));
+    CSB_TRY(work(G_CONTRIB, (size_t)132 * (n_ec + n_ep) + (size_t)84 * n_eo)); CSB_TRY(work(G_EDGE_CHI2, (size_t)(n_ec + n_ep + n_eo)));
+    CSB_TRY(work(G_H_CAM, (size_t)n_cam * 36)); CSB_TRY(work(G_B_CAM, (size_t)n_cam * 6)); CSB_TRY(work(G_H_CUBE, (size_t)n_cube * 81)); CSB_TRY(work(G_B_CUBE, (size_t)n_cube * 9));
+    CSB_TRY(work(G_CHI2, 1));
+
+    s.n_cam = n_cam; s.n_cube = n_cube; s.n_ec = n_ec; s.n_ep = n_ep; s.n_eo = n_eo;
+    BABuffers& B = s.B;
+    std::memset(&B, 0, sizeof B);
+    B.n_cam = n_cam; B.n_cube = n_cube; B.n_ec = n_ec; B.n_ep = n_ep; B.n_eo = n_eo;
+    auto I = [&](int slot) { return reinterpret_cast<int*>(s.dev[slot].p); };
+    auto D = [&](int slot) { return reinterpret_cast<double*>(s.dev[slot].p); };
+    auto L = [&](int slot) { return reinterpret_cast<int64_t*>(s.dev[slot].p); };
+    B.cam_fixed = I(G_CAM_FIXED); B.cube_fixed = I(G_CUBE_FIXED);
+    B.ec_cam = I(G_EC_CAM); B.ec_cube = I(G_EC_CUBE); B.ec_meas = D(G_EC_MEAS); B.ec_info = D(G_EC_INFO);
+    B.ep_cam = I(G_EP_CAM); B.ep_cube = I(G_EP_CUBE); B.ep_meas = D(G_EP_MEAS); B.ep_info = D(G_EP_INFO); B.ep_K = D(G_EP_K);
+    B.eo_i = I(G_EO_I); B.eo_j = I(G_EO_J); B.eo_meas = D(G_EO_MEAS); B.eo_info = D(G_EO_INFO);
+    B.cam_adj_ptr = I(G_CAM_ADJ_PTR); B.cam_adj_H = L(G_CAM_ADJ_H); B.cam_adj_b = L(G_CAM_ADJ_B);
+    B.cube_adj_ptr = I(G_CUBE_ADJ_PTR); B.cube_adj_H = L(G_CUBE_ADJ_H); B.cube_adj_b = L(G_CUBE_ADJ_B);
+    B.cams7 = D(G_CAMS7); B.cubes10 = D(G_CUBES10);
+    B.ec_err = D(G_EC_ERR); B.ep_err = D(G_EP_ERR); B.eo_err = D(G_EO_ERR);
+    B.ec_Ji = D(G_EC_JI); B.ec_Jj = D(G_EC_JJ); B.ep_Ji = D(G_EP_JI); B.ep_Jj = D(G_EP_JJ); B.eo_Ji = D(G_EO_JI); B.eo_Jj = D(G_EO_JJ);
+    B.ec_Hij = D(G_EC_HIJ); B.ep_Hij = D(G_EP_HIJ); B.eo_Hij = D(G_EO_HIJ);
+    B.contrib = D(G_CONTRIB); B.edge_chi2 = D(G_EDGE_CHI2);
+    B.H_cam = D(G_H_CAM); B.b_cam = D(G_B_CAM); B.H_cube = D(G_H_CUBE); B.b_cube = D(G_B_CUBE); B.chi2 = D(G_CHI2);
+    ba_solver_release(s);  // the structure of the reduced camera system (and the captured graphs) belong to the old topology
+    s.ran = false; s.have_J = false;
+    return CSB_OK;
+}
+
+bool in_range(const int32_t* idx, int n, int lim) {
+    for (int i = 0; i < n; i++) if (idx[i] < 0 || idx[i] >= lim) return false;
+    return true;
+}
+
+}  // namespace
 
 extern "C" {
 
 int csb_ba_set_graph(csb_context* c, const csb_ba_graph* g) {
     if (!c || !g) return CSB_ERR_INVALID;
-    if (g->n_cam < 0 || g->n_cube < 0 || g->n_ec < 0 || g->n_ep < 0 || g->n_eo < 0) { c->err = "negative size"; return CSB_ERR_INVALID; }
+    // everything is checked before the current graph is touched
+    if (g->n_cam < 0 || g->n_cube < 0 || g->n_ec < 0 || g->n_ep < 0 || g->n_eo < 0) { c->err = "csb_ba_set_graph: negative size"; return CSB_ERR_INVALID; }
+    if ((g->n_cam && !g->cam_fixed) || (g->n_cube && !g->cube_fixed) || (g->n_ec && (!g->ec_cam || !g->ec_cube || !g->ec_meas || !g->ec_info)) ||
+        (g->n_ep && (!g->ep_cam || !g->ep_cube || !g->ep_meas || !g->ep_info || !g->ep_K)) || (g->n_eo && (!g->eo_cam_i || !g->eo_cam_j || !g->eo_meas || !g->eo_info))) {
+        c->err = "csb_ba_set_graph: null array with a non-zero count";
+        return CSB_ERR_INVALID;
+    }
+    if (!in_range(g->ec_cam, g->n_ec, g->n_cam) || !in_range(g->ec_cube, g->n_ec, g->n_cube) || !in_range(g->ep_cam, g->n_ep, g->n_cam) ||
+        !in_range(g->ep_cube, g->n_ep, g->n_cube) || !in_range(g->eo_cam_i, g->n_eo, g->n_cam) || !in_range(g->eo_cam_j, g->n_eo, g->n_cam)) {
+        c->err = "csb_ba_set_graph: edge vertex index out of range";
+        return CSB_ERR_INVALID;
+    }
     CSB_CUDA(c, cudaSetDevice(c->device));
     CSB_CUDA(c, cudaStreamSynchronize(c->stream));
-    ba_release(c->ba);
     BAState& s = c->ba;
-    s.n_cam = g->n_cam; s.n_cube = g->n_cube; s.n_ec = g->n_ec; s.n_ep = g->n_ep; s.n_eo = g->n_eo;
-    auto chk = [&](const int32_t* idx, int n, int lim) { for (int i = 0; i < n; i++) if (idx[i] < 0 || idx[i] >= lim) return false; return true; };
-    if (!chk(g->ec_cam, g->n_ec, g->n_cam) || !chk(g->ec_cube, g->n_ec, g->n_cube) || !chk(g->ep_cam, g->n_ep, g->n_cam) || !chk(g->ep_cube, g->n_ep, g->n_cube) ||
-        !chk(g->eo_cam_i, g->n_eo, g->n_cam) || !chk(g->eo_cam_j, g->n_eo, g->n_cam)) { c->err = "edge vertex index out of range"; return CSB_ERR_INVALID; }
-    s.host.cam_fixed.assign(g->cam_fixed, g->cam_fixed + g->n_cam); s.host.cube_fixed.assign(g->cube_fixed, g->cube_fixed + g->n_cube);
-    s.host.ec_cam.assign(g->ec_cam, g->ec_cam + g->n_ec); s.host.ec_cube.assign(g->ec_cube, g->ec_cube + g->n_ec);
-    s.host.ep_cam.assign(g->ep_cam, g->ep_cam + g->n_ep); s.host.ep_cube.assign(g->ep_cube, g->ep_cube + g->n_ep);
-    s.host.eo_i.assign(g->eo_cam_i, g->eo_cam_i + g->n_eo); s.host.eo_j.assign(g->eo_cam_j, g->eo_cam_j + g->n_eo);
-    BABuffers& B = s.B;
-    std::memset(&B, 0, sizeof B);
-    B.n_cam = g->n_cam; B.n_cube = g->n_cube; B.n_ec = g->n_ec; B.n_ep = g->n_ep; B.n_eo = g->n_eo;
-    CSB_TRY(dev_upload(c, &B.cam_fixed, g->cam_fixed, (size_t)g->n_cam));
-    CSB_TRY(dev_upload(c, &B.cube_fixed, g->cube_fixed, (size_t)g->n_cube));
-    CSB_TRY(dev_upload(c, &B.ec_cam, g->ec_cam, (size_t)g->n_ec)); CSB_TRY(dev_upload(c, &B.ec_cube, g->ec_cube, (size_t)g->n_ec));
-    CSB_TRY(dev_upload(c, &B.ec_meas, g->ec_meas, (size_t)g->n_ec * 10)); CSB_TRY(dev_upload(c, &B.ec_info, g->ec_info, (size_t)g->n_ec * 81));
-    CSB_TRY(dev_upload(c, &B.ep_cam, g->ep_cam, (size_t)g->n_ep)); CSB_TRY(dev_upload(c, &B.ep_cube, g->ep_cube, (size_t)g->n_ep));
-    CSB_TRY(dev_upload(c, &B.ep_meas, g->ep_meas, (size_t)g->n_ep * 4)); CSB_TRY(dev_upload(c, &B.ep_info, g->ep_info, (size_t)g->n_ep * 16));
-    CSB_TRY(dev_upload(c, &B.ep_K, g->ep_K, (size_t)g->n_ep * 9));
-    CSB_TRY(dev_upload(c, &B.eo_i, g->eo_cam_i, (size_t)g->n_eo)); CSB_TRY(dev_upload(c, &B.eo_j, g->eo_cam_j, (size_t)g->n_eo));
-    CSB_TRY(dev_upload(c, &B.eo_meas, g->eo_meas, (size_t)g->n_eo * 7)); CSB_TRY(dev_upload(c, &B.eo_info, g->eo_info, (size_t)g->n_eo * 36));
-
-    // buildStructure(): per-vertex adjacency in edge order ec, ep, eo (block_solver.hpp:142-295 allocates the blocks;
-    // sparse_optimizer.cpp:482-487 fixes the edge order)
-    std::vector<std::vector<std::pair<int64_t, int64_t>>> cam_adj(g->n_cam), cube_adj(g->n_cube);
-    for (int e = 0; e < g->n_ec; e++) {
-        int64_t r = (int64_t)132 * e;
-        cam_adj[g->ec_cam[e]].push_back({r, r + 36});
-        cube_adj[g->ec_cube[e]].push_back({r + 42, r + 42 + 81});
-    }
-    for (int e = 0; e < g->n_ep; e++) {
-        int64_t r = (int64_t)132 * (g->n_ec + e);
-        cam_adj[g->ep_cam[e]].push_back({r, r + 36});
-        cube_adj[g->ep_cube[e]].push_back({r + 42, r + 42 + 81});
-    }
-    for (int e = 0; e < g->n_eo; e++) {
-        int64_t r = (int64_t)132 * (g->n_ec + g->n_ep) + (int64_t)84 * e;
-        cam_adj[g->eo_cam_i[e]].push_back({r, r + 36});
-        cam_adj[g->eo_cam_j[e]].push_back({r + 42, r + 42 + 36});
-    }
-    auto flatten = [&](const std::vector<std::vector<std::pair<int64_t, int64_t>>>& adj, const int** d_ptr, const int64_t** d_H, const int64_t** d_b) -> int {
-        std::vector<int> ptr(adj.size() + 1, 0);
-        std::vector<int64_t> hh, bb;
-        for (size_t v = 0; v < adj.size(); v++) {
-            ptr[v + 1] = ptr[v] + (int)adj[v].size();
-            for (auto& pr : adj[v]) { hh.push_back(pr.first); bb.push_back(pr.second); }
-        }
-        CSB_TRY(dev_upload(c, d_ptr, ptr.data(), ptr.size()));
-        CSB_TRY(dev_upload(c, d_H, hh.data(), hh.size()));
-        CSB_TRY(dev_upload(c, d_b, bb.data(), bb.size()));
-        CSB_CUDA(c, cudaStreamSynchronize(c->stream));  // host vectors go out of scope
-        return CSB_OK;
-    };
-    CSB_TRY(flatten(cam_adj, &B.cam_adj_ptr, &B.cam_adj_H, &B.cam_adj_b));
-    CSB_TRY(flatten(cube_adj, &B.cube_adj_ptr, &B.cube_adj_H, &B.cube_adj_b));
-
-    double* tmp = nullptr;
-    CSB_TRY(dev_alloc(c, &tmp, (size_t)g->n_cam * 7)); B.cams7 = tmp;
-    CSB_TRY(dev_alloc(c, &tmp, (size_t)g->n_cube * 10)); B.cubes10 = tmp;
-    CSB_TRY(dev_alloc(c, &B.ec_err, (size_t)g->n_ec * 9)); CSB_TRY(dev_alloc(c, &B.ep_err, (size_t)g->n_ep * 4)); CSB_TRY(dev_alloc(c, &B.eo_err, (size_t)g->n_eo * 6));
-    CSB_TRY(dev_alloc(c, &B.ec_Ji, (size_t)g->n_ec * 54)); CSB_TRY(dev_alloc(c, &B.ec_Jj, (size_t)g->n_ec * 81));
-    CSB_TRY(dev_alloc(c, &B.ep_Ji, (size_t)g->n_ep * 24)); CSB_TRY(dev_alloc(c, &B.ep_Jj, (size_t)g->n_ep * 36));
-    CSB_TRY(dev_alloc(c, &B.eo_Ji, (size_t)g->n_eo * 36)); CSB_TRY(dev_alloc(c, &B.eo_Jj, (size_t)g->n_eo * 36));
-    CSB_TRY(dev_alloc(c, &B.ec_Hij, (size_t)g->n_ec * 54)); CSB_TRY(dev_alloc(c, &B.ep_Hij, (size_t)g->n_ep * 54)); CSB_TRY(dev_alloc(c, &B.eo_Hij, (size_t)g->n_eo * 36));
-    CSB_TRY(dev_alloc(c, &B.contrib, (size_t)132 * (g->n_ec + g->n_ep) + (size_t)84 * g->n_eo));
-    CSB_TRY(dev_alloc(c, &B.edge_chi2, (size_t)(g->n_ec + g->n_ep + g->n_eo)));
-    CSB_TRY(dev_alloc(c, &B.H_cam, (size_t)g->n_cam * 36)); CSB_TRY(dev_alloc(c, &B.b_cam, (size_t)g->n_cam * 6));
-    CSB_TRY(dev_alloc(c, &B.H_cube, (size_t)g->n_cube * 81)); CSB_TRY(dev_alloc(c, &B.b_cube, (size_t)g->n_cube * 9));
-    CSB_TRY(dev_alloc(c, &B.chi2, 1));
+    ba_solver_release(s);
+    HostGraph& h = s.host;
+    h.cam_fixed.assign(g->cam_fixed, g->cam_fixed + g->n_cam); h.cube_fixed.assign(g->cube_fixed, g->cube_fixed + g->n_cube);
+    h.ec_cam.assign(g->ec_cam, g->ec_cam + g->n_ec); h.ec_cube.assign(g->ec_cube, g->ec_cube + g->n_ec);
+    h.ec_meas.assign(g->ec_meas, g->ec_meas + (size_t)g->n_ec * 10); h.ec_info.assign(g->ec_info, g->ec_info + (size_t)g->n_ec * 81);
+    h.ep_cam.assign(g->ep_cam, g->ep_cam + g->n_ep); h.ep_cube.assign(g->ep_cube, g->ep_cube + g->n_ep);
+    h.ep_meas.assign(g->ep_meas, g->ep_meas + (size_t)g->n_ep * 4); h.ep_info.assign(g->ep_info, g->ep_info + (size_t)g->n_ep * 16);
+    h.ep_K.assign(g->ep_K, g->ep_K + (size_t)g->n_ep * 9);
+    h.eo_i.assign(g->eo_cam_i, g->eo_cam_i + g->n_eo); h.eo_j.assign(g->eo_cam_j, g->eo_cam_j + g->n_eo);
+    h.eo_meas.assign(g->eo_meas, g->eo_meas + (size_t)g->n_eo * 7); h.eo_info.assign(g->eo_info, g->eo_info + (size_t)g->n_eo * 36);
+    s.has_graph = false; s.has_estimates = false;
+    CSB_TRY(sync_device(c, Counts{0, 0, 0, 0, 0}));
     CSB_CUDA(c, cudaStreamSynchronize(c->stream));
     s.has_graph = true;
+    return CSB_OK;
+}
+
+int csb_ba_add_frame(csb_context* c, const csb_ba_frame* f, int32_t* cam_index_out) {
+    if (!c || !f) return CSB_ERR_INVALID;
+    BAState& s = c->ba;
+    if (!s.has_graph) { c->err = "csb_ba_add_frame before csb_ba_set_graph (an empty graph is a valid start)"; return CSB_ERR_STATE; }
+    if (!f->cam7 || f->n_new_cubes < 0 || f->n_ec < 0 || f->n_eo < 0) { c->err = "csb_ba_add_frame: bad frame"; return CSB_ERR_INVALID; }
+    if ((f->n_new_cubes && (!f->new_cubes10 || !f->new_cube_fixed)) || (f->n_ec && (!f->ec_cube || !f->ec_meas || !f->ec_info)) ||
+        (f->n_eo && (!f->eo_cam_i || !f->eo_meas || !f->eo_info))) { c->err = "csb_ba_add_frame: null array with a non-zero count"; return CSB_ERR_INVALID; }
+    if (s.n_cam + s.n_cube > 0 && !s.has_estimates) { c->err = "csb_ba_add_frame: the existing vertices have no estimates yet"; return CSB_ERR_STATE; }
+    const Counts old{s.n_cam, s.n_cube, s.n_ec, s.n_ep, s.n_eo};
+    const int cam = old.n_cam, n_cube_new = old.n_cube + f->n_new_cubes;
+    if (!in_range(f->ec_cube, f->n_ec, n_cube_new) || !in_range(f->eo_cam_i, f->n_eo, cam)) { c->err = "csb_ba_add_frame: edge vertex index out of range"; return CSB_ERR_INVALID; }
+    CSB_CUDA(c, cudaSetDevice(c->device));
+    HostGraph& h = s.host;
+    h.cam_fixed.push_back(f->cam_fixed ? 1 : 0);
+    for (int i = 0; i < f->n_new_cubes; i++) h.cube_fixed.push_back(f->new_cube_fixed[i] ? 1 : 0);
+    for (int e = 0; e < f->n_ec; e++) { h.ec_cam.push_back(cam); h.ec_cube.push_back(f->ec_cube[e]); }
+    h.ec_meas.insert(h.ec_meas.end(), f->ec_meas, f->ec_meas + (size_t)f->n_ec * 10);
+    h.ec_info.insert(h.ec_info.end(), f->ec_info, f->ec_info + (size_t)f->n_ec * 81);
+    for (int e = 0; e < f->n_eo; e++) { h.eo_i.push_back(f->eo_cam_i[e]); h.eo_j.push_back(cam); }
+    h.eo_meas.insert(h.eo_meas.end(), f->eo_meas, f->eo_meas + (size_t)f->n_eo * 7);
+    h.eo_info.insert(h.eo_info.end(), f->eo_info, f->eo_info + (size_t)f->n_eo * 36);
+    CSB_TRY(sync_device(c, old));
+    // estimates of the new vertices behind the (possibly optimised) ones the device holds
+    CSB_CUDA(c, cudaMemcpyAsync(const_cast<double*>(s.B.cams7) + 7 * (size_t)cam, f->cam7, 56, cudaMemcpyHostToDevice, c->stream));
+    if (f->n_new_cubes)
+        CSB_CUDA(c, cudaMemcpyAsync(const_cast<double*>(s.B.cubes10) + 10 * (size_t)old.n_cube, f->new_cubes10, 80 * (size_t)f->n_new_cubes, cudaMemcpyHostToDevice, c->stream));
+    CSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    s.has_estimates = true;
+    if (cam_index_out) *cam_index_out = cam;
     return CSB_OK;
 }
 
@@ -415,6 +506,7 @@ static int ba_run_impl(csb_context* c, bool want_J) {
     CSB_CUDA(c, cudaSetDevice(c->device));
     CSB_CUDA(c, ba_launch(s.B, want_J, c->stream, &s.launches_last, s.analytic));
     s.ran = true;
+    s.have_J = want_J;
     return CSB_OK;
 }
 
@@ -433,6 +525,10 @@ int csb_ba_download(csb_context* c, const csb_ba_output* o) {
     if (!c || !o) return CSB_ERR_INVALID;
     BAState& s = c->ba;
     if (!s.ran) { c->err = "csb_ba_download before csb_ba_run"; return CSB_ERR_STATE; }
+    if (!s.have_J && (o->ec_Ji || o->ec_Jj || o->ep_Ji || o->ep_Jj || o->eo_Ji || o->eo_Jj)) {
+        c->err = "csb_ba_download: Jacobians requested, but the last run did not materialise them (use csb_ba_linearize with Jacobian pointers)";
+        return CSB_ERR_STATE;
+    }
     CSB_CUDA(c, cudaSetDevice(c->device));
     const BABuffers& B = s.B;
     auto dl = [&](double* dst, const double* src, size_t n) -> int {

@@ -47,7 +47,7 @@ struct SolveView {
     int n_blk;
     const int *cam_pl_ptr, *cam_pl_e;   // pl edges of every free camera, edge order
     const int *cube_pl_ptr, *cube_pl_e; // pl edges of every free cuboid, edge order
-    double *Ainv, *tl, *W, *S, *rhs, *x_cam, *x_cube, *scal;  // scal: [0] trial chi2, [1] scale, [2] max diag, [3] cholesky ok (1/0)
+    double *Ainv, *tl, *W, *S, *rhs, *x_cam, *x_cube, *scal;  // scal: [0] trial chi2, [1] scale, [2] max diag, [3] cholesky ok (1/0), [4] lambda of the trial
     double *trial_cams7, *trial_cubes10, *edge_chi2;
     double* linv;      // inverses of the diagonal Cholesky tiles (ld / 32 tiles of 32 x 32)
     unsigned* bar;     // grid barrier of k_chol_solve: [0] arrivals, [1] generation
@@ -59,9 +59,10 @@ __device__ __forceinline__ const double* pl_hij(const BABuffers& B, const SolveV
 }
 
 // ---- (H_ll + lambda I)^-1 by Cholesky, one thread per free cuboid ---------------------------------------------------
-__global__ void k_cube_inv(BABuffers B, SolveView V, double lambda) {
+__global__ void k_cube_inv(BABuffers B, SolveView V) {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= V.n_fl) return;
+    const double lambda = V.scal[4];
     const int v = V.fl_cube[l];
     double A[81], Li[81];
     for (int i = 0; i < 81; i++) A[i] = B.H_cube[81 * (size_t)v + i];  // symmetric: storage order irrelevant
@@ -118,9 +119,10 @@ __global__ void k_edge_w(BABuffers B, SolveView V) {
 }
 
 // one warp per listed 6x6 block of the lower block triangle of S (row-major, leading dimension ld)
-__global__ void __launch_bounds__(128) k_schur_blocks(BABuffers B, SolveView V, double lambda) {
+__global__ void __launch_bounds__(128) k_schur_blocks(BABuffers B, SolveView V) {
     const int blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (blk >= V.n_blk) return;
+    const double lambda = V.scal[4];
     const int I = V.blk_I[blk], J = V.blk_J[blk];
     for (int el = lane; el < 36; el += 32) {
         const int r = el / 6, c = el - r * 6;
@@ -143,16 +145,15 @@ __global__ void __launch_bounds__(128) k_schur_blocks(BABuffers B, SolveView V, 
     }
 }
 
-// padding rows/cols of S: identity on the diagonal so that the factorisation runs over full tiles
-__global__ void k_schur_pad(SolveView V) {
-    const int i = V.n + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < V.ld) { V.S[(size_t)i * V.ld + i] = 1.0; V.rhs[i] = 0.0; }
-}
-
+// r_I = b_I - sum_e W_e b_l(e); the threads past the system fill the padding rows / columns of S (identity on the diagonal, zero
+// right-hand side) so that the factorisation runs over full tiles.  Launched over ld threads, after S has been cleared.
 __global__ void k_schur_rhs(BABuffers B, SolveView V) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int I = t / 6, r = t - I * 6;
-    if (I >= V.n_fc) return;
+    if (t >= V.n) {
+        if (t < V.ld) { V.S[(size_t)t * V.ld + t] = 1.0; V.rhs[t] = 0.0; }
+        return;
+    }
     double acc = B.b_cam[6 * (size_t)V.fc_cam[I] + r];
     for (int q = V.cam_pl_ptr[I]; q < V.cam_pl_ptr[I + 1]; q++) {
         const int e = V.cam_pl_e[q];
@@ -473,9 +474,10 @@ __global__ void __launch_bounds__(128) k_edge_chi2(BABuffers B, const double* ca
 }
 
 // fixed-order reductions by one warp: out[0] = sum(edge chi2), out[1] = x^T (lambda x + b) + 1e-3
-__global__ void __launch_bounds__(32) k_trial_scalars(BABuffers B, SolveView V, double lambda) {
+__global__ void __launch_bounds__(32) k_trial_scalars(BABuffers B, SolveView V) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x;
+    const double lambda = V.scal[4];
     double s = 0;
     const int n_all = B.n_ec + B.n_ep + B.n_eo;
     for (int i = lane; i < n_all; i += 32) s += V.edge_chi2[i];
@@ -500,7 +502,6 @@ __global__ void __launch_bounds__(32) k_max_diag(BABuffers B, SolveView V) {
     if (lane == 0) V.scal[2] = m;
 }
 
-__global__ void k_set_flag(double* p, double v) { *p = v; }
 
 // ---- host side ------------------------------------------------------------------------------------------------------
 struct SolveState {
@@ -508,6 +509,11 @@ struct SolveState {
     int chol_ctas = 1;  // grid of the cooperative k_chol_solve: one CTA per SM, all resident
     SolveView V{};
     std::vector<void*> allocs;
+    // one LM trial / one linearisation as CUDA graphs (captured on first use; a failed capture leaves the direct launches)
+    cudaGraphExec_t trial_graph = nullptr, lin_graph[2] = {nullptr, nullptr};
+    bool trial_graph_failed = false, lin_graph_failed[2] = {false, false};
+    int trial_nodes = 0, lin_nodes[2] = {0, 0};
+    double* h_pin = nullptr;  // pinned: [0..1] = {cholesky-ok flag, lambda} going up, [2..6] = scalars coming back
 };
 
 }  // namespace csb
@@ -597,7 +603,7 @@ int build_solver(csb_context* c) {
     CSB_TRY(up(c, A, &V.cam_pl_ptr, cam_pl_ptr)); CSB_TRY(up(c, A, &V.cam_pl_e, cam_pl_e)); CSB_TRY(up(c, A, &V.cube_pl_ptr, cube_pl_ptr)); CSB_TRY(up(c, A, &V.cube_pl_e, cube_pl_e));
     CSB_TRY(al(c, A, &V.Ainv, 81 * (size_t)V.n_fl)); CSB_TRY(al(c, A, &V.tl, 9 * (size_t)V.n_fl)); CSB_TRY(al(c, A, &V.W, 54 * (size_t)V.n_pl));
     CSB_TRY(al(c, A, &V.S, (size_t)V.ld * V.ld)); CSB_TRY(al(c, A, &V.rhs, (size_t)V.ld)); CSB_TRY(al(c, A, &V.x_cube, 9 * (size_t)V.n_fl));
-    CSB_TRY(al(c, A, &V.scal, 8)); CSB_TRY(al(c, A, &V.trial_cams7, 7 * (size_t)s.n_cam)); CSB_TRY(al(c, A, &V.trial_cubes10, 10 * (size_t)s.n_cube));
+    CSB_TRY(al(c, A, &V.scal, 8)); CSB_CUDA(c, cudaMallocHost(&st->h_pin, 8 * sizeof(double))); CSB_TRY(al(c, A, &V.trial_cams7, 7 * (size_t)s.n_cam)); CSB_TRY(al(c, A, &V.trial_cubes10, 10 * (size_t)s.n_cube));
     CSB_TRY(al(c, A, &V.edge_chi2, (size_t)(s.n_ec + s.n_ep + s.n_eo)));
     CSB_TRY(al(c, A, &V.linv, (size_t)V.ld * NB)); CSB_TRY(al(c, A, &V.bar, 4));
     CSB_CUDA(c, cudaMemset(V.bar, 0, 16));
@@ -619,10 +625,57 @@ void ba_solver_release(BAState& s) {
     SolveState* st = reinterpret_cast<SolveState*>(s.solver);
     if (!st) return;
     for (void* p : st->allocs) cudaFree(p);
+    if (st->trial_graph) cudaGraphExecDestroy(st->trial_graph);
+    for (int i = 0; i < 2; i++) if (st->lin_graph[i]) cudaGraphExecDestroy(st->lin_graph[i]);
+    if (st->h_pin) cudaFreeHost(st->h_pin);
     delete st;
     s.solver = nullptr;
 }
 }  // namespace csb
+
+namespace {
+
+// the kernels of one LM trial, in stream order (10 kernels + 1 memset); returns the number of kernels
+int launch_trial(const BABuffers& B, const SolveView& V, const SolveState* st, int n_cam, int n_cube, int n_edges, cudaStream_t sm, cudaError_t* err) {
+    int n = 0;
+    if (V.n_fl) { k_cube_inv<<<(V.n_fl + 31) / 32, 32, 0, sm>>>(B, V); n++; }
+    if (V.n_pl) { k_edge_w<<<(V.n_pl * 54 + 127) / 128, 128, 0, sm>>>(B, V); n++; }
+    *err = cudaMemsetAsync(V.S, 0, sizeof(double) * (size_t)V.ld * V.ld, sm);
+    if (*err != cudaSuccess) return n;
+    if (V.n_blk) { k_schur_blocks<<<(V.n_blk * 32 + 127) / 128, 128, 0, sm>>>(B, V); n++; }
+    k_schur_rhs<<<(V.ld + 127) / 128, 128, 0, sm>>>(B, V); n++;
+    {
+        double* a_S = V.S; int a_ld = V.ld; double* a_v = V.rhs; double* a_linv = V.linv; double* a_ok = V.scal + 3; unsigned* a_bar = V.bar;
+        void* args[] = {&a_S, &a_ld, &a_v, &a_linv, &a_ok, &a_bar};
+        *err = cudaLaunchCooperativeKernel((const void*)k_chol_solve, dim3(st->chol_ctas), dim3(CF_THREADS), args, 0, sm);
+        if (*err != cudaSuccess) return n;
+        n++;
+    }
+    if (V.n_fl) { k_cube_back<<<V.n_fl, 32, 0, sm>>>(B, V); n++; }
+    k_apply<<<(n_cam + n_cube + 127) / 128, 128, 0, sm>>>(B, V); n++;
+    if (n_edges) { k_edge_chi2<<<(n_edges + 127) / 128, 128, 0, sm>>>(B, V.trial_cams7, V.trial_cubes10, V.edge_chi2); n++; }
+    k_trial_scalars<<<1, 32, 0, sm>>>(B, V); n++;
+    *err = cudaGetLastError();
+    return n;
+}
+
+// capture `body` (which issues work on `sm`) into an executable graph; on any failure the stream is left usable and *out stays NULL
+template <class F>
+bool capture_graph(cudaStream_t sm, cudaGraphExec_t* out, F body) {
+    if (cudaStreamBeginCapture(sm, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
+    const bool ok_body = body();
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(sm, &g);
+    if (e != cudaSuccess || !ok_body || !g) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return false; }
+    cudaGraphExec_t ex = nullptr;
+    const cudaError_t e2 = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    if (e2 != cudaSuccess) { cudaGetLastError(); return false; }
+    *out = ex;
+    return true;
+}
+
+}  // namespace
 
 extern "C" int csb_ba_optimize(csb_context* c, int iterations, double* cams7_out, double* cubes10_out, csb_ba_optimize_stats* stats) {
     if (!c || iterations < 0) return CSB_ERR_INVALID;
@@ -639,47 +692,50 @@ extern "C" int csb_ba_optimize(csb_context* c, int iterations, double* cams7_out
     const double tau = 1e-5, goodUp = 2. / 3., goodLow = 1. / 3.;
     const int maxTrials = 10;
     double lambda = -1, ni = 2;
-    int nBad = 0, it_done = 0, trials_total = 0, launches = 0;
-    double chi_final = 0, h_scal[4] = {0, 0, 0, 0};
+    int nBad = 0, it_done = 0, trials_total = 0, kernels = 0, launches = 0;
+    double chi_final = 0;
+    double* hp = st->h_pin;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (stats) { CSB_CUDA(c, cudaEventCreate(&ev0)); CSB_CUDA(c, cudaEventCreate(&ev1)); CSB_CUDA(c, cudaEventRecord(ev0, sm)); }
+    const int am = c->ba.analytic ? 1 : 0;
     for (int it = 0; it < iterations; it++) {
-        int nl = 0;
-        CSB_CUDA(c, ba_launch(B, false, sm, &nl, c->ba.analytic));  // computeActiveErrors + buildSystem at the current estimates
-        launches += nl;
-        if (it == 0) { k_max_diag<<<1, 32, 0, sm>>>(B, V); launches++; }
-        double h2[2];
-        CSB_CUDA(c, cudaMemcpyAsync(&h2[0], B.chi2, 8, cudaMemcpyDeviceToHost, sm));
-        CSB_CUDA(c, cudaMemcpyAsync(&h2[1], V.scal + 2, 8, cudaMemcpyDeviceToHost, sm));
+        // computeActiveErrors + buildSystem at the current estimates: one graph launch
+        if (!st->lin_graph[am] && !st->lin_graph_failed[am]) {
+            int nl = 0;
+            const bool analytic = c->ba.analytic;
+            if (!capture_graph(sm, &st->lin_graph[am], [&]() { return ba_launch(B, false, sm, &nl, analytic) == cudaSuccess; })) st->lin_graph_failed[am] = true;
+            st->lin_nodes[am] = nl;
+        }
+        if (st->lin_graph[am]) { CSB_CUDA(c, cudaGraphLaunch(st->lin_graph[am], sm)); kernels += st->lin_nodes[am]; launches++; }
+        else { int nl = 0; CSB_CUDA(c, ba_launch(B, false, sm, &nl, c->ba.analytic)); kernels += nl; launches += nl; }
+        if (it == 0) { k_max_diag<<<1, 32, 0, sm>>>(B, V); kernels++; launches++; }
+        CSB_CUDA(c, cudaMemcpyAsync(&hp[2], B.chi2, 8, cudaMemcpyDeviceToHost, sm));
+        CSB_CUDA(c, cudaMemcpyAsync(&hp[3], V.scal + 2, 8, cudaMemcpyDeviceToHost, sm));
         CSB_CUDA(c, cudaStreamSynchronize(sm));
-        double currentChi = h2[0], tempChi = currentChi;
+        double currentChi = hp[2], tempChi = currentChi;
         const double iniChi = currentChi;
-        if (it == 0) { lambda = tau * h2[1]; ni = 2; nBad = 0; }
+        if (it == 0) { lambda = tau * hp[3]; ni = 2; nBad = 0; }
         double rho = 0;
         int qmax = 0;
         do {
-            k_set_flag<<<1, 1, 0, sm>>>(V.scal + 3, 1.0);
-            if (V.n_fl) k_cube_inv<<<(V.n_fl + 31) / 32, 32, 0, sm>>>(B, V, lambda);
-            if (V.n_pl) k_edge_w<<<(V.n_pl * 54 + 127) / 128, 128, 0, sm>>>(B, V);
-            CSB_CUDA(c, cudaMemsetAsync(V.S, 0, sizeof(double) * (size_t)V.ld * V.ld, sm));
-            if (V.n_blk) k_schur_blocks<<<(V.n_blk * 32 + 127) / 128, 128, 0, sm>>>(B, V, lambda);
-            if (V.n_fc) k_schur_rhs<<<(V.n + 127) / 128, 128, 0, sm>>>(B, V);
-            k_schur_pad<<<1, NB, 0, sm>>>(V);
-            launches += 6;
-            {
-                double* a_S = V.S; int a_ld = V.ld; double* a_v = V.rhs; double* a_linv = V.linv; double* a_ok = V.scal + 3; unsigned* a_bar = V.bar;
-                void* args[] = {&a_S, &a_ld, &a_v, &a_linv, &a_ok, &a_bar};
-                CSB_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_chol_solve, dim3(st->chol_ctas), dim3(CF_THREADS), args, 0, sm));
-                launches++;
+            hp[0] = 1.0; hp[1] = lambda;  // cholesky-ok flag, lambda of this trial -> scal[3..4]
+            CSB_CUDA(c, cudaMemcpyAsync(V.scal + 3, hp, 16, cudaMemcpyHostToDevice, sm));
+            if (!st->trial_graph && !st->trial_graph_failed) {
+                cudaError_t ce = cudaSuccess;
+                int nk = 0;
+                if (!capture_graph(sm, &st->trial_graph, [&]() { nk = launch_trial(B, V, st, s.n_cam, s.n_cube, n_edges, sm, &ce); return ce == cudaSuccess; })) st->trial_graph_failed = true;
+                st->trial_nodes = nk;
             }
-            if (V.n_fl) k_cube_back<<<V.n_fl, 32, 0, sm>>>(B, V);
-            k_apply<<<(s.n_cam + s.n_cube + 127) / 128, 128, 0, sm>>>(B, V);
-            if (n_edges) k_edge_chi2<<<(n_edges + 127) / 128, 128, 0, sm>>>(B, V.trial_cams7, V.trial_cubes10, V.edge_chi2);
-            k_trial_scalars<<<1, 32, 0, sm>>>(B, V, lambda);
-            launches += 5;
-            CSB_CUDA(c, cudaGetLastError());
-            CSB_CUDA(c, cudaMemcpyAsync(h_scal, V.scal, 32, cudaMemcpyDeviceToHost, sm));
+            if (st->trial_graph) { CSB_CUDA(c, cudaGraphLaunch(st->trial_graph, sm)); kernels += st->trial_nodes; launches++; }
+            else {
+                cudaError_t ce = cudaSuccess;
+                const int nk = launch_trial(B, V, st, s.n_cam, s.n_cube, n_edges, sm, &ce);
+                CSB_CUDA(c, ce);
+                kernels += nk; launches += nk;
+            }
+            CSB_CUDA(c, cudaMemcpyAsync(&hp[4], V.scal, 32, cudaMemcpyDeviceToHost, sm));
             CSB_CUDA(c, cudaStreamSynchronize(sm));
+            const double* h_scal = &hp[4];
             const bool ok2 = h_scal[3] != 0.0;
             tempChi = ok2 ? h_scal[0] : std::numeric_limits<double>::max();
             rho = (currentChi - tempChi) / h_scal[1];
@@ -708,7 +764,7 @@ extern "C" int csb_ba_optimize(csb_context* c, int iterations, double* cams7_out
     CSB_CUDA(c, cudaStreamSynchronize(sm));
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
-        stats->iterations = it_done; stats->trials = trials_total; stats->n_kernel_launches = launches;
+        stats->iterations = it_done; stats->trials = trials_total; stats->n_kernel_launches = kernels; stats->n_launches = launches;
         stats->chi2 = chi_final; stats->lambda = lambda; stats->schur_dim = V.n;
         cudaEventElapsedTime(&stats->gpu_ms, ev0, ev1);
         cudaEventDestroy(ev0); cudaEventDestroy(ev1);

@@ -229,7 +229,15 @@ __global__ void __launch_bounds__(DM_THREADS, 4) k_distmap(DetectBuffers B, cons
 
     // ---- (1) Sobel, magnitude, non-maximum suppression
     {
-        const int n_wc = (8 * RB + DM_COLS - 1) / DM_COLS;
+        const int n_wc = (W + DM_COLS - 1) / DM_COLS;
+        // plane bytes past the last warp column (columns >= W, padding of the 32-pixel words): no edge, no candidate
+        {
+            const int b0 = n_wc * (DM_COLS / 8), nb = RB - b0;
+            for (int i = tid; i < H * nb; i += DM_THREADS) {
+                const int y = i / nb, b = b0 + (i - y * nb);
+                S8[(size_t)y * RB + b] = 0; W8[(size_t)y * RB + b] = 0;
+            }
+        }
         int n_st = (2 * DM_WARPS) / n_wc;
         n_st = max(1, min(n_st, (H + 7) >> 3));
         const int SR = (H + n_st - 1) / n_st;

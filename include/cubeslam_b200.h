@@ -214,6 +214,27 @@ typedef struct csb_ba_output {
 
 /* buildStructure(): upload topology, measurements and information matrices; build per-vertex adjacency. */
 int csb_ba_set_graph(csb_context* ctx, const csb_ba_graph* graph);
+/* One more keyframe for an online caller (object_slam/src/main_obj.cpp:738-803 adds, per frame, a VertexSE3Expmap, the EdgeSE3Cuboid
+ * measurements of that frame, an EdgeSE3Expmap to the previous frame and -- when a landmark is seen for the first time -- a VertexCuboid,
+ * then calls optimize() again).  The new camera gets index n_cam, the new cuboids n_cube .. n_cube + n_new_cubes - 1; ec edges start at the
+ * new camera, eo edges end at it.  The result is the same device state csb_ba_set_graph would build from the concatenated arrays (same
+ * edge order, so the same sums), but nothing is reallocated (arrays grow geometrically) and the estimates on the device -- e.g. the ones
+ * csb_ba_optimize left there -- are kept; the new vertices take the estimates passed here.  Start from csb_ba_set_graph (an empty
+ * graph, all counts 0, is allowed). */
+typedef struct csb_ba_frame {
+    const double* cam7;            /* estimate of the new camera: world->camera, x y z qx qy qz qw */
+    int32_t cam_fixed;
+    int32_t n_new_cubes;
+    const double* new_cubes10;     /* n_new_cubes x 10 */
+    const int32_t* new_cube_fixed; /* n_new_cubes */
+    int32_t n_ec;
+    const int32_t* ec_cube;        /* n_ec: cuboid index (may be one of the new ones) */
+    const double *ec_meas, *ec_info; /* n_ec x 10, n_ec x 81 */
+    int32_t n_eo;
+    const int32_t* eo_cam_i;       /* n_eo: the other (earlier) camera; the edge is (cam_i -> new camera) */
+    const double *eo_meas, *eo_info; /* n_eo x 7, n_eo x 36 */
+} csb_ba_frame;
+int csb_ba_add_frame(csb_context* ctx, const csb_ba_frame* frame, int32_t* cam_index_out);
 /* computeActiveErrors() + buildSystem() with HOST vertex estimates in, HOST blocks out. */
 int csb_ba_linearize(csb_context* ctx, const double* cams7, const double* cubes10, const csb_ba_output* out);
 /* Device-resident: upload estimates once, linearise repeatedly (async), download when needed. */
@@ -239,12 +260,12 @@ int csb_ba_set_jacobian_mode(csb_context* ctx, int mode);
 typedef struct csb_ba_optimize_stats {
     int32_t iterations;        /* outer LM iterations run */
     int32_t trials;            /* linear solves (lambda trials) over all iterations */
-    int32_t n_kernel_launches;
+    int32_t n_kernel_launches; /* kernels executed */
     int32_t schur_dim;         /* size of the reduced camera system (6 x free cameras) */
     double chi2;               /* activeRobustChi2 after the last accepted step */
     double lambda;
     float gpu_ms;              /* device time of the whole call */
-    float pad;
+    int32_t n_launches;        /* host launch calls: a linearisation and an LM trial are one CUDA-graph launch each */
 } csb_ba_optimize_stats;
 int csb_ba_optimize(csb_context* ctx, int iterations, double* cams7_out, double* cubes10_out, csb_ba_optimize_stats* stats);
 
@@ -348,7 +369,7 @@ typedef struct csb_edlines_stats {
     int64_t n_lines;     /* segments written over the whole batch */
     int64_t n_anchors, n_chain_px, n_chains;
     int64_t h2d_bytes, d2h_bytes;
-    int32_t n_kernel_launches;
+    int32_t n_kernel_launches; /* kernels executed */
     int32_t n_frames_failed; /* frames that hit EdgeDrawing's capacity errors (the reference prints "Line Detection not finished": no lines) */
     float gpu_ms_maps, gpu_ms_draw, gpu_ms_fit, reserved;
 } csb_edlines_stats;

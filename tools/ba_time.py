@@ -29,5 +29,5 @@ for _ in range(3):
     t0 = time.perf_counter()
     _, _, so = ctx.ba_optimize(5)
     wall = 1e3 * (time.perf_counter() - t0)
-    print("optimize(5): %.3f ms gpu, %.3f ms wall, %d iterations, %d linear solves, %d launches, chi2 %.6g" % (so.gpu_ms, wall, so.iterations, so.trials, so.n_kernel_launches, so.chi2))
+    print("optimize(5): %.3f ms gpu, %.3f ms wall, %d iterations, %d linear solves, %d kernels in %d launches, chi2 %.6g" % (so.gpu_ms, wall, so.iterations, so.trials, so.n_kernel_launches, so.n_launches, so.chi2))
 ctx.close()
