@@ -151,7 +151,7 @@ __global__ void k_schur_rhs(BABuffers B, SolveView V) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int I = t / 6, r = t - I * 6;
     if (t >= V.n) {
-        if (t < V.ld) { V.S[(size_t)t * V.ld + t] = 1.0; V.rhs[t] = 0.0; }
+        if (t < V.ld) { V.S[(size_t)t * V.ld + t] = 1.0; V.rhs[t] = 0.0; }  // (row ld of S is already zero there)
         return;
     }
     double acc = B.b_cam[6 * (size_t)V.fc_cam[I] + r];
@@ -163,6 +163,7 @@ __global__ void k_schur_rhs(BABuffers B, SolveView V) {
         for (int k = 0; k < 9; k++) acc = fma(-W[k * 6 + r], bl[k], acc);
     }
     V.rhs[6 * I + r] = acc;
+    V.S[(size_t)V.ld * V.ld + 6 * I + r] = acc;  // the right-hand side rides through the factorisation as row ld of S (k_chol_solve)
 }
 
 // ---- blocked Cholesky, lower, in place, row-major, 32x32 tiles ------------------------------------------------------
@@ -237,24 +238,41 @@ __global__ void __launch_bounds__(CF_THREADS) k_chol_solve(double* S, int ld, do
         const int k0 = k * NB;
         double* Lk = linv + (size_t)k * NB * NB;
         __syncthreads();  // the CTA's update of this tile is complete
+        CHOL_T(3);
         for (int i = tid; i < NB * NB; i += CF_THREADS) a[i / NB][i % NB] = S[(size_t)(k0 + i / NB) * ld + k0 + i % NB];
         __syncthreads();
-        for (int j = 0; j < NB; j++) {
-            // every thread forms 1 / sqrt(d_jj) itself: one barrier less per column, the column is scaled by a multiplication
-            double d = a[j][j];
-            if (!(d > 0)) { if (tid == 0) *ok_flag = 0.0; d = 1.0; }
-            const double sd = sqrt(d), inv = 1.0 / sd;
-            __syncthreads();  // everyone has read a[j][j] and (previous column) finished the trailing update
-            if (tid == j) { a[j][j] = sd; dinv[j] = inv; }
-            else if (tid > j && tid < NB) a[tid][j] *= inv;
-            __syncthreads();
-            for (int idx = tid; idx < NB * NB; idx += CF_THREADS) {
-                const int r = idx >> 5, c = idx & 31;
-                if (c > j && c <= r) a[r][c] = fma(-a[r][j], a[c][j], a[r][c]);
+        CHOL_T(5);
+        if (warp == 0) {
+            // the whole 32 x 32 factorisation in ONE warp (lane = row) on the shared-memory tile: __syncwarp instead of two block barriers per
+            // column, 1 / sqrt by rsqrt; the other warps wait at the barrier below
+            bool ok = true;
+            for (int j = 0; j < NB; j++) {
+                double d = a[j][j];
+                if (!(d > 0)) { ok = false; d = 1.0; }
+                const double inv = rsqrt(d);
+                const double lj = (lane == j) ? d * inv : a[lane][j] * inv;  // column j of L (rows >= j)
+                __syncwarp();
+                if (lane >= j) a[lane][j] = lj;
+                if (lane == j) dinv[j] = inv;
+                __syncwarp();
+                // trailing update of row `lane`, eight columns at a time: all loads, then the multiply-adds, then the stores (element by
+                // element every iteration would wait for the previous store)
+                for (int c0 = j + 1; c0 <= lane; c0 += 8) {
+                    double v[8], l[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) { const bool in = c0 + u <= lane; v[u] = in ? a[lane][c0 + u] : 0.0; l[u] = in ? a[c0 + u][j] : 0.0; }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) v[u] = fma(-lj, l[u], v[u]);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) if (c0 + u <= lane) a[lane][c0 + u] = v[u];
+                }
+                __syncwarp();
             }
+            if (!ok && lane == 0) *ok_flag = 0.0;
+            CHOL_T(6);
+            tri_inverse_tile(a, b, dinv, lane);
+            CHOL_T(7);
         }
-        __syncthreads();
-        if (warp == 0) tri_inverse_tile(a, b, dinv, lane);
         __syncthreads();
         for (int i = tid; i < NB * NB; i += CF_THREADS) {
             const int r = i / NB, c = i % NB;
@@ -275,7 +293,7 @@ __global__ void __launch_bounds__(CF_THREADS) k_chol_solve(double* S, int ld, do
             __syncthreads();
             for (int i = tid; i < NB * NB; i += CF_THREADS) b[i / NB][i % NB] = Lk[i];
             __syncthreads();
-            const int n_rows = ld - k0 - NB;
+            const int n_rows = ld - k0 - NB + 1;  // + the right-hand side, row `ld` of S: L y = r comes out of the factorisation
             for (int r = cta * (CF_THREADS / 32) + warp; r < n_rows; r += G * (CF_THREADS / 32)) {
                 double* p = S + (size_t)(k0 + NB + r) * ld + k0;
                 const double mine = p[lane];
@@ -297,6 +315,16 @@ __global__ void __launch_bounds__(CF_THREADS) k_chol_solve(double* S, int ld, do
             const int tt = tiles - k - 1;
             const int n_t = tt * (tt + 1) / 2;
             const int tx = tid & 15, ty = tid >> 4;
+            // the right-hand-side row against tile column tj: one warp each, taken from the far end of the CTA list (CTA 0 has the diagonal tile)
+            for (int tj = (int)(G - 1 - cta) * (CF_THREADS / 32) + warp; tj < tt; tj += (int)G * (CF_THREADS / 32)) {
+                const int c0 = k0 + NB + tj * NB;
+                const double yv = S[(size_t)ld * ld + k0 + lane];
+                const double* Lj = S + (size_t)(c0 + lane) * ld + k0;  // lane = column of the tile = row c0 + lane of L
+                double acc = 0;
+#pragma unroll
+                for (int q = 0; q < NB; q++) acc = fma(__shfl_sync(0xffffffffu, yv, q), Lj[q], acc);
+                S[(size_t)ld * ld + c0 + lane] -= acc;
+            }
             for (int t = cta; t < n_t; t += G) {
                 int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
                 while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
@@ -331,29 +359,24 @@ __global__ void __launch_bounds__(CF_THREADS) k_chol_solve(double* S, int ld, do
         CHOL_T(1);
     }
     if (cta != 0) return;
-    // ---- the two triangular solves: CTA 0 alone (1.4 M multiply-adds; the lower triangle streams through once per direction)
-    // L y = r, block row by block row: y_i = Linv_ii (r_i - sum_{c < 32 i} L[row][c] y[c]); a warp per row, lanes over the columns (coalesced)
-    for (int k = 0; k < tiles; k++) {
-        const int k0 = k * NB;
-        const double* Lk = linv + (size_t)k * NB * NB;
-        __syncthreads();  // y of the previous block rows is in v
-        for (int rr = warp; rr < NB; rr += CF_THREADS / 32) {
-            const double* p = S + (size_t)(k0 + rr) * ld;
-            double t = 0;
-            for (int c = lane; c < k0; c += 32) t = fma(p[c], v[c], t);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            if (lane == 0) xs[rr] = v[k0 + rr] - t;
-        }
+    // ---- L y = r is row `ld` of the factorised matrix (the right-hand side went through the panel / update steps as one more row);
+    // CTA 0 alone does the backward solve (0.7 M multiply-adds; the lower triangle streams through once)
+    {
+        // last tile column: only the right-hand-side row is left below it
+        const int k0 = (tiles - 1) * NB;
+        const double* Lk = linv + (size_t)(tiles - 1) * NB * NB;
         __syncthreads();
         if (warp == 0) {
-            const double rv = xs[lane];  // y_k = Linv r_k: lane = row
+            double* p = S + (size_t)ld * ld + k0;
+            const double mine = p[lane];
             double acc = 0;
 #pragma unroll
-            for (int q = 0; q < NB; q++) acc = fma((q <= lane) ? Lk[lane * NB + q] : 0.0, __shfl_sync(0xffffffffu, rv, q), acc);
-            v[k0 + lane] = acc;
+            for (int q = 0; q < NB; q++) acc = fma(__shfl_sync(0xffffffffu, mine, q), (q <= lane) ? Lk[lane * NB + q] : 0.0, acc);
+            p[lane] = acc;
         }
+        __syncthreads();
     }
+    for (int i = tid; i < ld; i += CF_THREADS) v[i] = S[(size_t)ld * ld + i];
     __syncthreads();
     CHOL_T(4);
     // L^T x = y
@@ -379,7 +402,7 @@ __global__ void __launch_bounds__(CF_THREADS) k_chol_solve(double* S, int ld, do
     }
     CHOL_T(5);
 #ifdef CSB_CHOL_DEBUG
-    if (tid == 0) printf("k_chol_solve cycles: diag %lld barrier %lld panel %lld update %lld fwd %lld bwd %lld\n", tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5]);
+    if (tid == 0) printf("k_chol_solve cycles: diag-rest %lld barrier %lld panel %lld update %lld fwd %lld bwd+tile-load %lld factor %lld inverse %lld\n", tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7]);
 #endif
 }
 
@@ -602,7 +625,7 @@ int build_solver(csb_context* c) {
     CSB_TRY(up(c, A, &V.blk_ptr, blk_ptr)); CSB_TRY(up(c, A, &V.blk_I, blk_I)); CSB_TRY(up(c, A, &V.blk_J, blk_J)); CSB_TRY(up(c, A, &V.blk_ent, blk_ent));
     CSB_TRY(up(c, A, &V.cam_pl_ptr, cam_pl_ptr)); CSB_TRY(up(c, A, &V.cam_pl_e, cam_pl_e)); CSB_TRY(up(c, A, &V.cube_pl_ptr, cube_pl_ptr)); CSB_TRY(up(c, A, &V.cube_pl_e, cube_pl_e));
     CSB_TRY(al(c, A, &V.Ainv, 81 * (size_t)V.n_fl)); CSB_TRY(al(c, A, &V.tl, 9 * (size_t)V.n_fl)); CSB_TRY(al(c, A, &V.W, 54 * (size_t)V.n_pl));
-    CSB_TRY(al(c, A, &V.S, (size_t)V.ld * V.ld)); CSB_TRY(al(c, A, &V.rhs, (size_t)V.ld)); CSB_TRY(al(c, A, &V.x_cube, 9 * (size_t)V.n_fl));
+    CSB_TRY(al(c, A, &V.S, (size_t)(V.ld + 1) * V.ld)); /* + the right-hand side as row ld */ CSB_TRY(al(c, A, &V.rhs, (size_t)V.ld)); CSB_TRY(al(c, A, &V.x_cube, 9 * (size_t)V.n_fl));
     CSB_TRY(al(c, A, &V.scal, 8)); CSB_CUDA(c, cudaMallocHost(&st->h_pin, 8 * sizeof(double))); CSB_TRY(al(c, A, &V.trial_cams7, 7 * (size_t)s.n_cam)); CSB_TRY(al(c, A, &V.trial_cubes10, 10 * (size_t)s.n_cube));
     CSB_TRY(al(c, A, &V.edge_chi2, (size_t)(s.n_ec + s.n_ep + s.n_eo)));
     CSB_TRY(al(c, A, &V.linv, (size_t)V.ld * NB)); CSB_TRY(al(c, A, &V.bar, 4));
@@ -640,7 +663,7 @@ int launch_trial(const BABuffers& B, const SolveView& V, const SolveState* st, i
     int n = 0;
     if (V.n_fl) { k_cube_inv<<<(V.n_fl + 31) / 32, 32, 0, sm>>>(B, V); n++; }
     if (V.n_pl) { k_edge_w<<<(V.n_pl * 54 + 127) / 128, 128, 0, sm>>>(B, V); n++; }
-    *err = cudaMemsetAsync(V.S, 0, sizeof(double) * (size_t)V.ld * V.ld, sm);
+    *err = cudaMemsetAsync(V.S, 0, sizeof(double) * (size_t)(V.ld + 1) * V.ld, sm);
     if (*err != cudaSuccess) return n;
     if (V.n_blk) { k_schur_blocks<<<(V.n_blk * 32 + 127) / 128, 128, 0, sm>>>(B, V); n++; }
     k_schur_rhs<<<(V.ld + 127) / 128, 128, 0, sm>>>(B, V); n++;

@@ -1,20 +1,21 @@
 // edlines.cu -- EDLines line detection on the GPU: the use_LSD = false branch of line_lbd_detect::detect_filter_lines
 // (line_lbd/class/line_lbd_allclass.cpp:130-149, 200-235; what object_slam selects, main_obj.cpp:503-505).  SURVEY.md 8 "next" row f-2.
 //
-// The algorithm lives in edlines_dev.cuh as one-thread-per-item functions (see there for the reference lines and for why: the same source
-// is executed on the host by tests/test_edlines_emul.py, bit for bit against oracle/oracle_edlines.cpp); this file holds the kernel
-// wrappers, the device workspaces and the C ABI.
+// The algorithm is stated in edlines_dev.cuh as one-thread-per-item functions (see there for the reference lines): that source is executed on
+// the host by tests/test_edlines_emul.py, bit for bit against oracle/oracle_edlines.cpp.  The streaming stages use those functions directly;
+// the two sequential stages have warp-cooperative production kernels here that make the same decisions and produce the same numbers
+// (tests/test_edlines_gpu.py: segment lists and descriptors bit-identical to the oracle on hardware).
 //
 //   lbd_launch_grad  (lbd.cu)  blur 5x5 + Sobel -> {dx, dy}                                 HBM / issue bound, shared with the LBD descriptor
 //   k_ed_pixel       thread per pixel: packed gradient + direction map                     HBM bound (4 B read, 2 B written per pixel)
 //   k_ed_anchor      thread per 32 anchor candidates: one word of the column-major bitmap  L2 bound
-//   k_ed_draw        one thread per frame: smart routing, edge chains                      latency bound (sequential by construction; frames run
-//                                                                                          side by side, one warp slot each)
-//   k_ed_fit         thread per chain: least-squares segments, validation, end points      latency bound, chains in parallel
+//   k_ed_draw_warp   one warp per frame: smart routing with the edge bitmap in shared memory, edge chains
+//                                                                                          latency bound (the walk is sequential by construction)
+//   k_ed_fit_warp    one warp per chain: least-squares segments, extension 32 pixels per step, validation with one det_atan2 per lane
 //   k_ed_emit        one thread per frame: ordered compaction, end-point order, length filter
+//   csb_edlines_describe -> k_lbd_describe (lbd.cu): the warp-cooperative LBD kernel on the detector's own key-line fields
 //
-// First version: correctness first (the drawing stage uses one lane of a warp per frame).  STATUS: the device code is validated on the host;
-// the kernels below had not run on hardware when this was written (tests/test_zz_edlines_gpu.py runs them in a child process).
+// k_ed_draw (one thread per frame) remains as the fallback for frames whose edge bitmap does not fit shared memory.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -25,7 +26,6 @@
 #include "edlines.h"
 #include "edlines_dev.cuh"
 #include "lbd.h"
-#include "lbd_dev.cuh"
 
 namespace csb {
 
@@ -197,23 +197,215 @@ __global__ void __launch_bounds__(32) k_ed_draw_warp(EdBuffers B, EdDims d) {
     atomicAdd(B.stats + 2, (unsigned long long)n_chains);
 }
 
-__global__ void __launch_bounds__(64) k_ed_fit(EdBuffers B, EdDims d) {
-    const int chain = blockIdx.x * blockDim.x + threadIdx.x, frame = blockIdx.y;
-    if (chain < B.n_chains[frame]) ed_fit(B, d, frame, chain);
+// ---- line fitting, one WARP per chain (the production kernel; ed_fit() is the one-thread transcription the host emulation shares) ------------
+// Same decisions and the same numbers as ed_fit(), with the per-pixel work spread over the lanes:
+//  * the least-squares sums are sums of integer products (exact in double, < 2^53), so a lane-strided accumulation + butterfly gives the very
+//    value the sequential loop gives; they are rounded to float once, like there;
+//  * the fit error of the 15 initial pixels is an inexact double sum: the squares come from 15 lanes, the additions run in pixel order;
+//  * extension: 32 chain pixels per step -- every lane tests one pixel against the line, a ballot gives the outlier mask, and the
+//    reference's "stop at the 4th consecutive outlier" is the first run of four ones in that mask (with the run carried in from the
+//    previous step prepended), found with shifts and ffs;
+//  * validation: gradient sums (integers) and the per-pixel direction test (one det_atan2 per pixel) lane-strided, counts added up;
+//  * everything scalar (the 2 x 2 solve, the NFA) is evaluated by all lanes on identical operands.
+__device__ __forceinline__ double warp_sum_exact(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ void ed_sums_warp(const ushort2* p, int n, bool horiz, int lane, double& sa2, double& sa, double& sab, double& sb) {
+    double a2 = 0, a1 = 0, ab = 0, b1 = 0;
+    for (int i = lane; i < n; i += 32) {
+        const ushort2 q = p[i];
+        const double a = (double)(horiz ? q.x : q.y), b = (double)(horiz ? q.y : q.x);
+        a2 += a * a; a1 += a; ab += a * b; b1 += b;
+    }
+    sa2 = warp_sum_exact(a2); sa = warp_sum_exact(a1); sab = warp_sum_exact(ab); sb = warp_sum_exact(b1);
+}
+
+__device__ void ed_fit_warp(const EdBuffers& B, const EdDims& d, int frame, int chain_id, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    const int W = d.w, H = d.h;
+    const uint16_t* gd = B.gd + (size_t)frame * W * H;
+    const short2* grad = B.grad + (size_t)frame * W * H;
+    const int* sid = B.chain_sid + (size_t)frame * (d.max_edges + 2);
+    const ushort2* ch = B.chain_px + (size_t)frame * d.chain_cap;
+    ushort2* ln = B.line_px + (size_t)frame * d.chain_cap;
+    EdLine* stage = B.stage + (size_t)frame * d.stage_cap;
+    int S = sid[chain_id];
+    const int E = sid[chain_id + 1];
+    const int slot_base = S / ED_MIN_LINE_LEN, slot_cap = (E - S) / ED_MIN_LINE_LEN;   // see ed_fit
+    for (int k = lane; k < slot_cap; k += 32) stage[slot_base + k].n_px = 0;
+    int n_lines = 0;
+    const double logNT = 2.0 * (log10((double)(unsigned)W) + log10((double)(unsigned)H));
+    int off = S, newOffsetS = off;
+    double lineFitErr = 0;
+    double eq[2] = {0, 0};
+    EdFit fit{};
+    unsigned long long n_staged = 0;
+    while (E > S + ED_MIN_LINE_LEN) {
+        bool horiz = false;
+        while (E > S + ED_MIN_LINE_LEN) {
+            const ushort2 first = ch[S];
+            horiz = ed_horizontal(gd[first.y * W + first.x]);
+            double sa2, sa, sab, sb;
+            ed_sums_warp(ch + S, ED_MIN_LINE_LEN, horiz, lane, sa2, sa, sab, sb);
+            fit.ATA[0] = (float)sa2; fit.ATA[1] = (float)sa; fit.ATA[2] = (float)sa; fit.ATA[3] = (float)ED_MIN_LINE_LEN;
+            fit.ATV[0] = (float)sab; fit.ATV[1] = (float)sb;
+            ed_solve(fit, eq);
+            double c2 = 0;
+            if (lane < ED_MIN_LINE_LEN) {
+                const ushort2 q = ch[S + lane];
+                const double xx = (double)q.x, yy = (double)q.y;
+                const double c = horiz ? yy - xx * eq[0] - eq[1] : xx - yy * eq[0] - eq[1];
+                c2 = c * c;
+            }
+            double fe = 0;
+#pragma unroll
+            for (int i = 0; i < ED_MIN_LINE_LEN; i++) fe += __shfl_sync(FULL, c2, i);
+            lineFitErr = sqrt(fe);
+            if (lineFitErr <= ED_FIT_ERR) break;
+            S += ED_SKIP;
+        }
+        if (lineFitErr > ED_FIT_ERR) break;
+        const int lineStart = off;
+        {
+            const ushort2 first = ch[S];
+            horiz = ed_horizontal(gd[first.y * W + first.x]);
+        }
+        double coef1 = 0;
+        bool bExtended = true, bFirstTry = true;
+        int tryTimes = 0;
+        while (bExtended) {
+            tryTimes++;
+            if (bFirstTry) {
+                bFirstTry = false;
+                if (lane < ED_MIN_LINE_LEN) ln[off + lane] = ch[S + lane];
+                off += ED_MIN_LINE_LEN; S += ED_MIN_LINE_LEN;
+                __syncwarp();
+            } else {
+                const int length = off - lineStart, newLength = off - newOffsetS;
+                if (length > 0 && newLength > 0) {
+                    const ushort2 first = ln[lineStart];
+                    const bool hz = ed_horizontal(gd[first.y * W + first.x]);
+                    double sa2, sa, sab, sb;
+                    ed_sums_warp(ln + newOffsetS, newLength, hz, lane, sa2, sa, sab, sb);
+                    fit.ATA[0] = fit.ATA[0] + (float)sa2; fit.ATA[1] = fit.ATA[1] + (float)sa; fit.ATA[2] = fit.ATA[2] + (float)sa;
+                    fit.ATA[3] = fit.ATA[3] + (float)newLength;
+                    fit.ATV[0] = fit.ATV[0] + (float)sab; fit.ATV[1] = fit.ATV[1] + (float)sb;
+                    ed_solve(fit, eq);
+                }
+            }
+            coef1 = horiz ? 1 / sqrt(eq[0] * eq[0] + 1) : 1 / sqrt(1 + eq[0] * eq[0]);
+            int numOfOutlier = 0;
+            newOffsetS = off;
+            while (E > S) {
+                const int n = min(32, E - S);
+                ushort2 q = make_ushort2(0, 0);
+                bool out = false;
+                if (lane < n) {
+                    q = ch[S + lane];
+                    const double xx = (double)q.x, yy = (double)q.y;
+                    const double dist = horiz ? fabs(eq[0] * xx - yy + eq[1]) * coef1 : fabs(xx - eq[0] * yy - eq[1]) * coef1;
+                    out = dist > ED_FIT_ERR;
+                }
+                const unsigned m = __ballot_sync(FULL, out);
+                // the run of outliers that entered this step (<= 3) goes in front of the mask; a run of four ends the extension
+                const unsigned long long M = ((unsigned long long)m << numOfOutlier) | ((1ull << numOfOutlier) - 1ull);
+                const unsigned long long Q = M & (M >> 1) & (M >> 2) & (M >> 3);
+                int consumed = n;
+                bool stop = false;
+                if (Q) {
+                    const int p = (__ffsll((long long)Q) - 1) + 3 - numOfOutlier;  // position (in this step) of the 4th consecutive outlier
+                    if (p < n) { consumed = p + 1; stop = true; }
+                }
+                if (lane < consumed) ln[off + lane] = q;
+                off += consumed; S += consumed;
+                if (stop) { numOfOutlier = 4; break; }
+                // the run of outliers at the end of this step (all of it an outlier: the run that came in grows)
+                const unsigned inv = ~m & ((n == 32) ? 0xffffffffu : ((1u << n) - 1u));
+                numOfOutlier = inv ? (n - 1 - (31 - __clz(inv))) : numOfOutlier + n;
+            }
+            __syncwarp();
+            off -= numOfOutlier;
+            S -= numOfOutlier;
+            if (!(off - newOffsetS > 0 && tryTimes < ED_TRY_TIME)) bExtended = false;
+        }
+        double le[3];
+        if (horiz) { le[0] = eq[0] * coef1; le[1] = -1 * coef1; le[2] = eq[1] * coef1; }
+        else { le[0] = 1 * coef1; le[1] = -eq[0] * coef1; le[2] = -eq[1] * coef1; }
+        // LineValidation_ (:2793-2873)
+        bool ok = true;
+        float direction = 0.f;
+        {
+            const int n = off - lineStart;
+            int mgx = 0, mgy = 0;
+            for (int i = lane; i < n; i += 32) {
+                const ushort2 q = ln[lineStart + i];
+                const short2 g = grad[q.y * W + q.x];
+                mgx += g.x; mgy += g.y;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { mgx += __shfl_xor_sync(FULL, mgx, o); mgy += __shfl_xor_sync(FULL, mgy, o); }
+            const double dx = fabs(le[1]), dy = fabs(le[0]);
+            if (mgx == 0 && mgy == 0) ok = false;
+            if (ok) {
+                if (mgx > 0 && mgy >= 0) direction = (float)det_atan2(-dy, dx);
+                if (mgx <= 0 && mgy > 0) direction = (float)det_atan2(dy, dx);
+                if (mgx < 0 && mgy <= 0) direction = (float)det_atan2(dy, -dx);
+                if (mgx >= 0 && mgy < 0) direction = (float)det_atan2(-dy, -dx);
+                const double ad = fabs((double)direction);
+                if (ad < 0.15 || ED_PI - ad < 0.15) {
+                    if (fabs(le[2]) < 10 || fabs((double)(unsigned)H - fabs(le[2])) < 10) ok = false;
+                }
+                if (ok && fabs(ad - ED_PI * 0.5) < 0.15) {
+                    if (fabs(le[2]) < 10 || fabs((double)(unsigned)W - fabs(le[2])) < 10) ok = false;
+                }
+            }
+            if (ok) {
+                int k = 0;
+                for (int i = lane; i < n; i += 32) {
+                    const ushort2 q = ln[lineStart + i];
+                    const short2 g = grad[q.y * W + q.x];
+                    const double pd = det_atan2(-(double)g.x, (double)g.y);
+                    const double dis = fabs((double)direction - pd);
+                    if (fabs(2 * ED_PI - dis) < 0.392699 || dis < 0.392699) k++;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) k += __shfl_xor_sync(FULL, k, o);
+                ok = ed_nfa(n, k, 0.125, logNT) > 0;
+            }
+        }
+        if (ok) {
+            if (lane == 0) {
+                const double a1 = le[1] * le[1], a2 = le[0] * le[0], a3 = le[0] * le[1], a4 = le[2] * le[0], a5 = le[2] * le[1];
+                EdLine L;
+                double Px = (double)ln[lineStart].x, Py = (double)ln[lineStart].y;
+                L.ep[0] = (float)(a1 * Px - a3 * Py - a4);
+                L.ep[1] = (float)(a2 * Py - a3 * Px - a5);
+                Px = (double)ln[off - 1].x; Py = (double)ln[off - 1].y;
+                L.ep[2] = (float)(a1 * Px - a3 * Py - a4);
+                L.ep[3] = (float)(a2 * Py - a3 * Px - a5);
+                L.direction = direction;
+                L.n_px = off - lineStart;
+                if (n_lines < slot_cap) stage[slot_base + n_lines] = L;
+            }
+            n_lines++;
+            n_staged++;
+        } else {
+            off = lineStart;
+        }
+    }
+    if (lane == 0 && n_staged) atomicAdd(B.stats + 3, n_staged);
+}
+
+constexpr int EDF_WARPS = 4;
+__global__ void __launch_bounds__(32 * EDF_WARPS) k_ed_fit_warp(EdBuffers B, EdDims d) {
+    const int chain = blockIdx.x * EDF_WARPS + (threadIdx.x >> 5), frame = blockIdx.y;
+    if (chain < B.n_chains[frame]) ed_fit_warp(B, d, frame, chain, threadIdx.x & 31);
 }
 
 __global__ void __launch_bounds__(32) k_ed_emit(EdBuffers B, EdDims d, int filter, float length_thres, int max_lines) {
     if (threadIdx.x == 0) ed_emit(B, d, blockIdx.x, filter, length_thres, max_lines);
-}
-
-// detect_descrip_lines with use_LSD = false: one thread per emitted key line (lbd_dev.cuh); weights = {gaussCoefG_[63], gaussCoefL_[21]}
-__global__ void __launch_bounds__(64) k_lbdk_line(EdBuffers B, EdDims d, int max_lines, const float* weights, uint8_t* desc, float* descf) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, frame = blockIdx.y;
-    if (i >= min(B.n_lines[frame], max_lines)) return;
-    const size_t row = (size_t)frame * max_lines + i;
-    const float2 k = B.keyl[row];
-    lbdk_line(B.grad + (size_t)frame * d.w * d.h, d.w, d.h, B.lines + 4 * row, k.x, (int)k.y, weights, weights + LBDK_ROWS, descf ? descf + 72 * row : nullptr,
-              desc + 32 * row);
 }
 
 struct EdState {
@@ -347,7 +539,7 @@ int csb_edlines_run(csb_context* c, int timed) {
         }
     }
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[2], st));
-    k_ed_fit<<<dim3((d.max_edges + 1 + 63) / 64, d.n_frames), 64, 0, st>>>(B, d);
+    k_ed_fit_warp<<<dim3((d.max_edges + 1 + EDF_WARPS - 1) / EDF_WARPS, d.n_frames), 32 * EDF_WARPS, 0, st>>>(B, d);
     k_ed_emit<<<d.n_frames, 32, 0, st>>>(B, d, s.params.filter, s.params.line_length_thres, s.params.max_lines);
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[3], st));
     CSB_CUDA(c, cudaGetLastError());
@@ -425,18 +617,19 @@ int csb_edlines_describe(csb_context* c, int want_float) {
     CSB_CUDA(c, cudaSetDevice(c->device));
     const size_t rows = (size_t)s.d.n_frames * s.params.max_lines;
     if (!s.weights_set) {
-        float wts[LBDK_ROWS + 3 * LBDK_BAND_W];
-        lbdk_weights(wts, wts + LBDK_ROWS);
-        CSB_CUDA(c, s.d_weights.ensure(sizeof wts));
-        CSB_CUDA(c, cudaMemcpyAsync(s.d_weights.p, wts, sizeof wts, cudaMemcpyHostToDevice, c->stream));
-        CSB_CUDA(c, cudaStreamSynchronize(c->stream));  // wts lives on this stack frame
+        CSB_CUDA(c, lbd_upload_weights(c->stream));
         s.weights_set = true;
     }
     CSB_CUDA(c, s.d_desc.ensure(rows * 32));
     if (want_float) CSB_CUDA(c, s.d_descf.ensure(rows * 72 * 4));
+    CSB_CUDA(c, s.d_weights.ensure((size_t)(s.d.n_frames + 1) * 4 + 64));  // scratch of the describe stage: line prefix + work counters
     EdBuffers B = ed_buffers(s);
-    k_lbdk_line<<<dim3((s.params.max_lines + 63) / 64, s.d.n_frames), 64, 0, c->stream>>>(B, s.d, s.params.max_lines, s.d_weights.as<float>(), s.d_desc.as<uint8_t>(),
-                                                                                           want_float ? s.d_descf.as<float>() : nullptr);
+    // the warp-cooperative descriptor kernel of lbd.cu on the detector's own key-line fields (k_lbdk_line is the one-thread-per-line
+    // transcription the host emulation shares)
+    int* prefix = s.d_weights.as<int>();
+    unsigned long long* ctr = reinterpret_cast<unsigned long long*>(s.d_weights.as<char>() + (((size_t)(s.d.n_frames + 1) * 4 + 15) & ~(size_t)15));
+    CSB_CUDA(c, lbd_describe_keylines(B.grad, B.lines, B.keyl, B.n_lines, s.d.n_frames, s.params.max_lines, s.d.w, s.d.h, s.d_desc.as<uint8_t>(),
+                                      want_float ? s.d_descf.as<float>() : nullptr, prefix, ctr, c->num_sms, c->stream));
     CSB_CUDA(c, cudaGetLastError());
     s.described = true;
     s.desc_float = want_float != 0;

@@ -242,6 +242,7 @@ struct LbdArgs {
     uint8_t* desc;         // n_frames x stride x 32
     float* descf;          // n_frames x stride x 72 or nullptr
     float* keyl;           // n_frames x stride x 4 {angle, numOfPixels, lineLength, 0} or nullptr
+    const float2* keyl_in; // nullptr: key-line fields as LSDDetector fills them; else n_frames x stride {lineDirection_, numOfPixels} from the detector (EDLines)
     int w, h, n_frames, stride;
 };
 
@@ -279,9 +280,18 @@ __global__ void __launch_bounds__(32 * LD_WARPS) k_lbd_describe(LbdArgs A) {
         if (e3 < 0) e3 = 0;
         if (e3 >= h) e3 = (float)h - 1.0f;
         const int px1 = __float2int_rn(e0), py1 = __float2int_rn(e1), px2 = __float2int_rn(e2), py2 = __float2int_rn(e3);  // cvRound
-        const int len = max(abs(px2 - px1), abs(py2 - py1)) + 1;  // cv::LineIterator count, 8-connected
+        int len = max(abs(px2 - px1), abs(py2 - py1)) + 1;  // cv::LineIterator count, 8-connected
         const float fy = e3 - e1, fx = e2 - e0;
-        const float angle = (float)det_atan2((double)fy, (double)fx);
+        float angle;
+        if (A.keyl_in) {
+            // detect_descrip_lines with use_LSD = false: the EDLines detector supplies direction = lineDirection_ and numOfPixels = pixels of
+            // the fitted chain segment, and its end points are used as projected, unclamped (binary_descriptor.cpp:1045-1140)
+            const float2 k = A.keyl_in[row];
+            angle = k.x;
+            len = (int)(short)(int)k.y;
+            e0 = ln.x; e1 = ln.y; e2 = ln.z; e3 = ln.w;
+        } else
+            angle = (float)det_atan2((double)fy, (double)fx);
         float dL0, dL1;
         {
             double sn, cs;
@@ -411,6 +421,42 @@ __global__ void __launch_bounds__(32 * LD_WARPS) k_lbd_describe(LbdArgs A) {
     }
 }
 
+// BinaryDescriptor ctor (binary_descriptor.cpp:232-258), integer divisions as written there -> the constant-memory band weights
+cudaError_t lbd_upload_weights(cudaStream_t st) {
+    float G[LBD_ROWS], L[3 * LBD_BAND_W];
+    double u = (LBD_BAND_W * 3 - 1) / 2;
+    double sigma = (LBD_BAND_W * 2 + 1) / 2;
+    double invsigma2 = -1 / (2 * sigma * sigma);
+    for (int i = 0; i < LBD_BAND_W * 3; i++) {
+        const double dis = i - u;
+        L[i] = (float)std::exp(dis * dis * invsigma2);
+    }
+    u = (LBD_BANDS * LBD_BAND_W - 1) / 2;
+    sigma = u;
+    invsigma2 = -1 / (2 * sigma * sigma);
+    for (int i = 0; i < LBD_ROWS; i++) {
+        const double dis = i - u;
+        G[i] = (float)std::exp(dis * dis * invsigma2);
+    }
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_lbd_G, G, sizeof G, 0, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbolAsync(c_lbd_L, L, sizeof L, 0, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(st);  // G / L live on this stack frame
+}
+
+// Descriptors of detector-supplied key lines (EDLines) with the warp-cooperative kernel: lines / keyl_in / desc rows are
+// n_frames x stride, counts[f] lines in frame f (clamped to stride); prefix (n_frames + 1 ints) and ctr (2 x u64) are scratch.
+cudaError_t lbd_describe_keylines(const short2* grad, const float* lines, const float2* keyl_in, const int* counts, int n_frames, int stride, int w, int h,
+                                  uint8_t* desc, float* descf, int* prefix, unsigned long long* ctr, int num_sms, cudaStream_t st) {
+    k_lbd_prefix<<<1, 1024, 0, st>>>(counts, n_frames, stride, prefix, ctr);
+    LbdArgs A{};
+    A.grad = grad; A.lines = lines; A.prefix = prefix; A.ctr = ctr; A.desc = desc; A.descf = descf; A.keyl = nullptr; A.keyl_in = keyl_in;
+    A.w = w; A.h = h; A.n_frames = n_frames; A.stride = stride;
+    k_lbd_describe<<<num_sms * LD_CTAS_PER_SM, 32 * LD_WARPS, 0, st>>>(A);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------------------
@@ -463,25 +509,7 @@ static int lbd_state(csb_context* c) {
     }
     LbdState& s = *c->lbd;
     if (!s.weights_set) {
-        // BinaryDescriptor ctor (binary_descriptor.cpp:232-258), integer divisions as written there
-        float G[LBD_ROWS], L[3 * LBD_BAND_W];
-        double u = (LBD_BAND_W * 3 - 1) / 2;
-        double sigma = (LBD_BAND_W * 2 + 1) / 2;
-        double invsigma2 = -1 / (2 * sigma * sigma);
-        for (int i = 0; i < LBD_BAND_W * 3; i++) {
-            const double dis = i - u;
-            L[i] = (float)std::exp(dis * dis * invsigma2);
-        }
-        u = (LBD_BANDS * LBD_BAND_W - 1) / 2;
-        sigma = u;
-        invsigma2 = -1 / (2 * sigma * sigma);
-        for (int i = 0; i < LBD_ROWS; i++) {
-            const double dis = i - u;
-            G[i] = (float)std::exp(dis * dis * invsigma2);
-        }
-        CSB_CUDA(c, cudaMemcpyToSymbolAsync(c_lbd_G, G, sizeof G, 0, cudaMemcpyHostToDevice, c->stream));
-        CSB_CUDA(c, cudaMemcpyToSymbolAsync(c_lbd_L, L, sizeof L, 0, cudaMemcpyHostToDevice, c->stream));
-        CSB_CUDA(c, cudaStreamSynchronize(c->stream));  // G / L live on this stack frame
+        CSB_CUDA(c, lbd_upload_weights(c->stream));
         s.weights_set = true;
     }
     return CSB_OK;
