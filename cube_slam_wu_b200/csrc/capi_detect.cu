@@ -384,7 +384,7 @@ int csb_detect_run(csb_context* c, int timed) {
         if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[3], st));
         CSB_CUDA(c, launch_recover(d.B, st));
         if (timed) CSB_CUDA(c, cudaEventRecord(d.ev[4], st));
-        d.launches_last = 4 + nsel + (d.gray_mode ? 2 : 0);  // prep_lines, vp_support, score, recover + select launches (+ distance maps)
+        d.launches_last = 4 + nsel + (d.gray_mode ? 1 : 0);  // prep_lines, vp_support, score, recover + select launches (+ k_distmap)
     } else if (timed) {
         CSB_CUDA(c, cudaEventRecord(d.ev[6], st));
         for (int i = 0; i < 5; i++) CSB_CUDA(c, cudaEventRecord(d.ev[i], st));
