@@ -334,22 +334,31 @@ template <class T>
 int sync_all(csb_context* c, int slot, const std::vector<T>& h) { return sync_tail(c, slot, h, 0); }
 
 struct Counts { int n_cam, n_cube, n_ec, n_ep, n_eo; };
+// measurements / information matrices of the NEW edges (caller memory; the host keeps the topology only)
+struct NewEdgeData { const double *ec_meas, *ec_info, *ep_meas, *ep_info, *ep_K, *eo_meas, *eo_info; };
+
+// device array of n_new records of `rec` doubles appended behind the n_old it already holds
+int append_dev(csb_context* c, int slot, const double* src, size_t n_old, size_t n_new, size_t rec) {
+    CSB_TRY(ensure(c, slot, (n_old + n_new) * rec * 8, n_old * rec * 8));
+    if (n_new) CSB_CUDA(c, cudaMemcpyAsync(reinterpret_cast<double*>(c->ba.dev[slot].p) + n_old * rec, src, n_new * rec * 8, cudaMemcpyHostToDevice, c->stream));
+    return CSB_OK;
+}
 
 // Brings the device state in line with c->ba.host after vertices / edges were appended (old = what the device already holds):
 // tails of the topology / measurement arrays, the per-vertex adjacency (rebuilt: the record offsets of the later edge types move when
 // an edge is inserted), the work buffers; the estimates of the existing vertices are preserved.
-int sync_device(csb_context* c, const Counts& old) {
+int sync_device(csb_context* c, const Counts& old, const NewEdgeData& nd) {
     BAState& s = c->ba;
     const HostGraph& h = s.host;
     const int n_cam = (int)h.cam_fixed.size(), n_cube = (int)h.cube_fixed.size(), n_ec = (int)h.ec_cam.size(), n_ep = (int)h.ep_cam.size(), n_eo = (int)h.eo_i.size();
     CSB_TRY(sync_tail(c, G_CAM_FIXED, h.cam_fixed, old.n_cam)); CSB_TRY(sync_tail(c, G_CUBE_FIXED, h.cube_fixed, old.n_cube));
     CSB_TRY(sync_tail(c, G_EC_CAM, h.ec_cam, old.n_ec)); CSB_TRY(sync_tail(c, G_EC_CUBE, h.ec_cube, old.n_ec));
-    CSB_TRY(sync_tail(c, G_EC_MEAS, h.ec_meas, (size_t)old.n_ec * 10)); CSB_TRY(sync_tail(c, G_EC_INFO, h.ec_info, (size_t)old.n_ec * 81));
+    CSB_TRY(append_dev(c, G_EC_MEAS, nd.ec_meas, old.n_ec, n_ec - old.n_ec, 10)); CSB_TRY(append_dev(c, G_EC_INFO, nd.ec_info, old.n_ec, n_ec - old.n_ec, 81));
     CSB_TRY(sync_tail(c, G_EP_CAM, h.ep_cam, old.n_ep)); CSB_TRY(sync_tail(c, G_EP_CUBE, h.ep_cube, old.n_ep));
-    CSB_TRY(sync_tail(c, G_EP_MEAS, h.ep_meas, (size_t)old.n_ep * 4)); CSB_TRY(sync_tail(c, G_EP_INFO, h.ep_info, (size_t)old.n_ep * 16));
-    CSB_TRY(sync_tail(c, G_EP_K, h.ep_K, (size_t)old.n_ep * 9));
+    CSB_TRY(append_dev(c, G_EP_MEAS, nd.ep_meas, old.n_ep, n_ep - old.n_ep, 4)); CSB_TRY(append_dev(c, G_EP_INFO, nd.ep_info, old.n_ep, n_ep - old.n_ep, 16));
+    CSB_TRY(append_dev(c, G_EP_K, nd.ep_K, old.n_ep, n_ep - old.n_ep, 9));
     CSB_TRY(sync_tail(c, G_EO_I, h.eo_i, old.n_eo)); CSB_TRY(sync_tail(c, G_EO_J, h.eo_j, old.n_eo));
-    CSB_TRY(sync_tail(c, G_EO_MEAS, h.eo_meas, (size_t)old.n_eo * 7)); CSB_TRY(sync_tail(c, G_EO_INFO, h.eo_info, (size_t)old.n_eo * 36));
+    CSB_TRY(append_dev(c, G_EO_MEAS, nd.eo_meas, old.n_eo, n_eo - old.n_eo, 7)); CSB_TRY(append_dev(c, G_EO_INFO, nd.eo_info, old.n_eo, n_eo - old.n_eo, 36));
 
     // buildStructure(): per-vertex adjacency in edge order ec, ep, eo (block_solver.hpp:142-295 allocates the blocks;
     // sparse_optimizer.cpp:482-487 fixes the edge order) -- counting sort, flat arrays
@@ -443,14 +452,10 @@ int csb_ba_set_graph(csb_context* c, const csb_ba_graph* g) {
     HostGraph& h = s.host;
     h.cam_fixed.assign(g->cam_fixed, g->cam_fixed + g->n_cam); h.cube_fixed.assign(g->cube_fixed, g->cube_fixed + g->n_cube);
     h.ec_cam.assign(g->ec_cam, g->ec_cam + g->n_ec); h.ec_cube.assign(g->ec_cube, g->ec_cube + g->n_ec);
-    h.ec_meas.assign(g->ec_meas, g->ec_meas + (size_t)g->n_ec * 10); h.ec_info.assign(g->ec_info, g->ec_info + (size_t)g->n_ec * 81);
     h.ep_cam.assign(g->ep_cam, g->ep_cam + g->n_ep); h.ep_cube.assign(g->ep_cube, g->ep_cube + g->n_ep);
-    h.ep_meas.assign(g->ep_meas, g->ep_meas + (size_t)g->n_ep * 4); h.ep_info.assign(g->ep_info, g->ep_info + (size_t)g->n_ep * 16);
-    h.ep_K.assign(g->ep_K, g->ep_K + (size_t)g->n_ep * 9);
     h.eo_i.assign(g->eo_cam_i, g->eo_cam_i + g->n_eo); h.eo_j.assign(g->eo_cam_j, g->eo_cam_j + g->n_eo);
-    h.eo_meas.assign(g->eo_meas, g->eo_meas + (size_t)g->n_eo * 7); h.eo_info.assign(g->eo_info, g->eo_info + (size_t)g->n_eo * 36);
     s.has_graph = false; s.has_estimates = false;
-    CSB_TRY(sync_device(c, Counts{0, 0, 0, 0, 0}));
+    CSB_TRY(sync_device(c, Counts{0, 0, 0, 0, 0}, NewEdgeData{g->ec_meas, g->ec_info, g->ep_meas, g->ep_info, g->ep_K, g->eo_meas, g->eo_info}));
     CSB_CUDA(c, cudaStreamSynchronize(c->stream));
     s.has_graph = true;
     return CSB_OK;
@@ -472,12 +477,8 @@ int csb_ba_add_frame(csb_context* c, const csb_ba_frame* f, int32_t* cam_index_o
     h.cam_fixed.push_back(f->cam_fixed ? 1 : 0);
     for (int i = 0; i < f->n_new_cubes; i++) h.cube_fixed.push_back(f->new_cube_fixed[i] ? 1 : 0);
     for (int e = 0; e < f->n_ec; e++) { h.ec_cam.push_back(cam); h.ec_cube.push_back(f->ec_cube[e]); }
-    h.ec_meas.insert(h.ec_meas.end(), f->ec_meas, f->ec_meas + (size_t)f->n_ec * 10);
-    h.ec_info.insert(h.ec_info.end(), f->ec_info, f->ec_info + (size_t)f->n_ec * 81);
     for (int e = 0; e < f->n_eo; e++) { h.eo_i.push_back(f->eo_cam_i[e]); h.eo_j.push_back(cam); }
-    h.eo_meas.insert(h.eo_meas.end(), f->eo_meas, f->eo_meas + (size_t)f->n_eo * 7);
-    h.eo_info.insert(h.eo_info.end(), f->eo_info, f->eo_info + (size_t)f->n_eo * 36);
-    CSB_TRY(sync_device(c, old));
+    CSB_TRY(sync_device(c, old, NewEdgeData{f->ec_meas, f->ec_info, nullptr, nullptr, nullptr, f->eo_meas, f->eo_info}));
     // estimates of the new vertices behind the (possibly optimised) ones the device holds
     CSB_CUDA(c, cudaMemcpyAsync(const_cast<double*>(s.B.cams7) + 7 * (size_t)cam, f->cam7, 56, cudaMemcpyHostToDevice, c->stream));
     if (f->n_new_cubes)

@@ -32,7 +32,6 @@ struct BABuffers {
 // host copy of the topology (structure of the reduced camera system is built from it on the first csb_ba_optimize)
 struct HostGraph {
     std::vector<int> cam_fixed, cube_fixed, ec_cam, ec_cube, ep_cam, ep_cube, eo_i, eo_j;
-    std::vector<double> ec_meas, ec_info, ep_meas, ep_info, ep_K, eo_meas, eo_info;  // kept so that csb_ba_add_frame can re-derive the device state
 };
 
 // a device array that grows geometrically (csb_ba_add_frame appends without reallocating every time)
