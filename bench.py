@@ -495,7 +495,7 @@ def run_ours(args, rank, local_rank, world):
                 for _ in range(5):
                     ctx.ba_run()
                 torch.cuda.synchronize()
-                reps = 200
+                reps = 1000  # M2 over >= 1000 back-to-back linearisations
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(stream)
                 for _ in range(reps):
@@ -505,9 +505,9 @@ def run_ours(args, rank, local_rank, world):
             ba_ms = a.elapsed_time(b) / reps
             ba_ach = ALGO_BYTES_PER_EDGE * n_edges / (ba_ms * 1e-3) / 1e9
             out["ba"] = {"metric": "ba_edges_linearised_per_sec", "value": n_edges / (ba_ms * 1e-3), "unit": "edges/s", "edges": n_edges,
-                         "ms_per_linearisation": ba_ms, "config": "config#4: 200 keyframes, 50 cuboids, 4000 EdgeSE3Cuboid + 199 EdgeSE3Expmap, 200 back-to-back linearisations (L2-resident; launch/FP64 bound)",
+                         "ms_per_linearisation": ba_ms, "config": "config#4: 200 keyframes, 50 cuboids, 4000 EdgeSE3Cuboid + 199 EdgeSE3Expmap, 1000 back-to-back linearisations (L2-resident; FP64 bound: 31 residual evaluations per edge, profiles/r02_ncu_ba.md)",
                          "roofline": {"bound": "hbm", "achieved": ba_ach, "peak": peak, "unit": "GB/s", "frac": ba_ach / peak, "traffic": None}}
-            try:  # closed-form Jacobians (row f-4): same 200 back-to-back linearisations
+            try:  # closed-form Jacobians (row f-4): same 1000 back-to-back linearisations
                 ctx.ba_set_jacobian_mode(True)
                 with torch.cuda.stream(stream):
                     for _ in range(5):
@@ -539,6 +539,41 @@ def run_ours(args, rank, local_rank, world):
                                                  "a linearisation and an LM trial are one CUDA-graph launch each"}
             except Exception as e:
                 out["ba"]["optimize"] = {"error": str(e)}
+            # SURVEY 8d's other form of M2: 256 graphs batched into one launch (the block-diagonal union of 256 copies of the config #4 graph:
+            # 1.07 M edges, 51 200 cameras, 12 800 cuboids), where the launch overheads of the 4 k-edge case are gone
+            try:
+                G = 256
+                nc, nq = len(g["cam_fixed"]), len(g["cube_fixed"])
+                ec0, eo0 = [np.asarray(a_) for a_ in g["ec"]], [np.asarray(a_) for a_ in g["eo"]]
+                offc = (np.arange(G, dtype=np.int32) * nc)[:, None]
+                offq = (np.arange(G, dtype=np.int32) * nq)[:, None]
+                ecb = ((ec0[0][None, :] + offc).ravel(), (ec0[1][None, :] + offq).ravel(), np.tile(ec0[2], (G, 1)), np.tile(ec0[3], (G, 1)))
+                eob = ((eo0[0][None, :] + offc).ravel(), (eo0[1][None, :] + offc).ravel(), np.tile(eo0[2], (G, 1)), np.tile(eo0[3], (G, 1)))
+                ctx.ba_set_graph(np.tile(np.asarray(g["cam_fixed"]), G), np.tile(np.asarray(g["cube_fixed"]), G), ec=ecb, eo=eob)
+                ctx.ba_upload_estimates(np.tile(np.asarray(g["cams7"]), (G, 1)), np.tile(np.asarray(g["cubes10"]), (G, 1)))
+                del ecb, eob
+                nb_edges = G * n_edges
+                res = {}
+                for mode, name in ((False, "numeric"), (True, "analytic")):
+                    ctx.ba_set_jacobian_mode(mode)
+                    with torch.cuda.stream(stream):
+                        for _ in range(2):
+                            ctx.ba_run()
+                        torch.cuda.synchronize()
+                        a.record(stream)
+                        for _ in range(10):
+                            ctx.ba_run()
+                        b.record(stream)
+                        torch.cuda.synchronize()
+                    ms_b = a.elapsed_time(b) / 10
+                    res[name] = {"ms_per_linearisation": ms_b, "edges_per_s": nb_edges / (ms_b * 1e-3), "implied_gb_per_s": ALGO_BYTES_PER_EDGE * nb_edges / (ms_b * 1e-3) / 1e9}
+                ctx.ba_set_jacobian_mode(False)
+                out["ba"]["batched_256_graphs"] = {"edges": nb_edges, **res,
+                                                   "roofline_frac_numeric": res["numeric"]["implied_gb_per_s"] / peak, "roofline_frac_analytic": res["analytic"]["implied_gb_per_s"] / peak}
+            except Exception as e:
+                out["ba"]["batched_256_graphs"] = {"error": str(e)}
+            finally:
+                ctx.ba_set_jacobian_mode(False)
         except Exception as e:  # the headline line must still print
             out["ba"] = {"error": str(e)}
 

@@ -242,33 +242,55 @@ __global__ void __launch_bounds__(CF_THREADS) k_chol_solve(double* S, int ld, do
         for (int i = tid; i < NB * NB; i += CF_THREADS) a[i / NB][i % NB] = S[(size_t)(k0 + i / NB) * ld + k0 + i % NB];
         __syncthreads();
         CHOL_T(5);
-        if (warp == 0) {
-            // the whole 32 x 32 factorisation in ONE warp (lane = row) on the shared-memory tile: __syncwarp instead of two block barriers per
-            // column, 1 / sqrt by rsqrt; the other warps wait at the barrier below
+        // Two-level blocking of the 32 x 32 tile: panels of 8 columns.  Inside a panel one warp (lane = row) factors column after column
+        // -- pivot by rsqrt, the at most seven panel columns to its right updated from registers, __syncwarp only -- then all 256 threads
+        // apply the panel to the rest of the tile as one rank-8 update (two block barriers per panel instead of two per column).
+        {
             bool ok = true;
-            for (int j = 0; j < NB; j++) {
-                double d = a[j][j];
-                if (!(d > 0)) { ok = false; d = 1.0; }
-                const double inv = rsqrt(d);
-                const double lj = (lane == j) ? d * inv : a[lane][j] * inv;  // column j of L (rows >= j)
-                __syncwarp();
-                if (lane >= j) a[lane][j] = lj;
-                if (lane == j) dinv[j] = inv;
-                __syncwarp();
-                // trailing update of row `lane`, eight columns at a time: all loads, then the multiply-adds, then the stores (element by
-                // element every iteration would wait for the previous store)
-                for (int c0 = j + 1; c0 <= lane; c0 += 8) {
-                    double v[8], l[8];
+            constexpr int PW = 8;
+            for (int p0 = 0; p0 < NB; p0 += PW) {
+                if (warp == 0) {
+                    for (int j = p0; j < p0 + PW; j++) {
+                        double d = a[j][j];
+                        if (!(d > 0)) { ok = false; d = 1.0; }
+                        const double inv = rsqrt(d);
+                        const double lj = (lane == j) ? d * inv : a[lane][j] * inv;  // column j of L (rows >= j)
+                        double v[PW - 1], l[PW - 1];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) { const bool in = c0 + u <= lane; v[u] = in ? a[lane][c0 + u] : 0.0; l[u] = in ? a[c0 + u][j] : 0.0; }
+                        for (int u = 0; u < PW - 1; u++) {
+                            const int cc = j + 1 + u;
+                            const bool in = cc < p0 + PW && cc <= lane;
+                            v[u] = in ? a[lane][cc] : 0.0;
+                            l[u] = in ? a[cc][j] : 0.0;
+                        }
+                        __syncwarp();
+                        if (lane >= j) a[lane][j] = lj;
+                        if (lane == j) dinv[j] = inv;
 #pragma unroll
-                    for (int u = 0; u < 8; u++) v[u] = fma(-lj, l[u], v[u]);
-#pragma unroll
-                    for (int u = 0; u < 8; u++) if (c0 + u <= lane) a[lane][c0 + u] = v[u];
+                        for (int u = 0; u < PW - 1; u++) {
+                            const int cc = j + 1 + u;
+                            // l[u] = a[cc][j] was read BEFORE it was scaled by 1 / sqrt(d_jj): scale it here (cc > j)
+                            if (cc < p0 + PW && cc <= lane) a[lane][cc] = fma(-lj, l[u] * inv, v[u]);
+                        }
+                        __syncwarp();
+                    }
                 }
-                __syncwarp();
+                __syncthreads();
+                const int r0 = p0 + PW, rem = NB - r0;
+                for (int idx = tid; idx < rem * rem; idx += CF_THREADS) {
+                    const int r = r0 + idx / rem, c = r0 + idx % rem;
+                    if (c <= r) {
+                        double acc = 0;
+#pragma unroll
+                        for (int q = 0; q < PW; q++) acc = fma(a[r][p0 + q], a[c][p0 + q], acc);
+                        a[r][c] -= acc;
+                    }
+                }
+                __syncthreads();
             }
-            if (!ok && lane == 0) *ok_flag = 0.0;
+            if (!ok && tid == 0) *ok_flag = 0.0;
+        }
+        if (warp == 0) {
             CHOL_T(6);
             tri_inverse_tile(a, b, dinv, lane);
             CHOL_T(7);
