@@ -65,62 +65,56 @@ struct EdWindow {
 __device__ __forceinline__ void edw_ensure(EdWindow&, int, int, int) {}
 __device__ __forceinline__ uint16_t edw_at(const EdWindow& w, int x, int y) { return __ldg(w.gd + (size_t)y * w.W + x); }
 
-// one walk, warp-uniform; returns the pixels written to `out` (global, capacity cap)
+// one walk, warp-uniform; returns the pixels written to `out` (global, capacity cap).  Same decisions as ed_walk() (edlines_dev.cuh), with the
+// dependent chain of a step cut to one level of loads: the three candidate pixels' packed gradients AND their edge bits are fetched
+// together, and the chosen candidate's values become the next step's `cur` / `visited` (ed_walk reloads both after the move; marking the
+// current pixel cannot change the bit of a different pixel, and the gradient map is read-only).
 __device__ __forceinline__ int edw_walk(EdWindow& w, uint32_t* edge, unsigned x, unsigned y, int lastDirection, ushort2* out, int cap, EdWalkState& st, int lane) {
     const int W = w.W, H = w.H;
+    const uint16_t* gd = w.gd;
     int n = 0;
     ushort2 mine = make_ushort2(0, 0);
-    while (true) {
-        edw_ensure(w, (int)x, (int)y, lane);
-        const int idx = (int)(y * (unsigned)W + x);
-        const uint16_t cur = edw_at(w, (int)x, (int)y);
-        if (!(ed_g(cur) > 0 && !((edge[idx >> 5] >> (idx & 31)) & 1u))) break;
+    int idx = (int)(y * (unsigned)W + x);
+    uint16_t cur = __ldg(gd + idx);
+    bool visited = (edge[idx >> 5] >> (idx & 31)) & 1u;
+    while (ed_g(cur) > 0 && !visited) {
         __syncwarp();
         if (lane == 0) edge[idx >> 5] |= 1u << (idx & 31);
         if ((n & 31) == lane) mine = make_ushort2((unsigned short)x, (unsigned short)y);
         n++;
         if ((n & 31) == 0) { const int o = n - 32 + lane; if (o < cap) out[o] = mine; }
         __syncwarp();
-        int shouldGo = 0;
-#define EDW_GV(dx, dy) ((unsigned char)ed_g(edw_at(w, (int)x + (dx), (int)y + (dy))))
+        // direction of this step (:1716-1850 and its three repetitions)
+        int dir;
         if (ed_horizontal(cur)) {
-            if (lastDirection == ED_UP || lastDirection == ED_DOWN) shouldGo = (x > st.lastX) ? ED_RIGHT : ED_LEFT;
-            st.lastX = x; st.lastY = y;
-            if (lastDirection == ED_RIGHT || shouldGo == ED_RIGHT) {
-                if (x == (unsigned)W - 1 || y == 0 || y == (unsigned)H - 1) break;
-                const unsigned char g1 = EDW_GV(1, -1), g2 = EDW_GV(1, 0), g3 = EDW_GV(1, 1);
-                if (g1 >= g2 && g1 >= g3) { x = x + 1; y = y - 1; }
-                else if (g3 >= g2 && g3 >= g1) { x = x + 1; y = y + 1; }
-                else { x = x + 1; }
-                lastDirection = ED_RIGHT;
-            } else if (lastDirection == ED_LEFT || shouldGo == ED_LEFT) {
-                if (x == 0 || y == 0 || y == (unsigned)H - 1) break;
-                const unsigned char g1 = EDW_GV(-1, -1), g2 = EDW_GV(-1, 0), g3 = EDW_GV(-1, 1);
-                if (g1 >= g2 && g1 >= g3) { x = x - 1; y = y - 1; }
-                else if (g3 >= g2 && g3 >= g1) { x = x - 1; y = y + 1; }
-                else { x = x - 1; }
-                lastDirection = ED_LEFT;
-            }
+            if (lastDirection == ED_UP || lastDirection == ED_DOWN) dir = (x > st.lastX) ? ED_RIGHT : ED_LEFT;
+            else dir = lastDirection;
         } else {
-            if (lastDirection == ED_RIGHT || lastDirection == ED_LEFT) shouldGo = (y > st.lastY) ? ED_DOWN : ED_UP;
-            st.lastX = x; st.lastY = y;
-            if (lastDirection == ED_DOWN || shouldGo == ED_DOWN) {
-                if (x == 0 || x == (unsigned)W - 1 || y == (unsigned)H - 1) break;
-                const unsigned char g1 = EDW_GV(1, 1), g2 = EDW_GV(0, 1), g3 = EDW_GV(-1, 1);
-                if (g1 >= g2 && g1 >= g3) { x = x + 1; y = y + 1; }
-                else if (g3 >= g2 && g3 >= g1) { x = x - 1; y = y + 1; }
-                else { y = y + 1; }
-                lastDirection = ED_DOWN;
-            } else if (lastDirection == ED_UP || shouldGo == ED_UP) {
-                if (x == 0 || x == (unsigned)W - 1 || y == 0) break;
-                const unsigned char g1 = EDW_GV(1, -1), g2 = EDW_GV(0, -1), g3 = EDW_GV(-1, -1);
-                if (g1 >= g2 && g1 >= g3) { x = x + 1; y = y - 1; }
-                else if (g3 >= g2 && g3 >= g1) { x = x - 1; y = y - 1; }
-                else { y = y - 1; }
-                lastDirection = ED_UP;
-            }
+            if (lastDirection == ED_RIGHT || lastDirection == ED_LEFT) dir = (y > st.lastY) ? ED_DOWN : ED_UP;
+            else dir = lastDirection;
         }
-#undef EDW_GV
+        st.lastX = x; st.lastY = y;
+        int o1, o2, o3, mx1, my1, mx2, my2, mx3, my3;
+        if (dir == ED_RIGHT || dir == ED_LEFT) {
+            const int sx = (dir == ED_RIGHT) ? 1 : -1;
+            if (x == (dir == ED_RIGHT ? (unsigned)W - 1 : 0u) || y == 0 || y == (unsigned)H - 1) break;
+            o2 = sx; o1 = sx - W; o3 = sx + W;
+            mx1 = sx; my1 = -1; mx2 = sx; my2 = 0; mx3 = sx; my3 = 1;
+        } else {
+            const int sy = (dir == ED_DOWN) ? 1 : -1;
+            if (x == 0 || x == (unsigned)W - 1 || y == (dir == ED_DOWN ? (unsigned)H - 1 : 0u)) break;
+            o2 = sy * W; o1 = o2 + 1; o3 = o2 - 1;
+            mx1 = 1; my1 = sy; mx2 = 0; my2 = sy; mx3 = -1; my3 = sy;
+        }
+        const int i1 = idx + o1, i2 = idx + o2, i3 = idx + o3;
+        const uint16_t r1 = __ldg(gd + i1), r2 = __ldg(gd + i2), r3 = __ldg(gd + i3);
+        const uint32_t e1 = edge[i1 >> 5], e2 = edge[i2 >> 5], e3 = edge[i3 >> 5];
+        // neighbours are compared through an unsigned-char cast in the reference (:1746-1748)
+        const unsigned char g1 = (unsigned char)ed_g(r1), g2 = (unsigned char)ed_g(r2), g3 = (unsigned char)ed_g(r3);
+        if (g1 >= g2 && g1 >= g3) { x += mx1; y += my1; idx = i1; cur = r1; visited = (e1 >> (i1 & 31)) & 1u; }
+        else if (g3 >= g2 && g3 >= g1) { x += mx3; y += my3; idx = i3; cur = r3; visited = (e3 >> (i3 & 31)) & 1u; }
+        else { x += mx2; y += my2; idx = i2; cur = r2; visited = (e2 >> (i2 & 31)) & 1u; }
+        lastDirection = dir;
     }
     // the staged tail
     if (n & 31) { const int o = (n & ~31) + lane; if (lane < (n & 31) && o < cap) out[o] = mine; }
@@ -399,9 +393,10 @@ __device__ void ed_fit_warp(const EdBuffers& B, const EdDims& d, int frame, int 
 }
 
 constexpr int EDF_WARPS = 4;
+constexpr int EDF_CTAS_PER_FRAME = 16;  // 64 warps per frame stride over its chains (a frame has tens of chains, the capacity is thousands)
 __global__ void __launch_bounds__(32 * EDF_WARPS) k_ed_fit_warp(EdBuffers B, EdDims d) {
-    const int chain = blockIdx.x * EDF_WARPS + (threadIdx.x >> 5), frame = blockIdx.y;
-    if (chain < B.n_chains[frame]) ed_fit_warp(B, d, frame, chain, threadIdx.x & 31);
+    const int frame = blockIdx.y, n = B.n_chains[frame];
+    for (int chain = blockIdx.x * EDF_WARPS + (threadIdx.x >> 5); chain < n; chain += gridDim.x * EDF_WARPS) ed_fit_warp(B, d, frame, chain, threadIdx.x & 31);
 }
 
 __global__ void __launch_bounds__(32) k_ed_emit(EdBuffers B, EdDims d, int filter, float length_thres, int max_lines) {
@@ -539,7 +534,7 @@ int csb_edlines_run(csb_context* c, int timed) {
         }
     }
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[2], st));
-    k_ed_fit_warp<<<dim3((d.max_edges + 1 + EDF_WARPS - 1) / EDF_WARPS, d.n_frames), 32 * EDF_WARPS, 0, st>>>(B, d);
+    k_ed_fit_warp<<<dim3(EDF_CTAS_PER_FRAME, d.n_frames), 32 * EDF_WARPS, 0, st>>>(B, d);
     k_ed_emit<<<d.n_frames, 32, 0, st>>>(B, d, s.params.filter, s.params.line_length_thres, s.params.max_lines);
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[3], st));
     CSB_CUDA(c, cudaGetLastError());

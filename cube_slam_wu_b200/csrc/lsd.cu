@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_lsd_maps(LsdBuffers B, LsdDims d
             }
             const double v = r0 * (double)b0 + r1 * (double)b1;
             sc[yy * SC_SP + xx] = v;
-            if (xx < SC_TW && yy < SC_TH) B.scaled[((size_t)f * d.H + dy) * d.W + dx] = v;  // kept for csb_lsd_debug_maps
+            if (B.scaled && xx < SC_TW && yy < SC_TH) B.scaled[((size_t)f * d.H + dy) * d.W + dx] = v;  // only for csb_lsd_debug_maps (8 B per scaled pixel otherwise)
         }
     }
     __syncthreads();
@@ -1375,6 +1375,7 @@ int csb_lsd_run(csb_context* c, int timed) {
     CSB_CUDA(c, cudaSetDevice(c->device));
     const LsdDims& d = s.d;
     LsdBuffers B = lsd_buffers(s);
+    B.scaled = nullptr;  // the scaled image itself is no input of any later stage: written only on request (csb_lsd_debug_maps)
     cudaStream_t st = c->stream;
     CSB_CUDA(c, cudaMemsetAsync(s.d_stats.p, 0, 128, st));
     if (timed) CSB_CUDA(c, cudaEventRecord(s.ev[0], st));
@@ -1468,7 +1469,15 @@ int csb_lsd_debug_maps(csb_context* c, int frame, double* scaled_out, double* mo
     CSB_CUDA(c, cudaSetDevice(c->device));
     CSB_CUDA(c, cudaStreamSynchronize(c->stream));
     const size_t n = (size_t)s.d.W * s.d.H, off = n * frame;
-    if (scaled_out) CSB_CUDA(c, cudaMemcpy(scaled_out, s.d_scaled.as<double>() + off, n * 8, cudaMemcpyDeviceToHost));
+    if (scaled_out) {
+        // the run does not keep the scaled image: the first stage is run again for it (the frames are still resident; it rewrites the same
+        // per-pixel maps, nothing a later download reads)
+        LsdBuffers B = lsd_buffers(s);
+        k_lsd_maps<<<dim3((s.d.W + SC_TW - 1) / SC_TW, (s.d.H + SC_TH - 1) / SC_TH, s.d.n_frames), SC_THREADS, 0, c->stream>>>(B, s.d, s.C);
+        CSB_CUDA(c, cudaGetLastError());
+        CSB_CUDA(c, cudaStreamSynchronize(c->stream));
+        CSB_CUDA(c, cudaMemcpy(scaled_out, s.d_scaled.as<double>() + off, n * 8, cudaMemcpyDeviceToHost));
+    }
     if (modgrad_out) CSB_CUDA(c, cudaMemcpy(modgrad_out, s.d_mg.as<double>() + off, n * 8, cudaMemcpyDeviceToHost));
     if (angles_out) {
         std::vector<float> deg(n);

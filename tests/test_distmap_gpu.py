@@ -61,6 +61,23 @@ def test_noise_frames_and_image_borders(ctx, csb):
     _run_gray(ctx, csb, batch, csb.DetectParams.default())
 
 
+def test_wide_and_tiny_rois(ctx, csb):
+    """ROI widths that take every column-per-thread class of the sweeps (<= 256, <= 512, <= 768, wider), the shared-memory row pass of ROIs
+    wider than 416 columns, and ROIs of a few pixels; textured frames so that every stage has work."""
+    from cube_slam_wu_b200 import synth
+    rng = np.random.default_rng(11)
+    batch = synth.make_kitti_batch(2, boxes_per_frame=8, seed=80)
+    W, Hh = batch["img_w"], batch["img_h"]
+    yy, xx = np.mgrid[0:Hh, 0:W]
+    tex = (127 + 90 * np.sin(xx / 7.0) * np.cos(yy / 5.0) + rng.normal(0, 12, (Hh, W))).clip(0, 255).astype(np.uint8)
+    batch["images"] = [tex, np.ascontiguousarray(tex[::-1, ::-1])]
+    b0 = batch["box_ranges"][0][0]
+    for k, bx in enumerate([[20, 20, 1190, 320, 0.5], [30, 40, 700, 200, 0.5], [100, 50, 450, 250, 0.5], [600, 200, 6, 5, 0.5], [5, 5, 3, 40, 0.5],
+                            [300, 100, 257, 9, 0.5], [640, 60, 513, 120, 0.5], [200, 150, 769, 100, 0.5]]):
+        batch["boxes"][b0 + k] = bx
+    _run_gray(ctx, csb, batch, csb.DetectParams.default(whether_sample_bbox_height=1))
+
+
 def test_blank_and_single_edge_rois(ctx, csb):
     """No edge pixel at all in a ROI (distance saturates at DIST_MAX) and a single vertical step edge."""
     from cube_slam_wu_b200 import synth
