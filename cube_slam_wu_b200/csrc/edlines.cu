@@ -77,7 +77,18 @@ __device__ __forceinline__ int edw_walk(EdWindow& w, uint32_t* edge, unsigned x,
     int idx = (int)(y * (unsigned)W + x);
     uint16_t cur = __ldg(gd + idx);
     bool visited = (edge[idx >> 5] >> (idx & 31)) & 1u;
+    // The lanes run the walk redundantly, so they can do something useful on the side: whenever the walk has left the middle of the window
+    // fetched last, lane l prefetches (to L1) the lines of row y - 16 + l left and right of x.  A vertical edge otherwise meets a new cache
+    // line -- an L2 round trip -- at every step.
+    int pfx = -100000, pfy = -100000;
     while (ed_g(cur) > 0 && !visited) {
+        if (abs((int)x - pfx) > 24 || abs((int)y - pfy) > 6) {
+            pfx = (int)x; pfy = (int)y;
+            const int ry = min(max((int)y - 16 + lane, 0), H - 1);
+            const uint16_t* row = gd + (size_t)ry * W;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(row + max((int)x - 40, 0)));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(row + min((int)x + 40, W - 1)));
+        }
         __syncwarp();
         if (lane == 0) edge[idx >> 5] |= 1u << (idx & 31);
         if ((n & 31) == lane) mine = make_ushort2((unsigned short)x, (unsigned short)y);
