@@ -339,7 +339,7 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
         CSB_CUDA(c, cudaMemsetAsync(misc, 0, 64, st));
         if (d.gray_mapped) {
             const long long whole = gray_total & ~(long long)15;  // the last (partial) 16-byte chunk goes by a plain copy: nothing is read past the caller's buffer
-            CSB_CUDA(c, d.d_segbits.ensure(4 * (size_t)((gray_total / 128 + 64) / 32 + 2)));
+            CSB_CUDA(c, d.d_segbits.ensure(4 * (size_t)((gray_total / CSB_GRAY_SEG + 64) / 32 + 2)));
             CSB_CUDA(c, launch_gray_gather(B, d.gray_mapped, d.d_gray.as<uint8_t>(), whole, d.d_segbits.as<unsigned>(), misc, c->num_sms, st));
             if (gray_total > whole) CSB_CUDA(c, cudaMemcpyAsync(d.d_gray.as<uint8_t>() + whole, gray + whole, (size_t)(gray_total - whole), cudaMemcpyHostToDevice, st));
         }
@@ -422,7 +422,7 @@ int csb_detect_download(csb_context* c, csb_cuboid* cuboids_out, int32_t* n_cubo
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
         for (int t = 0; t < d.n_tasks; t++) { stats->n_enumerated += d.ttab[t].n_enum; stats->n_scored += nv[t]; stats->n_kept += nk[t]; }
-        stats->h2d_bytes = d.h2d_bytes + (d.gray_mode ? 128 * (int64_t)reinterpret_cast<const int*>(hr + d.res_off_misc)[0] : 0);
+        stats->h2d_bytes = d.h2d_bytes + (d.gray_mode ? CSB_GRAY_SEG * (int64_t)reinterpret_cast<const int*>(hr + d.res_off_misc)[0] : 0);
         stats->d2h_bytes = d2h;
         stats->n_kernel_launches = d.launches_last;
         for (const TaskTab& t : d.ttab) stats->n_tasks_smem_map += (t.roi_w * t.roi_h <= d.map_cap_floats) ? 1 : 0;

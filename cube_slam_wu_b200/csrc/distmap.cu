@@ -437,15 +437,20 @@ __global__ void __launch_bounds__(DM_THREADS, 4) k_distmap(DetectBuffers B, cons
 }
 
 // ---- gray-frame upload without the copy engine: only what the ROIs read -----------------------------------------------------------
-// The packed gray frames of a batch are one linear byte array, cut into 128-byte segments (8 lanes x 16 bytes).  k_gray_mark sets
-// the bit of every segment that holds a pixel of some task's ROI or of its one-pixel Sobel halo (clamped to the image); k_gray_gather
-// copies the marked segments from the caller's pinned (device-mapped) buffer into the device frame buffer -- SM-initiated PCIe reads
-// run at the copy engine's rate (measured: 50 GB/s against 55), so the upload shrinks with the share of the frames the boxes cover.
-// Everything outside the marked segments is never read by k_canny in a way that reaches a result (magnitudes outside the ROI count as 0).
+// The packed gray frames of a batch are one linear byte array, cut into segments of CSB_GRAY_SEG bytes.  k_gray_mark sets the bit of every
+// segment that holds a pixel of some task's ROI or of its one-pixel Sobel halo (clamped to the image); k_gray_gather copies the marked
+// segments from the caller's pinned (device-mapped) buffer into the device frame buffer -- SM-initiated PCIe reads run at the copy engine's
+// rate (measured: 50 GB/s against 55), so the upload shrinks with the share of the frames the boxes cover.  A ROI row is ~220 bytes at an
+// arbitrary offset: with 128-byte segments it costs 2.7 segments (346 bytes), with 32-byte segments (one sector) 7.8 (250 bytes): 18 MB ->
+// 13 MB per bench step, which is what counts when eight ranks pull from one host.
+// Everything outside the marked segments is never read by k_distmap in a way that reaches a result (magnitudes outside the ROI count as 0).
 // The gather is a persistent kernel of small CTAs (64 threads, <= 32 registers, no shared memory) so that it finds room next to the
 // one-CTA-per-SM scoring kernel of another context and the transfer overlaps compute the way a copy-engine transfer would.
-constexpr int GSEG = 128;
+constexpr int GSEG = CSB_GRAY_SEG;
 constexpr int GG_THREADS = 64;
+constexpr int GG_LPS = GSEG / 16;       // lanes per segment (16 bytes each)
+constexpr int GG_SPI = 32 / GG_LPS;     // segments per load instruction of a warp
+static_assert(GSEG >= 16 && GSEG <= 128 && (GSEG & (GSEG - 1)) == 0, "CSB_GRAY_SEG");
 
 __global__ void __launch_bounds__(128) k_gray_mark(DetectBuffers B, unsigned* seg_bits) {
     const int task = blockIdx.x;
@@ -465,11 +470,11 @@ __global__ void __launch_bounds__(128) k_gray_mark(DetectBuffers B, unsigned* se
     }
 }
 
-// Each warp walks bitmap words (32 segments = 4 KB of frame); a load instruction moves four segments (lane / 8 = segment, lane % 8 = chunk),
-// two load instructions are in flight per lane before the stores.
+// Each warp walks bitmap words (32 segments); a load instruction moves GG_SPI segments (lane / GG_LPS = segment, lane % GG_LPS = 16-byte
+// chunk), two load instructions are in flight per lane before the stores.
 __global__ void __launch_bounds__(GG_THREADS, 8) k_gray_gather(const uint4* __restrict__ src, uint4* __restrict__ dst, const unsigned* __restrict__ seg_bits, int n_words,
                                                              long long n_chunks16, int* n_segments_out) {
-    const int lane = threadIdx.x & 31, sub = lane >> 3, ch = lane & 7;
+    const int lane = threadIdx.x & 31, sub = lane / GG_LPS, ch = lane % GG_LPS;
     const int warp = (blockIdx.x * GG_THREADS + threadIdx.x) >> 5, n_warps = (gridDim.x * GG_THREADS) >> 5;
     int n_mine = 0;
     for (int w = warp; w < n_words; w += n_warps) {
@@ -480,12 +485,12 @@ __global__ void __launch_bounds__(GG_THREADS, 8) k_gray_gather(const uint4* __re
             uint4 v[2];
 #pragma unroll
             for (int k = 0; k < 2; k++) {
-                // the (sub + 1)-th set bit of m, then drop up to four bits
+                // the (sub + 1)-th set bit of m, then drop up to GG_SPI bits
                 const unsigned b = __fns(m, 0, sub + 1);
                 o[k] = (b < 32u) ? ((long long)w * 32 + b) * (GSEG / 16) + ch : -1;
                 if (o[k] >= n_chunks16) o[k] = -1;
 #pragma unroll
-                for (int q = 0; q < 4; q++) m &= m - 1;
+                for (int q = 0; q < GG_SPI; q++) m &= m - 1;
                 if (o[k] >= 0) v[k] = src[o[k]];
             }
 #pragma unroll

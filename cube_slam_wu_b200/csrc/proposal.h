@@ -58,6 +58,8 @@ cudaError_t launch_select(const DetectBuffers& B, int max_hyp_per_task, int max_
 cudaError_t launch_recover(const DetectBuffers& B, cudaStream_t st);
 cudaError_t launch_rank(const DetectBuffers& B, int n_boxes, cudaStream_t st);
 cudaError_t launch_distmaps(const DetectBuffers& B, const uint8_t* gray, uint8_t* cmap, int* queue, unsigned* dtmp, float* maps, int max_roi_w, int max_pm_words, cudaStream_t st);
+// granularity of the ROI-segment upload of the gray frames (bytes; a power of two, 16 .. 128): see distmap.cu
+constexpr int CSB_GRAY_SEG = 32;
 cudaError_t launch_gray_gather(const DetectBuffers& B, const uint8_t* gray_host_mapped, uint8_t* gray_dev, long long n_bytes, unsigned* seg_bits, int* n_segments_out,
                                int num_sms, cudaStream_t st);
 cudaError_t score_phase_cycles(unsigned long long* out12, bool reset);

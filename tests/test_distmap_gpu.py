@@ -90,7 +90,7 @@ def test_blank_and_single_edge_rois(ctx, csb):
 
 
 def test_pinned_frames_are_fetched_by_roi_segments(ctx, csb):
-    """csb_detect_upload_gray with a PINNED gray buffer (CSB_OPT_GRAY_GATHER, default on): a kernel fetches only the 512-byte segments the
+    """csb_detect_upload_gray with a PINNED gray buffer (CSB_OPT_GRAY_GATHER, default on): a kernel fetches only the 32-byte segments the
     ROIs (+ Sobel halo) touch from the caller's memory.  Same maps, same cuboids as the whole-frame copy; fewer bytes over PCIe."""
     import torch
     from cube_slam_wu_b200 import synth
