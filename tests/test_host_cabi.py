@@ -129,3 +129,34 @@ def test_line_lbd_mirror_refuses_unported_modes(csb):
     d.use_LSD = False
     d.detect_filter_lines(np.zeros((8, 8), np.uint8))
     assert calls == [("lsd", 15.0, True), ("edlines", 15.0, True)]
+
+
+def test_ba_online_entry_points_without_a_context(csb):
+    """csb_ba_add_frame / csb_ba_optimize: argument errors, not crashes, with or without a GPU; the mirrored structs have the header's layout."""
+    L = csb.lib()
+    f = csb.BAFrame()
+    idx = C.c_int32(-1)
+    assert L.csb_ba_add_frame(None, C.byref(f), C.byref(idx)) == csb.CSB_ERR_INVALID
+    assert L.csb_ba_add_frame(None, None, None) == csb.CSB_ERR_INVALID
+    assert L.csb_ba_optimize(None, 5, None, None, None) == csb.CSB_ERR_INVALID
+    assert L.csb_ba_set_graph(None, None) == csb.CSB_ERR_INVALID
+    # csb_ba_frame: pointer, 2 x int32, 2 pointers, int32 (+ pad), 3 pointers, int32 (+ pad), 3 pointers
+    assert C.sizeof(csb.BAFrame) == 8 + 8 + 16 + 8 + 24 + 8 + 24
+    assert C.sizeof(csb.BAOptimizeStats) == 4 * 4 + 2 * 8 + 2 * 4
+    assert C.sizeof(csb.DetectStats) == 5 * 8 + 2 * 4 + 6 * 4
+
+
+def test_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference: the reference's CPU path (the oracle port, all host threads) on the bench workload; one JSON line with the
+    base contract's keys plus impl / cpu_baseline / e2e (no copies).  One step of one warm-up here; the driver runs it with its own K / W."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["impl"] == "reference" and d["metric"] == "cuboid_proposals_scored_per_sec" and d["unit"] == "proposals/s"
+    assert d["value"] > 0 and d["steps"] == 1 and d["higher_is_better"] is True and d["dtype"] == "f64"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"]
