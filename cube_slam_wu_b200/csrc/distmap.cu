@@ -238,8 +238,17 @@ __global__ void __launch_bounds__(DM_THREADS, 4) k_distmap(DetectBuffers B, cons
                 S8[(size_t)y * RB + b] = 0; W8[(size_t)y * RB + b] = 0;
             }
         }
-        int n_st = (2 * DM_WARPS) / n_wc;
-        n_st = max(1, min(n_st, (H + 7) >> 3));
+        // number of row strips: the one that wastes least -- idle warps in the last round of units against the two extra rows a strip
+        // starts with (score = units / (8 ceil(units / 8)) x SR / (SR + 2), compared as integers)
+        int n_st = 1;
+        {
+            long long best = -1;
+            for (int c = 1; c <= 2 * DM_WARPS && c <= H; c++) {
+                const int sr = (H + c - 1) / c, u = n_wc * ((H + sr - 1) / sr);
+                const long long score = (long long)u * sr * 1024 / ((long long)((u + DM_WARPS - 1) / DM_WARPS) * DM_WARPS * (sr + 2));
+                if (score > best) { best = score; n_st = c; }
+            }
+        }
         const int SR = (H + n_st - 1) / n_st;
         const int n_units = n_wc * n_st;
         for (int u = warp; u < n_units; u += DM_WARPS) {

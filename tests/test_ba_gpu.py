@@ -177,4 +177,8 @@ def test_analytic_mode_optimizes_to_the_same_point(ctx):
     (c0, q0, s0), (c1, q1, s1) = res
     assert s0.iterations == s1.iterations
     assert abs(s0.chi2 - s1.chi2) <= 1e-5 * max(1.0, s0.chi2)
-    assert np.abs(c0 - c1).max() < 1e-5 and np.abs(q0 - q1).max() < 1e-5
+    # Both runs stop by g2o's rule (chi2 gain below 1e-3 of chi2) after the same number of iterations, at the same chi2 to 1e-10; the estimates
+    # then agree as far as the numeric Jacobians' own round-off (4e-6 of the block scale, test above) pins a point in the flat directions of
+    # the cost: observed 3e-6 on the cameras, 1.2e-5 on the cuboids (it moves in the last digit with the summation order of the linear solve).
+    # Bar: the north star's 1e-4 for poses / scales.
+    assert np.abs(c0 - c1).max() < 1e-4 and np.abs(q0 - q1).max() < 1e-4
