@@ -78,9 +78,33 @@ public:
         g.n_ec = (int)ec_.size(); g.ec_cam = ec_cam.data(); g.ec_cube = ec_cube.data(); g.ec_meas = ec_meas.data(); g.ec_info = ec_info.data();
         g.n_ep = (int)ep_.size(); g.ep_cam = ep_cam.data(); g.ep_cube = ep_cube.data(); g.ep_meas = ep_meas.data(); g.ep_info = ep_info.data(); g.ep_K = ep_K.data();
         g.n_eo = (int)eo_.size(); g.eo_cam_i = eo_i.data(); g.eo_cam_j = eo_j.data(); g.eo_meas = eo_meas.data(); g.eo_info = eo_info.data();
+        // Online mode (main_obj.cpp:738-803 adds one keyframe per frame and optimises again): when the graph is the previous one plus ONE
+        // camera with its edges (and landmarks first seen by it), only that frame goes to the device (csb_ba_add_frame); anything else --
+        // also any change to an old measurement -- rebuilds the device graph.
+        bool done = false;
+        if (have_graph_ && grown_by_one_frame(ec_cam, ec_cube, ec_meas, ec_info, ep_cam, eo_i, eo_j, eo_meas, eo_info)) {
+            const size_t oc = ec_cam_.size(), oo = eo_i_.size(), oq = n_cube_prev_;
+            csb_ba_frame f = {};
+            Vector7d cv = cams_.back()->estimate().toVector();
+            f.cam7 = cv.data(); f.cam_fixed = cam_fixed_.back();
+            std::vector<double> nq;
+            for (size_t i = oq; i < cubes_.size(); i++) { Vector10d v = cubes_[i]->estimate().toVector(); nq.insert(nq.end(), v.data(), v.data() + 10); }
+            f.n_new_cubes = (int)(cubes_.size() - oq); f.new_cubes10 = nq.data(); f.new_cube_fixed = cube_fixed_.data() + oq;
+            f.n_ec = (int)(ec_cam.size() - oc); f.ec_cube = ec_cube.data() + oc; f.ec_meas = ec_meas.data() + 10 * oc; f.ec_info = ec_info.data() + 81 * oc;
+            f.n_eo = (int)(eo_i.size() - oo); f.eo_cam_i = eo_i.data() + oo; f.eo_meas = eo_meas.data() + 7 * oo; f.eo_info = eo_info.data() + 36 * oo;
+            int32_t idx = -1;
+            if (csb_ba_add_frame(ctx_, &f, &idx) == CSB_OK && idx == (int)cams_.size() - 1) { done = true; n_incremental_++; }
+        }
+        if (!done && csb_ba_set_graph(ctx_, &g) != CSB_OK) { have_graph_ = false; return false; }
         ec_cam_ = ec_cam; ec_cube_ = ec_cube; ep_cam_ = ep_cam; ep_cube_ = ep_cube; eo_i_ = eo_i; eo_j_ = eo_j;
-        return csb_ba_set_graph(ctx_, &g) == CSB_OK;
+        ec_meas_ = ec_meas; ec_info_ = ec_info; eo_meas_ = eo_meas; eo_info_ = eo_info;
+        n_cam_prev_ = cams_.size(); n_cube_prev_ = cubes_.size(); cam_fixed_prev_ = cam_fixed_; cube_fixed_prev_ = cube_fixed_;
+        have_graph_ = true;
+        return true;
     }
+
+    // how many buildStructure() calls were served by csb_ba_add_frame
+    int incrementalUpdates() const { return n_incremental_; }
 
     // One GPU linearisation instead of the per-edge loop; then copy blocks into the memory g2o mapped (Eigen blocks are
     // column-major, like the C ABI's) and gather b, exactly as block_solver.hpp:546-557 does.
@@ -117,6 +141,23 @@ public:
     }
 
 private:
+    template <class T>
+    static bool is_prefix(const std::vector<T>& a, const std::vector<T>& b) { return a.size() <= b.size() && std::equal(a.begin(), a.end(), b.begin()); }
+    // the marshalled graph = the one on the device + exactly one camera, whose cuboid edges start at it and whose odometry edges end at it
+    bool grown_by_one_frame(const std::vector<int32_t>& ec_cam, const std::vector<int32_t>& ec_cube, const std::vector<double>& ec_meas,
+                            const std::vector<double>& ec_info, const std::vector<int32_t>& ep_cam, const std::vector<int32_t>& eo_i,
+                            const std::vector<int32_t>& eo_j, const std::vector<double>& eo_meas, const std::vector<double>& eo_info) const
+    {
+        if (cams_.size() != n_cam_prev_ + 1 || cubes_.size() < n_cube_prev_ || !ep_cam.empty() || !ep_cam_.empty()) return false;
+        if (!is_prefix(cam_fixed_prev_, cam_fixed_) || !is_prefix(cube_fixed_prev_, cube_fixed_)) return false;
+        if (!is_prefix(ec_cam_, ec_cam) || !is_prefix(ec_cube_, ec_cube) || !is_prefix(ec_meas_, ec_meas) || !is_prefix(ec_info_, ec_info)) return false;
+        if (!is_prefix(eo_i_, eo_i) || !is_prefix(eo_j_, eo_j) || !is_prefix(eo_meas_, eo_meas) || !is_prefix(eo_info_, eo_info)) return false;
+        const int32_t nc = (int32_t)n_cam_prev_;
+        for (size_t e = ec_cam_.size(); e < ec_cam.size(); e++) if (ec_cam[e] != nc) return false;
+        for (size_t e = eo_i_.size(); e < eo_i.size(); e++) if (eo_j[e] != nc || eo_i[e] >= nc) return false;
+        return true;
+    }
+
     // blk = A^T Omega B of the edge (di x dj, column-major; A belongs to vertex 0).  The block g2o accumulates it into is found the way
     // buildStructure() allocated it: upper block triangle of _Hpp for two poses (stored transposed when vertex 0 has the larger
     // hessian index), _Hll for two marginalised vertices, _Hpl (pose row, landmark column) for a mixed pair.
@@ -145,6 +186,12 @@ private:
     std::vector<EdgeSE3CuboidProj*> ep_;
     std::vector<EdgeSE3Expmap*> eo_;
     std::vector<double> H_cam_, b_cam_, H_cube_, b_cube_, ec_Hij_, ep_Hij_, eo_Hij_;
+    // what the device graph was built from (the incremental path compares against it)
+    std::vector<double> ec_meas_, ec_info_, eo_meas_, eo_info_;
+    std::vector<int32_t> cam_fixed_prev_, cube_fixed_prev_;
+    size_t n_cam_prev_ = 0, n_cube_prev_ = 0;
+    bool have_graph_ = false;
+    int n_incremental_ = 0;
 };
 
 }  // namespace g2o

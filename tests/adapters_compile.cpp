@@ -123,6 +123,47 @@ int main(int argc, char** argv)
         for (int i = 0; i < 54; i++) nz = std::max(nz, std::fabs(ec_Hij[54 + i]));
         CHECK(nz > 1e-3);
         std::printf("BA adapter: diagonal blocks and b identical to csb_ba_linearize (max diff %g)\n", worst);
+
+        // ---- online mode: one more keyframe (camera 2, its cuboid edge, the odometry edge from camera 1): buildStructure() must hand only
+        // that frame to the device (csb_ba_add_frame) and the blocks must equal the ones of the grown graph loaded at once
+        g2o::VertexSE3Expmap cam2;
+        g2o::Vector7d c2v; c2v(0) = 0.6; c2v(1) = -0.15; c2v(2) = 0.1; c2v(3) = 0.02; c2v(4) = -0.03; c2v(5) = 0.05; c2v(6) = std::sqrt(1 - 0.0038);
+        cam2.setEstimate(g2o::SE3Quat(c2v));
+        g2o::EdgeSE3Cuboid e2;
+        g2o::Vector10d m2 = qv; m2(2) += 0.03; m2(8) -= 0.01;
+        e2.setVertex(0, &cam2); e2.setVertex(1, &cube); e2.setMeasurement(g2o::cuboid(m2));
+        g2o::EdgeSE3Expmap eo2; eo2.setVertex(0, &cam1); eo2.setVertex(1, &cam2); eo2.setMeasurement(g2o::SE3Quat(c1v));
+        opt._activeEdges = {&e0, &e1, &e2, &eo, &eo2};
+        opt._ivMap = {&cam1, &cam2, &cube};
+        CHECK(solver.buildStructure());
+        CHECK(solver.incrementalUpdates() == 1);
+        CHECK(solver.buildSystem());
+        {
+            const int32_t cam_fixed3[3] = {1, 0, 0}, ec_cam3[3] = {0, 1, 2}, ec_cube3[3] = {0, 0, 0}, eo_i3[2] = {0, 1}, eo_j3[2] = {1, 2};
+            std::vector<double> ec_meas3(30), ec_info3(243, 0.0), eo_meas3(14), eo_info3(72, 0.0), cams7_3(21, 0.0);
+            for (int i = 0; i < 10; i++) { ec_meas3[i] = m0(i); ec_meas3[10 + i] = m1(i); ec_meas3[20 + i] = m2(i); }
+            for (int e = 0; e < 3; e++) for (int i = 0; i < 9; i++) ec_info3[81 * e + 10 * i] = 1.0;
+            for (int e = 0; e < 2; e++) for (int i = 0; i < 6; i++) eo_info3[36 * e + 7 * i] = 1.0;
+            for (int i = 0; i < 7; i++) { eo_meas3[i] = c1v(i); eo_meas3[7 + i] = c1v(i); cams7_3[7 + i] = c1v(i); cams7_3[14 + i] = c2v(i); }
+            cams7_3[6] = 1.0;
+            csb_ba_graph g3 = {};
+            g3.n_cam = 3; g3.n_cube = 1; g3.cam_fixed = cam_fixed3; g3.cube_fixed = cube_fixed;
+            g3.n_ec = 3; g3.ec_cam = ec_cam3; g3.ec_cube = ec_cube3; g3.ec_meas = ec_meas3.data(); g3.ec_info = ec_info3.data();
+            g3.n_eo = 2; g3.eo_cam_i = eo_i3; g3.eo_cam_j = eo_j3; g3.eo_meas = eo_meas3.data(); g3.eo_info = eo_info3.data();
+            CHECK(csb_ba_set_graph(ctx, &g3) == CSB_OK);
+            std::vector<double> H_cam3(108), b_cam3(18), H_cube3(81), b_cube3(9);
+            csb_ba_output o3 = {};
+            o3.H_cam = H_cam3.data(); o3.b_cam = b_cam3.data(); o3.H_cube = H_cube3.data(); o3.b_cube = b_cube3.data();
+            CHECK(csb_ba_linearize(ctx, cams7_3.data(), cubes10.data(), &o3) == CSB_OK);
+            double w3 = 0;
+            for (int i = 0; i < 36; i++) w3 = std::max(w3, std::fabs(cam1.hessianData()[i] - H_cam3[36 + i]));
+            for (int i = 0; i < 36; i++) w3 = std::max(w3, std::fabs(cam2.hessianData()[i] - H_cam3[72 + i]));
+            for (int i = 0; i < 81; i++) w3 = std::max(w3, std::fabs(cube.hessianData()[i] - H_cube3[i]));
+            for (int i = 0; i < 6; i++) w3 = std::max(w3, std::fabs(solver.b()[cam2.colInHessian() + i] - b_cam3[12 + i]));
+            for (int i = 0; i < 9; i++) w3 = std::max(w3, std::fabs(solver.b()[cube.colInHessian() + i] - b_cube3[i]));
+            CHECK(w3 == 0.0);
+            std::printf("BA adapter, one more keyframe through csb_ba_add_frame: blocks identical to the grown graph loaded at once (max diff %g)\n", w3);
+        }
         csb_destroy(ctx);
     } catch (const std::exception& ex) {
         std::printf("exception: %s\n", ex.what());
