@@ -123,10 +123,29 @@ class GpuBackend:
                     dpitch=c.camera_pitch_delta, rank_index=int(c.rank_index), dist=c.edge_distance_error, angle=c.edge_angle_error)
 
     def optimize(self, cams, fixed, cube, ec, eo):
+        """The node adds one keyframe per frame and optimises again (main_obj.cpp:738-803): after the first frame the device graph grows by
+        csb_ba_add_frame (the frame's camera, its cuboid edge if the box gave one, the odometry edge from the previous frame); the first frame
+        -- or anything that is not 'the graph so far plus one frame' -- goes through csb_ba_set_graph."""
         ctx = self.ctx
-        ecs = (np.array(ec[0], np.int32), np.array(ec[1], np.int32), np.array(ec[2]).reshape(-1, 10), np.array(ec[3]).reshape(-1, 81)) if len(ec[0]) else None
-        eos = (np.array(eo[0], np.int32), np.array(eo[1], np.int32), np.array(eo[2]).reshape(-1, 7), np.array(eo[3]).reshape(-1, 36)) if len(eo[0]) else None
-        ctx.ba_set_graph(np.array(fixed, np.int32), np.zeros(1, np.int32), ec=ecs, ep=None, eo=eos)
+        n = len(cams)
+        state = getattr(self, "_ba_state", None)
+        grown = (state is not None and state == (n - 1, sum(1 for c in ec[0] if c < n - 1), sum(1 for j in eo[1] if j < n - 1)) and n >= 2)
+        if grown:
+            m_ec = [k for k, c in enumerate(ec[0]) if c == n - 1]
+            m_eo = [k for k, j in enumerate(eo[1]) if j == n - 1]
+            grown = all(k >= state[1] for k in m_ec) and all(k >= state[2] for k in m_eo)
+        if grown:
+            ecf = (np.array([ec[1][k] for k in m_ec], np.int32), np.array([ec[2][k] for k in m_ec]).reshape(-1, 10), np.array([ec[3][k] for k in m_ec]).reshape(-1, 81)) if m_ec else None
+            eof = (np.array([eo[0][k] for k in m_eo], np.int32), np.array([eo[2][k] for k in m_eo]).reshape(-1, 7), np.array([eo[3][k] for k in m_eo]).reshape(-1, 36)) if m_eo else None
+            idx = ctx.ba_add_frame(np.array(cams[-1]), cam_fixed=bool(fixed[-1]), ec=ecf, eo=eof)
+            assert idx == n - 1
+            self.n_add_frame = getattr(self, "n_add_frame", 0) + 1
+        else:
+            ecs = (np.array(ec[0], np.int32), np.array(ec[1], np.int32), np.array(ec[2]).reshape(-1, 10), np.array(ec[3]).reshape(-1, 81)) if len(ec[0]) else None
+            eos = (np.array(eo[0], np.int32), np.array(eo[1], np.int32), np.array(eo[2]).reshape(-1, 7), np.array(eo[3]).reshape(-1, 36)) if len(eo[0]) else None
+            ctx.ba_set_graph(np.array(fixed, np.int32), np.zeros(1, np.int32), ec=ecs, ep=None, eo=eos)
+        self._ba_state = (n, len(ec[0]), len(eo[0]))
+        # the caller's estimates (in the checked replay they are the ORACLE's, so that every frame compares like with like)
         ctx.ba_upload_estimates(np.array(cams), cube.reshape(1, 10))
         c2, q2, _ = ctx.ba_optimize(5)
         return c2, q2[0]

@@ -129,6 +129,22 @@ class _FakeCtx:
         self.calls.append("set_graph")
         self.g = (np.asarray(cam_fixed), np.asarray(cube_fixed), ec, eo)
 
+    def ba_add_frame(self, cam7, cam_fixed=False, new_cubes10=None, new_cube_fixed=None, ec=None, eo=None):
+        """csb_ba_add_frame: the stored graph + one camera, its cuboid edges (ec = cube, meas, info) and the odometry edges that end at it."""
+        self.calls.append("add_frame")
+        cam_fixed_, cube_fixed_, ec0, eo0 = self.g
+        assert new_cubes10 is None
+        cam = len(cam_fixed_)
+        cat = lambda a, b, shape: np.concatenate([np.asarray(a).reshape(shape), np.asarray(b).reshape(shape)]) if a is not None else np.asarray(b).reshape(shape)
+        if ec is not None:
+            old = ec0 if ec0 is not None else (None, None, None, None)
+            ec0 = (cat(old[0], np.full(len(ec[0]), cam, np.int32), (-1,)), cat(old[1], ec[0], (-1,)), cat(old[2], ec[1], (-1, 10)), cat(old[3], ec[2], (-1, 81)))
+        if eo is not None:
+            old = eo0 if eo0 is not None else (None, None, None, None)
+            eo0 = (cat(old[0], eo[0], (-1,)), cat(old[1], np.full(len(eo[0]), cam, np.int32), (-1,)), cat(old[2], eo[1], (-1, 7)), cat(old[3], eo[2], (-1, 36)))
+        self.g = (np.append(cam_fixed_, int(cam_fixed)), cube_fixed_, ec0, eo0)
+        return cam
+
     def ba_upload_estimates(self, cams7, cubes10):
         self.calls.append("upload")
         assert cams7.shape == (len(self.g[0]), 7) and cubes10.shape == (len(self.g[1]), 10)
@@ -155,6 +171,8 @@ def test_gpu_backend_glue_with_a_fake_context(seq, csb):
     assert np.array_equal(got["cube10"], ref["cube10"]) and np.array_equal(got["Twc"], ref["Twc"])
     assert fake.calls[:7] == ["blur3", "edlines", "blur4", "detect", "set_graph", "upload", "optimize"]
     assert fake.calls.count("detect") == sum(1 for b in boxes[:n] if len(b)) < n   # frames without a YOLO box skip detect_cuboid
+    # the device graph is loaded once and then grows frame by frame (csb_ba_add_frame), like the node's
+    assert fake.calls.count("set_graph") == 1 and fake.calls.count("add_frame") == n - 1
     fake2 = _FakeCtx(csb)
     replay.run(replay.GpuBackend(fake2, csb, use_lsd=True), frames, boxes, truth, n_frames=3)
     assert fake2.calls[0] == "lsd"

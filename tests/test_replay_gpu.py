@@ -1,6 +1,6 @@
 """The reference's object_slam node in online mode on its bundled TUM sequence (tests/replay.py; main_obj.cpp:479-841), every stage through the
-C ABI on the GPU -- csb_edlines_detect_batch (or csb_lsd_detect_batch), csb_detect_batch_gray, csb_ba_set_graph + csb_ba_optimize after every
-frame -- against (i) the CPU oracles stage by stage and (ii) the reference's own committed output files (main_obj.cpp:305-336 writes them)."""
+C ABI on the GPU -- csb_edlines_detect_batch (or csb_lsd_detect_batch), csb_detect_batch_gray, the graph loaded once (csb_ba_set_graph) and grown
+by csb_ba_add_frame, csb_ba_optimize after every frame -- against (i) the CPU oracles stage by stage and (ii) the reference's own committed output files (main_obj.cpp:305-336 writes them)."""
 import numpy as np
 import pytest
 
@@ -31,7 +31,9 @@ def test_gpu_replay_reproduces_the_reference_output_files(ctx, csb, seq):
     output_obj_poses.txt and output_cam_poses.txt at the files' printed precision -- the same bounds tests/test_reference_replay.py holds the
     oracle chain to -- and the drift against the oracle replay, reported separately."""
     frames, boxes, truth, out_obj, out_cam = seq
-    gpu = replay.run(replay.GpuBackend(ctx, csb), frames, boxes, truth)
+    backend = replay.GpuBackend(ctx, csb)
+    gpu = replay.run(backend, frames, boxes, truth)
+    assert backend.n_add_frame == len(frames) - 1   # one csb_ba_set_graph, then one csb_ba_add_frame per frame, like the node
     obj = gpu["obj"]
     dpos = np.linalg.norm(obj[:, :3] - out_obj[:, :3], axis=1)
     dyaw = np.abs(np.angle(np.exp(1j * (obj[:, 5] - out_obj[:, 5]))))
