@@ -476,7 +476,10 @@ def run_ours(args, rank, local_rank, world):
                "gpu_launches": (int(st.n_kernel_launches) + 1) * args.steps,
                "roofline": {"kernel": "k_score", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PROPOSAL * n_scored,
-                            "kernel_ms": k_ms, "note": "gather/FP64-issue bound, not HBM bound (SURVEY.md 8d)"},
+                            "kernel_ms": k_ms,
+                            "note": "FP64 / issue bound, not HBM bound (SURVEY.md 8d): ncu of this kernel (profiles/r02_ncu_score.md) shows 81 M warp instructions, "
+                                    "53 % issue-slot and 36 % FP64-pipe utilisation, 77 MB of DRAM traffic against 192 MB algorithmic (the gathers hit shared memory); "
+                                    "DESIGN.md section 8 lists what was measured against it"},
                "enumerated_per_s": n_enum_all * args.steps / (ms_total * 1e-3),
                "scored_per_step_per_gpu": n_scored, "enumerated_per_step_per_gpu": n_enum,
                "kernel_ms": {"prep_lines": float(np.mean([s[0] for s in score_ms])), "score": k_ms, "select": float(np.mean([s[2] for s in score_ms])),
