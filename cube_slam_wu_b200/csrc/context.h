@@ -77,6 +77,7 @@ struct DetectState {
     bool gray_gather_enabled = true;       // csb_set_option(CSB_OPT_GRAY_GATHER)
     cudaEvent_t ev_tables = nullptr;  // h_tables consumed by the device
     cudaEvent_t ev_order = nullptr;   // compute stream -> copy stream ordering of the streamed map upload
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // gray mode: the line kernels run on the copy stream beside k_distmap
     bool gray_mode = false;
     unsigned epoch = 0;
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
