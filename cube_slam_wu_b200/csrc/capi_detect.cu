@@ -156,7 +156,7 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
     if (d.gray_mode) {
         // gray frames are packed back to back (img_height x img_width bytes each)
         if (n_gray_bytes != gray_total) { c->err = "csb_detect_upload_gray: n_gray_bytes != sum of img_width*img_height"; return CSB_ERR_INVALID; }
-        CSB_CUDA(c, d.d_gray.ensure((size_t)gray_total + 64));
+        CSB_CUDA(c, d.d_gray.ensure_zeroed((size_t)gray_total + 64, st));  // cleared once: with the ROI-segment upload k_distmap's aligned word loads touch bytes of segments that are never fetched (they reach no result)
         // Pinned (device-mapped) caller memory: the frames are not copied as a whole -- once the task table is on the device, a kernel
         // fetches the 512-byte segments the ROIs touch straight from the caller's buffer (launch_gray_gather below).  Pageable memory
         // goes through the copy engine as one block.
@@ -288,7 +288,12 @@ static int detect_upload_impl(csb_context* c, const csb_frame* frames, int n_fra
     d.res_off_nkeep = align256(d.res_off_nvalid + 4 * NT);
     d.res_off_misc = align256(d.res_off_nkeep + 4 * NT);  // [0]: 128-byte segments fetched by the gray gather
     d.res_bytes = align256(d.res_off_misc + 64);
-    CSB_CUDA(c, d.d_results.ensure(d.res_bytes));
+    {
+        // the result arena goes to the host as one block: its padding and the unused cuboid slots are defined bytes (zero) from the start
+        const size_t cap_before = d.d_results.cap;
+        CSB_CUDA(c, d.d_results.ensure(d.res_bytes));
+        if (d.d_results.cap != cap_before) CSB_CUDA(c, cudaMemsetAsync(d.d_results.p, 0, d.d_results.cap, st));
+    }
     CSB_CUDA(c, d.h_results.ensure(d.res_bytes));
     if (d.gray_mode || n_map_floats <= 0) CSB_CUDA(c, d.d_maps.ensure(4 * (size_t)nm + 64));
     CSB_CUDA(c, d.d_ml_seg.ensure(32 * LT));

@@ -25,6 +25,14 @@ struct DevBuf {
         if (e == cudaSuccess) cap = want;
         return e;
     }
+    // like ensure(); a (re)allocated block is cleared once.  For output arrays that go to the host in strided blocks (rows beyond a frame's
+    // count, padding): the host trims them, but every byte it receives is a defined one.
+    cudaError_t ensure_zeroed(size_t bytes, cudaStream_t st) {
+        const size_t before = cap;
+        cudaError_t e = ensure(bytes);
+        if (e == cudaSuccess && cap != before) e = cudaMemsetAsync(p, 0, cap, st);
+        return e;
+    }
     void release() {
         if (p) cudaFree(p);
         p = nullptr;

@@ -495,8 +495,8 @@ int csb_edlines_upload(csb_context* c, const uint8_t* gray, int n_frames, int wi
     CSB_CUDA(c, s.d_sid.ensure(nf * (d.max_edges + 2) * 4));
     CSB_CUDA(c, s.d_nch.ensure(nf * 4));
     CSB_CUDA(c, s.d_stage.ensure(nf * d.stage_cap * sizeof(EdLine)));
-    CSB_CUDA(c, s.d_lines.ensure(nf * params->max_lines * 16));
-    CSB_CUDA(c, s.d_keyl.ensure(nf * params->max_lines * 8));
+    CSB_CUDA(c, s.d_lines.ensure_zeroed(nf * params->max_lines * 16, c->stream));
+    CSB_CUDA(c, s.d_keyl.ensure_zeroed(nf * params->max_lines * 8, c->stream));
     CSB_CUDA(c, s.d_nlines.ensure(nf * 4));
     CSB_CUDA(c, s.d_stats.ensure(64));
     cudaPointerAttributes pa{};
@@ -626,8 +626,8 @@ int csb_edlines_describe(csb_context* c, int want_float) {
         CSB_CUDA(c, lbd_upload_weights(c->stream));
         s.weights_set = true;
     }
-    CSB_CUDA(c, s.d_desc.ensure(rows * 32));
-    if (want_float) CSB_CUDA(c, s.d_descf.ensure(rows * 72 * 4));
+    CSB_CUDA(c, s.d_desc.ensure_zeroed(rows * 32, c->stream));
+    if (want_float) CSB_CUDA(c, s.d_descf.ensure_zeroed(rows * 72 * 4, c->stream));
     CSB_CUDA(c, s.d_weights.ensure((size_t)(s.d.n_frames + 1) * 4 + 64));  // scratch of the describe stage: line prefix + work counters
     EdBuffers B = ed_buffers(s);
     // the warp-cooperative descriptor kernel of lbd.cu on the detector's own key-line fields (k_lbdk_line is the one-thread-per-line

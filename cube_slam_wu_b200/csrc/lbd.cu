@@ -519,9 +519,9 @@ static int lbd_outputs(csb_context* c, LbdState& s) {
     const size_t rows = (size_t)s.n_frames * s.stride;
     CSB_CUDA(c, s.d_prefix.ensure((size_t)(s.n_frames + 1) * 4));
     CSB_CUDA(c, s.d_grad.ensure((size_t)s.n_frames * s.w * s.h * 4));
-    CSB_CUDA(c, s.d_desc.ensure(std::max<size_t>(rows, 1) * 32));
-    CSB_CUDA(c, s.d_keyl.ensure(std::max<size_t>(rows, 1) * 16));
-    if (s.want_float) CSB_CUDA(c, s.d_descf.ensure(std::max<size_t>(rows, 1) * 72 * 4));
+    CSB_CUDA(c, s.d_desc.ensure_zeroed(std::max<size_t>(rows, 1) * 32, c->stream));
+    CSB_CUDA(c, s.d_keyl.ensure_zeroed(std::max<size_t>(rows, 1) * 16, c->stream));
+    if (s.want_float) CSB_CUDA(c, s.d_descf.ensure_zeroed(std::max<size_t>(rows, 1) * 72 * 4, c->stream));
     CSB_CUDA(c, s.d_ctr.ensure(64));
     return CSB_OK;
 }

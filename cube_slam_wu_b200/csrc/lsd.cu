@@ -1336,7 +1336,7 @@ static int lsd_prepare(csb_context* c, int n_frames, int width, int height, cons
     CSB_CUDA(c, s.d_stage.ensure((size_t)n_frames * s.stage_cap * 16));
     CSB_CUDA(c, s.d_stage_key.ensure((size_t)n_frames * s.stage_cap * 4));
     CSB_CUDA(c, s.d_stage_owner.ensure((size_t)n_frames * s.stage_cap * 4));
-    CSB_CUDA(c, s.d_lines.ensure((size_t)n_frames * params->max_lines * 16));
+    CSB_CUDA(c, s.d_lines.ensure_zeroed((size_t)n_frames * params->max_lines * 16, c->stream));
     CSB_CUDA(c, s.d_nlines.ensure((size_t)n_frames * 4));
     CSB_CUDA(c, s.d_stats.ensure(128));
     CSB_CUDA(c, cudaFuncSetAttribute(k_lsd_grow<LSD_WARPS_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.grow_smem));
