@@ -444,6 +444,31 @@ def run_ours(args, rank, local_rank, world):
             e2e_extra[name] = fn(mode)
         except Exception as e:
             e2e_extra[name] = {"error": str(e)}
+    # one FRAME per blocking call: what a caller of the reference's detect_cuboid(rgb_img, ...) sees, frame after frame (rank 0's first frames)
+    try:
+        nf1 = min(16, len(batch["K"]))
+        per_frame = []
+        singles = []
+        for f in range(nf1):
+            b0_, b1_ = batch["box_ranges"][f]
+            l0_, l1_ = batch["line_ranges"][f]
+            sub = dict(K=batch["K"][f:f + 1], T=batch["T"][f:f + 1], boxes=batch["boxes"][b0_:b1_], lines=batch["lines"][l0_:l1_], box_ranges=[(0, b1_ - b0_)],
+                       line_ranges=[(0, l1_ - l0_)], images=[batch["images"][f]], img_w=batch["img_w"], img_h=batch["img_h"])
+            fr1, bx1, ln1, tk1, nt1, _, _ = pipeline.pack_inputs(csb, sub, params, with_maps=False)
+            tg1, g1 = pinned(np.ascontiguousarray(batch["images"][f].ravel(), np.uint8))
+            keep.append(tg1)
+            singles.append((fr1, bx1, ln1, tk1, nt1, g1))
+        for rep in range(4):
+            for (fr1, bx1, ln1, tk1, nt1, g1) in singles:
+                t0 = time.perf_counter()
+                ctx.detect_batch_gray(fr1, bx1, ln1, tk1, nt1, g1, params, want_stats=False)
+                if rep > 0:
+                    per_frame.append(time.perf_counter() - t0)
+        e2e_extra["single_frame_call_gray"] = {"ms_per_frame": 1e3 * float(np.median(per_frame)), "ms_per_frame_p90": 1e3 * float(np.percentile(per_frame, 90)),
+                                               "frames": nf1, "boxes_per_frame": BOXES_PER_FRAME,
+                                               "note": "one blocking csb_detect_batch_gray() per frame (pinned gray frame in, cuboids out), median over 3 passes of 16 frames"}
+    except Exception as e:
+        e2e_extra["single_frame_call_gray"] = {"error": str(e)}
     del pipe_ctx
     sampler.mark_end()  # the sampled window covers the timed regions of value, serial and e2e (all under load)
     clocks = sampler.stop()
