@@ -29,13 +29,15 @@
 
 #include <cstdint>
 
+#include <cstdlib>
+#include <cstring>
 #include "context.h"
 #include "ptx_helpers.cuh"
 
 namespace csb {
 
-constexpr int DM_THREADS = 256;
-constexpr int DM_WARPS = DM_THREADS / 32;
+constexpr int DM_THREADS_BATCH = 256;   // CTA of a batch launch: 4 ROIs per SM
+constexpr int DM_THREADS_FEW = 1024;    // few ROIs (a single frame): the whole SM works on one ROI, for latency
 constexpr int DM_COLS = 120;  // ROI columns a warp produces per row: lanes 1..30 x 4 pixels (lanes 0 and 31 only supply the magnitude halo)
 
 constexpr unsigned DT_HV = 62587u;                 // cvRound(0.955f  * 65536)
@@ -63,13 +65,13 @@ __device__ __forceinline__ unsigned spread16(unsigned x) {
 }
 
 // The two vertical sweeps of the distance transform (see k_distmap), thread = column x = tid + k * DM_THREADS.
-template <int CPT>
+template <int CPT, int DM_THREADS>
 __device__ __forceinline__ void dt_sweeps(int W, int H, int WPE, const unsigned* Sb, int* rowD, int* rowU, int WB, int* __restrict__ tmpD, int* __restrict__ tmpU, int tid) {
     const int HV = (int)DT_HV, DG = (int)DT_DG;
     int dprev[CPT], uprev[CPT];
 #pragma unroll
     for (int k = 0; k < CPT; k++) { dprev[k] = DT_INF; uprev[k] = DT_INF; }
-    const unsigned* ed = Sb + (tid >> 5);                  // word of column tid in row 0; column tid + 256 k is 8 k words further
+    const unsigned* ed = Sb + (tid >> 5);                  // word of column tid in row 0; column tid + DM_THREADS k is DM_THREADS / 32 k words further
     const unsigned* eu = Sb + (H - 1) * WPE + (tid >> 5);
     const int sh = tid & 31;
     int* gd = tmpD + tid;
@@ -84,8 +86,8 @@ __device__ __forceinline__ void dt_sweeps(int W, int H, int WPE, const unsigned*
                 int d = min(dprev[k] + HV, min(rowD[off_p + x], rowD[off_p + x + 2]) + DG);
                 int u = min(uprev[k] + HV, min(rowU[off_p + x], rowU[off_p + x + 2]) + DG);
                 d = min(d, DT_INF); u = min(u, DT_INF);
-                if ((ed[8 * k] >> sh) & 1u) d = 0;
-                if ((eu[8 * k] >> sh) & 1u) u = 0;
+                if ((ed[(DM_THREADS / 32) * k] >> sh) & 1u) d = 0;
+                if ((eu[(DM_THREADS / 32) * k] >> sh) & 1u) u = 0;
                 dprev[k] = d; uprev[k] = u;
                 rowD[off_c + x + 1] = d; rowU[off_c + x + 1] = u;
                 gd[k * DM_THREADS] = d;
@@ -95,6 +97,36 @@ __device__ __forceinline__ void dt_sweeps(int W, int H, int WPE, const unsigned*
         ed += WPE; eu -= WPE; gd += W; gu -= W;
         off_c ^= WB; off_p ^= WB;
         __syncthreads();
+    }
+}
+
+// The same two sweeps when the ROI is at most half a CTA wide: warps 0 .. nw - 1 run the downward sweep, warps nw .. 2 nw - 1 the upward
+// one, each group on its own named barrier (two shorter dependency chains side by side; the other warps wait at the caller's barrier).
+__device__ __forceinline__ void dt_sweeps_split(int W, int H, int WPE, const unsigned* Sb, int* rowD, int* rowU, int WB, int* __restrict__ tmpD, int* __restrict__ tmpU, int tid) {
+    const int HV = (int)DT_HV, DG = (int)DT_DG;
+    const int nw = (W + 31) >> 5, grp = (tid >> 5) / nw;
+    if (grp >= 2) return;
+    const int x = tid - grp * nw * 32;
+    const bool up = grp == 1;
+    const int step = up ? -1 : 1, y0 = up ? H - 1 : 0;
+    const unsigned* e = Sb + y0 * WPE + (x >> 5);
+    const int sh = x & 31;
+    int* row = up ? rowU : rowD;
+    int* g = (up ? tmpU : tmpD) + (size_t)y0 * W + x;
+    int prev = DT_INF, off_c = 0, off_p = WB;
+    for (int i = 0; i < H; i++) {
+        if (x < W) {
+            int d = min(prev + HV, min(row[off_p + x], row[off_p + x + 2]) + DG);
+            d = min(d, DT_INF);
+            if ((*e >> sh) & 1u) d = 0;
+            prev = d;
+            row[off_c + x + 1] = d;
+            *g = d;
+        }
+        e += step * WPE; g += step * W;
+        off_c ^= WB; off_p ^= WB;
+        if (up) asm volatile("bar.sync 2, %0;" ::"r"(nw * 32) : "memory");
+        else asm volatile("bar.sync 1, %0;" ::"r"(nw * 32) : "memory");
     }
 }
 
@@ -202,8 +234,10 @@ __device__ long long g_dm_phase[DM_PHASE_TASKS][8];
 //     dist(x) = min_x' (V(x') + a |x - x'|) with V = min(Down, Up): a prefix-min of V - a x and a suffix-min of V + a x, one warp per
 //     row (every lane scans a contiguous chunk in shared memory, the lanes' totals are combined with shuffles).  Checked against cv2 on
 //     the CPU (numpy model) before it was written, and bit for bit on the GPU by tests/test_distmap_gpu.py.
-__global__ void __launch_bounds__(DM_THREADS, 4) k_distmap(DetectBuffers B, const uint8_t* __restrict__ gray, uint8_t* cmap, int* queue, int* dtmp, float* maps,
+template <int DM_THREADS>
+__global__ void __launch_bounds__(DM_THREADS, 1024 / DM_THREADS) k_distmap(DetectBuffers B, const uint8_t* __restrict__ gray, uint8_t* cmap, int* queue, int* dtmp, float* maps,
                                                            int low, int high, int plane_words_cap, int work_ints) {
+    constexpr int DM_WARPS = DM_THREADS / 32;
     extern __shared__ __align__(16) unsigned char dm_smem[];
     unsigned* Sb = reinterpret_cast<unsigned*>(dm_smem);                 // edge bits, H * WPE words; the weak plane follows it
     int* work = reinterpret_cast<int*>(Sb + plane_words_cap);            // sweeps: 2 x 2 row buffers; row pass: 2 buffers per warp
@@ -240,14 +274,18 @@ __global__ void __launch_bounds__(DM_THREADS, 4) k_distmap(DetectBuffers B, cons
         }
         // number of row strips: the one that wastes least -- idle warps in the last round of units against the two extra rows a strip
         // starts with (score = units / (8 ceil(units / 8)) x SR / (SR + 2), compared as integers)
-        int n_st = 1;
+        int n_st;
         {
-            long long best = -1;
-            for (int c = 1; c <= 2 * DM_WARPS && c <= H; c++) {
-                const int sr = (H + c - 1) / c, u = n_wc * ((H + sr - 1) / sr);
-                const long long score = (long long)u * sr * 1024 / ((long long)((u + DM_WARPS - 1) / DM_WARPS) * DM_WARPS * (sr + 2));
-                if (score > best) { best = score; n_st = c; }
+            // (every warp finds it for itself: candidate c = lane + 1 + 32 i, best of the warp by shuffles, the smallest c on ties)
+            unsigned best = 0;  // score << 8 | (255 - c)
+            for (int c = lane + 1; c <= 2 * DM_WARPS && c <= H; c += 32) {
+                const unsigned sr = (H + c - 1) / c, u = n_wc * ((H + sr - 1) / sr);
+                const unsigned score = u * sr * 1024u / (((u + DM_WARPS - 1) / DM_WARPS) * DM_WARPS * (sr + 2));  // <= 1024
+                best = max(best, score << 8 | (unsigned)(255 - c));
             }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
+            n_st = 255 - (int)(best & 255u);
         }
         const int SR = (H + n_st - 1) / n_st;
         const int n_units = n_wc * n_st;
@@ -405,10 +443,13 @@ __global__ void __launch_bounds__(DM_THREADS, 4) k_distmap(DetectBuffers B, cons
     DM_PHASE(2);
     int* tmpD = dtmp + t.map_offset;
     int* tmpU = queue + t.map_offset;
-    if (W <= DM_THREADS) dt_sweeps<1>(W, H, WPE, Sb, rowD, rowU, WB, tmpD, tmpU, tid);
-    else if (W <= 2 * DM_THREADS) dt_sweeps<2>(W, H, WPE, Sb, rowD, rowU, WB, tmpD, tmpU, tid);
-    else if (W <= 3 * DM_THREADS) dt_sweeps<3>(W, H, WPE, Sb, rowD, rowU, WB, tmpD, tmpU, tid);
-    else dt_sweeps<5>(W, H, WPE, Sb, rowD, rowU, WB, tmpD, tmpU, tid);
+    if (2 * ((W + 31) & ~31) <= DM_THREADS) {
+        dt_sweeps_split(W, H, WPE, Sb, rowD, rowU, WB, tmpD, tmpU, tid);
+        __syncthreads();
+    } else if (W <= DM_THREADS) dt_sweeps<1, DM_THREADS>(W, H, WPE, Sb, rowD, rowU, WB, tmpD, tmpU, tid);
+    else if (W <= 2 * DM_THREADS) dt_sweeps<2, DM_THREADS>(W, H, WPE, Sb, rowD, rowU, WB, tmpD, tmpU, tid);
+    else if (W <= 3 * DM_THREADS) dt_sweeps<3, DM_THREADS>(W, H, WPE, Sb, rowD, rowU, WB, tmpD, tmpU, tid);
+    else dt_sweeps<5, DM_THREADS>(W, H, WPE, Sb, rowD, rowU, WB, tmpD, tmpU, tid);
     DM_PHASE(3);
     // ---- row pass (the sweeps end with a barrier: the block's global writes are visible to all its threads).
     // Scaled like OpenCV: (float)(unsigned) * 2^-16; unreachable -> DIST_MAX.
@@ -416,10 +457,11 @@ __global__ void __launch_bounds__(DM_THREADS, 4) k_distmap(DetectBuffers B, cons
         const int HV = (int)DT_HV;
         const int CH = ((W + 31) >> 5) | 1;   // odd chunk length: conflict-free shared-memory access at stride CH
         const int WP = 32 * CH;
+        const int n_rw = min(DM_WARPS, work_ints / (2 * WP));  // warps that get a buffer pair (all of them unless the ROI is very wide)
         int* buf = work + warp * 2 * WP;
         float* out = maps + t.map_offset;
         const float scale = 1.f / 65536.f;
-        for (int y = warp; y < H; y += DM_WARPS) {
+        for (int y = warp; y < H && warp < n_rw; y += n_rw) {
             const int* rd = tmpD + (size_t)y * W;
             const int* ru = tmpU + (size_t)y * W;
             if (CH <= 5) { row_load<5>(buf, rd, ru, W, CH, lane); row_scan_regs<5>(buf, CH, lane); }
@@ -525,15 +567,32 @@ cudaError_t launch_gray_gather(const DetectBuffers& B, const uint8_t* gray_host_
 
 cudaError_t launch_distmaps(const DetectBuffers& B, const uint8_t* gray, uint8_t* cmap, int* queue, unsigned* dtmp, float* maps, int max_roi_w, int max_pm_words, cudaStream_t st) {
     if (B.n_tasks == 0) return cudaSuccess;
-    if (max_roi_w > DM_THREADS * 5) return cudaErrorInvalidValue;  // ROI wider than 1280 px
+    if (max_roi_w > DM_THREADS_BATCH * 5) return cudaErrorInvalidValue;  // ROI wider than 1280 px
     const int plane_cap = (max_pm_words + 3) & ~3;  // >= 2 * H * ceil(W / 32) words for every task (capi_detect.cu)
     const int wp = 32 * (((max_roi_w + 31) >> 5) | 1);
-    const int work_ints = 2 * DM_WARPS * wp;  // >= 4 * (W + 2)
+    // few ROIs (one frame per call): one 1024-thread CTA per ROI -- four times the warps on the suppression units and on the row pass
+    bool few = B.n_tasks <= 148;  // at most one ROI per SM
+    if (const char* force = getenv("CSB_DISTMAP_CTA")) {  // the tests run every case through both variants
+        if (!strcmp(force, "1024")) few = true;
+        else if (!strcmp(force, "256")) few = false;
+    }
+    const int warps = (few ? DM_THREADS_FEW : DM_THREADS_BATCH) / 32;
+    // work space: row pass (2 buffers of wp ints per warp, as many warps as fit in ~96 KB, at least 8) | sweeps (4 * (W + 2)) | nothing else
+    int rw = warps;
+    while (rw > 8 && (size_t)2 * rw * wp * 4 > 96 * 1024) rw >>= 1;
+    const int work_ints = 2 * rw * wp;
     const size_t smem = 4 * (size_t)plane_cap + 4 * (size_t)work_ints;
     if (smem > 220 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(k_distmap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    k_distmap<<<B.n_tasks, DM_THREADS, smem, st>>>(B, gray, cmap, queue, reinterpret_cast<int*>(dtmp), maps, 80, 200, plane_cap, work_ints);
+    cudaError_t e;
+    if (few) {
+        e = cudaFuncSetAttribute(k_distmap<DM_THREADS_FEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_distmap<DM_THREADS_FEW><<<B.n_tasks, DM_THREADS_FEW, smem, st>>>(B, gray, cmap, queue, reinterpret_cast<int*>(dtmp), maps, 80, 200, plane_cap, work_ints);
+    } else {
+        e = cudaFuncSetAttribute(k_distmap<DM_THREADS_BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_distmap<DM_THREADS_BATCH><<<B.n_tasks, DM_THREADS_BATCH, smem, st>>>(B, gray, cmap, queue, reinterpret_cast<int*>(dtmp), maps, 80, 200, plane_cap, work_ints);
+    }
     return cudaGetLastError();
 }
 

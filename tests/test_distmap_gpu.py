@@ -12,6 +12,14 @@ import helpers as H
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["256", "1024"])
+def distmap_cta(request, monkeypatch):
+    """k_distmap has two CTA sizes: 256 threads for a batch (four ROIs per SM) and 1024 when a call holds at most one ROI per SM (a single
+    frame; latency).  launch_distmaps picks by task count; every case here runs through both (CSB_DISTMAP_CTA forces one)."""
+    monkeypatch.setenv("CSB_DISTMAP_CTA", request.param)
+    return request.param
+
+
 def _gray(batch):
     return np.ascontiguousarray(np.concatenate([im.ravel() for im in batch["images"]]).astype(np.uint8))
 
