@@ -49,6 +49,7 @@ def build(force=False, verbose=False):
         extra.append("-DCSB_DM_PHASES")  # per-task stage cycles of k_distmap (tools/distmap_phases.py)
     if os.environ.get("CSB_CHOL_DEBUG") == "1":
         extra.append("-DCSB_CHOL_DEBUG")  # k_chol_solve prints its per-phase cycle counts
+    extra += os.environ.get("CSB_NVCC_EXTRA", "").split()  # development: -D overrides for A/B builds (tools/pipelined_time.py)
     for src in CU_SOURCES + CPP_SOURCES:
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
         cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
