@@ -1,7 +1,7 @@
 """GPU debug helper: prints GPU vs oracle Jacobians of the EdgeSE3CuboidProj edges of the small test graph."""
 import sys, os
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import cube_slam_wu_b200 as csb
 from cube_slam_wu_b200 import synth

@@ -1,8 +1,8 @@
 """Times the EDLines kernels (and the descriptor stage on their key lines) on a batch of synthetic frames, checking the first frames against the
-oracle: python tools/edlines_time.py [n_frames] [w] [h]"""
+oracle: python tests/diag/edlines_time.py [n_frames] [w] [h]"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import cube_slam_wu_b200 as csb
 from cube_slam_wu_b200 import synth

@@ -10,20 +10,18 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
 
 
 def main():
     import torch
     import cube_slam_wu_b200 as csb
-    from cube_slam_wu_b200 import synth
-    import helpers as H
+    from cube_slam_wu_b200 import pipeline, synth
 
     torch.cuda.set_device(0)
     ctx = csb.Context(0)
     params = csb.DetectParams.default()
     batch = synth.make_kitti_batch(64, boxes_per_frame=8, seed=20260925)
-    frames, boxes, lines, tasks, n_tasks, maps, n_map = H.gpu_inputs(csb, batch, params)
+    frames, boxes, lines, tasks, n_tasks, maps, n_map = pipeline.pack_inputs(csb, batch, params)
 
     def pinned(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
