@@ -734,10 +734,11 @@ __device__ __forceinline__ double ordered_key_inv(unsigned long long k) {
     return __longlong_as_double((long long)b);
 }
 
-// k-th smallest (1-based) of v[0..N) by an 8-pass MSB radix select over the ordered keys; also returns how many elements
-// are strictly smaller.  All threads of the block call it; hist = 256 ints of shared memory.
+// k-th smallest (1-based) of v[0..N) by an MSB radix select over the ordered keys (8 bits per pass; the passes end as soon as one
+// candidate is left -- usually after two or three -- or after the eighth); also returns how many elements are strictly smaller.  All
+// threads of the block call it; hist = 256 ints of shared memory, s_bc = 3 ints, s_key = one 64-bit word.
 template <int THREADS>
-__device__ __forceinline__ double radix_select_kth(const double* v, int N, int k, int* hist, int* s_bc, int tid, int& n_less) {
+__device__ __forceinline__ double radix_select_kth(const double* v, int N, int k, int* hist, int* s_bc, unsigned long long* s_key, int tid, int& n_less) {
     unsigned long long prefix = 0, mask = 0;
     int rank = k - 1, below = 0;  // 0-based rank inside the current candidate set
     for (int pass = 0; pass < 8; pass++) {
@@ -759,19 +760,31 @@ __device__ __forceinline__ double radix_select_kth(const double* v, int N, int k
             for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += t; }
             int excl = inc - s;
             if (rank >= excl && rank < inc) {
-                int acc = excl, bin = 0;
+                int acc = excl, bin = 0, cnt = c[7];
 #pragma unroll
-                for (int q = 0; q < 8; q++) { if (rank >= acc + c[q]) { acc += c[q]; } else { bin = q; break; } }
+                for (int q = 0; q < 8; q++) { if (rank >= acc + c[q]) { acc += c[q]; } else { bin = q; cnt = c[q]; break; } }
                 s_bc[0] = 8 * tid + bin;
                 s_bc[1] = acc;  // elements of the candidate set below the chosen bin
+                s_bc[2] = cnt;  // elements in the chosen bin
             }
         }
         __syncthreads();
-        const int bin = s_bc[0], acc = s_bc[1];
+        const int bin = s_bc[0], acc = s_bc[1], cnt = s_bc[2];
         prefix |= ((unsigned long long)bin) << shift;
         mask |= 255ull << shift;
         rank -= acc;
         below += acc;
+        if (cnt == 1 && pass < 7) {
+            // one candidate left: it is the k-th smallest, nothing else shares its remaining bits
+            for (int i = tid; i < N; i += THREADS) {
+                const unsigned long long key = ordered_key(v[i]);
+                if ((key & mask) == prefix) *s_key = key;
+            }
+            __syncthreads();
+            prefix = *s_key;
+            __syncthreads();
+            break;
+        }
         __syncthreads();
     }
     n_less = below;
@@ -785,9 +798,11 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(DetectBuffers B, int 
     __shared__ int s_w[SELECT_THREADS / 32];
     __shared__ double s_red[4 * (SELECT_THREADS / 32)];
     __shared__ int s_hist[256];
-    __shared__ int s_bc[2];
+    __shared__ int s_bc[3];
+    __shared__ unsigned long long s_key;
     const int task = blockIdx.x, tid = threadIdx.x;
     const int N = B.n_valid[task];
+    if (N == 0 && n_lo == 0 && tid == 0) B.n_keep[task] = 0;  // (the first launch also covers the tasks without a valid proposal)
     if (N <= n_lo || N > n_hi) return;
     const TaskTab tt = B.ttab[task];
     const size_t ob = (size_t)tt.out_offset;
@@ -822,11 +837,11 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(DetectBuffers B, int 
         // angle list: sorted[k-1] > sorted[k-2] (:766)  <=>  exactly k-1 elements are strictly below the k-th smallest value;
         // then the kept k-1 are precisely those elements
         int lessA;
-        const double vkA = radix_select_kth<SELECT_THREADS>(va, N, k, s_hist, s_bc, tid, lessA);
+        const double vkA = radix_select_kth<SELECT_THREADS>(va, N, k, s_hist, s_bc, &s_key, tid, lessA);
         const bool angle_active = (lessA == k - 1);
         // distance list: dist_keep = first k-1 of std::partial_sort(iota, iota+k, end) (matrix_utils.cpp:327-335, unstable).
         int lessD;
-        const double vk = radix_select_kth<SELECT_THREADS>(vd, N, k, s_hist, s_bc, tid, lessD);
+        const double vk = radix_select_kth<SELECT_THREADS>(vd, N, k, s_hist, s_bc, &s_key, tid, lessD);
         // With the angle filter on, dist_keep is used as a SET = heap minus its top after __heap_select.  If only one element of
         // value vk is inside the heap (lessD == k-1) it is the top (the dropped k-th) and the set is exactly {d < vk}; otherwise
         // which of the tied elements stay depends on the heap -> replay.  With the angle filter off the kept list keeps
@@ -938,12 +953,6 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(DetectBuffers B, int 
         norm_score[j] = comb;
     }
     if (tid == 0) B.n_keep[task] = n_keep;
-}
-
-// zero-proposal tasks never enter k_select
-__global__ void k_select_init(DetectBuffers B) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < B.n_tasks) B.n_keep[t] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1204,8 +1213,7 @@ static size_t select_smem_bytes(int n) {
 }
 
 cudaError_t launch_select(const DetectBuffers& B, int max_hyp_per_task, int max_smem_optin, cudaStream_t st, int* n_launches) {
-    k_select_init<<<(B.n_tasks + 255) / 256, 256, 0, st>>>(B);
-    int L = 1;
+    int L = 0;
     // small-footprint variant: tasks with up to 2048 valid proposals (several CTAs per SM)
     const int small_cap = 2048;
     cudaError_t e = cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin - 2048);
