@@ -62,6 +62,28 @@ def test_plan_rejects_bad_ranges(csb):
         csb.detect_plan(frames, np.zeros((2, 5)), csb.DetectParams.default())
 
 
+def test_plan_empty_ragged_and_misordered_batches(csb):
+    """Ragged input on the host side of csb_detect_plan / csb_detect_upload (csrc/host_plan.cpp): an empty batch plans to nothing, frames
+    without boxes between frames with boxes keep the frame ids of the others, an ROI is clipped to the image (box_proposal_detail.cpp:262-270
+    expands by 10 px and clamps), and frame box ranges that overlap or go backwards are refused (k_rank / k_observe rely on a box's tasks
+    being contiguous)."""
+    K = np.eye(3); T = np.eye(4)
+    p = csb.DetectParams.default()
+    tasks, n, n_map = csb.detect_plan(csb.make_frames([], [], 100, 100, [], []), np.zeros((0, 5)), p)
+    assert (n, n_map) == (0, 0)
+    boxes = np.array([[10, 10, 100, 100, .5], [600, 400, 39, 79, .5]])
+    frames = csb.make_frames([K, K, K], [T, T, T], 640, 480, [(0, 1), (1, 1), (1, 2)], [(0, 0)] * 3)
+    tasks, n, n_map = csb.detect_plan(frames, boxes, p)
+    assert [(t.frame_id, t.box_id, t.roi_left, t.roi_top, t.roi_width, t.roi_height) for t in tasks[:n]] == \
+        [(0, 0, 0, 0, 120, 120), (2, 1, 590, 390, 49, 89)]
+    assert tasks[1].map_offset >= 120 * 120 and tasks[1].map_offset % 4 == 0 and n_map >= tasks[1].map_offset + 49 * 89
+    ot = O.plan(boxes, 640, 480, False)
+    assert [(b.left, b.top, b.width, b.height) for b in ot] == [(0, 0, 120, 120), (590, 390, 49, 89)]
+    for ranges in ([(0, 2), (1, 2)], [(1, 2), (0, 1)]):
+        with pytest.raises(csb.CsbError):
+            csb.detect_plan(csb.make_frames([K, K], [T, T], 640, 480, ranges, [(0, 0)] * 2), boxes, p)
+
+
 def test_no_cpu_fallback(csb):
     """Without a CUDA device csb_create fails and nothing computes.  (On a GPU box this test only checks the error paths.)"""
     import torch
