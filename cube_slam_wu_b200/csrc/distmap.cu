@@ -579,7 +579,7 @@ cudaError_t launch_distmaps(const DetectBuffers& B, const uint8_t* gray, uint8_t
     const int warps = (few ? DM_THREADS_FEW : DM_THREADS_BATCH) / 32;
     // work space: row pass (2 buffers of wp ints per warp, as many warps as fit in ~96 KB, at least 8) | sweeps (4 * (W + 2)) | nothing else
     int rw = warps;
-    while (rw > 8 && (size_t)2 * rw * wp * 4 > 96 * 1024) rw >>= 1;
+    while (rw > 8 && ((size_t)2 * rw * wp * 4 > 96 * 1024 || 4 * (size_t)plane_cap + (size_t)2 * rw * wp * 4 > 220 * 1024)) rw >>= 1;
     const int work_ints = 2 * rw * wp;
     const size_t smem = 4 * (size_t)plane_cap + 4 * (size_t)work_ints;
     if (smem > 220 * 1024) return cudaErrorInvalidValue;
