@@ -33,6 +33,24 @@ def load_sequence():
     return frames, boxes, ba["truth"], ba["out_obj"], ba["out_cam"]
 
 
+def write_base_folder(dst):
+    """the committed TUM fixture laid out like the reference's object_slam/data (what its node and cube_slam_wu_b200.node read): the JPEG
+    files byte for byte, the YOLO boxes (1-based, tab separated, empty file = no box), truth_cam_poses.txt with its four decimals"""
+    d = np.load(os.path.join(GOLD, "tum_online.npz"))
+    truth = np.load(os.path.join(GOLD, "tum_ba.npz"))["truth"]
+    os.makedirs(os.path.join(dst, "raw_imgs")); os.makedirs(os.path.join(dst, "filter_2d_obj_txts"))
+    for f in range(len(d["jpeg_off"]) - 1):
+        with open(os.path.join(dst, "raw_imgs", "%04d_rgb_raw.jpg" % f), "wb") as fh:
+            fh.write(d["jpeg"][d["jpeg_off"][f]:d["jpeg_off"][f + 1]].tobytes())
+        with open(os.path.join(dst, "filter_2d_obj_txts", "%04d_yolo2_0.15.txt" % f), "w") as fh:
+            for b in d["boxes"][d["boxes"][:, 0] == f][:, 1:]:
+                fh.write("%d\t%d\t%d\t%d\t%.2f\n" % (b[0], b[1], b[2], b[3], b[4]))
+    with open(os.path.join(dst, "truth_cam_poses.txt"), "w") as fh:
+        for r in truth:
+            fh.write("\t".join("%.4f" % v for v in r) + "\t\n")
+    return dst
+
+
 def pose_mat(v7):
     x, y, z, qx, qy, qz, qw = v7
     R = np.array([[1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw)],
