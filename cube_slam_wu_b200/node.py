@@ -1,7 +1,7 @@
 """object_slam's node in ONLINE mode on the B200 library: the host side of the reference's `incremental_build_graph`
 (object_slam/src/main_obj.cpp:479-841, online_detect_mode = true) with every compute stage behind the C ABI.
 
-    python -m cube_slam_wu_b200.node --base-folder <object_slam/data> [--out <dir>] [--lsd] [--blur-generation 3]
+    python -m cube_slam_wu_b200.node --base-folder <object_slam/data> [--out <dir>] [--lsd] [--blur-generation 3] [--offline]
 
 reads the reference's data folder as its node does (raw_imgs/%04d_rgb_raw.jpg, filter_2d_obj_txts/%04d_yolo2_0.15.txt,
 truth_cam_poses.txt: main_obj.cpp:879-893, 585-620) and writes output_cam_poses.txt / output_obj_poses.txt in the reference's formats
@@ -117,39 +117,30 @@ class ObjectSlamNode:
         return cub[0] if ncub[0] >= 1 else None
 
     # -- one frame -----------------------------------------------------------------------------------------------------------------
-    def add_frame(self, gray, boxes):
-        """gray: (h, w) uint8; boxes: (k, 5) x y w h prob, 0-based.  Returns the landmark estimate after this frame's optimisation."""
+    def _predict(self):
+        """constant-velocity prediction of the new frame's camera (:545-564): (Twc, odometry measurement)"""
         f = len(self.cams)
         odom = _IDENT.copy()
         if f == 0:
-            Twc = self.Twc0
-        else:
-            prev = self.cams[f - 1]
-            if f > 1:
-                odom = graph.se3_mul(prev, graph.se3_inv(self.cams[f - 2]))   # constant motion (:556-564)
-            Twc = graph.se3_inv(graph.se3_mul(odom, prev))
-        lines = self.detect_lines(gray)
-        self.n_lines.append(len(lines))
-        sample = f != 0
-        best = self.detect_cuboid(gray, boxes, lines, sample) if len(boxes) else None
+            return self.Twc0, odom
+        prev = self.cams[f - 1]
+        if f > 1:
+            odom = graph.se3_mul(prev, graph.se3_inv(self.cams[f - 2]))
+        return graph.se3_inv(graph.se3_mul(odom, prev)), odom
+
+    def _grow_and_optimize(self, Twc, odom, meas, proposal_error):
+        """vertices / edges of the new frame (:738-799) and graph.optimize (:803); meas = the cuboid in the camera frame or None"""
+        f = len(self.cams)
         ec = None
-        if best is not None:
-            cube_ground = cuboid_from_minimal([best.pos[0], best.pos[1], best.pos[2], 0, 0, best.rotY, best.scale[0], best.scale[1], best.scale[2]])
-            meas = cuboid_transform_to(cube_ground, Twc)
-            if sample:   # the detector's own camera: the first pose with the sampled roll / pitch (:655-672)
-                Tn = np.eye(4)
-                Tn[:3, :3] = np.asarray(synth.euler_zyx_to_rot(self.eul0[0] + best.camera_roll_delta, self.eul0[1] + best.camera_pitch_delta, self.eul0[2]))
-                Tn[:3, 3] = self.T0[:3, 3]
-                meas = cuboid_transform_to(cube_ground, graph.pose7_from_matrix(Tn))
-            quality = (1 - best.normalized_error + 0.5) / 2                         # (:732)
+        if meas is not None:
+            quality = (1 - proposal_error + 0.5) / 2                                 # meas_quality (:732)
             ec = (np.zeros(1, np.int32), meas.reshape(1, 10), ((2 * quality) ** 2 * np.eye(9)).reshape(1, 81))
         cam = graph.se3_inv(Twc)
         if f == 0:
-            if best is None:
+            if meas is None:
                 raise RuntimeError("object_slam node: the first frame has no cuboid -- the reference initialises its landmark from it (main_obj.cpp:745-751)")
             self.cube = cuboid_transform_from(meas, Twc)
-            self.ctx.ba_set_graph(np.ones(1, np.int32), np.zeros(1, np.int32),
-                                  ec=(np.zeros(1, np.int32), ec[0], ec[1], ec[2]), ep=None, eo=None)
+            self.ctx.ba_set_graph(np.ones(1, np.int32), np.zeros(1, np.int32), ec=(np.zeros(1, np.int32), ec[0], ec[1], ec[2]), ep=None, eo=None)
         else:
             eo = (np.array([f - 1], np.int32), odom.reshape(1, 7), np.eye(6).reshape(1, 36))
             idx = self.ctx.ba_add_frame(cam, cam_fixed=False, ec=ec, eo=eo)
@@ -162,6 +153,35 @@ class ObjectSlamNode:
         self.cube = np.array(cubes[0])
         self.history.append(self.cube.copy())
         return self.cube
+
+    def add_frame(self, gray, boxes):
+        """online_detect_mode = true.  gray: (h, w) uint8; boxes: (k, 5) x y w h prob, 0-based.  Returns the landmark estimate after this
+        frame's optimisation."""
+        Twc, odom = self._predict()
+        lines = self.detect_lines(gray)
+        self.n_lines.append(len(lines))
+        sample = len(self.cams) != 0
+        best = self.detect_cuboid(gray, boxes, lines, sample) if len(boxes) else None
+        if best is None:
+            return self._grow_and_optimize(Twc, odom, None, 0.0)
+        cube_ground = cuboid_from_minimal([best.pos[0], best.pos[1], best.pos[2], 0, 0, best.rotY, best.scale[0], best.scale[1], best.scale[2]])
+        meas = cuboid_transform_to(cube_ground, Twc)
+        if sample:   # the detector's own camera: the first pose with the sampled roll / pitch (:655-672)
+            Tn = np.eye(4)
+            Tn[:3, :3] = np.asarray(synth.euler_zyx_to_rot(self.eul0[0] + best.camera_roll_delta, self.eul0[1] + best.camera_pitch_delta, self.eul0[2]))
+            Tn[:3, 3] = self.T0[:3, 3]
+            meas = cuboid_transform_to(cube_ground, graph.pose7_from_matrix(Tn))
+        return self._grow_and_optimize(Twc, odom, meas, best.normalized_error)
+
+    def add_frame_offline(self, saved_cuboid, init_cam_pose_Twc):
+        """online_detect_mode = false (:686-712): the frame's cuboid comes from detect_cuboids_saved.txt (x y z yaw sx sy sz error, in the
+        ground frame of the saved camera pose pop_cam_poses_saved.txt) or is None; only the graph and the optimiser run."""
+        Twc, odom = self._predict()
+        if saved_cuboid is None:
+            return self._grow_and_optimize(Twc, odom, None, 0.0)
+        m = np.asarray(saved_cuboid, np.float64)
+        cube_ground = cuboid_from_minimal([m[0], m[1], m[2], 0, 0, m[3], m[4], m[5], m[6]])
+        return self._grow_and_optimize(Twc, odom, cuboid_transform_to(cube_ground, se3_from_vector7(init_cam_pose_Twc)), m[7])
 
     # -- results -------------------------------------------------------------------------------------------------------------------
     def cam_poses_Twc(self):
@@ -188,6 +208,23 @@ def read_base_folder(base_folder):
         b[:, :2] -= 1                                          # "change matlab coordinate to c++" (:620)
         boxes.append(b)
     return frames, boxes, truth
+
+
+def read_offline_tables(base_folder):
+    """detect_cuboids_saved.txt (frame x y z yaw sx sy sz error, at most one row per frame), pop_cam_poses_saved.txt and truth_cam_poses.txt
+    (time x y z qx qy qz qw): the inputs of the reference's offline mode (main_obj.cpp:879-893)"""
+    rd = lambda n, c: np.loadtxt(os.path.join(base_folder, n)).reshape(-1, c)
+    return rd("detect_cuboids_saved.txt", 9), rd("pop_cam_poses_saved.txt", 8), rd("truth_cam_poses.txt", 8)
+
+
+def run_offline(ctx, csb, det, pop, truth, n_frames=None, **node_args):
+    node = ObjectSlamNode(ctx, csb, truth[0, 1:8], **node_args)
+    row = 0
+    for f in range(len(truth) if n_frames is None else n_frames):
+        has = row < len(det) and int(det[row, 0]) == f          # "not all frame has observation" (:689-690)
+        node.add_frame_offline(det[row, 1:9] if has else None, pop[f, 1:8])
+        row += int(has)
+    return node
 
 
 def _eigen_row(values):
@@ -232,11 +269,16 @@ def main(argv=None):
     ap.add_argument("--out", default=None, help="where output_cam_poses.txt / output_obj_poses.txt go (default: the base folder, like the reference)")
     ap.add_argument("--lsd", action="store_true", help="line_lbd_obj.use_LSD = true (the reference's node runs EDLines)")
     ap.add_argument("--blur-generation", type=int, default=4, choices=[3, 4])
+    ap.add_argument("--offline", action="store_true", help="online_detect_mode = false: cuboids from detect_cuboids_saved.txt, poses from pop_cam_poses_saved.txt")
     ap.add_argument("--device", type=int, default=0)
     a = ap.parse_args(argv)
-    frames, boxes, truth = read_base_folder(a.base_folder)
     ctx = csb.Context(a.device)   # raises if the CUDA library is not built or no device is usable: there is no CPU path
-    node = run_sequence(ctx, csb, frames, boxes, truth, use_lsd=a.lsd, blur_generation=a.blur_generation)
+    if a.offline:
+        det, pop, truth = read_offline_tables(a.base_folder)
+        node = run_offline(ctx, csb, det, pop, truth)
+    else:
+        frames, boxes, truth = read_base_folder(a.base_folder)
+        node = run_sequence(ctx, csb, frames, boxes, truth, use_lsd=a.lsd, blur_generation=a.blur_generation)
     write_results(a.out or a.base_folder, truth[:, 0], node.cam_poses_Twc(), node.object_history_minimal())
     print("%d frames, %d cuboid edges, landmark %s" % (len(node.cams), node.n_cuboid_edges, _eigen_row(node.object_history_minimal()[-1])))
     return node

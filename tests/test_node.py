@@ -93,3 +93,21 @@ def test_first_frame_without_a_cuboid_is_an_error(seq, csb):
     blank = np.full_like(frames[0], 128)
     with pytest.raises(RuntimeError):
         nd.add_frame(blank, np.zeros((0, 5)))
+
+
+def test_offline_mode_matches_the_oracle_replay(csb, tmp_path):
+    """online_detect_mode = false (main_obj.cpp:686-712): saved cuboids + saved camera poses -> the same graph growth and optimiser calls.
+    Against the oracle's replay of that loop (tests/test_ba_gpu.py::tum_graph) on the reference's own tables; the tables also go through the
+    txt reader."""
+    import test_ba_gpu
+    d = np.load(os.path.join(replay.GOLD, "tum_ba.npz"))
+    for name, key, fmt in (("detect_cuboids_saved.txt", "det", "%.10g"), ("pop_cam_poses_saved.txt", "pop", "%.10f"), ("truth_cam_poses.txt", "truth", "%.4f")):
+        np.savetxt(os.path.join(tmp_path, name), d[key], fmt=fmt)
+    det, pop, truth = node.read_offline_tables(str(tmp_path))
+    assert np.allclose(det, d["det"], rtol=1e-9) and np.allclose(pop, d["pop"], atol=1e-9) and np.array_equal(truth, d["truth"])
+    fake = _FakeCtx(csb)
+    nd = node.run_offline(fake, csb, d["det"], d["pop"], d["truth"])
+    assert fake.calls.count("set_graph") == 1 and fake.calls.count("add_frame") == 57 and "detect" not in fake.calls and "edlines" not in fake.calls
+    assert nd.n_cuboid_edges == len(d["det"])
+    ref = test_ba_gpu.tum_graph(d)
+    assert np.abs(np.array(nd.cams) - ref["cams7"]).max() < 1e-5 and np.abs(nd.cube - ref["cubes10"][0]).max() < 1e-5
