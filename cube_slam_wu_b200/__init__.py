@@ -505,6 +505,56 @@ class Context:
         return dx, dy
 
 
+class detect_3d_cuboid:
+    """Host-side mirror of class detect_3d_cuboid (reference: detect_3d_cuboid/include/detect_3d_cuboid/detect_3d_cuboid.h:74-118): same
+    member names, defaults and meaning -- set_calibration, the configuration flags, detect_cuboid(img, transToWolrd, obj_bbox_coors, edges)
+    -- computing on the GPU through csb_detect_batch_gray (Canny + distance transform + the proposal sweep + scoring + ranking + 3D
+    recovery).  The plotting / saving switches of the reference are accepted and ignored (no images are produced)."""
+
+    def __init__(self, ctx):
+        self._ctx = ctx
+        self.Kalib = None
+        self.whether_plot_detail_images = self.whether_plot_final_images = self.whether_save_final_images = self.print_details = False
+        self.consider_config_1 = True                # detect_3d_cuboid.h:109-116
+        self.consider_config_2 = True
+        self.whether_sample_cam_roll_pitch = True
+        self.whether_sample_bbox_height = False
+        self.max_cuboid_num = 1
+        self.nominal_skew_ratio = 1.0
+        self.max_cut_skew = 3.0
+
+    def set_calibration(self, Kalib):
+        self.Kalib = np.asarray(Kalib, np.float64).reshape(3, 3).copy()
+
+    def params(self):
+        return DetectParams(int(self.consider_config_1), int(self.consider_config_2), int(self.whether_sample_cam_roll_pitch),
+                            int(self.whether_sample_bbox_height), int(self.max_cuboid_num), 0, float(self.nominal_skew_ratio), float(self.max_cut_skew))
+
+    def detect_cuboid(self, img, transToWolrd, obj_bbox_coors, edges):
+        """box_proposal_detail.cpp:65-861.  img: (h, w) uint8 gray or (h, w, 3) BGR (converted like cv::cvtColor BGR2GRAY); transToWolrd: 4x4
+        camera-to-world; obj_bbox_coors: (k, 5) x y w h prob, 0-based; edges: (n, 4) x1 y1 x2 y2.  Returns all_object_cuboids: one list per
+        2D box holding up to max_cuboid_num Cuboid records, best first (empty list: no valid proposal for that box)."""
+        if self.Kalib is None:
+            raise CsbError(CSB_ERR_STATE, "detect_3d_cuboid: set_calibration() has not been called")
+        img = np.asarray(img)
+        if img.ndim == 3:   # cv::cvtColor(BGR2GRAY), 8-bit fixed point of OpenCV 4.x: (B * 3735 + G * 19235 + R * 9798 + 2^14) >> 15
+            b, g, r = (img[..., i].astype(np.int32) for i in range(3))   # (bit-identical to cv2 4.13, tests/test_node.py)
+            img = ((b * 3735 + g * 19235 + r * 9798 + 16384) >> 15).astype(np.uint8)
+        if img.ndim != 2 or img.dtype != np.uint8:
+            raise CsbError(CSB_ERR_INVALID, "detect_3d_cuboid: img must be uint8, (h, w) or (h, w, 3)")
+        h, w = img.shape
+        boxes = np.ascontiguousarray(obj_bbox_coors, np.float64).reshape(-1, 5)
+        lines = np.ascontiguousarray(edges, np.float64).reshape(-1, 4) if len(edges) else np.zeros((0, 4))
+        if len(boxes) == 0:
+            return []
+        p = self.params()
+        frames = make_frames([self.Kalib], [np.asarray(transToWolrd, np.float64).reshape(4, 4)], w, h, [(0, len(boxes))], [(0, len(lines))])
+        tasks, n_tasks, _ = detect_plan(frames, boxes, p)
+        cub, ncub, _ = self._ctx.detect_batch_gray(frames, boxes, lines, tasks, n_tasks, np.ascontiguousarray(img.ravel()), p)
+        k = max(1, int(self.max_cuboid_num))
+        return [[cub[b * k + j] for j in range(int(ncub[b]))] for b in range(len(boxes))]
+
+
 class line_lbd_detect:
     """Host-side mirror of class line_lbd_detect (reference: line_lbd/include/line_lbd/line_lbd_allclass.h:20-60) for its LSD branch:
     same member names and meaning (use_LSD, line_length_thres, detect_filter_lines), computing on the GPU through the C ABI."""

@@ -86,6 +86,10 @@ class ObjectSlamNode:
         self.Twc0 = se3_from_vector7(first_cam_pose_Twc)   # fixed_init_cam_pose_Twc (:528): only the first truth pose is used
         self.T0 = pose_matrix(self.Twc0)
         self.eul0 = quat_to_euler_zyx(self.Twc0[3:7])     # cam_pose_raw.euler_angle after set_cam_pose(transToWolrd)
+        self.detector = csb.detect_3d_cuboid(ctx)          # detect_cuboid_obj (:494-500)
+        self.detector.set_calibration(self.K)
+        self.detector.whether_sample_bbox_height = False
+        self.detector.nominal_skew_ratio = self.skew
         self.cams = []            # optimised world -> camera poses (VertexSE3Expmap estimates), one per frame
         self.cube = None          # the landmark (VertexCuboid estimate), 10 doubles
         self.history = []         # the landmark after every frame's optimisation (cube_pose_opti_history)
@@ -105,16 +109,11 @@ class ObjectSlamNode:
         return np.ascontiguousarray(np.asarray(out[0], np.float64)).reshape(-1, 4)
 
     def detect_cuboid(self, gray, boxes, lines, sample_roll_pitch):
-        """the best cuboid of the frame's first 2D box (the reference's frames carry at most one), or None"""
-        csb = self.csb
-        H, W = gray.shape
-        params = csb.DetectParams.default(whether_sample_cam_roll_pitch=int(sample_roll_pitch), nominal_skew_ratio=self.skew)
-        frames = csb.make_frames([self.K], [self.T0], W, H, [(0, len(boxes))], [(0, len(lines))])
-        boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 5)
-        lines = np.ascontiguousarray(lines, np.float64).reshape(-1, 4) if len(lines) else np.zeros((0, 4))
-        tasks, n_tasks, _ = csb.detect_plan(frames, boxes, params)
-        cub, ncub, _ = self.ctx.detect_batch_gray(frames, boxes, lines, tasks, n_tasks, np.ascontiguousarray(gray.ravel(), np.uint8), params)
-        return cub[0] if ncub[0] >= 1 else None
+        """the best cuboid of the frame's first 2D box (frames_cuboids[0][0]; the reference's frames carry at most one box), or None"""
+        d = self.detector
+        d.whether_sample_cam_roll_pitch = bool(sample_roll_pitch)                    # (:624)
+        found = d.detect_cuboid(gray, self.T0, boxes, lines)
+        return found[0][0] if len(found) and len(found[0]) else None
 
     # -- one frame -----------------------------------------------------------------------------------------------------------------
     def _predict(self):

@@ -111,3 +111,30 @@ def test_offline_mode_matches_the_oracle_replay(csb, tmp_path):
     assert nd.n_cuboid_edges == len(d["det"])
     ref = test_ba_gpu.tum_graph(d)
     assert np.abs(np.array(nd.cams) - ref["cams7"]).max() < 1e-5 and np.abs(nd.cube - ref["cubes10"][0]).max() < 1e-5
+
+
+def test_detect_3d_cuboid_mirror(seq, csb):
+    """csb.detect_3d_cuboid: the reference class's member names and defaults (detect_3d_cuboid.h:74-118); a BGR frame is converted like
+    cv2.cvtColor (bit-identical); the call packs what csb_detect_batch_gray expects (checked by the stand-in context's assertions) and
+    returns one list per box."""
+    import cv2
+    frames, boxes, truth, _, _ = seq
+    det = csb.detect_3d_cuboid(_FakeCtx(csb))
+    assert (det.consider_config_1, det.consider_config_2, det.whether_sample_cam_roll_pitch, det.whether_sample_bbox_height, det.max_cuboid_num,
+            det.nominal_skew_ratio, det.max_cut_skew) == (True, True, True, False, 1, 1.0, 3.0)
+    with pytest.raises(csb.CsbError):
+        det.detect_cuboid(frames[0], np.eye(4), boxes[0], np.zeros((0, 4)))          # no calibration yet
+    det.set_calibration(node.K_TUM)
+    det.whether_sample_cam_roll_pitch = False
+    det.nominal_skew_ratio = 2
+    d = np.load(os.path.join(replay.GOLD, "tum_online.npz"))
+    bgr = cv2.imdecode(d["jpeg"][d["jpeg_off"][0]:d["jpeg_off"][1]], 1)
+    T0 = node.pose_matrix(node.se3_from_vector7(truth[0, 1:8]))
+    lines = np.asarray(det._ctx.edlines_detect_batch(frames[0][None], 15.0, True)[0][0], np.float64)
+    from_bgr = det.detect_cuboid(bgr, T0, boxes[0], lines)
+    from_gray = det.detect_cuboid(frames[0], T0, boxes[0], lines)
+    assert len(from_bgr) == len(boxes[0]) == 1 and len(from_bgr[0]) == 1
+    assert from_bgr[0][0].rank_index == from_gray[0][0].rank_index and np.array_equal(np.array(from_bgr[0][0].pos), np.array(from_gray[0][0].pos))
+    assert det.detect_cuboid(frames[0], T0, np.zeros((0, 5)), lines) == []
+    with pytest.raises(csb.CsbError):
+        det.detect_cuboid(frames[0].astype(np.float32), T0, boxes[0], lines)
