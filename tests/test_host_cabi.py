@@ -182,3 +182,16 @@ def test_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+
+
+def test_tools_and_diagnostics_compile_and_stay_off_the_oracle():
+    """Every script under tools/ and tests/diag/ byte-compiles; nothing under tools/, in the package or in bench.py's GPU arm imports the
+    oracle or the test helpers (the oracle is test infrastructure: only tests/, smoke() and bench.py's CPU legs may touch it)."""
+    import glob
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for f in glob.glob(os.path.join(root, "tools", "*.py")) + glob.glob(os.path.join(root, "tests", "diag", "*.py")):
+        py_compile.compile(f, doraise=True)
+    for f in glob.glob(os.path.join(root, "tools", "*.py")) + glob.glob(os.path.join(root, "cube_slam_wu_b200", "*.py")):
+        src = open(f).read()
+        assert "oracle_lib" not in src and "import helpers" not in src and "liboracle" not in src, f
