@@ -141,7 +141,9 @@ int csb_detect_download(csb_context* ctx, csb_cuboid* cuboids_out, int32_t* n_cu
  * (img_height x img_width bytes each, packed in frame order).  Every csb_detect_run() then starts with, per task ROI,
  *   cv::Canny(gray(roi), e, 80, 200)  +  cv::distanceTransform(255 - e, dist, CV_DIST_L2, 3)      (box_proposal_detail.cpp:320-327)
  * computed on the device with OpenCV's own algorithms (Sobel 3x3 that sees the ROI's true neighbours like a cv::Mat ROI view,
- * L1 magnitude, NMS, hysteresis; 16.16 fixed-point 3x3 chamfer transform) -- bit-identical to cv2 4.13 with IPP disabled. */
+ * L1 magnitude, NMS, hysteresis; 16.16 fixed-point 3x3 chamfer transform) -- bit-identical to cv2 4.13 with IPP disabled.
+ * One CTA per ROI: 256 threads in a batch, 1024 when the call holds at most one ROI per SM (one frame per call: latency); the environment
+ * variable CSB_DISTMAP_CTA=256|1024 forces one of the two (tests). */
 int csb_detect_upload_gray(csb_context* ctx, const csb_frame* frames, int n_frames, const double* boxes, int n_boxes, const double* lines,
                            int n_lines, const csb_task* tasks, int n_tasks, const uint8_t* gray, int64_t n_gray_bytes,
                            const csb_detect_params* params);
